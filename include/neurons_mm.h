@@ -1,0 +1,158 @@
+/*
+ * neurons_mm.h -- C ABI of libneurons_mm.so: the B200 (sm_100a) implementation of the AnimateDiff
+ * motion-module forward that NEURONS' video-reconstruction stage runs 28x per denoising step.
+ *
+ * The reference has NO native boundary for this path (it is pure Python on PyTorch); the interface
+ * replaced is the Python call
+ *     VanillaTemporalModule.forward(input_tensor[b,c,f,h,w], temb, encoder_hidden_states)
+ *         /root/reference/animatediff/models/motion_module.py:77-82  (-> :134-158, :210-222, :270-329)
+ * made from the five UNet block classes at animatediff/models/unet_blocks.py:275,411,511,661,754.
+ * Every entry point below cites the reference lines whose arithmetic it carries out.
+ *
+ * Conventions
+ *   - plain C, no torch / CUDA types: device pointers are `void*`, the stream is a `cudaStream_t`
+ *     passed as `void*` (0 = legacy default stream).
+ *   - every device pointer is BORROWED from the caller (PyTorch's caching allocator); the library
+ *     never allocates or frees device memory and never synchronises: all work is enqueued on the
+ *     caller's stream and is CUDA-graph capturable.
+ *   - every function returns NMM_OK (0) or a negative nmm_status; nmm_last_error() gives the text
+ *     (thread-local).  Nothing throws or exits across the ABI.  There is no CPU fallback: on a
+ *     machine without an sm_100 GPU the compute entry points return NMM_ERR_DEVICE.
+ *   - token order used by all intermediate buffers: n = (b*F + f)*P + p,  P = H*W  (the reference's
+ *     own "(b f) d c" order, motion_module.py:144), rows of C contiguous channels.
+ */
+#ifndef NEURONS_MM_H
+#define NEURONS_MM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NMM_ABI_VERSION 1
+#if defined(__GNUC__)
+#define NMM_API __attribute__((visibility("default")))
+#else
+#define NMM_API
+#endif
+#define NMM_MAX_LAYERS 4        /* num_transformer_block; 1 in every NEURONS config (inference-v3.yaml:10) */
+#define NMM_MAX_ATTN 4          /* len(attention_block_types); 2 in the UNet, 1 in SparseCtrl */
+#define NMM_MAX_FRAMES 32       /* temporal_position_encoding_max_len is 24 (UNet) / 32 (SparseCtrl) */
+#define NMM_GN_GROUPS 32        /* motion_module.py:95,109 */
+
+typedef enum nmm_status {
+    NMM_OK = 0,
+    NMM_ERR_BAD_ARG = -1,       /* null pointer, non-positive size, misaligned pointer               */
+    NMM_ERR_UNSUPPORTED = -2,   /* configuration the reference supports but this library does not    */
+    NMM_ERR_WORKSPACE = -3,     /* workspace / packed-weight buffer too small                         */
+    NMM_ERR_CUDA = -4,          /* a CUDA runtime call failed (text in nmm_last_error)                */
+    NMM_ERR_DEVICE = -5         /* no CUDA device, or the device is not sm_100                        */
+} nmm_status;
+
+typedef enum nmm_dtype {
+    NMM_F32 = 0,                /* parity mode: fp32 storage, fp32 FMA arithmetic (bar: max-abs 1e-4) */
+    NMM_BF16 = 1                /* production mode: bf16 storage + tcgen05 bf16 MMA, fp32 accumulate,
+                                   fp32 residual stream, norms / softmax in fp32 (bar: max-abs 2e-2)  */
+} nmm_dtype;
+
+/* Shape + hyper-parameters of one module call.  Mirrors the arguments that reach
+ * VanillaTemporalModule.__init__ (motion_module.py:49-60) and the runtime tensor geometry. */
+typedef struct nmm_shape {
+    int32_t batch, channels, frames, height, width;     /* logical x: [b, c, f, h, w]                 */
+    int32_t heads;              /* num_attention_heads (8)                                             */
+    int32_t layers;             /* num_transformer_block                                               */
+    int32_t attn_blocks;        /* number of "Temporal_Self" attention blocks per transformer block    */
+    int32_t pos_enc;            /* temporal_position_encoding (0/1)                                    */
+    int32_t max_len;            /* temporal_position_encoding_max_len; frames <= max_len is required   */
+    int32_t dtype;              /* nmm_dtype of x, y and of the arithmetic mode                        */
+    float eps_gn;               /* 1e-6, motion_module.py:109                                          */
+    float eps_ln;               /* 1e-5, nn.LayerNorm default (motion_module.py:201,207)               */
+    /* element strides of x and y for the b, c and f axes; (h, w) must be dense (stride W, 1).
+     * x may be the contiguous "b c f h w" tensor or the [B,F,C,H,W]-storage view every UNet call site
+     * passes; y is normally [B,F,C,H,W] storage like the reference's (motion_module.py:153-156). */
+    int64_t x_stride_b, x_stride_c, x_stride_f;
+    int64_t y_stride_b, y_stride_c, y_stride_f;
+} nmm_shape;
+
+/* Source parameters exactly as they sit in the nn.Module / checkpoint ("motion_modules.*" keys,
+ * animatediff/utils/util.py:107-121).  All pointers are device pointers of element type `dtype`
+ * (NMM_F32 or NMM_BF16), row-major [out_features, in_features] for weights. */
+typedef struct nmm_attn_params {
+    const void *norm_w, *norm_b;        /* transformer_blocks.L.norms.I.{weight,bias}        [C]      */
+    const void *to_q, *to_k, *to_v;     /* ...attention_blocks.I.to_{q,k,v}.weight           [C,C]    */
+    const void *to_out_w, *to_out_b;    /* ...attention_blocks.I.to_out.0.{weight,bias}      [C,C],[C]*/
+    const void *pe;                     /* ...attention_blocks.I.pos_encoder.pe  [max_len,C] or NULL
+                                           (non-persistent buffer, motion_module.py:234-239)          */
+} nmm_attn_params;
+
+typedef struct nmm_layer_params {
+    nmm_attn_params attn[NMM_MAX_ATTN];
+    const void *ff_norm_w, *ff_norm_b;  /* ff_norm.{weight,bias}                             [C]      */
+    const void *ff_proj_w, *ff_proj_b;  /* ff.net.0.proj.{weight,bias}  (GEGLU: value|gate)  [8C,C],[8C] */
+    const void *ff_out_w, *ff_out_b;    /* ff.net.2.{weight,bias}                            [C,4C],[C] */
+} nmm_layer_params;
+
+typedef struct nmm_params {
+    int32_t dtype;                      /* nmm_dtype of every tensor below                            */
+    const void *gn_w, *gn_b;            /* temporal_transformer.norm.{weight,bias}           [C]      */
+    const void *proj_in_w, *proj_in_b;  /* temporal_transformer.proj_in.{weight,bias}        [C,C],[C]*/
+    nmm_layer_params layer[NMM_MAX_LAYERS];
+    const void *proj_out_w, *proj_out_b;/* temporal_transformer.proj_out.{weight,bias}       [C,C],[C]*/
+} nmm_params;
+
+/* ---- library / device ------------------------------------------------------------------------ */
+NMM_API int nmm_abi_version(void);
+NMM_API const char *nmm_last_error(void);
+/* NMM_OK iff the current CUDA device is compute capability 10.x. */
+NMM_API int nmm_device_check(void);
+/* number of kernels this library has launched in this process (bench.py's `gpu_launches` claim). */
+NMM_API uint64_t nmm_launch_count(void);
+
+/* ---- whole-module forward (replaces motion_module.py:77-82 -> :134-158) ----------------------- */
+NMM_API int nmm_validate(const nmm_shape *s);
+NMM_API int nmm_packed_params_bytes(const nmm_shape *s, size_t *out_bytes);
+NMM_API int nmm_workspace_bytes(const nmm_shape *s, size_t *out_bytes);
+/* Convert + re-lay-out the module's parameters once (QKV concatenated, GEGLU value/gate rows
+ * interleaved, GEMM operands in the arithmetic dtype, biases / norm affines / PE in fp32). */
+NMM_API int nmm_pack_params(const nmm_shape *s, const nmm_params *src, void *packed, size_t packed_bytes, void *stream);
+/* y = module(x).  x, y: element type s->dtype with the strides in *s.  x and y must not alias. */
+NMM_API int nmm_forward(const nmm_shape *s, const void *x, void *y, const void *packed, void *workspace,
+                size_t workspace_bytes, void *stream);
+
+/* ---- per-stage entry points (kernel-level parity tests and micro-benchmarks) ------------------- */
+/* GroupNorm(32, C, eps_gn) statistics per (b, f, group): motion_module.py:142.  mean/rstd: fp32 [B*F*32]. */
+NMM_API int nmm_groupnorm_stats(const nmm_shape *s, const void *x, float *mean, float *rstd, void *workspace,
+                        size_t workspace_bytes, void *stream);
+/* GroupNorm apply fused with "(b f) c h w -> (b f) (h w) c": motion_module.py:142-144.
+ * tokens: [N, C] of s->dtype.  gn_w/gn_b: fp32 [C]. */
+NMM_API int nmm_groupnorm_tokens(const nmm_shape *s, const void *x, const float *gn_w, const float *gn_b, void *tokens,
+                         void *workspace, size_t workspace_bytes, void *stream);
+/* LayerNorm(C, eps_ln) (+ sinusoidal PE of the token's frame): motion_module.py:212 + :277-278 (pe != NULL)
+ * or :219 (pe == NULL).  h: fp32 [N,C]; out: [N,C] of s->dtype; w,b: fp32 [C]; pe: fp32 [max_len,C]. */
+NMM_API int nmm_layernorm_pe(const nmm_shape *s, const float *h, const float *w, const float *b, const float *pe,
+                     void *out, void *stream);
+/* softmax(q k^T / sqrt(d_h)) v per (b, p, head) over the frame axis: motion_module_new.py:258-287 with the
+ * head split/merge of :181-193 folded into the indexing.  qkv: [N,3C] (q|k|v), ctx: [N,C], both s->dtype. */
+NMM_API int nmm_temporal_attention(const nmm_shape *s, const void *qkv, void *ctx, void *stream);
+
+typedef enum nmm_epilogue {
+    NMM_EPI_STORE = 0,          /* acc (+ bias) -> `h` (fp32 [M,N]) if non-NULL and/or `out` ([M,N] of dtype) if non-NULL */
+    NMM_EPI_RESIDUAL = 1,       /* h = acc + bias + h (fp32, in place)   motion_module.py:213-219; optional
+                                   second copy of h in `dtype` to `out` (may be NULL)                          */
+    NMM_EPI_GEGLU = 2,          /* out[:, j] = (acc[2j]+b[2j]) * gelu_erf(acc[2j+1]+b[2j+1]) -> out [M,N/2];
+                                   W rows pre-interleaved value/gate     motion_module_new.py:516-518          */
+    NMM_EPI_OUTPUT = 3          /* y[b,c,f,p] = acc + bias + x[b,c,f,p]   motion_module.py:152-156             */
+} nmm_epilogue;
+
+/* D[M,N] = A[M,K] . W[N,K]^T with a fused epilogue.  A, W, out: element type `dtype` (NMM_BF16 runs on
+ * tcgen05 tensor cores with fp32 accumulation in TMEM; NMM_F32 runs on fp32 FMA).  bias: fp32 [N] or NULL.
+ * M = s->batch*frames*height*width is implied by `s` for NMM_EPI_OUTPUT; otherwise M is explicit. */
+NMM_API int nmm_linear(int32_t dtype, int32_t epilogue, int64_t M, int32_t N, int32_t K, const void *A, const void *W,
+               const float *bias, float *h, void *out, const nmm_shape *s, const void *x, void *y, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEURONS_MM_H */

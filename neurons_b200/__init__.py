@@ -1,0 +1,15 @@
+"""neurons_b200 -- B200-native (sm_100a) drop-in for the AnimateDiff motion module of xmed-lab/NEURONS.
+
+Public surface (mirrors /root/reference/animatediff/models/motion_module.py):
+    get_motion_module, VanillaTemporalModule      construct modules with the reference's signature / checkpoint layout
+    patch(model), invalidate(model)                rebind forward on reference modules already inside a UNet / ControlNet
+    torch.ops.neurons_mm.forward                   the custom op (CUDA dispatch key only)
+The arithmetic lives in libneurons_mm.so (C ABI: include/neurons_mm.h), built by `python -m neurons_b200.build`.
+"""
+from .lib import NmmError, launch_count, load as load_library          # noqa: F401
+from .ops import ModuleConfig                                           # noqa: F401
+from .motion_module import (VanillaTemporalModule, get_motion_module, invalidate, motion_forward, patch,   # noqa: F401
+                            zero_module)
+
+__all__ = ["VanillaTemporalModule", "get_motion_module", "patch", "invalidate", "motion_forward", "zero_module",
+           "ModuleConfig", "NmmError", "launch_count", "load_library"]

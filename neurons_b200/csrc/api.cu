@@ -1,0 +1,352 @@
+// C ABI of libneurons_mm.so (include/neurons_mm.h): validation, parameter packing, workspace carving and the
+// kernel sequence of one VanillaTemporalModule.forward (motion_module.py:77-82 -> :134-158 -> :210-222 -> :270-329).
+#include <cmath>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace nmm {
+
+std::atomic<uint64_t> g_launches{0};
+
+std::string &last_error_ref() {
+    static thread_local std::string s;
+    return s;
+}
+int fail(int status, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    last_error_ref() = buf;
+    return status;
+}
+
+// ---- packed parameter layout -------------------------------------------------------------------------
+struct AttnOff { size_t ln_w, ln_b, wqkv, wo, bo, pe; };
+struct LayerOff { AttnOff attn[NMM_MAX_ATTN]; size_t ff_ln_w, ff_ln_b, w1, b1, w2, b2; };
+struct PackedLayout { size_t gn_w, gn_b, w_in, b_in; LayerOff layer[NMM_MAX_LAYERS]; size_t w_out, b_out, total; };
+
+static PackedLayout packed_layout(const Geo &g) {
+    PackedLayout L;
+    memset(&L, 0, sizeof(L));
+    size_t off = 0;
+    const size_t C = g.C, ws = dtype_size(g.dtype);
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    L.gn_w = take(C * 4); L.gn_b = take(C * 4);
+    L.w_in = take(C * C * ws); L.b_in = take(C * 4);
+    for (int l = 0; l < g.layers; l++) {
+        for (int i = 0; i < g.A; i++) {
+            AttnOff &a = L.layer[l].attn[i];
+            a.ln_w = take(C * 4); a.ln_b = take(C * 4);
+            a.wqkv = take(3 * C * C * ws); a.wo = take(C * C * ws); a.bo = take(C * 4);
+            a.pe = take(g.pos_enc ? (size_t)g.max_len * C * 4 : 0);
+        }
+        LayerOff &lo = L.layer[l];
+        lo.ff_ln_w = take(C * 4); lo.ff_ln_b = take(C * 4);
+        lo.w1 = take(8 * C * C * ws); lo.b1 = take(8 * C * 4);
+        lo.w2 = take(4 * C * C * ws); lo.b2 = take(C * 4);
+    }
+    L.w_out = take(C * C * ws); L.b_out = take(C * 4);
+    L.total = off;
+    return L;
+}
+
+// ---- workspace layout --------------------------------------------------------------------------------
+struct WorkLayout { size_t gn_partial, tok, h, big, ctx, total; };
+static WorkLayout work_layout(const Geo &g) {
+    WorkLayout w;
+    size_t off = 0;
+    const size_t es = dtype_size(g.dtype), NC = (size_t)g.N * g.C;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
+    w.gn_partial = take(gn_partial_bytes(g));
+    w.tok = take(NC * es);          // GroupNorm tokens / LayerNorm output / GEMM-dtype copy of h for proj_out
+    w.h = take(NC * 4);             // fp32 residual stream
+    w.big = take(NC * 4 * es);      // qkv [N,3C] and GEGLU activations [N,4C] (never live together)
+    w.ctx = take(NC * es);          // attention context
+    w.total = off;
+    return w;
+}
+
+static int validate(const nmm_shape *s) {
+    if (!s) return fail(NMM_ERR_BAD_ARG, "shape is NULL");
+    if (s->batch <= 0 || s->channels <= 0 || s->frames <= 0 || s->height <= 0 || s->width <= 0)
+        return fail(NMM_ERR_BAD_ARG, "non-positive dimension");
+    if (s->dtype != NMM_F32 && s->dtype != NMM_BF16) return fail(NMM_ERR_BAD_ARG, "unknown dtype %d", s->dtype);
+    if (s->channels % NMM_GN_GROUPS != 0) return fail(NMM_ERR_BAD_ARG, "channels (%d) must be divisible by %d GroupNorm groups", s->channels, NMM_GN_GROUPS);
+    if (s->heads <= 0 || s->channels % s->heads != 0) return fail(NMM_ERR_BAD_ARG, "channels (%d) must be divisible by heads (%d)", s->channels, s->heads);
+    if (s->layers <= 0 || s->layers > NMM_MAX_LAYERS) return fail(NMM_ERR_UNSUPPORTED, "num_transformer_block %d outside [1,%d]", s->layers, NMM_MAX_LAYERS);
+    if (s->attn_blocks <= 0 || s->attn_blocks > NMM_MAX_ATTN) return fail(NMM_ERR_UNSUPPORTED, "%d attention blocks outside [1,%d]", s->attn_blocks, NMM_MAX_ATTN);
+    if (s->frames > NMM_MAX_FRAMES) return fail(NMM_ERR_UNSUPPORTED, "frames %d > %d", s->frames, NMM_MAX_FRAMES);
+    if (s->pos_enc && s->frames > s->max_len) return fail(NMM_ERR_BAD_ARG, "frames (%d) exceed temporal_position_encoding_max_len (%d)", s->frames, s->max_len);
+    if (s->heads * s->frames > 256) return fail(NMM_ERR_UNSUPPORTED, "heads*frames > 256");
+    if ((int64_t)s->batch * s->frames > 65535) return fail(NMM_ERR_UNSUPPORTED, "batch*frames > 65535");
+    if ((int64_t)s->batch * s->frames * s->height * s->width * (int64_t)s->channels >= ((int64_t)1 << 40)) return fail(NMM_ERR_UNSUPPORTED, "tensor too large");
+    return NMM_OK;
+}
+
+static int device_check() {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(NMM_ERR_DEVICE, "no CUDA device: %s", cudaGetErrorString(e)); }
+    int major = 0;
+    e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(NMM_ERR_DEVICE, "cannot query device: %s", cudaGetErrorString(e)); }
+    if (major != 10) return fail(NMM_ERR_DEVICE, "device compute capability %d.x is not sm_100 (this library is B200-only)", major);
+    return NMM_OK;
+}
+
+// ---- parameter packing kernels ---------------------------------------------------------------------------
+// dst[r, :] = src[map(r), :] with dtype conversion.  interleave_half > 0 : map(r) = r/2 + (r & 1) * interleave_half
+// (GEGLU: packed row 2j = value row j, packed row 2j+1 = gate row j + 4C; motion_module_new.py:516-517 chunk(2)).
+template <typename TS, typename TD>
+__global__ void convert_rows_kernel(const TS *__restrict__ src, TD *__restrict__ dst, int64_t rows, int64_t cols, int64_t half) {
+    const int64_t total = rows * cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / cols, c = i - r * cols;
+        const int64_t sr = half > 0 ? (r >> 1) + (r & 1) * half : r;
+        dst[i] = from_f32<TD>(to_f32(src[sr * cols + c]));
+    }
+}
+
+int launch_convert_rows(const void *src, int src_dtype, void *dst, int dst_dtype, int64_t rows, int64_t cols, int half, cudaStream_t st) {
+    if (!src || !dst) return fail(NMM_ERR_BAD_ARG, "NULL parameter tensor");
+    const int64_t total = rows * cols;
+    if (total == 0) return NMM_OK;
+    const int threads = 256;
+    const int blocks = (int)std::min<int64_t>(ceil_div(total, threads), 148 * 16);
+    if (src_dtype == NMM_F32 && dst_dtype == NMM_F32) convert_rows_kernel<float, float><<<blocks, threads, 0, st>>>((const float *)src, (float *)dst, rows, cols, half);
+    else if (src_dtype == NMM_F32 && dst_dtype == NMM_BF16) convert_rows_kernel<float, bf16><<<blocks, threads, 0, st>>>((const float *)src, (bf16 *)dst, rows, cols, half);
+    else if (src_dtype == NMM_BF16 && dst_dtype == NMM_F32) convert_rows_kernel<bf16, float><<<blocks, threads, 0, st>>>((const bf16 *)src, (float *)dst, rows, cols, half);
+    else if (src_dtype == NMM_BF16 && dst_dtype == NMM_BF16) convert_rows_kernel<bf16, bf16><<<blocks, threads, 0, st>>>((const bf16 *)src, (bf16 *)dst, rows, cols, half);
+    else return fail(NMM_ERR_BAD_ARG, "unknown parameter dtype");
+    NMM_LAUNCHED("convert_rows_kernel");
+    return NMM_OK;
+}
+
+// Sinusoidal table when the caller does not hand over the module's own `pe` buffer (motion_module.py:234-238).
+__global__ void make_pe_kernel(float *__restrict__ pe, int max_len, int C) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= max_len * C) return;
+    const int t = i / C, c = i % C;
+    const float div = expf((float)(c & ~1) * (-logf(10000.0f) / (float)C));
+    pe[i] = (c & 1) ? cosf((float)t * div) : sinf((float)t * div);
+}
+
+static int linear(const Geo &g, const LinearArgs &a, cudaStream_t st) {
+    return g.dtype == NMM_BF16 ? launch_linear_tc(a, st) : launch_linear_simt(a, st);
+}
+
+}  // namespace nmm
+
+using namespace nmm;
+
+extern "C" {
+
+int nmm_abi_version(void) { return NMM_ABI_VERSION; }
+const char *nmm_last_error(void) { return last_error_ref().c_str(); }
+uint64_t nmm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+int nmm_device_check(void) { return device_check(); }
+int nmm_validate(const nmm_shape *s) { return validate(s); }
+
+int nmm_packed_params_bytes(const nmm_shape *s, size_t *out_bytes) {
+    int rc = validate(s);
+    if (rc != NMM_OK) return rc;
+    if (!out_bytes) return fail(NMM_ERR_BAD_ARG, "out_bytes is NULL");
+    *out_bytes = packed_layout(geo_of(s)).total;
+    return NMM_OK;
+}
+
+int nmm_workspace_bytes(const nmm_shape *s, size_t *out_bytes) {
+    int rc = validate(s);
+    if (rc != NMM_OK) return rc;
+    if (!out_bytes) return fail(NMM_ERR_BAD_ARG, "out_bytes is NULL");
+    *out_bytes = work_layout(geo_of(s)).total;
+    return NMM_OK;
+}
+
+int nmm_pack_params(const nmm_shape *s, const nmm_params *src, void *packed, size_t packed_bytes, void *stream) {
+    int rc = validate(s);
+    if (rc != NMM_OK) return rc;
+    if (!src || !packed) return fail(NMM_ERR_BAD_ARG, "NULL argument");
+    if (src->dtype != NMM_F32 && src->dtype != NMM_BF16) return fail(NMM_ERR_BAD_ARG, "unknown source parameter dtype %d", src->dtype);
+    if ((rc = device_check()) != NMM_OK) return rc;
+    const Geo g = geo_of(s);
+    const PackedLayout L = packed_layout(g);
+    if (packed_bytes < L.total) return fail(NMM_ERR_WORKSPACE, "packed buffer too small: %zu < %zu", packed_bytes, L.total);
+    if (!aligned(packed, 256)) return fail(NMM_ERR_BAD_ARG, "packed buffer must be 256-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    char *base = (char *)packed;
+    const int sd = src->dtype, wd = g.dtype;
+    const int64_t C = g.C;
+#define PACK(srcp, off, dd, rows, cols, half)                                                        \
+    do {                                                                                             \
+        rc = launch_convert_rows((srcp), sd, base + (off), (dd), (rows), (cols), (half), st);        \
+        if (rc != NMM_OK) return rc;                                                                 \
+    } while (0)
+    PACK(src->gn_w, L.gn_w, NMM_F32, C, 1, 0); PACK(src->gn_b, L.gn_b, NMM_F32, C, 1, 0);
+    PACK(src->proj_in_w, L.w_in, wd, C, C, 0); PACK(src->proj_in_b, L.b_in, NMM_F32, C, 1, 0);
+    for (int l = 0; l < g.layers; l++) {
+        const nmm_layer_params &lp = src->layer[l];
+        const LayerOff &lo = L.layer[l];
+        for (int i = 0; i < g.A; i++) {
+            const nmm_attn_params &ap = lp.attn[i];
+            const AttnOff &ao = lo.attn[i];
+            PACK(ap.norm_w, ao.ln_w, NMM_F32, C, 1, 0); PACK(ap.norm_b, ao.ln_b, NMM_F32, C, 1, 0);
+            const size_t wbytes = (size_t)C * C * dtype_size(wd);
+            PACK(ap.to_q, ao.wqkv, wd, C, C, 0); PACK(ap.to_k, ao.wqkv + wbytes, wd, C, C, 0); PACK(ap.to_v, ao.wqkv + 2 * wbytes, wd, C, C, 0);
+            PACK(ap.to_out_w, ao.wo, wd, C, C, 0); PACK(ap.to_out_b, ao.bo, NMM_F32, C, 1, 0);
+            if (g.pos_enc) {
+                if (ap.pe) PACK(ap.pe, ao.pe, NMM_F32, (int64_t)g.max_len, C, 0);
+                else {
+                    const int n = g.max_len * g.C;
+                    make_pe_kernel<<<(n + 255) / 256, 256, 0, st>>>((float *)(base + ao.pe), g.max_len, g.C);
+                    NMM_LAUNCHED("make_pe_kernel");
+                }
+            }
+        }
+        PACK(lp.ff_norm_w, lo.ff_ln_w, NMM_F32, C, 1, 0); PACK(lp.ff_norm_b, lo.ff_ln_b, NMM_F32, C, 1, 0);
+        PACK(lp.ff_proj_w, lo.w1, wd, 8 * C, C, (int)(4 * C)); PACK(lp.ff_proj_b, lo.b1, NMM_F32, 8 * C, 1, (int)(4 * C));
+        PACK(lp.ff_out_w, lo.w2, wd, C, 4 * C, 0); PACK(lp.ff_out_b, lo.b2, NMM_F32, C, 1, 0);
+    }
+    PACK(src->proj_out_w, L.w_out, wd, C, C, 0); PACK(src->proj_out_b, L.b_out, NMM_F32, C, 1, 0);
+#undef PACK
+    return NMM_OK;
+}
+
+int nmm_forward(const nmm_shape *s, const void *x, void *y, const void *packed, void *workspace, size_t workspace_bytes, void *stream) {
+    int rc = validate(s);
+    if (rc != NMM_OK) return rc;
+    if (!x || !y || !packed || !workspace) return fail(NMM_ERR_BAD_ARG, "NULL argument");
+    if (x == y) return fail(NMM_ERR_BAD_ARG, "x and y must not alias");
+    if ((rc = device_check()) != NMM_OK) return rc;
+    const Geo g = geo_of(s);
+    const PackedLayout L = packed_layout(g);
+    const WorkLayout w = work_layout(g);
+    if (workspace_bytes < w.total) return fail(NMM_ERR_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, w.total);
+    if (!aligned(workspace, 1024) || !aligned(packed, 256)) return fail(NMM_ERR_BAD_ARG, "workspace must be 1024-byte and packed params 256-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const char *pk = (const char *)packed;
+    char *ws = (char *)workspace;
+    double *gn_partial = (double *)(ws + w.gn_partial);
+    void *tok = ws + w.tok, *big = ws + w.big, *ctx = ws + w.ctx;
+    float *h = (float *)(ws + w.h);
+    auto F32 = [&](size_t off) { return (const float *)(pk + off); };
+
+    // GroupNorm statistics, then normalise + re-layout to token-major           motion_module.py:137-144
+    if ((rc = launch_gn_stats(g, s, x, gn_partial, st)) != NMM_OK) return rc;
+    if ((rc = launch_gn_tokens(g, s, x, gn_partial, F32(L.gn_w), F32(L.gn_b), tok, st)) != NMM_OK) return rc;
+
+    LinearArgs a;
+    memset(&a, 0, sizeof(a));
+    a.M = g.N; a.F = g.F; a.P = g.P;
+    a.xsb = s->x_stride_b; a.xsc = s->x_stride_c; a.xsf = s->x_stride_f;
+    a.ysb = s->y_stride_b; a.ysc = s->y_stride_c; a.ysf = s->y_stride_f;
+
+    // proj_in -> fp32 residual stream h                                           :145
+    a.epilogue = NMM_EPI_STORE; a.N = g.C; a.K = g.C; a.A = tok; a.W = pk + L.w_in; a.bias = F32(L.b_in); a.h = h; a.out = nullptr;
+    if ((rc = linear(g, a, st)) != NMM_OK) return rc;
+
+    for (int l = 0; l < g.layers; l++) {
+        const LayerOff &lo = L.layer[l];
+        for (int i = 0; i < g.A; i++) {
+            const AttnOff &ao = lo.attn[i];
+            // n = LayerNorm(h) + pe[f]                                                :212, :277-278
+            if ((rc = launch_layernorm_pe(g, s, h, F32(ao.ln_w), F32(ao.ln_b), g.pos_enc ? F32(ao.pe) : nullptr, tok, st)) != NMM_OK) return rc;
+            // q|k|v = n . Wqkv^T                                                      :289,297,298
+            a.epilogue = NMM_EPI_STORE; a.N = 3 * g.C; a.K = g.C; a.A = tok; a.W = pk + ao.wqkv; a.bias = nullptr; a.h = nullptr; a.out = big;
+            if ((rc = linear(g, a, st)) != NMM_OK) return rc;
+            // softmax(q k^T / sqrt(dh)) v over frames                                 motion_module_new.py:258-287
+            if ((rc = launch_temporal_attention(g, big, ctx, st)) != NMM_OK) return rc;
+            // h = ctx . Wo^T + bo + h                                                 motion_module.py:321, :213-217
+            a.epilogue = NMM_EPI_RESIDUAL; a.N = g.C; a.K = g.C; a.A = ctx; a.W = pk + ao.wo; a.bias = F32(ao.bo); a.h = h; a.out = nullptr;
+            if ((rc = linear(g, a, st)) != NMM_OK) return rc;
+        }
+        // FeedForward: LayerNorm -> GEGLU -> Linear, + h                              :219; motion_module_new.py:441-471,497-518
+        if ((rc = launch_layernorm_pe(g, s, h, F32(lo.ff_ln_w), F32(lo.ff_ln_b), nullptr, tok, st)) != NMM_OK) return rc;
+        a.epilogue = NMM_EPI_GEGLU; a.N = 8 * g.C; a.K = g.C; a.A = tok; a.W = pk + lo.w1; a.bias = F32(lo.b1); a.h = nullptr; a.out = big;
+        if ((rc = linear(g, a, st)) != NMM_OK) return rc;
+        const bool last = (l == g.layers - 1);
+        a.epilogue = NMM_EPI_RESIDUAL; a.N = g.C; a.K = 4 * g.C; a.A = big; a.W = pk + lo.w2; a.bias = F32(lo.b2); a.h = h;
+        a.out = (last && g.dtype == NMM_BF16) ? tok : nullptr;      // bf16 copy of the final h = A operand of proj_out
+        if ((rc = linear(g, a, st)) != NMM_OK) return rc;
+    }
+    // y = proj_out(h) back in NCHW + x                                                :152-156
+    a.epilogue = NMM_EPI_OUTPUT; a.N = g.C; a.K = g.C; a.A = (g.dtype == NMM_BF16) ? (const void *)tok : (const void *)h;
+    a.W = pk + L.w_out; a.bias = F32(L.b_out); a.h = nullptr; a.out = nullptr; a.x = x; a.y = y;
+    if ((rc = linear(g, a, st)) != NMM_OK) return rc;
+    return NMM_OK;
+}
+
+// ---- per-stage entry points ------------------------------------------------------------------------------
+int nmm_groupnorm_stats(const nmm_shape *s, const void *x, float *mean, float *rstd, void *workspace, size_t workspace_bytes, void *stream) {
+    int rc = validate(s);
+    if (rc != NMM_OK) return rc;
+    if (!x || !mean || !rstd || !workspace) return fail(NMM_ERR_BAD_ARG, "NULL argument");
+    if ((rc = device_check()) != NMM_OK) return rc;
+    const Geo g = geo_of(s);
+    if (workspace_bytes < gn_partial_bytes(g)) return fail(NMM_ERR_WORKSPACE, "workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = launch_gn_stats(g, s, x, (double *)workspace, st)) != NMM_OK) return rc;
+    return launch_gn_finalize(g, s, (const double *)workspace, mean, rstd, st);
+}
+
+int nmm_groupnorm_tokens(const nmm_shape *s, const void *x, const float *gn_w, const float *gn_b, void *tokens, void *workspace,
+                         size_t workspace_bytes, void *stream) {
+    int rc = validate(s);
+    if (rc != NMM_OK) return rc;
+    if (!x || !gn_w || !gn_b || !tokens || !workspace) return fail(NMM_ERR_BAD_ARG, "NULL argument");
+    if ((rc = device_check()) != NMM_OK) return rc;
+    const Geo g = geo_of(s);
+    if (workspace_bytes < gn_partial_bytes(g)) return fail(NMM_ERR_WORKSPACE, "workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = launch_gn_stats(g, s, x, (double *)workspace, st)) != NMM_OK) return rc;
+    return launch_gn_tokens(g, s, x, (const double *)workspace, gn_w, gn_b, tokens, st);
+}
+
+int nmm_layernorm_pe(const nmm_shape *s, const float *h, const float *w, const float *b, const float *pe, void *out, void *stream) {
+    int rc = validate(s);
+    if (rc != NMM_OK) return rc;
+    if (!h || !w || !b || !out) return fail(NMM_ERR_BAD_ARG, "NULL argument");
+    if ((rc = device_check()) != NMM_OK) return rc;
+    return launch_layernorm_pe(geo_of(s), s, h, w, b, pe, out, (cudaStream_t)stream);
+}
+
+int nmm_temporal_attention(const nmm_shape *s, const void *qkv, void *ctx, void *stream) {
+    int rc = validate(s);
+    if (rc != NMM_OK) return rc;
+    if (!qkv || !ctx) return fail(NMM_ERR_BAD_ARG, "NULL argument");
+    if ((rc = device_check()) != NMM_OK) return rc;
+    return launch_temporal_attention(geo_of(s), qkv, ctx, (cudaStream_t)stream);
+}
+
+int nmm_linear(int32_t dtype, int32_t epilogue, int64_t M, int32_t N, int32_t K, const void *A, const void *W, const float *bias,
+               float *h, void *out, const nmm_shape *s, const void *x, void *y, void *stream) {
+    if (dtype != NMM_F32 && dtype != NMM_BF16) return fail(NMM_ERR_BAD_ARG, "unknown dtype %d", dtype);
+    if (!A || !W || M < 0 || N <= 0 || K <= 0) return fail(NMM_ERR_BAD_ARG, "bad GEMM arguments");
+    int rc = device_check();
+    if (rc != NMM_OK) return rc;
+    LinearArgs a;
+    memset(&a, 0, sizeof(a));
+    a.epilogue = epilogue; a.M = M; a.N = N; a.K = K; a.A = A; a.W = W; a.bias = bias; a.h = h; a.out = out;
+    switch (epilogue) {
+        case NMM_EPI_STORE: if (!h && !out) return fail(NMM_ERR_BAD_ARG, "STORE epilogue needs h or out"); break;
+        case NMM_EPI_RESIDUAL: if (!h) return fail(NMM_ERR_BAD_ARG, "RESIDUAL epilogue needs h"); break;
+        case NMM_EPI_GEGLU: if (!out || (N & 1)) return fail(NMM_ERR_BAD_ARG, "GEGLU epilogue needs out and even N"); break;
+        case NMM_EPI_OUTPUT: {
+            if ((rc = validate(s)) != NMM_OK) return rc;
+            if (!x || !y) return fail(NMM_ERR_BAD_ARG, "OUTPUT epilogue needs x and y");
+            const Geo g = geo_of(s);
+            if (g.N != M || g.C != N || s->dtype != dtype) return fail(NMM_ERR_BAD_ARG, "OUTPUT epilogue: shape does not match M/N/dtype");
+            a.x = x; a.y = y; a.F = g.F; a.P = g.P;
+            a.xsb = s->x_stride_b; a.xsc = s->x_stride_c; a.xsf = s->x_stride_f;
+            a.ysb = s->y_stride_b; a.ysc = s->y_stride_c; a.ysf = s->y_stride_f;
+            break;
+        }
+        default: return fail(NMM_ERR_BAD_ARG, "unknown epilogue %d", epilogue);
+    }
+    return dtype == NMM_BF16 ? launch_linear_tc(a, (cudaStream_t)stream) : launch_linear_simt(a, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,202 @@
+// Short-sequence temporal self-attention: softmax(q k^T * d_h^-1/2) v over the frame axis (F <= 32),
+// independently per (batch, spatial position, head).
+//
+// Reference arithmetic: CrossAttention._attention, motion_module_new.py:258-287 (baddbmm(beta=0, alpha=scale)
+// -> softmax(dim=-1) -> bmm), with reshape_heads_to_batch_dim / reshape_batch_dim_to_heads (:181-193) and the
+// "(b f) d c -> (b d) f c" / inverse rearranges of VersatileAttention.forward (motion_module.py:275,327) folded
+// into the addressing: a token row is n = (b*F + f)*P + p, so the F rows of one position are P rows apart.
+//
+// Mapping: one thread per (position, head, query frame).  A CTA stages the q|k|v rows of PB consecutive
+// positions x all F frames in shared memory with 16-byte coalesced loads (each frame contributes one
+// contiguous PB*3C-element run), keeps the F scores in registers, does the softmax in fp32 and writes its
+// context row back through shared memory so the global stores are 16-byte coalesced as well.
+// HBM-bound: bytes = 4*N*C*s (read qkv, write ctx), flops = 4*N*F*C.
+#include "common.cuh"
+
+namespace nmm {
+
+template <typename T, int VEC> struct RowVec;
+template <> struct RowVec<bf16, 8> {
+    static __device__ __forceinline__ void load(const bf16 *p, float (&f)[8]) {
+        uint4 v = *reinterpret_cast<const uint4 *>(p);
+        f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+        f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+    }
+    static __device__ __forceinline__ void store(bf16 *p, const float (&f)[8]) {
+        *reinterpret_cast<uint4 *>(p) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                                                   pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+    }
+};
+template <> struct RowVec<float, 4> {
+    static __device__ __forceinline__ void load(const float *p, float (&f)[4]) {
+        float4 v = *reinterpret_cast<const float4 *>(p);
+        f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+    }
+    static __device__ __forceinline__ void store(float *p, const float (&f)[4]) {
+        *reinterpret_cast<float4 *>(p) = make_float4(f[0], f[1], f[2], f[3]);
+    }
+};
+template <typename T> struct RowVec<T, 1> {
+    static __device__ __forceinline__ void load(const T *p, float (&f)[1]) { f[0] = to_f32(*p); }
+    static __device__ __forceinline__ void store(T *p, const float (&f)[1]) { *p = from_f32<T>(f[0]); }
+};
+
+// smem layout: [PB positions][F frames][3C + PAD] elements of T; PAD keeps consecutive frame rows on
+// different banks (row pitch in bytes = 3C*s + 16).
+template <typename T, int VEC, int FMAX>
+__global__ void __launch_bounds__(256) temporal_attention_kernel(const T *__restrict__ qkv, T *__restrict__ ctx, int B, int F,
+                                                                 int P, int C, int heads, int PB, float scale) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *sm = reinterpret_cast<T *>(smem_raw);
+    constexpr int PAD = 16 / (int)sizeof(T);
+    const int dh = C / heads;
+    const int pitch = 3 * C + PAD;
+    const int tiles_per_img = (P + PB - 1) / PB;
+    const int b = blockIdx.x / tiles_per_img;
+    const int p0 = (blockIdx.x % tiles_per_img) * PB;
+    const int npos = min(PB, P - p0);
+    const int tid = threadIdx.x, nthr = blockDim.x;
+
+    // ---- stage q|k|v: for each frame a contiguous run of npos*3C elements --------------------------
+    {
+        constexpr int LV = 16 / (int)sizeof(T);                     // elements per 16-byte load
+        const bool vec = (VEC > 1);                                 // host guarantees 16B alignment when VEC > 1
+        if (vec) {
+            const int vec_per_row = 3 * C / LV;
+            const int total = F * npos * vec_per_row;
+            for (int i = tid; i < total; i += nthr) {
+                int v = i % vec_per_row; int r = i / vec_per_row;   // r = f*npos + pl
+                int pl = r % npos, f = r / npos;
+                const T *src = qkv + ((int64_t)(b * F + f) * P + p0 + pl) * (3 * C) + v * LV;
+                uint4 val = __ldg(reinterpret_cast<const uint4 *>(src));
+                *reinterpret_cast<uint4 *>(sm + (pl * F + f) * pitch + v * LV) = val;
+            }
+        } else {
+            const int total = F * npos * 3 * C;
+            for (int i = tid; i < total; i += nthr) {
+                int e = i % (3 * C); int r = i / (3 * C);
+                int pl = r % npos, f = r / npos;
+                sm[(pl * F + f) * pitch + e] = qkv[((int64_t)(b * F + f) * P + p0 + pl) * (3 * C) + e];
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- one thread per (pl, head, f) ---------------------------------------------------------------
+    const int per_pos = heads * F;
+    const int pl = tid / per_pos;
+    const int hf = tid % per_pos;
+    const int head = hf / F, f = hf % F;
+    const bool active = pl < npos;             // tid < PB*heads*F by launch configuration
+    if (active) {
+        T *qrow = sm + (pl * F + f) * pitch + head * dh;             // this thread's query row (reused for output)
+        const T *kbase = sm + (pl * F) * pitch + C + head * dh;
+        const T *vbase = sm + (pl * F) * pitch + 2 * C + head * dh;
+        float sc[FMAX];
+#pragma unroll
+        for (int j = 0; j < FMAX; j++) sc[j] = 0.f;
+        for (int d = 0; d < dh; d += VEC) {
+            float q[VEC];
+            RowVec<T, VEC>::load(qrow + d, q);
+#pragma unroll
+            for (int j = 0; j < FMAX; j++) {
+                if (j < F) {
+                    float k[VEC];
+                    RowVec<T, VEC>::load(kbase + j * pitch + d, k);
+#pragma unroll
+                    for (int e = 0; e < VEC; e++) sc[j] = fmaf(q[e], k[e], sc[j]);
+                }
+            }
+        }
+        // softmax over the F keys (fp32; the reference computes it in the input dtype -- fp32 as shipped)
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < FMAX; j++) if (j < F) { sc[j] *= scale; mx = fmaxf(mx, sc[j]); }
+        float den = 0.f;
+#pragma unroll
+        for (int j = 0; j < FMAX; j++) if (j < F) { sc[j] = __expf(sc[j] - mx); den += sc[j]; }
+        const float inv = 1.0f / den;
+#pragma unroll
+        for (int j = 0; j < FMAX; j++) if (j < F) sc[j] *= inv;
+        for (int d = 0; d < dh; d += VEC) {
+            float o[VEC];
+#pragma unroll
+            for (int e = 0; e < VEC; e++) o[e] = 0.f;
+#pragma unroll
+            for (int j = 0; j < FMAX; j++) {
+                if (j < F) {
+                    float v[VEC];
+                    RowVec<T, VEC>::load(vbase + j * pitch + d, v);
+#pragma unroll
+                    for (int e = 0; e < VEC; e++) o[e] = fmaf(sc[j], v[e], o[e]);
+                }
+            }
+            RowVec<T, VEC>::store(qrow + d, o);                       // q slot is private to this thread
+        }
+    }
+    __syncthreads();
+
+    // ---- write ctx rows (the first C elements of each staged row) -----------------------------------
+    {
+        constexpr int LV = 16 / (int)sizeof(T);
+        if (VEC > 1) {
+            const int vec_per_row = C / LV;
+            const int total = F * npos * vec_per_row;
+            for (int i = tid; i < total; i += nthr) {
+                int v = i % vec_per_row; int r = i / vec_per_row;
+                int pl2 = r % npos, f2 = r / npos;
+                uint4 val = *reinterpret_cast<const uint4 *>(sm + (pl2 * F + f2) * pitch + v * LV);
+                *reinterpret_cast<uint4 *>(ctx + ((int64_t)(b * F + f2) * P + p0 + pl2) * C + v * LV) = val;
+            }
+        } else {
+            const int total = F * npos * C;
+            for (int i = tid; i < total; i += nthr) {
+                int e = i % C; int r = i / C;
+                int pl2 = r % npos, f2 = r / npos;
+                ctx[((int64_t)(b * F + f2) * P + p0 + pl2) * C + e] = sm[(pl2 * F + f2) * pitch + e];
+            }
+        }
+    }
+}
+
+template <typename T, int VEC>
+static int launch_attn_t(const Geo &g, const T *qkv, T *ctx, cudaStream_t st) {
+    const int per_pos = g.heads * g.F;
+    if (per_pos > 256) return fail(NMM_ERR_UNSUPPORTED, "heads*frames = %d > 256", per_pos);
+    const size_t row_bytes = (size_t)(3 * g.C) * sizeof(T) + 16;
+    const size_t smem_cap = 200 * 1024;
+    int PB = 256 / per_pos;
+    while (PB > 1 && (size_t)PB * g.F * row_bytes > 96 * 1024) PB--;       // keep >= 2 CTAs/SM when possible
+    if (PB > g.P) PB = g.P;
+    const size_t smem = (size_t)PB * g.F * row_bytes;
+    if (smem > smem_cap) return fail(NMM_ERR_UNSUPPORTED, "attention tile needs %zu B shared memory", smem);
+    const int threads = ((PB * per_pos + 31) / 32) * 32;
+    const int64_t blocks = (int64_t)g.B * ceil_div(g.P, PB);
+    if (blocks > 0x7fffffff) return fail(NMM_ERR_UNSUPPORTED, "attention grid too large");
+    const float scale = 1.0f / sqrtf((float)g.dh);
+#define ATTN_CASE(FM)                                                                                                    \
+    do {                                                                                                                 \
+        auto kern = temporal_attention_kernel<T, VEC, FM>;                                                               \
+        if (smem > 48 * 1024) NMM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        kern<<<(unsigned)blocks, threads, smem, st>>>(qkv, ctx, g.B, g.F, g.P, g.C, g.heads, PB, scale);                  \
+    } while (0)
+    if (g.F <= 8) ATTN_CASE(8);
+    else if (g.F <= 16) ATTN_CASE(16);
+    else ATTN_CASE(32);
+#undef ATTN_CASE
+    NMM_LAUNCHED("temporal_attention_kernel");
+    return NMM_OK;
+}
+
+int launch_temporal_attention(const Geo &g, const void *qkv, void *ctx, cudaStream_t st) {
+    if (g.F > NMM_MAX_FRAMES) return fail(NMM_ERR_UNSUPPORTED, "frames %d > %d", g.F, NMM_MAX_FRAMES);
+    const bool al = aligned(qkv, 16) && aligned(ctx, 16);
+    if (g.dtype == NMM_BF16) {
+        if (g.dh % 8 == 0 && al) return launch_attn_t<bf16, 8>(g, (const bf16 *)qkv, (bf16 *)ctx, st);
+        return launch_attn_t<bf16, 1>(g, (const bf16 *)qkv, (bf16 *)ctx, st);
+    }
+    if (g.dh % 4 == 0 && al) return launch_attn_t<float, 4>(g, (const float *)qkv, (float *)ctx, st);
+    return launch_attn_t<float, 1>(g, (const float *)qkv, (float *)ctx, st);
+}
+
+}  // namespace nmm

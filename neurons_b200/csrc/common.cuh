@@ -1,0 +1,123 @@
+// Shared host/device helpers for libneurons_mm.so (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+
+#include "../../include/neurons_mm.h"
+
+namespace nmm {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- error reporting (thread-local text behind nmm_last_error) ---------------------------------
+std::string &last_error_ref();
+int fail(int status, const char *fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+#define NMM_CUDA_OK(expr)                                                                           \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            return ::nmm::fail(NMM_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                               __FILE__, __LINE__);                                                 \
+    } while (0)
+
+// Count + check a kernel launch without synchronising (stays graph-capturable).
+#define NMM_LAUNCHED(name)                                                                          \
+    do {                                                                                            \
+        ::nmm::g_launches.fetch_add(1, std::memory_order_relaxed);                                  \
+        cudaError_t _e = cudaGetLastError();                                                        \
+        if (_e != cudaSuccess)                                                                      \
+            return ::nmm::fail(NMM_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(_e)); \
+    } while (0)
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+inline bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+// ---- geometry derived from nmm_shape -------------------------------------------------------------
+struct Geo {
+    int B, C, F, H, W, P, heads, dh, layers, A, max_len;
+    int64_t N;       // tokens
+    bool pos_enc;
+    int dtype;
+};
+inline Geo geo_of(const nmm_shape *s) {
+    Geo g;
+    g.B = s->batch; g.C = s->channels; g.F = s->frames; g.H = s->height; g.W = s->width;
+    g.P = s->height * s->width; g.heads = s->heads; g.dh = s->heads > 0 ? s->channels / s->heads : 0;
+    g.layers = s->layers; g.A = s->attn_blocks; g.max_len = s->max_len;
+    g.N = (int64_t)s->batch * s->frames * g.P; g.pos_enc = s->pos_enc != 0; g.dtype = s->dtype;
+    return g;
+}
+inline size_t dtype_size(int dtype) { return dtype == NMM_BF16 ? 2 : 4; }
+
+// ---- device helpers ------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);   // .x = lo (low 16 bits), .y = hi
+    return *reinterpret_cast<uint32_t *>(&t);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+
+// exact (erf) GELU, as torch.nn.functional.gelu default -- motion_module_new.py:510-518
+__device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
+
+// ---- internal kernels' host launchers (defined in the .cu files) ----------------------------------
+// GroupNorm
+size_t gn_partial_bytes(const Geo &g);
+int launch_gn_stats(const Geo &g, const nmm_shape *s, const void *x, double *partial, cudaStream_t st);
+int launch_gn_finalize(const Geo &g, const nmm_shape *s, const double *partial, float *mean, float *rstd, cudaStream_t st);
+int launch_gn_tokens(const Geo &g, const nmm_shape *s, const void *x, const double *partial, const float *gn_w,
+                     const float *gn_b, void *tokens, cudaStream_t st);
+// LayerNorm (+PE)
+int launch_layernorm_pe(const Geo &g, const nmm_shape *s, const float *h, const float *w, const float *b,
+                        const float *pe, void *out, cudaStream_t st);
+// attention
+int launch_temporal_attention(const Geo &g, const void *qkv, void *ctx, cudaStream_t st);
+
+// GEMM + epilogue
+struct LinearArgs {
+    int epilogue;            // nmm_epilogue
+    int64_t M;
+    int N, K;                // N = rows of W
+    const void *A;           // [M,K]  dtype
+    const void *W;           // [N,K]  dtype
+    const float *bias;       // [N] fp32 or null
+    float *h;                // RESIDUAL: fp32 [M,N] in/out
+    void *out;               // STORE: [M,N]; RESIDUAL: optional [M,N] copy; GEGLU: [M,N/2]   (dtype)
+    // OUTPUT epilogue
+    const void *x; void *y;
+    int F, P;
+    int64_t xsb, xsc, xsf, ysb, ysc, ysf;
+};
+int launch_linear_simt(const LinearArgs &a, cudaStream_t st);     // fp32
+int launch_linear_tc(const LinearArgs &a, cudaStream_t st);       // bf16 tcgen05
+// parameter packing
+int launch_convert_rows(const void *src, int src_dtype, void *dst, int dst_dtype, int64_t rows, int64_t cols,
+                        int interleave_half /*0 or rows/2*/, cudaStream_t st);
+
+}  // namespace nmm

@@ -1,0 +1,258 @@
+// bf16 GEMM on the 5th-generation tensor cores:  D[M,N] = A[M,K] . W[N,K]^T, fp32 accumulation in TMEM,
+// fused epilogues (epilogue.cuh).  This is the production kernel for every nn.Linear on the motion-module
+// path (motion_module.py:145,152,289,297,298,321; motion_module_new.py:466,516).
+//
+// Structure (persistent, warp-specialised, one CTA per SM):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2-D tiles of A (128 x 64) and W (block_n x 64), 128-byte swizzle,
+//               into a `stages`-deep shared-memory ring; completion via mbarrier complete_tx.
+//   warp 1      MMA issuer: one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=block_n, K=16)
+//               4x per stage, tcgen05.commit releases the stage / publishes the accumulator.
+//   warp 2      TMEM allocator (2 accumulator buffers of block_n fp32 columns -> epilogue overlaps the next tile).
+//   warps 4-7   epilogue: tcgen05.ld (lane == output row), bias / residual / GEGLU / NCHW-store, direct global stores.
+// Both operands are K-major in global memory ([rows, K] row-major), which is exactly how activations
+// (token-major) and nn.Linear weights ([out, in]) are laid out, so no transposes are ever materialised.
+#include <cuda.h>
+
+#include <mutex>
+
+#include "common.cuh"
+#include "epilogue.cuh"
+#include "ptx.cuh"
+
+namespace nmm {
+
+constexpr int TC_BM = 128, TC_BK = 64, TC_THREADS = 256;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;            // 16 KB per stage
+constexpr int TC_SMEM_BUDGET = 220 * 1024;
+
+struct TcParams {
+    int64_t M;
+    int N, K;
+    int block_n, stages, n_tiles, tmem_cols;
+    int64_t m_tiles;
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, TcParams p, EpiParams e) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B tiles need 1024-byte alignment
+    const uint32_t b_bytes = (uint32_t)p.block_n * TC_BK * 2;
+    const uint32_t stage_bytes = TC_A_BYTES + b_bytes;
+    const uint32_t bar_base = smem_base + (uint32_t)p.stages * stage_bytes;
+    // barriers: full[stages], empty[stages], tmem_full[2], tmem_empty[2]; then the TMEM base address
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * p.stages + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * p.stages + 2 + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * p.stages + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_kb = (p.K + TC_BK - 1) / TC_BK;
+    const int64_t total_tiles = p.m_tiles * p.n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tm_a);
+        ptx::prefetch_tensormap(&tm_w);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.stages; s++) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < 2; s++) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), 128); }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 2) ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int64_t m_blk = tile / p.n_tiles;
+                const int n_blk = (int)(tile - m_blk * p.n_tiles);
+                for (int kb = 0; kb < num_kb; kb++) {
+                    ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+                    ptx::mbar_expect_tx(full_bar(stage), stage_bytes);
+                    const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
+                    ptx::tma_load_2d(&tm_a, full_bar(stage), sa, kb * TC_BK, (int32_t)(m_blk * TC_BM));
+                    ptx::tma_load_2d(&tm_w, full_bar(stage), sa + TC_A_BYTES, kb * TC_BK, n_blk * p.block_n);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = ptx::umma_idesc_bf16(TC_BM, (uint32_t)p.block_n);
+            int stage = 0; uint32_t phase = 0;
+            int as = 0; uint32_t aphase = 0;
+            for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);           // epilogue has drained this accumulator
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.block_n);
+                for (int kb = 0; kb < num_kb; kb++) {
+                    ptx::mbar_wait(full_bar(stage), phase);              // TMA bytes have landed
+                    ptx::tc_fence_after();
+                    const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
+                    const uint64_t a_desc = ptx::umma_smem_desc_sw128(sa);
+                    const uint64_t b_desc = ptx::umma_smem_desc_sw128(sa + TC_A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; k++)                 // +32 bytes per K=16 step inside the swizzle atom
+                        ptx::umma_bf16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                    ptx::umma_commit(empty_bar(stage));                   // stage reusable once these MMAs retire
+                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                }
+                ptx::umma_commit(tfull_bar(as));                          // accumulator complete
+                if (++as == 2) { as = 0; aphase ^= 1u; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int q = warp & 3;                                           // TMEM lane quadrant this warp may access
+        int as = 0; uint32_t aphase = 0;
+        for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int64_t m_blk = tile / p.n_tiles;
+            const int n_blk = (int)(tile - m_blk * p.n_tiles);
+            ptx::mbar_wait(tfull_bar(as), aphase);
+            ptx::tc_fence_after();
+            const int64_t row = m_blk * TC_BM + q * 32 + lane;
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.block_n);
+            for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+                uint32_t r[16];
+                ptx::tmem_ld16(t_row + (uint32_t)c0, r);
+                ptx::tmem_ld_wait();
+                const int col0 = n_blk * p.block_n + c0;
+                if (row < p.M && col0 < p.N) {
+                    float acc[16];
+#pragma unroll
+                    for (int j = 0; j < 16; j++) acc[j] = __uint_as_float(r[j]);
+                    epilogue_apply<EPI, bf16, 16>(e, row, col0, acc);
+                }
+            }
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(tempty_bar(as));
+            if (++as == 2) { as = 0; aphase ^= 1u; }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+// [rows, cols] row-major bf16 with leading dimension ld (elements); box = box_rows x 64 columns, 128-byte swizzle.
+static int make_tmap(CUtensorMap *tm, const void *ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return fail(NMM_ERR_DEVICE, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+    if (!aligned(ptr, 16) || (ld * 2) % 16 != 0) return fail(NMM_ERR_BAD_ARG, "TMA operand must be 16-byte aligned with a 16-byte multiple row pitch");
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(NMM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return NMM_OK;
+}
+
+static int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+// N tile: a multiple of 16 in [16, 256] that divides N; the largest one that still yields >= 2 waves of tiles,
+// otherwise the largest that yields >= 1 wave, otherwise the smallest divisor >= 64 (small-M levels of the UNet).
+static int choose_block_n(int64_t m_tiles, int N, int sms) {
+    int best2 = 0, best1 = 0, smallest = 0;
+    for (int bn = 256; bn >= 16; bn -= 16) {
+        if (N % bn) continue;
+        const int64_t tiles = m_tiles * (N / bn);
+        if (!best2 && tiles >= 2 * sms) best2 = bn;
+        if (!best1 && tiles >= sms) best1 = bn;
+        if (bn >= 64 || smallest == 0) smallest = bn;
+    }
+    if (best2) return best2;
+    if (best1) return best1;
+    return smallest;
+}
+
+template <int EPI>
+static int launch_tc_t(const CUtensorMap &ta, const CUtensorMap &tw, const TcParams &p, const EpiParams &e, size_t smem, int grid,
+                       cudaStream_t st) {
+    auto kern = linear_tc_kernel<EPI>;
+    static bool attr_set = false;     // per template instantiation
+    if (!attr_set) {
+        NMM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET + 2048));
+        attr_set = true;
+    }
+    kern<<<grid, TC_THREADS, smem, st>>>(ta, tw, p, e);
+    NMM_LAUNCHED("linear_tc_kernel");
+    return NMM_OK;
+}
+
+int launch_linear_tc(const LinearArgs &a, cudaStream_t st) {
+    if (a.N % 16 != 0) return fail(NMM_ERR_UNSUPPORTED, "tcgen05 GEMM needs N %% 16 == 0 (N=%d)", a.N);
+    if (a.K % 8 != 0) return fail(NMM_ERR_UNSUPPORTED, "tcgen05 GEMM needs K %% 8 == 0 (K=%d)", a.K);
+    if (a.M <= 0) return NMM_OK;
+    TcParams p;
+    p.M = a.M; p.N = a.N; p.K = a.K;
+    p.m_tiles = ceil_div(a.M, TC_BM);
+    const int sms = num_sms();
+    p.block_n = choose_block_n(p.m_tiles, a.N, sms);
+    p.n_tiles = a.N / p.block_n;
+    const size_t stage_bytes = (size_t)TC_A_BYTES + (size_t)p.block_n * TC_BK * 2;
+    int stages = (int)((TC_SMEM_BUDGET - 1024) / stage_bytes);
+    if (stages > 8) stages = 8;
+    if (stages < 2) return fail(NMM_ERR_UNSUPPORTED, "tcgen05 GEMM: tile does not fit shared memory");
+    p.stages = stages;
+    int cols = 32;
+    while (cols < 2 * p.block_n) cols <<= 1;
+    p.tmem_cols = cols;
+    const size_t smem = 1024 /*alignment slack*/ + (size_t)stages * stage_bytes + 8 * (2 * stages + 4) + 16;
+    CUtensorMap ta, tw;
+    int rc = make_tmap(&ta, a.A, a.M, a.K, a.K, TC_BM);
+    if (rc != NMM_OK) return rc;
+    rc = make_tmap(&tw, a.W, a.N, a.K, a.K, p.block_n);
+    if (rc != NMM_OK) return rc;
+    const int64_t tiles = p.m_tiles * p.n_tiles;
+    const int grid = (int)(tiles < sms ? tiles : sms);
+    EpiParams e = epi_params_of(a);
+    switch (a.epilogue) {
+        case NMM_EPI_STORE: return launch_tc_t<NMM_EPI_STORE>(ta, tw, p, e, smem, grid, st);
+        case NMM_EPI_RESIDUAL: return launch_tc_t<NMM_EPI_RESIDUAL>(ta, tw, p, e, smem, grid, st);
+        case NMM_EPI_GEGLU: return launch_tc_t<NMM_EPI_GEGLU>(ta, tw, p, e, smem, grid, st);
+        case NMM_EPI_OUTPUT: return launch_tc_t<NMM_EPI_OUTPUT>(ta, tw, p, e, smem, grid, st);
+        default: return fail(NMM_ERR_BAD_ARG, "unknown epilogue %d", a.epilogue);
+    }
+}
+
+}  // namespace nmm

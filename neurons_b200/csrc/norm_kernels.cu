@@ -1,0 +1,337 @@
+// GroupNorm statistics, GroupNorm-apply fused with the (b f) c h w -> (b f)(h w) c re-layout, and
+// LayerNorm(+positional encoding).  All three are HBM-bound streaming kernels:
+//   gn_stats        reads x once                                   bytes = N*C*s
+//   gn_tokens       reads x once, writes tokens once               bytes = 2*N*C*s
+//   layernorm_pe    reads h (fp32) once, writes n once             bytes = N*C*(4+s)
+// Reference arithmetic: motion_module.py:142-144 (GroupNorm + permute/reshape), :212/:219 (LayerNorm),
+// :241-243 (x + pe[:, :f]).
+#include "common.cuh"
+
+namespace nmm {
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm statistics.  One (b,f,group) = cpg channels x P positions; each channel is a dense run of
+// P elements at x + b*sb + c*sc + f*sf.  The group's cpg*P elements are cut into `splits` chunks so the
+// grid has >= ~8 CTAs per SM; each CTA writes one (sum, sumsq) pair in double.  Finalisation (mean,
+// rstd) is done by the consumer, so there are no atomics and the result is deterministic.
+// ------------------------------------------------------------------------------------------------
+constexpr int GN_THREADS = 256;
+constexpr int GN_CHUNK = 8192;      // elements per CTA
+
+static int gn_splits(const Geo &g) {
+    int64_t per_group = (int64_t)(g.C / NMM_GN_GROUPS) * g.P;
+    return (int)ceil_div(per_group, GN_CHUNK);
+}
+size_t gn_partial_bytes(const Geo &g) {
+    return (size_t)g.B * g.F * NMM_GN_GROUPS * gn_splits(g) * 2 * sizeof(double);
+}
+
+template <typename T> struct Vec16;   // 16-byte vector of T
+template <> struct Vec16<float> { static constexpr int N = 4; };
+template <> struct Vec16<bf16> { static constexpr int N = 8; };
+
+template <typename T>
+__device__ __forceinline__ void accum16(const T *p, float &s, float &ss) {
+    uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+    if constexpr (sizeof(T) == 4) {
+        float f[4] = {__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w)};
+#pragma unroll
+        for (int i = 0; i < 4; i++) { s += f[i]; ss = fmaf(f[i], f[i], ss); }
+    } else {
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            float a = bf16_lo(w[i]), b = bf16_hi(w[i]);
+            s += a + b; ss = fmaf(a, a, ss); ss = fmaf(b, b, ss);
+        }
+    }
+}
+
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const T *__restrict__ x, double *__restrict__ partial,
+                                                              int C, int F, int P, int splits, int64_t sb, int64_t sc,
+                                                              int64_t sf) {
+    const int cpg = C / NMM_GN_GROUPS;
+    const int split = blockIdx.x % splits;
+    const int grp = (blockIdx.x / splits) % NMM_GN_GROUPS;
+    const int bf = blockIdx.x / (splits * NMM_GN_GROUPS);
+    const int b = bf / F, f = bf % F;
+    const T *base = x + (int64_t)b * sb + (int64_t)f * sf + (int64_t)grp * cpg * sc;
+    const int64_t total = (int64_t)cpg * P;
+    const int64_t e0 = (int64_t)split * GN_CHUNK;
+    const int64_t e1 = min(total, e0 + (int64_t)GN_CHUNK);
+    float s = 0.f, ss = 0.f;
+    if constexpr (VEC) {
+        constexpr int V = Vec16<T>::N;                 // P % V == 0, so a vector never straddles channels
+        for (int64_t e = e0 + (int64_t)threadIdx.x * V; e < e1; e += (int64_t)GN_THREADS * V) {
+            int c = (int)(e / P); int p = (int)(e - (int64_t)c * P);
+            accum16<T>(base + (int64_t)c * sc + p, s, ss);
+        }
+    } else {
+        for (int64_t e = e0 + threadIdx.x; e < e1; e += GN_THREADS) {
+            int c = (int)(e / P); int p = (int)(e - (int64_t)c * P);
+            float v = to_f32(base[(int64_t)c * sc + p]);
+            s += v; ss = fmaf(v, v, ss);
+        }
+    }
+    // block reduce in double (per-thread fp32 partials cover <= 32 elements each)
+    __shared__ double sh[2][GN_THREADS / 32];
+    double ds = (double)warp_sum(s), dss = (double)warp_sum(ss);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { sh[0][warp] = ds; sh[1][warp] = dss; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, c2 = 0;
+#pragma unroll
+        for (int i = 0; i < GN_THREADS / 32; i++) { a += sh[0][i]; c2 += sh[1][i]; }
+        partial[(int64_t)blockIdx.x * 2 + 0] = a;
+        partial[(int64_t)blockIdx.x * 2 + 1] = c2;
+    }
+}
+
+template <typename T>
+static bool x_vec_ok(const Geo &g, const nmm_shape *s, const void *x) {
+    const int V = 16 / (int)sizeof(T);
+    return g.P % V == 0 && s->x_stride_b % V == 0 && s->x_stride_c % V == 0 && s->x_stride_f % V == 0 && aligned(x, 16);
+}
+
+int launch_gn_stats(const Geo &g, const nmm_shape *s, const void *x, double *partial, cudaStream_t st) {
+    const int splits = gn_splits(g);
+    const int64_t blocks = (int64_t)g.B * g.F * NMM_GN_GROUPS * splits;
+    if (blocks > 0x7fffffff) return fail(NMM_ERR_UNSUPPORTED, "gn_stats grid too large");
+    dim3 grid((unsigned)blocks), block(GN_THREADS);
+    if (g.dtype == NMM_BF16) {
+        if (x_vec_ok<bf16>(g, s, x))
+            gn_stats_kernel<bf16, true><<<grid, block, 0, st>>>((const bf16 *)x, partial, g.C, g.F, g.P, splits, s->x_stride_b, s->x_stride_c, s->x_stride_f);
+        else
+            gn_stats_kernel<bf16, false><<<grid, block, 0, st>>>((const bf16 *)x, partial, g.C, g.F, g.P, splits, s->x_stride_b, s->x_stride_c, s->x_stride_f);
+    } else {
+        if (x_vec_ok<float>(g, s, x))
+            gn_stats_kernel<float, true><<<grid, block, 0, st>>>((const float *)x, partial, g.C, g.F, g.P, splits, s->x_stride_b, s->x_stride_c, s->x_stride_f);
+        else
+            gn_stats_kernel<float, false><<<grid, block, 0, st>>>((const float *)x, partial, g.C, g.F, g.P, splits, s->x_stride_b, s->x_stride_c, s->x_stride_f);
+    }
+    NMM_LAUNCHED("gn_stats_kernel");
+    return NMM_OK;
+}
+
+__device__ __forceinline__ void gn_finalize_one(const double *__restrict__ partial, int bf_grp, int splits, double count,
+                                                float eps, float &mean, float &rstd) {
+    double a = 0, c2 = 0;
+    for (int i = 0; i < splits; i++) {
+        a += partial[((int64_t)bf_grp * splits + i) * 2 + 0];
+        c2 += partial[((int64_t)bf_grp * splits + i) * 2 + 1];
+    }
+    double m = a / count;
+    double var = c2 / count - m * m;          // biased variance, as torch.nn.GroupNorm
+    if (var < 0) var = 0;
+    mean = (float)m;
+    rstd = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+__global__ void gn_finalize_kernel(const double *__restrict__ partial, float *__restrict__ mean, float *__restrict__ rstd,
+                                   int n, int splits, double count, float eps) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float m, r;
+    gn_finalize_one(partial, i, splits, count, eps, m, r);
+    mean[i] = m; rstd[i] = r;
+}
+
+int launch_gn_finalize(const Geo &g, const nmm_shape *s, const double *partial, float *mean, float *rstd, cudaStream_t st) {
+    const int n = g.B * g.F * NMM_GN_GROUPS;
+    gn_finalize_kernel<<<(n + 127) / 128, 128, 0, st>>>(partial, mean, rstd, n, gn_splits(g),
+                                                         (double)(g.C / NMM_GN_GROUPS) * g.P, s->eps_gn);
+    NMM_LAUNCHED("gn_finalize_kernel");
+    return NMM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm apply + transpose to token-major.
+//   tokens[(bf*P + p), c] = (x[b,c,f,p] - mean[bf,g]) * rstd[bf,g] * gamma[c] + beta[c]
+// Generic kernel: 32(c) x 32(p) tile through shared memory, any dtype / alignment / ragged edges.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) gn_tokens_generic_kernel(const T *__restrict__ x, const double *__restrict__ partial,
+                                                                const float *__restrict__ gamma, const float *__restrict__ beta,
+                                                                T *__restrict__ tokens, int C, int F, int P, int splits,
+                                                                float eps, int64_t sb, int64_t sc, int64_t sf) {
+    __shared__ float tile[32][33];
+    __shared__ float sc_a[32], sc_b[32];
+    const int bf = blockIdx.z, b = bf / F, f = bf % F;
+    const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+    const int cpg = C / NMM_GN_GROUPS;
+    if (threadIdx.x < 32) {
+        int c = c0 + threadIdx.x;
+        if (c < C) {
+            float m, r;
+            gn_finalize_one(partial, bf * NMM_GN_GROUPS + c / cpg, splits, (double)cpg * P, eps, m, r);
+            float a = r * gamma[c];
+            sc_a[threadIdx.x] = a; sc_b[threadIdx.x] = beta[c] - m * a;
+        }
+    }
+    __syncthreads();
+    const T *base = x + (int64_t)b * sb + (int64_t)f * sf;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int cl = ty + i * 8, c = c0 + cl, p = p0 + tx;
+        if (c < C && p < P) tile[cl][tx] = fmaf(to_f32(base[(int64_t)c * sc + p]), sc_a[cl], sc_b[cl]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int pl = ty + i * 8, p = p0 + pl, c = c0 + tx;
+        if (c < C && p < P) tokens[((int64_t)bf * P + p) * C + c] = from_f32<T>(tile[tx][pl]);
+    }
+}
+
+// Fast bf16 kernel: 64(c) x 64(p) tile, 16-byte loads along p, channel pairs packed as bf16x2 before the
+// shared-memory transpose (4-byte conflict-light stores), 16-byte stores along c.  Requires C % 64 == 0,
+// P % 64 == 0 and 16-byte aligned rows.
+__global__ void __launch_bounds__(256) gn_tokens_bf16_kernel(const bf16 *__restrict__ x, const double *__restrict__ partial,
+                                                             const float *__restrict__ gamma, const float *__restrict__ beta,
+                                                             bf16 *__restrict__ tokens, int C, int F, int P, int splits,
+                                                             float eps, int64_t sb, int64_t sc, int64_t sf) {
+    __shared__ uint32_t tile[64][33];            // [p][channel pair]
+    __shared__ float sc_a[64], sc_b[64];
+    const int bf = blockIdx.z, b = bf / F, f = bf % F;
+    const int c0 = blockIdx.y * 64, p0 = blockIdx.x * 64;
+    const int cpg = C / NMM_GN_GROUPS;
+    const int t = threadIdx.x;
+    if (t < 64) {
+        int c = c0 + t;
+        float m, r;
+        gn_finalize_one(partial, bf * NMM_GN_GROUPS + c / cpg, splits, (double)cpg * P, eps, m, r);
+        float a = r * gamma[c];
+        sc_a[t] = a; sc_b[t] = beta[c] - m * a;
+    }
+    const int pv = t & 7, cp = t >> 3;           // 8 p-vectors x 32 channel pairs
+    const bf16 *src = x + (int64_t)b * sb + (int64_t)f * sf + (int64_t)(c0 + 2 * cp) * sc + p0 + pv * 8;
+    uint4 v0 = __ldg(reinterpret_cast<const uint4 *>(src));
+    uint4 v1 = __ldg(reinterpret_cast<const uint4 *>(src + sc));
+    __syncthreads();
+    const float a0 = sc_a[2 * cp], b0 = sc_b[2 * cp], a1 = sc_a[2 * cp + 1], b1 = sc_b[2 * cp + 1];
+    const uint32_t w0[4] = {v0.x, v0.y, v0.z, v0.w}, w1[4] = {v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        tile[pv * 8 + 2 * i][cp] = pack_bf16x2(fmaf(bf16_lo(w0[i]), a0, b0), fmaf(bf16_lo(w1[i]), a1, b1));
+        tile[pv * 8 + 2 * i + 1][cp] = pack_bf16x2(fmaf(bf16_hi(w0[i]), a0, b0), fmaf(bf16_hi(w1[i]), a1, b1));
+    }
+    __syncthreads();
+    const int pl = t >> 2, q = t & 3;            // 64 rows x 4 quarter-rows (32 bytes each)
+    uint32_t o[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) o[i] = tile[pl][q * 8 + i];
+    bf16 *dst = tokens + ((int64_t)bf * P + p0 + pl) * C + c0 + q * 16;
+    reinterpret_cast<uint4 *>(dst)[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    reinterpret_cast<uint4 *>(dst)[1] = make_uint4(o[4], o[5], o[6], o[7]);
+}
+
+int launch_gn_tokens(const Geo &g, const nmm_shape *s, const void *x, const double *partial, const float *gn_w,
+                     const float *gn_b, void *tokens, cudaStream_t st) {
+    const int splits = gn_splits(g);
+    if (g.B * g.F > 65535) return fail(NMM_ERR_UNSUPPORTED, "batch*frames > 65535");
+    if (g.dtype == NMM_BF16 && g.C % 64 == 0 && g.P % 64 == 0 && x_vec_ok<bf16>(g, s, x) && aligned(tokens, 16)) {
+        dim3 grid(g.P / 64, g.C / 64, g.B * g.F);
+        gn_tokens_bf16_kernel<<<grid, 256, 0, st>>>((const bf16 *)x, partial, gn_w, gn_b, (bf16 *)tokens, g.C, g.F, g.P,
+                                                    splits, s->eps_gn, s->x_stride_b, s->x_stride_c, s->x_stride_f);
+        NMM_LAUNCHED("gn_tokens_bf16_kernel");
+        return NMM_OK;
+    }
+    dim3 grid((g.P + 31) / 32, (g.C + 31) / 32, g.B * g.F);
+    if (grid.y > 65535) return fail(NMM_ERR_UNSUPPORTED, "channels too large");
+    if (g.dtype == NMM_BF16)
+        gn_tokens_generic_kernel<bf16><<<grid, 256, 0, st>>>((const bf16 *)x, partial, gn_w, gn_b, (bf16 *)tokens, g.C, g.F,
+                                                             g.P, splits, s->eps_gn, s->x_stride_b, s->x_stride_c, s->x_stride_f);
+    else
+        gn_tokens_generic_kernel<float><<<grid, 256, 0, st>>>((const float *)x, partial, gn_w, gn_b, (float *)tokens, g.C, g.F,
+                                                              g.P, splits, s->eps_gn, s->x_stride_b, s->x_stride_c, s->x_stride_f);
+    NMM_LAUNCHED("gn_tokens_generic_kernel");
+    return NMM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over C (+ pe[frame of the token]).  One warp per token row; the row lives in registers
+// (two-pass mean / variance, fp32).  h is the fp32 residual stream; out is the GEMM operand dtype.
+// ITERS = C / 64 (each lane holds ITERS float2) for the register-resident path; ITERS = 0 is the
+// generic path (any C, re-reads the row from L1/L2).
+// ------------------------------------------------------------------------------------------------
+template <typename TOut, int ITERS>
+__global__ void __launch_bounds__(256) layernorm_pe_kernel(const float *__restrict__ h, const float *__restrict__ gamma,
+                                                           const float *__restrict__ beta, const float *__restrict__ pe,
+                                                           TOut *__restrict__ out, int64_t N, int C, int F, int P, float eps) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= N) return;
+    const float *hr = h + row * C;
+    const float *per = pe ? pe + (int64_t)((row / P) % F) * C : nullptr;
+    TOut *orow = out + row * C;
+    const float invC = 1.0f / (float)C;
+    if constexpr (ITERS > 0) {
+        float2 v[ITERS];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < ITERS; i++) {
+            v[i] = __ldg(reinterpret_cast<const float2 *>(hr) + lane + 32 * i);
+            s += v[i].x + v[i].y;
+        }
+        const float mu = warp_sum(s) * invC;
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < ITERS; i++) {
+            float a = v[i].x - mu, b = v[i].y - mu;
+            ss = fmaf(a, a, ss); ss = fmaf(b, b, ss);
+        }
+        const float rstd = rsqrtf(warp_sum(ss) * invC + eps);
+#pragma unroll
+        for (int i = 0; i < ITERS; i++) {
+            const int c2 = lane + 32 * i;                      // float2 index
+            float2 gm = __ldg(reinterpret_cast<const float2 *>(gamma) + c2);
+            float2 bt = __ldg(reinterpret_cast<const float2 *>(beta) + c2);
+            float a = fmaf((v[i].x - mu) * rstd, gm.x, bt.x), b = fmaf((v[i].y - mu) * rstd, gm.y, bt.y);
+            if (per) { float2 pp = __ldg(reinterpret_cast<const float2 *>(per) + c2); a += pp.x; b += pp.y; }
+            if constexpr (sizeof(TOut) == 2) reinterpret_cast<uint32_t *>(orow)[c2] = pack_bf16x2(a, b);
+            else reinterpret_cast<float2 *>(orow)[c2] = make_float2(a, b);
+        }
+    } else {
+        float s = 0.f;
+        for (int c = lane; c < C; c += 32) s += hr[c];
+        const float mu = warp_sum(s) * invC;
+        float ss = 0.f;
+        for (int c = lane; c < C; c += 32) { float a = hr[c] - mu; ss = fmaf(a, a, ss); }
+        const float rstd = rsqrtf(warp_sum(ss) * invC + eps);
+        for (int c = lane; c < C; c += 32) {
+            float a = fmaf((hr[c] - mu) * rstd, gamma[c], beta[c]);
+            if (per) a += per[c];
+            orow[c] = from_f32<TOut>(a);
+        }
+    }
+}
+
+template <typename TOut>
+static int launch_ln_t(const Geo &g, const nmm_shape *s, const float *h, const float *w, const float *b, const float *pe,
+                       TOut *out, cudaStream_t st) {
+    const int rows_per_block = 8;
+    const int64_t blocks = ceil_div(g.N, rows_per_block);
+    if (blocks > 0x7fffffff) return fail(NMM_ERR_UNSUPPORTED, "too many tokens");
+    dim3 grid((unsigned)blocks), block(rows_per_block * 32);
+#define LN_CASE(IT) layernorm_pe_kernel<TOut, IT><<<grid, block, 0, st>>>(h, w, b, pe, out, g.N, g.C, g.F, g.P, s->eps_ln)
+    switch (g.C) {
+        case 320: LN_CASE(5); break;
+        case 640: LN_CASE(10); break;
+        case 1280: LN_CASE(20); break;
+        default: LN_CASE(0); break;
+    }
+#undef LN_CASE
+    NMM_LAUNCHED("layernorm_pe_kernel");
+    return NMM_OK;
+}
+
+int launch_layernorm_pe(const Geo &g, const nmm_shape *s, const float *h, const float *w, const float *b, const float *pe,
+                        void *out, cudaStream_t st) {
+    if (g.dtype == NMM_BF16) return launch_ln_t<bf16>(g, s, h, w, b, pe, (bf16 *)out, st);
+    return launch_ln_t<float>(g, s, h, w, b, pe, (float *)out, st);
+}
+
+}  // namespace nmm

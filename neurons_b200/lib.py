@@ -1,0 +1,103 @@
+"""ctypes binding of libneurons_mm.so (the C ABI declared in include/neurons_mm.h).
+
+There is deliberately no fallback: if the shared object is missing, or a compute call is made without an
+sm_100 GPU, this raises -- the product path never routes through PyTorch eager or the CPU oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libneurons_mm.so")
+
+NMM_MAX_LAYERS = 4
+NMM_MAX_ATTN = 4
+NMM_MAX_FRAMES = 32
+NMM_F32, NMM_BF16 = 0, 1
+EPI_STORE, EPI_RESIDUAL, EPI_GEGLU, EPI_OUTPUT = 0, 1, 2, 3
+STATUS_NAMES = {0: "NMM_OK", -1: "NMM_ERR_BAD_ARG", -2: "NMM_ERR_UNSUPPORTED", -3: "NMM_ERR_WORKSPACE",
+                -4: "NMM_ERR_CUDA", -5: "NMM_ERR_DEVICE"}
+
+
+class NmmError(RuntimeError):
+    def __init__(self, status: int, text: str):
+        super().__init__(f"{STATUS_NAMES.get(status, status)}: {text}")
+        self.status = status
+
+
+class Shape(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("channels", C.c_int32), ("frames", C.c_int32), ("height", C.c_int32), ("width", C.c_int32),
+        ("heads", C.c_int32), ("layers", C.c_int32), ("attn_blocks", C.c_int32), ("pos_enc", C.c_int32),
+        ("max_len", C.c_int32), ("dtype", C.c_int32), ("eps_gn", C.c_float), ("eps_ln", C.c_float),
+        ("x_stride_b", C.c_int64), ("x_stride_c", C.c_int64), ("x_stride_f", C.c_int64),
+        ("y_stride_b", C.c_int64), ("y_stride_c", C.c_int64), ("y_stride_f", C.c_int64),
+    ]
+
+
+class AttnParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("norm_w", "norm_b", "to_q", "to_k", "to_v", "to_out_w", "to_out_b", "pe")]
+
+
+class LayerParams(C.Structure):
+    _fields_ = [("attn", AttnParams * NMM_MAX_ATTN)] + [
+        (n, C.c_void_p) for n in ("ff_norm_w", "ff_norm_b", "ff_proj_w", "ff_proj_b", "ff_out_w", "ff_out_b")]
+
+
+class Params(C.Structure):
+    _fields_ = [("dtype", C.c_int32), ("gn_w", C.c_void_p), ("gn_b", C.c_void_p), ("proj_in_w", C.c_void_p),
+                ("proj_in_b", C.c_void_p), ("layer", LayerParams * NMM_MAX_LAYERS), ("proj_out_w", C.c_void_p),
+                ("proj_out_b", C.c_void_p)]
+
+
+# name -> (restype, argtypes); must list every NMM_API symbol of include/neurons_mm.h (tests/test_abi.py checks)
+_SP = C.POINTER(Shape)
+SIGNATURES = {
+    "nmm_abi_version": (C.c_int, []),
+    "nmm_last_error": (C.c_char_p, []),
+    "nmm_device_check": (C.c_int, []),
+    "nmm_launch_count": (C.c_uint64, []),
+    "nmm_validate": (C.c_int, [_SP]),
+    "nmm_packed_params_bytes": (C.c_int, [_SP, C.POINTER(C.c_size_t)]),
+    "nmm_workspace_bytes": (C.c_int, [_SP, C.POINTER(C.c_size_t)]),
+    "nmm_pack_params": (C.c_int, [_SP, C.POINTER(Params), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "nmm_forward": (C.c_int, [_SP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "nmm_groupnorm_stats": (C.c_int, [_SP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "nmm_groupnorm_tokens": (C.c_int, [_SP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "nmm_layernorm_pe": (C.c_int, [_SP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nmm_temporal_attention": (C.c_int, [_SP, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nmm_linear": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                             C.c_void_p, C.c_void_p, _SP, C.c_void_p, C.c_void_p, C.c_void_p]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libneurons_mm.so (built in-tree by `python -m neurons_b200.build`).  Raises if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -m neurons_b200.build` "
+            "(there is no PyTorch/CPU fallback for the motion-module path)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the ABI and this binding disagree
+        fn.restype = res
+        fn.argtypes = args
+    if lib.nmm_abi_version() != 1:
+        raise RuntimeError(f"libneurons_mm.so ABI version {lib.nmm_abi_version()} != 1")
+    _lib = lib
+    return lib
+
+
+def check(status: int):
+    if status != 0:
+        raise NmmError(status, load().nmm_last_error().decode("utf-8", "replace"))
+
+
+def launch_count() -> int:
+    return int(load().nmm_launch_count())
