@@ -110,6 +110,21 @@ NMM_API int nmm_device_check(void);
 /* number of kernels this library has launched in this process (bench.py's `gpu_launches` claim). */
 NMM_API uint64_t nmm_launch_count(void);
 
+/* Optional per-kernel device timing for roofline reporting: between begin and end the library brackets every kernel
+ * launch with CUDA events on the launch stream (eager launches only; launches inside a stream capture are skipped).
+ * nmm_profile_end synchronises on the recorded events and fills one entry per kernel (NMM_PROFILE_KERNELS entries):
+ * launches, summed device ms, and the summed ALGORITHMIC flops / bytes of those launches. */
+#define NMM_PROFILE_KERNELS 7
+typedef struct nmm_kernel_profile {
+    const char *name;
+    uint64_t launches;
+    double total_ms;
+    double flops;
+    double bytes;
+} nmm_kernel_profile;
+NMM_API int nmm_profile_begin(void);
+NMM_API int nmm_profile_end(nmm_kernel_profile *out, int32_t max_kernels);
+
 /* ---- whole-module forward (replaces motion_module.py:77-82 -> :134-158) ----------------------- */
 NMM_API int nmm_validate(const nmm_shape *s);
 NMM_API int nmm_packed_params_bytes(const nmm_shape *s, size_t *out_bytes);

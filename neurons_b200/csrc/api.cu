@@ -2,6 +2,9 @@
 // kernel sequence of one VanillaTemporalModule.forward (motion_module.py:77-82 -> :134-158 -> :210-222 -> :270-329).
 #include <cmath>
 #include <cstring>
+#include <mutex>
+#include <utility>
+#include <vector>
 
 #include "common.cuh"
 
@@ -21,6 +24,39 @@ int fail(int status, const char *fmt, ...) {
     va_end(ap);
     last_error_ref() = buf;
     return status;
+}
+
+// ---- per-kernel device timing ---------------------------------------------------------------------------------
+namespace {
+struct ProfRecord { cudaEvent_t start, stop; int kid; double flops, bytes; };
+struct Profiler {
+    bool enabled = false;
+    std::vector<ProfRecord> rec;      // used records
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pool;   // reusable event pairs
+    std::mutex mu;
+} g_prof;
+}  // namespace
+
+ProfScope::ProfScope(int kid, cudaStream_t stream, double flops, double bytes) : slot(-1), st(stream) {
+    if (!g_prof.enabled) return;
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return;   // events cannot time inside a capture
+    ProfRecord r;
+    if (g_prof.pool.empty()) {
+        if (cudaEventCreate(&r.start) != cudaSuccess || cudaEventCreate(&r.stop) != cudaSuccess) return;
+    } else {
+        r.start = g_prof.pool.back().first; r.stop = g_prof.pool.back().second; g_prof.pool.pop_back();
+    }
+    r.kid = kid; r.flops = flops; r.bytes = bytes;
+    cudaEventRecord(r.start, stream);
+    g_prof.rec.push_back(r);
+    slot = (int)g_prof.rec.size() - 1;
+}
+ProfScope::~ProfScope() {
+    if (slot < 0) return;
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    if (slot < (int)g_prof.rec.size()) cudaEventRecord(g_prof.rec[slot].stop, st);
 }
 
 // ---- packed parameter layout -------------------------------------------------------------------------
@@ -116,6 +152,7 @@ int launch_convert_rows(const void *src, int src_dtype, void *dst, int dst_dtype
     if (total == 0) return NMM_OK;
     const int threads = 256;
     const int blocks = (int)std::min<int64_t>(ceil_div(total, threads), 148 * 16);
+    ProfScope prof(K_PACK, st, 0.0, (double)total * (dtype_size(src_dtype) + dtype_size(dst_dtype)));
     if (src_dtype == NMM_F32 && dst_dtype == NMM_F32) convert_rows_kernel<float, float><<<blocks, threads, 0, st>>>((const float *)src, (float *)dst, rows, cols, half);
     else if (src_dtype == NMM_F32 && dst_dtype == NMM_BF16) convert_rows_kernel<float, bf16><<<blocks, threads, 0, st>>>((const float *)src, (bf16 *)dst, rows, cols, half);
     else if (src_dtype == NMM_BF16 && dst_dtype == NMM_F32) convert_rows_kernel<bf16, float><<<blocks, threads, 0, st>>>((const bf16 *)src, (float *)dst, rows, cols, half);
@@ -149,6 +186,34 @@ const char *nmm_last_error(void) { return last_error_ref().c_str(); }
 uint64_t nmm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 int nmm_device_check(void) { return device_check(); }
 int nmm_validate(const nmm_shape *s) { return validate(s); }
+
+int nmm_profile_begin(void) {
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    for (auto &r : g_prof.rec) g_prof.pool.emplace_back(r.start, r.stop);
+    g_prof.rec.clear();
+    g_prof.enabled = true;
+    return NMM_OK;
+}
+
+int nmm_profile_end(nmm_kernel_profile *out, int32_t max_kernels) {
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    g_prof.enabled = false;
+    if (!out || max_kernels < K_COUNT) return fail(NMM_ERR_BAD_ARG, "nmm_profile_end needs room for %d kernels", (int)K_COUNT);
+    static const char *names[K_COUNT] = {"gn_stats", "gn_tokens", "layernorm_pe", "temporal_attention", "linear_fp32_fma",
+                                         "linear_bf16_tcgen05", "pack_params"};
+    for (int k = 0; k < K_COUNT; k++) { out[k].name = names[k]; out[k].launches = 0; out[k].total_ms = 0; out[k].flops = 0; out[k].bytes = 0; }
+    int rc = NMM_OK;
+    for (auto &r : g_prof.rec) {
+        float ms = 0.f;
+        cudaError_t e = cudaEventSynchronize(r.stop);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, r.start, r.stop);
+        if (e != cudaSuccess) { rc = fail(NMM_ERR_CUDA, "profile event: %s", cudaGetErrorString(e)); cudaGetLastError(); continue; }
+        out[r.kid].launches += 1; out[r.kid].total_ms += ms; out[r.kid].flops += r.flops; out[r.kid].bytes += r.bytes;
+        g_prof.pool.emplace_back(r.start, r.stop);
+    }
+    g_prof.rec.clear();
+    return rc;
+}
 
 int nmm_packed_params_bytes(const nmm_shape *s, size_t *out_bytes) {
     int rc = validate(s);

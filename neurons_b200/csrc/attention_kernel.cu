@@ -177,7 +177,12 @@ static int launch_attn_t(const Geo &g, const T *qkv, T *ctx, cudaStream_t st) {
 #define ATTN_CASE(FM)                                                                                                    \
     do {                                                                                                                 \
         auto kern = temporal_attention_kernel<T, VEC, FM>;                                                               \
-        if (smem > 48 * 1024) NMM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        static bool attr_set = false; /* once per instantiation; never inside a stream capture after warm-up */         \
+        if (!attr_set) {                                                                                                 \
+            NMM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));          \
+            attr_set = true;                                                                                             \
+        }                                                                                                                \
+        ProfScope prof(K_ATTENTION, st, 4.0 * g.N * g.F * g.C, 4.0 * g.N * g.C * sizeof(T));                             \
         kern<<<(unsigned)blocks, threads, smem, st>>>(qkv, ctx, g.B, g.F, g.P, g.C, g.heads, PB, scale);                  \
     } while (0)
     if (g.F <= 8) ATTN_CASE(8);

@@ -29,6 +29,15 @@ extern std::atomic<uint64_t> g_launches;
                                __FILE__, __LINE__);                                                 \
     } while (0)
 
+// ---- optional per-kernel device timing (bench.py roofline): CUDA events around every launch, on the launch stream ----
+enum KernelId { K_GN_STATS = 0, K_GN_TOKENS, K_LAYERNORM, K_ATTENTION, K_LINEAR_SIMT, K_LINEAR_TC, K_PACK, K_COUNT };
+struct ProfScope {          // records start on construction, stop on destruction; no-op unless profiling is enabled
+    int slot;
+    cudaStream_t st;
+    ProfScope(int kid, cudaStream_t stream, double flops, double bytes);
+    ~ProfScope();
+};
+
 // Count + check a kernel launch without synchronising (stays graph-capturable).
 #define NMM_LAUNCHED(name)                                                                          \
     do {                                                                                            \
@@ -114,6 +123,19 @@ struct LinearArgs {
     int F, P;
     int64_t xsb, xsc, xsf, ysb, ysc, ysf;
 };
+// algorithmic work of one Linear launch: 2*M*N*K flops; bytes = operands once + epilogue traffic once
+inline double linear_flops(const LinearArgs &a) { return 2.0 * (double)a.M * a.N * a.K; }
+inline double linear_bytes(const LinearArgs &a, int es) {
+    const double MN = (double)a.M * a.N;
+    double b = ((double)a.M * a.K + (double)a.N * a.K) * es + (a.bias ? 4.0 * a.N : 0.0);
+    switch (a.epilogue) {
+        case NMM_EPI_STORE: b += (a.h ? 4.0 * MN : 0.0) + (a.out ? es * MN : 0.0); break;
+        case NMM_EPI_RESIDUAL: b += 8.0 * MN + (a.out ? es * MN : 0.0); break;
+        case NMM_EPI_GEGLU: b += es * MN / 2; break;
+        default: b += 2.0 * es * MN; break;      // OUTPUT: read x, write y
+    }
+    return b;
+}
 int launch_linear_simt(const LinearArgs &a, cudaStream_t st);     // fp32
 int launch_linear_tc(const LinearArgs &a, cudaStream_t st);       // bf16 tcgen05
 // parameter packing

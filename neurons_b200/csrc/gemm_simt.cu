@@ -74,6 +74,7 @@ int launch_linear_simt(const LinearArgs &a, cudaStream_t st) {
     dim3 grid((a.N + SG_BN - 1) / SG_BN, (unsigned)mt), block(SG_THREADS);
     EpiParams e = epi_params_of(a);
     const float *A = (const float *)a.A, *W = (const float *)a.W;
+    ProfScope prof(K_LINEAR_SIMT, st, linear_flops(a), linear_bytes(a, 4));
     switch (a.epilogue) {
         case NMM_EPI_STORE: linear_simt_kernel<NMM_EPI_STORE><<<grid, block, 0, st>>>(A, W, a.K, e); break;
         case NMM_EPI_RESIDUAL: linear_simt_kernel<NMM_EPI_RESIDUAL><<<grid, block, 0, st>>>(A, W, a.K, e); break;

@@ -207,14 +207,17 @@ static int choose_block_n(int64_t m_tiles, int N, int sms) {
 
 template <int EPI>
 static int launch_tc_t(const CUtensorMap &ta, const CUtensorMap &tw, const TcParams &p, const EpiParams &e, size_t smem, int grid,
-                       cudaStream_t st) {
+                       cudaStream_t st, double flops, double bytes) {
     auto kern = linear_tc_kernel<EPI>;
     static bool attr_set = false;     // per template instantiation
     if (!attr_set) {
         NMM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET + 2048));
         attr_set = true;
     }
-    kern<<<grid, TC_THREADS, smem, st>>>(ta, tw, p, e);
+    {
+        ProfScope prof(K_LINEAR_TC, st, flops, bytes);
+        kern<<<grid, TC_THREADS, smem, st>>>(ta, tw, p, e);
+    }
     NMM_LAUNCHED("linear_tc_kernel");
     return NMM_OK;
 }
@@ -246,11 +249,12 @@ int launch_linear_tc(const LinearArgs &a, cudaStream_t st) {
     const int64_t tiles = p.m_tiles * p.n_tiles;
     const int grid = (int)(tiles < sms ? tiles : sms);
     EpiParams e = epi_params_of(a);
+    const double fl = linear_flops(a), by = linear_bytes(a, 2);
     switch (a.epilogue) {
-        case NMM_EPI_STORE: return launch_tc_t<NMM_EPI_STORE>(ta, tw, p, e, smem, grid, st);
-        case NMM_EPI_RESIDUAL: return launch_tc_t<NMM_EPI_RESIDUAL>(ta, tw, p, e, smem, grid, st);
-        case NMM_EPI_GEGLU: return launch_tc_t<NMM_EPI_GEGLU>(ta, tw, p, e, smem, grid, st);
-        case NMM_EPI_OUTPUT: return launch_tc_t<NMM_EPI_OUTPUT>(ta, tw, p, e, smem, grid, st);
+        case NMM_EPI_STORE: return launch_tc_t<NMM_EPI_STORE>(ta, tw, p, e, smem, grid, st, fl, by);
+        case NMM_EPI_RESIDUAL: return launch_tc_t<NMM_EPI_RESIDUAL>(ta, tw, p, e, smem, grid, st, fl, by);
+        case NMM_EPI_GEGLU: return launch_tc_t<NMM_EPI_GEGLU>(ta, tw, p, e, smem, grid, st, fl, by);
+        case NMM_EPI_OUTPUT: return launch_tc_t<NMM_EPI_OUTPUT>(ta, tw, p, e, smem, grid, st, fl, by);
         default: return fail(NMM_ERR_BAD_ARG, "unknown epilogue %d", a.epilogue);
     }
 }

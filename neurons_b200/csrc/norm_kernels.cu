@@ -100,6 +100,7 @@ int launch_gn_stats(const Geo &g, const nmm_shape *s, const void *x, double *par
     const int64_t blocks = (int64_t)g.B * g.F * NMM_GN_GROUPS * splits;
     if (blocks > 0x7fffffff) return fail(NMM_ERR_UNSUPPORTED, "gn_stats grid too large");
     dim3 grid((unsigned)blocks), block(GN_THREADS);
+    ProfScope prof(K_GN_STATS, st, 0.0, (double)g.N * g.C * dtype_size(g.dtype));
     if (g.dtype == NMM_BF16) {
         if (x_vec_ok<bf16>(g, s, x))
             gn_stats_kernel<bf16, true><<<grid, block, 0, st>>>((const bf16 *)x, partial, g.C, g.F, g.P, splits, s->x_stride_b, s->x_stride_c, s->x_stride_f);
@@ -234,6 +235,7 @@ int launch_gn_tokens(const Geo &g, const nmm_shape *s, const void *x, const doub
     if (g.B * g.F > 65535) return fail(NMM_ERR_UNSUPPORTED, "batch*frames > 65535");
     if (g.dtype == NMM_BF16 && g.C % 64 == 0 && g.P % 64 == 0 && x_vec_ok<bf16>(g, s, x) && aligned(tokens, 16)) {
         dim3 grid(g.P / 64, g.C / 64, g.B * g.F);
+        ProfScope prof(K_GN_TOKENS, st, 0.0, 2.0 * g.N * g.C * dtype_size(g.dtype));
         gn_tokens_bf16_kernel<<<grid, 256, 0, st>>>((const bf16 *)x, partial, gn_w, gn_b, (bf16 *)tokens, g.C, g.F, g.P,
                                                     splits, s->eps_gn, s->x_stride_b, s->x_stride_c, s->x_stride_f);
         NMM_LAUNCHED("gn_tokens_bf16_kernel");
@@ -241,6 +243,7 @@ int launch_gn_tokens(const Geo &g, const nmm_shape *s, const void *x, const doub
     }
     dim3 grid((g.P + 31) / 32, (g.C + 31) / 32, g.B * g.F);
     if (grid.y > 65535) return fail(NMM_ERR_UNSUPPORTED, "channels too large");
+    ProfScope prof(K_GN_TOKENS, st, 0.0, 2.0 * g.N * g.C * dtype_size(g.dtype));
     if (g.dtype == NMM_BF16)
         gn_tokens_generic_kernel<bf16><<<grid, 256, 0, st>>>((const bf16 *)x, partial, gn_w, gn_b, (bf16 *)tokens, g.C, g.F,
                                                              g.P, splits, s->eps_gn, s->x_stride_b, s->x_stride_c, s->x_stride_f);
@@ -316,6 +319,7 @@ static int launch_ln_t(const Geo &g, const nmm_shape *s, const float *h, const f
     const int64_t blocks = ceil_div(g.N, rows_per_block);
     if (blocks > 0x7fffffff) return fail(NMM_ERR_UNSUPPORTED, "too many tokens");
     dim3 grid((unsigned)blocks), block(rows_per_block * 32);
+    ProfScope prof(K_LAYERNORM, st, 0.0, (double)g.N * g.C * (4 + sizeof(TOut)));
 #define LN_CASE(IT) layernorm_pe_kernel<TOut, IT><<<grid, block, 0, st>>>(h, w, b, pe, out, g.N, g.C, g.F, g.P, s->eps_ln)
     switch (g.C) {
         case 320: LN_CASE(5); break;

@@ -51,6 +51,13 @@ class Params(C.Structure):
                 ("proj_out_b", C.c_void_p)]
 
 
+class KernelProfile(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("launches", C.c_uint64), ("total_ms", C.c_double), ("flops", C.c_double),
+                ("bytes", C.c_double)]
+
+
+PROFILE_KERNELS = 7
+
 # name -> (restype, argtypes); must list every NMM_API symbol of include/neurons_mm.h (tests/test_abi.py checks)
 _SP = C.POINTER(Shape)
 SIGNATURES = {
@@ -58,6 +65,8 @@ SIGNATURES = {
     "nmm_last_error": (C.c_char_p, []),
     "nmm_device_check": (C.c_int, []),
     "nmm_launch_count": (C.c_uint64, []),
+    "nmm_profile_begin": (C.c_int, []),
+    "nmm_profile_end": (C.c_int, [C.POINTER(KernelProfile), C.c_int32]),
     "nmm_validate": (C.c_int, [_SP]),
     "nmm_packed_params_bytes": (C.c_int, [_SP, C.POINTER(C.c_size_t)]),
     "nmm_workspace_bytes": (C.c_int, [_SP, C.POINTER(C.c_size_t)]),
@@ -97,6 +106,18 @@ def load() -> C.CDLL:
 def check(status: int):
     if status != 0:
         raise NmmError(status, load().nmm_last_error().decode("utf-8", "replace"))
+
+
+def profile_begin():
+    check(load().nmm_profile_begin())
+
+
+def profile_end():
+    """-> {kernel name: dict(launches, total_ms, flops, bytes)} for the launches since profile_begin()."""
+    arr = (KernelProfile * PROFILE_KERNELS)()
+    check(load().nmm_profile_end(arr, PROFILE_KERNELS))
+    return {k.name.decode(): dict(launches=int(k.launches), total_ms=float(k.total_ms), flops=float(k.flops), bytes=float(k.bytes))
+            for k in arr}
 
 
 def launch_count() -> int:

@@ -1,0 +1,304 @@
+"""GPU (-m gpu): the CUDA path through the C ABI against the CPU oracle and the committed golden fixtures.
+
+Bars (BASELINE.json north_star): fp32 mode max-abs <= 1e-4 vs the fp32 reference; bf16 mode max-abs <= 2e-2 vs the
+reference evaluated on the same bf16-rounded inputs and weights.  Stage-level tests use tighter, stage-appropriate
+tolerances written at each assert.
+"""
+import pytest
+import torch
+
+import neurons_b200 as nb
+from neurons_b200 import lib as nlib
+from neurons_b200 import ops
+from oracle import motion_oracle as mo
+from tests import helpers
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _require_b200(built_library):
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    with torch.cuda.device(0):
+        rc = built_library.nmm_device_check()
+    assert rc == 0, built_library.nmm_last_error()
+
+
+def _cfg(c: mo.MotionConfig) -> nb.ModuleConfig:
+    return nb.ModuleConfig(c.channels, c.heads, c.layers, c.attn_blocks, c.pos_enc, c.max_len)
+
+
+def _maxabs(a, b):
+    return (a.double().cpu() - b.double().cpu()).abs().max().item()
+
+
+SHAPES = [  # (C, F, H, W, B, layout)
+    (320, 8, 16, 16, 1, "bcfhw"),
+    (320, 16, 8, 8, 2, "bfchw"),
+    (640, 8, 8, 8, 1, "bfchw"),
+    (64, 5, 3, 5, 2, "bcfhw"),        # ragged: odd P, C not a multiple of 64
+    (1280, 16, 2, 2, 1, "bfchw"),
+    (32, 1, 1, 2, 1, "bcfhw"),
+]
+
+
+@pytest.mark.parametrize("C,F,H,W,B,layout", SHAPES)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_groupnorm_stats_and_tokens(C, F, H, W, B, layout, dtype):
+    cfg = mo.MotionConfig(C)
+    params = mo.make_params(cfg, 1)
+    x = mo.make_input((B, C, F, H, W), 2, layout=layout)
+    if dtype == torch.bfloat16:
+        x = helpers.round_bf16(x)
+    st = mo.forward_token_order(params, x, cfg, torch.float64)
+    xd = x.to(DEV, dtype)
+    assert xd.stride() == x.stride()
+    mean, rstd = ops.groupnorm_stats(_cfg(cfg), xd)
+    assert _maxabs(mean, st.gn_mean) <= 2e-6
+    assert (rstd.double().cpu() / st.gn_rstd - 1).abs().max().item() <= 5e-6
+    gw, gb = params["temporal_transformer.norm.weight"].to(DEV), params["temporal_transformer.norm.bias"].to(DEV)
+    tok = ops.groupnorm_tokens(_cfg(cfg), xd, gw, gb)
+    tol = 2e-5 if dtype == torch.float32 else 2 ** -7 * 1.01 * st.tokens.abs().max().item() / 2     # half-ulp of bf16 at the max
+    assert _maxabs(tok, st.tokens) <= tol
+
+
+@pytest.mark.parametrize("C,F,H,W,B", [(320, 8, 8, 8, 1), (640, 16, 4, 4, 1), (1280, 8, 2, 2, 2), (96, 3, 3, 3, 1)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("with_pe", [True, False])
+def test_layernorm_pe(C, F, H, W, B, dtype, with_pe):
+    cfg = mo.MotionConfig(C)
+    g = torch.Generator().manual_seed(5)
+    N = B * F * H * W
+    h = torch.randn(N, C, generator=g) * 1.7 + 0.3
+    w = 1 + 0.1 * torch.randn(C, generator=g)
+    b = 0.1 * torch.randn(C, generator=g)
+    pe = mo.positional_encoding(cfg.max_len, C)
+    ref = torch.nn.functional.layer_norm(h.double(), (C,), w.double(), b.double(), 1e-5)
+    if with_pe:
+        f_of_n = (torch.arange(N) // (H * W)) % F
+        ref = ref + pe.double()[f_of_n]
+    out = ops.layernorm_pe(_cfg(cfg), (B, F, H, W), h.to(DEV), w.to(DEV), b.to(DEV), pe.to(DEV) if with_pe else None, dtype)
+    tol = 1e-5 if dtype == torch.float32 else 2 ** -8 * 1.01 * ref.abs().max().item()
+    assert _maxabs(out, ref) <= tol
+
+
+@pytest.mark.parametrize("C,F,H,W,B", [(320, 8, 8, 8, 1), (320, 16, 4, 5, 2), (640, 24, 2, 2, 1), (1280, 16, 2, 2, 1),
+                                       (32, 1, 1, 2, 1), (64, 32, 2, 2, 1), (1280, 8, 4, 4, 1)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_temporal_attention(C, F, H, W, B, dtype):
+    cfg = mo.MotionConfig(C, max_len=32)
+    nh, dh, P = cfg.heads, cfg.head_dim, H * W
+    N = B * F * P
+    g = torch.Generator().manual_seed(7)
+    qkv = torch.randn(N, 3 * C, generator=g)
+    if dtype == torch.bfloat16:
+        qkv = helpers.round_bf16(qkv)
+    z = qkv.double().reshape(B, F, P, 3, nh, dh)
+    s = torch.einsum("bfphd,bgphd->bphfg", z[:, :, :, 0], z[:, :, :, 1]) * dh ** -0.5
+    ref = torch.einsum("bphfg,bgphd->bfphd", s.softmax(-1), z[:, :, :, 2]).reshape(N, C)
+    ctx = ops.temporal_attention(_cfg(cfg), (B, F, H, W), qkv.to(DEV, dtype))
+    tol = 2e-5 if dtype == torch.float32 else 2 ** -8 * 1.01 * ref.abs().max().item() + 1e-5
+    assert _maxabs(ctx, ref) <= tol
+
+
+GEMM_SHAPES = [  # (M, N, K)
+    (256, 320, 320), (1000, 960, 320), (300, 2560, 320), (130, 320, 1280), (64, 64, 64), (2, 32, 32), (513, 96, 128),
+    (4096, 640, 640), (128, 1280, 5120),
+]
+
+
+def _gemm_inputs(M, N, K, dtype, seed=3):
+    g = torch.Generator().manual_seed(seed)
+    A = torch.randn(M, K, generator=g)
+    W = torch.randn(N, K, generator=g) / K ** 0.5
+    bias = torch.randn(N, generator=g)
+    if dtype == torch.bfloat16:
+        A, W = helpers.round_bf16(A), helpers.round_bf16(W)
+    return A, W, bias
+
+
+def _gemm_tol(dtype, ref, K):
+    # fp32 accumulate of exactly-representable products: only summation-order error; bf16 outputs add one rounding
+    return 5e-5 if dtype == torch.float32 else 2e-4
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_linear_store_and_residual(M, N, K, dtype):
+    A, W, bias = _gemm_inputs(M, N, K, dtype)
+    ref = A.double() @ W.double().T + bias.double()
+    Ad, Wd, bd = A.to(DEV, dtype), W.to(DEV, dtype), bias.to(DEV)
+    # STORE into the fp32 residual stream (exact fp32 accumulate, no output rounding)
+    h = torch.full((M, N), float("nan"), device=DEV)
+    out = ops.linear(Ad, Wd, bd, nlib.EPI_STORE, h=h, want_out=True)
+    assert _maxabs(h, ref) <= _gemm_tol(dtype, ref, K)
+    out_tol = _gemm_tol(dtype, ref, K) if dtype == torch.float32 else 2 ** -8 * 1.01 * ref.abs().max().item()
+    assert _maxabs(out, ref) <= out_tol
+    # no-bias STORE (QKV projection)
+    out2 = ops.linear(Ad, Wd, None, nlib.EPI_STORE)
+    assert _maxabs(out2, ref - bias.double()) <= out_tol
+    # RESIDUAL: h = acc + bias + h, in place
+    g = torch.Generator().manual_seed(11)
+    h0 = torch.randn(M, N, generator=g)
+    h = h0.to(DEV).clone()
+    out3 = ops.linear(Ad, Wd, bd, nlib.EPI_RESIDUAL, h=h, want_out=True)
+    assert _maxabs(h, ref + h0.double()) <= _gemm_tol(dtype, ref, K)
+    assert _maxabs(out3, ref + h0.double()) <= (out_tol if dtype == torch.float32 else 2 ** -8 * 1.01 * (ref + h0.double()).abs().max().item())
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 2560, 320), (130, 512, 64), (2, 256, 32), (1024, 5120, 640)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_linear_geglu(M, N, K, dtype):
+    # library contract: W rows pre-interleaved (row 2j = value j, row 2j+1 = gate j); emulate the packing here
+    A, W, bias = _gemm_inputs(M, N, K, dtype)
+    half = N // 2
+    u = A.double() @ W.double().T + bias.double()
+    ref = u[:, :half] * torch.nn.functional.gelu(u[:, half:])       # value * gelu(gate), motion_module_new.py:516-518
+    Wi = torch.empty_like(W); Wi[0::2] = W[:half]; Wi[1::2] = W[half:]
+    bi = torch.empty_like(bias); bi[0::2] = bias[:half]; bi[1::2] = bias[half:]
+    out = ops.linear(A.to(DEV, dtype), Wi.to(DEV, dtype), bi.to(DEV), nlib.EPI_GEGLU)
+    assert out.shape == (M, half)
+    tol = 5e-5 if dtype == torch.float32 else 2 ** -8 * 1.01 * ref.abs().max().item() + 2e-4
+    assert _maxabs(out, ref) <= tol
+
+
+@pytest.mark.parametrize("C,F,H,W,B,layout", [(320, 8, 8, 8, 1, "bcfhw"), (64, 5, 3, 5, 2, "bfchw"), (640, 16, 4, 4, 1, "bfchw")])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_linear_output_epilogue(C, F, H, W, B, layout, dtype):
+    cfg = mo.MotionConfig(C)
+    N = B * F * H * W
+    A, Wt, bias = _gemm_inputs(N, C, C, dtype)
+    x = mo.make_input((B, C, F, H, W), 4, layout=layout)
+    if dtype == torch.bfloat16:
+        x = helpers.round_bf16(x)
+    y_tok = A.double() @ Wt.double().T + bias.double()                                   # [N, C], n = (b f) p
+    ref = y_tok.reshape(B, F, H * W, C).permute(0, 3, 1, 2).reshape(B, C, F, H, W) + x.double()
+    y = ops.linear(A.to(DEV, dtype), Wt.to(DEV, dtype), bias.to(DEV), nlib.EPI_OUTPUT, cfg=_cfg(cfg), x=x.to(DEV, dtype))
+    assert y.shape == x.shape and y.permute(0, 2, 1, 3, 4).is_contiguous()                # [B,F,C,H,W] storage like the reference
+    tol = 5e-5 if dtype == torch.float32 else 2 ** -8 * 1.01 * ref.abs().max().item()
+    assert _maxabs(y, ref) <= tol
+
+
+# ---- whole module ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", helpers.golden_names())
+def test_module_golden_fp32(name):
+    fx, cfg, params, x = helpers.load_golden(name)
+    m = helpers.mirror_module(cfg, params, DEV)
+    with torch.no_grad():
+        y = m(x.to(DEV), None, None)
+    assert y.shape == x.shape and y.dtype == torch.float32
+    assert y.stride() == fx["out_ref_fp32"].permute(0, 2, 1, 3, 4).contiguous().permute(0, 2, 1, 3, 4).stride()
+    assert _maxabs(y, fx["out_ref_fp32"]) <= helpers.TOL_FP32
+
+
+@pytest.mark.parametrize("name", helpers.golden_names())
+def test_module_golden_bf16(name):
+    fx, cfg, params, x = helpers.load_golden(name)
+    m = helpers.mirror_module(cfg, params, DEV, torch.bfloat16)        # weights rounded to bf16 == fixture's rounding
+    with torch.no_grad():
+        y = m(x.to(DEV, torch.bfloat16), None, None)
+    assert y.dtype == torch.bfloat16
+    assert _maxabs(y, fx["out_ref_bf16in"]) <= helpers.TOL_BF16
+
+
+def test_module_bf16_from_fp32_weights_matches_bf16_weights():
+    # packing converts fp32 parameters to bf16 with the same round-to-nearest as module.bfloat16()
+    fx, cfg, params, x = helpers.load_golden("c320_f8_8x8_a2")
+    xb = x.to(DEV, torch.bfloat16)
+    with torch.no_grad():
+        y1 = helpers.mirror_module(cfg, params, DEV, torch.bfloat16)(xb, None, None)
+        packed = ops.pack_params(_cfg(cfg), {k: v.to(DEV) for k, v in params.items()}, torch.bfloat16, torch.device(DEV))
+        y2 = ops.forward_packed(xb, packed, _cfg(cfg))
+    # pe table: module.bfloat16() rounds the buffer, the fp32 source does not -> results may differ by
+    # one bf16 ulp of the output where the pre-rounding values straddle a rounding boundary
+    assert _maxabs(y1, y2) <= 2 ** -7 * 1.01 * y1.float().abs().max().item()
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, helpers.TOL_FP32), (torch.bfloat16, helpers.TOL_BF16)])
+def test_module_config1_full_size_vs_oracle(dtype, tol):
+    """BASELINE config 1: 320 ch, 8 frames, 64x64 latent, batch 1 -- CUDA vs the oracle run live on the host CPU."""
+    cfg = mo.MotionConfig(320)
+    params = mo.make_params(cfg, 0)
+    x = mo.make_input((1, 320, 8, 64, 64), 0)
+    if dtype == torch.bfloat16:
+        params = {k: helpers.round_bf16(v) for k, v in params.items()}
+        x = helpers.round_bf16(x)
+    with torch.no_grad():
+        ref = mo.forward_reference_order(params, x, cfg)
+        y = helpers.mirror_module(cfg, params, DEV, dtype)(x.to(DEV, dtype), None, None)
+    assert _maxabs(y, ref) <= tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_module_properties_full_size(dtype):
+    """Size-independent properties at a NEURONS-sized call (B=2, 16 frames, 32x32 latent)."""
+    cfg = mo.MotionConfig(320)
+    params = mo.make_params(cfg, 4)
+    x = mo.make_input((2, 320, 16, 32, 32), 6, layout="bfchw").to(DEV, dtype)
+    m = helpers.mirror_module(cfg, params, DEV, dtype)
+    with torch.no_grad():
+        y1 = m(x, None, None)
+        y2 = m(x, None, None)
+        assert torch.equal(y1, y2)                                             # deterministic (no atomics anywhere)
+        yc = m(x.contiguous(), None, None)                                     # layout of x does not change the result
+        assert torch.equal(y1, yc)
+        # frames are coupled only through attention; batch entries are independent
+        y_b0 = m(x[:1], None, None)
+        assert torch.equal(y_b0, y1[:1])
+        # zero-initialised proj_out (the construction default, motion_module.py:74-75) makes the module the identity
+        nb.zero_module(m.temporal_transformer.proj_out)
+        nb.invalidate(m)
+        assert torch.equal(m(x, None, None), x)
+
+
+def test_lora_style_inplace_update_needs_invalidate():
+    fx, cfg, params, x = helpers.load_golden("c64_f16_4x4_a1_view")
+    m = helpers.mirror_module(cfg, params, DEV)
+    xd = x.to(DEV)
+    with torch.no_grad():
+        y0 = m(xd, None, None)
+        m.temporal_transformer.proj_out.weight.data += 0.05       # in place, like convert_lora_safetensor_to_diffusers.py:45
+        assert torch.equal(m(xd, None, None), y0)                  # cached pack (documented behaviour)
+        nb.invalidate(m)
+        y1 = m(xd, None, None)
+    assert not torch.equal(y1, y0)
+    p2 = dict(params); p2["temporal_transformer.proj_out.weight"] = params["temporal_transformer.proj_out.weight"] + 0.05
+    assert _maxabs(y1, mo.forward_reference_order(p2, x, cfg)) <= helpers.TOL_FP32
+
+
+def test_unsupported_inputs_raise():
+    cfg = mo.MotionConfig(64)
+    m = helpers.mirror_module(cfg, mo.make_params(cfg, 1), DEV)
+    with torch.no_grad():
+        with pytest.raises(nlib.NmmError):
+            m(torch.zeros(1, 64, 25, 2, 2, device=DEV), None, None)            # frames > max_len
+        with pytest.raises(TypeError):
+            m(torch.zeros(1, 64, 4, 2, 2, device=DEV, dtype=torch.float16), None, None)
+    with pytest.raises(RuntimeError, match="inference-only"):
+        m(torch.zeros(1, 64, 4, 2, 2, device=DEV), None, None)                 # grad mode with trainable params
+
+
+def test_launch_counter_and_graph_capture():
+    cfg = mo.MotionConfig(320)
+    m = helpers.mirror_module(cfg, mo.make_params(cfg, 1), DEV, torch.bfloat16)
+    x = mo.make_input((1, 320, 8, 16, 16), 1).to(DEV, torch.bfloat16)
+    with torch.no_grad():
+        y_eager = m(x, None, None)
+        n0 = nb.launch_count()
+        m(x, None, None)
+        per_call = nb.launch_count() - n0
+        assert per_call == 2 + 1 + 2 * 4 + 3 + 1              # gn(2) proj_in, 2x(ln qkv attn out), ln geglu ff_out, proj_out
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            m(x, None, None)                                  # warm-up on the side stream
+            s.synchronize()
+            with torch.cuda.graph(g, stream=s):
+                y_graph = m(x, None, None)
+        torch.cuda.current_stream().wait_stream(s)
+        g.replay()
+        torch.cuda.synchronize()
+    assert torch.equal(y_graph, y_eager)
