@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py -- motion-module throughput of one UNet denoising step (BASELINE.json config 2) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" = the 20 motion-module calls of one UNet3DConditionModel.forward at SD1.5 512x512 (64x64 latent), 8 frames,
+CFG batch 2, bf16 -- 20 distinct modules (417 M parameters), 20 distinct [2,C,8,L,L] activations in the
+[B,F,C,H,W]-storage layout the UNet hands over.  Per step the inputs + weights touched (1.2 GB) exceed the 126 MB L2.
+    value   motion-module TFLOP/s, algorithmic FLOPs / device time, inputs resident in HBM
+    e2e     same metric through the public module call with HOST buffers: pinned H2D of every input and D2H of every
+            output inside the timed region (copies pipelined against compute on separate streams)
+    roofline  the dominant kernel (tcgen05 bf16 GEMM): algorithmic FLOPs of its launches / their summed device time,
+            measured with CUDA events the library records around each launch on the launch stream
+    cpu_baseline  the oracle port of the reference module (oracle/motion_oracle.py) timed on the host cores
+Each rank runs a full replica (weak scaling, no collective on the path); time = max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LATENT, FRAMES, BATCH = 64, 8, 2
+METRIC, UNIT = "motion-module fwd TFLOP/s", "TFLOP/s"
+
+
+def workload_config(n_gpus):
+    return {"workload": "UNet3DConditionModel one denoising step, all 20 motion modules, SD1.5 512x512 (64x64 latent), 8 frames, CFG batch 2",
+            "baseline_config": "configs[1]", "latent": LATENT, "frames": FRAMES, "batch": BATCH, "calls_per_step": 20,
+            "layout": "[B,F,C,H,W]-storage views (UNet call sites)", "parallelism": f"dp{n_gpus} replicas, no collective on the path",
+            "l2": "inputs larger than L2: 20 distinct activations + 20 modules' weights = 1.2 GB per step vs 126 MB L2"}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md)."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 8 and parts[0].isdigit() and int(parts[0]) == self.gpu_index:
+                self.rows.append(parts)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[4:8]) if v.lower().startswith("active")})
+        pw = [float(r[3]) for r in self.rows if r[3].replace(".", "").isdigit()]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows), "power_w_max": max(pw) if pw else None}
+
+
+def physical_gpu_index(local_rank: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        ids = [v for v in vis.split(",") if v.strip() != ""]
+        if local_rank < len(ids) and ids[local_rank].strip().isdigit():
+            return int(ids[local_rank])
+    return local_rank
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"bf16_tflops": p.get("bf16_tflops"), "bf16_tflops_sustained": p.get("bf16_tflops_sustained"),
+                "hbm_gbs": p.get("hbm_gbs"), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_reference_time(sample: str, threads: int):
+    """Time the oracle port of the reference module (fp32, torch CPU, all host threads) on a bounded sample.
+    Returns (tflops, seconds, description).  This is the ONE place bench.py executes oracle/ (as the baseline)."""
+    from neurons_b200 import workloads as wl
+    from oracle import motion_oracle as mo
+    torch.set_num_threads(threads)
+    calls = wl.unet_step_calls(LATENT)
+    if sample == "step":
+        chosen, desc = calls, "one full step: all 20 calls"
+    elif sample == "shapes":
+        seen, chosen = set(), []
+        for c in calls:
+            if (c.channels, c.side) not in seen:
+                seen.add((c.channels, c.side)); chosen.append(c)
+        desc = "one call per distinct (channels, latent) of the step: (320,64) (640,32) (1280,16) (1280,8), batch 2, 8 frames"
+    else:
+        chosen, desc = [calls[0]], "one (320 ch, 64x64) call of the step, batch 2, 8 frames"
+    params = {}
+    for c in chosen:
+        if c.channels not in params:
+            cfg = mo.MotionConfig(c.channels, 8, 1, c.attn_blocks, True, c.max_len)
+            g = torch.Generator().manual_seed(c.channels)
+            params[c.channels] = (cfg, {k: (torch.rand(s, generator=g) * 2 - 1) / (s[-1] ** 0.5 if len(s) == 2 else 1.0)
+                                        for k, s in mo.param_shapes(cfg).items()})
+    xs = {}
+    for c in chosen:
+        key = (c.channels, c.side)
+        if key not in xs:
+            xs[key] = mo.make_input((BATCH, c.channels, FRAMES, c.side, c.side), 1, layout="bfchw")
+    flops = wl.step_flops(chosen, BATCH, FRAMES)
+
+    def run():
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            for c in chosen:
+                cfg, p = params[c.channels]
+                mo.forward_reference_order(p, xs[(c.channels, c.side)], cfg)
+        return time.perf_counter() - t0
+    return flops, run, desc
+
+
+def run_reference_arm(args, rank):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port; the reference is pure Python
+    and ships no installable package), all host threads, same metric/config.  Rank 0 only."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    # size the per-step sample so that (steps + warmup) steps end within ~150 s
+    flops1, run1, _ = cpu_reference_time("one", threads)
+    t_probe = min(run1(), run1())
+    rate = flops1 / t_probe
+    from neurons_b200 import workloads as wl
+    calls = wl.unet_step_calls(LATENT)
+    total_steps = args.steps + args.warmup
+    est_step = wl.step_flops(calls, BATCH, FRAMES) / rate
+    est_shapes = est_step / 5.0
+    sample = "step" if est_step * total_steps <= 150 else ("shapes" if est_shapes * total_steps <= 150 else "one")
+    flops, run, desc = cpu_reference_time(sample, threads)
+    for _ in range(args.warmup):
+        run()
+    times = [run() for _ in range(args.steps)]
+    ms = 1e3 * sum(times) / len(times)
+    val = flops / (ms * 1e-3) / 1e12
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the host-CPU baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    import torch.distributed as dist
+    import neurons_b200 as nb
+    from neurons_b200 import lib as nlib
+    from neurons_b200 import workloads as wl
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the motion-module path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    calls = wl.unet_step_calls(LATENT)
+    flops_step = wl.step_flops(calls, BATCH, FRAMES)
+    kwargs = dict(num_attention_heads=8, num_transformer_block=1, attention_block_types=("Temporal_Self", "Temporal_Self"),
+                  temporal_position_encoding=True, temporal_position_encoding_max_len=24, temporal_attention_dim_div=1,
+                  zero_initialize=False)      # random-init weights of the v3 architecture; proj_out NOT zeroed (else identity)
+    torch.manual_seed(1234 + rank)
+    modules, xs_dev, xs_host, ys_host = [], [], [], []
+    with torch.no_grad():
+        for c in calls:
+            with torch.device(dev):
+                m = nb.get_motion_module(c.channels, "Vanilla", kwargs)
+            modules.append(m.to(torch.bfloat16).eval())
+            x = torch.randn(BATCH, FRAMES, c.channels, c.side, c.side, device=dev, dtype=torch.bfloat16).permute(0, 2, 1, 3, 4)
+            xs_dev.append(x)
+            xs_host.append(torch.empty((BATCH, FRAMES, c.channels, c.side, c.side), dtype=torch.bfloat16).pin_memory())
+            xs_host[-1].copy_(x.permute(0, 2, 1, 3, 4))
+            ys_host.append(torch.empty((BATCH, FRAMES, c.channels, c.side, c.side), dtype=torch.bfloat16).pin_memory())
+    h2d_bytes = sum(t.numel() * 2 for t in xs_host)
+    d2h_bytes = sum(t.numel() * 2 for t in ys_host)
+
+    def step_resident():
+        for m, x in zip(modules, xs_dev):
+            m(x, None, None)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        # ---------------- device-resident arm ("value") ----------------
+        for _ in range(args.warmup):
+            step_resident()
+        barrier()
+        sampler = ClockSampler(physical_gpu_index(local_rank))
+        sampler.start()
+        launches0 = nb.launch_count()
+        nlib.profile_begin()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(args.steps):
+            step_resident()
+        ev1.record()
+        barrier()
+        ms_total = ev0.elapsed_time(ev1)
+        prof = nlib.profile_end()
+        launches = nb.launch_count() - launches0
+        clocks = sampler.stop()
+
+        # ---------------- end-to-end arm: host buffers, copies inside the timed region ----------------
+        s_in, s_out, s_c = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.current_stream()
+        x_stage = [torch.empty_like(x.permute(0, 2, 1, 3, 4).contiguous()) for x in xs_dev]     # [B,F,C,H,W] device staging
+        ev_in = [torch.cuda.Event() for _ in calls]
+        ev_c = [torch.cuda.Event() for _ in calls]
+
+        def step_e2e():
+            for i, m in enumerate(modules):
+                with torch.cuda.stream(s_in):
+                    s_in.wait_event(ev_c[i])                       # previous step's compute on this staging buffer is done
+                    x_stage[i].copy_(xs_host[i], non_blocking=True)
+                    ev_in[i].record(s_in)
+                s_c.wait_event(ev_in[i])
+                y = m(x_stage[i].permute(0, 2, 1, 3, 4), None, None)
+                ev_c[i].record(s_c)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_c[i])
+                    ys_host[i].copy_(y.permute(0, 2, 1, 3, 4), non_blocking=True)
+                    y.record_stream(s_out)
+
+        for _ in range(2):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_e2e()
+        torch.cuda.synchronize()
+        e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
+
+    # max over ranks
+    t = torch.tensor([ms_total, e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = float(t[0]), float(t[1])
+    ms_step = ms_total / args.steps
+    value = world * flops_step / (ms_step * 1e-3) / 1e12
+    e2e_value = world * flops_step / (e2e_ms * 1e-3) / 1e12
+
+    if rank == 0:
+        peaks = measured_peaks()
+        gemm = prof["linear_bf16_tcgen05"]
+        # the GEMM is timed inside a long (multi-second) step -> sustained cuBLAS figure is the denominator
+        peak_tf = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
+        ach = gemm["flops"] / (gemm["total_ms"] * 1e-3) / 1e12 if gemm["total_ms"] > 0 else 0.0
+        roofline = {"kernel": "linear_tc_kernel (tcgen05 bf16 GEMM + fused epilogue)", "bound": "tensor", "achieved": ach,
+                    "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None, "traffic": None,
+                    "peak_source": peaks["source"] + ", bf16_tflops_sustained", "launches": gemm["launches"],
+                    "share_of_step": gemm["total_ms"] / ms_total if ms_total else None,
+                    "other_kernels": {k: {"launches": v["launches"], "ms_per_step": v["total_ms"] / args.steps,
+                                          "GBps": (v["bytes"] / (v["total_ms"] * 1e-3) / 1e9) if v["total_ms"] > 0 else None,
+                                          "frac_of_hbm_peak": (v["bytes"] / (v["total_ms"] * 1e-3) / 1e9 / peaks["hbm_gbs"]) if v["total_ms"] > 0 and peaks["hbm_gbs"] else None}
+                                      for k, v in prof.items() if v["launches"] and k != "linear_bf16_tcgen05"}}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            flops, run, desc = cpu_reference_time("step", threads)
+            secs = run()
+            cpu = {"value": flops / secs / 1e12, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc + f" ({secs:.1f} s)"}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic", "config": workload_config(world), "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+                "flops_per_step": flops_step}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

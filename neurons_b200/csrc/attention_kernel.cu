@@ -41,16 +41,20 @@ template <typename T> struct RowVec<T, 1> {
     static __device__ __forceinline__ void store(T *p, const float (&f)[1]) { *p = from_f32<T>(f[0]); }
 };
 
-// smem layout: [PB positions][F frames][3C + PAD] elements of T; PAD keeps consecutive frame rows on
-// different banks (row pitch in bytes = 3C*s + 16).
+// A CTA handles PB positions x HB heads (blockIdx.y selects the head group; HB == heads for the UNet's 320/640-channel
+// levels, fewer for 1280 channels so the tile fits shared memory).
+// smem layout: [PB positions][F frames][q(HB*dh) | k(HB*dh) | v(HB*dh) | PAD] elements of T; PAD keeps consecutive frame
+// rows on different banks (row pitch in bytes = 3*HB*dh*s + 16).
 template <typename T, int VEC, int FMAX>
 __global__ void __launch_bounds__(256) temporal_attention_kernel(const T *__restrict__ qkv, T *__restrict__ ctx, int B, int F,
-                                                                 int P, int C, int heads, int PB, float scale) {
+                                                                 int P, int C, int heads, int PB, int HB, float scale) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *sm = reinterpret_cast<T *>(smem_raw);
     constexpr int PAD = 16 / (int)sizeof(T);
     const int dh = C / heads;
-    const int pitch = 3 * C + PAD;
+    const int W = HB * dh;                      // channels of this head group
+    const int c_off = blockIdx.y * W;           // first channel of the head group
+    const int pitch = 3 * W + PAD;
     const int tiles_per_img = (P + PB - 1) / PB;
     const int b = blockIdx.x / tiles_per_img;
     const int p0 = (blockIdx.x % tiles_per_img) * PB;
@@ -62,36 +66,38 @@ __global__ void __launch_bounds__(256) temporal_attention_kernel(const T *__rest
         constexpr int LV = 16 / (int)sizeof(T);                     // elements per 16-byte load
         const bool vec = (VEC > 1);                                 // host guarantees 16B alignment when VEC > 1
         if (vec) {
-            const int vec_per_row = 3 * C / LV;
+            const int vec_per_seg = W / LV, vec_per_row = 3 * vec_per_seg;
             const int total = F * npos * vec_per_row;
             for (int i = tid; i < total; i += nthr) {
                 int v = i % vec_per_row; int r = i / vec_per_row;   // r = f*npos + pl
                 int pl = r % npos, f = r / npos;
-                const T *src = qkv + ((int64_t)(b * F + f) * P + p0 + pl) * (3 * C) + v * LV;
+                int seg = v / vec_per_seg, within = v - seg * vec_per_seg;     // seg: 0 = q, 1 = k, 2 = v
+                const T *src = qkv + ((int64_t)(b * F + f) * P + p0 + pl) * (3 * C) + seg * C + c_off + within * LV;
                 uint4 val = __ldg(reinterpret_cast<const uint4 *>(src));
                 *reinterpret_cast<uint4 *>(sm + (pl * F + f) * pitch + v * LV) = val;
             }
         } else {
-            const int total = F * npos * 3 * C;
+            const int total = F * npos * 3 * W;
             for (int i = tid; i < total; i += nthr) {
-                int e = i % (3 * C); int r = i / (3 * C);
+                int e = i % (3 * W); int r = i / (3 * W);
                 int pl = r % npos, f = r / npos;
-                sm[(pl * F + f) * pitch + e] = qkv[((int64_t)(b * F + f) * P + p0 + pl) * (3 * C) + e];
+                int seg = e / W, within = e - seg * W;
+                sm[(pl * F + f) * pitch + e] = qkv[((int64_t)(b * F + f) * P + p0 + pl) * (3 * C) + seg * C + c_off + within];
             }
         }
     }
     __syncthreads();
 
     // ---- one thread per (pl, head, f) ---------------------------------------------------------------
-    const int per_pos = heads * F;
+    const int per_pos = HB * F;
     const int pl = tid / per_pos;
     const int hf = tid % per_pos;
     const int head = hf / F, f = hf % F;
     const bool active = pl < npos;             // tid < PB*heads*F by launch configuration
     if (active) {
         T *qrow = sm + (pl * F + f) * pitch + head * dh;             // this thread's query row (reused for output)
-        const T *kbase = sm + (pl * F) * pitch + C + head * dh;
-        const T *vbase = sm + (pl * F) * pitch + 2 * C + head * dh;
+        const T *kbase = sm + (pl * F) * pitch + W + head * dh;
+        const T *vbase = sm + (pl * F) * pitch + 2 * W + head * dh;
         float sc[FMAX];
 #pragma unroll
         for (int j = 0; j < FMAX; j++) sc[j] = 0.f;
@@ -136,24 +142,24 @@ __global__ void __launch_bounds__(256) temporal_attention_kernel(const T *__rest
     }
     __syncthreads();
 
-    // ---- write ctx rows (the first C elements of each staged row) -----------------------------------
+    // ---- write ctx rows (the first W elements of each staged row) -----------------------------------
     {
         constexpr int LV = 16 / (int)sizeof(T);
         if (VEC > 1) {
-            const int vec_per_row = C / LV;
+            const int vec_per_row = W / LV;
             const int total = F * npos * vec_per_row;
             for (int i = tid; i < total; i += nthr) {
                 int v = i % vec_per_row; int r = i / vec_per_row;
                 int pl2 = r % npos, f2 = r / npos;
                 uint4 val = *reinterpret_cast<const uint4 *>(sm + (pl2 * F + f2) * pitch + v * LV);
-                *reinterpret_cast<uint4 *>(ctx + ((int64_t)(b * F + f2) * P + p0 + pl2) * C + v * LV) = val;
+                *reinterpret_cast<uint4 *>(ctx + ((int64_t)(b * F + f2) * P + p0 + pl2) * C + c_off + v * LV) = val;
             }
         } else {
-            const int total = F * npos * C;
+            const int total = F * npos * W;
             for (int i = tid; i < total; i += nthr) {
-                int e = i % C; int r = i / C;
+                int e = i % W; int r = i / W;
                 int pl2 = r % npos, f2 = r / npos;
-                ctx[((int64_t)(b * F + f2) * P + p0 + pl2) * C + e] = sm[(pl2 * F + f2) * pitch + e];
+                ctx[((int64_t)(b * F + f2) * P + p0 + pl2) * C + c_off + e] = sm[(pl2 * F + f2) * pitch + e];
             }
         }
     }
@@ -161,18 +167,28 @@ __global__ void __launch_bounds__(256) temporal_attention_kernel(const T *__rest
 
 template <typename T, int VEC>
 static int launch_attn_t(const Geo &g, const T *qkv, T *ctx, cudaStream_t st) {
-    const int per_pos = g.heads * g.F;
-    if (per_pos > 256) return fail(NMM_ERR_UNSUPPORTED, "heads*frames = %d > 256", per_pos);
-    const size_t row_bytes = (size_t)(3 * g.C) * sizeof(T) + 16;
-    const size_t smem_cap = 200 * 1024;
-    int PB = 256 / per_pos;
-    while (PB > 1 && (size_t)PB * g.F * row_bytes > 96 * 1024) PB--;       // keep >= 2 CTAs/SM when possible
-    if (PB > g.P) PB = g.P;
-    const size_t smem = (size_t)PB * g.F * row_bytes;
-    if (smem > smem_cap) return fail(NMM_ERR_UNSUPPORTED, "attention tile needs %zu B shared memory", smem);
+    if (g.heads * g.F > 256 && g.F > 256) return fail(NMM_ERR_UNSUPPORTED, "frames too large");
+    const size_t smem_cap = 200 * 1024, smem_pref = 96 * 1024;       // <= 96 KB keeps two CTAs resident per SM
+    auto row_bytes = [&](int hb) { return (size_t)(3 * hb * g.dh) * sizeof(T) + 16; };
+    // heads per CTA: the largest divisor of `heads` whose tile fits the preferred budget, else the largest that fits at all
+    int HB = 0, PB = 1;
+    for (int pass = 0; pass < 2 && HB == 0; pass++) {
+        const size_t budget = pass == 0 ? smem_pref : smem_cap;
+        for (int hb = g.heads; hb >= 1; hb--) {
+            if (g.heads % hb || hb * g.F > 256) continue;
+            int pb = 256 / (hb * g.F);
+            if (pb > g.P) pb = g.P;
+            while (pb > 1 && (size_t)pb * g.F * row_bytes(hb) > budget) pb--;
+            if ((size_t)pb * g.F * row_bytes(hb) <= budget) { HB = hb; PB = pb; break; }
+        }
+    }
+    if (HB == 0) return fail(NMM_ERR_UNSUPPORTED, "attention tile does not fit shared memory (C=%d, F=%d)", g.C, g.F);
+    const int per_pos = HB * g.F;
+    const size_t smem = (size_t)PB * g.F * row_bytes(HB);
     const int threads = ((PB * per_pos + 31) / 32) * 32;
     const int64_t blocks = (int64_t)g.B * ceil_div(g.P, PB);
     if (blocks > 0x7fffffff) return fail(NMM_ERR_UNSUPPORTED, "attention grid too large");
+    const dim3 grid((unsigned)blocks, (unsigned)(g.heads / HB));
     const float scale = 1.0f / sqrtf((float)g.dh);
 #define ATTN_CASE(FM)                                                                                                    \
     do {                                                                                                                 \
@@ -183,7 +199,7 @@ static int launch_attn_t(const Geo &g, const T *qkv, T *ctx, cudaStream_t st) {
             attr_set = true;                                                                                             \
         }                                                                                                                \
         ProfScope prof(K_ATTENTION, st, 4.0 * g.N * g.F * g.C, 4.0 * g.N * g.C * sizeof(T));                             \
-        kern<<<(unsigned)blocks, threads, smem, st>>>(qkv, ctx, g.B, g.F, g.P, g.C, g.heads, PB, scale);                  \
+        kern<<<grid, threads, smem, st>>>(qkv, ctx, g.B, g.F, g.P, g.C, g.heads, PB, HB, scale);                          \
     } while (0)
     if (g.F <= 8) ATTN_CASE(8);
     else if (g.F <= 16) ATTN_CASE(16);

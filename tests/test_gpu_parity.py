@@ -44,7 +44,7 @@ SHAPES = [  # (C, F, H, W, B, layout)
 
 
 @pytest.mark.parametrize("C,F,H,W,B,layout", SHAPES)
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
 def test_groupnorm_stats_and_tokens(C, F, H, W, B, layout, dtype):
     cfg = mo.MotionConfig(C)
     params = mo.make_params(cfg, 1)
@@ -64,7 +64,7 @@ def test_groupnorm_stats_and_tokens(C, F, H, W, B, layout, dtype):
 
 
 @pytest.mark.parametrize("C,F,H,W,B", [(320, 8, 8, 8, 1), (640, 16, 4, 4, 1), (1280, 8, 2, 2, 2), (96, 3, 3, 3, 1)])
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
 @pytest.mark.parametrize("with_pe", [True, False])
 def test_layernorm_pe(C, F, H, W, B, dtype, with_pe):
     cfg = mo.MotionConfig(C)
@@ -85,7 +85,7 @@ def test_layernorm_pe(C, F, H, W, B, dtype, with_pe):
 
 @pytest.mark.parametrize("C,F,H,W,B", [(320, 8, 8, 8, 1), (320, 16, 4, 5, 2), (640, 24, 2, 2, 1), (1280, 16, 2, 2, 1),
                                        (32, 1, 1, 2, 1), (64, 32, 2, 2, 1), (1280, 8, 4, 4, 1)])
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
 def test_temporal_attention(C, F, H, W, B, dtype):
     cfg = mo.MotionConfig(C, max_len=32)
     nh, dh, P = cfg.heads, cfg.head_dim, H * W
@@ -124,7 +124,7 @@ def _gemm_tol(dtype, ref, K):
 
 
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
 def test_linear_store_and_residual(M, N, K, dtype):
     A, W, bias = _gemm_inputs(M, N, K, dtype)
     ref = A.double() @ W.double().T + bias.double()
@@ -148,7 +148,7 @@ def test_linear_store_and_residual(M, N, K, dtype):
 
 
 @pytest.mark.parametrize("M,N,K", [(256, 2560, 320), (130, 512, 64), (2, 256, 32), (1024, 5120, 640)])
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
 def test_linear_geglu(M, N, K, dtype):
     # library contract: W rows pre-interleaved (row 2j = value j, row 2j+1 = gate j); emulate the packing here
     A, W, bias = _gemm_inputs(M, N, K, dtype)
@@ -164,7 +164,7 @@ def test_linear_geglu(M, N, K, dtype):
 
 
 @pytest.mark.parametrize("C,F,H,W,B,layout", [(320, 8, 8, 8, 1, "bcfhw"), (64, 5, 3, 5, 2, "bfchw"), (640, 16, 4, 4, 1, "bfchw")])
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
 def test_linear_output_epilogue(C, F, H, W, B, layout, dtype):
     cfg = mo.MotionConfig(C)
     N = B * F * H * W
@@ -215,7 +215,7 @@ def test_module_bf16_from_fp32_weights_matches_bf16_weights():
     assert _maxabs(y1, y2) <= 2 ** -7 * 1.01 * y1.float().abs().max().item()
 
 
-@pytest.mark.parametrize("dtype,tol", [(torch.float32, helpers.TOL_FP32), (torch.bfloat16, helpers.TOL_BF16)])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, helpers.TOL_FP32), (torch.bfloat16, helpers.TOL_BF16)], ids=["fp32", "bf16"])
 def test_module_config1_full_size_vs_oracle(dtype, tol):
     """BASELINE config 1: 320 ch, 8 frames, 64x64 latent, batch 1 -- CUDA vs the oracle run live on the host CPU."""
     cfg = mo.MotionConfig(320)
@@ -230,7 +230,7 @@ def test_module_config1_full_size_vs_oracle(dtype, tol):
     assert _maxabs(y, ref) <= tol
 
 
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
 def test_module_properties_full_size(dtype):
     """Size-independent properties at a NEURONS-sized call (B=2, 16 frames, 32x32 latent)."""
     cfg = mo.MotionConfig(320)
