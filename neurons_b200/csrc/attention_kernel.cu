@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(256) temporal_attention_kernel(const T *__rest
 template <typename T, int VEC>
 static int launch_attn_t(const Geo &g, const T *qkv, T *ctx, cudaStream_t st) {
     if (g.heads * g.F > 256 && g.F > 256) return fail(NMM_ERR_UNSUPPORTED, "frames too large");
-    const size_t smem_cap = 200 * 1024, smem_pref = 96 * 1024;       // <= 96 KB keeps two CTAs resident per SM
+    const size_t smem_cap = 200 * 1024, smem_pref = 32 * 1024;       // <= 32 KB: ~7 CTAs per SM, so load / compute / store phases of different CTAs overlap
     auto row_bytes = [&](int hb) { return (size_t)(3 * hb * g.dh) * sizeof(T) + 16; };
     // heads per CTA: the largest divisor of `heads` whose tile fits the preferred budget, else the largest that fits at all
     int HB = 0, PB = 1;

@@ -19,12 +19,17 @@ struct EpiParams {
     void *y;
     int F, P;
     int64_t xsb, xsc, xsf, ysb, ysc, ysf;
+    int nchw_vec;      // OUTPUT: P % 32 == 0 and x / y rows 16-byte aligned -> 8-position (16-byte) vector path
 };
 
 inline EpiParams epi_params_of(const LinearArgs &a) {
     EpiParams e;
     e.M = a.M; e.N = a.N; e.bias = a.bias; e.h = a.h; e.out = a.out; e.x = a.x; e.y = a.y; e.F = a.F; e.P = a.P;
     e.xsb = a.xsb; e.xsc = a.xsc; e.xsf = a.xsf; e.ysb = a.ysb; e.ysc = a.ysc; e.ysf = a.ysf;
+    e.nchw_vec = 0;
+    if (a.epilogue == NMM_EPI_OUTPUT && a.P > 0 && a.P % 32 == 0 && aligned(a.x, 16) && aligned(a.y, 16) && a.xsb % 8 == 0 &&
+        a.xsc % 8 == 0 && a.xsf % 8 == 0 && a.ysb % 8 == 0 && a.ysc % 8 == 0 && a.ysf % 8 == 0)
+        e.nchw_vec = 1;
     return e;
 }
 

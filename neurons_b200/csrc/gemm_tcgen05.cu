@@ -8,7 +8,8 @@
 //   warp 1      MMA issuer: one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=block_n, K=16)
 //               4x per stage, tcgen05.commit releases the stage / publishes the accumulator.
 //   warp 2      TMEM allocator (2 accumulator buffers of block_n fp32 columns -> epilogue overlaps the next tile).
-//   warps 4-7   epilogue: tcgen05.ld (lane == output row), bias / residual / GEGLU / NCHW-store, direct global stores.
+//   warps 4-11  epilogue: tcgen05.ld (lane == output row) -> warp-private shared-memory transpose -> bias / residual / GEGLU
+//               with fully coalesced 16-byte global accesses; the NCHW store of proj_out is coalesced along p as is.
 // Both operands are K-major in global memory ([rows, K] row-major), which is exactly how activations
 // (token-major) and nn.Linear weights ([out, in]) are laid out, so no transposes are ever materialised.
 #include <cuda.h>
@@ -21,9 +22,13 @@
 
 namespace nmm {
 
-constexpr int TC_BM = 128, TC_BK = 64, TC_THREADS = 256;
+constexpr int TC_BM = 128, TC_BK = 64;
+constexpr int TC_EPI_WARPS = 8;                           // two warps per TMEM lane quadrant, alternating column chunks
+constexpr int TC_THREADS = 128 + 32 * TC_EPI_WARPS;       // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4-11: epilogue
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;            // 16 KB per stage
 constexpr int TC_SMEM_BUDGET = 220 * 1024;
+constexpr int TC_STAGE_PITCH = 36;                        // floats per staged row: 32 columns + 4 pad (conflict-free 16-byte accesses)
+constexpr int TC_STAGE_BYTES = TC_EPI_WARPS * 32 * TC_STAGE_PITCH * 4;   // 36 KB of warp-private transpose buffers
 
 struct TcParams {
     int64_t M;
@@ -31,6 +36,50 @@ struct TcParams {
     int block_n, stages, n_tiles, tmem_cols;
     int64_t m_tiles;
 };
+
+
+// ---- coalesced epilogue ------------------------------------------------------------------------------------------
+// tcgen05.ld hands each lane ONE ROW of the accumulator (lane == TMEM lane == output row), so a direct store makes every
+// lane of a warp hit a different 128-byte line.  Each epilogue warp therefore transposes its 32 x 32 fp32 chunk through a
+// private shared-memory buffer: after the transpose 8 consecutive lanes own 32 consecutive columns of one row
+// (128 contiguous bytes of fp32), so the residual read-modify-write and all stores are fully coalesced.
+template <int EPI>
+__device__ __forceinline__ void epi_chunk(const EpiParams &e, float *stage, int lane, int64_t row0, int col0, int width,
+                                          const uint32_t (&acc)[32], const float4 (&res)[8]) {
+    // registers (row per lane) -> staging buffer
+    float4 *mine = reinterpret_cast<float4 *>(stage + lane * TC_STAGE_PITCH);
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+        if (j * 4 < width)
+            mine[j] = make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]), __uint_as_float(acc[4 * j + 2]),
+                                  __uint_as_float(acc[4 * j + 3]));
+    __syncwarp();
+    const int cl = (lane & 7) * 4, rl = lane >> 3;
+    const int col = col0 + cl;
+    if (cl < width) {
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4 *>(e.bias + col));
+#pragma unroll
+        for (int it = 0; it < 8; it++) {
+            const int rr = it * 4 + rl;
+            const int64_t row = row0 + rr;
+            if (row >= e.M) continue;
+            float4 v = *reinterpret_cast<const float4 *>(stage + rr * TC_STAGE_PITCH + cl);
+            v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+            if constexpr (EPI == NMM_EPI_RESIDUAL) { v.x += res[it].x; v.y += res[it].y; v.z += res[it].z; v.w += res[it].w; }
+            if constexpr (EPI == NMM_EPI_GEGLU) {
+                bf16 *dst = reinterpret_cast<bf16 *>(e.out) + row * (e.N / 2) + col / 2;
+                *reinterpret_cast<uint32_t *>(dst) = pack_bf16x2(v.x * gelu_erf_fast(v.y), v.z * gelu_erf_fast(v.w));
+            } else {
+                if (e.h != nullptr) *reinterpret_cast<float4 *>(e.h + row * e.N + col) = v;
+                if (e.out != nullptr)
+                    *reinterpret_cast<uint2 *>(reinterpret_cast<bf16 *>(e.out) + row * e.N + col) =
+                        make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+            }
+        }
+    }
+    __syncwarp();            // the next chunk overwrites the staging buffer
+}
 
 template <int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -46,6 +95,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * p.stages + s); };
     auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * p.stages + 2 + s); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * p.stages + 4);
+    // warp-private transpose buffers of the epilogue warps (generic pointer: plain ld/st.shared)
+    float *stage_base = reinterpret_cast<float *>(smem_raw + (smem_base - ptx::smem_u32(smem_raw)) + (size_t)p.stages * stage_bytes + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = (p.K + TC_BK - 1) / TC_BK;
@@ -57,7 +108,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.stages; s++) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < 2; s++) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), 128); }
+        for (int s = 0; s < 2; s++) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), 32 * TC_EPI_WARPS); }
         ptx::fence_mbar_init();
     }
     if (warp == 2) ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
@@ -113,24 +164,130 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     } else if (warp >= 4) {
         // ===================== epilogue =====================
         const int q = warp & 3;                                           // TMEM lane quadrant this warp may access
+        const int half = (warp - 4) >> 2;                                 // which of the quadrant's two warps
+        float *stage = stage_base + (warp - 4) * 32 * TC_STAGE_PITCH;
         int as = 0; uint32_t aphase = 0;
         for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int64_t m_blk = tile / p.n_tiles;
             const int n_blk = (int)(tile - m_blk * p.n_tiles);
-            ptx::mbar_wait(tfull_bar(as), aphase);
-            ptx::tc_fence_after();
-            const int64_t row = m_blk * TC_BM + q * 32 + lane;
+            const int64_t row0 = m_blk * TC_BM + q * 32;
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.block_n);
-            for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-                uint32_t r[16];
-                ptx::tmem_ld16(t_row + (uint32_t)c0, r);
-                ptx::tmem_ld_wait();
-                const int col0 = n_blk * p.block_n + c0;
-                if (row < p.M && col0 < p.N) {
-                    float acc[16];
+            if constexpr (EPI == NMM_EPI_OUTPUT) {
+                // y[b,c,f,p] = acc + bias[c] + x[b,c,f,p]: the output is channel-major, rows (p) are the contiguous axis
+                if (e.nchw_vec) {
+                    // 32 x 32 chunk through the transpose buffer (pitch 33: conflict-free both ways); afterwards 4 lanes own
+                    // 32 consecutive positions of one channel -> 16-byte loads of x and stores of y, 64 contiguous bytes per channel
+                    const int cq = lane >> 2, rg = lane & 3;
+                    const int64_t rowg = row0 + 8 * rg;                      // first of this lane's 8 rows
+                    const bool rows_ok = row0 < p.M;                          // M % 32 == 0 on this path: all-or-nothing per warp
+                    const int64_t bfi = rowg / e.P;
+                    const int pp = (int)(rowg - bfi * e.P);
+                    const int64_t bb = bfi / e.F, ff = bfi - bb * e.F;
+                    const bf16 *xrow = reinterpret_cast<const bf16 *>(e.x) + bb * e.xsb + ff * e.xsf + pp;
+                    bf16 *yrow = reinterpret_cast<bf16 *>(e.y) + bb * e.ysb + ff * e.ysf + pp;
+                    bool waited = false;
+                    for (int c0 = half * 32; c0 < p.block_n; c0 += 64) {
+                        const int width = min(32, p.block_n - c0);
+                        const int col0 = n_blk * p.block_n + c0;
+                        uint4 xin[4];
 #pragma unroll
-                    for (int j = 0; j < 16; j++) acc[j] = __uint_as_float(r[j]);
-                    epilogue_apply<EPI, bf16, 16>(e, row, col0, acc);
+                        for (int j = 0; j < 4; j++) {
+                            const int c = cq + 8 * j;
+                            xin[j] = (rows_ok && c < width) ? __ldg(reinterpret_cast<const uint4 *>(xrow + (int64_t)(col0 + c) * e.xsc))
+                                                            : make_uint4(0u, 0u, 0u, 0u);
+                        }
+                        if (!waited) {
+                            ptx::mbar_wait(tfull_bar(as), aphase);
+                            ptx::tc_fence_after();
+                            waited = true;
+                        }
+                        uint32_t lo[16], hi[16];
+                        ptx::tmem_ld16(t_row + (uint32_t)c0, lo);
+                        if (width > 16) ptx::tmem_ld16(t_row + (uint32_t)c0 + 16u, hi);
+                        ptx::tmem_ld_wait();
+                        uint32_t *srow = reinterpret_cast<uint32_t *>(stage) + lane * 33;
+#pragma unroll
+                        for (int j = 0; j < 16; j++) srow[j] = lo[j];
+                        if (width > 16) {
+#pragma unroll
+                            for (int j = 0; j < 16; j++) srow[16 + j] = hi[j];
+                        }
+                        __syncwarp();
+                        if (rows_ok) {
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                const int c = cq + 8 * j;
+                                if (c < width) {
+                                    const float bias = e.bias ? __ldg(e.bias + col0 + c) : 0.f;
+                                    const float *sc = stage + (8 * rg) * 33 + c;
+                                    const uint32_t xw[4] = {xin[j].x, xin[j].y, xin[j].z, xin[j].w};
+                                    uint32_t o[4];
+#pragma unroll
+                                    for (int i = 0; i < 4; i++)
+                                        o[i] = pack_bf16x2(sc[(2 * i) * 33] + bias + bf16_lo(xw[i]), sc[(2 * i + 1) * 33] + bias + bf16_hi(xw[i]));
+                                    *reinterpret_cast<uint4 *>(yrow + (int64_t)(col0 + c) * e.ysc) = make_uint4(o[0], o[1], o[2], o[3]);
+                                }
+                            }
+                        }
+                        __syncwarp();
+                    }
+                    if (!waited) {
+                        ptx::mbar_wait(tfull_bar(as), aphase);
+                        ptx::tc_fence_after();
+                    }
+                } else {
+                    // generic (ragged P / unaligned) path: one position per lane, 2-byte accesses coalesced along p
+                    ptx::mbar_wait(tfull_bar(as), aphase);
+                    ptx::tc_fence_after();
+                    const int64_t row = row0 + lane;
+                    for (int c0 = half * 16; c0 < p.block_n; c0 += 32) {
+                        uint32_t r[16];
+                        ptx::tmem_ld16(t_row + (uint32_t)c0, r);
+                        ptx::tmem_ld_wait();
+                        const int col0 = n_blk * p.block_n + c0;
+                        if (row < p.M && col0 < p.N) {
+                            float acc[16];
+#pragma unroll
+                            for (int j = 0; j < 16; j++) acc[j] = __uint_as_float(r[j]);
+                            epilogue_apply<EPI, bf16, 16>(e, row, col0, acc);
+                        }
+                    }
+                }
+            } else {
+                const int cl = (lane & 7) * 4, rl = lane >> 3;
+                bool waited = false;
+                for (int c0 = half * 32; c0 < p.block_n; c0 += 64) {
+                    const int width = min(32, p.block_n - c0);
+                    const int col0 = n_blk * p.block_n + c0;
+                    float4 res[8];
+                    if constexpr (EPI == NMM_EPI_RESIDUAL) {
+                        // prefetch the residual rows in the coalesced layout before waiting on the accumulator
+#pragma unroll
+                        for (int it = 0; it < 8; it++) {
+                            const int64_t row = row0 + it * 4 + rl;
+                            res[it] = (cl < width && row < e.M) ? *reinterpret_cast<const float4 *>(e.h + row * e.N + col0 + cl)
+                                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
+                    if (!waited) {
+                        ptx::mbar_wait(tfull_bar(as), aphase);
+                        ptx::tc_fence_after();
+                        waited = true;
+                    }
+                    uint32_t r[32];
+                    {
+                        uint32_t lo[16], hi[16];
+                        ptx::tmem_ld16(t_row + (uint32_t)c0, lo);
+                        if (width > 16) ptx::tmem_ld16(t_row + (uint32_t)c0 + 16u, hi);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; j++) { r[j] = lo[j]; r[16 + j] = (width > 16) ? hi[j] : 0u; }
+                    }
+                    epi_chunk<EPI>(e, stage, lane, row0, col0, width, r, res);
+                }
+                if (!waited) {                                            // this warp had no chunk in the tile
+                    ptx::mbar_wait(tfull_bar(as), aphase);
+                    ptx::tc_fence_after();
                 }
             }
             ptx::tc_fence_before();
@@ -233,14 +390,15 @@ int launch_linear_tc(const LinearArgs &a, cudaStream_t st) {
     p.block_n = choose_block_n(p.m_tiles, a.N, sms);
     p.n_tiles = a.N / p.block_n;
     const size_t stage_bytes = (size_t)TC_A_BYTES + (size_t)p.block_n * TC_BK * 2;
-    int stages = (int)((TC_SMEM_BUDGET - 1024) / stage_bytes);
+    int stages = (int)((TC_SMEM_BUDGET - 1024 - 512 - TC_STAGE_BYTES) / stage_bytes);
     if (stages > 8) stages = 8;
     if (stages < 2) return fail(NMM_ERR_UNSUPPORTED, "tcgen05 GEMM: tile does not fit shared memory");
     p.stages = stages;
     int cols = 32;
     while (cols < 2 * p.block_n) cols <<= 1;
     p.tmem_cols = cols;
-    const size_t smem = 1024 /*alignment slack*/ + (size_t)stages * stage_bytes + 8 * (2 * stages + 4) + 16;
+    // alignment slack + operand ring + 256 B of barriers + transpose buffers
+    const size_t smem = 1024 + (size_t)stages * stage_bytes + 256 + TC_STAGE_BYTES;
     CUtensorMap ta, tw;
     int rc = make_tmap(&ta, a.A, a.M, a.K, a.K, TC_BM);
     if (rc != NMM_OK) return rc;

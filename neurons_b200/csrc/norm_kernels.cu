@@ -31,8 +31,7 @@ template <> struct Vec16<float> { static constexpr int N = 4; };
 template <> struct Vec16<bf16> { static constexpr int N = 8; };
 
 template <typename T>
-__device__ __forceinline__ void accum16(const T *p, float &s, float &ss) {
-    uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+__device__ __forceinline__ void accum16v(const uint4 v, float &s, float &ss) {
     if constexpr (sizeof(T) == 4) {
         float f[4] = {__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w)};
 #pragma unroll
@@ -63,10 +62,21 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const T *__restric
     float s = 0.f, ss = 0.f;
     if constexpr (VEC) {
         constexpr int V = Vec16<T>::N;                 // P % V == 0, so a vector never straddles channels
-        for (int64_t e = e0 + (int64_t)threadIdx.x * V; e < e1; e += (int64_t)GN_THREADS * V) {
-            int c = (int)(e / P); int p = (int)(e - (int64_t)c * P);
-            accum16<T>(base + (int64_t)c * sc + p, s, ss);
+        constexpr int PER_THREAD = GN_CHUNK / (GN_THREADS * V);
+        const int tot = (int)total, base_e = (int)e0;  // cpg*P < 2^31 (validated)
+        // issue every load of this thread before the first accumulate (4 x 16 B in flight per thread for bf16)
+        uint4 v[PER_THREAD];
+        bool ok[PER_THREAD];
+#pragma unroll
+        for (int i = 0; i < PER_THREAD; i++) {
+            const int e = base_e + (i * GN_THREADS + (int)threadIdx.x) * V;
+            ok[i] = e < tot;
+            const int c = ok[i] ? e / P : 0;
+            const int p = ok[i] ? e - c * P : 0;
+            v[i] = ok[i] ? __ldg(reinterpret_cast<const uint4 *>(base + (int64_t)c * sc + p)) : make_uint4(0u, 0u, 0u, 0u);
         }
+#pragma unroll
+        for (int i = 0; i < PER_THREAD; i++) accum16v<T>(v[i], s, ss);      // zero vectors add nothing
     } else {
         for (int64_t e = e0 + threadIdx.x; e < e1; e += GN_THREADS) {
             int c = (int)(e / P); int p = (int)(e - (int64_t)c * P);
@@ -255,79 +265,100 @@ int launch_gn_tokens(const Geo &g, const nmm_shape *s, const void *x, const doub
 }
 
 // ------------------------------------------------------------------------------------------------
-// LayerNorm over C (+ pe[frame of the token]).  One warp per token row; the row lives in registers
-// (two-pass mean / variance, fp32).  h is the fp32 residual stream; out is the GEMM operand dtype.
-// ITERS = C / 64 (each lane holds ITERS float2) for the register-resident path; ITERS = 0 is the
-// generic path (any C, re-reads the row from L1/L2).
+// LayerNorm over C (+ pe[frame of the token]).  h is the fp32 residual stream; out is the GEMM operand dtype.
+// Vector kernel: one 16-lane half-warp per token row, the row lives in registers as IT4 = C/64 float4 per lane
+// (two-pass mean / variance in fp32), every global access is 16 bytes per lane.  Generic kernel: one warp per row, any C.
 // ------------------------------------------------------------------------------------------------
-template <typename TOut, int ITERS>
-__global__ void __launch_bounds__(256) layernorm_pe_kernel(const float *__restrict__ h, const float *__restrict__ gamma,
-                                                           const float *__restrict__ beta, const float *__restrict__ pe,
-                                                           TOut *__restrict__ out, int64_t N, int C, int F, int P, float eps) {
+__device__ __forceinline__ float half_warp_sum(float v) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <typename TOut, int IT4>
+__global__ void __launch_bounds__(256) layernorm_pe_vec_kernel(const float *__restrict__ h, const float *__restrict__ gamma,
+                                                               const float *__restrict__ beta, const float *__restrict__ pe,
+                                                               TOut *__restrict__ out, int64_t N, int F, int P, float eps) {
+    constexpr int C = IT4 * 64;
+    const int l16 = threadIdx.x & 15;
+    int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4);
+    const bool valid = row < N;
+    if (!valid) row = N - 1;                         // keep the whole warp in the shuffles; stores are predicated
+    const float4 *hr = reinterpret_cast<const float4 *>(h + row * C);
+    float4 v[IT4];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < IT4; i++) {
+        v[i] = __ldg(hr + l16 + 16 * i);
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mu = half_warp_sum(s) * (1.0f / C);
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < IT4; i++) {
+        const float a = v[i].x - mu, b = v[i].y - mu, c = v[i].z - mu, d = v[i].w - mu;
+        ss = fmaf(a, a, ss); ss = fmaf(b, b, ss); ss = fmaf(c, c, ss); ss = fmaf(d, d, ss);
+    }
+    const float rstd = rsqrtf(half_warp_sum(ss) * (1.0f / C) + eps);
+    const float4 *per = pe ? reinterpret_cast<const float4 *>(pe + (int64_t)((row / P) % F) * C) : nullptr;
+    TOut *orow = out + row * C;
+#pragma unroll
+    for (int i = 0; i < IT4; i++) {
+        const int c4 = l16 + 16 * i;
+        const float4 gm = __ldg(reinterpret_cast<const float4 *>(gamma) + c4);
+        const float4 bt = __ldg(reinterpret_cast<const float4 *>(beta) + c4);
+        float4 o;
+        o.x = fmaf((v[i].x - mu) * rstd, gm.x, bt.x); o.y = fmaf((v[i].y - mu) * rstd, gm.y, bt.y);
+        o.z = fmaf((v[i].z - mu) * rstd, gm.z, bt.z); o.w = fmaf((v[i].w - mu) * rstd, gm.w, bt.w);
+        if (per) { const float4 pp = __ldg(per + c4); o.x += pp.x; o.y += pp.y; o.z += pp.z; o.w += pp.w; }
+        if (valid) {
+            if constexpr (sizeof(TOut) == 2) reinterpret_cast<uint2 *>(orow)[c4] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+            else reinterpret_cast<float4 *>(orow)[c4] = o;
+        }
+    }
+}
+
+template <typename TOut>
+__global__ void __launch_bounds__(256) layernorm_pe_generic_kernel(const float *__restrict__ h, const float *__restrict__ gamma,
+                                                                   const float *__restrict__ beta, const float *__restrict__ pe,
+                                                                   TOut *__restrict__ out, int64_t N, int C, int F, int P, float eps) {
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= N) return;
+    if (row >= N) return;                            // warp-uniform
     const float *hr = h + row * C;
     const float *per = pe ? pe + (int64_t)((row / P) % F) * C : nullptr;
     TOut *orow = out + row * C;
     const float invC = 1.0f / (float)C;
-    if constexpr (ITERS > 0) {
-        float2 v[ITERS];
-        float s = 0.f;
-#pragma unroll
-        for (int i = 0; i < ITERS; i++) {
-            v[i] = __ldg(reinterpret_cast<const float2 *>(hr) + lane + 32 * i);
-            s += v[i].x + v[i].y;
-        }
-        const float mu = warp_sum(s) * invC;
-        float ss = 0.f;
-#pragma unroll
-        for (int i = 0; i < ITERS; i++) {
-            float a = v[i].x - mu, b = v[i].y - mu;
-            ss = fmaf(a, a, ss); ss = fmaf(b, b, ss);
-        }
-        const float rstd = rsqrtf(warp_sum(ss) * invC + eps);
-#pragma unroll
-        for (int i = 0; i < ITERS; i++) {
-            const int c2 = lane + 32 * i;                      // float2 index
-            float2 gm = __ldg(reinterpret_cast<const float2 *>(gamma) + c2);
-            float2 bt = __ldg(reinterpret_cast<const float2 *>(beta) + c2);
-            float a = fmaf((v[i].x - mu) * rstd, gm.x, bt.x), b = fmaf((v[i].y - mu) * rstd, gm.y, bt.y);
-            if (per) { float2 pp = __ldg(reinterpret_cast<const float2 *>(per) + c2); a += pp.x; b += pp.y; }
-            if constexpr (sizeof(TOut) == 2) reinterpret_cast<uint32_t *>(orow)[c2] = pack_bf16x2(a, b);
-            else reinterpret_cast<float2 *>(orow)[c2] = make_float2(a, b);
-        }
-    } else {
-        float s = 0.f;
-        for (int c = lane; c < C; c += 32) s += hr[c];
-        const float mu = warp_sum(s) * invC;
-        float ss = 0.f;
-        for (int c = lane; c < C; c += 32) { float a = hr[c] - mu; ss = fmaf(a, a, ss); }
-        const float rstd = rsqrtf(warp_sum(ss) * invC + eps);
-        for (int c = lane; c < C; c += 32) {
-            float a = fmaf((hr[c] - mu) * rstd, gamma[c], beta[c]);
-            if (per) a += per[c];
-            orow[c] = from_f32<TOut>(a);
-        }
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += hr[c];
+    const float mu = warp_sum(s) * invC;
+    float ss = 0.f;
+    for (int c = lane; c < C; c += 32) { float a = hr[c] - mu; ss = fmaf(a, a, ss); }
+    const float rstd = rsqrtf(warp_sum(ss) * invC + eps);
+    for (int c = lane; c < C; c += 32) {
+        float a = fmaf((hr[c] - mu) * rstd, gamma[c], beta[c]);
+        if (per) a += per[c];
+        orow[c] = from_f32<TOut>(a);
     }
 }
 
 template <typename TOut>
 static int launch_ln_t(const Geo &g, const nmm_shape *s, const float *h, const float *w, const float *b, const float *pe,
                        TOut *out, cudaStream_t st) {
-    const int rows_per_block = 8;
-    const int64_t blocks = ceil_div(g.N, rows_per_block);
-    if (blocks > 0x7fffffff) return fail(NMM_ERR_UNSUPPORTED, "too many tokens");
-    dim3 grid((unsigned)blocks), block(rows_per_block * 32);
     ProfScope prof(K_LAYERNORM, st, 0.0, (double)g.N * g.C * (4 + sizeof(TOut)));
-#define LN_CASE(IT) layernorm_pe_kernel<TOut, IT><<<grid, block, 0, st>>>(h, w, b, pe, out, g.N, g.C, g.F, g.P, s->eps_ln)
-    switch (g.C) {
-        case 320: LN_CASE(5); break;
-        case 640: LN_CASE(10); break;
-        case 1280: LN_CASE(20); break;
-        default: LN_CASE(0); break;
+    const bool vec_ok = aligned(h, 16) && aligned(w, 16) && aligned(b, 16) && aligned(out, 16) && (pe == nullptr || aligned(pe, 16));
+    if (vec_ok && (g.C == 320 || g.C == 640 || g.C == 1280)) {
+        const int64_t blocks = ceil_div(g.N, 16);                    // 16 rows (half-warps) per 256-thread CTA
+        if (blocks > 0x7fffffff) return fail(NMM_ERR_UNSUPPORTED, "too many tokens");
+        dim3 grid((unsigned)blocks), block(256);
+        if (g.C == 320) layernorm_pe_vec_kernel<TOut, 5><<<grid, block, 0, st>>>(h, w, b, pe, out, g.N, g.F, g.P, s->eps_ln);
+        else if (g.C == 640) layernorm_pe_vec_kernel<TOut, 10><<<grid, block, 0, st>>>(h, w, b, pe, out, g.N, g.F, g.P, s->eps_ln);
+        else layernorm_pe_vec_kernel<TOut, 20><<<grid, block, 0, st>>>(h, w, b, pe, out, g.N, g.F, g.P, s->eps_ln);
+    } else {
+        const int64_t blocks = ceil_div(g.N, 8);
+        if (blocks > 0x7fffffff) return fail(NMM_ERR_UNSUPPORTED, "too many tokens");
+        layernorm_pe_generic_kernel<TOut><<<(unsigned)blocks, 256, 0, st>>>(h, w, b, pe, out, g.N, g.C, g.F, g.P, s->eps_ln);
     }
-#undef LN_CASE
     NMM_LAUNCHED("layernorm_pe_kernel");
     return NMM_OK;
 }

@@ -1,0 +1,98 @@
+#!/usr/bin/env python
+"""Per-kernel micro-benchmark at the shapes of one UNet step (B=2, 8 frames, 64x64 latent by default).
+
+Times every stage of the module separately through the C ABI's per-stage entry points, with an L2 flush between
+iterations, and prints achieved TFLOP/s and GB/s against the measured peaks.  Development tool; bench.py is the
+contract benchmark.
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from neurons_b200 import lib as nlib  # noqa: E402
+from neurons_b200 import ops  # noqa: E402
+
+
+def timed(fn, flush, iters=5, warm=2):
+    """Median device time (ms) of the library kernels `fn` launches, from the library's own CUDA events
+    (host/Python launch overhead excluded), with an L2 flush before every iteration."""
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        torch.cuda.synchronize()
+        nlib.profile_begin()
+        fn()
+        prof = nlib.profile_end()
+        ts.append(sum(v["total_ms"] for v in prof.values()))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=2)
+    ap.add_argument("--frames", type=int, default=8)
+    ap.add_argument("--latent", type=int, default=64)
+    ap.add_argument("--out", default="gpurun_out/stage_bench.json")
+    ap.add_argument("--levels", default="320,640,1280")
+    a = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.isfile(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    rows = []
+    bf = torch.bfloat16
+    for C in [int(c) for c in a.levels.split(",")]:
+        side = a.latent * 320 // C
+        B, F = a.batch, a.frames
+        P = side * side
+        M = B * F * P
+        cfg = ops.ModuleConfig(C)
+        g = torch.Generator(device=dev).manual_seed(0)
+        x = torch.randn(B, F, C, side, side, device=dev, dtype=bf, generator=g).permute(0, 2, 1, 3, 4)
+        gw, gb = torch.ones(C, device=dev), torch.zeros(C, device=dev)
+        act = torch.randn(M, C, device=dev, dtype=bf, generator=g)
+        act4 = torch.randn(M, 4 * C, device=dev, dtype=bf, generator=g)
+        qkv = torch.randn(M, 3 * C, device=dev, dtype=bf, generator=g)
+        h = torch.randn(M, C, device=dev, generator=g)
+        w_cc = torch.randn(C, C, device=dev, dtype=bf, generator=g) / C ** 0.5
+        w_qkv = torch.randn(3 * C, C, device=dev, dtype=bf, generator=g) / C ** 0.5
+        w_1 = torch.randn(8 * C, C, device=dev, dtype=bf, generator=g) / C ** 0.5
+        w_2 = torch.randn(C, 4 * C, device=dev, dtype=bf, generator=g) / (4 * C) ** 0.5
+        bias = torch.randn(C, device=dev, generator=g)
+        bias8 = torch.randn(8 * C, device=dev, generator=g)
+        pe = torch.randn(24, C, device=dev, generator=g)
+        es = 2
+        stages = [
+            ("gn_stats", lambda: ops.groupnorm_stats(cfg, x), 0.0, M * C * es),
+            ("gn_tokens(+stats)", lambda: ops.groupnorm_tokens(cfg, x, gw, gb), 0.0, 3 * M * C * es),
+            ("layernorm_pe", lambda: ops.layernorm_pe(cfg, (B, F, side, side), h, gw, gb, pe, bf), 0.0, M * C * (4 + es)),
+            ("attention", lambda: ops.temporal_attention(cfg, (B, F, side, side), qkv), 4.0 * M * F * C, 4 * M * C * es),
+            ("proj_in  C->C  store h", lambda: ops.linear(act, w_cc, bias, nlib.EPI_STORE, h=h, want_out=False), 2.0 * M * C * C, M * C * (es + 4)),
+            ("qkv      C->3C store", lambda: ops.linear(act, w_qkv, None, nlib.EPI_STORE), 2.0 * M * C * 3 * C, M * C * es * 4),
+            ("to_out   C->C  residual", lambda: ops.linear(act, w_cc, bias, nlib.EPI_RESIDUAL, h=h, want_out=False), 2.0 * M * C * C, M * C * (es + 8)),
+            ("geglu    C->8C", lambda: ops.linear(act, w_1, bias8, nlib.EPI_GEGLU), 2.0 * M * C * 8 * C, M * C * es * 5),
+            ("ff_out   4C->C residual+copy", lambda: ops.linear(act4, w_2, bias, nlib.EPI_RESIDUAL, h=h, want_out=True), 2.0 * M * 4 * C * C, M * C * (4 * es + 8 + es)),
+            ("proj_out C->C  nchw+x", lambda: ops.linear(act, w_cc, bias, nlib.EPI_OUTPUT, cfg=cfg, x=x), 2.0 * M * C * C, M * C * es * 3),
+        ]
+        for name, fn, flops, byts in stages:
+            ms = timed(fn, flush)
+            rows.append(dict(C=C, side=side, M=M, stage=name, ms=ms, tflops=flops / ms / 1e9, gbps=byts / ms / 1e6,
+                             frac_tensor=flops / ms / 1e9 / peaks["bf16_tflops"], frac_hbm=byts / ms / 1e6 / peaks["hbm_gbs"]))
+            r = rows[-1]
+            print(f"C={C:5d} M={M:6d} {name:32s} {ms*1e3:9.1f} us  {r['tflops']:8.1f} TF/s ({r['frac_tensor']*100:5.1f}%)  "
+                  f"{r['gbps']:8.1f} GB/s ({r['frac_hbm']*100:5.1f}%)", flush=True)
+        del x, act, act4, qkv, h
+    os.makedirs(os.path.dirname(a.out), exist_ok=True)
+    json.dump(rows, open(a.out, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
