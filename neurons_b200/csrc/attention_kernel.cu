@@ -61,28 +61,34 @@ __global__ void __launch_bounds__(256) temporal_attention_kernel(const T *__rest
     const int npos = min(PB, P - p0);
     const int tid = threadIdx.x, nthr = blockDim.x;
 
-    // ---- stage q|k|v: for each frame a contiguous run of npos*3C elements --------------------------
+    // ---- stage q|k|v with cp.async (16-byte LDGSTS, no register staging): one warp per (frame, position) row at a time,
+    //      lanes striding over the row's vectors; the three segments (q, k, v of this head group) are W elements each --------
     {
-        constexpr int LV = 16 / (int)sizeof(T);                     // elements per 16-byte load
-        const bool vec = (VEC > 1);                                 // host guarantees 16B alignment when VEC > 1
-        if (vec) {
-            const int vec_per_seg = W / LV, vec_per_row = 3 * vec_per_seg;
-            const int total = F * npos * vec_per_row;
-            for (int i = tid; i < total; i += nthr) {
-                int v = i % vec_per_row; int r = i / vec_per_row;   // r = f*npos + pl
-                int pl = r % npos, f = r / npos;
-                int seg = v / vec_per_seg, within = v - seg * vec_per_seg;     // seg: 0 = q, 1 = k, 2 = v
-                const T *src = qkv + ((int64_t)(b * F + f) * P + p0 + pl) * (3 * C) + seg * C + c_off + within * LV;
-                uint4 val = __ldg(reinterpret_cast<const uint4 *>(src));
-                *reinterpret_cast<uint4 *>(sm + (pl * F + f) * pitch + v * LV) = val;
+        constexpr int LV = 16 / (int)sizeof(T);                     // elements per 16-byte copy
+        const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
+        const int rows = F * npos;
+        if (VEC > 1) {                                              // host guarantees 16-byte alignment when VEC > 1
+            const int vec_per_seg = W / LV;
+            for (int r = warp; r < rows; r += nwarps) {
+                const int f = r / npos, pl = r - f * npos;
+                const T *src_row = qkv + ((int64_t)(b * F + f) * P + p0 + pl) * (3 * C) + c_off;
+                const uint32_t dst_row = (uint32_t)__cvta_generic_to_shared(sm + (pl * F + f) * pitch);
+#pragma unroll
+                for (int seg = 0; seg < 3; seg++)
+                    for (int v = lane; v < vec_per_seg; v += 32)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_row + (uint32_t)((seg * W + v * LV) * sizeof(T))),
+                                     "l"(src_row + seg * C + v * LV)
+                                     : "memory");
             }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         } else {
-            const int total = F * npos * 3 * W;
-            for (int i = tid; i < total; i += nthr) {
-                int e = i % (3 * W); int r = i / (3 * W);
-                int pl = r % npos, f = r / npos;
-                int seg = e / W, within = e - seg * W;
-                sm[(pl * F + f) * pitch + e] = qkv[((int64_t)(b * F + f) * P + p0 + pl) * (3 * C) + seg * C + c_off + within];
+            for (int r = warp; r < rows; r += nwarps) {
+                const int f = r / npos, pl = r - f * npos;
+                const T *src_row = qkv + ((int64_t)(b * F + f) * P + p0 + pl) * (3 * C) + c_off;
+                T *dst_row = sm + (pl * F + f) * pitch;
+                for (int seg = 0; seg < 3; seg++)
+                    for (int e = lane; e < W; e += 32) dst_row[seg * W + e] = src_row[seg * C + e];
             }
         }
     }
@@ -142,24 +148,20 @@ __global__ void __launch_bounds__(256) temporal_attention_kernel(const T *__rest
     }
     __syncthreads();
 
-    // ---- write ctx rows (the first W elements of each staged row) -----------------------------------
+    // ---- write ctx rows (the first W elements of each staged row): one warp per row, 16-byte coalesced stores ----------
     {
         constexpr int LV = 16 / (int)sizeof(T);
-        if (VEC > 1) {
-            const int vec_per_row = W / LV;
-            const int total = F * npos * vec_per_row;
-            for (int i = tid; i < total; i += nthr) {
-                int v = i % vec_per_row; int r = i / vec_per_row;
-                int pl2 = r % npos, f2 = r / npos;
-                uint4 val = *reinterpret_cast<const uint4 *>(sm + (pl2 * F + f2) * pitch + v * LV);
-                *reinterpret_cast<uint4 *>(ctx + ((int64_t)(b * F + f2) * P + p0 + pl2) * C + c_off + v * LV) = val;
-            }
-        } else {
-            const int total = F * npos * W;
-            for (int i = tid; i < total; i += nthr) {
-                int e = i % W; int r = i / W;
-                int pl2 = r % npos, f2 = r / npos;
-                ctx[((int64_t)(b * F + f2) * P + p0 + pl2) * C + c_off + e] = sm[(pl2 * F + f2) * pitch + e];
+        const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
+        const int rows = F * npos;
+        for (int r = warp; r < rows; r += nwarps) {
+            const int f2 = r / npos, pl2 = r - f2 * npos;
+            const T *src_row = sm + (pl2 * F + f2) * pitch;
+            T *dst_row = ctx + ((int64_t)(b * F + f2) * P + p0 + pl2) * C + c_off;
+            if (VEC > 1) {
+                for (int v = lane; v < W / LV; v += 32)
+                    *reinterpret_cast<uint4 *>(dst_row + v * LV) = *reinterpret_cast<const uint4 *>(src_row + v * LV);
+            } else {
+                for (int e = lane; e < W; e += 32) dst_row[e] = src_row[e];
             }
         }
     }

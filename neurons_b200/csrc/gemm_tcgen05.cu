@@ -56,25 +56,41 @@ __device__ __forceinline__ void epi_chunk(const EpiParams &e, float *stage, int 
     __syncwarp();
     const int cl = (lane & 7) * 4, rl = lane >> 3;
     const int col = col0 + cl;
-    if (cl < width) {
+    if (cl < width) {                                    // warp-uniform per 8-lane group; width is 16 or 32
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (e.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4 *>(e.bias + col));
+        // straight-line code (no branches inside the unrolled loops) so the 8 rows overlap: all loads, then math, then
+        // predicated stores
+        float4 v[8];
+#pragma unroll
+        for (int it = 0; it < 8; it++) v[it] = *reinterpret_cast<const float4 *>(stage + (it * 4 + rl) * TC_STAGE_PITCH + cl);
 #pragma unroll
         for (int it = 0; it < 8; it++) {
-            const int rr = it * 4 + rl;
-            const int64_t row = row0 + rr;
-            if (row >= e.M) continue;
-            float4 v = *reinterpret_cast<const float4 *>(stage + rr * TC_STAGE_PITCH + cl);
-            v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
-            if constexpr (EPI == NMM_EPI_RESIDUAL) { v.x += res[it].x; v.y += res[it].y; v.z += res[it].z; v.w += res[it].w; }
-            if constexpr (EPI == NMM_EPI_GEGLU) {
-                bf16 *dst = reinterpret_cast<bf16 *>(e.out) + row * (e.N / 2) + col / 2;
-                *reinterpret_cast<uint32_t *>(dst) = pack_bf16x2(v.x * gelu_erf_fast(v.y), v.z * gelu_erf_fast(v.w));
-            } else {
-                if (e.h != nullptr) *reinterpret_cast<float4 *>(e.h + row * e.N + col) = v;
-                if (e.out != nullptr)
-                    *reinterpret_cast<uint2 *>(reinterpret_cast<bf16 *>(e.out) + row * e.N + col) =
-                        make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+            v[it].x += b4.x; v[it].y += b4.y; v[it].z += b4.z; v[it].w += b4.w;
+            if constexpr (EPI == NMM_EPI_RESIDUAL) { v[it].x += res[it].x; v[it].y += res[it].y; v[it].z += res[it].z; v[it].w += res[it].w; }
+        }
+        if constexpr (EPI == NMM_EPI_GEGLU) {
+            uint32_t o[8];
+#pragma unroll
+            for (int it = 0; it < 8; it++) o[it] = pack_bf16x2(v[it].x * gelu_erf_fast(v[it].y), v[it].z * gelu_erf_fast(v[it].w));
+            bf16 *dst = reinterpret_cast<bf16 *>(e.out) + (row0 + rl) * (e.N / 2) + col / 2;
+#pragma unroll
+            for (int it = 0; it < 8; it++)
+                if (row0 + it * 4 + rl < e.M) *reinterpret_cast<uint32_t *>(dst + (int64_t)(it * 4) * (e.N / 2)) = o[it];
+        } else {
+            if (e.h != nullptr) {
+                float *dst = e.h + (row0 + rl) * e.N + col;
+#pragma unroll
+                for (int it = 0; it < 8; it++)
+                    if (row0 + it * 4 + rl < e.M) *reinterpret_cast<float4 *>(dst + (int64_t)(it * 4) * e.N) = v[it];
+            }
+            if (e.out != nullptr) {
+                bf16 *dst = reinterpret_cast<bf16 *>(e.out) + (row0 + rl) * e.N + col;
+#pragma unroll
+                for (int it = 0; it < 8; it++)
+                    if (row0 + it * 4 + rl < e.M)
+                        *reinterpret_cast<uint2 *>(dst + (int64_t)(it * 4) * e.N) =
+                            make_uint2(pack_bf16x2(v[it].x, v[it].y), pack_bf16x2(v[it].z, v[it].w));
             }
         }
     }
