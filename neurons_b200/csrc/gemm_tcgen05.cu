@@ -14,6 +14,8 @@
 // (token-major) and nn.Linear weights ([out, in]) are laid out, so no transposes are ever materialised.
 #include <cuda.h>
 
+#include <cstdlib>
+#include <cstring>
 #include <mutex>
 
 #include "common.cuh"
@@ -35,6 +37,8 @@ struct TcParams {
     int N, K;
     int block_n, stages, n_tiles, tmem_cols;
     int64_t m_tiles;
+    int cluster;             // CTAs per cluster along M (1 or 2): the W tile is loaded once per cluster and multicast
+    int64_t cluster_tiles;   // ceil(m_tiles / cluster) * n_tiles
 };
 
 
@@ -116,20 +120,25 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = (p.K + TC_BK - 1) / TC_BK;
-    const int64_t total_tiles = p.m_tiles * p.n_tiles;
+    // Tile schedule: a cluster walks (m_group, n_blk) pairs; CTA `rank` of the cluster owns m-block m_group*cluster + rank.
+    // Both CTAs of a cluster run the same number of iterations (a phantom m-block past the end is all zero-fill + masked).
+    const uint32_t rank = p.cluster > 1 ? ptx::cluster_ctarank() : 0u;
+    const int64_t cluster_id = blockIdx.x / p.cluster, num_clusters = gridDim.x / p.cluster;
+    const uint16_t mc_mask = (uint16_t)((1u << p.cluster) - 1u);
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tm_a);
         ptx::prefetch_tensormap(&tm_w);
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < p.stages; s++) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < p.stages; s++) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), (uint32_t)p.cluster); }
         for (int s = 0; s < 2; s++) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), 32 * TC_EPI_WARPS); }
         ptx::fence_mbar_init();
     }
     if (warp == 2) ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     ptx::tc_fence_before();
-    __syncthreads();
+    if (p.cluster > 1) ptx::cluster_sync();          // peers' barriers must be initialised before any multicast / remote arrive
+    else __syncthreads();
     ptx::tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -138,15 +147,22 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int64_t m_blk = tile / p.n_tiles;
-                const int n_blk = (int)(tile - m_blk * p.n_tiles);
+            const uint32_t slice_rows = (uint32_t)(p.block_n / p.cluster);            // rows of the W tile this CTA fetches
+            const uint32_t slice_bytes = slice_rows * TC_BK * 2;
+            for (int64_t ct = cluster_id; ct < p.cluster_tiles; ct += num_clusters) {
+                const int64_t m_grp = ct / p.n_tiles;
+                const int n_blk = (int)(ct - m_grp * p.n_tiles);
+                const int64_t m_blk = m_grp * p.cluster + rank;
                 for (int kb = 0; kb < num_kb; kb++) {
-                    ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+                    ptx::mbar_wait(empty_bar(stage), phase ^ 1u);       // every CTA of the cluster has consumed this stage
                     ptx::mbar_expect_tx(full_bar(stage), stage_bytes);
                     const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
                     ptx::tma_load_2d(&tm_a, full_bar(stage), sa, kb * TC_BK, (int32_t)(m_blk * TC_BM));
-                    ptx::tma_load_2d(&tm_w, full_bar(stage), sa + TC_A_BYTES, kb * TC_BK, n_blk * p.block_n);
+                    if (p.cluster > 1)
+                        ptx::tma_load_2d_mc(&tm_w, full_bar(stage), sa + TC_A_BYTES + rank * slice_bytes, kb * TC_BK,
+                                            n_blk * p.block_n + (int)(rank * slice_rows), mc_mask);
+                    else
+                        ptx::tma_load_2d(&tm_w, full_bar(stage), sa + TC_A_BYTES, kb * TC_BK, n_blk * p.block_n);
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -157,7 +173,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             const uint32_t idesc = ptx::umma_idesc_bf16(TC_BM, (uint32_t)p.block_n);
             int stage = 0; uint32_t phase = 0;
             int as = 0; uint32_t aphase = 0;
-            for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int64_t ct = cluster_id; ct < p.cluster_tiles; ct += num_clusters) {
                 ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);           // epilogue has drained this accumulator
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.block_n);
@@ -170,7 +186,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
                     for (int k = 0; k < TC_BK / 16; k++)                 // +32 bytes per K=16 step inside the swizzle atom
                         ptx::umma_bf16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
-                    ptx::umma_commit(empty_bar(stage));                   // stage reusable once these MMAs retire
+                    // stage reusable (in every CTA of the cluster: peers multicast W into it) once these MMAs retire
+                    if (p.cluster > 1) ptx::umma_commit_mc(empty_bar(stage), mc_mask);
+                    else ptx::umma_commit(empty_bar(stage));
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
                 ptx::umma_commit(tfull_bar(as));                          // accumulator complete
@@ -183,9 +201,10 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const int half = (warp - 4) >> 2;                                 // which of the quadrant's two warps
         float *stage = stage_base + (warp - 4) * 32 * TC_STAGE_PITCH;
         int as = 0; uint32_t aphase = 0;
-        for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int64_t m_blk = tile / p.n_tiles;
-            const int n_blk = (int)(tile - m_blk * p.n_tiles);
+        for (int64_t ct = cluster_id; ct < p.cluster_tiles; ct += num_clusters) {
+            const int64_t m_grp = ct / p.n_tiles;
+            const int n_blk = (int)(ct - m_grp * p.n_tiles);
+            const int64_t m_blk = m_grp * p.cluster + rank;
             const int64_t row0 = m_blk * TC_BM + q * 32;
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.block_n);
             if constexpr (EPI == NMM_EPI_OUTPUT) {
@@ -311,8 +330,10 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             if (++as == 2) { as = 0; aphase ^= 1u; }
         }
     }
+    __syncwarp();                                    // lanes 1-31 of the single-thread roles rejoin lane 0 before the aligned barrier
     ptx::tc_fence_before();
-    __syncthreads();
+    if (p.cluster > 1) ptx::cluster_sync();          // a peer may still multicast into / arrive on this CTA's shared memory
+    else __syncthreads();
     if (warp == 2) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
@@ -387,9 +408,23 @@ static int launch_tc_t(const CUtensorMap &ta, const CUtensorMap &tw, const TcPar
         NMM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET + 2048));
         attr_set = true;
     }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)p.cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = p.cluster > 1 ? 1 : 0;
     {
         ProfScope prof(K_LINEAR_TC, st, flops, bytes);
-        kern<<<grid, TC_THREADS, smem, st>>>(ta, tw, p, e);
+        cudaError_t le = cudaLaunchKernelEx(&cfg, kern, ta, tw, p, e);
+        if (le != cudaSuccess) return fail(NMM_ERR_CUDA, "cudaLaunchKernelEx(linear_tc_kernel) failed: %s", cudaGetErrorString(le));
     }
     NMM_LAUNCHED("linear_tc_kernel");
     return NMM_OK;
@@ -403,8 +438,15 @@ int launch_linear_tc(const LinearArgs &a, cudaStream_t st) {
     p.M = a.M; p.N = a.N; p.K = a.K;
     p.m_tiles = ceil_div(a.M, TC_BM);
     const int sms = num_sms();
-    p.block_n = choose_block_n(p.m_tiles, a.N, sms);
+    // CTA pairs along M share every W tile through TMA multicast: halves the L2 -> SM traffic of the weights, which is what
+    // bounds these GEMMs (each 128-row tile otherwise re-reads all of W from L2).  148 SMs = 74 pairs.
+    static const int force_cluster = getenv("NMM_GEMM_CLUSTER") ? atoi(getenv("NMM_GEMM_CLUSTER")) : 0;
+    p.cluster = (p.m_tiles >= 2 && sms % 2 == 0) ? 2 : 1;
+    if (force_cluster == 1 || force_cluster == 2) p.cluster = force_cluster;
+    const int64_t m_groups = ceil_div(p.m_tiles, p.cluster);
+    p.block_n = choose_block_n(m_groups * p.cluster, a.N, sms);
     p.n_tiles = a.N / p.block_n;
+    p.cluster_tiles = m_groups * p.n_tiles;
     const size_t stage_bytes = (size_t)TC_A_BYTES + (size_t)p.block_n * TC_BK * 2;
     int stages = (int)((TC_SMEM_BUDGET - 1024 - 512 - TC_STAGE_BYTES) / stage_bytes);
     if (stages > 8) stages = 8;
@@ -418,10 +460,11 @@ int launch_linear_tc(const LinearArgs &a, cudaStream_t st) {
     CUtensorMap ta, tw;
     int rc = make_tmap(&ta, a.A, a.M, a.K, a.K, TC_BM);
     if (rc != NMM_OK) return rc;
-    rc = make_tmap(&tw, a.W, a.N, a.K, a.K, p.block_n);
+    rc = make_tmap(&tw, a.W, a.N, a.K, a.K, p.block_n / p.cluster);      // each CTA of a cluster fetches its slice of the W tile
     if (rc != NMM_OK) return rc;
-    const int64_t tiles = p.m_tiles * p.n_tiles;
-    const int grid = (int)(tiles < sms ? tiles : sms);
+    const int64_t ctas = p.cluster_tiles * p.cluster;
+    const int max_grid = sms / p.cluster * p.cluster;
+    const int grid = (int)(ctas < max_grid ? ctas : max_grid);
     EpiParams e = epi_params_of(a);
     const double fl = linear_flops(a), by = linear_bytes(a, 2);
     switch (a.epilogue) {
