@@ -37,7 +37,7 @@ struct TcParams {
     int N, K;
     int block_n, stages, n_tiles, tmem_cols;
     int64_t m_tiles;
-    int cluster;             // CTAs per cluster along M (1 or 2): the W tile is loaded once per cluster and multicast
+    int cluster;             // CTAs per tile along M: 1 (cta_group::1) or 2 (cta_group::2 pair, each CTA stages half of W)
     int64_t cluster_tiles;   // ceil(m_tiles / cluster) * n_tiles
 };
 
@@ -101,13 +101,19 @@ __device__ __forceinline__ void epi_chunk(const EpiParams &e, float *stage, int 
     __syncwarp();            // the next chunk overwrites the staging buffer
 }
 
-template <int EPI>
+template <int EPI, int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, TcParams p, EpiParams e) {
+    // CG == 1: one CTA per 128 x block_n tile (tcgen05.mma.cta_group::1).
+    // CG == 2: a CTA pair (cluster of 2 along M) computes a 256 x block_n tile with ONE tcgen05.mma.cta_group::2 stream issued
+    //          by the even CTA: each CTA stages its own 128 rows of A and HALF of the W tile (block_n/2 rows); the tensor core
+    //          reads the two W halves from both CTAs' shared memory and each CTA's TMEM receives its own 128 x block_n
+    //          accumulator.  Per SM and k-block the shared-memory fill drops from 16 KB + block_n*128 B to 16 KB + block_n*64 B
+    //          -- the L2 -> SM ingest rate, not HBM or the tensor pipe, is what bounds the single-CTA kernel.
     extern __shared__ unsigned char smem_raw[];
     const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B tiles need 1024-byte alignment
-    const uint32_t b_bytes = (uint32_t)p.block_n * TC_BK * 2;
-    const uint32_t stage_bytes = TC_A_BYTES + b_bytes;
+    const uint32_t b_rows = (uint32_t)p.block_n / CG;                           // W rows staged by this CTA
+    const uint32_t stage_bytes = TC_A_BYTES + b_rows * TC_BK * 2;
     const uint32_t bar_base = smem_base + (uint32_t)p.stages * stage_bytes;
     // barriers: full[stages], empty[stages], tmem_full[2], tmem_empty[2]; then the TMEM base address
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -120,83 +126,84 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = (p.K + TC_BK - 1) / TC_BK;
-    // Tile schedule: a cluster walks (m_group, n_blk) pairs; CTA `rank` of the cluster owns m-block m_group*cluster + rank.
-    // Both CTAs of a cluster run the same number of iterations (a phantom m-block past the end is all zero-fill + masked).
-    const uint32_t rank = p.cluster > 1 ? ptx::cluster_ctarank() : 0u;
-    const int64_t cluster_id = blockIdx.x / p.cluster, num_clusters = gridDim.x / p.cluster;
-    const uint16_t mc_mask = (uint16_t)((1u << p.cluster) - 1u);
+    // Tile schedule: a cluster walks (m_group, n_blk) pairs; CTA `rank` of the cluster owns m-block m_group*CG + rank.
+    // Both CTAs of a pair run the same number of iterations (a phantom m-block past the end is all zero-fill + masked).
+    const uint32_t rank = CG > 1 ? ptx::cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
+    const int64_t cluster_id = blockIdx.x / CG, num_clusters = gridDim.x / CG;
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tm_a);
         ptx::prefetch_tensormap(&tm_w);
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < p.stages; s++) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), (uint32_t)p.cluster); }
-        for (int s = 0; s < 2; s++) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), 32 * TC_EPI_WARPS); }
+        for (int s = 0; s < p.stages; s++) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
+        // tmem_empty collects one arrive per epilogue warp of every CTA of the pair (it lives in the MMA-issuing CTA)
+        for (int s = 0; s < 2; s++) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), TC_EPI_WARPS * CG); }
         ptx::fence_mbar_init();
     }
-    if (warp == 2) ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    if (warp == 2) ptx::tmem_alloc<CG>(tmem_slot, (uint32_t)p.tmem_cols);
     ptx::tc_fence_before();
-    if (p.cluster > 1) ptx::cluster_sync();          // peers' barriers must be initialised before any multicast / remote arrive
+    if (CG > 1) ptx::cluster_sync();                 // the peer's barriers must exist before any remote arrive / complete_tx
     else __syncthreads();
     ptx::tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
+        // ===================== TMA producer (every CTA: its A rows, its slice of W) =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            const uint32_t slice_rows = (uint32_t)(p.block_n / p.cluster);            // rows of the W tile this CTA fetches
-            const uint32_t slice_bytes = slice_rows * TC_BK * 2;
             for (int64_t ct = cluster_id; ct < p.cluster_tiles; ct += num_clusters) {
                 const int64_t m_grp = ct / p.n_tiles;
                 const int n_blk = (int)(ct - m_grp * p.n_tiles);
-                const int64_t m_blk = m_grp * p.cluster + rank;
+                const int64_t m_blk = m_grp * CG + rank;
                 for (int kb = 0; kb < num_kb; kb++) {
-                    ptx::mbar_wait(empty_bar(stage), phase ^ 1u);       // every CTA of the cluster has consumed this stage
-                    ptx::mbar_expect_tx(full_bar(stage), stage_bytes);
+                    ptx::mbar_wait(empty_bar(stage), phase ^ 1u);       // the MMAs that read this stage have retired
                     const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
-                    ptx::tma_load_2d(&tm_a, full_bar(stage), sa, kb * TC_BK, (int32_t)(m_blk * TC_BM));
-                    if (p.cluster > 1)
-                        ptx::tma_load_2d_mc(&tm_w, full_bar(stage), sa + TC_A_BYTES + rank * slice_bytes, kb * TC_BK,
-                                            n_blk * p.block_n + (int)(rank * slice_rows), mc_mask);
-                    else
+                    if (CG == 1) {
+                        ptx::mbar_expect_tx(full_bar(stage), stage_bytes);
+                        ptx::tma_load_2d(&tm_a, full_bar(stage), sa, kb * TC_BK, (int32_t)(m_blk * TC_BM));
                         ptx::tma_load_2d(&tm_w, full_bar(stage), sa + TC_A_BYTES, kb * TC_BK, n_blk * p.block_n);
+                    } else {
+                        // both CTAs' bytes are counted on the even CTA's barrier (the only one the MMA thread waits on)
+                        if (leader) ptx::mbar_expect_tx(full_bar(stage), 2u * stage_bytes);
+                        const uint32_t bar0 = full_bar(stage) & ptx::PEER_MASK;
+                        ptx::tma_load_2d_2sm(&tm_a, bar0, sa, kb * TC_BK, (int32_t)(m_blk * TC_BM));
+                        ptx::tma_load_2d_2sm(&tm_w, bar0, sa + TC_A_BYTES, kb * TC_BK, n_blk * p.block_n + (int)(rank * b_rows));
+                    }
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc = ptx::umma_idesc_bf16(TC_BM, (uint32_t)p.block_n);
+        // ===================== MMA issuer (one thread of the even CTA) =====================
+        if (lane == 0 && leader) {
+            const uint32_t idesc = ptx::umma_idesc_bf16(TC_BM * CG, (uint32_t)p.block_n);
             int stage = 0; uint32_t phase = 0;
             int as = 0; uint32_t aphase = 0;
             for (int64_t ct = cluster_id; ct < p.cluster_tiles; ct += num_clusters) {
-                ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);           // epilogue has drained this accumulator
+                ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);           // every epilogue warp (of both CTAs) drained this accumulator
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.block_n);
                 for (int kb = 0; kb < num_kb; kb++) {
-                    ptx::mbar_wait(full_bar(stage), phase);              // TMA bytes have landed
+                    ptx::mbar_wait(full_bar(stage), phase);              // TMA bytes (of both CTAs) have landed
                     ptx::tc_fence_after();
                     const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
                     const uint64_t a_desc = ptx::umma_smem_desc_sw128(sa);
                     const uint64_t b_desc = ptx::umma_smem_desc_sw128(sa + TC_A_BYTES);
 #pragma unroll
                     for (int k = 0; k < TC_BK / 16; k++)                 // +32 bytes per K=16 step inside the swizzle atom
-                        ptx::umma_bf16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
-                    // stage reusable (in every CTA of the cluster: peers multicast W into it) once these MMAs retire
-                    if (p.cluster > 1) ptx::umma_commit_mc(empty_bar(stage), mc_mask);
-                    else ptx::umma_commit(empty_bar(stage));
+                        ptx::umma_bf16<CG>(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                    ptx::umma_commit<CG>(empty_bar(stage));               // stage reusable (in both CTAs) once these MMAs retire
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
-                ptx::umma_commit(tfull_bar(as));                          // accumulator complete
+                ptx::umma_commit<CG>(tfull_bar(as));                      // accumulator complete (signalled in both CTAs)
                 if (++as == 2) { as = 0; aphase ^= 1u; }
             }
         }
     } else if (warp >= 4) {
-        // ===================== epilogue =====================
+        // ===================== epilogue (every CTA: its own 128 TMEM lanes) =====================
         const int q = warp & 3;                                           // TMEM lane quadrant this warp may access
         const int half = (warp - 4) >> 2;                                 // which of the quadrant's two warps
         float *stage = stage_base + (warp - 4) * 32 * TC_STAGE_PITCH;
@@ -204,9 +211,17 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         for (int64_t ct = cluster_id; ct < p.cluster_tiles; ct += num_clusters) {
             const int64_t m_grp = ct / p.n_tiles;
             const int n_blk = (int)(ct - m_grp * p.n_tiles);
-            const int64_t m_blk = m_grp * p.cluster + rank;
+            const int64_t m_blk = m_grp * CG + rank;
             const int64_t row0 = m_blk * TC_BM + q * 32;
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.block_n);
+            bool waited = false;
+            auto wait_acc = [&]() {
+                if (!waited) {
+                    ptx::mbar_wait(tfull_bar(as), aphase);
+                    ptx::tc_fence_after();
+                    waited = true;
+                }
+            };
             if constexpr (EPI == NMM_EPI_OUTPUT) {
                 // y[b,c,f,p] = acc + bias[c] + x[b,c,f,p]: the output is channel-major, rows (p) are the contiguous axis
                 if (e.nchw_vec) {
@@ -220,7 +235,6 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     const int64_t bb = bfi / e.F, ff = bfi - bb * e.F;
                     const bf16 *xrow = reinterpret_cast<const bf16 *>(e.x) + bb * e.xsb + ff * e.xsf + pp;
                     bf16 *yrow = reinterpret_cast<bf16 *>(e.y) + bb * e.ysb + ff * e.ysf + pp;
-                    bool waited = false;
                     for (int c0 = half * 32; c0 < p.block_n; c0 += 64) {
                         const int width = min(32, p.block_n - c0);
                         const int col0 = n_blk * p.block_n + c0;
@@ -231,11 +245,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                             xin[j] = (rows_ok && c < width) ? __ldg(reinterpret_cast<const uint4 *>(xrow + (int64_t)(col0 + c) * e.xsc))
                                                             : make_uint4(0u, 0u, 0u, 0u);
                         }
-                        if (!waited) {
-                            ptx::mbar_wait(tfull_bar(as), aphase);
-                            ptx::tc_fence_after();
-                            waited = true;
-                        }
+                        wait_acc();
                         uint32_t lo[16], hi[16];
                         ptx::tmem_ld16(t_row + (uint32_t)c0, lo);
                         if (width > 16) ptx::tmem_ld16(t_row + (uint32_t)c0 + 16u, hi);
@@ -266,14 +276,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         }
                         __syncwarp();
                     }
-                    if (!waited) {
-                        ptx::mbar_wait(tfull_bar(as), aphase);
-                        ptx::tc_fence_after();
-                    }
                 } else {
                     // generic (ragged P / unaligned) path: one position per lane, 2-byte accesses coalesced along p
-                    ptx::mbar_wait(tfull_bar(as), aphase);
-                    ptx::tc_fence_after();
+                    wait_acc();
                     const int64_t row = row0 + lane;
                     for (int c0 = half * 16; c0 < p.block_n; c0 += 32) {
                         uint32_t r[16];
@@ -290,7 +295,6 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 }
             } else {
                 const int cl = (lane & 7) * 4, rl = lane >> 3;
-                bool waited = false;
                 for (int c0 = half * 32; c0 < p.block_n; c0 += 64) {
                     const int width = min(32, p.block_n - c0);
                     const int col0 = n_blk * p.block_n + c0;
@@ -304,11 +308,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
                         }
                     }
-                    if (!waited) {
-                        ptx::mbar_wait(tfull_bar(as), aphase);
-                        ptx::tc_fence_after();
-                        waited = true;
-                    }
+                    wait_acc();
                     uint32_t r[32];
                     {
                         uint32_t lo[16], hi[16];
@@ -320,23 +320,24 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     }
                     epi_chunk<EPI>(e, stage, lane, row0, col0, width, r, res);
                 }
-                if (!waited) {                                            // this warp had no chunk in the tile
-                    ptx::mbar_wait(tfull_bar(as), aphase);
-                    ptx::tc_fence_after();
-                }
             }
+            wait_acc();                                                   // a warp without a chunk in this tile still follows the phases
             ptx::tc_fence_before();
-            ptx::mbar_arrive(tempty_bar(as));
+            __syncwarp();
+            if (lane == 0) {
+                if (CG == 1) ptx::mbar_arrive(tempty_bar(as));
+                else ptx::mbar_arrive_cluster(tempty_bar(as) & ptx::PEER_MASK);      // the even CTA's barrier
+            }
             if (++as == 2) { as = 0; aphase ^= 1u; }
         }
     }
     __syncwarp();                                    // lanes 1-31 of the single-thread roles rejoin lane 0 before the aligned barrier
     ptx::tc_fence_before();
-    if (p.cluster > 1) ptx::cluster_sync();          // a peer may still multicast into / arrive on this CTA's shared memory
+    if (CG > 1) ptx::cluster_sync();                 // the peer may still read this CTA's shared memory / arrive on its barriers
     else __syncthreads();
     if (warp == 2) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+        ptx::tmem_dealloc<CG>(tmem_base, (uint32_t)p.tmem_cols);
     }
 }
 
@@ -399,10 +400,10 @@ static int choose_block_n(int64_t m_tiles, int N, int sms) {
     return smallest;
 }
 
-template <int EPI>
+template <int EPI, int CG>
 static int launch_tc_t(const CUtensorMap &ta, const CUtensorMap &tw, const TcParams &p, const EpiParams &e, size_t smem, int grid,
                        cudaStream_t st, double flops, double bytes) {
-    auto kern = linear_tc_kernel<EPI>;
+    auto kern = linear_tc_kernel<EPI, CG>;
     static bool attr_set = false;     // per template instantiation
     if (!attr_set) {
         NMM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET + 2048));
@@ -416,11 +417,11 @@ static int launch_tc_t(const CUtensorMap &ta, const CUtensorMap &tw, const TcPar
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)p.cluster;
+    attr[0].val.clusterDim.x = (unsigned)CG;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = p.cluster > 1 ? 1 : 0;
+    cfg.numAttrs = CG > 1 ? 1 : 0;
     {
         ProfScope prof(K_LINEAR_TC, st, flops, bytes);
         cudaError_t le = cudaLaunchKernelEx(&cfg, kern, ta, tw, p, e);
@@ -438,8 +439,8 @@ int launch_linear_tc(const LinearArgs &a, cudaStream_t st) {
     p.M = a.M; p.N = a.N; p.K = a.K;
     p.m_tiles = ceil_div(a.M, TC_BM);
     const int sms = num_sms();
-    // CTA pairs along M share every W tile through TMA multicast: halves the L2 -> SM traffic of the weights, which is what
-    // bounds these GEMMs (each 128-row tile otherwise re-reads all of W from L2).  148 SMs = 74 pairs.
+    // CTA pairs along M (tcgen05 cta_group::2): each CTA stages half of every W tile, which cuts the L2 -> SM fill per FLOP
+    // by a third -- the quantity that bounds the single-CTA kernel.  148 SMs = 74 pairs.  NMM_GEMM_CLUSTER=1|2 forces a mode.
     static const int force_cluster = getenv("NMM_GEMM_CLUSTER") ? atoi(getenv("NMM_GEMM_CLUSTER")) : 0;
     p.cluster = (p.m_tiles >= 2 && sms % 2 == 0) ? 2 : 1;
     if (force_cluster == 1 || force_cluster == 2) p.cluster = force_cluster;
@@ -447,7 +448,7 @@ int launch_linear_tc(const LinearArgs &a, cudaStream_t st) {
     p.block_n = choose_block_n(m_groups * p.cluster, a.N, sms);
     p.n_tiles = a.N / p.block_n;
     p.cluster_tiles = m_groups * p.n_tiles;
-    const size_t stage_bytes = (size_t)TC_A_BYTES + (size_t)p.block_n * TC_BK * 2;
+    const size_t stage_bytes = (size_t)TC_A_BYTES + (size_t)(p.block_n / p.cluster) * TC_BK * 2;     // per CTA
     int stages = (int)((TC_SMEM_BUDGET - 1024 - 512 - TC_STAGE_BYTES) / stage_bytes);
     if (stages > 8) stages = 8;
     if (stages < 2) return fail(NMM_ERR_UNSUPPORTED, "tcgen05 GEMM: tile does not fit shared memory");
@@ -467,13 +468,17 @@ int launch_linear_tc(const LinearArgs &a, cudaStream_t st) {
     const int grid = (int)(ctas < max_grid ? ctas : max_grid);
     EpiParams e = epi_params_of(a);
     const double fl = linear_flops(a), by = linear_bytes(a, 2);
+#define TC_DISPATCH(EPI)                                                                                   \
+    return p.cluster == 2 ? launch_tc_t<EPI, 2>(ta, tw, p, e, smem, grid, st, fl, by)                      \
+                          : launch_tc_t<EPI, 1>(ta, tw, p, e, smem, grid, st, fl, by)
     switch (a.epilogue) {
-        case NMM_EPI_STORE: return launch_tc_t<NMM_EPI_STORE>(ta, tw, p, e, smem, grid, st, fl, by);
-        case NMM_EPI_RESIDUAL: return launch_tc_t<NMM_EPI_RESIDUAL>(ta, tw, p, e, smem, grid, st, fl, by);
-        case NMM_EPI_GEGLU: return launch_tc_t<NMM_EPI_GEGLU>(ta, tw, p, e, smem, grid, st, fl, by);
-        case NMM_EPI_OUTPUT: return launch_tc_t<NMM_EPI_OUTPUT>(ta, tw, p, e, smem, grid, st, fl, by);
+        case NMM_EPI_STORE: TC_DISPATCH(NMM_EPI_STORE);
+        case NMM_EPI_RESIDUAL: TC_DISPATCH(NMM_EPI_RESIDUAL);
+        case NMM_EPI_GEGLU: TC_DISPATCH(NMM_EPI_GEGLU);
+        case NMM_EPI_OUTPUT: TC_DISPATCH(NMM_EPI_OUTPUT);
         default: return fail(NMM_ERR_BAD_ARG, "unknown epilogue %d", a.epilogue);
     }
+#undef TC_DISPATCH
 }
 
 }  // namespace nmm
