@@ -49,8 +49,12 @@ def _headers():
     return hs
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, trace: bool = False) -> str:
+    """trace=True builds a development variant (libneurons_mm_trace.so, -DNMM_TRACE: per-tile timestamps in the GEMM)."""
     nvcc = find_nvcc()
+    global BUILD, LIB
+    if trace:
+        BUILD, LIB = os.path.join(HERE, "build_trace"), os.path.join(HERE, "libneurons_mm_trace.so")
     os.makedirs(BUILD, exist_ok=True)
     headers = _headers()
     objs, jobs = [], []
@@ -59,7 +63,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         o = os.path.join(BUILD, src.replace(".cu", ".o"))
         objs.append(o)
         if force or not _newer(o, [s, __file__] + headers):
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            cmd = [nvcc] + NVCC_FLAGS + (["-DNMM_TRACE"] if trace else []) + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             jobs.append(cmd)
 
     def run(cmd):
@@ -86,5 +90,6 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--trace", action="store_true")
     a = ap.parse_args()
-    print(build(a.force, a.verbose))
+    print(build(a.force, a.verbose, a.trace))

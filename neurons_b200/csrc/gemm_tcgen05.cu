@@ -39,8 +39,23 @@ struct TcParams {
     int64_t m_tiles;
     int cluster;             // CTAs per tile along M: 1 (cta_group::1) or 2 (cta_group::2 pair, each CTA stages half of W)
     int64_t cluster_tiles;   // ceil(m_tiles / cluster) * n_tiles
+    unsigned long long *trace;   // NMM_TRACE builds only: per-tile timestamps of CTA 0 (development instrumentation)
+    int debug;               // NMM_GEMM_DEBUG (timing experiments only, results invalid): 1 = epilogue does nothing, 2 = no TMA loads
 };
 
+
+#ifdef NMM_TRACE
+// event slots per tile (CTA 0 only, first TRACE_TILES tiles): 0 mma:tile start, 1 mma:accumulator free, 2 mma:first stage full,
+// 3 mma:all issued, 4 prod:first load issued, 5 prod:last load issued, 6 epi(w4):before tfull wait, 7 epi:accumulator ready,
+// 8..11 epi: chunk k done, 12 epi: released, 13 epi(w8): ready, 14 epi(w8): released
+constexpr int TRACE_TILES = 48, TRACE_SLOTS = 16;
+#define TRACE(tile_no, slot)                                                                          \
+    do {                                                                                              \
+        if (p.trace != nullptr && blockIdx.x == 0 && (tile_no) < TRACE_TILES) p.trace[(tile_no) * TRACE_SLOTS + (slot)] = clock64(); \
+    } while (0)
+#else
+#define TRACE(tile_no, slot) do { } while (0)
+#endif
 
 // ---- coalesced epilogue ------------------------------------------------------------------------------------------
 // tcgen05.ld hands each lane ONE ROW of the accumulator (lane == TMEM lane == output row), so a direct store makes every
@@ -49,7 +64,8 @@ struct TcParams {
 // (128 contiguous bytes of fp32), so the residual read-modify-write and all stores are fully coalesced.
 template <int EPI>
 __device__ __forceinline__ void epi_chunk(const EpiParams &e, float *stage, int lane, int64_t row0, int col0, int width,
-                                          const uint32_t (&acc)[32], const float4 (&res)[8]) {
+                                          const uint32_t (&acc)[32], const float4 (&res)[8], int debug) {
+    (void)debug;
     // registers (row per lane) -> staging buffer
     float4 *mine = reinterpret_cast<float4 *>(stage + lane * TC_STAGE_PITCH);
 #pragma unroll
@@ -154,14 +170,19 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         // ===================== TMA producer (every CTA: its A rows, its slice of W) =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int64_t ct = cluster_id; ct < p.cluster_tiles; ct += num_clusters) {
+            int tile_no = 0;
+            for (int64_t ct = cluster_id; ct < p.cluster_tiles; ct += num_clusters, tile_no++) {
                 const int64_t m_grp = ct / p.n_tiles;
                 const int n_blk = (int)(ct - m_grp * p.n_tiles);
                 const int64_t m_blk = m_grp * CG + rank;
                 for (int kb = 0; kb < num_kb; kb++) {
                     ptx::mbar_wait(empty_bar(stage), phase ^ 1u);       // the MMAs that read this stage have retired
+                    if (kb == 0) TRACE(tile_no, 4);
+                    if (kb == num_kb - 1) TRACE(tile_no, 5);
                     const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
-                    if (CG == 1) {
+                    if (p.debug & 2) {                                  // timing experiment: MMA on whatever is in shared memory
+                        if (leader) ptx::mbar_arrive(full_bar(stage));
+                    } else if (CG == 1) {
                         ptx::mbar_expect_tx(full_bar(stage), stage_bytes);
                         ptx::tma_load_2d(&tm_a, full_bar(stage), sa, kb * TC_BK, (int32_t)(m_blk * TC_BM));
                         ptx::tma_load_2d(&tm_w, full_bar(stage), sa + TC_A_BYTES, kb * TC_BK, n_blk * p.block_n);
@@ -182,12 +203,16 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             const uint32_t idesc = ptx::umma_idesc_bf16(TC_BM * CG, (uint32_t)p.block_n);
             int stage = 0; uint32_t phase = 0;
             int as = 0; uint32_t aphase = 0;
-            for (int64_t ct = cluster_id; ct < p.cluster_tiles; ct += num_clusters) {
+            int tile_no = 0;
+            for (int64_t ct = cluster_id; ct < p.cluster_tiles; ct += num_clusters, tile_no++) {
+                TRACE(tile_no, 0);
                 ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);           // every epilogue warp (of both CTAs) drained this accumulator
+                TRACE(tile_no, 1);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.block_n);
                 for (int kb = 0; kb < num_kb; kb++) {
                     ptx::mbar_wait(full_bar(stage), phase);              // TMA bytes (of both CTAs) have landed
+                    if (kb == 0) TRACE(tile_no, 2);
                     ptx::tc_fence_after();
                     const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
                     const uint64_t a_desc = ptx::umma_smem_desc_sw128(sa);
@@ -199,6 +224,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
                 ptx::umma_commit<CG>(tfull_bar(as));                      // accumulator complete (signalled in both CTAs)
+                TRACE(tile_no, 3);
                 if (++as == 2) { as = 0; aphase ^= 1u; }
             }
         }
@@ -208,11 +234,13 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const int half = (warp - 4) >> 2;                                 // which of the quadrant's two warps
         float *stage = stage_base + (warp - 4) * 32 * TC_STAGE_PITCH;
         int as = 0; uint32_t aphase = 0;
-        for (int64_t ct = cluster_id; ct < p.cluster_tiles; ct += num_clusters) {
+        int tile_no = 0;
+        for (int64_t ct = cluster_id; ct < p.cluster_tiles; ct += num_clusters, tile_no++) {
             const int64_t m_grp = ct / p.n_tiles;
             const int n_blk = (int)(ct - m_grp * p.n_tiles);
             const int64_t m_blk = m_grp * CG + rank;
             const int64_t row0 = m_blk * TC_BM + q * 32;
+            if (warp == 4 && lane == 0) TRACE(tile_no, 6);
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.block_n);
             bool waited = false;
             auto wait_acc = [&]() {
@@ -220,9 +248,13 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     ptx::mbar_wait(tfull_bar(as), aphase);
                     ptx::tc_fence_after();
                     waited = true;
+                    if (warp == 4 && lane == 0) TRACE(tile_no, 7);
+                    if (warp == 8 && lane == 0) TRACE(tile_no, 13);
                 }
             };
-            if constexpr (EPI == NMM_EPI_OUTPUT) {
+            if (p.debug & 1) {
+                // timing experiment: drain nothing
+            } else if constexpr (EPI == NMM_EPI_OUTPUT) {
                 // y[b,c,f,p] = acc + bias[c] + x[b,c,f,p]: the output is channel-major, rows (p) are the contiguous axis
                 if (e.nchw_vec) {
                     // 32 x 32 chunk through the transpose buffer (pitch 33: conflict-free both ways); afterwards 4 lanes own
@@ -318,12 +350,15 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
                         for (int j = 0; j < 16; j++) { r[j] = lo[j]; r[16 + j] = (width > 16) ? hi[j] : 0u; }
                     }
-                    epi_chunk<EPI>(e, stage, lane, row0, col0, width, r, res);
+                    epi_chunk<EPI>(e, stage, lane, row0, col0, width, r, res, p.debug);
+                    if (warp == 4 && lane == 0 && c0 / 64 < 4) TRACE(tile_no, 8 + c0 / 64);
                 }
             }
             wait_acc();                                                   // a warp without a chunk in this tile still follows the phases
             ptx::tc_fence_before();
             __syncwarp();
+            if (warp == 4 && lane == 0) TRACE(tile_no, 12);
+            if (warp == 8 && lane == 0) TRACE(tile_no, 14);
             if (lane == 0) {
                 if (CG == 1) ptx::mbar_arrive(tempty_bar(as));
                 else ptx::mbar_arrive_cluster(tempty_bar(as) & ptx::PEER_MASK);      // the even CTA's barrier
@@ -374,6 +409,25 @@ static int make_tmap(CUtensorMap *tm, const void *ptr, int64_t rows, int64_t col
     if (r != CUDA_SUCCESS) return fail(NMM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return NMM_OK;
 }
+
+#ifdef NMM_TRACE
+static unsigned long long *g_trace_dev = nullptr;
+extern "C" __attribute__((visibility("default"))) int nmm_debug_trace_dump(const char *path) {
+    if (!g_trace_dev) return -1;
+    static unsigned long long host[TRACE_TILES * TRACE_SLOTS];
+    cudaDeviceSynchronize();
+    cudaMemcpy(host, g_trace_dev, sizeof(host), cudaMemcpyDeviceToHost);
+    FILE *f = fopen(path, "w");
+    if (!f) return -2;
+    for (int t = 0; t < TRACE_TILES; t++) {
+        for (int s = 0; s < TRACE_SLOTS; s++) fprintf(f, "%llu ", host[t * TRACE_SLOTS + s]);
+        fprintf(f, "\n");
+    }
+    fclose(f);
+    cudaMemset(g_trace_dev, 0, sizeof(host));
+    return 0;
+}
+#endif
 
 static int num_sms() {
     static int n = 0;
@@ -442,10 +496,19 @@ int launch_linear_tc(const LinearArgs &a, cudaStream_t st) {
     // CTA pairs along M (tcgen05 cta_group::2): each CTA stages half of every W tile, which cuts the L2 -> SM fill per FLOP
     // by a third -- the quantity that bounds the single-CTA kernel.  148 SMs = 74 pairs.  NMM_GEMM_CLUSTER=1|2 forces a mode.
     static const int force_cluster = getenv("NMM_GEMM_CLUSTER") ? atoi(getenv("NMM_GEMM_CLUSTER")) : 0;
+    static const int debug_flags = getenv("NMM_GEMM_DEBUG") ? atoi(getenv("NMM_GEMM_DEBUG")) : 0;
+    static const int force_bn = getenv("NMM_GEMM_BLOCK_N") ? atoi(getenv("NMM_GEMM_BLOCK_N")) : 0;
+    p.debug = debug_flags;
+    p.trace = nullptr;
+#ifdef NMM_TRACE
+    if (!g_trace_dev) { cudaMalloc(&g_trace_dev, TRACE_TILES * TRACE_SLOTS * 8); cudaMemset(g_trace_dev, 0, TRACE_TILES * TRACE_SLOTS * 8); }
+    p.trace = g_trace_dev;
+#endif
     p.cluster = (p.m_tiles >= 2 && sms % 2 == 0) ? 2 : 1;
     if (force_cluster == 1 || force_cluster == 2) p.cluster = force_cluster;
     const int64_t m_groups = ceil_div(p.m_tiles, p.cluster);
     p.block_n = choose_block_n(m_groups * p.cluster, a.N, sms);
+    if (force_bn >= 16 && force_bn <= 256 && force_bn % 16 == 0 && a.N % force_bn == 0) p.block_n = force_bn;
     p.n_tiles = a.N / p.block_n;
     p.cluster_tiles = m_groups * p.n_tiles;
     const size_t stage_bytes = (size_t)TC_A_BYTES + (size_t)(p.block_n / p.cluster) * TC_BK * 2;     // per CTA

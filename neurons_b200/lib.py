@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libneurons_mm.so")
+LIB_PATH = os.path.join(HERE, os.environ.get("NMM_LIB", "libneurons_mm.so"))     # NMM_LIB: development variants only
 
 NMM_MAX_LAYERS = 4
 NMM_MAX_ATTN = 4
