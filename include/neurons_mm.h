@@ -154,8 +154,9 @@ NMM_API int nmm_temporal_attention(const nmm_shape *s, const void *qkv, void *ct
 
 typedef enum nmm_epilogue {
     NMM_EPI_STORE = 0,          /* acc (+ bias) -> `h` (fp32 [M,N]) if non-NULL and/or `out` ([M,N] of dtype) if non-NULL */
-    NMM_EPI_RESIDUAL = 1,       /* h = acc + bias + h (fp32, in place)   motion_module.py:213-219; optional
-                                   second copy of h in `dtype` to `out` (may be NULL)                          */
+    NMM_EPI_RESIDUAL = 1,       /* out == NULL: h = acc + bias + h (fp32, in place)   motion_module.py:213-219;
+                                   out != NULL: out = acc + bias + h in `dtype`, h is only read (the last
+                                   feed-forward: its sum is consumed once, by proj_out)                        */
     NMM_EPI_GEGLU = 2,          /* out[:, j] = (acc[2j]+b[2j]) * gelu_erf(acc[2j+1]+b[2j+1]) -> out [M,N/2];
                                    W rows pre-interleaved value/gate     motion_module_new.py:516-518          */
     NMM_EPI_OUTPUT = 3          /* y[b,c,f,p] = acc + bias + x[b,c,f,p]   motion_module.py:152-156             */

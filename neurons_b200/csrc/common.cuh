@@ -147,7 +147,7 @@ inline double linear_bytes(const LinearArgs &a, int es) {
     double b = ((double)a.M * a.K + (double)a.N * a.K) * es + (a.bias ? 4.0 * a.N : 0.0);
     switch (a.epilogue) {
         case NMM_EPI_STORE: b += (a.h ? 4.0 * MN : 0.0) + (a.out ? es * MN : 0.0); break;
-        case NMM_EPI_RESIDUAL: b += 8.0 * MN + (a.out ? es * MN : 0.0); break;
+        case NMM_EPI_RESIDUAL: b += 4.0 * MN + (a.out ? es * MN : 4.0 * MN); break;
         case NMM_EPI_GEGLU: b += es * MN / 2; break;
         default: b += 2.0 * es * MN; break;      // OUTPUT: read x, write y
     }

@@ -1,7 +1,7 @@
 // Fused GEMM epilogues shared by the fp32 FMA GEMM and the tcgen05 GEMM.
 // Each call handles NC consecutive output columns of ONE row held in registers (fp32 accumulators).
 //   STORE     out = acc + bias                                         Linear            motion_module.py:145, :289-298
-//   RESIDUAL  h   = acc + bias + h   (+ optional copy in GEMM dtype)   "attn(...) + hidden_states", "ff(...) + hidden_states"  :213-219
+//   RESIDUAL  h   = acc + bias + h   (or out = acc + bias + h)         "attn(...) + hidden_states", "ff(...) + hidden_states"  :213-219
 //   GEGLU     out = (acc_v + b_v) * gelu_erf(acc_g + b_g)              GEGLU.forward     motion_module_new.py:516-518
 //   OUTPUT    y[b,c,f,p] = acc + bias + x[b,c,f,p]                     proj_out, back to NCHW, + residual      motion_module.py:152-156
 #pragma once
@@ -76,8 +76,9 @@ __device__ __forceinline__ void epilogue_apply(const EpiParams &e, int64_t row, 
             float4 r = reinterpret_cast<const float4 *>(hp)[i];
             acc[4 * i] += r.x; acc[4 * i + 1] += r.y; acc[4 * i + 2] += r.z; acc[4 * i + 3] += r.w;
         }
-        store_row<NC>(hp, acc);
+        // out == NULL: h updated in place; out != NULL: only the copy in the GEMM dtype is written (h is left untouched)
         if (e.out != nullptr) store_row<NC>(reinterpret_cast<T *>(e.out) + row * e.N + col0, acc);
+        else store_row<NC>(hp, acc);
     } else if constexpr (EPI == NMM_EPI_GEGLU) {
         float o[NC / 2];
 #pragma unroll

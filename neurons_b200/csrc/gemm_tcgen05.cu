@@ -1,17 +1,27 @@
 // bf16 GEMM on the 5th-generation tensor cores:  D[M,N] = A[M,K] . W[N,K]^T, fp32 accumulation in TMEM,
-// fused epilogues (epilogue.cuh).  This is the production kernel for every nn.Linear on the motion-module
-// path (motion_module.py:145,152,289,297,298,321; motion_module_new.py:466,516).
+// fused epilogues.  This is the production kernel for every nn.Linear on the motion-module path
+// (motion_module.py:145,152,289,297,298,321; motion_module_new.py:466,516).
 //
-// Structure (persistent, warp-specialised, one CTA per SM):
-//   warp 0      TMA producer: cp.async.bulk.tensor 2-D tiles of A (128 x 64) and W (block_n x 64), 128-byte swizzle,
-//               into a `stages`-deep shared-memory ring; completion via mbarrier complete_tx.
-//   warp 1      MMA issuer: one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=block_n, K=16)
-//               4x per stage, tcgen05.commit releases the stage / publishes the accumulator.
-//   warp 2      TMEM allocator (2 accumulator buffers of block_n fp32 columns -> epilogue overlaps the next tile).
-//   warps 4-11  epilogue: tcgen05.ld (lane == output row) -> warp-private shared-memory transpose -> bias / residual / GEGLU
-//               with fully coalesced 16-byte global accesses; the NCHW store of proj_out is coalesced along p as is.
-// Both operands are K-major in global memory ([rows, K] row-major), which is exactly how activations
-// (token-major) and nn.Linear weights ([out, in]) are laid out, so no transposes are ever materialised.
+// Structure (persistent, warp-specialised, one CTA per SM; CG = CTAs per tile along M):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2-D tiles of A (128 x 64) and of this CTA's slice of W (block_n/CG x 64),
+//               128-byte swizzle, into a `stages`-deep shared-memory ring; completion via mbarrier complete_tx.
+//               For the residual epilogue it also L2-prefetches the tile's fp32 residual rows.
+//   warp 1      MMA issuer (one thread, of the even CTA when CG == 2): tcgen05.mma.cta_group::CG.kind::f16
+//               (M = 128*CG, N = block_n, K = 16) 4x per stage; tcgen05.commit releases the stage / publishes the accumulator.
+//   warp 2      TMEM allocator (2 accumulator buffers of block_n fp32 columns -> the epilogue overlaps the next tile's MMAs).
+//   warps 4-11  epilogue, two warps per TMEM lane quadrant alternating 32-column chunks: tcgen05.ld (lane == output row) ->
+//               bias / residual / GEGLU in registers -> the lane writes its row into a swizzled shared-memory box ->
+//               ONE TMA store per chunk (cp.async.bulk.tensor, rows past M clipped by the hardware).  The residual chunk
+//               arrives by TMA load into the same box (double-buffered).  proj_out's NCHW store goes through a transpose buffer.
+// Both operands are K-major in global memory ([rows, K] row-major), which is exactly how activations (token-major) and
+// nn.Linear weights ([out, in]) are laid out, so no transposes are ever materialised.
+//
+// Measured bounds that shaped this (profiles/, scripts/micro/tmem_bw.cu, scripts/gemm_trace.py):
+//   * tcgen05.ld moves >= 245 B/clk/SM and overlaps fully with tcgen05.mma -- TMEM reads are not the limit;
+//   * a 128 x 240 tile needs 46 KB of operand fill per 480 MMA-cycles; with ~2500-cycle TMA latency under load and 3 stages the
+//     mainloop starves -> cta_group::2 halves the W fill per CTA (more stages in flight per byte of shared memory);
+//   * an epilogue that stores from registers with per-lane addressing costs ~1100-1400 issue cycles per 32-column chunk
+//     (address arithmetic + predicates + 2 warps/SMSP) -- TMA stores cut that to a few dozen instructions.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -28,9 +38,10 @@ constexpr int TC_BM = 128, TC_BK = 64;
 constexpr int TC_EPI_WARPS = 8;                           // two warps per TMEM lane quadrant, alternating column chunks
 constexpr int TC_THREADS = 128 + 32 * TC_EPI_WARPS;       // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4-11: epilogue
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;            // 16 KB per stage
-constexpr int TC_SMEM_BUDGET = 220 * 1024;
-constexpr int TC_STAGE_PITCH = 36;                        // floats per staged row: 32 columns + 4 pad (conflict-free 16-byte accesses)
-constexpr int TC_STAGE_BYTES = TC_EPI_WARPS * 32 * TC_STAGE_PITCH * 4;   // 36 KB of warp-private transpose buffers
+constexpr int TC_SMEM_MAX = 226 * 1024;                   // dynamic shared memory requested at most (227 KB is the hardware cap)
+constexpr int TC_BAR_BYTES = 1024;                        // barrier area (keeps the epilogue boxes 1024-byte aligned)
+constexpr int TC_EPI_BUF = 8192;                          // per epilogue warp: two 4 KB boxes (32 rows x 128 B)
+constexpr int TC_XPOSE_PITCH = 33;                        // proj_out transpose buffer: floats per row (conflict-free both ways)
 
 struct TcParams {
     int64_t M;
@@ -43,11 +54,10 @@ struct TcParams {
     int debug;               // NMM_GEMM_DEBUG (timing experiments only, results invalid): 1 = epilogue does nothing, 2 = no TMA loads
 };
 
-
 #ifdef NMM_TRACE
 // event slots per tile (CTA 0 only, first TRACE_TILES tiles): 0 mma:tile start, 1 mma:accumulator free, 2 mma:first stage full,
 // 3 mma:all issued, 4 prod:first load issued, 5 prod:last load issued, 6 epi(w4):before tfull wait, 7 epi:accumulator ready,
-// 8..11 epi: chunk k done, 12 epi: released, 13 epi(w8): ready, 14 epi(w8): released
+// 8..11 epi(w4): chunk k done, 12 epi(w4): released, 13 epi(w8): ready, 14 epi(w8): released
 constexpr int TRACE_TILES = 48, TRACE_SLOTS = 16;
 #define TRACE(tile_no, slot)                                                                          \
     do {                                                                                              \
@@ -57,93 +67,48 @@ constexpr int TRACE_TILES = 48, TRACE_SLOTS = 16;
 #define TRACE(tile_no, slot) do { } while (0)
 #endif
 
-// ---- coalesced epilogue ------------------------------------------------------------------------------------------
-// tcgen05.ld hands each lane ONE ROW of the accumulator (lane == TMEM lane == output row), so a direct store makes every
-// lane of a warp hit a different 128-byte line.  Each epilogue warp therefore transposes its 32 x 32 fp32 chunk through a
-// private shared-memory buffer: after the transpose 8 consecutive lanes own 32 consecutive columns of one row
-// (128 contiguous bytes of fp32), so the residual read-modify-write and all stores are fully coalesced.
-template <int EPI>
-__device__ __forceinline__ void epi_chunk(const EpiParams &e, float *stage, int lane, int64_t row0, int col0, int width,
-                                          const uint32_t (&acc)[32], const float4 (&res)[8], int debug) {
-    (void)debug;
-    // registers (row per lane) -> staging buffer
-    float4 *mine = reinterpret_cast<float4 *>(stage + lane * TC_STAGE_PITCH);
-#pragma unroll
-    for (int j = 0; j < 8; j++)
-        if (j * 4 < width)
-            mine[j] = make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]), __uint_as_float(acc[4 * j + 2]),
-                                  __uint_as_float(acc[4 * j + 3]));
-    __syncwarp();
-    const int cl = (lane & 7) * 4, rl = lane >> 3;
-    const int col = col0 + cl;
-    if (cl < width) {                                    // warp-uniform per 8-lane group; width is 16 or 32
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (e.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4 *>(e.bias + col));
-        // straight-line code (no branches inside the unrolled loops) so the 8 rows overlap: all loads, then math, then
-        // predicated stores
-        float4 v[8];
-#pragma unroll
-        for (int it = 0; it < 8; it++) v[it] = *reinterpret_cast<const float4 *>(stage + (it * 4 + rl) * TC_STAGE_PITCH + cl);
-#pragma unroll
-        for (int it = 0; it < 8; it++) {
-            v[it].x += b4.x; v[it].y += b4.y; v[it].z += b4.z; v[it].w += b4.w;
-            if constexpr (EPI == NMM_EPI_RESIDUAL) { v[it].x += res[it].x; v[it].y += res[it].y; v[it].z += res[it].z; v[it].w += res[it].w; }
-        }
-        if constexpr (EPI == NMM_EPI_GEGLU) {
-            uint32_t o[8];
-#pragma unroll
-            for (int it = 0; it < 8; it++) o[it] = pack_bf16x2(v[it].x * gelu_erf_fast(v[it].y), v[it].z * gelu_erf_fast(v[it].w));
-            bf16 *dst = reinterpret_cast<bf16 *>(e.out) + (row0 + rl) * (e.N / 2) + col / 2;
-#pragma unroll
-            for (int it = 0; it < 8; it++)
-                if (row0 + it * 4 + rl < e.M) *reinterpret_cast<uint32_t *>(dst + (int64_t)(it * 4) * (e.N / 2)) = o[it];
-        } else {
-            if (e.h != nullptr) {
-                float *dst = e.h + (row0 + rl) * e.N + col;
-#pragma unroll
-                for (int it = 0; it < 8; it++)
-                    if (row0 + it * 4 + rl < e.M) *reinterpret_cast<float4 *>(dst + (int64_t)(it * 4) * e.N) = v[it];
-            }
-            if (e.out != nullptr) {
-                bf16 *dst = reinterpret_cast<bf16 *>(e.out) + (row0 + rl) * e.N + col;
-#pragma unroll
-                for (int it = 0; it < 8; it++)
-                    if (row0 + it * 4 + rl < e.M)
-                        *reinterpret_cast<uint2 *>(dst + (int64_t)(it * 4) * e.N) =
-                            make_uint2(pack_bf16x2(v[it].x, v[it].y), pack_bf16x2(v[it].z, v[it].w));
-            }
-        }
-    }
-    __syncwarp();            // the next chunk overwrites the staging buffer
+// ---- swizzled shared-memory boxes shared with TMA ------------------------------------------------------------------------
+// fp32 box: 32 rows x 32 columns (128 B rows), CU_TENSOR_MAP_SWIZZLE_128B: 16-byte chunk j of row r lives at chunk j ^ (r & 7).
+__device__ __forceinline__ uint32_t box_f32_addr(uint32_t box, int row, int chunk) { return box + row * 128 + ((chunk ^ (row & 7)) << 4); }
+// bf16 box: 32 rows x 32 columns (64 B rows), CU_TENSOR_MAP_SWIZZLE_64B: chunk j of row r lives at chunk j ^ ((r >> 1) & 3).
+__device__ __forceinline__ uint32_t box_bf16_addr(uint32_t box, int row, int chunk) { return box + row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4); }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
 }
 
 template <int EPI, int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, TcParams p, EpiParams e) {
+linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
+                 const __grid_constant__ CUtensorMap tm_h,      // fp32 [M,N], box 32 x 32, 128-byte swizzle (residual load / h store)
+                 const __grid_constant__ CUtensorMap tm_o,      // bf16 [M,N or N/2], box 32 x 32, 64-byte swizzle (`out` store)
+                 TcParams p, EpiParams e) {
     // CG == 1: one CTA per 128 x block_n tile (tcgen05.mma.cta_group::1).
     // CG == 2: a CTA pair (cluster of 2 along M) computes a 256 x block_n tile with ONE tcgen05.mma.cta_group::2 stream issued
     //          by the even CTA: each CTA stages its own 128 rows of A and HALF of the W tile (block_n/2 rows); the tensor core
-    //          reads the two W halves from both CTAs' shared memory and each CTA's TMEM receives its own 128 x block_n
-    //          accumulator.  Per SM and k-block the shared-memory fill drops from 16 KB + block_n*128 B to 16 KB + block_n*64 B
-    //          -- the L2 -> SM ingest rate, not HBM or the tensor pipe, is what bounds the single-CTA kernel.
+    //          reads the two W halves from both CTAs' shared memory and each CTA's TMEM receives its own 128 x block_n accumulator.
     extern __shared__ unsigned char smem_raw[];
     const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B tiles need 1024-byte alignment
     const uint32_t b_rows = (uint32_t)p.block_n / CG;                           // W rows staged by this CTA
     const uint32_t stage_bytes = TC_A_BYTES + b_rows * TC_BK * 2;
     const uint32_t bar_base = smem_base + (uint32_t)p.stages * stage_bytes;
-    // barriers: full[stages], empty[stages], tmem_full[2], tmem_empty[2]; then the TMEM base address
+    // barrier area: full[stages], empty[stages], tmem_full[2], tmem_empty[2], TMEM base address; +512: per-epilogue-warp load barriers
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
     auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * p.stages + s); };
     auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * p.stages + 2 + s); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * p.stages + 4);
-    // warp-private transpose buffers of the epilogue warps (generic pointer: plain ld/st.shared)
-    float *stage_base = reinterpret_cast<float *>(smem_raw + (smem_base - ptx::smem_u32(smem_raw)) + (size_t)p.stages * stage_bytes + 256);
+    auto load_bar = [&](int ew, int b) { return bar_base + 512u + 8u * (ew * 2 + b); };
+    const uint32_t epi_base = bar_base + TC_BAR_BYTES;                          // 8 x 8 KB, 1024-byte aligned
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = (p.K + TC_BK - 1) / TC_BK;
     // Tile schedule: a cluster walks (m_group, n_blk) pairs; CTA `rank` of the cluster owns m-block m_group*CG + rank.
-    // Both CTAs of a pair run the same number of iterations (a phantom m-block past the end is all zero-fill + masked).
+    // Both CTAs of a pair run the same number of iterations (a phantom m-block past the end is all zero-fill + clipped).
     const uint32_t rank = CG > 1 ? ptx::cluster_ctarank() : 0u;
     const bool leader = rank == 0;
     const int64_t cluster_id = blockIdx.x / CG, num_clusters = gridDim.x / CG;
@@ -151,11 +116,14 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tm_a);
         ptx::prefetch_tensormap(&tm_w);
+        if (EPI == NMM_EPI_RESIDUAL || e.h != nullptr) ptx::prefetch_tensormap(&tm_h);
+        if (e.out != nullptr) ptx::prefetch_tensormap(&tm_o);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.stages; s++) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
         // tmem_empty collects one arrive per epilogue warp of every CTA of the pair (it lives in the MMA-issuing CTA)
         for (int s = 0; s < 2; s++) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), TC_EPI_WARPS * CG); }
+        for (int w = 0; w < TC_EPI_WARPS; w++) { ptx::mbar_init(load_bar(w, 0), 1); ptx::mbar_init(load_bar(w, 1), 1); }
         ptx::fence_mbar_init();
     }
     if (warp == 2) ptx::tmem_alloc<CG>(tmem_slot, (uint32_t)p.tmem_cols);
@@ -175,6 +143,13 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 const int64_t m_grp = ct / p.n_tiles;
                 const int n_blk = (int)(ct - m_grp * p.n_tiles);
                 const int64_t m_blk = m_grp * CG + rank;
+                if constexpr (EPI == NMM_EPI_RESIDUAL) {
+                    // the epilogue will read-modify-write this tile's fp32 residual rows: pull them into L2 now
+                    if (!(p.debug & 2))
+                        for (int c0 = 0; c0 < p.block_n; c0 += 32)
+                            for (int r0 = 0; r0 < TC_BM; r0 += 32)
+                                ptx::tma_prefetch_l2_2d(&tm_h, n_blk * p.block_n + c0, (int32_t)(m_blk * TC_BM + r0));
+                }
                 for (int kb = 0; kb < num_kb; kb++) {
                     ptx::mbar_wait(empty_bar(stage), phase ^ 1u);       // the MMAs that read this stage have retired
                     if (kb == 0) TRACE(tile_no, 4);
@@ -230,9 +205,12 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         }
     } else if (warp >= 4) {
         // ===================== epilogue (every CTA: its own 128 TMEM lanes) =====================
+        const int ew = warp - 4;
         const int q = warp & 3;                                           // TMEM lane quadrant this warp may access
-        const int half = (warp - 4) >> 2;                                 // which of the quadrant's two warps
-        float *stage = stage_base + (warp - 4) * 32 * TC_STAGE_PITCH;
+        const int half = ew >> 2;                                         // which of the quadrant's two warps
+        const uint32_t box0 = epi_base + (uint32_t)ew * TC_EPI_BUF, box1 = box0 + 4096u;
+        float *xpose = reinterpret_cast<float *>(smem_raw + (box0 - ptx::smem_u32(smem_raw)));      // proj_out transpose buffer
+        uint32_t lph0 = 0u, lph1 = 0u;                                    // phases of this warp's two residual-load barriers
         int as = 0; uint32_t aphase = 0;
         int tile_no = 0;
         for (int64_t ct = cluster_id; ct < p.cluster_tiles; ct += num_clusters, tile_no++) {
@@ -240,8 +218,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             const int n_blk = (int)(ct - m_grp * p.n_tiles);
             const int64_t m_blk = m_grp * CG + rank;
             const int64_t row0 = m_blk * TC_BM + q * 32;
-            if (warp == 4 && lane == 0) TRACE(tile_no, 6);
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.block_n);
+            if (warp == 4 && lane == 0) TRACE(tile_no, 6);
             bool waited = false;
             auto wait_acc = [&]() {
                 if (!waited) {
@@ -268,42 +246,32 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     const bf16 *xrow = reinterpret_cast<const bf16 *>(e.x) + bb * e.xsb + ff * e.xsf + pp;
                     bf16 *yrow = reinterpret_cast<bf16 *>(e.y) + bb * e.ysb + ff * e.ysf + pp;
                     for (int c0 = half * 32; c0 < p.block_n; c0 += 64) {
-                        const int width = min(32, p.block_n - c0);
                         const int col0 = n_blk * p.block_n + c0;
                         uint4 xin[4];
 #pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            const int c = cq + 8 * j;
-                            xin[j] = (rows_ok && c < width) ? __ldg(reinterpret_cast<const uint4 *>(xrow + (int64_t)(col0 + c) * e.xsc))
-                                                            : make_uint4(0u, 0u, 0u, 0u);
-                        }
+                        for (int j = 0; j < 4; j++)
+                            xin[j] = rows_ok ? __ldg(reinterpret_cast<const uint4 *>(xrow + (int64_t)(col0 + cq + 8 * j) * e.xsc)) : make_uint4(0u, 0u, 0u, 0u);
                         wait_acc();
-                        uint32_t lo[16], hi[16];
-                        ptx::tmem_ld16(t_row + (uint32_t)c0, lo);
-                        if (width > 16) ptx::tmem_ld16(t_row + (uint32_t)c0 + 16u, hi);
+                        uint32_t r[32];
+                        ptx::tmem_ld32(t_row + (uint32_t)c0, r);
                         ptx::tmem_ld_wait();
-                        uint32_t *srow = reinterpret_cast<uint32_t *>(stage) + lane * 33;
+                        uint32_t *srow = reinterpret_cast<uint32_t *>(xpose) + lane * TC_XPOSE_PITCH;
 #pragma unroll
-                        for (int j = 0; j < 16; j++) srow[j] = lo[j];
-                        if (width > 16) {
-#pragma unroll
-                            for (int j = 0; j < 16; j++) srow[16 + j] = hi[j];
-                        }
+                        for (int j = 0; j < 32; j++) srow[j] = r[j];
                         __syncwarp();
                         if (rows_ok) {
 #pragma unroll
                             for (int j = 0; j < 4; j++) {
                                 const int c = cq + 8 * j;
-                                if (c < width) {
-                                    const float bias = e.bias ? __ldg(e.bias + col0 + c) : 0.f;
-                                    const float *sc = stage + (8 * rg) * 33 + c;
-                                    const uint32_t xw[4] = {xin[j].x, xin[j].y, xin[j].z, xin[j].w};
-                                    uint32_t o[4];
+                                const float bias = e.bias ? __ldg(e.bias + col0 + c) : 0.f;
+                                const float *sc = xpose + (8 * rg) * TC_XPOSE_PITCH + c;
+                                const uint32_t xw[4] = {xin[j].x, xin[j].y, xin[j].z, xin[j].w};
+                                uint32_t o[4];
 #pragma unroll
-                                    for (int i = 0; i < 4; i++)
-                                        o[i] = pack_bf16x2(sc[(2 * i) * 33] + bias + bf16_lo(xw[i]), sc[(2 * i + 1) * 33] + bias + bf16_hi(xw[i]));
-                                    *reinterpret_cast<uint4 *>(yrow + (int64_t)(col0 + c) * e.ysc) = make_uint4(o[0], o[1], o[2], o[3]);
-                                }
+                                for (int i = 0; i < 4; i++)
+                                    o[i] = pack_bf16x2(sc[(2 * i) * TC_XPOSE_PITCH] + bias + bf16_lo(xw[i]),
+                                                       sc[(2 * i + 1) * TC_XPOSE_PITCH] + bias + bf16_hi(xw[i]));
+                                *reinterpret_cast<uint4 *>(yrow + (int64_t)(col0 + c) * e.ysc) = make_uint4(o[0], o[1], o[2], o[3]);
                             }
                         }
                         __syncwarp();
@@ -312,59 +280,138 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     // generic (ragged P / unaligned) path: one position per lane, 2-byte accesses coalesced along p
                     wait_acc();
                     const int64_t row = row0 + lane;
-                    for (int c0 = half * 16; c0 < p.block_n; c0 += 32) {
-                        uint32_t r[16];
-                        ptx::tmem_ld16(t_row + (uint32_t)c0, r);
-                        ptx::tmem_ld_wait();
-                        const int col0 = n_blk * p.block_n + c0;
-                        if (row < p.M && col0 < p.N) {
-                            float acc[16];
+                    for (int c0 = half * 32; c0 < p.block_n; c0 += 64) {
 #pragma unroll
-                            for (int j = 0; j < 16; j++) acc[j] = __uint_as_float(r[j]);
-                            epilogue_apply<EPI, bf16, 16>(e, row, col0, acc);
+                        for (int hc = 0; hc < 2; hc++) {
+                            uint32_t r[16];
+                            ptx::tmem_ld16(t_row + (uint32_t)(c0 + 16 * hc), r);
+                            ptx::tmem_ld_wait();
+                            const int col0 = n_blk * p.block_n + c0 + 16 * hc;
+                            if (row < p.M && col0 < p.N) {
+                                float acc[16];
+#pragma unroll
+                                for (int j = 0; j < 16; j++) acc[j] = __uint_as_float(r[j]);
+                                epilogue_apply<EPI, bf16, 16>(e, row, col0, acc);
+                            }
                         }
                     }
                 }
-            } else {
-                const int cl = (lane & 7) * 4, rl = lane >> 3;
-                for (int c0 = half * 32; c0 < p.block_n; c0 += 64) {
-                    const int width = min(32, p.block_n - c0);
+            } else if constexpr (EPI == NMM_EPI_GEGLU) {
+                // 64 accumulator columns (32 value/gate pairs) per chunk -> 32 bf16 outputs per row -> one 32 x 32 bf16 box
+                for (int c0 = half * 64; c0 < p.block_n; c0 += 128) {
                     const int col0 = n_blk * p.block_n + c0;
-                    float4 res[8];
-                    if constexpr (EPI == NMM_EPI_RESIDUAL) {
-                        // prefetch the residual rows in the coalesced layout before waiting on the accumulator
+                    wait_acc();
+                    uint32_t o[16];
 #pragma unroll
-                        for (int it = 0; it < 8; it++) {
-                            const int64_t row = row0 + it * 4 + rl;
-                            res[it] = (cl < width && row < e.M) ? *reinterpret_cast<const float4 *>(e.h + row * e.N + col0 + cl)
-                                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int hc = 0; hc < 2; hc++) {
+                        uint32_t r[32];
+                        ptx::tmem_ld32(t_row + (uint32_t)(c0 + 32 * hc), r);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (e.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4 *>(e.bias + col0 + 32 * hc) + j);
+                            const float v0 = __uint_as_float(r[4 * j]) + b4.x, g0 = __uint_as_float(r[4 * j + 1]) + b4.y;
+                            const float v1 = __uint_as_float(r[4 * j + 2]) + b4.z, g1 = __uint_as_float(r[4 * j + 3]) + b4.w;
+                            o[8 * hc + j] = pack_bf16x2(v0 * gelu_erf_fast(g0), v1 * gelu_erf_fast(g1));
+                        }
+                    }
+                    if (lane == 0) ptx::bulk_wait_read0();                // the box of the previous chunk has been read
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 4; j++) sts128(box_bf16_addr(box0, lane, j), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                    ptx::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) { ptx::tma_store_2d(&tm_o, box0, col0 / 2, (int32_t)row0); ptx::bulk_commit(); }
+                    if (warp == 4 && lane == 0 && c0 / 128 < 4) TRACE(tile_no, 8 + c0 / 128);
+                }
+            } else {
+                // STORE / RESIDUAL: 32-column chunks.  RESIDUAL: the fp32 residual chunk is TMA-loaded into box (k & 1) one chunk
+                // ahead, summed in place and TMA-stored from the same box (or written as bf16 into the box when only `out` is wanted).
+                const int first = half * 32;
+                int k = 0;
+                if constexpr (EPI == NMM_EPI_RESIDUAL) {
+                    if (lane == 0 && first < p.block_n) {
+                        ptx::bulk_wait_read0();
+                        ptx::mbar_expect_tx(load_bar(ew, 0), 4096u);
+                        ptx::tma_load_2d(&tm_h, load_bar(ew, 0), box0, n_blk * p.block_n + first, (int32_t)row0);
+                    }
+                }
+                for (int c0 = first; c0 < p.block_n; c0 += 64, k++) {
+                    const int col0 = n_blk * p.block_n + c0;
+                    const uint32_t box = (EPI == NMM_EPI_RESIDUAL && (k & 1)) ? box1 : box0;
+                    if constexpr (EPI == NMM_EPI_RESIDUAL) {
+                        if (lane == 0 && c0 + 64 < p.block_n) {           // next chunk's residual into the other box
+                            ptx::bulk_wait_read0();                       // ... once the store that used it has been read
+                            const int nb = (k + 1) & 1;
+                            ptx::mbar_expect_tx(load_bar(ew, nb), 4096u);
+                            ptx::tma_load_2d(&tm_h, load_bar(ew, nb), nb ? box1 : box0, col0 + 64, (int32_t)row0);
                         }
                     }
                     wait_acc();
                     uint32_t r[32];
-                    {
-                        uint32_t lo[16], hi[16];
-                        ptx::tmem_ld16(t_row + (uint32_t)c0, lo);
-                        if (width > 16) ptx::tmem_ld16(t_row + (uint32_t)c0 + 16u, hi);
-                        ptx::tmem_ld_wait();
+                    ptx::tmem_ld32(t_row + (uint32_t)c0, r);
+                    ptx::tmem_ld_wait();
+                    float v[32];
 #pragma unroll
-                        for (int j = 0; j < 16; j++) { r[j] = lo[j]; r[16 + j] = (width > 16) ? hi[j] : 0u; }
+                    for (int j = 0; j < 8; j++) {
+                        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (e.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4 *>(e.bias + col0) + j);
+                        v[4 * j] = __uint_as_float(r[4 * j]) + b4.x; v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b4.y;
+                        v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b4.z; v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b4.w;
                     }
-                    epi_chunk<EPI>(e, stage, lane, row0, col0, width, r, res, p.debug);
-                    if (warp == 4 && lane == 0 && c0 / 64 < 4) TRACE(tile_no, 8 + c0 / 64);
+                    if constexpr (EPI == NMM_EPI_RESIDUAL) {
+                        if (k & 1) { ptx::mbar_wait(load_bar(ew, 1), lph1); lph1 ^= 1u; }
+                        else { ptx::mbar_wait(load_bar(ew, 0), lph0); lph0 ^= 1u; }
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            const float4 h4 = lds128(box_f32_addr(box, lane, j));
+                            v[4 * j] += h4.x; v[4 * j + 1] += h4.y; v[4 * j + 2] += h4.z; v[4 * j + 3] += h4.w;
+                        }
+                        __syncwarp();                                     // every lane has read its row before the box is overwritten
+                    } else {
+                        if (lane == 0) ptx::bulk_wait_read0();            // the previous chunk's boxes have been read
+                        __syncwarp();
+                    }
+                    const bool want_o = e.out != nullptr;
+                    // RESIDUAL with `out`: only the bf16 copy is produced (the last feed-forward: h itself is dead afterwards)
+                    const bool want_h = e.h != nullptr && !(EPI == NMM_EPI_RESIDUAL && want_o);
+                    // fp32 result -> `box` (128-byte rows); bf16 result -> box1 for STORE, the (already consumed) same box for RESIDUAL
+                    const uint32_t obox = (EPI == NMM_EPI_RESIDUAL) ? box : box1;
+                    if (want_h) {
+#pragma unroll
+                        for (int j = 0; j < 8; j++)
+                            sts128(box_f32_addr(box, lane, j), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+                                   __float_as_uint(v[4 * j + 3]));
+                    }
+                    if (want_o) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            sts128(box_bf16_addr(obox, lane, j), pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                   pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+                    }
+                    ptx::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (want_h) ptx::tma_store_2d(&tm_h, box, col0, (int32_t)row0);
+                        if (want_o) ptx::tma_store_2d(&tm_o, obox, col0, (int32_t)row0);
+                        ptx::bulk_commit();
+                    }
+                    if (warp == 4 && lane == 0 && k < 4) TRACE(tile_no, 8 + k);
                 }
             }
             wait_acc();                                                   // a warp without a chunk in this tile still follows the phases
-            ptx::tc_fence_before();
-            __syncwarp();
             if (warp == 4 && lane == 0) TRACE(tile_no, 12);
             if (warp == 8 && lane == 0) TRACE(tile_no, 14);
+            ptx::tc_fence_before();
+            __syncwarp();
             if (lane == 0) {
                 if (CG == 1) ptx::mbar_arrive(tempty_bar(as));
                 else ptx::mbar_arrive_cluster(tempty_bar(as) & ptx::PEER_MASK);      // the even CTA's barrier
             }
             if (++as == 2) { as = 0; aphase ^= 1u; }
         }
+        if (lane == 0) ptx::bulk_wait_all();                              // all TMA stores of this warp have completed
     }
     __syncwarp();                                    // lanes 1-31 of the single-thread roles rejoin lane 0 before the aligned barrier
     ptx::tc_fence_before();
@@ -394,18 +441,18 @@ static EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
-// [rows, cols] row-major bf16 with leading dimension ld (elements); box = box_rows x 64 columns, 128-byte swizzle.
-static int make_tmap(CUtensorMap *tm, const void *ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+// [rows, cols] row-major tensor with leading dimension ld (elements); box = box_rows x box_cols.
+static int make_tmap(CUtensorMap *tm, const void *ptr, CUtensorMapDataType dt, int esize, int64_t rows, int64_t cols, int64_t ld,
+                     int box_rows, int box_cols, CUtensorMapSwizzle swz) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return fail(NMM_ERR_DEVICE, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
-    if (!aligned(ptr, 16) || (ld * 2) % 16 != 0) return fail(NMM_ERR_BAD_ARG, "TMA operand must be 16-byte aligned with a 16-byte multiple row pitch");
+    if (!aligned(ptr, 16) || (ld * esize) % 16 != 0) return fail(NMM_ERR_BAD_ARG, "TMA operand must be 16-byte aligned with a 16-byte multiple row pitch");
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * esize};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = fn(tm, dt, 2, const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(NMM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return NMM_OK;
 }
@@ -438,11 +485,12 @@ static int num_sms() {
     return n;
 }
 
-// N tile: a multiple of 16 in [16, 256] that divides N; the largest one that still yields >= 2 waves of tiles,
-// otherwise the largest that yields >= 1 wave, otherwise the smallest divisor >= 64 (small-M levels of the UNet).
-static int choose_block_n(int64_t m_tiles, int N, int sms) {
+// N tile: a multiple of `gran` (32; 64 for GEGLU, whose chunks are 64 accumulator columns) in [gran, 256] that divides N;
+// the largest one that still yields >= 2 waves of tiles, otherwise the largest that yields >= 1 wave, otherwise the smallest
+// divisor >= 64 (small-M levels of the UNet).  Returns 0 when no such divisor exists.
+static int choose_block_n(int64_t m_tiles, int N, int sms, int gran) {
     int best2 = 0, best1 = 0, smallest = 0;
-    for (int bn = 256; bn >= 16; bn -= 16) {
+    for (int bn = 256; bn >= gran; bn -= gran) {
         if (N % bn) continue;
         const int64_t tiles = m_tiles * (N / bn);
         if (!best2 && tiles >= 2 * sms) best2 = bn;
@@ -455,12 +503,12 @@ static int choose_block_n(int64_t m_tiles, int N, int sms) {
 }
 
 template <int EPI, int CG>
-static int launch_tc_t(const CUtensorMap &ta, const CUtensorMap &tw, const TcParams &p, const EpiParams &e, size_t smem, int grid,
-                       cudaStream_t st, double flops, double bytes) {
+static int launch_tc_t(const CUtensorMap &ta, const CUtensorMap &tw, const CUtensorMap &th, const CUtensorMap &to, const TcParams &p,
+                       const EpiParams &e, size_t smem, int grid, cudaStream_t st, double flops, double bytes) {
     auto kern = linear_tc_kernel<EPI, CG>;
     static bool attr_set = false;     // per template instantiation
     if (!attr_set) {
-        NMM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET + 2048));
+        NMM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX));
         attr_set = true;
     }
     cudaLaunchConfig_t cfg;
@@ -478,7 +526,7 @@ static int launch_tc_t(const CUtensorMap &ta, const CUtensorMap &tw, const TcPar
     cfg.numAttrs = CG > 1 ? 1 : 0;
     {
         ProfScope prof(K_LINEAR_TC, st, flops, bytes);
-        cudaError_t le = cudaLaunchKernelEx(&cfg, kern, ta, tw, p, e);
+        cudaError_t le = cudaLaunchKernelEx(&cfg, kern, ta, tw, th, to, p, e);
         if (le != cudaSuccess) return fail(NMM_ERR_CUDA, "cudaLaunchKernelEx(linear_tc_kernel) failed: %s", cudaGetErrorString(le));
     }
     NMM_LAUNCHED("linear_tc_kernel");
@@ -486,15 +534,16 @@ static int launch_tc_t(const CUtensorMap &ta, const CUtensorMap &tw, const TcPar
 }
 
 int launch_linear_tc(const LinearArgs &a, cudaStream_t st) {
-    if (a.N % 16 != 0) return fail(NMM_ERR_UNSUPPORTED, "tcgen05 GEMM needs N %% 16 == 0 (N=%d)", a.N);
+    if (a.N % 32 != 0) return fail(NMM_ERR_UNSUPPORTED, "tcgen05 GEMM needs N %% 32 == 0 (N=%d)", a.N);
+    if (a.epilogue == NMM_EPI_GEGLU && a.N % 64 != 0) return fail(NMM_ERR_UNSUPPORTED, "GEGLU epilogue needs N %% 64 == 0 (N=%d)", a.N);
     if (a.K % 8 != 0) return fail(NMM_ERR_UNSUPPORTED, "tcgen05 GEMM needs K %% 8 == 0 (K=%d)", a.K);
     if (a.M <= 0) return NMM_OK;
     TcParams p;
     p.M = a.M; p.N = a.N; p.K = a.K;
     p.m_tiles = ceil_div(a.M, TC_BM);
     const int sms = num_sms();
-    // CTA pairs along M (tcgen05 cta_group::2): each CTA stages half of every W tile, which cuts the L2 -> SM fill per FLOP
-    // by a third -- the quantity that bounds the single-CTA kernel.  148 SMs = 74 pairs.  NMM_GEMM_CLUSTER=1|2 forces a mode.
+    // CTA pairs along M (tcgen05 cta_group::2): each CTA stages half of every W tile, so more k-blocks fit in flight per byte of
+    // shared memory -- what the TMA-latency-bound mainloop needs.  148 SMs = 74 pairs.  NMM_GEMM_CLUSTER=1|2 forces a mode.
     static const int force_cluster = getenv("NMM_GEMM_CLUSTER") ? atoi(getenv("NMM_GEMM_CLUSTER")) : 0;
     static const int debug_flags = getenv("NMM_GEMM_DEBUG") ? atoi(getenv("NMM_GEMM_DEBUG")) : 0;
     static const int force_bn = getenv("NMM_GEMM_BLOCK_N") ? atoi(getenv("NMM_GEMM_BLOCK_N")) : 0;
@@ -507,33 +556,47 @@ int launch_linear_tc(const LinearArgs &a, cudaStream_t st) {
     p.cluster = (p.m_tiles >= 2 && sms % 2 == 0) ? 2 : 1;
     if (force_cluster == 1 || force_cluster == 2) p.cluster = force_cluster;
     const int64_t m_groups = ceil_div(p.m_tiles, p.cluster);
-    p.block_n = choose_block_n(m_groups * p.cluster, a.N, sms);
-    if (force_bn >= 16 && force_bn <= 256 && force_bn % 16 == 0 && a.N % force_bn == 0) p.block_n = force_bn;
+    const int gran = a.epilogue == NMM_EPI_GEGLU ? 64 : 32;
+    p.block_n = choose_block_n(m_groups * p.cluster, a.N, sms, gran);
+    if (force_bn >= gran && force_bn <= 256 && force_bn % gran == 0 && a.N % force_bn == 0) p.block_n = force_bn;
+    if (p.block_n == 0) return fail(NMM_ERR_UNSUPPORTED, "tcgen05 GEMM: no N tile for N=%d", a.N);
     p.n_tiles = a.N / p.block_n;
     p.cluster_tiles = m_groups * p.n_tiles;
     const size_t stage_bytes = (size_t)TC_A_BYTES + (size_t)(p.block_n / p.cluster) * TC_BK * 2;     // per CTA
-    int stages = (int)((TC_SMEM_BUDGET - 1024 - 512 - TC_STAGE_BYTES) / stage_bytes);
+    const size_t fixed = 1024 /*alignment slack*/ + TC_BAR_BYTES + (size_t)TC_EPI_WARPS * TC_EPI_BUF;
+    int stages = (int)((TC_SMEM_MAX - fixed) / stage_bytes);
     if (stages > 8) stages = 8;
     if (stages < 2) return fail(NMM_ERR_UNSUPPORTED, "tcgen05 GEMM: tile does not fit shared memory");
     p.stages = stages;
     int cols = 32;
     while (cols < 2 * p.block_n) cols <<= 1;
     p.tmem_cols = cols;
-    // alignment slack + operand ring + 256 B of barriers + transpose buffers
-    const size_t smem = 1024 + (size_t)stages * stage_bytes + 256 + TC_STAGE_BYTES;
-    CUtensorMap ta, tw;
-    int rc = make_tmap(&ta, a.A, a.M, a.K, a.K, TC_BM);
+    const size_t smem = fixed + (size_t)stages * stage_bytes;
+    CUtensorMap ta, tw, th, to;
+    int rc = make_tmap(&ta, a.A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.M, a.K, a.K, TC_BM, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != NMM_OK) return rc;
-    rc = make_tmap(&tw, a.W, a.N, a.K, a.K, p.block_n / p.cluster);      // each CTA of a cluster fetches its slice of the W tile
+    // each CTA of a pair fetches its slice of the W tile
+    rc = make_tmap(&tw, a.W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.N, a.K, a.K, p.block_n / p.cluster, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != NMM_OK) return rc;
+    memset(&th, 0, sizeof(th));
+    memset(&to, 0, sizeof(to));
+    if (a.h != nullptr && a.epilogue != NMM_EPI_OUTPUT && a.epilogue != NMM_EPI_GEGLU) {
+        rc = make_tmap(&th, a.h, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.M, a.N, a.N, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc != NMM_OK) return rc;
+    }
+    if (a.out != nullptr && a.epilogue != NMM_EPI_OUTPUT) {
+        const int64_t ncols = a.epilogue == NMM_EPI_GEGLU ? a.N / 2 : a.N;
+        rc = make_tmap(&to, a.out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.M, ncols, ncols, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+        if (rc != NMM_OK) return rc;
+    }
     const int64_t ctas = p.cluster_tiles * p.cluster;
     const int max_grid = sms / p.cluster * p.cluster;
     const int grid = (int)(ctas < max_grid ? ctas : max_grid);
     EpiParams e = epi_params_of(a);
     const double fl = linear_flops(a), by = linear_bytes(a, 2);
 #define TC_DISPATCH(EPI)                                                                                   \
-    return p.cluster == 2 ? launch_tc_t<EPI, 2>(ta, tw, p, e, smem, grid, st, fl, by)                      \
-                          : launch_tc_t<EPI, 1>(ta, tw, p, e, smem, grid, st, fl, by)
+    return p.cluster == 2 ? launch_tc_t<EPI, 2>(ta, tw, th, to, p, e, smem, grid, st, fl, by)              \
+                          : launch_tc_t<EPI, 1>(ta, tw, th, to, p, e, smem, grid, st, fl, by)
     switch (a.epilogue) {
         case NMM_EPI_STORE: TC_DISPATCH(NMM_EPI_STORE);
         case NMM_EPI_RESIDUAL: TC_DISPATCH(NMM_EPI_RESIDUAL);

@@ -35,7 +35,7 @@ def main():
     L.nmm_debug_trace_dump(path.encode())
     rows = [[int(v) for v in ln.split()] for ln in open(path)]
     t0 = min(v for r in rows for v in r if v)
-    names = ["mma:start", "mma:accfree", "mma:1stfull", "mma:issued", "tma:first", "tma:last", "epi:wait", "epi:ready", "c0", "c1", "c2", "c3",
+    names = ["mma:start", "mma:accfree", "mma:1stfull", "mma:issued", "tma:first", "tma:last", "epi:wait", "epi:ready", "c0:ldtm", "c0:sts", "c0:lds", "c0:stg",
              "epi:rel", "epi8:ready", "epi8:rel"]
     print(which, C, "cycles relative to first event;", " ".join(f"{n:>11s}" for n in names))
     for i, r in enumerate(rows[:20]):

@@ -79,7 +79,7 @@ def main():
             ("qkv      C->3C store", lambda: ops.linear(act, w_qkv, None, nlib.EPI_STORE), 2.0 * M * C * 3 * C, M * C * es * 4),
             ("to_out   C->C  residual", lambda: ops.linear(act, w_cc, bias, nlib.EPI_RESIDUAL, h=h, want_out=False), 2.0 * M * C * C, M * C * (es + 8)),
             ("geglu    C->8C", lambda: ops.linear(act, w_1, bias8, nlib.EPI_GEGLU), 2.0 * M * C * 8 * C, M * C * es * 5),
-            ("ff_out   4C->C residual+copy", lambda: ops.linear(act4, w_2, bias, nlib.EPI_RESIDUAL, h=h, want_out=True), 2.0 * M * 4 * C * C, M * C * (4 * es + 8 + es)),
+            ("ff_out   4C->C residual+copy", lambda: ops.linear(act4, w_2, bias, nlib.EPI_RESIDUAL, h=h, want_out=True), 2.0 * M * 4 * C * C, M * C * (4 * es + 4 + es)),
             ("proj_out C->C  nchw+x", lambda: ops.linear(act, w_cc, bias, nlib.EPI_OUTPUT, cfg=cfg, x=x), 2.0 * M * C * C, M * C * es * 3),
         ]
         for name, fn, flops, byts in stages:

@@ -138,12 +138,16 @@ def test_linear_store_and_residual(M, N, K, dtype):
     # no-bias STORE (QKV projection)
     out2 = ops.linear(Ad, Wd, None, nlib.EPI_STORE)
     assert _maxabs(out2, ref - bias.double()) <= out_tol
-    # RESIDUAL: h = acc + bias + h, in place
+    # RESIDUAL: h = acc + bias + h, in place ...
     g = torch.Generator().manual_seed(11)
     h0 = torch.randn(M, N, generator=g)
     h = h0.to(DEV).clone()
-    out3 = ops.linear(Ad, Wd, bd, nlib.EPI_RESIDUAL, h=h, want_out=True)
+    assert ops.linear(Ad, Wd, bd, nlib.EPI_RESIDUAL, h=h, want_out=False) is None
     assert _maxabs(h, ref + h0.double()) <= _gemm_tol(dtype, ref, K)
+    # ... or, with `out`, the sum goes to out only and h is left untouched
+    h = h0.to(DEV).clone()
+    out3 = ops.linear(Ad, Wd, bd, nlib.EPI_RESIDUAL, h=h, want_out=True)
+    assert torch.equal(h.cpu(), h0)
     assert _maxabs(out3, ref + h0.double()) <= (out_tol if dtype == torch.float32 else 2 ** -8 * 1.01 * (ref + h0.double()).abs().max().item())
 
 
