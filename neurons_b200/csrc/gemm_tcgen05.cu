@@ -485,21 +485,34 @@ static int num_sms() {
     return n;
 }
 
-// N tile: a multiple of `gran` (32; 64 for GEGLU, whose chunks are 64 accumulator columns) in [gran, 256] that divides N;
-// the largest one that still yields >= 2 waves of tiles, otherwise the largest that yields >= 1 wave, otherwise the smallest
-// divisor >= 64 (small-M levels of the UNet).  Returns 0 when no such divisor exists.
-static int choose_block_n(int64_t m_tiles, int N, int sms, int gran) {
-    int best2 = 0, best1 = 0, smallest = 0;
-    for (int bn = 256; bn >= gran; bn -= gran) {
-        if (N % bn) continue;
-        const int64_t tiles = m_tiles * (N / bn);
-        if (!best2 && tiles >= 2 * sms) best2 = bn;
-        if (!best1 && tiles >= sms) best1 = bn;
-        if (bn >= 64 || smallest == 0) smallest = bn;
+// Tile selection.  Candidates: N tile = a multiple of `gran` (32; 64 for GEGLU, whose chunks are 64 accumulator columns) in
+// [gran, 256] that divides N, x CTAs per tile CG in {1, 2}.  Cost model (cycles, from the measurements in the file header):
+//   per k-block   max( MMA: 2*bn ,  operand fill: (16 KB + bn*128/CG bytes) / 64 B/clk of per-SM TMA ingest )
+//   per tile      num_kb * that + a fixed per-tile overhead (barrier round trips, epilogue tail)
+//   whole GEMM    ceil(cluster_tiles / resident clusters) * per tile            (wave quantisation)
+// The per-SM ingest of ~64 B/clk is why only (CG = 2, bn = 256) can keep the tensor pipe fully fed, and why small tiles lose.
+struct TilePlan { int block_n, cluster; };
+static TilePlan choose_tiles(int64_t m_tiles, int N, int K, int sms, int gran, int force_cluster, int force_bn) {
+    TilePlan best = {0, 1};
+    double best_cost = 1e300;
+    const int num_kb = (K + TC_BK - 1) / TC_BK;
+    for (int cg = 1; cg <= 2; cg++) {
+        if (force_cluster && cg != force_cluster) continue;
+        if (cg == 2 && (m_tiles < 2 || sms % 2 != 0)) continue;
+        const int64_t m_groups = ceil_div(m_tiles, cg);
+        for (int bn = 256; bn >= gran; bn -= gran) {
+            if (N % bn) continue;
+            if (force_bn && bn != force_bn) continue;
+            const double mma = 2.0 * bn, fill = (16384.0 + bn * 128.0 / cg) / 64.0;
+            // + per-tile overhead; a CTA pair also pays for keeping two CTAs in lock-step (measured: pairs lose for K = 320)
+            const double per_tile = num_kb * (mma > fill ? mma : fill) + 1500.0 + 4.0 * bn + (cg == 2 ? 1500.0 : 0.0);
+            const int64_t cluster_tiles = m_groups * (N / bn);
+            const int64_t resident = sms / cg;
+            const double cost = (double)ceil_div(cluster_tiles, resident) * per_tile;
+            if (cost < best_cost) { best_cost = cost; best.block_n = bn; best.cluster = cg; }
+        }
     }
-    if (best2) return best2;
-    if (best1) return best1;
-    return smallest;
+    return best;
 }
 
 template <int EPI, int CG>
@@ -542,24 +555,23 @@ int launch_linear_tc(const LinearArgs &a, cudaStream_t st) {
     p.M = a.M; p.N = a.N; p.K = a.K;
     p.m_tiles = ceil_div(a.M, TC_BM);
     const int sms = num_sms();
-    // CTA pairs along M (tcgen05 cta_group::2): each CTA stages half of every W tile, so more k-blocks fit in flight per byte of
-    // shared memory -- what the TMA-latency-bound mainloop needs.  148 SMs = 74 pairs.  NMM_GEMM_CLUSTER=1|2 forces a mode.
-    static const int force_cluster = getenv("NMM_GEMM_CLUSTER") ? atoi(getenv("NMM_GEMM_CLUSTER")) : 0;
-    static const int debug_flags = getenv("NMM_GEMM_DEBUG") ? atoi(getenv("NMM_GEMM_DEBUG")) : 0;
-    static const int force_bn = getenv("NMM_GEMM_BLOCK_N") ? atoi(getenv("NMM_GEMM_BLOCK_N")) : 0;
+    // NMM_GEMM_CLUSTER=1|2 / NMM_GEMM_BLOCK_N force a tiling (development).
+    const int force_cluster = getenv("NMM_GEMM_CLUSTER") ? atoi(getenv("NMM_GEMM_CLUSTER")) : 0;
+    const int debug_flags = getenv("NMM_GEMM_DEBUG") ? atoi(getenv("NMM_GEMM_DEBUG")) : 0;
+    const int force_bn = getenv("NMM_GEMM_BLOCK_N") ? atoi(getenv("NMM_GEMM_BLOCK_N")) : 0;
     p.debug = debug_flags;
     p.trace = nullptr;
 #ifdef NMM_TRACE
     if (!g_trace_dev) { cudaMalloc(&g_trace_dev, TRACE_TILES * TRACE_SLOTS * 8); cudaMemset(g_trace_dev, 0, TRACE_TILES * TRACE_SLOTS * 8); }
     p.trace = g_trace_dev;
 #endif
-    p.cluster = (p.m_tiles >= 2 && sms % 2 == 0) ? 2 : 1;
-    if (force_cluster == 1 || force_cluster == 2) p.cluster = force_cluster;
-    const int64_t m_groups = ceil_div(p.m_tiles, p.cluster);
     const int gran = a.epilogue == NMM_EPI_GEGLU ? 64 : 32;
-    p.block_n = choose_block_n(m_groups * p.cluster, a.N, sms, gran);
-    if (force_bn >= gran && force_bn <= 256 && force_bn % gran == 0 && a.N % force_bn == 0) p.block_n = force_bn;
-    if (p.block_n == 0) return fail(NMM_ERR_UNSUPPORTED, "tcgen05 GEMM: no N tile for N=%d", a.N);
+    const TilePlan plan = choose_tiles(p.m_tiles, a.N, a.K, sms, gran, (force_cluster == 1 || force_cluster == 2) ? force_cluster : 0,
+                                       (force_bn >= gran && force_bn <= 256 && force_bn % gran == 0 && a.N % force_bn == 0) ? force_bn : 0);
+    if (plan.block_n == 0) return fail(NMM_ERR_UNSUPPORTED, "tcgen05 GEMM: no N tile for N=%d", a.N);
+    p.block_n = plan.block_n;
+    p.cluster = plan.cluster;
+    const int64_t m_groups = ceil_div(p.m_tiles, p.cluster);
     p.n_tiles = a.N / p.block_n;
     p.cluster_tiles = m_groups * p.n_tiles;
     const size_t stage_bytes = (size_t)TC_A_BYTES + (size_t)(p.block_n / p.cluster) * TC_BK * 2;     // per CTA
