@@ -11,6 +11,8 @@
 // contiguous PB*3C-element run), keeps the F scores in registers, does the softmax in fp32 and writes its
 // context row back through shared memory so the global stores are 16-byte coalesced as well.
 // HBM-bound: bytes = 4*N*C*s (read qkv, write ctx), flops = 4*N*F*C.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace nmm {
@@ -211,10 +213,230 @@ static int launch_attn_t(const Geo &g, const T *qkv, T *ctx, cudaStream_t st) {
     return NMM_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Tensor-core variant for the shapes NEURONS actually runs (bf16, F = 8 or 16 frames, d_h % 8 == 0).
+// One warp per (position, head) problem: S = Q K^T and O = P V on mma.sync (m16n8k16 / m16n8k8 bf16 -> fp32).  These are
+// F x F x d_h problems (8 x 8 x 40 ...): far below the 64-row minimum of tcgen05, so the warp-level MMA is the right tool;
+// it replaces ~1500 scalar instructions per thread of the SIMT kernel with ~20 MMAs + ~25 ldmatrix per warp.
+// Staging, head-group tiling and the coalesced write-back are shared with the SIMT kernel above.
+// The probabilities are fed to the second MMA as a bf16 hi + lo pair (two MMAs), so P carries ~16 mantissa bits.
+// ------------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldsm_x1(uint32_t addr, uint32_t &r0) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x1.shared.b16 {%0}, [%1];" : "=r"(r0) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t addr, uint32_t &r0, uint32_t &r1) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x1_t(uint32_t addr, uint32_t &r0) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x1.trans.shared.b16 {%0}, [%1];" : "=r"(r0) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2_t(uint32_t addr, uint32_t &r0, uint32_t &r1) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ void mma_k16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma_k8(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5}, {%6}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(b0));
+}
+// split two fp32 into bf16 hi and bf16 lo (residual) pairs
+__device__ __forceinline__ void split_bf16x2(float x, float y, uint32_t &hi, uint32_t &lo) {
+    hi = pack_bf16x2(x, y);
+    lo = pack_bf16x2(x - bf16_lo(hi), y - bf16_hi(hi));
+}
+
+template <int F>      // 8 or 16
+__global__ void __launch_bounds__(256) temporal_attention_mma_kernel(const bf16 *__restrict__ qkv, bf16 *__restrict__ ctx, int B, int P,
+                                                                     int C, int heads, int PB, int HB, float scale_log2e) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    bf16 *sm = reinterpret_cast<bf16 *>(smem_raw);
+    constexpr int PAD = 8;
+    constexpr int NT = F / 8;                   // key tiles of 8
+    const int dh = C / heads;
+    const int W = HB * dh;
+    const int c_off = blockIdx.y * W;
+    const int pitch = 3 * W + PAD;              // elements; (pitch*2/4) % 32 == 4 for W % 64 == 0: ldmatrix rows hit distinct banks
+    const int tiles_per_img = (P + PB - 1) / PB;
+    const int b = blockIdx.x / tiles_per_img;
+    const int p0 = (blockIdx.x % tiles_per_img) * PB;
+    const int npos = min(PB, P - p0);
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
+    const int rows = F * npos;
+
+    // ---- stage q|k|v rows with cp.async (same layout as the SIMT kernel) ------------------------------------------------
+    {
+        const int vec_per_seg = W / 8;
+        for (int r = warp; r < rows; r += nwarps) {
+            const int f = r / npos, pl = r - f * npos;
+            const bf16 *src_row = qkv + ((int64_t)(b * F + f) * P + p0 + pl) * (3 * C) + c_off;
+            const uint32_t dst_row = (uint32_t)__cvta_generic_to_shared(sm + (pl * F + f) * pitch);
+#pragma unroll
+            for (int seg = 0; seg < 3; seg++)
+                for (int v = lane; v < vec_per_seg; v += 32)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_row + (uint32_t)((seg * W + v * 8) * 2)), "l"(src_row + seg * C + v * 8)
+                                 : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+
+    // ---- one warp per (position, head) ------------------------------------------------------------------------------------
+    const uint32_t sm_u32 = (uint32_t)__cvta_generic_to_shared(sm);
+    const int lrow = lane & 7, lmat = lane >> 3;          // ldmatrix: lanes 8m..8m+7 address the rows of matrix m
+    const int crow = lane >> 2, ccol = (lane & 3) * 2;     // accumulator fragment: row crow (and crow + 8), columns ccol, ccol + 1
+    for (int prob = warp; prob < npos * HB; prob += nwarps) {
+        const int pl = prob / HB, hd = prob - pl * HB;
+        const uint32_t qb = sm_u32 + (uint32_t)(((pl * F) * pitch + hd * dh) * 2);     // row f at + f * pitch * 2 bytes
+        const uint32_t kb = qb + (uint32_t)(W * 2), vb = qb + (uint32_t)(2 * W * 2);
+        const uint32_t rstride = (uint32_t)(pitch * 2);
+        float s[NT][4];
+#pragma unroll
+        for (int j = 0; j < NT; j++) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; }
+        // S = Q K^T over d in steps of 16 (+ one step of 8 when d_h % 16 == 8)
+        int k0 = 0;
+        for (; k0 + 16 <= dh; k0 += 16) {
+            uint32_t a0, a1 = 0u, a2, a3 = 0u;
+            if constexpr (F == 16) {
+                // matrices: (rows 0-7, k0), (rows 8-15, k0), (rows 0-7, k0+8), (rows 8-15, k0+8)
+                ldsm_x4(qb + (uint32_t)(lrow + 8 * (lmat & 1)) * rstride + (uint32_t)((k0 + 8 * (lmat >> 1)) * 2), a0, a1, a2, a3);
+            } else {
+                ldsm_x2(qb + (uint32_t)lrow * rstride + (uint32_t)((k0 + 8 * (lmat & 1)) * 2), a0, a2);   // rows 8-15 are padding
+            }
+#pragma unroll
+            for (int j = 0; j < NT; j++) {
+                uint32_t b0, b1;
+                ldsm_x2(kb + (uint32_t)(8 * j + lrow) * rstride + (uint32_t)((k0 + 8 * (lmat & 1)) * 2), b0, b1);
+                mma_k16(s[j], a0, a1, a2, a3, b0, b1);
+            }
+        }
+        if (k0 < dh) {      // 8 remaining columns
+            uint32_t a0, a1 = 0u;
+            if constexpr (F == 16) ldsm_x2(qb + (uint32_t)(lrow + 8 * (lmat & 1)) * rstride + (uint32_t)(k0 * 2), a0, a1);
+            else ldsm_x1(qb + (uint32_t)lrow * rstride + (uint32_t)(k0 * 2), a0);
+#pragma unroll
+            for (int j = 0; j < NT; j++) {
+                uint32_t b0;
+                ldsm_x1(kb + (uint32_t)(8 * j + lrow) * rstride + (uint32_t)(k0 * 2), b0);
+                mma_k8(s[j], a0, a1, b0);
+            }
+        }
+        // softmax over the keys of row crow (regs 0,1) and row crow + 8 (regs 2,3; F == 16 only), fp32, base-2 exponentials
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < NT; j++) { mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1])); mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3])); }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < NT; j++) {
+            s[j][0] = exp2f((s[j][0] - mx0) * scale_log2e); s[j][1] = exp2f((s[j][1] - mx0) * scale_log2e);
+            sum0 += s[j][0] + s[j][1];
+            if constexpr (F == 16) {
+                s[j][2] = exp2f((s[j][2] - mx1) * scale_log2e); s[j][3] = exp2f((s[j][3] - mx1) * scale_log2e);
+                sum1 += s[j][2] + s[j][3];
+            }
+        }
+        sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+        sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+        const float inv0 = 1.0f / sum0, inv1 = (F == 16) ? 1.0f / sum1 : 0.f;
+        // P as the A operand of the second MMA (accumulator layout == A layout for these shapes), bf16 hi + lo
+        uint32_t ph[4] = {0u, 0u, 0u, 0u}, pl_[4] = {0u, 0u, 0u, 0u};
+        split_bf16x2(s[0][0] * inv0, s[0][1] * inv0, ph[0], pl_[0]);                       // row crow, keys 0-7
+        if constexpr (F == 16) {
+            split_bf16x2(s[0][2] * inv1, s[0][3] * inv1, ph[1], pl_[1]);                   // row crow + 8, keys 0-7
+            split_bf16x2(s[1][0] * inv0, s[1][1] * inv0, ph[2], pl_[2]);                   // row crow, keys 8-15
+            split_bf16x2(s[1][2] * inv1, s[1][3] * inv1, ph[3], pl_[3]);                   // row crow + 8, keys 8-15
+        }
+        __syncwarp();                                   // all of this warp's reads of the q rows are done: reuse them for O
+        // O = P V, 8 output columns per MMA
+        for (int n0 = 0; n0 < dh; n0 += 8) {
+            float o[4] = {0.f, 0.f, 0.f, 0.f};
+            if constexpr (F == 16) {
+                uint32_t b0, b1;
+                ldsm_x2_t(vb + (uint32_t)(lrow + 8 * (lmat & 1)) * rstride + (uint32_t)(n0 * 2), b0, b1);   // keys 0-7, keys 8-15
+                mma_k16(o, ph[0], ph[1], ph[2], ph[3], b0, b1);
+                mma_k16(o, pl_[0], pl_[1], pl_[2], pl_[3], b0, b1);
+            } else {
+                uint32_t b0;
+                ldsm_x1_t(vb + (uint32_t)lrow * rstride + (uint32_t)(n0 * 2), b0);
+                mma_k8(o, ph[0], 0u, b0);
+                mma_k8(o, pl_[0], 0u, b0);
+            }
+            // context row crow (and crow + 8) into the q slot of this problem
+            bf16 *orow = sm + ((pl * F) + crow) * pitch + hd * dh + n0 + ccol;
+            *reinterpret_cast<uint32_t *>(orow) = pack_bf16x2(o[0], o[1]);
+            if constexpr (F == 16) *reinterpret_cast<uint32_t *>(orow + 8 * pitch) = pack_bf16x2(o[2], o[3]);
+        }
+    }
+    __syncthreads();
+
+    // ---- write ctx rows: one warp per row, 16-byte coalesced stores --------------------------------------------------------
+    for (int r = warp; r < rows; r += nwarps) {
+        const int f2 = r / npos, pl2 = r - f2 * npos;
+        const bf16 *src_row = sm + (pl2 * F + f2) * pitch;
+        bf16 *dst_row = ctx + ((int64_t)(b * F + f2) * P + p0 + pl2) * C + c_off;
+        for (int v = lane; v < W / 8; v += 32)
+            *reinterpret_cast<uint4 *>(dst_row + v * 8) = *reinterpret_cast<const uint4 *>(src_row + v * 8);
+    }
+}
+
+// bf16, F in {8, 16}, d_h % 8 == 0, 16-byte aligned: the tensor-core kernel.  Returns -100 when the shape is not eligible.
+static int launch_attn_mma(const Geo &g, const bf16 *qkv, bf16 *ctx, cudaStream_t st) {
+    if (!(g.F == 8 || g.F == 16) || g.dh % 8 != 0 || g.dh < 8) return -100;
+    // head group: W = HB * dh as close to 320 channels as the head count allows and a multiple of 64 (bank-conflict-free rows)
+    int HB = 0;
+    for (int hb = g.heads; hb >= 1; hb--)
+        if (g.heads % hb == 0 && (hb * g.dh) % 64 == 0 && hb * g.dh <= 320) { HB = hb; break; }
+    if (HB == 0) return -100;
+    const int W = HB * g.dh;
+    const size_t row_bytes = (size_t)(3 * W + 8) * 2;
+    int PB = (int)((40 * 1024) / (g.F * row_bytes));                  // <= 40 KB per CTA: ~5 CTAs per SM
+    if (PB < 1) PB = 1;
+    if (PB > g.P) PB = g.P;
+    const size_t smem = (size_t)PB * g.F * row_bytes;
+    if (smem > 200 * 1024) return -100;
+    int warps = PB * HB;                                               // one problem per warp per pass, at most 8 warps
+    if (warps > 8) warps = 8;
+    const int64_t blocks = (int64_t)g.B * ceil_div(g.P, PB);
+    if (blocks > 0x7fffffff) return -100;
+    const dim3 grid((unsigned)blocks, (unsigned)(g.heads / HB));
+    const float scale_log2e = (1.0f / sqrtf((float)g.dh)) * 1.4426950408889634f;
+#define ATTN_MMA(FF)                                                                                                     \
+    do {                                                                                                                 \
+        auto kern = temporal_attention_mma_kernel<FF>;                                                                   \
+        static bool attr_set = false;                                                                                    \
+        if (!attr_set) {                                                                                                 \
+            NMM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));            \
+            attr_set = true;                                                                                             \
+        }                                                                                                                \
+        ProfScope prof(K_ATTENTION, st, 4.0 * g.N * g.F * g.C, 4.0 * g.N * g.C * 2);                                      \
+        kern<<<grid, warps * 32, smem, st>>>(qkv, ctx, g.B, g.P, g.C, g.heads, PB, HB, scale_log2e);                      \
+    } while (0)
+    if (g.F == 8) ATTN_MMA(8);
+    else ATTN_MMA(16);
+#undef ATTN_MMA
+    NMM_LAUNCHED("temporal_attention_mma_kernel");
+    return NMM_OK;
+}
+
 int launch_temporal_attention(const Geo &g, const void *qkv, void *ctx, cudaStream_t st) {
     if (g.F > NMM_MAX_FRAMES) return fail(NMM_ERR_UNSUPPORTED, "frames %d > %d", g.F, NMM_MAX_FRAMES);
     const bool al = aligned(qkv, 16) && aligned(ctx, 16);
     if (g.dtype == NMM_BF16) {
+        if (al && !getenv("NMM_ATTN_SIMT")) {
+            const int rc = launch_attn_mma(g, (const bf16 *)qkv, (bf16 *)ctx, st);
+            if (rc != -100) return rc;
+        }
         if (g.dh % 8 == 0 && al) return launch_attn_t<bf16, 8>(g, (const bf16 *)qkv, (bf16 *)ctx, st);
         return launch_attn_t<bf16, 1>(g, (const bf16 *)qkv, (bf16 *)ctx, st);
     }

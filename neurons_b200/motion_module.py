@@ -203,11 +203,17 @@ class _Engine:
         self.key = None
         self.packed = None
         self.cfg = None
+        self.tensors = None      # name -> tensor, collected once (module.to() / .data updates keep the same objects)
+        self.shape_cache = {}    # (shape, strides, dtype) -> (nmm_shape struct, workspace bytes)
 
     def get(self, module: nn.Module, x: torch.Tensor):
-        tensors = _param_tensors(module)
-        key = (x.dtype, x.device) + tuple((t.data_ptr(), t.dtype) for t in tensors.values())
+        if self.tensors is None:
+            self.tensors = _param_tensors(module)
+        tensors = self.tensors
+        key = (x.dtype, x.device) + tuple([t.data_ptr() for t in tensors.values()])
         if key != self.key:
+            self.tensors = tensors = _param_tensors(module)      # re-scan the tree (parameters may have been replaced)
+            key = (x.dtype, x.device) + tuple([t.data_ptr() for t in tensors.values()])
             self.cfg = config_of(module)
             dev_tensors = {}
             for k, t in tensors.items():
@@ -235,9 +241,11 @@ def motion_forward(module: nn.Module, input_tensor: torch.Tensor) -> torch.Tenso
         raise RuntimeError("neurons_b200: the motion module runs on CUDA (sm_100) only; there is no CPU path")
     if torch.is_grad_enabled() and (input_tensor.requires_grad or any(p.requires_grad for p in module.parameters())):
         raise RuntimeError("neurons_b200: the motion-module op is inference-only; call it under torch.no_grad()")
-    cfg, packed = _engine_of(module).get(module, input_tensor)
-    return torch.ops.neurons_mm.forward(input_tensor, packed, cfg.channels, cfg.heads, cfg.layers, cfg.attn_blocks,
-                                        cfg.pos_enc, cfg.max_len)
+    eng = _engine_of(module)
+    cfg, packed = eng.get(module, input_tensor)
+    # same computation as torch.ops.neurons_mm.forward (ops.forward_packed is its CUDA implementation), called directly with this
+    # module's shape cache so the per-call host work is one dict lookup, two allocations and one C call
+    return ops.forward_packed(input_tensor, packed, cfg, shape_cache=eng.shape_cache)
 
 
 def invalidate(model: nn.Module) -> int:
@@ -248,6 +256,7 @@ def invalidate(model: nn.Module) -> int:
         if eng is not None:
             eng.key = None
             eng.packed = None
+            eng.tensors = None
             n += 1
     return n
 

@@ -158,19 +158,31 @@ def workspace_bytes(shape: _lib.Shape) -> int:
     return n.value
 
 
-def forward_packed(x: torch.Tensor, packed: torch.Tensor, cfg: ModuleConfig, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """y = module(x) through nmm_forward.  Returns logical [B,C,F,H,W] over [B,F,C,H,W] storage."""
+def forward_packed(x: torch.Tensor, packed: torch.Tensor, cfg: ModuleConfig, out: Optional[torch.Tensor] = None,
+                   shape_cache: Optional[dict] = None) -> torch.Tensor:
+    """y = module(x) through nmm_forward.  Returns logical [B,C,F,H,W] over [B,F,C,H,W] storage.
+    `shape_cache` (optional dict owned by the caller) memoises the validated nmm_shape + workspace size per input geometry."""
     _require_cuda(x, "x")
     _require_cuda(packed, "packed")
     x = _dense_hw(x)
     B, Cc, F, H, W = x.shape
     if out is None:
         out = torch.empty((B, F, Cc, H, W), dtype=x.dtype, device=x.device).permute(0, 2, 1, 3, 4)
-    shape = make_shape(cfg, x, out)
-    _lib.check(_lib.load().nmm_validate(C.byref(shape)))
-    ws_bytes = workspace_bytes(shape)
+    key = (x.shape, x.stride(), out.stride(), x.dtype) if shape_cache is not None else None
+    hit = shape_cache.get(key) if shape_cache is not None else None
+    if hit is None:
+        shape = make_shape(cfg, x, out)
+        _lib.check(_lib.load().nmm_validate(C.byref(shape)))
+        hit = (shape, workspace_bytes(shape))
+        if shape_cache is not None:
+            shape_cache[key] = hit
+    shape, ws_bytes = hit
     ws, ws_ptr = _aligned_ws(ws_bytes, x.device)
-    with torch.cuda.device(x.device):
+    if x.device.index != torch.cuda.current_device():
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().nmm_forward(C.byref(shape), x.data_ptr(), out.data_ptr(), packed.data_ptr(), ws_ptr,
+                                               ws_bytes, _stream_ptr(x.device)))
+    else:
         _lib.check(_lib.load().nmm_forward(C.byref(shape), x.data_ptr(), out.data_ptr(), packed.data_ptr(), ws_ptr,
                                            ws_bytes, _stream_ptr(x.device)))
     return out

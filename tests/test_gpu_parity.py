@@ -256,6 +256,22 @@ def test_module_properties_full_size(dtype):
         assert torch.equal(m(x, None, None), x)
 
 
+def test_custom_op_matches_module_call():
+    # torch.ops.neurons_mm.forward (CUDA dispatch key) is the same computation the module's forward reaches directly
+    fx, cfg, params, x = helpers.load_golden("c64_f16_4x4_a1_view")
+    m = helpers.mirror_module(cfg, params, DEV, torch.bfloat16)
+    xb = x.to(DEV, torch.bfloat16)
+    with torch.no_grad():
+        y_mod = m(xb, None, None)
+        packed = ops.pack_params(_cfg(cfg), {k: v for k, v in nb.motion_module._param_tensors(m).items()
+                                             if not k.endswith("pos_encoder.pe")} |
+                                 {k: v[0] for k, v in nb.motion_module._param_tensors(m).items() if k.endswith("pos_encoder.pe")},
+                                 torch.bfloat16, torch.device(DEV))
+        y_op = torch.ops.neurons_mm.forward(xb, packed, cfg.channels, cfg.heads, cfg.layers, cfg.attn_blocks, cfg.pos_enc, cfg.max_len)
+    assert torch.equal(y_mod, y_op)
+    assert _maxabs(y_op, fx["out_ref_bf16in"]) <= helpers.TOL_BF16
+
+
 def test_lora_style_inplace_update_needs_invalidate():
     fx, cfg, params, x = helpers.load_golden("c64_f16_4x4_a1_view")
     m = helpers.mirror_module(cfg, params, DEV)
