@@ -138,6 +138,8 @@ static int device_check() {
 // (GEGLU: packed row 2j = value row j, packed row 2j+1 = gate row j + 4C; motion_module_new.py:516-517 chunk(2)).
 template <typename TS, typename TD>
 __global__ void convert_rows_kernel(const TS *__restrict__ src, TD *__restrict__ dst, int64_t rows, int64_t cols, int64_t half) {
+    pdl_wait();                    // PDL: the previous kernel has completed (no-op without the launch attribute)
+    pdl_launch_dependents();       // let the next kernel's launch + prologue overlap this kernel
     const int64_t total = rows * cols;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / cols, c = i - r * cols;
@@ -153,10 +155,10 @@ int launch_convert_rows(const void *src, int src_dtype, void *dst, int dst_dtype
     const int threads = 256;
     const int blocks = (int)std::min<int64_t>(ceil_div(total, threads), 148 * 16);
     ProfScope prof(K_PACK, st, 0.0, (double)total * (dtype_size(src_dtype) + dtype_size(dst_dtype)));
-    if (src_dtype == NMM_F32 && dst_dtype == NMM_F32) convert_rows_kernel<float, float><<<blocks, threads, 0, st>>>((const float *)src, (float *)dst, rows, cols, half);
-    else if (src_dtype == NMM_F32 && dst_dtype == NMM_BF16) convert_rows_kernel<float, bf16><<<blocks, threads, 0, st>>>((const float *)src, (bf16 *)dst, rows, cols, half);
-    else if (src_dtype == NMM_BF16 && dst_dtype == NMM_F32) convert_rows_kernel<bf16, float><<<blocks, threads, 0, st>>>((const bf16 *)src, (float *)dst, rows, cols, half);
-    else if (src_dtype == NMM_BF16 && dst_dtype == NMM_BF16) convert_rows_kernel<bf16, bf16><<<blocks, threads, 0, st>>>((const bf16 *)src, (bf16 *)dst, rows, cols, half);
+    if (src_dtype == NMM_F32 && dst_dtype == NMM_F32) launch_pdl(convert_rows_kernel<float, float>, blocks, threads, 0, st, (const float *)src, (float *)dst, rows, cols, half);
+    else if (src_dtype == NMM_F32 && dst_dtype == NMM_BF16) launch_pdl(convert_rows_kernel<float, bf16>, blocks, threads, 0, st, (const float *)src, (bf16 *)dst, rows, cols, half);
+    else if (src_dtype == NMM_BF16 && dst_dtype == NMM_F32) launch_pdl(convert_rows_kernel<bf16, float>, blocks, threads, 0, st, (const bf16 *)src, (float *)dst, rows, cols, half);
+    else if (src_dtype == NMM_BF16 && dst_dtype == NMM_BF16) launch_pdl(convert_rows_kernel<bf16, bf16>, blocks, threads, 0, st, (const bf16 *)src, (bf16 *)dst, rows, cols, half);
     else return fail(NMM_ERR_BAD_ARG, "unknown parameter dtype");
     NMM_LAUNCHED("convert_rows_kernel");
     return NMM_OK;
@@ -164,6 +166,8 @@ int launch_convert_rows(const void *src, int src_dtype, void *dst, int dst_dtype
 
 // Sinusoidal table when the caller does not hand over the module's own `pe` buffer (motion_module.py:234-238).
 __global__ void make_pe_kernel(float *__restrict__ pe, int max_len, int C) {
+    pdl_wait();                    // PDL: the previous kernel has completed (no-op without the launch attribute)
+    pdl_launch_dependents();       // let the next kernel's launch + prologue overlap this kernel
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= max_len * C) return;
     const int t = i / C, c = i % C;
@@ -266,7 +270,7 @@ int nmm_pack_params(const nmm_shape *s, const nmm_params *src, void *packed, siz
                 if (ap.pe) PACK(ap.pe, ao.pe, NMM_F32, (int64_t)g.max_len, C, 0);
                 else {
                     const int n = g.max_len * g.C;
-                    make_pe_kernel<<<(n + 255) / 256, 256, 0, st>>>((float *)(base + ao.pe), g.max_len, g.C);
+                    launch_pdl(make_pe_kernel, (n + 255) / 256, 256, 0, st, (float *)(base + ao.pe), g.max_len, g.C);
                     NMM_LAUNCHED("make_pe_kernel");
                 }
             }

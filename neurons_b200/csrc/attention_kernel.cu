@@ -50,6 +50,8 @@ template <typename T> struct RowVec<T, 1> {
 template <typename T, int VEC, int FMAX>
 __global__ void __launch_bounds__(256) temporal_attention_kernel(const T *__restrict__ qkv, T *__restrict__ ctx, int B, int F,
                                                                  int P, int C, int heads, int PB, int HB, float scale) {
+    pdl_wait();                    // PDL: the previous kernel has completed (no-op without the launch attribute)
+    pdl_launch_dependents();       // let the next kernel's launch + prologue overlap this kernel
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *sm = reinterpret_cast<T *>(smem_raw);
     constexpr int PAD = 16 / (int)sizeof(T);
@@ -203,7 +205,7 @@ static int launch_attn_t(const Geo &g, const T *qkv, T *ctx, cudaStream_t st) {
             attr_set = true;                                                                                             \
         }                                                                                                                \
         ProfScope prof(K_ATTENTION, st, 4.0 * g.N * g.F * g.C, 4.0 * g.N * g.C * sizeof(T));                             \
-        kern<<<grid, threads, smem, st>>>(qkv, ctx, g.B, g.F, g.P, g.C, g.heads, PB, HB, scale);                          \
+        launch_pdl(kern, grid, threads, smem, st, qkv, ctx, g.B, g.F, g.P, g.C, g.heads, PB, HB, scale);                          \
     } while (0)
     if (g.F <= 8) ATTN_CASE(8);
     else if (g.F <= 16) ATTN_CASE(16);
@@ -256,6 +258,8 @@ __device__ __forceinline__ void split_bf16x2(float x, float y, uint32_t &hi, uin
 template <int F>      // 8 or 16
 __global__ void __launch_bounds__(256) temporal_attention_mma_kernel(const bf16 *__restrict__ qkv, bf16 *__restrict__ ctx, int B, int P,
                                                                      int C, int heads, int PB, int HB, float scale_log2e) {
+    pdl_wait();                    // PDL: the previous kernel has completed (no-op without the launch attribute)
+    pdl_launch_dependents();       // let the next kernel's launch + prologue overlap this kernel
     extern __shared__ __align__(16) unsigned char smem_raw[];
     bf16 *sm = reinterpret_cast<bf16 *>(smem_raw);
     constexpr int PAD = 8;
@@ -420,7 +424,7 @@ static int launch_attn_mma(const Geo &g, const bf16 *qkv, bf16 *ctx, cudaStream_
             attr_set = true;                                                                                             \
         }                                                                                                                \
         ProfScope prof(K_ATTENTION, st, 4.0 * g.N * g.F * g.C, 4.0 * g.N * g.C * 2);                                      \
-        kern<<<grid, warps * 32, smem, st>>>(qkv, ctx, g.B, g.P, g.C, g.heads, PB, HB, scale_log2e);                      \
+        launch_pdl(kern, grid, warps * 32, smem, st, qkv, ctx, g.B, g.P, g.C, g.heads, PB, HB, scale_log2e);                      \
     } while (0)
     if (g.F == 8) ATTN_MMA(8);
     else ATTN_MMA(16);

@@ -14,6 +14,8 @@ constexpr int SG_BM = 128, SG_BN = 64, SG_BK = 16, SG_THREADS = 256;
 template <int EPI>
 __global__ void __launch_bounds__(SG_THREADS) linear_simt_kernel(const float *__restrict__ A, const float *__restrict__ W,
                                                                  int K, EpiParams e) {
+    pdl_wait();                    // PDL: the previous kernel has completed (no-op without the launch attribute)
+    pdl_launch_dependents();       // let the next kernel's launch + prologue overlap this kernel
     __shared__ __align__(16) float As[SG_BK][SG_BM + 4];
     __shared__ __align__(16) float Bs[SG_BK][SG_BN + 4];
     const int tid = threadIdx.x;
@@ -76,10 +78,10 @@ int launch_linear_simt(const LinearArgs &a, cudaStream_t st) {
     const float *A = (const float *)a.A, *W = (const float *)a.W;
     ProfScope prof(K_LINEAR_SIMT, st, linear_flops(a), linear_bytes(a, 4));
     switch (a.epilogue) {
-        case NMM_EPI_STORE: linear_simt_kernel<NMM_EPI_STORE><<<grid, block, 0, st>>>(A, W, a.K, e); break;
-        case NMM_EPI_RESIDUAL: linear_simt_kernel<NMM_EPI_RESIDUAL><<<grid, block, 0, st>>>(A, W, a.K, e); break;
-        case NMM_EPI_GEGLU: linear_simt_kernel<NMM_EPI_GEGLU><<<grid, block, 0, st>>>(A, W, a.K, e); break;
-        case NMM_EPI_OUTPUT: linear_simt_kernel<NMM_EPI_OUTPUT><<<grid, block, 0, st>>>(A, W, a.K, e); break;
+        case NMM_EPI_STORE: launch_pdl(linear_simt_kernel<NMM_EPI_STORE>, grid, block, 0, st, A, W, a.K, e); break;
+        case NMM_EPI_RESIDUAL: launch_pdl(linear_simt_kernel<NMM_EPI_RESIDUAL>, grid, block, 0, st, A, W, a.K, e); break;
+        case NMM_EPI_GEGLU: launch_pdl(linear_simt_kernel<NMM_EPI_GEGLU>, grid, block, 0, st, A, W, a.K, e); break;
+        case NMM_EPI_OUTPUT: launch_pdl(linear_simt_kernel<NMM_EPI_OUTPUT>, grid, block, 0, st, A, W, a.K, e); break;
         default: return fail(NMM_ERR_BAD_ARG, "unknown epilogue %d", a.epilogue);
     }
     NMM_LAUNCHED("linear_simt_kernel");

@@ -127,6 +127,10 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         ptx::fence_mbar_init();
     }
     if (warp == 2) ptx::tmem_alloc<CG>(tmem_slot, (uint32_t)p.tmem_cols);
+    // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail;
+    // from here on this kernel touches memory the previous kernel produced.
+    pdl_wait();
+    pdl_launch_dependents();
     ptx::tc_fence_before();
     if (CG > 1) ptx::cluster_sync();                 // the peer's barriers must exist before any remote arrive / complete_tx
     else __syncthreads();
@@ -530,13 +534,15 @@ static int launch_tc_t(const CUtensorMap &ta, const CUtensorMap &tw, const CUten
     cfg.blockDim = dim3(TC_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)CG;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = (unsigned)CG;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = CG > 1 ? 1 : 0;
+    cfg.numAttrs = CG > 1 ? 2 : 1;
     {
         ProfScope prof(K_LINEAR_TC, st, flops, bytes);
         cudaError_t le = cudaLaunchKernelEx(&cfg, kern, ta, tw, th, to, p, e);

@@ -50,6 +50,8 @@ template <typename T, bool VEC>
 __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const T *__restrict__ x, double *__restrict__ partial,
                                                               int C, int F, int P, int splits, int64_t sb, int64_t sc,
                                                               int64_t sf) {
+    pdl_wait();                    // PDL: the previous kernel has completed (no-op without the launch attribute)
+    pdl_launch_dependents();       // let the next kernel's launch + prologue overlap this kernel
     const int cpg = C / NMM_GN_GROUPS;
     const int split = blockIdx.x % splits;
     const int grp = (blockIdx.x / splits) % NMM_GN_GROUPS;
@@ -113,14 +115,14 @@ int launch_gn_stats(const Geo &g, const nmm_shape *s, const void *x, double *par
     ProfScope prof(K_GN_STATS, st, 0.0, (double)g.N * g.C * dtype_size(g.dtype));
     if (g.dtype == NMM_BF16) {
         if (x_vec_ok<bf16>(g, s, x))
-            gn_stats_kernel<bf16, true><<<grid, block, 0, st>>>((const bf16 *)x, partial, g.C, g.F, g.P, splits, s->x_stride_b, s->x_stride_c, s->x_stride_f);
+            launch_pdl(gn_stats_kernel<bf16, true>, grid, block, 0, st, (const bf16 *)x, partial, g.C, g.F, g.P, splits, s->x_stride_b, s->x_stride_c, s->x_stride_f);
         else
-            gn_stats_kernel<bf16, false><<<grid, block, 0, st>>>((const bf16 *)x, partial, g.C, g.F, g.P, splits, s->x_stride_b, s->x_stride_c, s->x_stride_f);
+            launch_pdl(gn_stats_kernel<bf16, false>, grid, block, 0, st, (const bf16 *)x, partial, g.C, g.F, g.P, splits, s->x_stride_b, s->x_stride_c, s->x_stride_f);
     } else {
         if (x_vec_ok<float>(g, s, x))
-            gn_stats_kernel<float, true><<<grid, block, 0, st>>>((const float *)x, partial, g.C, g.F, g.P, splits, s->x_stride_b, s->x_stride_c, s->x_stride_f);
+            launch_pdl(gn_stats_kernel<float, true>, grid, block, 0, st, (const float *)x, partial, g.C, g.F, g.P, splits, s->x_stride_b, s->x_stride_c, s->x_stride_f);
         else
-            gn_stats_kernel<float, false><<<grid, block, 0, st>>>((const float *)x, partial, g.C, g.F, g.P, splits, s->x_stride_b, s->x_stride_c, s->x_stride_f);
+            launch_pdl(gn_stats_kernel<float, false>, grid, block, 0, st, (const float *)x, partial, g.C, g.F, g.P, splits, s->x_stride_b, s->x_stride_c, s->x_stride_f);
     }
     NMM_LAUNCHED("gn_stats_kernel");
     return NMM_OK;
@@ -142,6 +144,8 @@ __device__ __forceinline__ void gn_finalize_one(const double *__restrict__ parti
 
 __global__ void gn_finalize_kernel(const double *__restrict__ partial, float *__restrict__ mean, float *__restrict__ rstd,
                                    int n, int splits, double count, float eps) {
+    pdl_wait();                    // PDL: the previous kernel has completed (no-op without the launch attribute)
+    pdl_launch_dependents();       // let the next kernel's launch + prologue overlap this kernel
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float m, r;
@@ -151,7 +155,7 @@ __global__ void gn_finalize_kernel(const double *__restrict__ partial, float *__
 
 int launch_gn_finalize(const Geo &g, const nmm_shape *s, const double *partial, float *mean, float *rstd, cudaStream_t st) {
     const int n = g.B * g.F * NMM_GN_GROUPS;
-    gn_finalize_kernel<<<(n + 127) / 128, 128, 0, st>>>(partial, mean, rstd, n, gn_splits(g),
+    launch_pdl(gn_finalize_kernel, (n + 127) / 128, 128, 0, st, partial, mean, rstd, n, gn_splits(g),
                                                          (double)(g.C / NMM_GN_GROUPS) * g.P, s->eps_gn);
     NMM_LAUNCHED("gn_finalize_kernel");
     return NMM_OK;
@@ -167,6 +171,8 @@ __global__ void __launch_bounds__(256) gn_tokens_generic_kernel(const T *__restr
                                                                 const float *__restrict__ gamma, const float *__restrict__ beta,
                                                                 T *__restrict__ tokens, int C, int F, int P, int splits,
                                                                 float eps, int64_t sb, int64_t sc, int64_t sf) {
+    pdl_wait();                    // PDL: the previous kernel has completed (no-op without the launch attribute)
+    pdl_launch_dependents();       // let the next kernel's launch + prologue overlap this kernel
     __shared__ float tile[32][33];
     __shared__ float sc_a[32], sc_b[32];
     const int bf = blockIdx.z, b = bf / F, f = bf % F;
@@ -204,6 +210,8 @@ __global__ void __launch_bounds__(256) gn_tokens_bf16_kernel(const bf16 *__restr
                                                              const float *__restrict__ gamma, const float *__restrict__ beta,
                                                              bf16 *__restrict__ tokens, int C, int F, int P, int splits,
                                                              float eps, int64_t sb, int64_t sc, int64_t sf) {
+    pdl_wait();                    // PDL: the previous kernel has completed (no-op without the launch attribute)
+    pdl_launch_dependents();       // let the next kernel's launch + prologue overlap this kernel
     __shared__ uint32_t tile[64][33];            // [p][channel pair]
     __shared__ float sc_a[64], sc_b[64];
     const int bf = blockIdx.z, b = bf / F, f = bf % F;
@@ -246,7 +254,7 @@ int launch_gn_tokens(const Geo &g, const nmm_shape *s, const void *x, const doub
     if (g.dtype == NMM_BF16 && g.C % 64 == 0 && g.P % 64 == 0 && x_vec_ok<bf16>(g, s, x) && aligned(tokens, 16)) {
         dim3 grid(g.P / 64, g.C / 64, g.B * g.F);
         ProfScope prof(K_GN_TOKENS, st, 0.0, 2.0 * g.N * g.C * dtype_size(g.dtype));
-        gn_tokens_bf16_kernel<<<grid, 256, 0, st>>>((const bf16 *)x, partial, gn_w, gn_b, (bf16 *)tokens, g.C, g.F, g.P,
+        launch_pdl(gn_tokens_bf16_kernel, grid, 256, 0, st, (const bf16 *)x, partial, gn_w, gn_b, (bf16 *)tokens, g.C, g.F, g.P,
                                                     splits, s->eps_gn, s->x_stride_b, s->x_stride_c, s->x_stride_f);
         NMM_LAUNCHED("gn_tokens_bf16_kernel");
         return NMM_OK;
@@ -255,10 +263,10 @@ int launch_gn_tokens(const Geo &g, const nmm_shape *s, const void *x, const doub
     if (grid.y > 65535) return fail(NMM_ERR_UNSUPPORTED, "channels too large");
     ProfScope prof(K_GN_TOKENS, st, 0.0, 2.0 * g.N * g.C * dtype_size(g.dtype));
     if (g.dtype == NMM_BF16)
-        gn_tokens_generic_kernel<bf16><<<grid, 256, 0, st>>>((const bf16 *)x, partial, gn_w, gn_b, (bf16 *)tokens, g.C, g.F,
+        launch_pdl(gn_tokens_generic_kernel<bf16>, grid, 256, 0, st, (const bf16 *)x, partial, gn_w, gn_b, (bf16 *)tokens, g.C, g.F,
                                                              g.P, splits, s->eps_gn, s->x_stride_b, s->x_stride_c, s->x_stride_f);
     else
-        gn_tokens_generic_kernel<float><<<grid, 256, 0, st>>>((const float *)x, partial, gn_w, gn_b, (float *)tokens, g.C, g.F,
+        launch_pdl(gn_tokens_generic_kernel<float>, grid, 256, 0, st, (const float *)x, partial, gn_w, gn_b, (float *)tokens, g.C, g.F,
                                                               g.P, splits, s->eps_gn, s->x_stride_b, s->x_stride_c, s->x_stride_f);
     NMM_LAUNCHED("gn_tokens_generic_kernel");
     return NMM_OK;
@@ -279,6 +287,8 @@ template <typename TOut, int IT4>
 __global__ void __launch_bounds__(256) layernorm_pe_vec_kernel(const float *__restrict__ h, const float *__restrict__ gamma,
                                                                const float *__restrict__ beta, const float *__restrict__ pe,
                                                                TOut *__restrict__ out, int64_t N, int F, int P, float eps) {
+    pdl_wait();                    // PDL: the previous kernel has completed (no-op without the launch attribute)
+    pdl_launch_dependents();       // let the next kernel's launch + prologue overlap this kernel
     constexpr int C = IT4 * 64;
     const int l16 = threadIdx.x & 15;
     int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4);
@@ -322,6 +332,8 @@ template <typename TOut>
 __global__ void __launch_bounds__(256) layernorm_pe_generic_kernel(const float *__restrict__ h, const float *__restrict__ gamma,
                                                                    const float *__restrict__ beta, const float *__restrict__ pe,
                                                                    TOut *__restrict__ out, int64_t N, int C, int F, int P, float eps) {
+    pdl_wait();                    // PDL: the previous kernel has completed (no-op without the launch attribute)
+    pdl_launch_dependents();       // let the next kernel's launch + prologue overlap this kernel
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= N) return;                            // warp-uniform
@@ -351,13 +363,13 @@ static int launch_ln_t(const Geo &g, const nmm_shape *s, const float *h, const f
         const int64_t blocks = ceil_div(g.N, 16);                    // 16 rows (half-warps) per 256-thread CTA
         if (blocks > 0x7fffffff) return fail(NMM_ERR_UNSUPPORTED, "too many tokens");
         dim3 grid((unsigned)blocks), block(256);
-        if (g.C == 320) layernorm_pe_vec_kernel<TOut, 5><<<grid, block, 0, st>>>(h, w, b, pe, out, g.N, g.F, g.P, s->eps_ln);
-        else if (g.C == 640) layernorm_pe_vec_kernel<TOut, 10><<<grid, block, 0, st>>>(h, w, b, pe, out, g.N, g.F, g.P, s->eps_ln);
-        else layernorm_pe_vec_kernel<TOut, 20><<<grid, block, 0, st>>>(h, w, b, pe, out, g.N, g.F, g.P, s->eps_ln);
+        if (g.C == 320) launch_pdl(layernorm_pe_vec_kernel<TOut, 5>, grid, block, 0, st, h, w, b, pe, out, g.N, g.F, g.P, s->eps_ln);
+        else if (g.C == 640) launch_pdl(layernorm_pe_vec_kernel<TOut, 10>, grid, block, 0, st, h, w, b, pe, out, g.N, g.F, g.P, s->eps_ln);
+        else launch_pdl(layernorm_pe_vec_kernel<TOut, 20>, grid, block, 0, st, h, w, b, pe, out, g.N, g.F, g.P, s->eps_ln);
     } else {
         const int64_t blocks = ceil_div(g.N, 8);
         if (blocks > 0x7fffffff) return fail(NMM_ERR_UNSUPPORTED, "too many tokens");
-        layernorm_pe_generic_kernel<TOut><<<(unsigned)blocks, 256, 0, st>>>(h, w, b, pe, out, g.N, g.C, g.F, g.P, s->eps_ln);
+        launch_pdl(layernorm_pe_generic_kernel<TOut>, (unsigned)blocks, 256, 0, st, h, w, b, pe, out, g.N, g.C, g.F, g.P, s->eps_ln);
     }
     NMM_LAUNCHED("layernorm_pe_kernel");
     return NMM_OK;
