@@ -249,7 +249,6 @@ def main():
         sampler = ClockSampler(physical_gpu_index(local_rank))
         sampler.start()
         launches0 = nb.launch_count()
-        nlib.profile_begin()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         for _ in range(args.steps):
@@ -257,8 +256,18 @@ def main():
         ev1.record()
         barrier()
         ms_total = ev0.elapsed_time(ev1)
-        prof = nlib.profile_end()
         launches = nb.launch_count() - launches0
+        # ---------------- same K steps again with the library's per-kernel CUDA events (roofline of the dominant kernel) --------
+        # (kept out of the `value` region: an event between two kernels defeats programmatic dependent launch)
+        nlib.profile_begin()
+        ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev2.record()
+        for _ in range(args.steps):
+            step_resident()
+        ev3.record()
+        barrier()
+        ms_profiled = ev2.elapsed_time(ev3)
+        prof = nlib.profile_end()
         clocks = sampler.stop()
 
         # ---------------- end-to-end arm: host buffers, copies inside the timed region ----------------
@@ -308,7 +317,9 @@ def main():
         roofline = {"kernel": "linear_tc_kernel (tcgen05 bf16 GEMM + fused epilogue)", "bound": "tensor", "achieved": ach,
                     "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None, "traffic": None,
                     "peak_source": peaks["source"] + ", bf16_tflops_sustained", "launches": gemm["launches"],
-                    "share_of_step": gemm["total_ms"] / ms_total if ms_total else None,
+                    "measured_over": f"a second pass of the same {args.steps} steps with a CUDA-event pair around every kernel launch "
+                                     f"({ms_profiled / args.steps:.3f} ms/step with the events in the stream)",
+                    "share_of_step": gemm["total_ms"] / ms_profiled if ms_profiled else None,
                     "other_kernels": {k: {"launches": v["launches"], "ms_per_step": v["total_ms"] / args.steps,
                                           "GBps": (v["bytes"] / (v["total_ms"] * 1e-3) / 1e9) if v["total_ms"] > 0 else None,
                                           "frac_of_hbm_peak": (v["bytes"] / (v["total_ms"] * 1e-3) / 1e9 / peaks["hbm_gbs"]) if v["total_ms"] > 0 and peaks["hbm_gbs"] else None}
