@@ -1,6 +1,7 @@
 // C ABI of libneurons_mm.so (include/neurons_mm.h): validation, parameter packing, workspace carving and the
 // kernel sequence of one VanillaTemporalModule.forward (motion_module.py:77-82 -> :134-158 -> :210-222 -> :270-329).
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <utility>
@@ -89,17 +90,33 @@ static PackedLayout packed_layout(const Geo &g) {
     return L;
 }
 
-// ---- workspace layout --------------------------------------------------------------------------------
+// ---- chunked execution + workspace layout ---------------------------------------------------------------------------
+// Every stage after the GroupNorm statistics is local to a spatial position (Linear / LayerNorm / GEGLU per token, attention per
+// position over the frames), so the module is run chunk by chunk over position ranges [p0, p0 + pc).  With pc chosen so that a
+// chunk's intermediates (tokens 2 B + residual 4 B + qkv|act 8 B + ctx 2 B per token-channel in bf16 mode) stay around 40 MB,
+// they are produced and consumed inside the 126 MB L2 and the same workspace addresses are overwritten by the next chunk before
+// their dirty lines are ever evicted: the intermediates never reach HBM (write bandwidth, ~3.2-3.9 TB/s on this part, is what
+// bounds the unchunked pipeline).  HBM traffic per call drops from ~116 B to ~6 B per token-channel (x twice, y once).
+// Chunk-local token order: row = (b*F + f)*pc + (p - p0).   NMM_CHUNK_TOKENS overrides the target (0 = no chunking).
+static int chunk_positions(const Geo &g) {
+    int64_t target = 8192;                                   // tokens per chunk
+    if (const char *e = getenv("NMM_CHUNK_TOKENS")) target = atoll(e);
+    if (target <= 0 || g.P % 64 != 0) return g.P;
+    int64_t pc = target / ((int64_t)g.B * g.F) / 64 * 64;
+    if (pc < 64) pc = 64;
+    return pc >= g.P ? g.P : (int)pc;
+}
+
 struct WorkLayout { size_t gn_partial, tok, h, big, ctx, total; };
 static WorkLayout work_layout(const Geo &g) {
     WorkLayout w;
     size_t off = 0;
-    const size_t es = dtype_size(g.dtype), NC = (size_t)g.N * g.C;
+    const size_t es = dtype_size(g.dtype), NC = (size_t)g.B * g.F * chunk_positions(g) * g.C;     // one chunk
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
     w.gn_partial = take(gn_partial_bytes(g));
     w.tok = take(NC * es);          // GroupNorm tokens / LayerNorm output / GEMM-dtype copy of h for proj_out
     w.h = take(NC * 4);             // fp32 residual stream
-    w.big = take(NC * 4 * es);      // qkv [N,3C] and GEGLU activations [N,4C] (never live together)
+    w.big = take(NC * 4 * es);      // qkv [n,3C] and GEGLU activations [n,4C] (never live together)
     w.ctx = take(NC * es);          // attention context
     w.total = off;
     return w;
@@ -303,48 +320,63 @@ int nmm_forward(const nmm_shape *s, const void *x, void *y, const void *packed, 
     float *h = (float *)(ws + w.h);
     auto F32 = [&](size_t off) { return (const float *)(pk + off); };
 
-    // GroupNorm statistics, then normalise + re-layout to token-major           motion_module.py:137-144
+    // GroupNorm statistics over the whole tensor                                       motion_module.py:142
     if ((rc = launch_gn_stats(g, s, x, gn_partial, st)) != NMM_OK) return rc;
-    if ((rc = launch_gn_tokens(g, s, x, gn_partial, F32(L.gn_w), F32(L.gn_b), tok, st)) != NMM_OK) return rc;
 
-    LinearArgs a;
-    memset(&a, 0, sizeof(a));
-    a.M = g.N; a.F = g.F; a.P = g.P;
-    a.xsb = s->x_stride_b; a.xsc = s->x_stride_c; a.xsf = s->x_stride_f;
-    a.ysb = s->y_stride_b; a.ysc = s->y_stride_c; a.ysf = s->y_stride_f;
+    const int pc = chunk_positions(g);
+    const size_t es = dtype_size(g.dtype);
+    for (int p0 = 0; p0 < g.P; p0 += pc) {
+        // geometry of this chunk: positions [p0, p0 + pn) of every (b, f) image; x / y offset to the chunk's first position
+        const int pn = (g.P - p0 < pc) ? g.P - p0 : pc;
+        Geo gc = g;
+        gc.H = 1; gc.W = pn; gc.P = pn; gc.N = (int64_t)g.B * g.F * pn;
+        nmm_shape sc = *s;
+        sc.height = 1; sc.width = pn;
+        const char *xc = (const char *)x + (size_t)p0 * es;
+        char *yc = (char *)y + (size_t)p0 * es;
 
-    // proj_in -> fp32 residual stream h                                           :145
-    a.epilogue = NMM_EPI_STORE; a.N = g.C; a.K = g.C; a.A = tok; a.W = pk + L.w_in; a.bias = F32(L.b_in); a.h = h; a.out = nullptr;
-    if ((rc = linear(g, a, st)) != NMM_OK) return rc;
+        // normalise + re-layout to token-major                                          :142-144
+        if ((rc = launch_gn_tokens(gc, &sc, g, xc, gn_partial, F32(L.gn_w), F32(L.gn_b), tok, st)) != NMM_OK) return rc;
 
-    for (int l = 0; l < g.layers; l++) {
-        const LayerOff &lo = L.layer[l];
-        for (int i = 0; i < g.A; i++) {
-            const AttnOff &ao = lo.attn[i];
-            // n = LayerNorm(h) + pe[f]                                                :212, :277-278
-            if ((rc = launch_layernorm_pe(g, s, h, F32(ao.ln_w), F32(ao.ln_b), g.pos_enc ? F32(ao.pe) : nullptr, tok, st)) != NMM_OK) return rc;
-            // q|k|v = n . Wqkv^T                                                      :289,297,298
-            a.epilogue = NMM_EPI_STORE; a.N = 3 * g.C; a.K = g.C; a.A = tok; a.W = pk + ao.wqkv; a.bias = nullptr; a.h = nullptr; a.out = big;
+        LinearArgs a;
+        memset(&a, 0, sizeof(a));
+        a.M = gc.N; a.F = g.F; a.P = pn;
+        a.xsb = s->x_stride_b; a.xsc = s->x_stride_c; a.xsf = s->x_stride_f;
+        a.ysb = s->y_stride_b; a.ysc = s->y_stride_c; a.ysf = s->y_stride_f;
+
+        // proj_in -> fp32 residual stream h                                             :145
+        a.epilogue = NMM_EPI_STORE; a.N = g.C; a.K = g.C; a.A = tok; a.W = pk + L.w_in; a.bias = F32(L.b_in); a.h = h; a.out = nullptr;
+        if ((rc = linear(g, a, st)) != NMM_OK) return rc;
+
+        for (int l = 0; l < g.layers; l++) {
+            const LayerOff &lo = L.layer[l];
+            for (int i = 0; i < g.A; i++) {
+                const AttnOff &ao = lo.attn[i];
+                // n = LayerNorm(h) + pe[f]                                              :212, :277-278
+                if ((rc = launch_layernorm_pe(gc, &sc, h, F32(ao.ln_w), F32(ao.ln_b), g.pos_enc ? F32(ao.pe) : nullptr, tok, st)) != NMM_OK) return rc;
+                // q|k|v = n . Wqkv^T                                                    :289,297,298
+                a.epilogue = NMM_EPI_STORE; a.N = 3 * g.C; a.K = g.C; a.A = tok; a.W = pk + ao.wqkv; a.bias = nullptr; a.h = nullptr; a.out = big;
+                if ((rc = linear(g, a, st)) != NMM_OK) return rc;
+                // softmax(q k^T / sqrt(dh)) v over frames                               motion_module_new.py:258-287
+                if ((rc = launch_temporal_attention(gc, big, ctx, st)) != NMM_OK) return rc;
+                // h = ctx . Wo^T + bo + h                                               motion_module.py:321, :213-217
+                a.epilogue = NMM_EPI_RESIDUAL; a.N = g.C; a.K = g.C; a.A = ctx; a.W = pk + ao.wo; a.bias = F32(ao.bo); a.h = h; a.out = nullptr;
+                if ((rc = linear(g, a, st)) != NMM_OK) return rc;
+            }
+            // FeedForward: LayerNorm -> GEGLU -> Linear, + h                            :219; motion_module_new.py:441-471,497-518
+            if ((rc = launch_layernorm_pe(gc, &sc, h, F32(lo.ff_ln_w), F32(lo.ff_ln_b), nullptr, tok, st)) != NMM_OK) return rc;
+            a.epilogue = NMM_EPI_GEGLU; a.N = 8 * g.C; a.K = g.C; a.A = tok; a.W = pk + lo.w1; a.bias = F32(lo.b1); a.h = nullptr; a.out = big;
             if ((rc = linear(g, a, st)) != NMM_OK) return rc;
-            // softmax(q k^T / sqrt(dh)) v over frames                                 motion_module_new.py:258-287
-            if ((rc = launch_temporal_attention(g, big, ctx, st)) != NMM_OK) return rc;
-            // h = ctx . Wo^T + bo + h                                                 motion_module.py:321, :213-217
-            a.epilogue = NMM_EPI_RESIDUAL; a.N = g.C; a.K = g.C; a.A = ctx; a.W = pk + ao.wo; a.bias = F32(ao.bo); a.h = h; a.out = nullptr;
+            const bool last = (l == g.layers - 1);
+            a.epilogue = NMM_EPI_RESIDUAL; a.N = g.C; a.K = 4 * g.C; a.A = big; a.W = pk + lo.w2; a.bias = F32(lo.b2); a.h = h;
+            a.out = (last && g.dtype == NMM_BF16) ? tok : nullptr;      // bf16 h + ff(...) = the A operand of proj_out (h itself is dead)
             if ((rc = linear(g, a, st)) != NMM_OK) return rc;
         }
-        // FeedForward: LayerNorm -> GEGLU -> Linear, + h                              :219; motion_module_new.py:441-471,497-518
-        if ((rc = launch_layernorm_pe(g, s, h, F32(lo.ff_ln_w), F32(lo.ff_ln_b), nullptr, tok, st)) != NMM_OK) return rc;
-        a.epilogue = NMM_EPI_GEGLU; a.N = 8 * g.C; a.K = g.C; a.A = tok; a.W = pk + lo.w1; a.bias = F32(lo.b1); a.h = nullptr; a.out = big;
-        if ((rc = linear(g, a, st)) != NMM_OK) return rc;
-        const bool last = (l == g.layers - 1);
-        a.epilogue = NMM_EPI_RESIDUAL; a.N = g.C; a.K = 4 * g.C; a.A = big; a.W = pk + lo.w2; a.bias = F32(lo.b2); a.h = h;
-        a.out = (last && g.dtype == NMM_BF16) ? tok : nullptr;      // bf16 copy of the final h = A operand of proj_out
+        // y = proj_out(h) back in NCHW + x                                              :152-156
+        a.epilogue = NMM_EPI_OUTPUT; a.N = g.C; a.K = g.C; a.A = (g.dtype == NMM_BF16) ? (const void *)tok : (const void *)h;
+        a.W = pk + L.w_out; a.bias = F32(L.b_out); a.h = nullptr; a.out = nullptr; a.x = xc; a.y = yc;
         if ((rc = linear(g, a, st)) != NMM_OK) return rc;
     }
-    // y = proj_out(h) back in NCHW + x                                                :152-156
-    a.epilogue = NMM_EPI_OUTPUT; a.N = g.C; a.K = g.C; a.A = (g.dtype == NMM_BF16) ? (const void *)tok : (const void *)h;
-    a.W = pk + L.w_out; a.bias = F32(L.b_out); a.h = nullptr; a.out = nullptr; a.x = x; a.y = y;
-    if ((rc = linear(g, a, st)) != NMM_OK) return rc;
     return NMM_OK;
 }
 
@@ -371,7 +403,7 @@ int nmm_groupnorm_tokens(const nmm_shape *s, const void *x, const float *gn_w, c
     if (workspace_bytes < gn_partial_bytes(g)) return fail(NMM_ERR_WORKSPACE, "workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = launch_gn_stats(g, s, x, (double *)workspace, st)) != NMM_OK) return rc;
-    return launch_gn_tokens(g, s, x, (const double *)workspace, gn_w, gn_b, tokens, st);
+    return launch_gn_tokens(g, s, g, x, (const double *)workspace, gn_w, gn_b, tokens, st);
 }
 
 int nmm_layernorm_pe(const nmm_shape *s, const float *h, const float *w, const float *b, const float *pe, void *out, void *stream) {

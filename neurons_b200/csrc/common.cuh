@@ -139,7 +139,7 @@ __device__ __forceinline__ float gelu_erf_fast(float v) {
 size_t gn_partial_bytes(const Geo &g);
 int launch_gn_stats(const Geo &g, const nmm_shape *s, const void *x, double *partial, cudaStream_t st);
 int launch_gn_finalize(const Geo &g, const nmm_shape *s, const double *partial, float *mean, float *rstd, cudaStream_t st);
-int launch_gn_tokens(const Geo &g, const nmm_shape *s, const void *x, const double *partial, const float *gn_w,
+int launch_gn_tokens(const Geo &g, const nmm_shape *s, const Geo &full, const void *x, const double *partial, const float *gn_w,
                      const float *gn_b, void *tokens, cudaStream_t st);
 // LayerNorm (+PE)
 int launch_layernorm_pe(const Geo &g, const nmm_shape *s, const float *h, const float *w, const float *b,

@@ -169,7 +169,7 @@ int launch_gn_finalize(const Geo &g, const nmm_shape *s, const double *partial, 
 template <typename T>
 __global__ void __launch_bounds__(256) gn_tokens_generic_kernel(const T *__restrict__ x, const double *__restrict__ partial,
                                                                 const float *__restrict__ gamma, const float *__restrict__ beta,
-                                                                T *__restrict__ tokens, int C, int F, int P, int splits,
+                                                                T *__restrict__ tokens, int C, int F, int P, int splits, double count,
                                                                 float eps, int64_t sb, int64_t sc, int64_t sf) {
     pdl_wait();                    // PDL: the previous kernel has completed (no-op without the launch attribute)
     pdl_launch_dependents();       // let the next kernel's launch + prologue overlap this kernel
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(256) gn_tokens_generic_kernel(const T *__restr
         int c = c0 + threadIdx.x;
         if (c < C) {
             float m, r;
-            gn_finalize_one(partial, bf * NMM_GN_GROUPS + c / cpg, splits, (double)cpg * P, eps, m, r);
+            gn_finalize_one(partial, bf * NMM_GN_GROUPS + c / cpg, splits, count, eps, m, r);
             float a = r * gamma[c];
             sc_a[threadIdx.x] = a; sc_b[threadIdx.x] = beta[c] - m * a;
         }
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(256) gn_tokens_generic_kernel(const T *__restr
 // P % 64 == 0 and 16-byte aligned rows.
 __global__ void __launch_bounds__(256) gn_tokens_bf16_kernel(const bf16 *__restrict__ x, const double *__restrict__ partial,
                                                              const float *__restrict__ gamma, const float *__restrict__ beta,
-                                                             bf16 *__restrict__ tokens, int C, int F, int P, int splits,
+                                                             bf16 *__restrict__ tokens, int C, int F, int P, int splits, double count,
                                                              float eps, int64_t sb, int64_t sc, int64_t sf) {
     pdl_wait();                    // PDL: the previous kernel has completed (no-op without the launch attribute)
     pdl_launch_dependents();       // let the next kernel's launch + prologue overlap this kernel
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(256) gn_tokens_bf16_kernel(const bf16 *__restr
     if (t < 64) {
         int c = c0 + t;
         float m, r;
-        gn_finalize_one(partial, bf * NMM_GN_GROUPS + c / cpg, splits, (double)cpg * P, eps, m, r);
+        gn_finalize_one(partial, bf * NMM_GN_GROUPS + c / cpg, splits, count, eps, m, r);
         float a = r * gamma[c];
         sc_a[t] = a; sc_b[t] = beta[c] - m * a;
     }
@@ -247,15 +247,18 @@ __global__ void __launch_bounds__(256) gn_tokens_bf16_kernel(const bf16 *__restr
     reinterpret_cast<uint4 *>(dst)[1] = make_uint4(o[4], o[5], o[6], o[7]);
 }
 
-int launch_gn_tokens(const Geo &g, const nmm_shape *s, const void *x, const double *partial, const float *gn_w,
+// `g` / `s` describe the positions being converted (possibly a chunk of the image: x already offset to its first position);
+// `full` is the geometry the statistics were computed over (splits and element count of a whole group).
+int launch_gn_tokens(const Geo &g, const nmm_shape *s, const Geo &full, const void *x, const double *partial, const float *gn_w,
                      const float *gn_b, void *tokens, cudaStream_t st) {
-    const int splits = gn_splits(g);
+    const int splits = gn_splits(full);
+    const double count = (double)(full.C / NMM_GN_GROUPS) * full.P;
     if (g.B * g.F > 65535) return fail(NMM_ERR_UNSUPPORTED, "batch*frames > 65535");
     if (g.dtype == NMM_BF16 && g.C % 64 == 0 && g.P % 64 == 0 && x_vec_ok<bf16>(g, s, x) && aligned(tokens, 16)) {
         dim3 grid(g.P / 64, g.C / 64, g.B * g.F);
         ProfScope prof(K_GN_TOKENS, st, 0.0, 2.0 * g.N * g.C * dtype_size(g.dtype));
         launch_pdl(gn_tokens_bf16_kernel, grid, 256, 0, st, (const bf16 *)x, partial, gn_w, gn_b, (bf16 *)tokens, g.C, g.F, g.P,
-                                                    splits, s->eps_gn, s->x_stride_b, s->x_stride_c, s->x_stride_f);
+                   splits, count, s->eps_gn, s->x_stride_b, s->x_stride_c, s->x_stride_f);
         NMM_LAUNCHED("gn_tokens_bf16_kernel");
         return NMM_OK;
     }
@@ -264,10 +267,10 @@ int launch_gn_tokens(const Geo &g, const nmm_shape *s, const void *x, const doub
     ProfScope prof(K_GN_TOKENS, st, 0.0, 2.0 * g.N * g.C * dtype_size(g.dtype));
     if (g.dtype == NMM_BF16)
         launch_pdl(gn_tokens_generic_kernel<bf16>, grid, 256, 0, st, (const bf16 *)x, partial, gn_w, gn_b, (bf16 *)tokens, g.C, g.F,
-                                                             g.P, splits, s->eps_gn, s->x_stride_b, s->x_stride_c, s->x_stride_f);
+                   g.P, splits, count, s->eps_gn, s->x_stride_b, s->x_stride_c, s->x_stride_f);
     else
         launch_pdl(gn_tokens_generic_kernel<float>, grid, 256, 0, st, (const float *)x, partial, gn_w, gn_b, (float *)tokens, g.C, g.F,
-                                                              g.P, splits, s->eps_gn, s->x_stride_b, s->x_stride_c, s->x_stride_f);
+                   g.P, splits, count, s->eps_gn, s->x_stride_b, s->x_stride_c, s->x_stride_f);
     NMM_LAUNCHED("gn_tokens_generic_kernel");
     return NMM_OK;
 }

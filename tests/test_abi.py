@@ -71,8 +71,10 @@ def test_sizes(built_library):
     # 2.26 M parameters in bf16 + fp32 vectors + PE tables
     assert 2 * 2_250_000 < n.value < 2 * 2_400_000
     assert built_library.nmm_workspace_bytes(C.byref(s), C.byref(n)) == 0
+    # the module runs chunk by chunk over position ranges (L2-resident intermediates): the workspace holds ONE chunk
+    # (tokens 2 B + residual 4 B + qkv|act 8 B + ctx 2 B per token-channel) plus the GroupNorm partial sums
     tokens = 8 * 64 * 64
-    assert n.value >= tokens * 320 * (2 + 4 + 8 + 2)
+    assert 4096 * 320 * (2 + 4 + 8 + 2) <= n.value <= tokens * 320 * (2 + 4 + 8 + 2) + (1 << 20)
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
