@@ -96,10 +96,12 @@ static PackedLayout packed_layout(const Geo &g) {
 // chunk's intermediates (tokens 2 B + residual 4 B + qkv|act 8 B + ctx 2 B per token-channel in bf16 mode) stay around 40 MB,
 // they are produced and consumed inside the 126 MB L2 and the same workspace addresses are overwritten by the next chunk before
 // their dirty lines are ever evicted: the intermediates never reach HBM (write bandwidth, ~3.2-3.9 TB/s on this part, is what
-// bounds the unchunked pipeline).  HBM traffic per call drops from ~116 B to ~6 B per token-channel (x twice, y once).
-// Chunk-local token order: row = (b*F + f)*pc + (p - p0).   NMM_CHUNK_TOKENS overrides the target (0 = no chunking).
+// bounds the unchunked pipeline).  HBM traffic per call would drop from ~116 B to ~6 B per token-channel (x twice, y once).
+// Chunk-local token order: row = (b*F + f)*pc + (p - p0).   NMM_CHUNK_TOKENS=<tokens> enables it (experiment; default off).
 static int chunk_positions(const Geo &g) {
-    int64_t target = 8192;                                   // tokens per chunk
+    // Measured on B200 (profiles/r1_chunk_sweep.txt): chunking LOSES at every chunk size (4096 tokens: 14.2 ms/step, 16384: 8.7,
+    // off: 8.0) -- the per-kernel fixed cost (launch, ramp, tail; ~10 us) outweighs the saved HBM traffic, so it is off by default.
+    int64_t target = 0;                                      // tokens per chunk; 0 = whole tensor
     if (const char *e = getenv("NMM_CHUNK_TOKENS")) target = atoll(e);
     if (target <= 0 || g.P % 64 != 0) return g.P;
     int64_t pc = target / ((int64_t)g.B * g.F) / 64 * 64;

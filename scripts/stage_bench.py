@@ -42,15 +42,16 @@ def main():
     ap.add_argument("--frames", type=int, default=8)
     ap.add_argument("--latent", type=int, default=64)
     ap.add_argument("--out", default="gpurun_out/stage_bench.json")
-    ap.add_argument("--levels", default="320,640,1280")
+    ap.add_argument("--levels", default="320,640,1280", help="channel counts; 'C@side' overrides the latent side, e.g. 1280@8")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.isfile(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     rows = []
     bf = torch.bfloat16
-    for C in [int(c) for c in a.levels.split(",")]:
-        side = a.latent * 320 // C
+    for lev in a.levels.split(","):
+        C = int(lev.split("@")[0])
+        side = int(lev.split("@")[1]) if "@" in lev else a.latent * 320 // C
         B, F = a.batch, a.frames
         P = side * side
         M = B * F * P
