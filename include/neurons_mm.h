@@ -69,6 +69,11 @@ typedef struct nmm_shape {
     int32_t dtype;              /* nmm_dtype of x, y and of the arithmetic mode                        */
     float eps_gn;               /* 1e-6, motion_module.py:109                                          */
     float eps_ln;               /* 1e-5, nn.LayerNorm default (motion_module.py:201,207)               */
+    int32_t ln_fold;            /* bf16 mode only: 1 = LayerNorm folded into the consuming GEMM (the producing GEMM emits
+                                   row statistics + a bf16 copy of the residual; QKV / GEGLU run on gamma-folded weights and
+                                   apply rstd*(acc - mean*g) + c (+ pe.W^T) in their epilogue): 3 kernels and one fp32 read of
+                                   the residual stream fewer per block.  0 = separate LayerNorm kernel.  Must be the same in
+                                   nmm_pack_params and nmm_forward (it changes the packed layout).                          */
     /* element strides of x and y for the b, c and f axes; (h, w) must be dense (stride W, 1).
      * x may be the contiguous "b c f h w" tensor or the [B,F,C,H,W]-storage view every UNet call site
      * passes; y is normally [B,F,C,H,W] storage like the reference's (motion_module.py:153-156). */

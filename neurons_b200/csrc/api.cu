@@ -61,8 +61,8 @@ ProfScope::~ProfScope() {
 }
 
 // ---- packed parameter layout -------------------------------------------------------------------------
-struct AttnOff { size_t ln_w, ln_b, wqkv, wo, bo, pe; };
-struct LayerOff { AttnOff attn[NMM_MAX_ATTN]; size_t ff_ln_w, ff_ln_b, w1, b1, w2, b2; };
+struct AttnOff { size_t ln_w, ln_b, wqkv, wo, bo, pe, g_qkv, c_qkv, pew; };           // g/c/pew: LayerNorm-folding tables
+struct LayerOff { AttnOff attn[NMM_MAX_ATTN]; size_t ff_ln_w, ff_ln_b, w1, b1, w2, b2, g1, c1; };
 struct PackedLayout { size_t gn_w, gn_b, w_in, b_in; LayerOff layer[NMM_MAX_LAYERS]; size_t w_out, b_out, total; };
 
 static PackedLayout packed_layout(const Geo &g) {
@@ -79,11 +79,14 @@ static PackedLayout packed_layout(const Geo &g) {
             a.ln_w = take(C * 4); a.ln_b = take(C * 4);
             a.wqkv = take(3 * C * C * ws); a.wo = take(C * C * ws); a.bo = take(C * 4);
             a.pe = take(g.pos_enc ? (size_t)g.max_len * C * 4 : 0);
+            a.g_qkv = take(g.ln_fold ? 3 * C * 4 : 0); a.c_qkv = take(g.ln_fold ? 3 * C * 4 : 0);
+            a.pew = take(g.ln_fold && g.pos_enc ? (size_t)g.max_len * 3 * C * 4 : 0);
         }
         LayerOff &lo = L.layer[l];
         lo.ff_ln_w = take(C * 4); lo.ff_ln_b = take(C * 4);
         lo.w1 = take(8 * C * C * ws); lo.b1 = take(8 * C * 4);
         lo.w2 = take(4 * C * C * ws); lo.b2 = take(C * 4);
+        lo.g1 = take(g.ln_fold ? 8 * C * 4 : 0); lo.c1 = take(g.ln_fold ? 8 * C * 4 : 0);
     }
     L.w_out = take(C * C * ws); L.b_out = take(C * 4);
     L.total = off;
@@ -109,7 +112,7 @@ static int chunk_positions(const Geo &g) {
     return pc >= g.P ? g.P : (int)pc;
 }
 
-struct WorkLayout { size_t gn_partial, tok, h, big, ctx, total; };
+struct WorkLayout { size_t gn_partial, tok, tok2, h, big, ctx, ln_part, total; };
 static WorkLayout work_layout(const Geo &g) {
     WorkLayout w;
     size_t off = 0;
@@ -120,6 +123,10 @@ static WorkLayout work_layout(const Geo &g) {
     w.h = take(NC * 4);             // fp32 residual stream
     w.big = take(NC * 4 * es);      // qkv [n,3C] and GEGLU activations [n,4C] (never live together)
     w.ctx = take(NC * es);          // attention context
+    // LayerNorm folding: second token buffer (bf16 copy of the residual stream) + per-row partial statistics
+    // ([n][2 * n_tiles][2] fp32, n_tiles <= C / 32)
+    w.tok2 = take(g.ln_fold ? NC * es : 0);
+    w.ln_part = take(g.ln_fold ? NC / 32 * 2 * 2 * 4 : 0);
     w.total = off;
     return w;
 }
@@ -181,6 +188,88 @@ int launch_convert_rows(const void *src, int src_dtype, void *dst, int dst_dtype
     else return fail(NMM_ERR_BAD_ARG, "unknown parameter dtype");
     NMM_LAUNCHED("convert_rows_kernel");
     return NMM_OK;
+}
+
+// ---- LayerNorm folding (pack time) -------------------------------------------------------------------------------------------
+// For a Linear that consumes LayerNorm(h) (+ pe):   (LN(h) + pe) . W^T + b
+//     = rstd * ( h . (gamma (.) W)^T  -  mean * g )  +  c  +  pe . W^T,      g[n] = sum_c gamma[c] W[n,c],  c[n] = sum_c beta[c] W[n,c] + b[n]
+// so the GEMM can run on the RAW residual rows with the gamma-folded weight W' = bf16(gamma (.) W) and the epilogue finishes the
+// normalisation.  g is summed over the bf16-ROUNDED W' (exactly what the tensor core multiplies), c and pe.W^T in fp32.
+// Row mapping as in convert_rows_kernel (GEGLU interleave).
+template <typename TS>
+__global__ void fold_weight_kernel(const TS *__restrict__ src, const TS *__restrict__ gamma, bf16 *__restrict__ dst, int64_t rows,
+                                   int64_t cols, int64_t half) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int64_t total = rows * cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / cols, c = i - r * cols;
+        const int64_t sr = half > 0 ? (r >> 1) + (r & 1) * half : r;
+        dst[i] = __float2bfloat16_rn(to_f32(src[sr * cols + c]) * to_f32(gamma[c]));
+    }
+}
+// one 128-thread CTA per output row r: g[r], c[r] and pew[f][r] (f < max_len; pew may be null)
+template <typename TS>
+__global__ void __launch_bounds__(128) fold_tables_kernel(const TS *__restrict__ src, const bf16 *__restrict__ folded,
+                                                          const TS *__restrict__ beta, const TS *__restrict__ bias,
+                                                          const TS *__restrict__ pe, float *__restrict__ g_out,
+                                                          float *__restrict__ c_out, float *__restrict__ pew_out, int64_t cols,
+                                                          int64_t half, int max_len, int64_t pew_pitch) {
+    pdl_wait();
+    pdl_launch_dependents();
+    __shared__ float red[4];
+    const int64_t r = blockIdx.x;
+    const int64_t sr = half > 0 ? (r >> 1) + (r & 1) * half : r;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    auto block_sum = [&](float v) {
+        v = warp_sum(v);
+        __syncthreads();
+        if (lane == 0) red[warp] = v;
+        __syncthreads();
+        return red[0] + red[1] + red[2] + red[3];
+    };
+    float gs = 0.f, cs = 0.f;
+    for (int64_t c = threadIdx.x; c < cols; c += 128) {
+        gs += to_f32(folded[r * cols + c]);
+        cs = fmaf(to_f32(beta[c]), to_f32(src[sr * cols + c]), cs);
+    }
+    gs = block_sum(gs);
+    cs = block_sum(cs);
+    if (threadIdx.x == 0) { g_out[r] = gs; c_out[r] = cs + (bias ? to_f32(bias[sr]) : 0.f); }
+    if (pew_out != nullptr) {
+        for (int f = 0; f < max_len; f++) {
+            float ps = 0.f;
+            for (int64_t c = threadIdx.x; c < cols; c += 128) ps = fmaf(to_f32(pe[(int64_t)f * cols + c]), to_f32(src[sr * cols + c]), ps);
+            ps = block_sum(ps);
+            if (threadIdx.x == 0) pew_out[(int64_t)f * pew_pitch + r] = ps;
+        }
+    }
+}
+
+template <typename TS>
+static int fold_linear_t(const void *w, const void *gamma, const void *beta, const void *bias, const void *pe, bf16 *dst_w, float *g_out,
+                         float *c_out, float *pew_out, int64_t rows, int64_t cols, int half, int max_len, int64_t pew_pitch, cudaStream_t st) {
+    if (!w || !gamma || !beta) return fail(NMM_ERR_BAD_ARG, "NULL parameter tensor");
+    const int blocks = (int)std::min<int64_t>(ceil_div(rows * cols, 256), 148 * 16);
+    {
+        ProfScope prof(K_PACK, st, 0.0, (double)rows * cols * (sizeof(TS) + 2));
+        launch_pdl(fold_weight_kernel<TS>, blocks, 256, 0, st, (const TS *)w, (const TS *)gamma, dst_w, rows, cols, (int64_t)half);
+    }
+    NMM_LAUNCHED("fold_weight_kernel");
+    {
+        ProfScope prof(K_PACK, st, 0.0, (double)rows * cols * (sizeof(TS) + 2));
+        launch_pdl(fold_tables_kernel<TS>, (unsigned)rows, 128, 0, st, (const TS *)w, (const bf16 *)dst_w, (const TS *)beta, (const TS *)bias,
+                   (const TS *)pe, g_out, c_out, pew_out, cols, (int64_t)half, max_len, pew_pitch);
+    }
+    NMM_LAUNCHED("fold_tables_kernel");
+    return NMM_OK;
+}
+static int fold_linear(int src_dtype, const void *w, const void *gamma, const void *beta, const void *bias, const void *pe, void *dst_w,
+                       float *g_out, float *c_out, float *pew_out, int64_t rows, int64_t cols, int half, int max_len, int64_t pew_pitch,
+                       cudaStream_t st) {
+    if (src_dtype == NMM_F32)
+        return fold_linear_t<float>(w, gamma, beta, bias, pe, (bf16 *)dst_w, g_out, c_out, pew_out, rows, cols, half, max_len, pew_pitch, st);
+    return fold_linear_t<bf16>(w, gamma, beta, bias, pe, (bf16 *)dst_w, g_out, c_out, pew_out, rows, cols, half, max_len, pew_pitch, st);
 }
 
 // Sinusoidal table when the caller does not hand over the module's own `pe` buffer (motion_module.py:234-238).
@@ -283,7 +372,6 @@ int nmm_pack_params(const nmm_shape *s, const nmm_params *src, void *packed, siz
             const AttnOff &ao = lo.attn[i];
             PACK(ap.norm_w, ao.ln_w, NMM_F32, C, 1, 0); PACK(ap.norm_b, ao.ln_b, NMM_F32, C, 1, 0);
             const size_t wbytes = (size_t)C * C * dtype_size(wd);
-            PACK(ap.to_q, ao.wqkv, wd, C, C, 0); PACK(ap.to_k, ao.wqkv + wbytes, wd, C, C, 0); PACK(ap.to_v, ao.wqkv + 2 * wbytes, wd, C, C, 0);
             PACK(ap.to_out_w, ao.wo, wd, C, C, 0); PACK(ap.to_out_b, ao.bo, NMM_F32, C, 1, 0);
             if (g.pos_enc) {
                 if (ap.pe) PACK(ap.pe, ao.pe, NMM_F32, (int64_t)g.max_len, C, 0);
@@ -293,9 +381,32 @@ int nmm_pack_params(const nmm_shape *s, const nmm_params *src, void *packed, siz
                     NMM_LAUNCHED("make_pe_kernel");
                 }
             }
+            if (g.ln_fold) {
+                // gamma-folded q|k|v weights + tables; pe.W^T needs the module's pe in the SOURCE dtype: use the caller's buffer
+                // when given, else the fp32 table just generated (source dtype fp32 only)
+                const void *pe_src = ap.pe;
+                if (g.pos_enc && !pe_src && sd != NMM_F32) return fail(NMM_ERR_BAD_ARG, "LayerNorm folding needs the pos_encoder.pe buffer for bf16 parameters");
+                if (g.pos_enc && !pe_src) pe_src = base + ao.pe;
+                const void *srcs[3] = {ap.to_q, ap.to_k, ap.to_v};
+                for (int m = 0; m < 3; m++) {
+                    rc = fold_linear(sd, srcs[m], ap.norm_w, ap.norm_b, nullptr, g.pos_enc ? pe_src : nullptr, base + ao.wqkv + m * wbytes,
+                                     (float *)(base + ao.g_qkv) + m * C, (float *)(base + ao.c_qkv) + m * C,
+                                     g.pos_enc ? (float *)(base + ao.pew) + m * C : nullptr, C, C, 0, g.max_len, 3 * C, st);
+                    if (rc != NMM_OK) return rc;
+                }
+            } else {
+                PACK(ap.to_q, ao.wqkv, wd, C, C, 0); PACK(ap.to_k, ao.wqkv + wbytes, wd, C, C, 0); PACK(ap.to_v, ao.wqkv + 2 * wbytes, wd, C, C, 0);
+            }
         }
         PACK(lp.ff_norm_w, lo.ff_ln_w, NMM_F32, C, 1, 0); PACK(lp.ff_norm_b, lo.ff_ln_b, NMM_F32, C, 1, 0);
-        PACK(lp.ff_proj_w, lo.w1, wd, 8 * C, C, (int)(4 * C)); PACK(lp.ff_proj_b, lo.b1, NMM_F32, 8 * C, 1, (int)(4 * C));
+        PACK(lp.ff_proj_b, lo.b1, NMM_F32, 8 * C, 1, (int)(4 * C));
+        if (g.ln_fold) {
+            rc = fold_linear(sd, lp.ff_proj_w, lp.ff_norm_w, lp.ff_norm_b, lp.ff_proj_b, nullptr, base + lo.w1, (float *)(base + lo.g1),
+                             (float *)(base + lo.c1), nullptr, 8 * C, C, (int)(4 * C), 0, 0, st);
+            if (rc != NMM_OK) return rc;
+        } else {
+            PACK(lp.ff_proj_w, lo.w1, wd, 8 * C, C, (int)(4 * C));
+        }
         PACK(lp.ff_out_w, lo.w2, wd, C, 4 * C, 0); PACK(lp.ff_out_b, lo.b2, NMM_F32, C, 1, 0);
     }
     PACK(src->proj_out_w, L.w_out, wd, C, C, 0); PACK(src->proj_out_b, L.b_out, NMM_F32, C, 1, 0);
@@ -346,33 +457,61 @@ int nmm_forward(const nmm_shape *s, const void *x, void *y, const void *packed, 
         a.xsb = s->x_stride_b; a.xsc = s->x_stride_c; a.xsf = s->x_stride_f;
         a.ysb = s->y_stride_b; a.ysc = s->y_stride_c; a.ysf = s->y_stride_f;
 
+        // LayerNorm folding (bf16 mode): every GEMM that writes the residual stream also writes a bf16 copy of it (tok2) and per-row
+        // partial statistics; QKV / GEGLU then run on tok2 with gamma-folded weights and finish the normalisation in their epilogue.
+        const bool fold = g.ln_fold;
+        void *tok2 = ws + w.tok2;
+        float *ln_part = (float *)(ws + w.ln_part);
+        int nparts = 0;                                   // partial slots the last residual-writing GEMM filled
+        auto producer = [&](LinearArgs &la) {            // la writes h: add the fold outputs
+            if (!fold) return;
+            int bn = 0, cl = 0;
+            plan_linear_tc(la.M, la.N, la.K, la.epilogue, &bn, &cl);
+            nparts = 2 * (la.N / bn);
+            la.out = tok2; la.ln_part_out = ln_part;
+        };
+        auto consumer = [&](LinearArgs &la, const float *gg, const float *cc, const float *pew) {
+            la.A = tok2; la.bias = nullptr; la.ln_part_in = ln_part; la.ln_nparts = nparts; la.ln_g = gg; la.ln_c = cc; la.ln_pew = pew;
+            la.ln_eps = s->eps_ln;
+        };
+        auto clear_fold = [&](LinearArgs &la) { la.ln_part_out = nullptr; la.ln_part_in = nullptr; la.ln_pew = nullptr; la.no_h_store = 0; };
+
         // proj_in -> fp32 residual stream h                                             :145
         a.epilogue = NMM_EPI_STORE; a.N = g.C; a.K = g.C; a.A = tok; a.W = pk + L.w_in; a.bias = F32(L.b_in); a.h = h; a.out = nullptr;
+        producer(a);
         if ((rc = linear(g, a, st)) != NMM_OK) return rc;
+        clear_fold(a);
 
         for (int l = 0; l < g.layers; l++) {
             const LayerOff &lo = L.layer[l];
             for (int i = 0; i < g.A; i++) {
                 const AttnOff &ao = lo.attn[i];
-                // n = LayerNorm(h) + pe[f]                                              :212, :277-278
-                if ((rc = launch_layernorm_pe(gc, &sc, h, F32(ao.ln_w), F32(ao.ln_b), g.pos_enc ? F32(ao.pe) : nullptr, tok, st)) != NMM_OK) return rc;
-                // q|k|v = n . Wqkv^T                                                    :289,297,298
+                // q|k|v = (LayerNorm(h) + pe[f]) . Wqkv^T                               :212, :277-278, :289,297,298
                 a.epilogue = NMM_EPI_STORE; a.N = 3 * g.C; a.K = g.C; a.A = tok; a.W = pk + ao.wqkv; a.bias = nullptr; a.h = nullptr; a.out = big;
+                if (fold) consumer(a, F32(ao.g_qkv), F32(ao.c_qkv), g.pos_enc ? F32(ao.pew) : nullptr);
+                else if ((rc = launch_layernorm_pe(gc, &sc, h, F32(ao.ln_w), F32(ao.ln_b), g.pos_enc ? F32(ao.pe) : nullptr, tok, st)) != NMM_OK) return rc;
                 if ((rc = linear(g, a, st)) != NMM_OK) return rc;
+                clear_fold(a);
                 // softmax(q k^T / sqrt(dh)) v over frames                               motion_module_new.py:258-287
                 if ((rc = launch_temporal_attention(gc, big, ctx, st)) != NMM_OK) return rc;
                 // h = ctx . Wo^T + bo + h                                               motion_module.py:321, :213-217
                 a.epilogue = NMM_EPI_RESIDUAL; a.N = g.C; a.K = g.C; a.A = ctx; a.W = pk + ao.wo; a.bias = F32(ao.bo); a.h = h; a.out = nullptr;
+                producer(a);
                 if ((rc = linear(g, a, st)) != NMM_OK) return rc;
+                clear_fold(a);
             }
             // FeedForward: LayerNorm -> GEGLU -> Linear, + h                            :219; motion_module_new.py:441-471,497-518
-            if ((rc = launch_layernorm_pe(gc, &sc, h, F32(lo.ff_ln_w), F32(lo.ff_ln_b), nullptr, tok, st)) != NMM_OK) return rc;
             a.epilogue = NMM_EPI_GEGLU; a.N = 8 * g.C; a.K = g.C; a.A = tok; a.W = pk + lo.w1; a.bias = F32(lo.b1); a.h = nullptr; a.out = big;
+            if (fold) consumer(a, F32(lo.g1), F32(lo.c1), nullptr);
+            else if ((rc = launch_layernorm_pe(gc, &sc, h, F32(lo.ff_ln_w), F32(lo.ff_ln_b), nullptr, tok, st)) != NMM_OK) return rc;
             if ((rc = linear(g, a, st)) != NMM_OK) return rc;
+            clear_fold(a);
             const bool last = (l == g.layers - 1);
-            a.epilogue = NMM_EPI_RESIDUAL; a.N = g.C; a.K = 4 * g.C; a.A = big; a.W = pk + lo.w2; a.bias = F32(lo.b2); a.h = h;
-            a.out = (last && g.dtype == NMM_BF16) ? tok : nullptr;      // bf16 h + ff(...) = the A operand of proj_out (h itself is dead)
+            a.epilogue = NMM_EPI_RESIDUAL; a.N = g.C; a.K = 4 * g.C; a.A = big; a.W = pk + lo.w2; a.bias = F32(lo.b2); a.h = h; a.out = nullptr;
+            if (last && g.dtype == NMM_BF16) { a.out = tok; a.no_h_store = 1; }   // bf16 h + ff(...) = the A operand of proj_out (h itself is dead)
+            else producer(a);
             if ((rc = linear(g, a, st)) != NMM_OK) return rc;
+            clear_fold(a);
         }
         // y = proj_out(h) back in NCHW + x                                              :152-156
         a.epilogue = NMM_EPI_OUTPUT; a.N = g.C; a.K = g.C; a.A = (g.dtype == NMM_BF16) ? (const void *)tok : (const void *)h;
@@ -435,7 +574,10 @@ int nmm_linear(int32_t dtype, int32_t epilogue, int64_t M, int32_t N, int32_t K,
     a.epilogue = epilogue; a.M = M; a.N = N; a.K = K; a.A = A; a.W = W; a.bias = bias; a.h = h; a.out = out;
     switch (epilogue) {
         case NMM_EPI_STORE: if (!h && !out) return fail(NMM_ERR_BAD_ARG, "STORE epilogue needs h or out"); break;
-        case NMM_EPI_RESIDUAL: if (!h) return fail(NMM_ERR_BAD_ARG, "RESIDUAL epilogue needs h"); break;
+        case NMM_EPI_RESIDUAL:
+            if (!h) return fail(NMM_ERR_BAD_ARG, "RESIDUAL epilogue needs h");
+            a.no_h_store = out != nullptr;      // documented contract: with `out`, h is only read
+            break;
         case NMM_EPI_GEGLU: if (!out || (N & 1)) return fail(NMM_ERR_BAD_ARG, "GEGLU epilogue needs out and even N"); break;
         case NMM_EPI_OUTPUT: {
             if ((rc = validate(s)) != NMM_OK) return rc;

@@ -79,6 +79,7 @@ struct Geo {
     int64_t N;       // tokens
     bool pos_enc;
     int dtype;
+    bool ln_fold;    // bf16 mode with the LayerNorms folded into the QKV / GEGLU GEMMs
 };
 inline Geo geo_of(const nmm_shape *s) {
     Geo g;
@@ -86,6 +87,7 @@ inline Geo geo_of(const nmm_shape *s) {
     g.P = s->height * s->width; g.heads = s->heads; g.dh = s->heads > 0 ? s->channels / s->heads : 0;
     g.layers = s->layers; g.A = s->attn_blocks; g.max_len = s->max_len;
     g.N = (int64_t)s->batch * s->frames * g.P; g.pos_enc = s->pos_enc != 0; g.dtype = s->dtype;
+    g.ln_fold = s->ln_fold != 0 && s->dtype == NMM_BF16;
     return g;
 }
 inline size_t dtype_size(int dtype) { return dtype == NMM_BF16 ? 2 : 4; }
@@ -157,11 +159,26 @@ struct LinearArgs {
     const float *bias;       // [N] fp32 or null
     float *h;                // RESIDUAL: fp32 [M,N] in/out
     void *out;               // STORE: [M,N]; RESIDUAL: optional [M,N] copy; GEGLU: [M,N/2]   (dtype)
+    int no_h_store;          // RESIDUAL: h is only read, the sum goes to `out` alone (the last feed-forward)
     // OUTPUT epilogue
     const void *x; void *y;
     int F, P;
     int64_t xsb, xsc, xsf, ysb, ysc, ysf;
+    // LayerNorm folding (bf16 tensor-core path only; see gemm_tcgen05.cu "LayerNorm folding"):
+    //   producer side: this GEMM writes the residual stream -> also emit per-row partial (sum, sum of squares) of the new h
+    float *ln_part_out;      // [M][NMM_LN_PARTS][2] fp32 or null
+    //   consumer side: A holds the RAW bf16 residual rows and W is gamma-folded; the epilogue applies
+    //   out = rstd * (acc - mean * g[n]) + c[n] (+ pew[frame][n]) with mean / rstd from the partials of the producer
+    const float *ln_part_in; // [M][NMM_LN_PARTS][2] or null
+    int ln_nparts;           // valid partial slots per row (2 * n_tiles of the producer GEMM)
+    const float *ln_g, *ln_c;   // [N] fp32: g[n] = sum_c W'[n,c];  c[n] = sum_c beta[c] W[n,c] + bias[n]
+    const float *ln_pew;     // [max_len][N] fp32 or null: pe[f] . W^T
+    float ln_eps;
 };
+constexpr int NMM_LN_PARTS = 16;     // partial-statistics slots per row: 2 epilogue warps x up to 8 N tiles of the producer
+// N tile / CTA-pair plan the tensor-core GEMM will use for (M, N, K): lets the caller know how many partial-statistics slots
+// a producer GEMM fills (2 * N / block_n)
+void plan_linear_tc(int64_t M, int N, int K, int epilogue, int *block_n, int *cluster);
 // algorithmic work of one Linear launch: 2*M*N*K flops; bytes = operands once + epilogue traffic once
 inline double linear_flops(const LinearArgs &a) { return 2.0 * (double)a.M * a.N * a.K; }
 inline double linear_bytes(const LinearArgs &a, int es) {

@@ -20,12 +20,21 @@ struct EpiParams {
     int F, P;
     int64_t xsb, xsc, xsf, ysb, ysc, ysf;
     int nchw_vec;      // OUTPUT: P % 32 == 0 and x / y rows 16-byte aligned -> 8-position (16-byte) vector path
+    int no_h_store;
+    float *ln_part_out;
+    const float *ln_part_in;
+    int ln_nparts, ln_K;
+    const float *ln_g, *ln_c, *ln_pew;
+    float ln_eps;
 };
 
 inline EpiParams epi_params_of(const LinearArgs &a) {
     EpiParams e;
     e.M = a.M; e.N = a.N; e.bias = a.bias; e.h = a.h; e.out = a.out; e.x = a.x; e.y = a.y; e.F = a.F; e.P = a.P;
     e.xsb = a.xsb; e.xsc = a.xsc; e.xsf = a.xsf; e.ysb = a.ysb; e.ysc = a.ysc; e.ysf = a.ysf;
+    e.no_h_store = a.no_h_store;
+    e.ln_part_out = a.ln_part_out; e.ln_part_in = a.ln_part_in; e.ln_nparts = a.ln_nparts; e.ln_K = a.K;
+    e.ln_g = a.ln_g; e.ln_c = a.ln_c; e.ln_pew = a.ln_pew; e.ln_eps = a.ln_eps;
     e.nchw_vec = 0;
     if (a.epilogue == NMM_EPI_OUTPUT && a.P > 0 && a.P % 32 == 0 && aligned(a.x, 16) && aligned(a.y, 16) && a.xsb % 8 == 0 &&
         a.xsc % 8 == 0 && a.xsf % 8 == 0 && a.ysb % 8 == 0 && a.ysc % 8 == 0 && a.ysf % 8 == 0)
@@ -76,9 +85,8 @@ __device__ __forceinline__ void epilogue_apply(const EpiParams &e, int64_t row, 
             float4 r = reinterpret_cast<const float4 *>(hp)[i];
             acc[4 * i] += r.x; acc[4 * i + 1] += r.y; acc[4 * i + 2] += r.z; acc[4 * i + 3] += r.w;
         }
-        // out == NULL: h updated in place; out != NULL: only the copy in the GEMM dtype is written (h is left untouched)
         if (e.out != nullptr) store_row<NC>(reinterpret_cast<T *>(e.out) + row * e.N + col0, acc);
-        else store_row<NC>(hp, acc);
+        if (!e.no_h_store) store_row<NC>(hp, acc);
     } else if constexpr (EPI == NMM_EPI_GEGLU) {
         float o[NC / 2];
 #pragma unroll

@@ -50,6 +50,7 @@ struct TcParams {
     int64_t m_tiles;
     int cluster;             // CTAs per tile along M: 1 (cta_group::1) or 2 (cta_group::2 pair, each CTA stages half of W)
     int64_t cluster_tiles;   // ceil(m_tiles / cluster) * n_tiles
+    int epi_buf;             // bytes of shared memory per epilogue warp (8 KB; 12 KB when a residual epilogue also writes a bf16 copy)
     unsigned long long *trace;   // NMM_TRACE builds only: per-tile timestamps of CTA 0 (development instrumentation)
     int debug;               // NMM_GEMM_DEBUG (timing experiments only, results invalid): 1 = epilogue does nothing, 2 = no TMA loads
 };
@@ -212,7 +213,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const int ew = warp - 4;
         const int q = warp & 3;                                           // TMEM lane quadrant this warp may access
         const int half = ew >> 2;                                         // which of the quadrant's two warps
-        const uint32_t box0 = epi_base + (uint32_t)ew * TC_EPI_BUF, box1 = box0 + 4096u;
+        const uint32_t box0 = epi_base + (uint32_t)ew * (uint32_t)p.epi_buf, box1 = box0 + 4096u, box2 = box0 + 8192u;
+        // LayerNorm folding, consumer side: per-row mean / rstd of the A rows from the producer's partial sums (lane == row)
+        const bool ln_in = e.ln_part_in != nullptr;
         float *xpose = reinterpret_cast<float *>(smem_raw + (box0 - ptx::smem_u32(smem_raw)));      // proj_out transpose buffer
         uint32_t lph0 = 0u, lph1 = 0u;                                    // phases of this warp's two residual-load barriers
         int as = 0; uint32_t aphase = 0;
@@ -224,6 +227,21 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             const int64_t row0 = m_blk * TC_BM + q * 32;
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.block_n);
             if (warp == 4 && lane == 0) TRACE(tile_no, 6);
+            float ln_mu = 0.f, ln_rstd = 0.f;
+            const float *pew_row = nullptr;
+            if (ln_in) {
+                const int64_t row = row0 + lane;
+                if (row < p.M) {
+                    float s1 = 0.f, s2 = 0.f;
+                    const float2 *pp = reinterpret_cast<const float2 *>(e.ln_part_in) + row * e.ln_nparts;
+                    for (int i = 0; i < e.ln_nparts; i++) { const float2 t2 = __ldg(pp + i); s1 += t2.x; s2 += t2.y; }
+                    const float inv = 1.0f / (float)e.ln_K;
+                    ln_mu = s1 * inv;
+                    ln_rstd = rsqrtf(fmaxf(s2 * inv - ln_mu * ln_mu, 0.f) + e.ln_eps);
+                    if (e.ln_pew != nullptr) pew_row = e.ln_pew + (int64_t)((row / e.P) % e.F) * e.N;
+                }
+            }
+            float st1 = 0.f, st2 = 0.f;                                  // producer side: partial statistics of this lane's row
             bool waited = false;
             auto wait_acc = [&]() {
                 if (!waited) {
@@ -313,10 +331,20 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         ptx::tmem_ld_wait();
 #pragma unroll
                         for (int j = 0; j < 8; j++) {
-                            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (e.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4 *>(e.bias + col0 + 32 * hc) + j);
-                            const float v0 = __uint_as_float(r[4 * j]) + b4.x, g0 = __uint_as_float(r[4 * j + 1]) + b4.y;
-                            const float v1 = __uint_as_float(r[4 * j + 2]) + b4.z, g1 = __uint_as_float(r[4 * j + 3]) + b4.w;
+                            float v0, g0, v1, g1;
+                            if (ln_in) {      // out = rstd * (acc - mean * g[n]) + c[n]
+                                const float4 gg = __ldg(reinterpret_cast<const float4 *>(e.ln_g + col0 + 32 * hc) + j);
+                                const float4 cc = __ldg(reinterpret_cast<const float4 *>(e.ln_c + col0 + 32 * hc) + j);
+                                v0 = fmaf(ln_rstd, __uint_as_float(r[4 * j]) - ln_mu * gg.x, cc.x);
+                                g0 = fmaf(ln_rstd, __uint_as_float(r[4 * j + 1]) - ln_mu * gg.y, cc.y);
+                                v1 = fmaf(ln_rstd, __uint_as_float(r[4 * j + 2]) - ln_mu * gg.z, cc.z);
+                                g1 = fmaf(ln_rstd, __uint_as_float(r[4 * j + 3]) - ln_mu * gg.w, cc.w);
+                            } else {
+                                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (e.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4 *>(e.bias + col0 + 32 * hc) + j);
+                                v0 = __uint_as_float(r[4 * j]) + b4.x; g0 = __uint_as_float(r[4 * j + 1]) + b4.y;
+                                v1 = __uint_as_float(r[4 * j + 2]) + b4.z; g1 = __uint_as_float(r[4 * j + 3]) + b4.w;
+                            }
                             o[8 * hc + j] = pack_bf16x2(v0 * gelu_erf_fast(g0), v1 * gelu_erf_fast(g1));
                         }
                     }
@@ -357,12 +385,28 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     ptx::tmem_ld32(t_row + (uint32_t)c0, r);
                     ptx::tmem_ld_wait();
                     float v[32];
+                    if (ln_in) {              // out = rstd * (acc - mean * g[n]) + c[n] (+ pe[frame] . W^T)
 #pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (e.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4 *>(e.bias + col0) + j);
-                        v[4 * j] = __uint_as_float(r[4 * j]) + b4.x; v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b4.y;
-                        v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b4.z; v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b4.w;
+                        for (int j = 0; j < 8; j++) {
+                            const float4 gg = __ldg(reinterpret_cast<const float4 *>(e.ln_g + col0) + j);
+                            float4 cc = __ldg(reinterpret_cast<const float4 *>(e.ln_c + col0) + j);
+                            if (pew_row != nullptr) {
+                                const float4 pw = __ldg(reinterpret_cast<const float4 *>(pew_row + col0) + j);
+                                cc.x += pw.x; cc.y += pw.y; cc.z += pw.z; cc.w += pw.w;
+                            }
+                            v[4 * j] = fmaf(ln_rstd, __uint_as_float(r[4 * j]) - ln_mu * gg.x, cc.x);
+                            v[4 * j + 1] = fmaf(ln_rstd, __uint_as_float(r[4 * j + 1]) - ln_mu * gg.y, cc.y);
+                            v[4 * j + 2] = fmaf(ln_rstd, __uint_as_float(r[4 * j + 2]) - ln_mu * gg.z, cc.z);
+                            v[4 * j + 3] = fmaf(ln_rstd, __uint_as_float(r[4 * j + 3]) - ln_mu * gg.w, cc.w);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (e.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4 *>(e.bias + col0) + j);
+                            v[4 * j] = __uint_as_float(r[4 * j]) + b4.x; v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b4.y;
+                            v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b4.z; v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b4.w;
+                        }
                     }
                     if constexpr (EPI == NMM_EPI_RESIDUAL) {
                         if (k & 1) { ptx::mbar_wait(load_bar(ew, 1), lph1); lph1 ^= 1u; }
@@ -372,16 +416,21 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                             const float4 h4 = lds128(box_f32_addr(box, lane, j));
                             v[4 * j] += h4.x; v[4 * j + 1] += h4.y; v[4 * j + 2] += h4.z; v[4 * j + 3] += h4.w;
                         }
+                        if (e.out != nullptr && !e.no_h_store && lane == 0) ptx::bulk_wait_read0();   // third box (bf16 copy) free again
                         __syncwarp();                                     // every lane has read its row before the box is overwritten
                     } else {
                         if (lane == 0) ptx::bulk_wait_read0();            // the previous chunk's boxes have been read
                         __syncwarp();
                     }
                     const bool want_o = e.out != nullptr;
-                    // RESIDUAL with `out`: only the bf16 copy is produced (the last feed-forward: h itself is dead afterwards)
-                    const bool want_h = e.h != nullptr && !(EPI == NMM_EPI_RESIDUAL && want_o);
-                    // fp32 result -> `box` (128-byte rows); bf16 result -> box1 for STORE, the (already consumed) same box for RESIDUAL
-                    const uint32_t obox = (EPI == NMM_EPI_RESIDUAL) ? box : box1;
+                    const bool want_h = e.h != nullptr && !e.no_h_store;
+                    if (e.ln_part_out != nullptr) {                       // producer side of the LayerNorm folding
+#pragma unroll
+                        for (int j = 0; j < 32; j++) { st1 += v[j]; st2 = fmaf(v[j], v[j], st2); }
+                    }
+                    // fp32 result -> `box` (128-byte rows); bf16 result -> box1 for STORE; for RESIDUAL the consumed residual box
+                    // itself when h is not stored, else the third box (host sizes the per-warp buffer accordingly)
+                    const uint32_t obox = (EPI == NMM_EPI_RESIDUAL) ? (want_h ? box2 : box) : box1;
                     if (want_h) {
 #pragma unroll
                         for (int j = 0; j < 8; j++)
@@ -405,6 +454,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 }
             }
             wait_acc();                                                   // a warp without a chunk in this tile still follows the phases
+            if (e.ln_part_out != nullptr && row0 + lane < p.M)            // slot = (N tile, which warp of the quadrant); zeros if no chunk
+                reinterpret_cast<float2 *>(e.ln_part_out)[(row0 + lane) * (2 * p.n_tiles) + n_blk * 2 + half] = make_float2(st1, st2);
             if (warp == 4 && lane == 0) TRACE(tile_no, 12);
             if (warp == 8 && lane == 0) TRACE(tile_no, 14);
             ptx::tc_fence_before();
@@ -519,6 +570,16 @@ static TilePlan choose_tiles(int64_t m_tiles, int N, int K, int sms, int gran, i
     return best;
 }
 
+void plan_linear_tc(int64_t M, int N, int K, int epilogue, int *block_n, int *cluster) {
+    const int force_cluster = getenv("NMM_GEMM_CLUSTER") ? atoi(getenv("NMM_GEMM_CLUSTER")) : 0;
+    const int force_bn = getenv("NMM_GEMM_BLOCK_N") ? atoi(getenv("NMM_GEMM_BLOCK_N")) : 0;
+    const int gran = epilogue == NMM_EPI_GEGLU ? 64 : 32;
+    const TilePlan plan = choose_tiles(ceil_div(M, TC_BM), N, K, num_sms(), gran, (force_cluster == 1 || force_cluster == 2) ? force_cluster : 0,
+                                       (force_bn >= gran && force_bn <= 256 && force_bn % gran == 0 && N % force_bn == 0) ? force_bn : 0);
+    *block_n = plan.block_n;
+    *cluster = plan.cluster;
+}
+
 template <int EPI, int CG>
 static int launch_tc_t(const CUtensorMap &ta, const CUtensorMap &tw, const CUtensorMap &th, const CUtensorMap &to, const TcParams &p,
                        const EpiParams &e, size_t smem, int grid, cudaStream_t st, double flops, double bytes) {
@@ -581,7 +642,8 @@ int launch_linear_tc(const LinearArgs &a, cudaStream_t st) {
     p.n_tiles = a.N / p.block_n;
     p.cluster_tiles = m_groups * p.n_tiles;
     const size_t stage_bytes = (size_t)TC_A_BYTES + (size_t)(p.block_n / p.cluster) * TC_BK * 2;     // per CTA
-    const size_t fixed = 1024 /*alignment slack*/ + TC_BAR_BYTES + (size_t)TC_EPI_WARPS * TC_EPI_BUF;
+    p.epi_buf = (a.epilogue == NMM_EPI_RESIDUAL && a.out != nullptr && !a.no_h_store) ? 12288 : TC_EPI_BUF;
+    const size_t fixed = 1024 /*alignment slack*/ + TC_BAR_BYTES + (size_t)TC_EPI_WARPS * p.epi_buf;
     int stages = (int)((TC_SMEM_MAX - fixed) / stage_bytes);
     if (stages > 8) stages = 8;
     if (stages < 2) return fail(NMM_ERR_UNSUPPORTED, "tcgen05 GEMM: tile does not fit shared memory");

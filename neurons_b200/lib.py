@@ -30,7 +30,7 @@ class Shape(C.Structure):
     _fields_ = [
         ("batch", C.c_int32), ("channels", C.c_int32), ("frames", C.c_int32), ("height", C.c_int32), ("width", C.c_int32),
         ("heads", C.c_int32), ("layers", C.c_int32), ("attn_blocks", C.c_int32), ("pos_enc", C.c_int32),
-        ("max_len", C.c_int32), ("dtype", C.c_int32), ("eps_gn", C.c_float), ("eps_ln", C.c_float),
+        ("max_len", C.c_int32), ("dtype", C.c_int32), ("eps_gn", C.c_float), ("eps_ln", C.c_float), ("ln_fold", C.c_int32),
         ("x_stride_b", C.c_int64), ("x_stride_c", C.c_int64), ("x_stride_f", C.c_int64),
         ("y_stride_b", C.c_int64), ("y_stride_c", C.c_int64), ("y_stride_f", C.c_int64),
     ]

@@ -8,6 +8,7 @@ animatediff/pipelines/pipeline_neuroclips.py:320).
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Dict, Optional
 
@@ -28,6 +29,7 @@ class ModuleConfig:
     attn_blocks: int = 2
     pos_enc: bool = True
     max_len: int = 24
+    ln_fold: bool = True      # bf16 mode: fold the LayerNorms into the QKV / GEGLU GEMMs (NMM_LN_FOLD=0 in the environment disables)
 
 
 def _dtype_code(dt: torch.dtype) -> int:
@@ -36,6 +38,10 @@ def _dtype_code(dt: torch.dtype) -> int:
     if dt == torch.bfloat16:
         return _lib.NMM_BF16
     raise TypeError(f"neurons_mm supports float32 and bfloat16 activations, got {dt}")
+
+
+def _ln_fold(cfg: "ModuleConfig") -> int:
+    return int(bool(cfg.ln_fold) and os.environ.get("NMM_LN_FOLD", "1") != "0")
 
 
 def _stream_ptr(device) -> int:
@@ -58,6 +64,7 @@ def make_shape(cfg: ModuleConfig, x: torch.Tensor, y: Optional[torch.Tensor] = N
     s.pos_enc, s.max_len = int(cfg.pos_enc), cfg.max_len
     s.dtype = _dtype_code(x.dtype)
     s.eps_gn, s.eps_ln = GN_EPS, LN_EPS
+    s.ln_fold = _ln_fold(cfg)
     s.x_stride_b, s.x_stride_c, s.x_stride_f = x.stride(0), x.stride(1), x.stride(2)
     if y is not None:
         s.y_stride_b, s.y_stride_c, s.y_stride_f = y.stride(0), y.stride(1), y.stride(2)
@@ -80,6 +87,7 @@ def packed_params_bytes(cfg: ModuleConfig, dtype: torch.dtype, frames: int = 1) 
     s.frames = frames
     s.channels, s.heads, s.layers, s.attn_blocks = cfg.channels, cfg.heads, cfg.layers, cfg.attn_blocks
     s.pos_enc, s.max_len, s.dtype = int(cfg.pos_enc), cfg.max_len, _dtype_code(dtype)
+    s.eps_gn, s.eps_ln, s.ln_fold = GN_EPS, LN_EPS, _ln_fold(cfg)
     n = C.c_size_t()
     _lib.check(_lib.load().nmm_packed_params_bytes(C.byref(s), C.byref(n)))
     return n.value
@@ -139,6 +147,7 @@ def pack_params(cfg: ModuleConfig, tensors: Dict[str, torch.Tensor], compute_dty
     s.batch = s.frames = s.height = s.width = 1
     s.channels, s.heads, s.layers, s.attn_blocks = cfg.channels, cfg.heads, cfg.layers, cfg.attn_blocks
     s.pos_enc, s.max_len, s.dtype = int(cfg.pos_enc), cfg.max_len, _dtype_code(compute_dtype)
+    s.eps_gn, s.eps_ln, s.ln_fold = GN_EPS, LN_EPS, _ln_fold(cfg)
     with torch.cuda.device(device):
         _lib.check(lib.nmm_pack_params(C.byref(s), C.byref(p), packed.data_ptr(), nbytes, _stream_ptr(device)))
     del keep
@@ -244,7 +253,7 @@ def _shape_for_tokens(cfg: ModuleConfig, B: int, F: int, H: int, W: int, dtype: 
     s.batch, s.channels, s.frames, s.height, s.width = B, cfg.channels, F, H, W
     s.heads, s.layers, s.attn_blocks = cfg.heads, cfg.layers, cfg.attn_blocks
     s.pos_enc, s.max_len, s.dtype = int(cfg.pos_enc), cfg.max_len, _dtype_code(dtype)
-    s.eps_gn, s.eps_ln = GN_EPS, LN_EPS
+    s.eps_gn, s.eps_ln, s.ln_fold = GN_EPS, LN_EPS, 0
     P = H * W
     s.x_stride_b, s.x_stride_c, s.x_stride_f = cfg.channels * F * P, F * P, P
     s.y_stride_b, s.y_stride_c, s.y_stride_f = F * cfg.channels * P, P, cfg.channels * P
