@@ -136,6 +136,22 @@ __device__ __forceinline__ float gelu_erf_fast(float v) {
     return 0.5f * v * (1.0f + copysignf(erf_abs, v));
 }
 
+// GELU(v) = v * Phi(v) with the normal CDF as a logistic of an odd polynomial, Phi(v) ~= 1 / (1 + exp(-v (a + b v^2 + c v^4))),
+// coefficients from a minimax fit of |v * (Phi_fit - Phi)| over [0, 8] (scripts: see DESIGN.md): max |GELU error| = 2.5e-5 absolute.
+// 8 FMA/ALU-pipe instructions + 2 SFU ops (ex2, rcp) instead of ~22: the GEGLU epilogue at K = 320 is instruction-issue bound
+// (128 x 128 GELUs per tile against 2560 MMA cycles).  Only used where the result is rounded to bf16 (ulp 2^-8 relative).
+__device__ __forceinline__ float gelu_logistic(float v) {
+    constexpr float L2E = 1.4426950408889634f;
+    const float vc = fminf(fmaxf(v, -8.5f), 8.5f);       // the fitted polynomial is valid on [-8.5, 8.5]; beyond, Phi is 0 / 1 to 1e-17
+    const float v2 = vc * vc;
+    float p = fmaf(0.0007030335782406193f * L2E, v2, -0.07401129205054635f * L2E);
+    p = fmaf(p, v2, -1.5950157685560156f * L2E);
+    const float e = exp2f(p * vc);                      // exp(-z), z = v (a + b v^2 + c v^4)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return v * r;
+}
+
 // ---- internal kernels' host launchers (defined in the .cu files) ----------------------------------
 // GroupNorm
 size_t gn_partial_bytes(const Geo &g);
