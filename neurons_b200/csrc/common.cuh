@@ -118,11 +118,14 @@ __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v 
 
 // exact (erf) GELU, as torch.nn.functional.gelu default -- motion_module_new.py:510-518
 __device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
-// Same function with erf from Abramowitz-Stegun 7.1.28, erf(x) = 1 - (1 + a1 x + ... + a6 x^6)^-16, |error| <= 3e-7:
-// branch-free, 6 FMA + 4 squarings + ONE SFU op (the approximate reciprocal).  Used by the bf16 GEMM epilogue, where
-// the SFU (16 lanes/clk/SM) and instruction-level parallelism bound the GEGLU epilogue and the result is rounded to bf16.
+// Same function from Abramowitz-Stegun 7.1.28, erfc(x) = (1 + a1 x + ... + a6 x^6)^-16 for x >= 0 (|error| <= 3e-7), written as
+//   GELU(v) = v * Phi(v),  Phi(v) = 1 - r/2 (v >= 0),  r/2 (v < 0),  r = erfc(|v| / sqrt 2)
+// branch-free, 16 instructions with ONE SFU op (the approximate reciprocal).  Used by the bf16 GEGLU epilogue, which is
+// instruction-issue bound at K = 320 (128 x 128 GELUs per tile against 2560 MMA cycles); SFU-heavier forms (logistic of a
+// polynomial: ex2 + rcp, measured 1.7x slower) and SFU-free polynomials (2e-4 error at degree 13) both lose on B200.
+// For |v| > ~15 the 16th power overflows to +inf and rcp gives exactly 0, i.e. Phi = 1 or 0 as it should.
 __device__ __forceinline__ float gelu_erf_fast(float v) {
-    const float x = fminf(fabsf(v) * 0.70710678118654752440f, 10.0f);
+    const float x = fabsf(v) * 0.70710678118654752440f;
     float p = fmaf(0.0000430638f, x, 0.0002765672f);
     p = fmaf(p, x, 0.0001520143f);
     p = fmaf(p, x, 0.0092705272f);
@@ -132,24 +135,8 @@ __device__ __forceinline__ float gelu_erf_fast(float v) {
     p = p * p; p = p * p; p = p * p; p = p * p;          // ^16
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p));
-    const float erf_abs = 1.0f - r;
-    return 0.5f * v * (1.0f + copysignf(erf_abs, v));
-}
-
-// GELU(v) = v * Phi(v) with the normal CDF as a logistic of an odd polynomial, Phi(v) ~= 1 / (1 + exp(-v (a + b v^2 + c v^4))),
-// coefficients from a minimax fit of |v * (Phi_fit - Phi)| over [0, 8] (scripts: see DESIGN.md): max |GELU error| = 2.5e-5 absolute.
-// 8 FMA/ALU-pipe instructions + 2 SFU ops (ex2, rcp) instead of ~22: the GEGLU epilogue at K = 320 is instruction-issue bound
-// (128 x 128 GELUs per tile against 2560 MMA cycles).  Only used where the result is rounded to bf16 (ulp 2^-8 relative).
-__device__ __forceinline__ float gelu_logistic(float v) {
-    constexpr float L2E = 1.4426950408889634f;
-    const float vc = fminf(fmaxf(v, -8.5f), 8.5f);       // the fitted polynomial is valid on [-8.5, 8.5]; beyond, Phi is 0 / 1 to 1e-17
-    const float v2 = vc * vc;
-    float p = fmaf(0.0007030335782406193f * L2E, v2, -0.07401129205054635f * L2E);
-    p = fmaf(p, v2, -1.5950157685560156f * L2E);
-    const float e = exp2f(p * vc);                      // exp(-z), z = v (a + b v^2 + c v^4)
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
-    return v * r;
+    const float hr = (0.5f * v) * r;                     // v * erfc(|x|) / 2
+    return v >= 0.f ? v - hr : hr;
 }
 
 // ---- internal kernels' host launchers (defined in the .cu files) ----------------------------------

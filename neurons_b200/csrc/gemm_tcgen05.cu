@@ -345,7 +345,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                                 v0 = __uint_as_float(r[4 * j]) + b4.x; g0 = __uint_as_float(r[4 * j + 1]) + b4.y;
                                 v1 = __uint_as_float(r[4 * j + 2]) + b4.z; g1 = __uint_as_float(r[4 * j + 3]) + b4.w;
                             }
-                            o[8 * hc + j] = pack_bf16x2(v0 * gelu_logistic(g0), v1 * gelu_logistic(g1));
+                            o[8 * hc + j] = pack_bf16x2(v0 * gelu_erf_fast(g0), v1 * gelu_erf_fast(g1));
                         }
                     }
                     if (lane == 0) ptx::bulk_wait_read0();                // the box of the previous chunk has been read
