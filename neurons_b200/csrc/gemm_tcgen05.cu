@@ -82,7 +82,10 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
     return v;
 }
 
-template <int EPI, int CG>
+// LNF: LayerNorm-folding roles compiled in (consumer transform / producer statistics).  Kept out of the default instantiation:
+// a run-time branch inside the unrolled epilogue loops costs the GEGLU epilogue its instruction-level parallelism (measured
+// 128 -> 204 us at C = 320).
+template <int EPI, int CG, bool LNF>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
                  const __grid_constant__ CUtensorMap tm_h,      // fp32 [M,N], box 32 x 32, 128-byte swizzle (residual load / h store)
@@ -215,7 +218,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const int half = ew >> 2;                                         // which of the quadrant's two warps
         const uint32_t box0 = epi_base + (uint32_t)ew * (uint32_t)p.epi_buf, box1 = box0 + 4096u, box2 = box0 + 8192u;
         // LayerNorm folding, consumer side: per-row mean / rstd of the A rows from the producer's partial sums (lane == row)
-        const bool ln_in = e.ln_part_in != nullptr;
+        const bool ln_in = LNF && e.ln_part_in != nullptr;
         float *xpose = reinterpret_cast<float *>(smem_raw + (box0 - ptx::smem_u32(smem_raw)));      // proj_out transpose buffer
         uint32_t lph0 = 0u, lph1 = 0u;                                    // phases of this warp's two residual-load barriers
         int as = 0; uint32_t aphase = 0;
@@ -424,7 +427,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     }
                     const bool want_o = e.out != nullptr;
                     const bool want_h = e.h != nullptr && !e.no_h_store;
-                    if (e.ln_part_out != nullptr) {                       // producer side of the LayerNorm folding
+                    if (LNF && e.ln_part_out != nullptr) {                // producer side of the LayerNorm folding
 #pragma unroll
                         for (int j = 0; j < 32; j++) { st1 += v[j]; st2 = fmaf(v[j], v[j], st2); }
                     }
@@ -454,7 +457,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 }
             }
             wait_acc();                                                   // a warp without a chunk in this tile still follows the phases
-            if (e.ln_part_out != nullptr && row0 + lane < p.M)            // slot = (N tile, which warp of the quadrant); zeros if no chunk
+            if (LNF && e.ln_part_out != nullptr && row0 + lane < p.M)     // slot = (N tile, which warp of the quadrant); zeros if no chunk
                 reinterpret_cast<float2 *>(e.ln_part_out)[(row0 + lane) * (2 * p.n_tiles) + n_blk * 2 + half] = make_float2(st1, st2);
             if (warp == 4 && lane == 0) TRACE(tile_no, 12);
             if (warp == 8 && lane == 0) TRACE(tile_no, 14);
@@ -580,10 +583,10 @@ void plan_linear_tc(int64_t M, int N, int K, int epilogue, int *block_n, int *cl
     *cluster = plan.cluster;
 }
 
-template <int EPI, int CG>
+template <int EPI, int CG, bool LNF>
 static int launch_tc_t(const CUtensorMap &ta, const CUtensorMap &tw, const CUtensorMap &th, const CUtensorMap &to, const TcParams &p,
                        const EpiParams &e, size_t smem, int grid, cudaStream_t st, double flops, double bytes) {
-    auto kern = linear_tc_kernel<EPI, CG>;
+    auto kern = linear_tc_kernel<EPI, CG, LNF>;
     static bool attr_set = false;     // per template instantiation
     if (!attr_set) {
         NMM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX));
@@ -674,9 +677,13 @@ int launch_linear_tc(const LinearArgs &a, cudaStream_t st) {
     const int grid = (int)(ctas < max_grid ? ctas : max_grid);
     EpiParams e = epi_params_of(a);
     const double fl = linear_flops(a), by = linear_bytes(a, 2);
+    const bool lnf = a.ln_part_in != nullptr || a.ln_part_out != nullptr;
 #define TC_DISPATCH(EPI)                                                                                   \
-    return p.cluster == 2 ? launch_tc_t<EPI, 2>(ta, tw, th, to, p, e, smem, grid, st, fl, by)              \
-                          : launch_tc_t<EPI, 1>(ta, tw, th, to, p, e, smem, grid, st, fl, by)
+    if (lnf)                                                                                               \
+        return p.cluster == 2 ? launch_tc_t<EPI, 2, true>(ta, tw, th, to, p, e, smem, grid, st, fl, by)    \
+                              : launch_tc_t<EPI, 1, true>(ta, tw, th, to, p, e, smem, grid, st, fl, by);   \
+    return p.cluster == 2 ? launch_tc_t<EPI, 2, false>(ta, tw, th, to, p, e, smem, grid, st, fl, by)       \
+                          : launch_tc_t<EPI, 1, false>(ta, tw, th, to, p, e, smem, grid, st, fl, by)
     switch (a.epilogue) {
         case NMM_EPI_STORE: TC_DISPATCH(NMM_EPI_STORE);
         case NMM_EPI_RESIDUAL: TC_DISPATCH(NMM_EPI_RESIDUAL);
