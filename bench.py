@@ -314,8 +314,15 @@ def main():
         # the GEMM is timed inside a long (multi-second) step -> sustained cuBLAS figure is the denominator
         peak_tf = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
         ach = gemm["flops"] / (gemm["total_ms"] * 1e-3) / 1e12 if gemm["total_ms"] > 0 else 0.0
+        traffic = None          # DRAM bytes per launch of the dominant kernel from the committed ncu capture of this same step
+        tpath = os.path.join(ROOT, "profiles", "r1_ncu_gemm_traffic.json")
+        if os.path.isfile(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
         roofline = {"kernel": "linear_tc_kernel (tcgen05 bf16 GEMM + fused epilogue)", "bound": "tensor", "achieved": ach,
-                    "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None, "traffic": None,
+                    "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None, "traffic": traffic,
+                    "traffic_note": "dram__bytes_read+write per launch, ncu capture of this step (profiles/r1_ncu_step_summary.txt); "
+                                    "algorithmic bytes per launch = %.1f MB" % (gemm["bytes"] / max(gemm["launches"], 1) / 1e6),
                     "peak_source": peaks["source"] + ", bf16_tflops_sustained", "launches": gemm["launches"],
                     "measured_over": f"a second pass of the same {args.steps} steps with a CUDA-event pair around every kernel launch "
                                      f"({ms_profiled / args.steps:.3f} ms/step with the events in the stream)",
