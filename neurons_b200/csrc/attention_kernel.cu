@@ -239,6 +239,9 @@ __device__ __forceinline__ void ldsm_x1_t(uint32_t addr, uint32_t &r0) {
 __device__ __forceinline__ void ldsm_x2_t(uint32_t addr, uint32_t &r0, uint32_t &r1) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
 }
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
 __device__ __forceinline__ void mma_k16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
@@ -394,6 +397,219 @@ __global__ void __launch_bounds__(256) temporal_attention_mma_kernel(const bf16 
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// Compile-time specialisation of the kernel above for the head sizes of the SD1.5 levels (d_h = 40 / 80 / 160 with 8 heads):
+// the head group is always W = 320 channels wide (8, 4 or 2 heads), so pitch, row offsets and every loop bound are constants.
+// The runtime-shaped kernel spends ~580 warp instructions per (position, head) problem, >50 % of them integer address
+// arithmetic (ncu: issue slots 81 % busy, ALU pipe 52 %, DRAM 52 %) -- i.e. it is issue-bound, not HBM-bound.  Here every
+// ldmatrix / st.shared address is base + immediate, the loops are fully unrolled and staging / write-back use a flat chunk
+// index, which removes most of that overhead.
+// ------------------------------------------------------------------------------------------------------------------------
+template <int F, int DH>      // F in {8, 16}; DH in {40, 80, 160}
+__global__ void __launch_bounds__(256) temporal_attention_mma_fixed_kernel(const bf16 *__restrict__ qkv, bf16 *__restrict__ ctx, int P, int C,
+                                                                           int PB, float scale_log2e) {
+    pdl_wait();
+    pdl_launch_dependents();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    bf16 *sm = reinterpret_cast<bf16 *>(smem_raw);
+    constexpr int W = 320, HB = W / DH, NT = F / 8;
+    constexpr int PITCH = 3 * W + 8;            // elements; 1936 B per row: (1936 / 4) % 32 == 4 -> ldmatrix rows hit distinct banks
+    constexpr uint32_t RS = PITCH * 2;          // row stride in bytes
+    constexpr int CHUNKS_IN = 3 * W / 8;        // 16-byte chunks per staged row (q|k|v)
+    constexpr int CHUNKS_OUT = W / 8;
+    const int c_off = blockIdx.y * W;
+    const int tiles_per_img = (P + PB - 1) / PB;
+    const int b = blockIdx.x / tiles_per_img;
+    const int p0 = (blockIdx.x - b * tiles_per_img) * PB;
+    const int npos = min(PB, P - p0);
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
+    const int rows = F * npos;                  // smem row r = pl * F + f
+    const uint32_t sm_u32 = (uint32_t)__cvta_generic_to_shared(sm);
+
+    {
+        // ---- stage q|k|v rows: one warp per row, 120 16-byte chunks = 4 cp.async per lane (the last with 24 lanes) ------------
+        // chunk w of a row lives at src_row + w * 8 + seg * (C - 320) elements, seg = w / 40 (the q | k | v segment)
+        const bf16 *src0 = qkv + ((int64_t)b * F * P + p0) * (3 * (int64_t)C) + c_off;
+        const uint32_t row_elems = 3u * (uint32_t)C, seg_skip = (uint32_t)(C - W);
+        for (uint32_t r = warp; r < (uint32_t)rows; r += nwarps) {
+            const uint32_t pl = r / F, f = r % F;                                     // F is a power of two
+            const bf16 *srow = src0 + (f * (uint32_t)P + pl) * row_elems + lane * 8;   // element offset < 2^31: checked by the launcher
+            const uint32_t drow = sm_u32 + r * RS + lane * 16;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (k < 3 || lane < 24) {
+                    const uint32_t seg = k == 0 ? 0u : k == 1 ? (lane >= 8 ? 1u : 0u) : k == 2 ? (lane >= 16 ? 2u : 1u) : 2u;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(drow + k * 512), "l"(srow + k * 256 + seg * seg_skip) : "memory");
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+    }
+
+    // ---- one warp per (position, head) ------------------------------------------------------------------------------------
+    const int lrow = lane & 7, lmat = lane >> 3;
+    const int crow = lane >> 2, ccol = (lane & 3) * 2;
+    for (int prob = warp; prob < npos * HB; prob += nwarps) {
+        const int pl = prob / HB, hd = prob - pl * HB;
+        const uint32_t qb = sm_u32 + (uint32_t)(pl * F) * RS + (uint32_t)(hd * DH * 2);
+        constexpr uint32_t KOFF = W * 2, VOFF = 2 * W * 2;
+        // per-lane ldmatrix base addresses (constant offsets are added as immediates below)
+        const uint32_t q_ld = qb + (F == 16 ? (uint32_t)(lrow + 8 * (lmat & 1)) * RS + (uint32_t)(16 * (lmat >> 1))
+                                            : (uint32_t)lrow * RS + (uint32_t)(16 * lmat));
+        const uint32_t k_ld = qb + KOFF + (uint32_t)lrow * RS + (uint32_t)(16 * lmat);          // 4 matrices = 32 columns (F == 8) ...
+        const uint32_t k_ld2 = qb + KOFF + (uint32_t)lrow * RS + (uint32_t)(16 * (lmat & 1));   // ... or 2 matrices = 16 columns
+        float s[NT][4];
+#pragma unroll
+        for (int j = 0; j < NT; j++) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; }
+        if constexpr (F == 8) {
+            // 32 head-dim columns per step: one ldmatrix.x4 for Q (rows 0-7), one for K (keys 0-7), two k16 MMAs
+#pragma unroll
+            for (int k0 = 0; k0 + 32 <= DH; k0 += 32) {
+                uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
+                ldsm_x4(q_ld + k0 * 2, a0, a1, a2, a3);
+                ldsm_x4(k_ld + k0 * 2, b0, b1, b2, b3);
+                mma_k16(s[0], a0, 0u, a1, 0u, b0, b1);
+                mma_k16(s[0], a2, 0u, a3, 0u, b2, b3);
+            }
+            constexpr int K1 = DH / 32 * 32;
+            if constexpr (DH - K1 >= 16) {
+                uint32_t a0, a2, b0, b1;
+                ldsm_x2(q_ld + K1 * 2, a0, a2);
+                ldsm_x2(k_ld + K1 * 2, b0, b1);
+                mma_k16(s[0], a0, 0u, a2, 0u, b0, b1);
+            }
+            constexpr int K2 = DH / 16 * 16;
+            if constexpr (DH - K2 == 8) {
+                uint32_t a0, b0;
+                ldsm_x1(q_ld + K2 * 2, a0);
+                ldsm_x1(k_ld + K2 * 2, b0);
+                mma_k8(s[0], a0, 0u, b0);
+            }
+        } else {
+#pragma unroll
+            for (int k0 = 0; k0 + 16 <= DH; k0 += 16) {
+                uint32_t a0, a1, a2, a3;
+                ldsm_x4(q_ld + k0 * 2, a0, a1, a2, a3);
+#pragma unroll
+                for (int j = 0; j < NT; j++) {
+                    uint32_t b0, b1;
+                    ldsm_x2(k_ld2 + (uint32_t)(8 * j) * RS + k0 * 2, b0, b1);
+                    mma_k16(s[j], a0, a1, a2, a3, b0, b1);
+                }
+            }
+            constexpr int K2 = DH / 16 * 16;
+            if constexpr (DH - K2 == 8) {
+                uint32_t a0, a1;
+                ldsm_x2(qb + (uint32_t)(lrow + 8 * (lmat & 1)) * RS + K2 * 2, a0, a1);
+#pragma unroll
+                for (int j = 0; j < NT; j++) {
+                    uint32_t b0;
+                    ldsm_x1(qb + KOFF + (uint32_t)(8 * j + lrow) * RS + K2 * 2, b0);
+                    mma_k8(s[j], a0, a1, b0);
+                }
+            }
+        }
+        // softmax (fp32, base-2 exponentials) over the keys of row crow (regs 0,1) and row crow + 8 (regs 2,3; F == 16 only)
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < NT; j++) { mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1])); mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3])); }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        if constexpr (F == 16) { mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2)); }
+        float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < NT; j++) {
+            s[j][0] = exp2f((s[j][0] - mx0) * scale_log2e); s[j][1] = exp2f((s[j][1] - mx0) * scale_log2e);
+            sum0 += s[j][0] + s[j][1];
+            if constexpr (F == 16) {
+                s[j][2] = exp2f((s[j][2] - mx1) * scale_log2e); s[j][3] = exp2f((s[j][3] - mx1) * scale_log2e);
+                sum1 += s[j][2] + s[j][3];
+            }
+        }
+        sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+        if constexpr (F == 16) { sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2); }
+        const float inv0 = 1.0f / sum0, inv1 = (F == 16) ? 1.0f / sum1 : 0.f;
+        uint32_t ph[4] = {0u, 0u, 0u, 0u}, pl_[4] = {0u, 0u, 0u, 0u};
+        split_bf16x2(s[0][0] * inv0, s[0][1] * inv0, ph[0], pl_[0]);
+        if constexpr (F == 16) {
+            split_bf16x2(s[0][2] * inv1, s[0][3] * inv1, ph[1], pl_[1]);
+            split_bf16x2(s[1][0] * inv0, s[1][1] * inv0, ph[2], pl_[2]);
+            split_bf16x2(s[1][2] * inv1, s[1][3] * inv1, ph[3], pl_[3]);
+        }
+        __syncwarp();                                   // all of this warp's reads of the q rows are done: reuse them for O
+        // O = P V: one ldmatrix.x4.trans feeds 32 (F == 8) or 16 (F == 16) output columns
+        const uint32_t o_st = qb + (uint32_t)crow * RS + (uint32_t)(ccol * 2);
+        if constexpr (F == 8) {
+            const uint32_t v_ld = qb + VOFF + (uint32_t)lrow * RS + (uint32_t)(16 * lmat);
+#pragma unroll
+            for (int n0 = 0; n0 + 32 <= DH; n0 += 32) {
+                uint32_t bv[4];
+                ldsm_x4_t(v_ld + n0 * 2, bv[0], bv[1], bv[2], bv[3]);
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    float o[4] = {0.f, 0.f, 0.f, 0.f};
+                    mma_k8(o, ph[0], 0u, bv[q]);
+                    mma_k8(o, pl_[0], 0u, bv[q]);
+                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(o_st + (n0 + 8 * q) * 2), "r"(pack_bf16x2(o[0], o[1])) : "memory");
+                }
+            }
+            constexpr int N1 = DH / 32 * 32;
+#pragma unroll
+            for (int n0 = N1; n0 < DH; n0 += 8) {
+                uint32_t b0;
+                ldsm_x1_t(qb + VOFF + (uint32_t)lrow * RS + n0 * 2, b0);
+                float o[4] = {0.f, 0.f, 0.f, 0.f};
+                mma_k8(o, ph[0], 0u, b0);
+                mma_k8(o, pl_[0], 0u, b0);
+                asm volatile("st.shared.b32 [%0], %1;" ::"r"(o_st + n0 * 2), "r"(pack_bf16x2(o[0], o[1])) : "memory");
+            }
+        } else {
+            // matrices: (keys 0-7, n0), (keys 8-15, n0), (keys 0-7, n0 + 8), (keys 8-15, n0 + 8)
+            const uint32_t v_ld = qb + VOFF + (uint32_t)(lrow + 8 * (lmat & 1)) * RS + (uint32_t)(16 * (lmat >> 1));
+#pragma unroll
+            for (int n0 = 0; n0 + 16 <= DH; n0 += 16) {
+                uint32_t bv[4];
+                ldsm_x4_t(v_ld + n0 * 2, bv[0], bv[1], bv[2], bv[3]);
+#pragma unroll
+                for (int q = 0; q < 2; q++) {
+                    float o[4] = {0.f, 0.f, 0.f, 0.f};
+                    mma_k16(o, ph[0], ph[1], ph[2], ph[3], bv[2 * q], bv[2 * q + 1]);
+                    mma_k16(o, pl_[0], pl_[1], pl_[2], pl_[3], bv[2 * q], bv[2 * q + 1]);
+                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(o_st + (n0 + 8 * q) * 2), "r"(pack_bf16x2(o[0], o[1])) : "memory");
+                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(o_st + 8 * RS + (n0 + 8 * q) * 2), "r"(pack_bf16x2(o[2], o[3])) : "memory");
+                }
+            }
+            constexpr int N1 = DH / 16 * 16;
+            if constexpr (DH - N1 == 8) {
+                uint32_t b0, b1;
+                ldsm_x2_t(qb + VOFF + (uint32_t)(lrow + 8 * (lmat & 1)) * RS + N1 * 2, b0, b1);
+                float o[4] = {0.f, 0.f, 0.f, 0.f};
+                mma_k16(o, ph[0], ph[1], ph[2], ph[3], b0, b1);
+                mma_k16(o, pl_[0], pl_[1], pl_[2], pl_[3], b0, b1);
+                asm volatile("st.shared.b32 [%0], %1;" ::"r"(o_st + N1 * 2), "r"(pack_bf16x2(o[0], o[1])) : "memory");
+                asm volatile("st.shared.b32 [%0], %1;" ::"r"(o_st + 8 * RS + N1 * 2), "r"(pack_bf16x2(o[2], o[3])) : "memory");
+            }
+        }
+    }
+    {
+        __syncthreads();
+        // ---- write ctx rows: one warp per row, 40 16-byte chunks (lanes 0-31, then lanes 0-7) ----------------------------------
+        bf16 *dst0 = ctx + ((int64_t)b * F * P + p0) * (int64_t)C + c_off;
+        for (uint32_t r = warp; r < (uint32_t)rows; r += nwarps) {
+            const uint32_t pl = r / F, f = r % F;
+            const bf16 *srow = sm + r * PITCH + lane * 8;
+            bf16 *drow = dst0 + (f * (uint32_t)P + pl) * (uint32_t)C + lane * 8;
+            const uint4 v0 = *reinterpret_cast<const uint4 *>(srow);
+            uint4 v1 = make_uint4(0u, 0u, 0u, 0u);
+            if (lane < 8) v1 = *reinterpret_cast<const uint4 *>(srow + 256);
+            *reinterpret_cast<uint4 *>(drow) = v0;
+            if (lane < 8) *reinterpret_cast<uint4 *>(drow + 256) = v1;
+        }
+    }
+}
+
 // bf16, F in {8, 16}, d_h % 8 == 0, 16-byte aligned: the tensor-core kernel.  Returns -100 when the shape is not eligible.
 static int launch_attn_mma(const Geo &g, const bf16 *qkv, bf16 *ctx, cudaStream_t st) {
     if (!(g.F == 8 || g.F == 16) || g.dh % 8 != 0 || g.dh < 8) return -100;
@@ -402,6 +618,42 @@ static int launch_attn_mma(const Geo &g, const bf16 *qkv, bf16 *ctx, cudaStream_
     for (int hb = g.heads; hb >= 1; hb--)
         if (g.heads % hb == 0 && (hb * g.dh) % 64 == 0 && hb * g.dh <= 320) { HB = hb; break; }
     if (HB == 0) return -100;
+    // SD1.5 levels (d_h = 40 / 80 / 160, head groups of exactly 320 channels): compile-time specialised kernel
+    if ((g.dh == 40 || g.dh == 80 || g.dh == 160) && HB * g.dh == 320 && (int64_t)g.F * g.P * 3 * g.C < (1ll << 31) && !getenv("NMM_ATTN_GENERIC")) {
+        const size_t row_b = (size_t)(3 * 320 + 8) * 2;
+        static const int pb_env = getenv("NMM_ATTN_PB") ? atoi(getenv("NMM_ATTN_PB")) : 0;
+        int PBf = pb_env > 0 ? pb_env : (int)((40 * 1024) / (g.F * row_b));
+        if (PBf < 1) PBf = 1;
+        if (PBf > g.P) PBf = g.P;
+        if (pb_env <= 0)                                                 // small levels: more, smaller CTAs until the grid is >= 4 per SM
+            while (PBf > 1 && (int64_t)g.B * ceil_div(g.P, PBf) * (g.heads / HB) < 4 * 148) PBf--;
+        const size_t smem_f = (size_t)PBf * g.F * row_b;
+        if (smem_f > 200 * 1024) return fail(NMM_ERR_UNSUPPORTED, "attention tile of %d positions needs %zu bytes of shared memory", PBf, smem_f);
+        const int64_t nblk = (int64_t)g.B * ceil_div(g.P, PBf);
+        if (nblk > 0x7fffffff) return -100;
+        const dim3 gridf((unsigned)nblk, (unsigned)(g.heads / HB));
+        const float sl2 = (1.0f / sqrtf((float)g.dh)) * 1.4426950408889634f;
+        const int thr_f = std::min(256, std::max(128, PBf * HB * 32));      // one warp per problem, at least 4 warps for staging
+#define ATTN_FIXED(FF, DD)                                                                                               \
+    do {                                                                                                                 \
+        auto kern = temporal_attention_mma_fixed_kernel<FF, DD>;                                                         \
+        static bool attr_set = false;                                                                                    \
+        if (!attr_set) {                                                                                                 \
+            NMM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));            \
+            attr_set = true;                                                                                             \
+        }                                                                                                                \
+        ProfScope prof(K_ATTENTION, st, 4.0 * g.N * g.F * g.C, 4.0 * g.N * g.C * 2);                                      \
+        launch_pdl(kern, gridf, thr_f, smem_f, st, qkv, ctx, g.P, g.C, PBf, sl2);                                          \
+    } while (0)
+        if (g.F == 8) {
+            if (g.dh == 40) ATTN_FIXED(8, 40); else if (g.dh == 80) ATTN_FIXED(8, 80); else ATTN_FIXED(8, 160);
+        } else {
+            if (g.dh == 40) ATTN_FIXED(16, 40); else if (g.dh == 80) ATTN_FIXED(16, 80); else ATTN_FIXED(16, 160);
+        }
+#undef ATTN_FIXED
+        NMM_LAUNCHED("temporal_attention_mma_fixed_kernel");
+        return NMM_OK;
+    }
     const int W = HB * g.dh;
     const size_t row_bytes = (size_t)(3 * W + 8) * 2;
     int PB = (int)((40 * 1024) / (g.F * row_bytes));                  // <= 40 KB per CTA: ~5 CTAs per SM

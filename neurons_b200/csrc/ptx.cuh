@@ -72,6 +72,15 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *m, uint32_t src_
                  : "l"(reinterpret_cast<uint64_t>(m)), "r"(src_smem), "r"(c0), "r"(c1)
                  : "memory");
 }
+// 1-D bulk copies (no tensor map): global -> shared completing on an mbarrier, shared -> global in a bulk group.
+// Addresses and sizes are multiples of 16 bytes.
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store_1d(void *dst, uint32_t src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until the shared-memory SOURCE of all of this thread's committed bulk stores has been read (buffers reusable)
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }

@@ -43,7 +43,9 @@ def main():
     ap.add_argument("--latent", type=int, default=64)
     ap.add_argument("--out", default="gpurun_out/stage_bench.json")
     ap.add_argument("--levels", default="320,640,1280", help="channel counts; 'C@side' overrides the latent side, e.g. 1280@8")
+    ap.add_argument("--only", default="", help="comma-separated substrings: run only the stages whose name contains one")
     a = ap.parse_args()
+    only = [t for t in a.only.split(",") if t]
     dev = torch.device("cuda", 0)
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.isfile(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -84,6 +86,8 @@ def main():
             ("proj_out C->C  nchw+x", lambda: ops.linear(act, w_cc, bias, nlib.EPI_OUTPUT, cfg=cfg, x=x), 2.0 * M * C * C, M * C * es * 3),
         ]
         for name, fn, flops, byts in stages:
+            if only and not any(t in name for t in only):
+                continue
             ms = timed(fn, flush)
             rows.append(dict(C=C, side=side, M=M, stage=name, ms=ms, tflops=flops / ms / 1e9, gbps=byts / ms / 1e6,
                              frac_tensor=flops / ms / 1e9 / peaks["bf16_tflops"], frac_hbm=byts / ms / 1e6 / peaks["hbm_gbs"]))
