@@ -149,6 +149,13 @@ NMM_API int nmm_groupnorm_stats(const nmm_shape *s, const void *x, float *mean, 
  * tokens: [N, C] of s->dtype.  gn_w/gn_b: fp32 [C]. */
 NMM_API int nmm_groupnorm_tokens(const nmm_shape *s, const void *x, const float *gn_w, const float *gn_b, void *tokens,
                          void *workspace, size_t workspace_bytes, void *stream);
+/* GroupNorm + re-layout + proj_in in ONE tensor-core kernel (bf16 only): motion_module.py:142-145.
+ * h_out[N, C_out] fp32 = GroupNorm(x) as tokens . W^T + bias.  The A tiles are TMA-loaded straight from x (channel rows of positions,
+ * an M-major operand) and normalised in shared memory, so the token tensor is never materialised.  W: [C_out, C] bf16; bias: fp32 [C_out]
+ * or NULL.  Needs H*W % 64 == 0, N % 128 == 0, 16-byte aligned x / strides; otherwise NMM_ERR_UNSUPPORTED (use
+ * nmm_groupnorm_tokens + nmm_linear; nmm_forward picks automatically). */
+NMM_API int nmm_groupnorm_linear(const nmm_shape *s, const void *x, const float *gn_w, const float *gn_b, const void *W, int32_t c_out,
+                         const float *bias, float *h_out, void *workspace, size_t workspace_bytes, void *stream);
 /* LayerNorm(C, eps_ln) (+ sinusoidal PE of the token's frame): motion_module.py:212 + :277-278 (pe != NULL)
  * or :219 (pe == NULL).  h: fp32 [N,C]; out: [N,C] of s->dtype; w,b: fp32 [C]; pe: fp32 [max_len,C]. */
 NMM_API int nmm_layernorm_pe(const nmm_shape *s, const float *h, const float *w, const float *b, const float *pe,

@@ -449,7 +449,9 @@ int nmm_forward(const nmm_shape *s, const void *x, void *y, const void *packed, 
         char *yc = (char *)y + (size_t)p0 * es;
 
         // normalise + re-layout to token-major                                          :142-144
-        if ((rc = launch_gn_tokens(gc, &sc, g, xc, gn_partial, F32(L.gn_w), F32(L.gn_b), tok, st)) != NMM_OK) return rc;
+        // bf16, whole image, 64-position aligned: proj_in TMA-loads x itself and normalises the tile in shared memory (no token buffer)
+        const bool gn_fused = g.dtype == NMM_BF16 && !g.ln_fold && pn == g.P && linear_tc_gn_fusable(gc.N, pn, x, s->x_stride_b, s->x_stride_c, s->x_stride_f);
+        if (!gn_fused && (rc = launch_gn_tokens(gc, &sc, g, xc, gn_partial, F32(L.gn_w), F32(L.gn_b), tok, st)) != NMM_OK) return rc;
 
         LinearArgs a;
         memset(&a, 0, sizeof(a));
@@ -479,7 +481,12 @@ int nmm_forward(const nmm_shape *s, const void *x, void *y, const void *packed, 
         // proj_in -> fp32 residual stream h                                             :145
         a.epilogue = NMM_EPI_STORE; a.N = g.C; a.K = g.C; a.A = tok; a.W = pk + L.w_in; a.bias = F32(L.b_in); a.h = h; a.out = nullptr;
         producer(a);
+        if (gn_fused) {
+            a.A = nullptr; a.gn_x = x; a.gn_partial = gn_partial; a.gn_splits = gn_splits_of(g);
+            a.gn_count = (double)(g.C / NMM_GN_GROUPS) * g.P; a.gn_eps = s->eps_gn; a.gn_w = F32(L.gn_w); a.gn_b = F32(L.gn_b); a.gn_B = g.B;
+        }
         if ((rc = linear(g, a, st)) != NMM_OK) return rc;
+        a.gn_x = nullptr;
         clear_fold(a);
 
         for (int l = 0; l < g.layers; l++) {
@@ -545,6 +552,28 @@ int nmm_groupnorm_tokens(const nmm_shape *s, const void *x, const float *gn_w, c
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = launch_gn_stats(g, s, x, (double *)workspace, st)) != NMM_OK) return rc;
     return launch_gn_tokens(g, s, g, x, (const double *)workspace, gn_w, gn_b, tokens, st);
+}
+
+int nmm_groupnorm_linear(const nmm_shape *s, const void *x, const float *gn_w, const float *gn_b, const void *W, int32_t c_out,
+                         const float *bias, float *h_out, void *workspace, size_t workspace_bytes, void *stream) {
+    int rc = validate(s);
+    if (rc != NMM_OK) return rc;
+    if (!x || !gn_w || !gn_b || !W || !h_out || !workspace) return fail(NMM_ERR_BAD_ARG, "NULL argument");
+    if ((rc = device_check()) != NMM_OK) return rc;
+    const Geo g = geo_of(s);
+    if (g.dtype != NMM_BF16) return fail(NMM_ERR_UNSUPPORTED, "nmm_groupnorm_linear is bf16 only");
+    if (!linear_tc_gn_fusable(g.N, g.P, x, s->x_stride_b, s->x_stride_c, s->x_stride_f))
+        return fail(NMM_ERR_UNSUPPORTED, "nmm_groupnorm_linear needs H*W %% 64 == 0, N %% 128 == 0 and 16-byte aligned x / strides");
+    if (workspace_bytes < gn_partial_bytes(g)) return fail(NMM_ERR_WORKSPACE, "workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = launch_gn_stats(g, s, x, (double *)workspace, st)) != NMM_OK) return rc;
+    LinearArgs a;
+    memset(&a, 0, sizeof(a));
+    a.epilogue = NMM_EPI_STORE; a.M = g.N; a.N = c_out; a.K = g.C; a.W = W; a.bias = bias; a.h = h_out;
+    a.F = g.F; a.P = g.P; a.xsb = s->x_stride_b; a.xsc = s->x_stride_c; a.xsf = s->x_stride_f;
+    a.gn_x = x; a.gn_partial = (const double *)workspace; a.gn_splits = gn_splits_of(g); a.gn_count = (double)(g.C / NMM_GN_GROUPS) * g.P;
+    a.gn_eps = s->eps_gn; a.gn_w = gn_w; a.gn_b = gn_b; a.gn_B = g.B;
+    return launch_linear_tc(a, st);
 }
 
 int nmm_layernorm_pe(const nmm_shape *s, const float *h, const float *w, const float *b, const float *pe, void *out, void *stream) {

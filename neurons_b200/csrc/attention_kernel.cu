@@ -415,8 +415,6 @@ __global__ void __launch_bounds__(256) temporal_attention_mma_fixed_kernel(const
     constexpr int W = 320, HB = W / DH, NT = F / 8;
     constexpr int PITCH = 3 * W + 8;            // elements; 1936 B per row: (1936 / 4) % 32 == 4 -> ldmatrix rows hit distinct banks
     constexpr uint32_t RS = PITCH * 2;          // row stride in bytes
-    constexpr int CHUNKS_IN = 3 * W / 8;        // 16-byte chunks per staged row (q|k|v)
-    constexpr int CHUNKS_OUT = W / 8;
     const int c_off = blockIdx.y * W;
     const int tiles_per_img = (P + PB - 1) / PB;
     const int b = blockIdx.x / tiles_per_img;

@@ -142,6 +142,21 @@ __device__ __forceinline__ float gelu_erf_fast(float v) {
 // ---- internal kernels' host launchers (defined in the .cu files) ----------------------------------
 // GroupNorm
 size_t gn_partial_bytes(const Geo &g);
+int gn_splits_of(const Geo &g);          // partial (sum, sumsq) pairs per (b, f, group) written by gn_stats
+// mean / rstd of one (b, f, group) from the partial sums of gn_stats (fp64 accumulation; biased variance, as torch.nn.GroupNorm)
+__device__ __forceinline__ void gn_finalize_one(const double *__restrict__ partial, int bf_grp, int splits, double count, float eps,
+                                                float &mean, float &rstd) {
+    double a = 0, c2 = 0;
+    for (int i = 0; i < splits; i++) {
+        a += partial[((int64_t)bf_grp * splits + i) * 2 + 0];
+        c2 += partial[((int64_t)bf_grp * splits + i) * 2 + 1];
+    }
+    double m = a / count;
+    double var = c2 / count - m * m;
+    if (var < 0) var = 0;
+    mean = (float)m;
+    rstd = (float)(1.0 / sqrt(var + (double)eps));
+}
 int launch_gn_stats(const Geo &g, const nmm_shape *s, const void *x, double *partial, cudaStream_t st);
 int launch_gn_finalize(const Geo &g, const nmm_shape *s, const double *partial, float *mean, float *rstd, cudaStream_t st);
 int launch_gn_tokens(const Geo &g, const nmm_shape *s, const Geo &full, const void *x, const double *partial, const float *gn_w,
@@ -167,6 +182,14 @@ struct LinearArgs {
     const void *x; void *y;
     int F, P;
     int64_t xsb, xsc, xsf, ysb, ysc, ysf;
+    // GroupNorm-fused A operand (bf16 tensor-core path, STORE epilogue: proj_in).  A is NULL; the A tiles are TMA-loaded straight
+    // from x [b, c, f, p] (channel rows of positions = an M-major operand), normalised in shared memory
+    // (x * rstd*gamma[c] + beta[c] - mean*rstd*gamma[c], rounded to bf16 exactly like the stand-alone gn_tokens kernel) and fed to
+    // the tensor core through an MN-major descriptor.  Uses F, P, xsb/xsc/xsf above; needs P % 64 == 0 and M % 128 == 0.
+    const void *gn_x;
+    const double *gn_partial; int gn_splits; double gn_count; float gn_eps;
+    const float *gn_w, *gn_b;
+    int gn_B;
     // LayerNorm folding (bf16 tensor-core path only; see gemm_tcgen05.cu "LayerNorm folding"):
     //   producer side: this GEMM writes the residual stream -> also emit per-row partial (sum, sum of squares) of the new h
     float *ln_part_out;      // [M][NMM_LN_PARTS][2] fp32 or null
@@ -181,6 +204,7 @@ struct LinearArgs {
 constexpr int NMM_LN_PARTS = 16;     // partial-statistics slots per row: 2 epilogue warps x up to 8 N tiles of the producer
 // N tile / CTA-pair plan the tensor-core GEMM will use for (M, N, K): lets the caller know how many partial-statistics slots
 // a producer GEMM fills (2 * N / block_n)
+bool linear_tc_gn_fusable(int64_t M, int P, const void *x, int64_t sb, int64_t sc, int64_t sf);
 void plan_linear_tc(int64_t M, int N, int K, int epilogue, int *block_n, int *cluster);
 // algorithmic work of one Linear launch: 2*M*N*K flops; bytes = operands once + epilogue traffic once
 inline double linear_flops(const LinearArgs &a) { return 2.0 * (double)a.M * a.N * a.K; }

@@ -55,6 +55,18 @@ struct TcParams {
     int debug;               // NMM_GEMM_DEBUG (timing experiments only, results invalid): 1 = epilogue does nothing, 2 = no TMA loads
 };
 
+// GroupNorm-fused A operand (GNA instantiation): where the statistics and affine parameters live, and the x geometry
+struct GnParams {
+    const double *partial;   // [b*f*32][splits][2] from gn_stats
+    const float *gamma, *beta;
+    int splits;
+    double count;
+    float eps;
+    int C, F, P;
+};
+constexpr int TC_GN_WARPS = 4;                            // GNA: warps 12-15 normalise the A tile in shared memory (one 128-byte row each)
+constexpr int TC_A_HALF = TC_A_BYTES / 2;                 // GNA: the A stage is two boxes of 64 channels x 64 positions
+
 #ifdef NMM_TRACE
 // event slots per tile (CTA 0 only, first TRACE_TILES tiles): 0 mma:tile start, 1 mma:accumulator free, 2 mma:first stage full,
 // 3 mma:all issued, 4 prod:first load issued, 5 prod:last load issued, 6 epi(w4):before tfull wait, 7 epi:accumulator ready,
@@ -85,12 +97,12 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 // LNF: LayerNorm-folding roles compiled in (consumer transform / producer statistics).  Kept out of the default instantiation:
 // a run-time branch inside the unrolled epilogue loops costs the GEGLU epilogue its instruction-level parallelism (measured
 // 128 -> 204 us at C = 320).
-template <int EPI, int CG, bool LNF>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int EPI, int CG, bool LNF, bool GNA>
+__global__ void __launch_bounds__(GNA ? TC_THREADS + 32 * TC_GN_WARPS : TC_THREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
                  const __grid_constant__ CUtensorMap tm_h,      // fp32 [M,N], box 32 x 32, 128-byte swizzle (residual load / h store)
                  const __grid_constant__ CUtensorMap tm_o,      // bf16 [M,N or N/2], box 32 x 32, 64-byte swizzle (`out` store)
-                 TcParams p, EpiParams e) {
+                 TcParams p, EpiParams e, GnParams gn) {
     // CG == 1: one CTA per 128 x block_n tile (tcgen05.mma.cta_group::1).
     // CG == 2: a CTA pair (cluster of 2 along M) computes a 256 x block_n tile with ONE tcgen05.mma.cta_group::2 stream issued
     //          by the even CTA: each CTA stages its own 128 rows of A and HALF of the W tile (block_n/2 rows); the tensor core
@@ -107,6 +119,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * p.stages + 2 + s); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * p.stages + 4);
     auto load_bar = [&](int ew, int b) { return bar_base + 512u + 8u * (ew * 2 + b); };
+    auto conv_bar = [&](int s) { return bar_base + 768u + 8u * s; };          // GNA: A tile of stage s normalised
     const uint32_t epi_base = bar_base + TC_BAR_BYTES;                          // 8 x 8 KB, 1024-byte aligned
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -128,6 +141,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         // tmem_empty collects one arrive per epilogue warp of every CTA of the pair (it lives in the MMA-issuing CTA)
         for (int s = 0; s < 2; s++) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), TC_EPI_WARPS * CG); }
         for (int w = 0; w < TC_EPI_WARPS; w++) { ptx::mbar_init(load_bar(w, 0), 1); ptx::mbar_init(load_bar(w, 1), 1); }
+        if (GNA) for (int s = 0; s < p.stages; s++) ptx::mbar_init(conv_bar(s), TC_GN_WARPS);
         ptx::fence_mbar_init();
     }
     if (warp == 2) ptx::tmem_alloc<CG>(tmem_slot, (uint32_t)p.tmem_cols);
@@ -158,6 +172,15 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                             for (int r0 = 0; r0 < TC_BM; r0 += 32)
                                 ptx::tma_prefetch_l2_2d(&tm_h, n_blk * p.block_n + c0, (int32_t)(m_blk * TC_BM + r0));
                 }
+                int gp[2] = {0, 0}, gf[2] = {0, 0}, gb[2] = {0, 0};     // GNA: (position, frame, batch) of the tile's two 64-token halves
+                if constexpr (GNA) {
+#pragma unroll
+                    for (int j = 0; j < 2; j++) {
+                        const int64_t n = m_blk * TC_BM + 64 * j;
+                        const int bf = (int)(n / gn.P);
+                        gp[j] = (int)(n - (int64_t)bf * gn.P); gb[j] = bf / gn.F; gf[j] = bf - gb[j] * gn.F;
+                    }
+                }
                 for (int kb = 0; kb < num_kb; kb++) {
                     ptx::mbar_wait(empty_bar(stage), phase ^ 1u);       // the MMAs that read this stage have retired
                     if (kb == 0) TRACE(tile_no, 4);
@@ -165,6 +188,12 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
                     if (p.debug & 2) {                                  // timing experiment: MMA on whatever is in shared memory
                         if (leader) ptx::mbar_arrive(full_bar(stage));
+                    } else if (GNA) {
+                        // A = x[b, kb*64 .. +64 channels, f, 64 positions] for each half of the 128-token tile (M-major boxes)
+                        ptx::mbar_expect_tx(full_bar(stage), stage_bytes);
+                        ptx::tma_load_4d(&tm_a, full_bar(stage), sa, gp[0], kb * TC_BK, gf[0], gb[0]);
+                        ptx::tma_load_4d(&tm_a, full_bar(stage), sa + TC_A_HALF, gp[1], kb * TC_BK, gf[1], gb[1]);
+                        ptx::tma_load_2d(&tm_w, full_bar(stage), sa + TC_A_BYTES, kb * TC_BK, n_blk * p.block_n);
                     } else if (CG == 1) {
                         ptx::mbar_expect_tx(full_bar(stage), stage_bytes);
                         ptx::tma_load_2d(&tm_a, full_bar(stage), sa, kb * TC_BK, (int32_t)(m_blk * TC_BM));
@@ -183,7 +212,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     } else if (warp == 1) {
         // ===================== MMA issuer (one thread of the even CTA) =====================
         if (lane == 0 && leader) {
-            const uint32_t idesc = ptx::umma_idesc_bf16(TC_BM * CG, (uint32_t)p.block_n);
+            const uint32_t idesc = ptx::umma_idesc_bf16(TC_BM * CG, (uint32_t)p.block_n) | (GNA ? ptx::UMMA_IDESC_A_MN_MAJOR : 0u);
             int stage = 0; uint32_t phase = 0;
             int as = 0; uint32_t aphase = 0;
             int tile_no = 0;
@@ -194,15 +223,31 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.block_n);
                 for (int kb = 0; kb < num_kb; kb++) {
-                    ptx::mbar_wait(full_bar(stage), phase);              // TMA bytes (of both CTAs) have landed
+                    // TMA bytes (of both CTAs) have landed; GNA: ... and the converter warps have normalised the A tile
+                    ptx::mbar_wait(GNA ? conv_bar(stage) : full_bar(stage), phase);
                     if (kb == 0) TRACE(tile_no, 2);
                     ptx::tc_fence_after();
                     const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
-                    const uint64_t a_desc = ptx::umma_smem_desc_sw128(sa);
                     const uint64_t b_desc = ptx::umma_smem_desc_sw128(sa + TC_A_BYTES);
+                    if constexpr (GNA) {
+                        // M-major A: 64-position blocks 8 KB apart (LBO), 8-channel groups 1 KB apart (SBO); K = 16 channels = 2 KB
+                        const uint64_t a_desc = ptx::umma_smem_desc_mn_sw128(sa, TC_A_HALF, 1024);
+                        if (p.debug & 16) {            // timing experiment: K-major descriptors on the same bytes (results invalid)
+                            const uint64_t a_k = ptx::umma_smem_desc_sw128(sa);
+                            const uint32_t idk = idesc & ~ptx::UMMA_IDESC_A_MN_MAJOR;
 #pragma unroll
-                    for (int k = 0; k < TC_BK / 16; k++)                 // +32 bytes per K=16 step inside the swizzle atom
-                        ptx::umma_bf16<CG>(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                            for (int k = 0; k < TC_BK / 16; k++)
+                                ptx::umma_bf16<CG>(d_tmem, a_k + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idk, (kb | k) != 0 ? 1u : 0u);
+                        } else
+#pragma unroll
+                        for (int k = 0; k < TC_BK / 16; k++)
+                            ptx::umma_bf16<CG>(d_tmem, a_desc + (uint64_t)(k * (2048 >> 4)), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                    } else {
+                        const uint64_t a_desc = ptx::umma_smem_desc_sw128(sa);
+#pragma unroll
+                        for (int k = 0; k < TC_BK / 16; k++)             // +32 bytes per K=16 step inside the swizzle atom
+                            ptx::umma_bf16<CG>(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
                     ptx::umma_commit<CG>(empty_bar(stage));               // stage reusable (in both CTAs) once these MMAs retire
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
@@ -211,7 +256,59 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 if (++as == 2) { as = 0; aphase ^= 1u; }
             }
         }
-    } else if (warp >= 4) {
+    } else if (GNA && warp >= 4 + TC_EPI_WARPS) {
+        // ===================== GroupNorm converter (GNA): normalise the A tile in place =====================
+        // Thread (j, row): the 128-byte row of channel kb*64 + row in half j (64 positions of image bf_j).  The affine is per
+        // (image, channel), so the 128-byte swizzle inside the row is irrelevant; the 16-byte chunks are visited in a rotated
+        // order so that 8 consecutive lanes hit 8 different bank groups.
+        const int t = (int)threadIdx.x - 32 * (4 + TC_EPI_WARPS);
+        const int j = t >> 6, row = t & 63;
+        const int cpg = gn.C / NMM_GN_GROUPS;
+        // gamma / beta of every channel -> shared memory once per CTA (a per-k-block global load would sit on the converter's
+        // critical path: ~L2 latency per 64 channels)
+        float *sm_gb = reinterpret_cast<float *>(smem_raw + (epi_base + (uint32_t)TC_EPI_WARPS * (uint32_t)p.epi_buf - ptx::smem_u32(smem_raw)));
+        const int kpad = num_kb * TC_BK;
+        for (int c = t; c < kpad; c += 32 * TC_GN_WARPS) {
+            sm_gb[c] = c < gn.C ? __ldg(gn.gamma + c) : 0.f;              // channels past C: zero rows (W's columns there are zero-filled too)
+            sm_gb[kpad + c] = c < gn.C ? __ldg(gn.beta + c) : 0.f;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_GN_WARPS) : "memory");     // converter warps only
+        int stage = 0; uint32_t phase = 0;
+        for (int64_t ct = cluster_id; ct < p.cluster_tiles; ct += num_clusters) {
+            const int64_t m_blk = (ct / p.n_tiles) * CG + rank;
+            const int bf = (int)((m_blk * TC_BM + 64 * j) / gn.P);
+            // lane g holds mean / rstd of group g of image bf (all 32 lanes of a warp share j, hence bf)
+            float mean_g, rstd_g;
+            gn_finalize_one(gn.partial, bf * NMM_GN_GROUPS + lane, gn.splits, gn.count, gn.eps, mean_g, rstd_g);
+            for (int kb = 0; kb < num_kb; kb++) {
+                const int c = kb * TC_BK + row;
+                const int grp = min(c / cpg, NMM_GN_GROUPS - 1);
+                const float mu = __shfl_sync(0xffffffffu, mean_g, grp), rs = __shfl_sync(0xffffffffu, rstd_g, grp);
+                const float ca = rs * sm_gb[c], cb = sm_gb[kpad + c] - mu * ca;
+                ptx::mbar_wait(full_bar(stage), phase);
+                const uint32_t rbase = smem_base + (uint32_t)stage * stage_bytes + (uint32_t)(j * TC_A_HALF + row * 128);
+                if (!(p.debug & 4)) {
+                    // all 8 loads first (independent, pipelined), then the arithmetic, then the stores
+                    uint32_t w[8][4];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const uint32_t addr = rbase + (uint32_t)(((i + row) & 7) << 4);
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[i][0]), "=r"(w[i][1]), "=r"(w[i][2]), "=r"(w[i][3]) : "r"(addr) : "memory");
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+#pragma unroll
+                        for (int k = 0; k < 4; k++) w[i][k] = pack_bf16x2(fmaf(bf16_lo(w[i][k]), ca, cb), fmaf(bf16_hi(w[i][k]), ca, cb));
+                        sts128(rbase + (uint32_t)(((i + row) & 7) << 4), w[i][0], w[i][1], w[i][2], w[i][3]);
+                    }
+                }
+                if (!(p.debug & 8)) ptx::fence_proxy_async();               // generic-proxy writes -> visible to the tensor core's async proxy
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(conv_bar(stage));
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp >= 4 && warp < 4 + TC_EPI_WARPS) {
         // ===================== epilogue (every CTA: its own 128 TMEM lanes) =====================
         const int ew = warp - 4;
         const int q = warp & 3;                                           // TMEM lane quadrant this warp may access
@@ -515,6 +612,25 @@ static int make_tmap(CUtensorMap *tm, const void *ptr, CUtensorMapDataType dt, i
     return NMM_OK;
 }
 
+// x [B, C, F, P] (element strides sb, sc, sf; unit stride along P) as a 4-D tensor (p, c, f, b); box = 64 positions x 64 channels.
+static int make_tmap_x(CUtensorMap *tm, const void *x, int B, int C, int F, int P, int64_t sb, int64_t sc, int64_t sf) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return fail(NMM_ERR_DEVICE, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+    cuuint64_t dims[4] = {(cuuint64_t)P, (cuuint64_t)C, (cuuint64_t)F, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)sc * 2, (cuuint64_t)sf * 2, (cuuint64_t)sb * 2};
+    cuuint32_t box[4] = {64, 64, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(NMM_ERR_CUDA, "cuTensorMapEncodeTiled (x, 4-D) failed with CUresult %d", (int)r);
+    return NMM_OK;
+}
+
+// Can proj_in take its A operand straight from x (GroupNorm applied in shared memory)?  See LinearArgs::gn_x.
+bool linear_tc_gn_fusable(int64_t M, int P, const void *x, int64_t sb, int64_t sc, int64_t sf) {
+    return P % 64 == 0 && M % TC_BM == 0 && aligned(x, 16) && sb % 8 == 0 && sc % 8 == 0 && sf % 8 == 0 && !getenv("NMM_NO_GN_FUSE");
+}
+
 #ifdef NMM_TRACE
 static unsigned long long *g_trace_dev = nullptr;
 extern "C" __attribute__((visibility("default"))) int nmm_debug_trace_dump(const char *path) {
@@ -583,10 +699,10 @@ void plan_linear_tc(int64_t M, int N, int K, int epilogue, int *block_n, int *cl
     *cluster = plan.cluster;
 }
 
-template <int EPI, int CG, bool LNF>
+template <int EPI, int CG, bool LNF, bool GNA = false>
 static int launch_tc_t(const CUtensorMap &ta, const CUtensorMap &tw, const CUtensorMap &th, const CUtensorMap &to, const TcParams &p,
-                       const EpiParams &e, size_t smem, int grid, cudaStream_t st, double flops, double bytes) {
-    auto kern = linear_tc_kernel<EPI, CG, LNF>;
+                       const EpiParams &e, size_t smem, int grid, cudaStream_t st, double flops, double bytes, const GnParams &gn = GnParams()) {
+    auto kern = linear_tc_kernel<EPI, CG, LNF, GNA>;
     static bool attr_set = false;     // per template instantiation
     if (!attr_set) {
         NMM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX));
@@ -595,7 +711,7 @@ static int launch_tc_t(const CUtensorMap &ta, const CUtensorMap &tw, const CUten
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(TC_THREADS);
+    cfg.blockDim = dim3(GNA ? TC_THREADS + 32 * TC_GN_WARPS : TC_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
@@ -609,7 +725,7 @@ static int launch_tc_t(const CUtensorMap &ta, const CUtensorMap &tw, const CUten
     cfg.numAttrs = CG > 1 ? 2 : 1;
     {
         ProfScope prof(K_LINEAR_TC, st, flops, bytes);
-        cudaError_t le = cudaLaunchKernelEx(&cfg, kern, ta, tw, th, to, p, e);
+        cudaError_t le = cudaLaunchKernelEx(&cfg, kern, ta, tw, th, to, p, e, gn);
         if (le != cudaSuccess) return fail(NMM_ERR_CUDA, "cudaLaunchKernelEx(linear_tc_kernel) failed: %s", cudaGetErrorString(le));
     }
     NMM_LAUNCHED("linear_tc_kernel");
@@ -635,8 +751,12 @@ int launch_linear_tc(const LinearArgs &a, cudaStream_t st) {
     if (!g_trace_dev) { cudaMalloc(&g_trace_dev, TRACE_TILES * TRACE_SLOTS * 8); cudaMemset(g_trace_dev, 0, TRACE_TILES * TRACE_SLOTS * 8); }
     p.trace = g_trace_dev;
 #endif
+    const bool gna = a.gn_x != nullptr;
+    if (gna && (a.epilogue != NMM_EPI_STORE || a.ln_part_in != nullptr || a.ln_part_out != nullptr || a.gn_B <= 0 ||
+                !linear_tc_gn_fusable(a.M, a.P, a.gn_x, a.xsb, a.xsc, a.xsf) || (int64_t)a.gn_B * a.F * a.P != a.M))
+        return fail(NMM_ERR_UNSUPPORTED, "GroupNorm-fused A operand: needs the STORE epilogue, P %% 64 == 0, M %% 128 == 0 and 16-byte aligned x");
     const int gran = a.epilogue == NMM_EPI_GEGLU ? 64 : 32;
-    const TilePlan plan = choose_tiles(p.m_tiles, a.N, a.K, sms, gran, (force_cluster == 1 || force_cluster == 2) ? force_cluster : 0,
+    const TilePlan plan = choose_tiles(p.m_tiles, a.N, a.K, sms, gran, gna ? 1 : (force_cluster == 1 || force_cluster == 2) ? force_cluster : 0,
                                        (force_bn >= gran && force_bn <= 256 && force_bn % gran == 0 && a.N % force_bn == 0) ? force_bn : 0);
     if (plan.block_n == 0) return fail(NMM_ERR_UNSUPPORTED, "tcgen05 GEMM: no N tile for N=%d", a.N);
     p.block_n = plan.block_n;
@@ -646,7 +766,8 @@ int launch_linear_tc(const LinearArgs &a, cudaStream_t st) {
     p.cluster_tiles = m_groups * p.n_tiles;
     const size_t stage_bytes = (size_t)TC_A_BYTES + (size_t)(p.block_n / p.cluster) * TC_BK * 2;     // per CTA
     p.epi_buf = (a.epilogue == NMM_EPI_RESIDUAL && a.out != nullptr && !a.no_h_store) ? 12288 : TC_EPI_BUF;
-    const size_t fixed = 1024 /*alignment slack*/ + TC_BAR_BYTES + (size_t)TC_EPI_WARPS * p.epi_buf;
+    const size_t gn_coef = a.gn_x != nullptr ? (size_t)ceil_div(a.K, TC_BK) * TC_BK * 8 : 0;      // GNA: gamma | beta in shared memory
+    const size_t fixed = 1024 /*alignment slack*/ + TC_BAR_BYTES + (size_t)TC_EPI_WARPS * p.epi_buf + gn_coef;
     int stages = (int)((TC_SMEM_MAX - fixed) / stage_bytes);
     if (stages > 8) stages = 8;
     if (stages < 2) return fail(NMM_ERR_UNSUPPORTED, "tcgen05 GEMM: tile does not fit shared memory");
@@ -656,7 +777,8 @@ int launch_linear_tc(const LinearArgs &a, cudaStream_t st) {
     p.tmem_cols = cols;
     const size_t smem = fixed + (size_t)stages * stage_bytes;
     CUtensorMap ta, tw, th, to;
-    int rc = make_tmap(&ta, a.A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.M, a.K, a.K, TC_BM, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B);
+    int rc = gna ? make_tmap_x(&ta, a.gn_x, a.gn_B, a.K, a.F, a.P, a.xsb, a.xsc, a.xsf)
+                 : make_tmap(&ta, a.A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.M, a.K, a.K, TC_BM, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != NMM_OK) return rc;
     // each CTA of a pair fetches its slice of the W tile
     rc = make_tmap(&tw, a.W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.N, a.K, a.K, p.block_n / p.cluster, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -678,6 +800,12 @@ int launch_linear_tc(const LinearArgs &a, cudaStream_t st) {
     EpiParams e = epi_params_of(a);
     const double fl = linear_flops(a), by = linear_bytes(a, 2);
     const bool lnf = a.ln_part_in != nullptr || a.ln_part_out != nullptr;
+    if (gna) {
+        GnParams gn;
+        gn.partial = a.gn_partial; gn.gamma = a.gn_w; gn.beta = a.gn_b; gn.splits = a.gn_splits; gn.count = a.gn_count; gn.eps = a.gn_eps;
+        gn.C = a.K; gn.F = a.F; gn.P = a.P;
+        return launch_tc_t<NMM_EPI_STORE, 1, false, true>(ta, tw, th, to, p, e, smem, grid, st, fl, by, gn);
+    }
 #define TC_DISPATCH(EPI)                                                                                   \
     if (lnf)                                                                                               \
         return p.cluster == 2 ? launch_tc_t<EPI, 2, true>(ta, tw, th, to, p, e, smem, grid, st, fl, by)    \

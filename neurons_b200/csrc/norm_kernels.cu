@@ -22,6 +22,7 @@ static int gn_splits(const Geo &g) {
     int64_t per_group = (int64_t)(g.C / NMM_GN_GROUPS) * g.P;
     return (int)ceil_div(per_group, GN_CHUNK);
 }
+int gn_splits_of(const Geo &g) { return gn_splits(g); }
 size_t gn_partial_bytes(const Geo &g) {
     return (size_t)g.B * g.F * NMM_GN_GROUPS * gn_splits(g) * 2 * sizeof(double);
 }
@@ -126,20 +127,6 @@ int launch_gn_stats(const Geo &g, const nmm_shape *s, const void *x, double *par
     }
     NMM_LAUNCHED("gn_stats_kernel");
     return NMM_OK;
-}
-
-__device__ __forceinline__ void gn_finalize_one(const double *__restrict__ partial, int bf_grp, int splits, double count,
-                                                float eps, float &mean, float &rstd) {
-    double a = 0, c2 = 0;
-    for (int i = 0; i < splits; i++) {
-        a += partial[((int64_t)bf_grp * splits + i) * 2 + 0];
-        c2 += partial[((int64_t)bf_grp * splits + i) * 2 + 1];
-    }
-    double m = a / count;
-    double var = c2 / count - m * m;          // biased variance, as torch.nn.GroupNorm
-    if (var < 0) var = 0;
-    mean = (float)m;
-    rstd = (float)(1.0 / sqrt(var + (double)eps));
 }
 
 __global__ void gn_finalize_kernel(const double *__restrict__ partial, float *__restrict__ mean, float *__restrict__ rstd,

@@ -53,6 +53,11 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap *m, uint32_t bar, 
 // Address of "the same object in the even CTA of my pair": shared::cluster addresses carry the CTA rank in bit 24.
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;
 // 2-CTA form: `bar` may name the mbarrier of either CTA of the pair (both CTAs signal the even CTA's barrier).
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap *m, uint32_t bar, uint32_t dst_smem, int32_t c0, int32_t c1, int32_t c2, int32_t c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst_smem), "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap *m, uint32_t bar, uint32_t dst_smem, int32_t c0, int32_t c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -195,6 +200,19 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
+// Shared-memory matrix descriptor for an MN-major operand (the M/N index is the contiguous one), 128-byte swizzle:
+// canonical layout ((8,n),(8,k)) : ((1,LBO),(8,SBO)) in 16-byte units -- rows of 64 elements along M (128 B), consecutive k
+// 128 B apart, groups of 8 k `sbo_bytes` apart, 64-element blocks along M `lbo_bytes` apart.
+__device__ __forceinline__ uint64_t umma_smem_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+constexpr uint32_t UMMA_IDESC_A_MN_MAJOR = 1u << 15;     // instruction descriptor: A operand is M-major
 // Instruction descriptor, kind::f16: D fp32 (c_format=1 @4), A/B bf16 (format 1 @7, @10), both K-major (bits 15,16 = 0),
 // N >> 3 @17, M >> 4 @24.
 __host__ __device__ inline uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {

@@ -252,6 +252,25 @@ def groupnorm_tokens(cfg: ModuleConfig, x: torch.Tensor, gn_w: torch.Tensor, gn_
     return tok
 
 
+def groupnorm_linear(cfg: ModuleConfig, x: torch.Tensor, gn_w: torch.Tensor, gn_b: torch.Tensor, weight: torch.Tensor,
+                     bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """GroupNorm + token re-layout + Linear in one tensor-core kernel (bf16): fp32 [N, C_out].  motion_module.py:142-145."""
+    x = _dense_hw(x)
+    shape = make_shape(cfg, x)
+    c_out = weight.shape[0]
+    h = torch.empty((_tokens(cfg, x), c_out), dtype=torch.float32, device=x.device)
+    ws_bytes = workspace_bytes(shape)
+    ws, ws_ptr = _aligned_ws(ws_bytes, x.device)
+    gn_w, gn_b = gn_w.float().contiguous(), gn_b.float().contiguous()
+    weight = weight.to(x.dtype).contiguous()
+    bias = bias.float().contiguous() if bias is not None else None
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().nmm_groupnorm_linear(C.byref(shape), x.data_ptr(), gn_w.data_ptr(), gn_b.data_ptr(), weight.data_ptr(), c_out,
+                                                    bias.data_ptr() if bias is not None else None, h.data_ptr(), ws_ptr, ws_bytes,
+                                                    _stream_ptr(x.device)))
+    return h
+
+
 def _shape_for_tokens(cfg: ModuleConfig, B: int, F: int, H: int, W: int, dtype: torch.dtype) -> _lib.Shape:
     s = _lib.Shape()
     s.batch, s.channels, s.frames, s.height, s.width = B, cfg.channels, F, H, W

@@ -76,6 +76,7 @@ def main():
         stages = [
             ("gn_stats", lambda: ops.groupnorm_stats(cfg, x), 0.0, M * C * es),
             ("gn_tokens(+stats)", lambda: ops.groupnorm_tokens(cfg, x, gw, gb), 0.0, 3 * M * C * es),
+            ("gn_stats+proj_in fused", lambda: ops.groupnorm_linear(cfg, x, gw, gb, w_cc, bias), 2.0 * M * C * C, M * C * (2 * es + 4)),
             ("layernorm_pe", lambda: ops.layernorm_pe(cfg, (B, F, side, side), h, gw, gb, pe, bf), 0.0, M * C * (4 + es)),
             ("attention", lambda: ops.temporal_attention(cfg, (B, F, side, side), qkv), 4.0 * M * F * C, 4 * M * C * es),
             ("proj_in  C->C  store h", lambda: ops.linear(act, w_cc, bias, nlib.EPI_STORE, h=h, want_out=False), 2.0 * M * C * C, M * C * (es + 4)),

@@ -63,6 +63,28 @@ def test_groupnorm_stats_and_tokens(C, F, H, W, B, layout, dtype):
     assert _maxabs(tok, st.tokens) <= tol
 
 
+@pytest.mark.parametrize("C,F,H,W,B,layout", [(320, 8, 8, 8, 1, "bcfhw"), (320, 8, 16, 16, 2, "bfchw"), (640, 16, 8, 8, 1, "bfchw"),
+                                              (1280, 8, 8, 8, 2, "bfchw"), (96, 2, 8, 8, 1, "bcfhw")])
+def test_groupnorm_linear_fused_matches_two_kernel_path(C, F, H, W, B, layout):
+    """GroupNorm + re-layout + proj_in in one tcgen05 kernel (x tiles TMA-loaded as an M-major operand, normalised in shared
+    memory) against gn_tokens + linear (bit-identical operands -> same accumulation) and against the fp64 oracle."""
+    cfg = mo.MotionConfig(C)
+    params = mo.make_params(cfg, 1)
+    x = helpers.round_bf16(mo.make_input((B, C, F, H, W), 2, layout=layout))
+    st = mo.forward_token_order(params, x, cfg, torch.float64)
+    xd = x.to(DEV, torch.bfloat16)
+    gw, gb = params["temporal_transformer.norm.weight"].to(DEV), params["temporal_transformer.norm.bias"].to(DEV)
+    w = helpers.round_bf16(params["temporal_transformer.proj_in.weight"]).to(DEV, torch.bfloat16)
+    b = params["temporal_transformer.proj_in.bias"].to(DEV)
+    fused = ops.groupnorm_linear(_cfg(cfg), xd, gw, gb, w, b)
+    tok = ops.groupnorm_tokens(_cfg(cfg), xd, gw, gb)
+    h2 = torch.empty_like(fused)
+    ops.linear(tok, w, b, nlib.EPI_STORE, h=h2, want_out=False)
+    assert torch.equal(fused, h2)
+    ref = st.tokens @ w.double().cpu().T + b.double().cpu()
+    assert _maxabs(fused, ref) <= 2e-2
+
+
 @pytest.mark.parametrize("C,F,H,W,B", [(320, 8, 8, 8, 1), (640, 16, 4, 4, 1), (1280, 8, 2, 2, 2), (96, 3, 3, 3, 1)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
 @pytest.mark.parametrize("with_pe", [True, False])
@@ -326,7 +348,8 @@ def test_launch_counter_and_graph_capture():
         n0 = nb.launch_count()
         m(x, None, None)
         per_call = nb.launch_count() - n0
-        assert per_call == 2 + 1 + 2 * 4 + 3 + 1              # gn(2) proj_in, 2x(ln qkv attn out), ln geglu ff_out, proj_out
+        # gn_stats, GroupNorm-fused proj_in (16x16 positions: x is TMA-loaded by the GEMM), 2x(ln qkv attn out), ln geglu ff_out, proj_out
+        assert per_call == 1 + 1 + 2 * 4 + 3 + 1
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         s = torch.cuda.Stream()
