@@ -108,6 +108,50 @@ def measured_peaks():
 
 
 # ---------------------------------------------------------------------------------------------------------------
+def clip_loop(nb, wl, dev, clips: int = 3):
+    """Second half of BASELINE.json's metric: 25-step clips/s at the NEURONS 'enhance' shape (configs[2]: CFG batch 2, 16 frames,
+    256x256 video = 32x32 latent) -- the motion modules ONLY (20 UNet + 8 SparseCtrl-ControlNet calls per denoising step,
+    scripts/neuroclips_video_enhance.py:356-358, pipeline_neuroclips.py:433-483); the rest of the UNet is outside the path.
+    One step is captured in a CUDA graph and replayed 25 times per clip.  Returns (ms per clip on this rank, flops per clip)."""
+    F, L, B, steps = 16, 32, 2, 25
+    calls = wl.unet_step_calls(L) + wl.controlnet_step_calls(L)
+    mods, xs = [], []
+    with torch.no_grad():
+        for c in calls:
+            kw = dict(num_attention_heads=8, num_transformer_block=1, attention_block_types=("Temporal_Self",) * c.attn_blocks,
+                      temporal_position_encoding=True, temporal_position_encoding_max_len=c.max_len, temporal_attention_dim_div=1,
+                      zero_initialize=False)
+            with torch.device(dev):
+                mods.append(nb.get_motion_module(c.channels, "Vanilla", kw).to(torch.bfloat16).eval())
+            xs.append(torch.randn(B, F, c.channels, c.side, c.side, device=dev, dtype=torch.bfloat16).permute(0, 2, 1, 3, 4))
+
+        def one_step():
+            for m, x in zip(mods, xs):
+                m(x, None, None)
+
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                one_step()
+            side.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                one_step()
+        torch.cuda.current_stream().wait_stream(side)
+        for _ in range(steps):
+            graph.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(clips * steps):
+            graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+    flops_clip = steps * sum(wl.module_flops(c.channels, B * F * c.side * c.side, F, c.attn_blocks) for c in calls)
+    return e0.elapsed_time(e1) / clips, flops_clip
+
+
 def cpu_reference_time(sample: str, threads: int):
     """Time the oracle port of the reference module (fp32, torch CPU, all host threads) on a bounded sample.
     Returns (tflops, seconds, description).  This is the ONE place bench.py executes oracle/ (as the baseline)."""
@@ -187,6 +231,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the host-CPU baseline leg")
+    ap.add_argument("--no-clips", action="store_true", help="skip the 25-step clip loop (secondary metric)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -299,11 +344,12 @@ def main():
         torch.cuda.synchronize()
         e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
 
+    clip_ms, clip_flops = (0.0, 0.0) if args.no_clips else clip_loop(nb, wl, dev)
     # max over ranks
-    t = torch.tensor([ms_total, e2e_ms], device=dev, dtype=torch.float64)
+    t = torch.tensor([ms_total, e2e_ms, clip_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms = float(t[0]), float(t[1])
+    ms_total, e2e_ms, clip_ms = float(t[0]), float(t[1]), float(t[2])
     ms_step = ms_total / args.steps
     value = world * flops_step / (ms_step * 1e-3) / 1e12
     e2e_value = world * flops_step / (e2e_ms * 1e-3) / 1e12
@@ -342,6 +388,11 @@ def main():
                 "data": "synthetic", "config": workload_config(world), "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+                "clips": None if args.no_clips else {
+                    "metric": "25-step video clips/s, motion modules only", "value": world * 1e3 / clip_ms, "unit": "clips/s", "ms_per_clip": clip_ms,
+                    "tflops": world * clip_flops / (clip_ms * 1e-3) / 1e12,
+                    "workload": "BASELINE configs[2] shape: 25 DDIM steps x (20 UNet + 8 SparseCtrl ControlNet motion-module calls), CFG batch 2, "
+                                "16 frames, 32x32 latent, bf16; one step captured in a CUDA graph; the rest of the UNet is outside the path"},
                 "flops_per_step": flops_step}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -156,6 +156,13 @@ NMM_API int nmm_groupnorm_tokens(const nmm_shape *s, const void *x, const float 
  * nmm_groupnorm_tokens + nmm_linear; nmm_forward picks automatically). */
 NMM_API int nmm_groupnorm_linear(const nmm_shape *s, const void *x, const float *gn_w, const float *gn_b, const void *W, int32_t c_out,
                          const float *bias, float *h_out, void *workspace, size_t workspace_bytes, void *stream);
+/* Denoise-loop glue: classifier-free guidance + one deterministic DDIM update in a single elementwise kernel,
+ * pipeline_neuroclips.py:478-483 + DDIMScheduler.step (eta = 0, epsilon prediction, clip_sample = false):
+ *   eps = eps_uncond + guidance * (eps_cond - eps_uncond)            (eps_cond == NULL: eps = eps_uncond, guidance ignored)
+ *   latents = sqrt(a_prev) * (latents - sqrt(1 - a_t) * eps) / sqrt(a_t) + sqrt(1 - a_prev) * eps        (in place)
+ * n elements of `dtype` (NMM_F32 / NMM_BF16), fp32 arithmetic; alpha_t / alpha_prev = alphas_cumprod at t and at the previous step. */
+NMM_API int nmm_cfg_ddim_step(int32_t dtype, int64_t n, void *latents, const void *eps_uncond, const void *eps_cond, float guidance,
+                      double alpha_t, double alpha_prev, void *stream);
 /* LayerNorm(C, eps_ln) (+ sinusoidal PE of the token's frame): motion_module.py:212 + :277-278 (pe != NULL)
  * or :219 (pe == NULL).  h: fp32 [N,C]; out: [N,C] of s->dtype; w,b: fp32 [C]; pe: fp32 [max_len,C]. */
 NMM_API int nmm_layernorm_pe(const nmm_shape *s, const float *h, const float *w, const float *b, const float *pe,

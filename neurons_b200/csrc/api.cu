@@ -576,6 +576,15 @@ int nmm_groupnorm_linear(const nmm_shape *s, const void *x, const float *gn_w, c
     return launch_linear_tc(a, st);
 }
 
+int nmm_cfg_ddim_step(int32_t dtype, int64_t n, void *latents, const void *eps_uncond, const void *eps_cond, float guidance, double alpha_t,
+                      double alpha_prev, void *stream) {
+    if (dtype != NMM_F32 && dtype != NMM_BF16) return fail(NMM_ERR_BAD_ARG, "dtype must be NMM_F32 or NMM_BF16");
+    if (n < 0 || (n > 0 && (!latents || !eps_uncond))) return fail(NMM_ERR_BAD_ARG, "NULL argument");
+    int rc = device_check();
+    if (rc != NMM_OK) return rc;
+    return launch_cfg_ddim(dtype, n, latents, eps_uncond, eps_cond, guidance, alpha_t, alpha_prev, (cudaStream_t)stream);
+}
+
 int nmm_layernorm_pe(const nmm_shape *s, const float *h, const float *w, const float *b, const float *pe, void *out, void *stream) {
     int rc = validate(s);
     if (rc != NMM_OK) return rc;

@@ -271,6 +271,24 @@ def groupnorm_linear(cfg: ModuleConfig, x: torch.Tensor, gn_w: torch.Tensor, gn_
     return h
 
 
+def cfg_ddim_step(latents: torch.Tensor, eps_uncond: torch.Tensor, eps_cond: Optional[torch.Tensor], guidance: float, alpha_t: float,
+                  alpha_prev: float) -> torch.Tensor:
+    """In-place fused classifier-free guidance + DDIM update on CUDA tensors (pipeline_neuroclips.py:478-483); returns `latents`."""
+    if not latents.is_cuda:
+        raise RuntimeError("neurons_b200.ops.cfg_ddim_step: CUDA tensors only (there is no CPU path)")
+    if not latents.is_contiguous():
+        raise ValueError("latents must be contiguous (updated in place)")
+    eu = eps_uncond.to(latents.dtype).contiguous()
+    ec = eps_cond.to(latents.dtype).contiguous() if eps_cond is not None else None
+    if eu.shape != latents.shape or (ec is not None and ec.shape != latents.shape):
+        raise ValueError("eps tensors must have the shape of latents")
+    with torch.cuda.device(latents.device):
+        _lib.check(_lib.load().nmm_cfg_ddim_step(_dtype_code(latents.dtype), latents.numel(), latents.data_ptr(), eu.data_ptr(),
+                                                 ec.data_ptr() if ec is not None else None, float(guidance), float(alpha_t), float(alpha_prev),
+                                                 _stream_ptr(latents.device)))
+    return latents
+
+
 def _shape_for_tokens(cfg: ModuleConfig, B: int, F: int, H: int, W: int, dtype: torch.dtype) -> _lib.Shape:
     s = _lib.Shape()
     s.batch, s.channels, s.frames, s.height, s.width = B, cfg.channels, F, H, W

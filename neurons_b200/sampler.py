@@ -40,18 +40,21 @@ class DDIMSchedule:
         a = float(self.alphas_cumprod[t])
         return (a ** 0.5) * x0 + ((1.0 - a) ** 0.5) * noise
 
+    def alphas(self, t: int, num_inference_steps: int):
+        """(alphas_cumprod[t], alphas_cumprod[previous timestep]) of one update."""
+        prev_t = t - self.num_train_timesteps // num_inference_steps
+        return float(self.alphas_cumprod[t]), float(self.alphas_cumprod[prev_t]) if prev_t >= 0 else self.final_alpha_cumprod
+
     def step(self, eps: torch.Tensor, t: int, x: torch.Tensor, num_inference_steps: int) -> torch.Tensor:
         """Deterministic DDIM update (eta = 0, epsilon prediction, no sample clipping)."""
-        prev_t = t - self.num_train_timesteps // num_inference_steps
-        a_t = float(self.alphas_cumprod[t])
-        a_prev = float(self.alphas_cumprod[prev_t]) if prev_t >= 0 else self.final_alpha_cumprod
+        a_t, a_prev = self.alphas(t, num_inference_steps)
         x0 = (x - ((1.0 - a_t) ** 0.5) * eps) / (a_t ** 0.5)
         return (a_prev ** 0.5) * x0 + ((1.0 - a_prev) ** 0.5) * eps
 
 
 def denoise(denoiser: Callable[[torch.Tensor, int, Optional[torch.Tensor]], torch.Tensor], latents: torch.Tensor,
             context: Optional[torch.Tensor], schedule: DDIMSchedule, num_inference_steps: int = 25, guidance_scale: float = 8.5,
-            noise: Optional[torch.Tensor] = None, low_strength: Optional[float] = None) -> torch.Tensor:
+            noise: Optional[torch.Tensor] = None, low_strength: Optional[float] = None, fused_step: bool = False) -> torch.Tensor:
     """latents: [b, 4, f, h, w].  With `noise` + `low_strength` the clean latents are first noised to the start timestep exactly as
     pipeline_neuroclips.py:410-423 does; the loop then always runs over ALL timesteps (as the reference does, :433)."""
     ts = schedule.timesteps(num_inference_steps)
@@ -61,10 +64,18 @@ def denoise(denoiser: Callable[[torch.Tensor, int, Optional[torch.Tensor]], torc
         steps = ts[:t_start]
         latents = schedule.add_noise(latents, noise, steps[0] if steps else ts[0])
     cfg = guidance_scale > 1.0
+    if fused_step:
+        latents = latents.contiguous().clone()            # updated in place by the fused kernel; never the caller's tensor
     with torch.no_grad():
         for t in ts:
             x2 = torch.cat([latents] * 2) if cfg else latents                     # :435
             eps = denoiser(x2, t, context).to(latents.dtype)                      # :470-475
+            if fused_step:                                                        # :478-483 in one CUDA kernel (ops.cfg_ddim_step)
+                from . import ops
+                a_t, a_prev = schedule.alphas(t, num_inference_steps)
+                eps_u, eps_c = eps.chunk(2) if cfg else (eps, None)
+                latents = ops.cfg_ddim_step(latents, eps_u, eps_c, guidance_scale, a_t, a_prev)       # in place on our private copy
+                continue
             if cfg:
                 eps_u, eps_c = eps.chunk(2)                                       # :478-480
                 eps = eps_u + guidance_scale * (eps_c - eps_u)

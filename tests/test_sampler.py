@@ -66,3 +66,43 @@ def test_ddim_25_step_cosine_vs_oracle():
     assert torch.isfinite(out_gpu).all() and torch.isfinite(out_ref).all()
     cos = torch.nn.functional.cosine_similarity(out_gpu.flatten(), out_ref.flatten(), dim=0).item()
     assert cos >= 0.999, cos
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("n", [4 * 16 * 32 * 32, 1003, 8])
+@pytest.mark.parametrize("with_cfg", [True, False])
+def test_fused_cfg_ddim_step_matches_schedule_step(dtype, n, with_cfg):
+    """nmm_cfg_ddim_step (one elementwise kernel) against DDIMSchedule.step + the CFG combine in fp64."""
+    from neurons_b200 import ops
+    dev = "cuda:0"
+    g = torch.Generator().manual_seed(n)
+    x, eu, ec = (torch.randn(n, generator=g).to(dtype) for _ in range(3))
+    sch = sampler.DDIMSchedule()
+    for t in (961, 481, 1):
+        a_t, a_prev = sch.alphas(t, 25)
+        eps = eu.double() + 8.5 * (ec.double() - eu.double()) if with_cfg else eu.double()
+        ref = sch.step(eps, t, x.double(), 25)
+        out = ops.cfg_ddim_step(x.to(dev).clone(), eu.to(dev), ec.to(dev) if with_cfg else None, 8.5, a_t, a_prev)
+        scale = ref.abs().max().item()
+        tol = (2e-6 if dtype == torch.float32 else 2 ** -8 * 1.01) * scale
+        assert (out.double().cpu() - ref).abs().max().item() <= tol
+
+
+@pytest.mark.gpu
+def test_denoise_fused_step_matches_unfused_and_keeps_input():
+    from neurons_b200 import ops  # noqa: F401
+    dev = "cuda:0"
+    g = torch.Generator().manual_seed(11)
+    lat0 = torch.randn(1, 4, 8, 8, 8, generator=g).to(dev)
+    keep = lat0.clone()
+    w = torch.randn(4, 4, generator=g).to(dev) * 0.3
+
+    def den(x2, t, c):
+        return torch.einsum("oc,bcfhw->bofhw", w, x2) * (t / 1000.0)
+
+    sch = sampler.DDIMSchedule()
+    a = sampler.denoise(den, lat0, None, sch, 25, 8.5)
+    b = sampler.denoise(den, lat0, None, sch, 25, 8.5, fused_step=True)
+    assert torch.equal(lat0, keep)
+    assert (a - b).abs().max().item() <= 1e-5 * a.abs().max().item()
