@@ -156,6 +156,13 @@ NMM_API int nmm_groupnorm_tokens(const nmm_shape *s, const void *x, const float 
  * nmm_groupnorm_tokens + nmm_linear; nmm_forward picks automatically). */
 NMM_API int nmm_groupnorm_linear(const nmm_shape *s, const void *x, const float *gn_w, const float *gn_b, const void *W, int32_t c_out,
                          const float *bias, float *h_out, void *workspace, size_t workspace_bytes, void *stream);
+/* InflatedGroupNorm(32 groups, eps_gn) of a [b, c, f, h, w] tensor, optionally followed by SiLU, written in the layout the y strides
+ * describe: the norm1 / norm2 (+ nonlinearity) of ResnetBlock3D either side of the motion module (SURVEY 8(f) N1;
+ * animatediff/models/resnet.py:21-29,182-198).  Only batch, channels, frames, height, width, dtype, eps_gn and the strides of *s are
+ * used.  gn_w / gn_b: fp32 [C].  workspace: nmm_groupnorm_workspace_bytes(s), 256-byte aligned.  x and y must not alias. */
+NMM_API int nmm_groupnorm_workspace_bytes(const nmm_shape *s, size_t *bytes);
+NMM_API int nmm_inflated_groupnorm(const nmm_shape *s, const void *x, void *y, const float *gn_w, const float *gn_b, int32_t silu,
+                           void *workspace, size_t workspace_bytes, void *stream);
 /* Denoise-loop glue: classifier-free guidance + one deterministic DDIM update in a single elementwise kernel,
  * pipeline_neuroclips.py:478-483 + DDIMScheduler.step (eta = 0, epsilon prediction, clip_sample = false):
  *   eps = eps_uncond + guidance * (eps_cond - eps_uncond)            (eps_cond == NULL: eps = eps_uncond, guidance ignored)

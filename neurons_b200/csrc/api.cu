@@ -576,6 +576,38 @@ int nmm_groupnorm_linear(const nmm_shape *s, const void *x, const float *gn_w, c
     return launch_linear_tc(a, st);
 }
 
+static size_t gn_ws_layout(const Geo &g, size_t *stats_off) {
+    const size_t part = (gn_partial_bytes(g) + 255) / 256 * 256;
+    if (stats_off) *stats_off = part;
+    return part + (size_t)g.B * g.F * NMM_GN_GROUPS * 2 * sizeof(float);
+}
+
+int nmm_groupnorm_workspace_bytes(const nmm_shape *s, size_t *bytes) {
+    int rc = validate(s);
+    if (rc != NMM_OK) return rc;
+    if (!bytes) return fail(NMM_ERR_BAD_ARG, "NULL argument");
+    *bytes = gn_ws_layout(geo_of(s), nullptr);
+    return NMM_OK;
+}
+
+int nmm_inflated_groupnorm(const nmm_shape *s, const void *x, void *y, const float *gn_w, const float *gn_b, int32_t silu, void *workspace,
+                           size_t workspace_bytes, void *stream) {
+    int rc = validate(s);
+    if (rc != NMM_OK) return rc;
+    if (!x || !y || !gn_w || !gn_b || !workspace) return fail(NMM_ERR_BAD_ARG, "NULL argument");
+    if ((rc = device_check()) != NMM_OK) return rc;
+    const Geo g = geo_of(s);
+    size_t stats_off = 0;
+    if (workspace_bytes < gn_ws_layout(g, &stats_off)) return fail(NMM_ERR_WORKSPACE, "workspace too small");
+    if (!aligned(workspace, 256)) return fail(NMM_ERR_BAD_ARG, "workspace must be 256-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    double *partial = (double *)workspace;
+    float *mean = (float *)((char *)workspace + stats_off), *rstd = mean + (size_t)g.B * g.F * NMM_GN_GROUPS;
+    if ((rc = launch_gn_stats(g, s, x, partial, st)) != NMM_OK) return rc;
+    if ((rc = launch_gn_finalize(g, s, partial, mean, rstd, st)) != NMM_OK) return rc;
+    return launch_gn_apply(g, s, x, y, mean, rstd, gn_w, gn_b, silu ? 1 : 0, st);
+}
+
 int nmm_cfg_ddim_step(int32_t dtype, int64_t n, void *latents, const void *eps_uncond, const void *eps_cond, float guidance, double alpha_t,
                       double alpha_prev, void *stream) {
     if (dtype != NMM_F32 && dtype != NMM_BF16) return fail(NMM_ERR_BAD_ARG, "dtype must be NMM_F32 or NMM_BF16");

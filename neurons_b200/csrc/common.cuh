@@ -204,6 +204,8 @@ struct LinearArgs {
 constexpr int NMM_LN_PARTS = 16;     // partial-statistics slots per row: 2 epilogue warps x up to 8 N tiles of the producer
 // N tile / CTA-pair plan the tensor-core GEMM will use for (M, N, K): lets the caller know how many partial-statistics slots
 // a producer GEMM fills (2 * N / block_n)
+int launch_gn_apply(const Geo &g, const nmm_shape *s, const void *x, void *y, const float *mean, const float *rstd, const float *gn_w,
+                    const float *gn_b, int silu, cudaStream_t st);
 int launch_cfg_ddim(int dtype, int64_t n, void *x, const void *eu, const void *ec, float g, double a_t, double a_prev, cudaStream_t st);
 bool linear_tc_gn_fusable(int64_t M, int P, const void *x, int64_t sb, int64_t sc, int64_t sf);
 void plan_linear_tc(int64_t M, int N, int K, int epilogue, int *block_n, int *cluster);

@@ -263,6 +263,87 @@ int launch_gn_tokens(const Geo &g, const nmm_shape *s, const Geo &full, const vo
 }
 
 // ------------------------------------------------------------------------------------------------
+// InflatedGroupNorm (+ optional SiLU) in place of layout: y[b,c,f,p] = act(GroupNorm per (b,f) image of x) -- the norm1 / norm2 +
+// nonlinearity of ResnetBlock3D either side of the motion module (animatediff/models/resnet.py:21-29,182-198).
+// The reference rearranges b c f h w -> (b f) c h w (a copy), normalises, and rearranges back (another copy); here x is read in
+// its own strides and y written in its own strides: 2 passes over x (statistics, apply) instead of ~6.
+// ------------------------------------------------------------------------------------------------
+constexpr int GNA_CHUNK = 4096;       // elements of one (b, f) image per CTA
+
+__device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+
+template <typename T, bool VEC, bool SILU>
+__global__ void __launch_bounds__(256) gn_apply_kernel(const T *__restrict__ x, T *__restrict__ y, const float *__restrict__ mean,
+                                                       const float *__restrict__ rstd, const float *__restrict__ gamma,
+                                                       const float *__restrict__ beta, int C, int F, int P, int64_t xsb, int64_t xsc, int64_t xsf,
+                                                       int64_t ysb, int64_t ysc, int64_t ysf) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int bf = blockIdx.y, b = bf / F, f = bf - b * F;
+    const int cpg = C / NMM_GN_GROUPS;
+    const int64_t total = (int64_t)C * P;
+    const T *xb = x + (int64_t)b * xsb + (int64_t)f * xsf;
+    T *yb = y + (int64_t)b * ysb + (int64_t)f * ysf;
+    constexpr int V = VEC ? 16 / (int)sizeof(T) : 1;
+    for (int64_t e = ((int64_t)blockIdx.x * GNA_CHUNK) + (int64_t)threadIdx.x * V; e < min(total, ((int64_t)blockIdx.x + 1) * GNA_CHUNK); e += 256 * V) {
+        const int c = (int)(e / P), p = (int)(e - (int64_t)c * P);
+        const int gi = bf * NMM_GN_GROUPS + c / cpg;
+        const float a = __ldg(rstd + gi) * __ldg(gamma + c);
+        const float bb = __ldg(beta + c) - __ldg(mean + gi) * a;
+        if constexpr (VEC) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(xb + (int64_t)c * xsc + p));
+            uint4 o;
+            if constexpr (sizeof(T) == 4) {
+                float r[4] = {__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w)};
+#pragma unroll
+                for (int i = 0; i < 4; i++) { r[i] = fmaf(r[i], a, bb); if (SILU) r[i] = silu_f(r[i]); }
+                o = make_uint4(__float_as_uint(r[0]), __float_as_uint(r[1]), __float_as_uint(r[2]), __float_as_uint(r[3]));
+            } else {
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                uint32_t ow[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    float lo = fmaf(bf16_lo(w[i]), a, bb), hi = fmaf(bf16_hi(w[i]), a, bb);
+                    if (SILU) { lo = silu_f(lo); hi = silu_f(hi); }
+                    ow[i] = pack_bf16x2(lo, hi);
+                }
+                o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            }
+            *reinterpret_cast<uint4 *>(yb + (int64_t)c * ysc + p) = o;
+        } else {
+            float r = fmaf(to_f32(xb[(int64_t)c * xsc + p]), a, bb);
+            if (SILU) r = silu_f(r);
+            yb[(int64_t)c * ysc + p] = from_f32<T>(r);
+        }
+    }
+}
+
+int launch_gn_apply(const Geo &g, const nmm_shape *s, const void *x, void *y, const float *mean, const float *rstd, const float *gn_w,
+                    const float *gn_b, int silu, cudaStream_t st) {
+    if (g.B * g.F > 65535) return fail(NMM_ERR_UNSUPPORTED, "batch*frames > 65535");
+    const int64_t chunks = ceil_div((int64_t)g.C * g.P, GNA_CHUNK);
+    if (chunks > 0x7fffffff) return fail(NMM_ERR_UNSUPPORTED, "gn_apply grid too large");
+    const dim3 grid((unsigned)chunks, (unsigned)(g.B * g.F));
+    const int es = (int)dtype_size(g.dtype), V = 16 / es;
+    const bool vec = g.P % V == 0 && GNA_CHUNK % (256 * V) == 0 && aligned(x, 16) && aligned(y, 16) && s->x_stride_b % V == 0 && s->x_stride_c % V == 0 &&
+                     s->x_stride_f % V == 0 && s->y_stride_b % V == 0 && s->y_stride_c % V == 0 && s->y_stride_f % V == 0;
+    ProfScope prof(K_GN_TOKENS, st, 0.0, 2.0 * g.N * g.C * es);
+#define GNA_CASE(T, VV, SS)                                                                                                          \
+    launch_pdl(gn_apply_kernel<T, VV, SS>, grid, 256, 0, st, (const T *)x, (T *)y, mean, rstd, gn_w, gn_b, g.C, g.F, g.P, s->x_stride_b,  \
+               s->x_stride_c, s->x_stride_f, s->y_stride_b, s->y_stride_c, s->y_stride_f)
+    if (g.dtype == NMM_BF16) {
+        if (vec) { if (silu) GNA_CASE(bf16, true, true); else GNA_CASE(bf16, true, false); }
+        else { if (silu) GNA_CASE(bf16, false, true); else GNA_CASE(bf16, false, false); }
+    } else {
+        if (vec) { if (silu) GNA_CASE(float, true, true); else GNA_CASE(float, true, false); }
+        else { if (silu) GNA_CASE(float, false, true); else GNA_CASE(float, false, false); }
+    }
+#undef GNA_CASE
+    NMM_LAUNCHED("gn_apply_kernel");
+    return NMM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // LayerNorm over C (+ pe[frame of the token]).  h is the fp32 residual stream; out is the GEMM operand dtype.
 // Vector kernel: one 16-lane half-warp per token row, the row lives in registers as IT4 = C/64 float4 per lane
 // (two-pass mean / variance in fp32), every global access is 16 bytes per lane.  Generic kernel: one warp per row, any C.

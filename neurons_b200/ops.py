@@ -271,6 +271,29 @@ def groupnorm_linear(cfg: ModuleConfig, x: torch.Tensor, gn_w: torch.Tensor, gn_
     return h
 
 
+def inflated_groupnorm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5, silu: bool = False,
+                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """InflatedGroupNorm(32, C, eps) of x [b, c, f, h, w] (+ SiLU): animatediff/models/resnet.py:21-29 (+ :185-186 / :198).
+    Returns a contiguous [b, c, f, h, w] tensor (what the reference's rearrange-back produces) unless `out` is given."""
+    if not x.is_cuda:
+        raise RuntimeError("neurons_b200.ops.inflated_groupnorm: CUDA tensors only (there is no CPU path)")
+    x = _dense_hw(x)
+    y = out if out is not None else torch.empty(x.shape, dtype=x.dtype, device=x.device)
+    if y.shape != x.shape or y.dtype != x.dtype or _dense_hw(y) is not y:
+        raise ValueError("out must have the shape / dtype of x and dense (h, w)")
+    shape = make_shape(ModuleConfig(x.shape[1], heads=1, pos_enc=False), x, y)
+    shape.eps_gn = eps
+    n = C.c_size_t()
+    lib = _lib.load()
+    _lib.check(lib.nmm_groupnorm_workspace_bytes(C.byref(shape), C.byref(n)))
+    ws, ws_ptr = _aligned_ws(n.value, x.device)
+    w, b = weight.float().contiguous(), bias.float().contiguous()
+    with torch.cuda.device(x.device):
+        _lib.check(lib.nmm_inflated_groupnorm(C.byref(shape), x.data_ptr(), y.data_ptr(), w.data_ptr(), b.data_ptr(), int(silu), ws_ptr, n.value,
+                                              _stream_ptr(x.device)))
+    return y
+
+
 def cfg_ddim_step(latents: torch.Tensor, eps_uncond: torch.Tensor, eps_cond: Optional[torch.Tensor], guidance: float, alpha_t: float,
                   alpha_prev: float) -> torch.Tensor:
     """In-place fused classifier-free guidance + DDIM update on CUDA tensors (pipeline_neuroclips.py:478-483); returns `latents`."""

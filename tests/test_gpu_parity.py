@@ -363,3 +363,27 @@ def test_launch_counter_and_graph_capture():
         g.replay()
         torch.cuda.synchronize()
     assert torch.equal(y_graph, y_eager)
+
+
+@pytest.mark.parametrize("C,F,H,W,B,layout", [(320, 8, 8, 8, 2, "bcfhw"), (640, 16, 4, 4, 1, "bfchw"), (64, 3, 3, 5, 2, "bcfhw"), (1280, 2, 8, 8, 1, "bfchw")])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("silu", [False, True])
+def test_inflated_groupnorm_silu(C, F, H, W, B, layout, dtype, silu):
+    """InflatedGroupNorm (+ SiLU) of ResnetBlock3D (resnet.py:21-29,185-186) against torch GroupNorm in fp64."""
+    x = mo.make_input((B, C, F, H, W), 4, layout=layout)
+    if dtype == torch.bfloat16:
+        x = helpers.round_bf16(x)
+    g = torch.Generator().manual_seed(C)
+    w = 1 + 0.2 * torch.randn(C, generator=g)
+    b = 0.2 * torch.randn(C, generator=g)
+    xr = x.double().permute(0, 2, 1, 3, 4).reshape(B * F, C, H, W)                    # "b c f h w -> (b f) c h w"
+    ref = torch.nn.functional.group_norm(xr, 32, w.double(), b.double(), 1e-5)
+    if silu:
+        ref = torch.nn.functional.silu(ref)
+    ref = ref.reshape(B, F, C, H, W).permute(0, 2, 1, 3, 4)
+    xd = x.to(DEV, dtype)
+    assert xd.stride() == x.stride()
+    y = ops.inflated_groupnorm(xd, w.to(DEV), b.to(DEV), 1e-5, silu=silu)
+    assert y.is_contiguous() and y.shape == x.shape
+    tol = 2e-5 if dtype == torch.float32 else 2 ** -8 * 1.01 * ref.abs().max().item()
+    assert _maxabs(y, ref) <= tol

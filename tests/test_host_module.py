@@ -85,3 +85,20 @@ def test_set_attention_slice_walker_compat():
     attn.set_attention_slice(4)
     with pytest.raises(ValueError):
         attn.set_attention_slice(9)
+
+
+def test_inflated_groupnorm_mirror_keeps_checkpoint_layout_and_has_no_cpu_path():
+    import neurons_b200 as nb
+    ref = torch.nn.GroupNorm(32, 64, eps=1e-5)
+    ours = nb.InflatedGroupNorm(32, 64, eps=1e-5)
+    assert list(ours.state_dict().keys()) == list(ref.state_dict().keys())
+    ours.load_state_dict(ref.state_dict())
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ours(torch.zeros(1, 64, 2, 2, 2))
+    with pytest.raises(NotImplementedError):
+        nb.InflatedGroupNorm(16, 64)
+
+    class InflatedGroupNorm(torch.nn.GroupNorm):          # stands for the reference class (matched by name)
+        pass
+    model = torch.nn.Sequential(InflatedGroupNorm(32, 64), torch.nn.GroupNorm(32, 64), InflatedGroupNorm(8, 64))
+    assert nb.patch_group_norms(model) == 1
