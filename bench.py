@@ -344,6 +344,21 @@ def main():
         torch.cuda.synchronize()
         e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
 
+        # the same host<->device traffic with no compute: the PCIe floor of the e2e arm (both directions concurrently)
+        def step_copies():
+            for i in range(len(modules)):
+                with torch.cuda.stream(s_in):
+                    x_stage[i].copy_(xs_host[i], non_blocking=True)
+                with torch.cuda.stream(s_out):
+                    ys_host[i].copy_(x_stage[i], non_blocking=True)
+        step_copies()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            step_copies()
+        torch.cuda.synchronize()
+        copy_ms = 1e3 * (time.perf_counter() - t0) / 3
+
     clip_ms, clip_flops = (0.0, 0.0) if args.no_clips else clip_loop(nb, wl, dev)
     # max over ranks
     t = torch.tensor([ms_total, e2e_ms, clip_ms], device=dev, dtype=torch.float64)
@@ -386,7 +401,10 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic", "config": workload_config(world), "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
+                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                        "copies_alone_ms_per_step": copy_ms,
+                        "note": "PCIe-bound when copies_alone_ms_per_step >= ms_per_step of the device-resident arm: the step's inputs and outputs "
+                                "(h2d + d2h bytes) cross the host link inside the timed region, both directions concurrently"},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                 "clips": None if args.no_clips else {
                     "metric": "25-step video clips/s, motion modules only", "value": world * 1e3 / clip_ms, "unit": "clips/s", "ms_per_clip": clip_ms,
