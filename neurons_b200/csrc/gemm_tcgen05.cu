@@ -256,33 +256,6 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 if (++as == 2) { as = 0; aphase ^= 1u; }
             }
         }
-    } else if (EPI == NMM_EPI_OUTPUT && warp == 3) {
-        // ===================== x prefetcher (proj_out): the epilogue adds x[b, c, f, p] (channel rows of positions) ================
-        // One tile ahead of the accumulators: each lane pulls the 128-position run of one channel into L2, so the epilogue's
-        // 16-byte loads of x hit L2 instead of paying an HBM round trip per 32-column chunk.
-        if (e.nchw_vec && !(p.debug & 2)) {
-            const int seg = (e.P % 128 == 0) ? 128 : (e.P % 64 == 0) ? 64 : 32;
-            auto prefetch_tile = [&](int64_t ct) {
-                const int64_t m_grp = ct / p.n_tiles;
-                const int n_blk = (int)(ct - m_grp * p.n_tiles);
-                const int64_t m_blk = m_grp * CG + rank;
-                for (int r0 = 0; r0 < TC_BM; r0 += seg) {
-                    const int64_t row = m_blk * TC_BM + r0;
-                    if (row >= p.M) break;
-                    const int64_t bfi = row / e.P;
-                    const int64_t bb = bfi / e.F, ff = bfi - bb * e.F;
-                    const bf16 *xr = reinterpret_cast<const bf16 *>(e.x) + bb * e.xsb + ff * e.xsf + (row - bfi * e.P) + (int64_t)(n_blk * p.block_n) * e.xsc;
-                    for (int c = lane; c < p.block_n; c += 32) ptx::bulk_prefetch_l2(xr + (int64_t)c * e.xsc, (uint32_t)(seg * 2));
-                }
-            };
-            int as = 0; uint32_t aphase = 0;
-            if (cluster_id < p.cluster_tiles) prefetch_tile(cluster_id);
-            for (int64_t ct = cluster_id; ct < p.cluster_tiles; ct += num_clusters) {
-                if (ct + num_clusters < p.cluster_tiles) prefetch_tile(ct + num_clusters);
-                ptx::mbar_wait(tfull_bar(as), aphase);                    // pace: one tile ahead of the epilogue
-                if (++as == 2) { as = 0; aphase ^= 1u; }
-            }
-        }
     } else if (GNA && warp >= 4 + TC_EPI_WARPS) {
         // ===================== GroupNorm converter (GNA): normalise the A tile in place =====================
         // Thread (j, row): the 128-byte row of channel kb*64 + row in half j (64 positions of image bf_j).  The affine is per

@@ -16,7 +16,7 @@ namespace nmm {
 // rstd) is done by the consumer, so there are no atomics and the result is deterministic.
 // ------------------------------------------------------------------------------------------------
 constexpr int GN_THREADS = 256;
-constexpr int GN_CHUNK = 8192;      // elements per CTA
+constexpr int GN_CHUNK = 16384;     // elements per CTA (8 x 16-byte loads in flight per thread in bf16)
 
 static int gn_splits(const Geo &g) {
     int64_t per_group = (int64_t)(g.C / NMM_GN_GROUPS) * g.P;
@@ -431,9 +431,13 @@ static int launch_ln_t(const Geo &g, const nmm_shape *s, const float *h, const f
     ProfScope prof(K_LAYERNORM, st, 0.0, (double)g.N * g.C * (4 + sizeof(TOut)));
     const bool vec_ok = aligned(h, 16) && aligned(w, 16) && aligned(b, 16) && aligned(out, 16) && (pe == nullptr || aligned(pe, 16));
     if (vec_ok && (g.C == 320 || g.C == 640 || g.C == 1280)) {
-        const int64_t blocks = ceil_div(g.N, 16);                    // 16 rows (half-warps) per 256-thread CTA
+        // 16 rows (half-warps) per 256-thread CTA; at the small UNet levels fewer rows per CTA so that the grid still covers the
+        // 148 SMs several times over (1024 tokens in 16-row CTAs would be 64 CTAs)
+        int threads = 256;
+        while (threads > 64 && ceil_div(g.N, threads / 16) < 4 * 148) threads >>= 1;
+        const int64_t blocks = ceil_div(g.N, threads / 16);
         if (blocks > 0x7fffffff) return fail(NMM_ERR_UNSUPPORTED, "too many tokens");
-        dim3 grid((unsigned)blocks), block(256);
+        dim3 grid((unsigned)blocks), block((unsigned)threads);
         if (g.C == 320) launch_pdl(layernorm_pe_vec_kernel<TOut, 5>, grid, block, 0, st, h, w, b, pe, out, g.N, g.F, g.P, s->eps_ln);
         else if (g.C == 640) launch_pdl(layernorm_pe_vec_kernel<TOut, 10>, grid, block, 0, st, h, w, b, pe, out, g.N, g.F, g.P, s->eps_ln);
         else launch_pdl(layernorm_pe_vec_kernel<TOut, 20>, grid, block, 0, st, h, w, b, pe, out, g.N, g.F, g.P, s->eps_ln);

@@ -86,10 +86,6 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst_smem, const void *src,
 __device__ __forceinline__ void bulk_store_1d(void *dst, uint32_t src_smem, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
 }
-// L2 prefetch of `bytes` (multiple of 16) contiguous bytes at a 16-byte aligned global address
-__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until the shared-memory SOURCE of all of this thread's committed bulk stores has been read (buffers reusable)
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
