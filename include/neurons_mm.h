@@ -135,7 +135,7 @@ NMM_API int nmm_validate(const nmm_shape *s);
 NMM_API int nmm_packed_params_bytes(const nmm_shape *s, size_t *out_bytes);
 NMM_API int nmm_workspace_bytes(const nmm_shape *s, size_t *out_bytes);
 /* Convert + re-lay-out the module's parameters once (QKV concatenated, GEGLU value/gate rows
- * interleaved, GEMM operands in the arithmetic dtype, biases / norm affines / PE in fp32). */
+ * interleaved in groups of four, GEMM operands in the arithmetic dtype, biases / norm affines / PE in fp32). */
 NMM_API int nmm_pack_params(const nmm_shape *s, const nmm_params *src, void *packed, size_t packed_bytes, void *stream);
 /* y = module(x).  x, y: element type s->dtype with the strides in *s.  x and y must not alias. */
 NMM_API int nmm_forward(const nmm_shape *s, const void *x, void *y, const void *packed, void *workspace,
@@ -183,8 +183,9 @@ typedef enum nmm_epilogue {
     NMM_EPI_RESIDUAL = 1,       /* out == NULL: h = acc + bias + h (fp32, in place)   motion_module.py:213-219;
                                    out != NULL: out = acc + bias + h in `dtype`, h is only read (the last
                                    feed-forward: its sum is consumed once, by proj_out)                        */
-    NMM_EPI_GEGLU = 2,          /* out[:, j] = (acc[2j]+b[2j]) * gelu_erf(acc[2j+1]+b[2j+1]) -> out [M,N/2];
-                                   W rows pre-interleaved value/gate     motion_module_new.py:516-518          */
+    NMM_EPI_GEGLU = 2,          /* out[:, 2q+i] = (acc[4q+i]+b[4q+i]) * gelu_erf(acc[4q+2+i]+b[4q+2+i]), i = 0,1 -> out [M,N/2];
+                                   W rows (and bias) pre-interleaved in groups of four: value 2q, value 2q+1, gate 2q, gate 2q+1
+                                   (N % 4 == 0)                          motion_module_new.py:516-518          */
     NMM_EPI_OUTPUT = 3          /* y[b,c,f,p] = acc + bias + x[b,c,f,p]   motion_module.py:152-156             */
 } nmm_epilogue;
 

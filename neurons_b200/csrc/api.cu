@@ -160,8 +160,12 @@ static int device_check() {
 }
 
 // ---- parameter packing kernels ---------------------------------------------------------------------------
-// dst[r, :] = src[map(r), :] with dtype conversion.  interleave_half > 0 : map(r) = r/2 + (r & 1) * interleave_half
-// (GEGLU: packed row 2j = value row j, packed row 2j+1 = gate row j + 4C; motion_module_new.py:516-517 chunk(2)).
+// dst[r, :] = src[map(r), :] with dtype conversion.  interleave_half > 0 : GEGLU packing in groups of four rows
+//   packed rows 4q .. 4q+3  =  value 2q, value 2q+1, gate 2q, gate 2q+1        (gate j = source row j + half; motion_module_new.py:516-517 chunk(2))
+// so that the accumulator columns of one thread hold (v0, v1, g0, g1): register-adjacent pairs for the packed fp32x2 epilogue math.
+__host__ __device__ inline int64_t geglu_src_row(int64_t r, int64_t half) {
+    return half > 0 ? 2 * (r >> 2) + (r & 1) + ((r >> 1) & 1) * half : r;
+}
 template <typename TS, typename TD>
 __global__ void convert_rows_kernel(const TS *__restrict__ src, TD *__restrict__ dst, int64_t rows, int64_t cols, int64_t half) {
     pdl_wait();                    // PDL: the previous kernel has completed (no-op without the launch attribute)
@@ -169,7 +173,7 @@ __global__ void convert_rows_kernel(const TS *__restrict__ src, TD *__restrict__
     const int64_t total = rows * cols;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / cols, c = i - r * cols;
-        const int64_t sr = half > 0 ? (r >> 1) + (r & 1) * half : r;
+        const int64_t sr = geglu_src_row(r, half);
         dst[i] = from_f32<TD>(to_f32(src[sr * cols + c]));
     }
 }
@@ -204,7 +208,7 @@ __global__ void fold_weight_kernel(const TS *__restrict__ src, const TS *__restr
     const int64_t total = rows * cols;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / cols, c = i - r * cols;
-        const int64_t sr = half > 0 ? (r >> 1) + (r & 1) * half : r;
+        const int64_t sr = geglu_src_row(r, half);
         dst[i] = __float2bfloat16_rn(to_f32(src[sr * cols + c]) * to_f32(gamma[c]));
     }
 }
@@ -219,7 +223,7 @@ __global__ void __launch_bounds__(128) fold_tables_kernel(const TS *__restrict__
     pdl_launch_dependents();
     __shared__ float red[4];
     const int64_t r = blockIdx.x;
-    const int64_t sr = half > 0 ? (r >> 1) + (r & 1) * half : r;
+    const int64_t sr = geglu_src_row(r, half);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     auto block_sum = [&](float v) {
         v = warp_sum(v);
@@ -648,7 +652,7 @@ int nmm_linear(int32_t dtype, int32_t epilogue, int64_t M, int32_t N, int32_t K,
             if (!h) return fail(NMM_ERR_BAD_ARG, "RESIDUAL epilogue needs h");
             a.no_h_store = out != nullptr;      // documented contract: with `out`, h is only read
             break;
-        case NMM_EPI_GEGLU: if (!out || (N & 1)) return fail(NMM_ERR_BAD_ARG, "GEGLU epilogue needs out and even N"); break;
+        case NMM_EPI_GEGLU: if (!out || (N & 3)) return fail(NMM_ERR_BAD_ARG, "GEGLU epilogue needs out and N %% 4 == 0 (rows packed in groups of four)"); break;
         case NMM_EPI_OUTPUT: {
             if ((rc = validate(s)) != NMM_OK) return rc;
             if (!x || !y) return fail(NMM_ERR_BAD_ARG, "OUTPUT epilogue needs x and y");

@@ -3,6 +3,7 @@
 //   STORE     out = acc + bias                                         Linear            motion_module.py:145, :289-298
 //   RESIDUAL  h   = acc + bias + h   (or out = acc + bias + h)         "attn(...) + hidden_states", "ff(...) + hidden_states"  :213-219
 //   GEGLU     out = (acc_v + b_v) * gelu_erf(acc_g + b_g)              GEGLU.forward     motion_module_new.py:516-518
+//             (columns in groups of four: value 2q, value 2q+1, gate 2q, gate 2q+1 -> outputs 2q, 2q+1)
 //   OUTPUT    y[b,c,f,p] = acc + bias + x[b,c,f,p]                     proj_out, back to NCHW, + residual      motion_module.py:152-156
 #pragma once
 #include "common.cuh"
@@ -90,7 +91,10 @@ __device__ __forceinline__ void epilogue_apply(const EpiParams &e, int64_t row, 
     } else if constexpr (EPI == NMM_EPI_GEGLU) {
         float o[NC / 2];
 #pragma unroll
-        for (int j = 0; j < NC / 2; j++) o[j] = acc[2 * j] * gelu_erf(acc[2 * j + 1]);
+        for (int q = 0; q < NC / 4; q++) {      // columns 4q .. 4q+3 = value 2q, value 2q+1, gate 2q, gate 2q+1
+            o[2 * q] = acc[4 * q] * gelu_erf(acc[4 * q + 2]);
+            o[2 * q + 1] = acc[4 * q + 1] * gelu_erf(acc[4 * q + 3]);
+        }
         T *dst = reinterpret_cast<T *>(e.out) + row * (e.N / 2) + col0 / 2;
         if constexpr (NC / 2 >= 4) {
             store_row<NC / 2>(dst, o);

@@ -27,6 +27,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <type_traits>
 
 #include "common.cuh"
 #include "epilogue.cuh"
@@ -424,30 +425,43 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     const int col0 = n_blk * p.block_n + c0;
                     wait_acc();
                     uint32_t o[16];
+                    // both 32-column halves are requested before the single tcgen05.wait::ld: one exposed TMEM latency per chunk
+                    uint32_t r[2][32];
+                    ptx::tmem_ld32(t_row + (uint32_t)c0, r[0]);
+                    ptx::tmem_ld32(t_row + (uint32_t)(c0 + 32), r[1]);
+                    auto half_chunk = [&](auto HAS_BIAS, int hc) {
+                        float4 b4[8];
+                        if constexpr (decltype(HAS_BIAS)::value) {
 #pragma unroll
-                    for (int hc = 0; hc < 2; hc++) {
-                        uint32_t r[32];
-                        ptx::tmem_ld32(t_row + (uint32_t)(c0 + 32 * hc), r);
-                        ptx::tmem_ld_wait();
+                            for (int j = 0; j < 8; j++) b4[j] = __ldg(reinterpret_cast<const float4 *>(e.bias + col0 + 32 * hc) + j);
+                        }
+                        if (hc == 0) ptx::tmem_ld_wait();
 #pragma unroll
                         for (int j = 0; j < 8; j++) {
+                            // accumulator columns 4j .. 4j+3 = value 2q, value 2q+1, gate 2q, gate 2q+1 (packing order, api.cu)
                             float v0, g0, v1, g1;
                             if (ln_in) {      // out = rstd * (acc - mean * g[n]) + c[n]
                                 const float4 gg = __ldg(reinterpret_cast<const float4 *>(e.ln_g + col0 + 32 * hc) + j);
                                 const float4 cc = __ldg(reinterpret_cast<const float4 *>(e.ln_c + col0 + 32 * hc) + j);
-                                v0 = fmaf(ln_rstd, __uint_as_float(r[4 * j]) - ln_mu * gg.x, cc.x);
-                                g0 = fmaf(ln_rstd, __uint_as_float(r[4 * j + 1]) - ln_mu * gg.y, cc.y);
-                                v1 = fmaf(ln_rstd, __uint_as_float(r[4 * j + 2]) - ln_mu * gg.z, cc.z);
-                                g1 = fmaf(ln_rstd, __uint_as_float(r[4 * j + 3]) - ln_mu * gg.w, cc.w);
+                                v0 = fmaf(ln_rstd, __uint_as_float(r[hc][4 * j]) - ln_mu * gg.x, cc.x);
+                                v1 = fmaf(ln_rstd, __uint_as_float(r[hc][4 * j + 1]) - ln_mu * gg.y, cc.y);
+                                g0 = fmaf(ln_rstd, __uint_as_float(r[hc][4 * j + 2]) - ln_mu * gg.z, cc.z);
+                                g1 = fmaf(ln_rstd, __uint_as_float(r[hc][4 * j + 3]) - ln_mu * gg.w, cc.w);
+                            } else if constexpr (decltype(HAS_BIAS)::value) {
+                                // (v0, v1) and (g0, g1) are register-adjacent pairs of the TMEM load and of the bias vector: packed adds
+                                f32x2_unpack(f32x2_add(f32x2_pack(__uint_as_float(r[hc][4 * j]), __uint_as_float(r[hc][4 * j + 1])), f32x2_pack(b4[j].x, b4[j].y)), v0, v1);
+                                f32x2_unpack(f32x2_add(f32x2_pack(__uint_as_float(r[hc][4 * j + 2]), __uint_as_float(r[hc][4 * j + 3])), f32x2_pack(b4[j].z, b4[j].w)), g0, g1);
                             } else {
-                                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                                if (e.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4 *>(e.bias + col0 + 32 * hc) + j);
-                                v0 = __uint_as_float(r[4 * j]) + b4.x; g0 = __uint_as_float(r[4 * j + 1]) + b4.y;
-                                v1 = __uint_as_float(r[4 * j + 2]) + b4.z; g1 = __uint_as_float(r[4 * j + 3]) + b4.w;
+                                v0 = __uint_as_float(r[hc][4 * j]); v1 = __uint_as_float(r[hc][4 * j + 1]);
+                                g0 = __uint_as_float(r[hc][4 * j + 2]); g1 = __uint_as_float(r[hc][4 * j + 3]);
                             }
-                            o[8 * hc + j] = pack_bf16x2(v0 * gelu_erf_fast(g0), v1 * gelu_erf_fast(g1));
+                            float y0, y1;
+                            geglu_pair(v0, g0, v1, g1, y0, y1);
+                            o[8 * hc + j] = pack_bf16x2(y0, y1);
                         }
-                    }
+                    };
+                    if (e.bias != nullptr && !ln_in) { half_chunk(std::true_type{}, 0); half_chunk(std::true_type{}, 1); }
+                    else { half_chunk(std::false_type{}, 0); half_chunk(std::false_type{}, 1); }
                     if (lane == 0) ptx::bulk_wait_read0();                // the box of the previous chunk has been read
                     __syncwarp();
 #pragma unroll

@@ -176,13 +176,13 @@ def test_linear_store_and_residual(M, N, K, dtype):
 @pytest.mark.parametrize("M,N,K", [(256, 2560, 320), (130, 512, 64), (2, 256, 32), (1024, 5120, 640)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
 def test_linear_geglu(M, N, K, dtype):
-    # library contract: W rows pre-interleaved (row 2j = value j, row 2j+1 = gate j); emulate the packing here
+    # library contract: W rows pre-interleaved in groups of four (value 2q, value 2q+1, gate 2q, gate 2q+1); emulate the packing here
     A, W, bias = _gemm_inputs(M, N, K, dtype)
     half = N // 2
     u = A.double() @ W.double().T + bias.double()
     ref = u[:, :half] * torch.nn.functional.gelu(u[:, half:])       # value * gelu(gate), motion_module_new.py:516-518
-    Wi = torch.empty_like(W); Wi[0::2] = W[:half]; Wi[1::2] = W[half:]
-    bi = torch.empty_like(bias); bi[0::2] = bias[:half]; bi[1::2] = bias[half:]
+    Wi = torch.empty_like(W); Wi[0::4] = W[0:half:2]; Wi[1::4] = W[1:half:2]; Wi[2::4] = W[half::2]; Wi[3::4] = W[half + 1::2]
+    bi = torch.empty_like(bias); bi[0::4] = bias[0:half:2]; bi[1::4] = bias[1:half:2]; bi[2::4] = bias[half::2]; bi[3::4] = bias[half + 1::2]
     out = ops.linear(A.to(DEV, dtype), Wi.to(DEV, dtype), bi.to(DEV), nlib.EPI_GEGLU)
     assert out.shape == (M, half)
     tol = 5e-5 if dtype == torch.float32 else 2 ** -8 * 1.01 * ref.abs().max().item() + 2e-4
