@@ -288,6 +288,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 const float ca = rs * sm_gb[c], cb = sm_gb[kpad + c] - mu * ca;
                 ptx::mbar_wait(full_bar(stage), phase);
                 const uint32_t rbase = smem_base + (uint32_t)stage * stage_bytes + (uint32_t)(j * TC_A_HALF + row * 128);
+                const uint64_t ca2 = f32x2_pack(ca, ca), cb2 = f32x2_pack(cb, cb);
                 if (!(p.debug & 4)) {
                     // all 8 loads first (independent, pipelined), then the arithmetic, then the stores
                     uint32_t w[8][4];
@@ -299,7 +300,11 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
 #pragma unroll
-                        for (int k = 0; k < 4; k++) w[i][k] = pack_bf16x2(fmaf(bf16_lo(w[i][k]), ca, cb), fmaf(bf16_hi(w[i][k]), ca, cb));
+                        for (int k = 0; k < 4; k++) {      // both bf16 halves of the word through one packed fp32x2 FMA (same rounding as fmaf)
+                            float lo, hi;
+                            f32x2_unpack(f32x2_fma(f32x2_pack(bf16_lo(w[i][k]), bf16_hi(w[i][k])), ca2, cb2), lo, hi);
+                            w[i][k] = pack_bf16x2(lo, hi);
+                        }
                         sts128(rbase + (uint32_t)(((i + row) & 7) << 4), w[i][0], w[i][1], w[i][2], w[i][3]);
                     }
                 }
