@@ -199,10 +199,9 @@ static int launch_attn_t(const Geo &g, const T *qkv, T *ctx, cudaStream_t st) {
 #define ATTN_CASE(FM)                                                                                                    \
     do {                                                                                                                 \
         auto kern = temporal_attention_kernel<T, VEC, FM>;                                                               \
-        static bool attr_set = false; /* once per instantiation; never inside a stream capture after warm-up */         \
-        if (!attr_set) {                                                                                                 \
+        static DeviceOnce once; /* per instantiation and device; never inside a stream capture after warm-up */            \
+        if (once.first()) {                                                                                              \
             NMM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));          \
-            attr_set = true;                                                                                             \
         }                                                                                                                \
         ProfScope prof(K_ATTENTION, st, 4.0 * g.N * g.F * g.C, 4.0 * g.N * g.C * sizeof(T));                             \
         launch_pdl(kern, grid, threads, smem, st, qkv, ctx, g.B, g.F, g.P, g.C, g.heads, PB, HB, scale);                          \
@@ -635,10 +634,9 @@ static int launch_attn_mma(const Geo &g, const bf16 *qkv, bf16 *ctx, cudaStream_
 #define ATTN_FIXED(FF, DD)                                                                                               \
     do {                                                                                                                 \
         auto kern = temporal_attention_mma_fixed_kernel<FF, DD>;                                                         \
-        static bool attr_set = false;                                                                                    \
-        if (!attr_set) {                                                                                                 \
+        static DeviceOnce once;                                                                                          \
+        if (once.first()) {                                                                                              \
             NMM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));            \
-            attr_set = true;                                                                                             \
         }                                                                                                                \
         ProfScope prof(K_ATTENTION, st, 4.0 * g.N * g.F * g.C, 4.0 * g.N * g.C * 2);                                      \
         launch_pdl(kern, gridf, thr_f, smem_f, st, qkv, ctx, g.P, g.C, PBf, sl2);                                          \
@@ -668,10 +666,9 @@ static int launch_attn_mma(const Geo &g, const bf16 *qkv, bf16 *ctx, cudaStream_
 #define ATTN_MMA(FF)                                                                                                     \
     do {                                                                                                                 \
         auto kern = temporal_attention_mma_kernel<FF>;                                                                   \
-        static bool attr_set = false;                                                                                    \
-        if (!attr_set) {                                                                                                 \
+        static DeviceOnce once;                                                                                          \
+        if (once.first()) {                                                                                              \
             NMM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));            \
-            attr_set = true;                                                                                             \
         }                                                                                                                \
         ProfScope prof(K_ATTENTION, st, 4.0 * g.N * g.F * g.C, 4.0 * g.N * g.C * 2);                                      \
         launch_pdl(kern, grid, warps * 32, smem, st, qkv, ctx, g.B, g.P, g.C, g.heads, PB, HB, scale_log2e);                      \

@@ -39,6 +39,18 @@ struct ProfScope {          // records start on construction, stop on destructio
     ~ProfScope();
 };
 
+// cudaFuncSetAttribute is per device: a "done" flag per (kernel instantiation, device ordinal).  Usage:
+//     static DeviceOnce once;  if (once.first()) NMM_CUDA_OK(cudaFuncSetAttribute(...));
+struct DeviceOnce {
+    std::atomic<bool> done[64];
+    DeviceOnce() { for (auto &d : done) d.store(false, std::memory_order_relaxed); }
+    bool first() {                      // true exactly until mark() has been called for the current device
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+        return !done[dev].exchange(true, std::memory_order_relaxed);
+    }
+};
+
 // Count + check a kernel launch without synchronising (stays graph-capturable).
 #define NMM_LAUNCHED(name)                                                                          \
     do {                                                                                            \

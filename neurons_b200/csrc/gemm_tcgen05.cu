@@ -722,11 +722,8 @@ template <int EPI, int CG, bool LNF, bool GNA = false>
 static int launch_tc_t(const CUtensorMap &ta, const CUtensorMap &tw, const CUtensorMap &th, const CUtensorMap &to, const TcParams &p,
                        const EpiParams &e, size_t smem, int grid, cudaStream_t st, double flops, double bytes, const GnParams &gn = GnParams()) {
     auto kern = linear_tc_kernel<EPI, CG, LNF, GNA>;
-    static bool attr_set = false;     // per template instantiation
-    if (!attr_set) {
-        NMM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX));
-        attr_set = true;
-    }
+    static DeviceOnce once;           // per template instantiation and device
+    if (once.first()) NMM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX));
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)grid);
