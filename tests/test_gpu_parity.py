@@ -106,7 +106,9 @@ def test_layernorm_pe(C, F, H, W, B, dtype, with_pe):
 
 
 @pytest.mark.parametrize("C,F,H,W,B", [(320, 8, 8, 8, 1), (320, 16, 4, 5, 2), (640, 24, 2, 2, 1), (1280, 16, 2, 2, 1),
-                                       (32, 1, 1, 2, 1), (64, 32, 2, 2, 1), (1280, 8, 4, 4, 1)])
+                                       (32, 1, 1, 2, 1), (64, 32, 2, 2, 1), (1280, 8, 4, 4, 1),
+                                       # ragged position counts (last tile of the specialised kernel holds fewer positions), every d_h x F variant
+                                       (640, 8, 3, 5, 2), (1280, 8, 3, 3, 1), (640, 16, 3, 3, 2), (320, 8, 3, 5, 1), (320, 8, 33, 33, 1)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
 def test_temporal_attention(C, F, H, W, B, dtype):
     cfg = mo.MotionConfig(C, max_len=32)
