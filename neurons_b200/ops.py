@@ -30,8 +30,8 @@ class ModuleConfig:
     pos_enc: bool = True
     max_len: int = 24
     # bf16 mode: fold the LayerNorms into the QKV / GEGLU GEMMs (3 launches and one fp32 read of the residual fewer per call).
-    # Measured on B200 it is time-neutral (the GEMM epilogue, not the LayerNorm kernel, is the bottleneck it moves work into:
-    # 8.90 vs 8.83 ms/step), so the default keeps the separate, exactly-LayerNorm kernel; NMM_LN_FOLD=1 / ln_fold=True enables it.
+    # Measured on B200 it is slower (it moves work into the GEMM epilogue, which is the bottleneck: 8.5 vs 7.6 ms/step), so the
+    # default keeps the separate, exactly-LayerNorm kernel; NMM_LN_FOLD=1 / ln_fold=True enables it (kept as a tested option).
     ln_fold: bool = False
 
 

@@ -281,7 +281,7 @@ def test_module_properties_full_size(dtype):
 
 
 def test_layernorm_folding_matches_separate_layernorm(monkeypatch):
-    # NMM_LN_FOLD=1 folds the LayerNorms into the QKV / GEGLU GEMMs (12 instead of 15 launches per call); the default runs the
+    # NMM_LN_FOLD=1 folds the LayerNorms into the QKV / GEGLU GEMMs (3 launches fewer per call); the default runs the
     # separate LayerNorm kernel.  Both variants must meet the bar and agree closely.
     fx, cfg, params, x = helpers.load_golden("c320_f16_8x8_a2_view")
     xb = x.to(DEV, torch.bfloat16)
