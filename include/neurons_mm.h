@@ -189,6 +189,12 @@ typedef enum nmm_epilogue {
     NMM_EPI_OUTPUT = 3          /* y[b,c,f,p] = acc + bias + x[b,c,f,p]   motion_module.py:152-156             */
 } nmm_epilogue;
 
+/* QKV projection with the temporal attention fused into its epilogue (bf16; d_h in {40, 80}; frames in {8, 16};
+ * H*W % (128 / frames) == 0): ctx = attention(tokens . Wq^T, tokens . Wk^T, tokens . Wv^T) -- motion_module.py:289-321 with
+ * motion_module_new.py:258-287.  tokens: [N, C]; wqkv: [3C, C] rows of to_q, then to_k, then to_v; w_scratch: 3C*C elements (receives the
+ * tile-ordered copy the kernel consumes); ctx: [N, C].  Otherwise NMM_ERR_UNSUPPORTED (use nmm_linear + nmm_temporal_attention;
+ * nmm_forward picks automatically). */
+NMM_API int nmm_qkv_attention(const nmm_shape *s, const void *tokens, const void *wqkv, void *w_scratch, void *ctx, void *stream);
 /* D[M,N] = A[M,K] . W[N,K]^T with a fused epilogue.  A, W, out: element type `dtype` (NMM_BF16 runs on
  * tcgen05 tensor cores with fp32 accumulation in TMEM; NMM_F32 runs on fp32 FMA).  bias: fp32 [N] or NULL.
  * M = s->batch*frames*height*width is implied by `s` for NMM_EPI_OUTPUT; otherwise M is explicit. */

@@ -61,9 +61,14 @@ ProfScope::~ProfScope() {
 }
 
 // ---- packed parameter layout -------------------------------------------------------------------------
-struct AttnOff { size_t ln_w, ln_b, wqkv, wo, bo, pe, g_qkv, c_qkv, pew; };           // g/c/pew: LayerNorm-folding tables
+struct AttnOff { size_t ln_w, ln_b, wqkv, wqkv_t, wo, bo, pe, g_qkv, c_qkv, pew; };   // wqkv_t: tile-ordered copy (fused attention); g/c/pew: LayerNorm folding
 struct LayerOff { AttnOff attn[NMM_MAX_ATTN]; size_t ff_ln_w, ff_ln_b, w1, b1, w2, b2, g1, c1; };
 struct PackedLayout { size_t gn_w, gn_b, w_in, b_in; LayerOff layer[NMM_MAX_LAYERS]; size_t w_out, b_out, total; };
+
+// does this module keep a tile-ordered q|k|v weight for the fused QKV + attention kernel?  (shape-independent part of the test)
+static bool attn_fuse_weights(const Geo &g) {
+    return g.dtype == NMM_BF16 && !g.ln_fold && g.C % NMM_ATTN_TILE_CH == 0 && (g.dh == 40 || g.dh == 80);
+}
 
 static PackedLayout packed_layout(const Geo &g) {
     PackedLayout L;
@@ -78,6 +83,7 @@ static PackedLayout packed_layout(const Geo &g) {
             AttnOff &a = L.layer[l].attn[i];
             a.ln_w = take(C * 4); a.ln_b = take(C * 4);
             a.wqkv = take(3 * C * C * ws); a.wo = take(C * C * ws); a.bo = take(C * 4);
+            a.wqkv_t = take(attn_fuse_weights(g) ? 3 * C * C * ws : 0);
             a.pe = take(g.pos_enc ? (size_t)g.max_len * C * 4 : 0);
             a.g_qkv = take(g.ln_fold ? 3 * C * 4 : 0); a.c_qkv = take(g.ln_fold ? 3 * C * 4 : 0);
             a.pew = take(g.ln_fold && g.pos_enc ? (size_t)g.max_len * 3 * C * 4 : 0);
@@ -191,6 +197,31 @@ int launch_convert_rows(const void *src, int src_dtype, void *dst, int dst_dtype
     else if (src_dtype == NMM_BF16 && dst_dtype == NMM_BF16) launch_pdl(convert_rows_kernel<bf16, bf16>, blocks, threads, 0, st, (const bf16 *)src, (bf16 *)dst, rows, cols, half);
     else return fail(NMM_ERR_BAD_ARG, "unknown parameter dtype");
     NMM_LAUNCHED("convert_rows_kernel");
+    return NMM_OK;
+}
+
+// q|k|v weight [3C, C] (rows: all of q, then k, then v) -> tile order of the fused QKV + attention kernel: for each 80-channel tile t,
+// its 80 q rows, then its 80 k rows, then its 80 v rows (tile t = rows 240 t .. 240 t + 239).  bf16, 16-byte vector copy.
+__global__ void qkv_tile_order_kernel(const bf16 *__restrict__ src, bf16 *__restrict__ dst, int C) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int vec_per_row = C / 8;
+    const int64_t total = (int64_t)3 * C * vec_per_row;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / vec_per_row), v = (int)(i - (int64_t)r * vec_per_row);
+        const int t = r / (3 * NMM_ATTN_TILE_CH), w = r - t * 3 * NMM_ATTN_TILE_CH;
+        const int seg = w / NMM_ATTN_TILE_CH, j = w - seg * NMM_ATTN_TILE_CH;
+        const int sr = seg * C + t * NMM_ATTN_TILE_CH + j;
+        reinterpret_cast<uint4 *>(dst)[i] = __ldg(reinterpret_cast<const uint4 *>(src) + (int64_t)sr * vec_per_row + v);
+    }
+}
+static int launch_qkv_tile_order(const void *src, void *dst, int C, cudaStream_t st) {
+    if (C % NMM_ATTN_TILE_CH != 0 || C % 8 != 0 || !aligned(src, 16) || !aligned(dst, 16)) return fail(NMM_ERR_UNSUPPORTED, "qkv tile order needs C %% 80 == 0");
+    const int64_t total = (int64_t)3 * C * (C / 8);
+    const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), 148 * 16);
+    ProfScope prof(K_PACK, st, 0.0, (double)total * 32);
+    launch_pdl(qkv_tile_order_kernel, blocks, 256, 0, st, (const bf16 *)src, (bf16 *)dst, C);
+    NMM_LAUNCHED("qkv_tile_order_kernel");
     return NMM_OK;
 }
 
@@ -400,6 +431,7 @@ int nmm_pack_params(const nmm_shape *s, const nmm_params *src, void *packed, siz
                 }
             } else {
                 PACK(ap.to_q, ao.wqkv, wd, C, C, 0); PACK(ap.to_k, ao.wqkv + wbytes, wd, C, C, 0); PACK(ap.to_v, ao.wqkv + 2 * wbytes, wd, C, C, 0);
+                if (attn_fuse_weights(g) && (rc = launch_qkv_tile_order(base + ao.wqkv, base + ao.wqkv_t, (int)C, st)) != NMM_OK) return rc;
             }
         }
         PACK(lp.ff_norm_w, lo.ff_ln_w, NMM_F32, C, 1, 0); PACK(lp.ff_norm_b, lo.ff_ln_b, NMM_F32, C, 1, 0);
@@ -501,10 +533,15 @@ int nmm_forward(const nmm_shape *s, const void *x, void *y, const void *packed, 
                 a.epilogue = NMM_EPI_STORE; a.N = 3 * g.C; a.K = g.C; a.A = tok; a.W = pk + ao.wqkv; a.bias = nullptr; a.h = nullptr; a.out = big;
                 if (fold) consumer(a, F32(ao.g_qkv), F32(ao.c_qkv), g.pos_enc ? F32(ao.pew) : nullptr);
                 else if ((rc = launch_layernorm_pe(gc, &sc, h, F32(ao.ln_w), F32(ao.ln_b), g.pos_enc ? F32(ao.pe) : nullptr, tok, st)) != NMM_OK) return rc;
+                // bf16, d_h 40 / 80, 8 or 16 frames: the attention runs inside the projection's epilogue (q | k | v never leave the SM)
+                const bool attn_fused = attn_fuse_weights(g) && pn == g.P && linear_tc_attn_fusable(g.C, g.heads, g.F, g.P);
+                if (attn_fused) {
+                    a.epilogue = NMM_EPI_QKV_ATTN; a.W = pk + ao.wqkv_t; a.out = ctx; a.attn_B = g.B; a.attn_heads = g.heads;
+                }
                 if ((rc = linear(g, a, st)) != NMM_OK) return rc;
                 clear_fold(a);
                 // softmax(q k^T / sqrt(dh)) v over frames                               motion_module_new.py:258-287
-                if ((rc = launch_temporal_attention(gc, big, ctx, st)) != NMM_OK) return rc;
+                if (!attn_fused && (rc = launch_temporal_attention(gc, big, ctx, st)) != NMM_OK) return rc;
                 // h = ctx . Wo^T + bo + h                                               motion_module.py:321, :213-217
                 a.epilogue = NMM_EPI_RESIDUAL; a.N = g.C; a.K = g.C; a.A = ctx; a.W = pk + ao.wo; a.bias = F32(ao.bo); a.h = h; a.out = nullptr;
                 producer(a);
@@ -635,6 +672,23 @@ int nmm_temporal_attention(const nmm_shape *s, const void *qkv, void *ctx, void 
     if (!qkv || !ctx) return fail(NMM_ERR_BAD_ARG, "NULL argument");
     if ((rc = device_check()) != NMM_OK) return rc;
     return launch_temporal_attention(geo_of(s), qkv, ctx, (cudaStream_t)stream);
+}
+
+int nmm_qkv_attention(const nmm_shape *s, const void *tokens, const void *wqkv, void *w_scratch, void *ctx, void *stream) {
+    int rc = validate(s);
+    if (rc != NMM_OK) return rc;
+    if (!tokens || !wqkv || !w_scratch || !ctx) return fail(NMM_ERR_BAD_ARG, "NULL argument");
+    if ((rc = device_check()) != NMM_OK) return rc;
+    const Geo g = geo_of(s);
+    if (g.dtype != NMM_BF16 || !linear_tc_attn_fusable(g.C, g.heads, g.F, g.P))
+        return fail(NMM_ERR_UNSUPPORTED, "nmm_qkv_attention: bf16, d_h in {40, 80}, frames in {8, 16}, H*W %% (128 / frames) == 0 only");
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = launch_qkv_tile_order(wqkv, w_scratch, g.C, st)) != NMM_OK) return rc;
+    LinearArgs a;
+    memset(&a, 0, sizeof(a));
+    a.epilogue = NMM_EPI_QKV_ATTN; a.M = g.N; a.N = 3 * g.C; a.K = g.C; a.A = tokens; a.W = w_scratch; a.out = ctx;
+    a.F = g.F; a.P = g.P; a.attn_B = g.B; a.attn_heads = g.heads;
+    return launch_linear_tc(a, st);
 }
 
 int nmm_linear(int32_t dtype, int32_t epilogue, int64_t M, int32_t N, int32_t K, const void *A, const void *W, const float *bias,

@@ -14,6 +14,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "attention_core.cuh"
 
 namespace nmm {
 
@@ -223,40 +224,6 @@ static int launch_attn_t(const Geo &g, const T *qkv, T *ctx, cudaStream_t st) {
 // Staging, head-group tiling and the coalesced write-back are shared with the SIMT kernel above.
 // The probabilities are fed to the second MMA as a bf16 hi + lo pair (two MMAs), so P carries ~16 mantissa bits.
 // ------------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void ldsm_x1(uint32_t addr, uint32_t &r0) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x1.shared.b16 {%0}, [%1];" : "=r"(r0) : "r"(addr));
-}
-__device__ __forceinline__ void ldsm_x2(uint32_t addr, uint32_t &r0, uint32_t &r1) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
-}
-__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
-}
-__device__ __forceinline__ void ldsm_x1_t(uint32_t addr, uint32_t &r0) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x1.trans.shared.b16 {%0}, [%1];" : "=r"(r0) : "r"(addr));
-}
-__device__ __forceinline__ void ldsm_x2_t(uint32_t addr, uint32_t &r0, uint32_t &r1) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
-}
-__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
-}
-__device__ __forceinline__ void mma_k16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ void mma_k8(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5}, {%6}, {%0, %1, %2, %3};"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-                 : "r"(a0), "r"(a1), "r"(b0));
-}
-// split two fp32 into bf16 hi and bf16 lo (residual) pairs
-__device__ __forceinline__ void split_bf16x2(float x, float y, uint32_t &hi, uint32_t &lo) {
-    hi = pack_bf16x2(x, y);
-    lo = pack_bf16x2(x - bf16_lo(hi), y - bf16_hi(hi));
-}
-
 template <int F>      // 8 or 16
 __global__ void __launch_bounds__(256) temporal_attention_mma_kernel(const bf16 *__restrict__ qkv, bf16 *__restrict__ ctx, int B, int P,
                                                                      int C, int heads, int PB, int HB, float scale_log2e) {
@@ -411,7 +378,7 @@ __global__ void __launch_bounds__(256) temporal_attention_mma_fixed_kernel(const
     pdl_launch_dependents();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     bf16 *sm = reinterpret_cast<bf16 *>(smem_raw);
-    constexpr int W = 320, HB = W / DH, NT = F / 8;
+    constexpr int W = 320;
     constexpr int PITCH = 3 * W + 8;            // elements; 1936 B per row: (1936 / 4) % 32 == 4 -> ldmatrix rows hit distinct banks
     constexpr uint32_t RS = PITCH * 2;          // row stride in bytes
     const int c_off = blockIdx.y * W;
@@ -446,150 +413,7 @@ __global__ void __launch_bounds__(256) temporal_attention_mma_fixed_kernel(const
         __syncthreads();
     }
 
-    // ---- one warp per (position, head) ------------------------------------------------------------------------------------
-    const int lrow = lane & 7, lmat = lane >> 3;
-    const int crow = lane >> 2, ccol = (lane & 3) * 2;
-    for (int prob = warp; prob < npos * HB; prob += nwarps) {
-        const int pl = prob / HB, hd = prob - pl * HB;
-        const uint32_t qb = sm_u32 + (uint32_t)(pl * F) * RS + (uint32_t)(hd * DH * 2);
-        constexpr uint32_t KOFF = W * 2, VOFF = 2 * W * 2;
-        // per-lane ldmatrix base addresses (constant offsets are added as immediates below)
-        const uint32_t q_ld = qb + (F == 16 ? (uint32_t)(lrow + 8 * (lmat & 1)) * RS + (uint32_t)(16 * (lmat >> 1))
-                                            : (uint32_t)lrow * RS + (uint32_t)(16 * lmat));
-        const uint32_t k_ld = qb + KOFF + (uint32_t)lrow * RS + (uint32_t)(16 * lmat);          // 4 matrices = 32 columns (F == 8) ...
-        const uint32_t k_ld2 = qb + KOFF + (uint32_t)lrow * RS + (uint32_t)(16 * (lmat & 1));   // ... or 2 matrices = 16 columns
-        float s[NT][4];
-#pragma unroll
-        for (int j = 0; j < NT; j++) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; }
-        if constexpr (F == 8) {
-            // 32 head-dim columns per step: one ldmatrix.x4 for Q (rows 0-7), one for K (keys 0-7), two k16 MMAs
-#pragma unroll
-            for (int k0 = 0; k0 + 32 <= DH; k0 += 32) {
-                uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
-                ldsm_x4(q_ld + k0 * 2, a0, a1, a2, a3);
-                ldsm_x4(k_ld + k0 * 2, b0, b1, b2, b3);
-                mma_k16(s[0], a0, 0u, a1, 0u, b0, b1);
-                mma_k16(s[0], a2, 0u, a3, 0u, b2, b3);
-            }
-            constexpr int K1 = DH / 32 * 32;
-            if constexpr (DH - K1 >= 16) {
-                uint32_t a0, a2, b0, b1;
-                ldsm_x2(q_ld + K1 * 2, a0, a2);
-                ldsm_x2(k_ld + K1 * 2, b0, b1);
-                mma_k16(s[0], a0, 0u, a2, 0u, b0, b1);
-            }
-            constexpr int K2 = DH / 16 * 16;
-            if constexpr (DH - K2 == 8) {
-                uint32_t a0, b0;
-                ldsm_x1(q_ld + K2 * 2, a0);
-                ldsm_x1(k_ld + K2 * 2, b0);
-                mma_k8(s[0], a0, 0u, b0);
-            }
-        } else {
-#pragma unroll
-            for (int k0 = 0; k0 + 16 <= DH; k0 += 16) {
-                uint32_t a0, a1, a2, a3;
-                ldsm_x4(q_ld + k0 * 2, a0, a1, a2, a3);
-#pragma unroll
-                for (int j = 0; j < NT; j++) {
-                    uint32_t b0, b1;
-                    ldsm_x2(k_ld2 + (uint32_t)(8 * j) * RS + k0 * 2, b0, b1);
-                    mma_k16(s[j], a0, a1, a2, a3, b0, b1);
-                }
-            }
-            constexpr int K2 = DH / 16 * 16;
-            if constexpr (DH - K2 == 8) {
-                uint32_t a0, a1;
-                ldsm_x2(qb + (uint32_t)(lrow + 8 * (lmat & 1)) * RS + K2 * 2, a0, a1);
-#pragma unroll
-                for (int j = 0; j < NT; j++) {
-                    uint32_t b0;
-                    ldsm_x1(qb + KOFF + (uint32_t)(8 * j + lrow) * RS + K2 * 2, b0);
-                    mma_k8(s[j], a0, a1, b0);
-                }
-            }
-        }
-        // softmax (fp32, base-2 exponentials) over the keys of row crow (regs 0,1) and row crow + 8 (regs 2,3; F == 16 only)
-        float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < NT; j++) { mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1])); mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3])); }
-        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-        if constexpr (F == 16) { mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2)); }
-        float sum0 = 0.f, sum1 = 0.f;
-#pragma unroll
-        for (int j = 0; j < NT; j++) {
-            s[j][0] = exp2f((s[j][0] - mx0) * scale_log2e); s[j][1] = exp2f((s[j][1] - mx0) * scale_log2e);
-            sum0 += s[j][0] + s[j][1];
-            if constexpr (F == 16) {
-                s[j][2] = exp2f((s[j][2] - mx1) * scale_log2e); s[j][3] = exp2f((s[j][3] - mx1) * scale_log2e);
-                sum1 += s[j][2] + s[j][3];
-            }
-        }
-        sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
-        if constexpr (F == 16) { sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2); }
-        const float inv0 = 1.0f / sum0, inv1 = (F == 16) ? 1.0f / sum1 : 0.f;
-        uint32_t ph[4] = {0u, 0u, 0u, 0u}, pl_[4] = {0u, 0u, 0u, 0u};
-        split_bf16x2(s[0][0] * inv0, s[0][1] * inv0, ph[0], pl_[0]);
-        if constexpr (F == 16) {
-            split_bf16x2(s[0][2] * inv1, s[0][3] * inv1, ph[1], pl_[1]);
-            split_bf16x2(s[1][0] * inv0, s[1][1] * inv0, ph[2], pl_[2]);
-            split_bf16x2(s[1][2] * inv1, s[1][3] * inv1, ph[3], pl_[3]);
-        }
-        __syncwarp();                                   // all of this warp's reads of the q rows are done: reuse them for O
-        // O = P V: one ldmatrix.x4.trans feeds 32 (F == 8) or 16 (F == 16) output columns
-        const uint32_t o_st = qb + (uint32_t)crow * RS + (uint32_t)(ccol * 2);
-        if constexpr (F == 8) {
-            const uint32_t v_ld = qb + VOFF + (uint32_t)lrow * RS + (uint32_t)(16 * lmat);
-#pragma unroll
-            for (int n0 = 0; n0 + 32 <= DH; n0 += 32) {
-                uint32_t bv[4];
-                ldsm_x4_t(v_ld + n0 * 2, bv[0], bv[1], bv[2], bv[3]);
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    float o[4] = {0.f, 0.f, 0.f, 0.f};
-                    mma_k8(o, ph[0], 0u, bv[q]);
-                    mma_k8(o, pl_[0], 0u, bv[q]);
-                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(o_st + (n0 + 8 * q) * 2), "r"(pack_bf16x2(o[0], o[1])) : "memory");
-                }
-            }
-            constexpr int N1 = DH / 32 * 32;
-#pragma unroll
-            for (int n0 = N1; n0 < DH; n0 += 8) {
-                uint32_t b0;
-                ldsm_x1_t(qb + VOFF + (uint32_t)lrow * RS + n0 * 2, b0);
-                float o[4] = {0.f, 0.f, 0.f, 0.f};
-                mma_k8(o, ph[0], 0u, b0);
-                mma_k8(o, pl_[0], 0u, b0);
-                asm volatile("st.shared.b32 [%0], %1;" ::"r"(o_st + n0 * 2), "r"(pack_bf16x2(o[0], o[1])) : "memory");
-            }
-        } else {
-            // matrices: (keys 0-7, n0), (keys 8-15, n0), (keys 0-7, n0 + 8), (keys 8-15, n0 + 8)
-            const uint32_t v_ld = qb + VOFF + (uint32_t)(lrow + 8 * (lmat & 1)) * RS + (uint32_t)(16 * (lmat >> 1));
-#pragma unroll
-            for (int n0 = 0; n0 + 16 <= DH; n0 += 16) {
-                uint32_t bv[4];
-                ldsm_x4_t(v_ld + n0 * 2, bv[0], bv[1], bv[2], bv[3]);
-#pragma unroll
-                for (int q = 0; q < 2; q++) {
-                    float o[4] = {0.f, 0.f, 0.f, 0.f};
-                    mma_k16(o, ph[0], ph[1], ph[2], ph[3], bv[2 * q], bv[2 * q + 1]);
-                    mma_k16(o, pl_[0], pl_[1], pl_[2], pl_[3], bv[2 * q], bv[2 * q + 1]);
-                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(o_st + (n0 + 8 * q) * 2), "r"(pack_bf16x2(o[0], o[1])) : "memory");
-                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(o_st + 8 * RS + (n0 + 8 * q) * 2), "r"(pack_bf16x2(o[2], o[3])) : "memory");
-                }
-            }
-            constexpr int N1 = DH / 16 * 16;
-            if constexpr (DH - N1 == 8) {
-                uint32_t b0, b1;
-                ldsm_x2_t(qb + VOFF + (uint32_t)(lrow + 8 * (lmat & 1)) * RS + N1 * 2, b0, b1);
-                float o[4] = {0.f, 0.f, 0.f, 0.f};
-                mma_k16(o, ph[0], ph[1], ph[2], ph[3], b0, b1);
-                mma_k16(o, pl_[0], pl_[1], pl_[2], pl_[3], b0, b1);
-                asm volatile("st.shared.b32 [%0], %1;" ::"r"(o_st + N1 * 2), "r"(pack_bf16x2(o[0], o[1])) : "memory");
-                asm volatile("st.shared.b32 [%0], %1;" ::"r"(o_st + 8 * RS + N1 * 2), "r"(pack_bf16x2(o[2], o[3])) : "memory");
-            }
-        }
-    }
+    attention_tile_mma<F, DH, W>(sm_u32, npos, warp, nwarps, lane, scale_log2e);
     {
         __syncthreads();
         // ---- write ctx rows: one warp per row, 40 16-byte chunks (lanes 0-31, then lanes 0-7) ----------------------------------

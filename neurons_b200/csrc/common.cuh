@@ -207,6 +207,11 @@ int launch_layernorm_pe(const Geo &g, const nmm_shape *s, const float *h, const 
 int launch_temporal_attention(const Geo &g, const void *qkv, void *ctx, cudaStream_t st);
 
 // GEMM + epilogue
+// Internal epilogue (not part of the C ABI enum): the QKV projection with the temporal attention fused into its epilogue --
+// the tile's q | k | v never leave the SM (gemm_tcgen05.cu, "QKV + attention").
+constexpr int NMM_EPI_QKV_ATTN = 4;
+constexpr int NMM_ATTN_TILE_CH = 80;      // channels of q (and of k, v) per N tile of the fused kernel: 2 heads of 40 or 1 head of 80
+
 struct LinearArgs {
     int epilogue;            // nmm_epilogue
     int64_t M;
@@ -229,6 +234,10 @@ struct LinearArgs {
     const double *gn_partial; int gn_splits; double gn_count; float gn_eps;
     const float *gn_w, *gn_b;
     int gn_B;
+    // NMM_EPI_QKV_ATTN: A = LayerNorm output tokens [M, K]; W = the q|k|v weight with rows regrouped per 80-channel tile
+    // (q rows 80t..80t+79, then the k rows, then the v rows of the same channels); out = ctx [M, K].  Uses F, P above, attn_B
+    // images and attn_heads; needs d_h in {40, 80}, F in {8, 16}, P % (128 / F) == 0.
+    int attn_B, attn_heads;
     // LayerNorm folding (bf16 tensor-core path only; see gemm_tcgen05.cu "LayerNorm folding"):
     //   producer side: this GEMM writes the residual stream -> also emit per-row partial (sum, sum of squares) of the new h
     float *ln_part_out;      // [M][NMM_LN_PARTS][2] fp32 or null
@@ -246,6 +255,7 @@ constexpr int NMM_LN_PARTS = 16;     // partial-statistics slots per row: 2 epil
 int launch_gn_apply(const Geo &g, const nmm_shape *s, const void *x, void *y, const float *mean, const float *rstd, const float *gn_w,
                     const float *gn_b, int silu, cudaStream_t st);
 int launch_cfg_ddim(int dtype, int64_t n, void *x, const void *eu, const void *ec, float g, double a_t, double a_prev, cudaStream_t st);
+bool linear_tc_attn_fusable(int C, int heads, int F, int P);
 bool linear_tc_gn_fusable(int64_t M, int P, const void *x, int64_t sb, int64_t sc, int64_t sf);
 void plan_linear_tc(int64_t M, int N, int K, int epilogue, int *block_n, int *cluster);
 // algorithmic work of one Linear launch: 2*M*N*K flops; bytes = operands once + epilogue traffic once
@@ -257,6 +267,8 @@ inline double linear_bytes(const LinearArgs &a, int es) {
         case NMM_EPI_STORE: b += (a.h ? 4.0 * MN : 0.0) + (a.out ? es * MN : 0.0); break;
         case NMM_EPI_RESIDUAL: b += 4.0 * MN + (a.out ? es * MN : 4.0 * MN); break;
         case NMM_EPI_GEGLU: b += es * MN / 2; break;
+        case NMM_EPI_QKV_ATTN: b += es * (double)a.M * a.K; break;      // only ctx is written
+
         default: b += 2.0 * es * MN; break;      // OUTPUT: read x, write y
     }
     return b;

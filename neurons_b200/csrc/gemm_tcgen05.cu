@@ -30,6 +30,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "attention_core.cuh"
 #include "epilogue.cuh"
 #include "ptx.cuh"
 
@@ -65,6 +66,15 @@ struct GnParams {
     float eps;
     int C, F, P;
 };
+// QKV + attention (EPI == NMM_EPI_QKV_ATTN): geometry of the fused epilogue
+struct AttnParams {
+    bf16 *ctx;               // [M, C] attention output
+    int C, F, P, dh;
+    int ppt;                 // positions per tile = 128 / F
+    int tiles_per_img;       // P / ppt
+    float scale_log2e;       // d_h^-1/2 * log2(e)
+};
+constexpr int TC_ATTN_PITCH = 3 * NMM_ATTN_TILE_CH + 8;   // elements per row of the shared-memory q|k|v tile (496 bytes)
 constexpr int TC_GN_WARPS = 4;                            // GNA: warps 12-15 normalise the A tile in shared memory (one 128-byte row each)
 constexpr int TC_A_HALF = TC_A_BYTES / 2;                 // GNA: the A stage is two boxes of 64 channels x 64 positions
 
@@ -103,7 +113,7 @@ __global__ void __launch_bounds__(GNA ? TC_THREADS + 32 * TC_GN_WARPS : TC_THREA
 linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
                  const __grid_constant__ CUtensorMap tm_h,      // fp32 [M,N], box 32 x 32, 128-byte swizzle (residual load / h store)
                  const __grid_constant__ CUtensorMap tm_o,      // bf16 [M,N or N/2], box 32 x 32, 64-byte swizzle (`out` store)
-                 TcParams p, EpiParams e, GnParams gn) {
+                 TcParams p, EpiParams e, GnParams gn, AttnParams at) {
     // CG == 1: one CTA per 128 x block_n tile (tcgen05.mma.cta_group::1).
     // CG == 2: a CTA pair (cluster of 2 along M) computes a 256 x block_n tile with ONE tcgen05.mma.cta_group::2 stream issued
     //          by the even CTA: each CTA stages its own 128 rows of A and HALF of the W tile (block_n/2 rows); the tensor core
@@ -189,6 +199,13 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
                     if (p.debug & 2) {                                  // timing experiment: MMA on whatever is in shared memory
                         if (leader) ptx::mbar_arrive(full_bar(stage));
+                    } else if (EPI == NMM_EPI_QKV_ATTN) {
+                        // A rows = (position, frame) pairs of one image: box (64 channels, F frames, 128/F positions) of the tokens
+                        // viewed as (c, b*F + f, p) -> shared-memory row pl * F + f, the attention tile order
+                        ptx::mbar_expect_tx(full_bar(stage), stage_bytes);
+                        const int img = (int)(m_blk / at.tiles_per_img);
+                        ptx::tma_load_3d(&tm_a, full_bar(stage), sa, kb * TC_BK, img * at.F, (int)(m_blk - (int64_t)img * at.tiles_per_img) * at.ppt);
+                        ptx::tma_load_2d(&tm_w, full_bar(stage), sa + TC_A_BYTES, kb * TC_BK, n_blk * p.block_n);
                     } else if (GNA) {
                         // A = x[b, kb*64 .. +64 channels, f, 64 positions] for each half of the 128-token tile (M-major boxes)
                         ptx::mbar_expect_tx(full_bar(stage), stage_bytes);
@@ -360,6 +377,98 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             };
             if (p.debug & 1) {
                 // timing experiment: drain nothing
+            } else if constexpr (EPI == NMM_EPI_QKV_ATTN) {
+                // ---- QKV + attention: the 128 x 240 accumulator tile is q | k | v (80 channels each) of 128/F positions x F frames.
+                // 1. every warp dumps its 32 rows x half of the columns as bf16 into the shared q|k|v tile (row = TMEM lane =
+                //    pl * F + f: consecutive lanes -> consecutive 496-byte rows, conflict-free) and releases the accumulator;
+                // 2. one warp per (position, head): softmax(q k^T / sqrt d) v on mma.sync, result into the q slot (attention_core.cuh);
+                // 3. the q slots (128 rows x 160 bytes) go to ctx with 16-byte stores.
+                const uint32_t xb = epi_base;                           // the epilogue buffers hold the tile (63.5 KB of 64 KB)
+                wait_acc();
+                {
+                    const uint32_t rowaddr = xb + (uint32_t)(q * 32 + lane) * (TC_ATTN_PITCH * 2);
+                    const int cbeg = half ? 128 : 0, cend = half ? 240 : 128;
+                    for (int c0 = cbeg; c0 < cend; c0 += 32) {
+                        if (c0 + 32 <= cend) {
+                            uint32_t r[32];
+                            ptx::tmem_ld32(t_row + (uint32_t)c0, r);
+                            ptx::tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 4; j++)
+                                sts128(rowaddr + (uint32_t)((c0 + 8 * j) * 2),
+                                       pack_bf16x2(__uint_as_float(r[8 * j]), __uint_as_float(r[8 * j + 1])), pack_bf16x2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3])),
+                                       pack_bf16x2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5])), pack_bf16x2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7])));
+                        } else {
+                            uint32_t r[16];
+                            ptx::tmem_ld16(t_row + (uint32_t)c0, r);
+                            ptx::tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 2; j++)
+                                sts128(rowaddr + (uint32_t)((c0 + 8 * j) * 2),
+                                       pack_bf16x2(__uint_as_float(r[8 * j]), __uint_as_float(r[8 * j + 1])), pack_bf16x2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3])),
+                                       pack_bf16x2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5])), pack_bf16x2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7])));
+                        }
+                    }
+                }
+                if (warp == 4 && lane == 0) TRACE(tile_no, 8);
+                // the accumulator is drained: hand it back to the MMA warp before the attention math
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");      // the whole q|k|v tile is in shared memory
+                if (warp == 4 && lane == 0) TRACE(tile_no, 9);
+                {
+                    // problems (pl, head) of this warp, two at a time (interleaved instruction streams); each finished problem's
+                    // F x d_h block of context is copied to global memory by the same warp: no block-wide barrier in between
+                    const int img = (int)(m_blk / at.tiles_per_img);
+                    const int p0 = (int)(m_blk - (int64_t)img * at.tiles_per_img) * at.ppt;
+                    bf16 *dst0 = at.ctx + ((int64_t)img * at.F * at.P + p0) * at.C + n_blk * NMM_ATTN_TILE_CH;
+                    const int hb = NMM_ATTN_TILE_CH / at.dh;              // heads per tile: 2 (d_h 40) or 1 (d_h 80)
+                    const int nprob = at.ppt * hb;
+                    auto qaddr = [&](int prob) {
+                        const int pl = prob / hb, hd = prob - pl * hb;
+                        return xb + (uint32_t)(pl * at.F) * (TC_ATTN_PITCH * 2) + (uint32_t)(hd * at.dh * 2);
+                    };
+                    auto copy_out = [&](int prob) {                       // F rows x (d_h / 8) 16-byte chunks
+                        const int pl = prob / hb, hd = prob - pl * hb;
+                        const int cpr = at.dh / 8;
+                        for (int i = lane; i < at.F * cpr; i += 32) {
+                            const int f = i / cpr, v = i - f * cpr;
+                            const float4 val = lds128(xb + (uint32_t)(pl * at.F + f) * (TC_ATTN_PITCH * 2) + (uint32_t)((hd * at.dh + v * 8) * 2));
+                            *reinterpret_cast<float4 *>(dst0 + ((int64_t)f * at.P + pl) * at.C + hd * at.dh + v * 8) = val;
+                        }
+                    };
+                    auto run = [&](auto FF, auto DD) {
+                        constexpr int F_ = decltype(FF)::value, D_ = decltype(DD)::value;
+                        int prob = ew;
+                        for (; prob + TC_EPI_WARPS < nprob; prob += 2 * TC_EPI_WARPS) {
+                            const uint32_t qb2[2] = {qaddr(prob), qaddr(prob + TC_EPI_WARPS)};
+                            attention_problems<F_, D_, NMM_ATTN_TILE_CH, 2>(qb2, lane, at.scale_log2e);
+                            __syncwarp();
+                            if (!(p.debug & 64)) { copy_out(prob); copy_out(prob + TC_EPI_WARPS); }
+                        }
+                        if (prob < nprob) {
+                            const uint32_t qb1[1] = {qaddr(prob)};
+                            attention_problems<F_, D_, NMM_ATTN_TILE_CH, 1>(qb1, lane, at.scale_log2e);
+                            __syncwarp();
+                            if (!(p.debug & 64)) copy_out(prob);
+                        }
+                    };
+                    if (p.debug & 32) {
+                        // timing experiment: no attention math
+                    } else if (at.F == 8) {
+                        if (at.dh == 40) run(std::integral_constant<int, 8>{}, std::integral_constant<int, 40>{});
+                        else run(std::integral_constant<int, 8>{}, std::integral_constant<int, 80>{});
+                    } else {
+                        if (at.dh == 40) run(std::integral_constant<int, 16>{}, std::integral_constant<int, 40>{});
+                        else run(std::integral_constant<int, 16>{}, std::integral_constant<int, 80>{});
+                    }
+                }
+                if (warp == 4 && lane == 0) TRACE(tile_no, 10);
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");      // every warp is done with the tile: free for the next dump
+                if (warp == 4 && lane == 0) TRACE(tile_no, 12);
+                if (++as == 2) { as = 0; aphase ^= 1u; }
+                continue;
             } else if constexpr (EPI == NMM_EPI_OUTPUT) {
                 // y[b,c,f,p] = acc + bias[c] + x[b,c,f,p]: the output is channel-major, rows (p) are the contiguous axis
                 if (e.nchw_vec) {
@@ -645,6 +754,28 @@ static int make_tmap_x(CUtensorMap *tm, const void *x, int B, int C, int F, int 
     return NMM_OK;
 }
 
+// tokens [B*F*P, C] viewed as (c, b*F + f, p) -- note the dimension ORDER: frames before positions, so that a box of
+// (64 channels, F frames, 128/F positions) lands in shared memory as rows pl * F + f, the attention tile order.
+static int make_tmap_tokens_pf(CUtensorMap *tm, const void *tok, int B, int C, int F, int P, int ppt) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return fail(NMM_ERR_DEVICE, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)B * F, (cuuint64_t)P};
+    cuuint64_t strides[2] = {(cuuint64_t)P * C * 2, (cuuint64_t)C * 2};
+    cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)F, (cuuint32_t)ppt};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(tok), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(NMM_ERR_CUDA, "cuTensorMapEncodeTiled (tokens, 3-D) failed with CUresult %d", (int)r);
+    return NMM_OK;
+}
+
+// Can the temporal attention run inside the QKV projection's epilogue?  See LinearArgs (NMM_EPI_QKV_ATTN).
+bool linear_tc_attn_fusable(int C, int heads, int F, int P) {
+    if (heads <= 0 || C % heads != 0 || C % NMM_ATTN_TILE_CH != 0) return false;
+    const int dh = C / heads;
+    return (dh == 40 || dh == 80) && (F == 8 || F == 16) && P % (TC_BM / F) == 0 && !getenv("NMM_NO_ATTN_FUSE");
+}
+
 // Can proj_in take its A operand straight from x (GroupNorm applied in shared memory)?  See LinearArgs::gn_x.
 bool linear_tc_gn_fusable(int64_t M, int P, const void *x, int64_t sb, int64_t sc, int64_t sf) {
     return P % 64 == 0 && M % TC_BM == 0 && aligned(x, 16) && sb % 8 == 0 && sc % 8 == 0 && sf % 8 == 0 && !getenv("NMM_NO_GN_FUSE");
@@ -720,7 +851,8 @@ void plan_linear_tc(int64_t M, int N, int K, int epilogue, int *block_n, int *cl
 
 template <int EPI, int CG, bool LNF, bool GNA = false>
 static int launch_tc_t(const CUtensorMap &ta, const CUtensorMap &tw, const CUtensorMap &th, const CUtensorMap &to, const TcParams &p,
-                       const EpiParams &e, size_t smem, int grid, cudaStream_t st, double flops, double bytes, const GnParams &gn = GnParams()) {
+                       const EpiParams &e, size_t smem, int grid, cudaStream_t st, double flops, double bytes, const GnParams &gn = GnParams(),
+                       const AttnParams &at = AttnParams()) {
     auto kern = linear_tc_kernel<EPI, CG, LNF, GNA>;
     static DeviceOnce once;           // per template instantiation and device
     if (once.first()) NMM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX));
@@ -741,7 +873,7 @@ static int launch_tc_t(const CUtensorMap &ta, const CUtensorMap &tw, const CUten
     cfg.numAttrs = CG > 1 ? 2 : 1;
     {
         ProfScope prof(K_LINEAR_TC, st, flops, bytes);
-        cudaError_t le = cudaLaunchKernelEx(&cfg, kern, ta, tw, th, to, p, e, gn);
+        cudaError_t le = cudaLaunchKernelEx(&cfg, kern, ta, tw, th, to, p, e, gn, at);
         if (le != cudaSuccess) return fail(NMM_ERR_CUDA, "cudaLaunchKernelEx(linear_tc_kernel) failed: %s", cudaGetErrorString(le));
     }
     NMM_LAUNCHED("linear_tc_kernel");
@@ -768,12 +900,17 @@ int launch_linear_tc(const LinearArgs &a, cudaStream_t st) {
     if (!g_trace_dev) { cudaMalloc(&g_trace_dev, TRACE_TILES * TRACE_SLOTS * 8); cudaMemset(g_trace_dev, 0, TRACE_TILES * TRACE_SLOTS * 8); }
     p.trace = g_trace_dev;
 #endif
+    const bool attn = a.epilogue == NMM_EPI_QKV_ATTN;
+    if (attn && (a.out == nullptr || a.A == nullptr || a.N != 3 * a.K || a.attn_B <= 0 || !linear_tc_attn_fusable(a.K, a.attn_heads, a.F, a.P) ||
+                 (int64_t)a.attn_B * a.F * a.P != a.M || a.ln_part_in != nullptr || a.ln_part_out != nullptr || a.gn_x != nullptr))
+        return fail(NMM_ERR_UNSUPPORTED, "fused QKV + attention: needs d_h in {40, 80}, F in {8, 16}, P %% (128 / F) == 0");
     const bool gna = a.gn_x != nullptr;
     if (gna && (a.epilogue != NMM_EPI_STORE || a.ln_part_in != nullptr || a.ln_part_out != nullptr || a.gn_B <= 0 ||
                 !linear_tc_gn_fusable(a.M, a.P, a.gn_x, a.xsb, a.xsc, a.xsf) || (int64_t)a.gn_B * a.F * a.P != a.M))
         return fail(NMM_ERR_UNSUPPORTED, "GroupNorm-fused A operand: needs the STORE epilogue, P %% 64 == 0, M %% 128 == 0 and 16-byte aligned x");
     const int gran = a.epilogue == NMM_EPI_GEGLU ? 64 : 32;
-    const TilePlan plan = choose_tiles(p.m_tiles, a.N, a.K, sms, gran, gna ? 1 : (force_cluster == 1 || force_cluster == 2) ? force_cluster : 0,
+    const TilePlan plan = attn ? TilePlan{3 * NMM_ATTN_TILE_CH, 1} :
+                          choose_tiles(p.m_tiles, a.N, a.K, sms, gran, gna ? 1 : (force_cluster == 1 || force_cluster == 2) ? force_cluster : 0,
                                        (force_bn >= gran && force_bn <= 256 && force_bn % gran == 0 && a.N % force_bn == 0) ? force_bn : 0);
     if (plan.block_n == 0) return fail(NMM_ERR_UNSUPPORTED, "tcgen05 GEMM: no N tile for N=%d", a.N);
     p.block_n = plan.block_n;
@@ -794,7 +931,8 @@ int launch_linear_tc(const LinearArgs &a, cudaStream_t st) {
     p.tmem_cols = cols;
     const size_t smem = fixed + (size_t)stages * stage_bytes;
     CUtensorMap ta, tw, th, to;
-    int rc = gna ? make_tmap_x(&ta, a.gn_x, a.gn_B, a.K, a.F, a.P, a.xsb, a.xsc, a.xsf)
+    int rc = attn ? make_tmap_tokens_pf(&ta, a.A, a.attn_B, a.K, a.F, a.P, TC_BM / a.F)
+             : gna ? make_tmap_x(&ta, a.gn_x, a.gn_B, a.K, a.F, a.P, a.xsb, a.xsc, a.xsf)
                  : make_tmap(&ta, a.A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.M, a.K, a.K, TC_BM, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != NMM_OK) return rc;
     // each CTA of a pair fetches its slice of the W tile
@@ -806,7 +944,7 @@ int launch_linear_tc(const LinearArgs &a, cudaStream_t st) {
         rc = make_tmap(&th, a.h, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.M, a.N, a.N, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc != NMM_OK) return rc;
     }
-    if (a.out != nullptr && a.epilogue != NMM_EPI_OUTPUT) {
+    if (a.out != nullptr && a.epilogue != NMM_EPI_OUTPUT && !attn) {
         const int64_t ncols = a.epilogue == NMM_EPI_GEGLU ? a.N / 2 : a.N;
         rc = make_tmap(&to, a.out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.M, ncols, ncols, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
         if (rc != NMM_OK) return rc;
@@ -817,6 +955,13 @@ int launch_linear_tc(const LinearArgs &a, cudaStream_t st) {
     EpiParams e = epi_params_of(a);
     const double fl = linear_flops(a), by = linear_bytes(a, 2);
     const bool lnf = a.ln_part_in != nullptr || a.ln_part_out != nullptr;
+    if (attn) {
+        AttnParams at;
+        at.ctx = (bf16 *)a.out; at.C = a.K; at.F = a.F; at.P = a.P; at.dh = a.K / a.attn_heads; at.ppt = TC_BM / a.F; at.tiles_per_img = a.P / at.ppt;
+        at.scale_log2e = (1.0f / sqrtf((float)at.dh)) * 1.4426950408889634f;
+        // algorithmic work of the pair of kernels it replaces: the projection's FLOPs + the attention's
+        return launch_tc_t<NMM_EPI_QKV_ATTN, 1, false, false>(ta, tw, th, to, p, e, smem, grid, st, fl + 4.0 * a.M * a.F * a.K, by, GnParams(), at);
+    }
     if (gna) {
         GnParams gn;
         gn.partial = a.gn_partial; gn.gamma = a.gn_w; gn.beta = a.gn_b; gn.splits = a.gn_splits; gn.count = a.gn_count; gn.eps = a.gn_eps;

@@ -53,6 +53,11 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap *m, uint32_t bar, 
 // Address of "the same object in the even CTA of my pair": shared::cluster addresses carry the CTA rank in bit 24.
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;
 // 2-CTA form: `bar` may name the mbarrier of either CTA of the pair (both CTAs signal the even CTA's barrier).
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap *m, uint32_t bar, uint32_t dst_smem, int32_t c0, int32_t c1, int32_t c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst_smem), "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_load_4d(const CUtensorMap *m, uint32_t bar, uint32_t dst_smem, int32_t c0, int32_t c1, int32_t c2, int32_t c3) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                  ::"r"(dst_smem), "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)

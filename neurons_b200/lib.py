@@ -81,6 +81,7 @@ SIGNATURES = {
     "nmm_cfg_ddim_step": (C.c_int, [C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_double, C.c_double, C.c_void_p]),
     "nmm_layernorm_pe": (C.c_int, [_SP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nmm_temporal_attention": (C.c_int, [_SP, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nmm_qkv_attention": (C.c_int, [_SP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nmm_linear": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                              C.c_void_p, C.c_void_p, _SP, C.c_void_p, C.c_void_p, C.c_void_p]),
 }

@@ -294,6 +294,20 @@ def inflated_groupnorm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor
     return y
 
 
+def qkv_attention(cfg: ModuleConfig, bfhw, tokens: torch.Tensor, wqkv: torch.Tensor) -> torch.Tensor:
+    """QKV projection + temporal attention in one tensor-core kernel (bf16): ctx [N, C].  wqkv: [3C, C] = cat(to_q, to_k, to_v)."""
+    B, F, H, W = bfhw
+    shape = _shape_for_tokens(cfg, B, F, H, W, tokens.dtype)
+    tokens = tokens.contiguous()
+    wqkv = wqkv.to(tokens.dtype).contiguous()
+    scratch = torch.empty_like(wqkv)
+    ctx = torch.empty_like(tokens)
+    with torch.cuda.device(tokens.device):
+        _lib.check(_lib.load().nmm_qkv_attention(C.byref(shape), tokens.data_ptr(), wqkv.data_ptr(), scratch.data_ptr(), ctx.data_ptr(),
+                                                 _stream_ptr(tokens.device)))
+    return ctx
+
+
 def cfg_ddim_step(latents: torch.Tensor, eps_uncond: torch.Tensor, eps_cond: Optional[torch.Tensor], guidance: float, alpha_t: float,
                   alpha_prev: float) -> torch.Tensor:
     """In-place fused classifier-free guidance + DDIM update on CUDA tensors (pipeline_neuroclips.py:478-483); returns `latents`."""

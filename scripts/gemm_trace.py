@@ -18,9 +18,15 @@ def main():
     act4 = torch.randn(M, 4 * C, device=dev, dtype=bf, generator=g)
     h = torch.randn(M, C, device=dev, generator=g)
     bias = torch.randn(8 * C, device=dev, generator=g)
-    W = {"qkv": (3 * C, C), "geglu": (8 * C, C), "to_out": (C, C), "ff_out": (C, 4 * C)}[which]
+    if which == "qkvattn":
+        side = int((M // 16) ** 0.5)
+        cfg = ops.ModuleConfig(C)
+        wq = torch.randn(3 * C, C, device=dev, dtype=bf, generator=g) / C ** 0.5
+        fn = lambda: ops.qkv_attention(cfg, (2, 8, side, side), act, wq)
+    W = {"qkvattn": (3 * C, C), "qkv": (3 * C, C), "geglu": (8 * C, C), "to_out": (C, C), "ff_out": (C, 4 * C)}[which]
     w = torch.randn(*W, device=dev, dtype=bf, generator=g) / W[1] ** 0.5
-    fn = {"qkv": lambda: ops.linear(act, w, None, nlib.EPI_STORE),
+    fn0 = fn if which == "qkvattn" else None
+    fn = {"qkvattn": fn0, "qkv": lambda: ops.linear(act, w, None, nlib.EPI_STORE),
           "geglu": lambda: ops.linear(act, w, bias, nlib.EPI_GEGLU),
           "to_out": lambda: ops.linear(act, w, bias[:C], nlib.EPI_RESIDUAL, h=h, want_out=False),
           "ff_out": lambda: ops.linear(act4, w, bias[:C], nlib.EPI_RESIDUAL, h=h, want_out=True)}[which]

@@ -79,6 +79,7 @@ def main():
             ("gn_stats+proj_in fused", lambda: ops.groupnorm_linear(cfg, x, gw, gb, w_cc, bias), 2.0 * M * C * C, M * C * (2 * es + 4)),
             ("layernorm_pe", lambda: ops.layernorm_pe(cfg, (B, F, side, side), h, gw, gb, pe, bf), 0.0, M * C * (4 + es)),
             ("attention", lambda: ops.temporal_attention(cfg, (B, F, side, side), qkv), 4.0 * M * F * C, 4 * M * C * es),
+            ("qkv+attention fused", lambda: ops.qkv_attention(cfg, (B, F, side, side), act, w_qkv), 2.0 * M * C * 3 * C + 4.0 * M * F * C, M * C * es * 2),
             ("proj_in  C->C  store h", lambda: ops.linear(act, w_cc, bias, nlib.EPI_STORE, h=h, want_out=False), 2.0 * M * C * C, M * C * (es + 4)),
             ("qkv      C->3C store", lambda: ops.linear(act, w_qkv, None, nlib.EPI_STORE), 2.0 * M * C * 3 * C, M * C * es * 4),
             ("to_out   C->C  residual", lambda: ops.linear(act, w_cc, bias, nlib.EPI_RESIDUAL, h=h, want_out=False), 2.0 * M * C * C, M * C * (es + 8)),

@@ -350,8 +350,9 @@ def test_launch_counter_and_graph_capture():
         n0 = nb.launch_count()
         m(x, None, None)
         per_call = nb.launch_count() - n0
-        # gn_stats, GroupNorm-fused proj_in (16x16 positions: x is TMA-loaded by the GEMM), 2x(ln qkv attn out), ln geglu ff_out, proj_out
-        assert per_call == 1 + 1 + 2 * 4 + 3 + 1
+        # gn_stats, GroupNorm-fused proj_in (16x16 positions: x is TMA-loaded by the GEMM), 2x(ln, qkv with the attention in its epilogue,
+        # out), ln geglu ff_out, proj_out
+        assert per_call == 1 + 1 + 2 * 3 + 3 + 1
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         s = torch.cuda.Stream()
@@ -389,3 +390,24 @@ def test_inflated_groupnorm_silu(C, F, H, W, B, layout, dtype, silu):
     assert y.is_contiguous() and y.shape == x.shape
     tol = 2e-5 if dtype == torch.float32 else 2 ** -8 * 1.01 * ref.abs().max().item()
     assert _maxabs(y, ref) <= tol
+
+
+@pytest.mark.parametrize("C,F,H,W,B", [(320, 8, 8, 8, 2), (320, 16, 4, 4, 1), (640, 8, 4, 4, 2), (640, 16, 8, 8, 1), (320, 8, 4, 4, 1)])
+def test_qkv_attention_fused_matches_two_kernel_path(C, F, H, W, B):
+    """QKV projection with the temporal attention in its epilogue (q | k | v stay in shared memory) against
+    nmm_linear + nmm_temporal_attention (same bf16 rounding of q, k, v) and against the fp64 formula."""
+    cfg = mo.MotionConfig(C, max_len=32)
+    nh, dh, P = cfg.heads, cfg.head_dim, H * W
+    N = B * F * P
+    g = torch.Generator().manual_seed(C + F)
+    tok = helpers.round_bf16(torch.randn(N, C, generator=g))
+    wqkv = helpers.round_bf16(torch.randn(3 * C, C, generator=g) / C ** 0.5)
+    tokd, wd = tok.to(DEV, torch.bfloat16), wqkv.to(DEV, torch.bfloat16)
+    fused = ops.qkv_attention(_cfg(cfg), (B, F, H, W), tokd, wd)
+    qkv = ops.linear(tokd, wd, None, nlib.EPI_STORE)
+    two = ops.temporal_attention(_cfg(cfg), (B, F, H, W), qkv)
+    assert _maxabs(fused, two.float().cpu().double()) <= 2 ** -7 * two.float().abs().max().item()      # <= 1 bf16 ulp (P is fp32 vs hi+lo)
+    z = (tok.double() @ wqkv.double().T).reshape(B, F, P, 3, nh, dh)
+    s = torch.einsum("bfphd,bgphd->bphfg", z[:, :, :, 0], z[:, :, :, 1]) * dh ** -0.5
+    ref = torch.einsum("bphfg,bgphd->bfphd", s.softmax(-1), z[:, :, :, 2]).reshape(N, C)
+    assert _maxabs(fused, ref) <= 2e-2 * max(1.0, ref.abs().max().item())
