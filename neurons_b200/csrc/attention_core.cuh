@@ -163,7 +163,28 @@ __device__ __forceinline__ void attention_problems(const uint32_t (&qb)[NP], int
     __syncwarp();                                   // all of this warp's reads of the q rows are done: reuse them for O
     // ---- O = P V: one ldmatrix.x4.trans feeds 32 (F == 8) or 16 (F == 16) output columns ---------------------------------------------
     const uint32_t o_off = (uint32_t)crow * RS + (uint32_t)(ccol * 2);
-    if constexpr (F == 8) {
+    if constexpr (F == 8 && NP == 2) {
+        // Two 8-frame problems share every m16n8k16: A = blockdiag(P_0, P_1) (rows 0-7 / keys 0-7 = problem 0, rows 8-15 / keys 8-15 =
+        // problem 1), B = [V_0; V_1] -> D rows 0-7 = P_0 V_0, rows 8-15 = P_1 V_1.  Half the tensor-core instructions of two separate
+        // m16n8k8 streams -- legacy mma.sync shares the tensor pipe with the tcgen05 mainloop, so the count is what matters here.
+        const uint32_t vsel = qb[(lmat & 1)] + VOFF + (uint32_t)lrow * RS;     // ldmatrix matrices 0,2 <- problem 0's V rows; 1,3 <- problem 1's
+#pragma unroll
+        for (int n0 = 0; n0 < DH; n0 += 16) {
+            uint32_t bv[4] = {0u, 0u, 0u, 0u};
+            if (n0 + 16 <= DH) ldsm_x4_t(vsel + (uint32_t)((n0 + 8 * (lmat >> 1)) * 2), bv[0], bv[1], bv[2], bv[3]);
+            else ldsm_x2_t(vsel + (uint32_t)(n0 * 2), bv[0], bv[1]);                   // last 8 columns (lanes 0-15 address)
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                if (n0 + 8 * q < DH) {
+                    float o[4] = {0.f, 0.f, 0.f, 0.f};
+                    mma_k16(o, ph[0][0], 0u, 0u, ph[1][0], bv[2 * q], bv[2 * q + 1]);
+                    mma_k16(o, pl_[0][0], 0u, 0u, pl_[1][0], bv[2 * q], bv[2 * q + 1]);
+                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(qb[0] + o_off + (n0 + 8 * q) * 2), "r"(pack_bf16x2(o[0], o[1])) : "memory");
+                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(qb[1] + o_off + (n0 + 8 * q) * 2), "r"(pack_bf16x2(o[2], o[3])) : "memory");
+                }
+            }
+        }
+    } else if constexpr (F == 8) {
         const uint32_t v_off = VOFF + (uint32_t)lrow * RS + (uint32_t)(16 * lmat);
 #pragma unroll
         for (int n0 = 0; n0 + 32 <= DH; n0 += 32) {

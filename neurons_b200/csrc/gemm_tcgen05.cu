@@ -429,23 +429,31 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         const int pl = prob / hb, hd = prob - pl * hb;
                         return xb + (uint32_t)(pl * at.F) * (TC_ATTN_PITCH * 2) + (uint32_t)(hd * at.dh * 2);
                     };
-                    auto copy_out = [&](int prob) {                       // F rows x (d_h / 8) 16-byte chunks
-                        const int pl = prob / hb, hd = prob - pl * hb;
-                        const int cpr = at.dh / 8;
-                        for (int i = lane; i < at.F * cpr; i += 32) {
-                            const int f = i / cpr, v = i - f * cpr;
-                            const float4 val = lds128(xb + (uint32_t)(pl * at.F + f) * (TC_ATTN_PITCH * 2) + (uint32_t)((hd * at.dh + v * 8) * 2));
-                            *reinterpret_cast<float4 *>(dst0 + ((int64_t)f * at.P + pl) * at.C + hd * at.dh + v * 8) = val;
-                        }
-                    };
                     auto run = [&](auto FF, auto DD) {
                         constexpr int F_ = decltype(FF)::value, D_ = decltype(DD)::value;
+                        auto copy_out = [&](int prob) {                   // F rows x (d_h / 8) 16-byte chunks, all bounds compile-time
+                            constexpr int HB_ = NMM_ATTN_TILE_CH / D_, CPR = D_ / 8;
+                            const int pl = prob / HB_, hd = prob - pl * HB_;
+                            const uint32_t src = xb + (uint32_t)(pl * F_) * (TC_ATTN_PITCH * 2) + (uint32_t)(hd * D_ * 2);
+                            bf16 *dst = dst0 + (int64_t)pl * at.C + hd * D_;
+#pragma unroll
+                            for (int i0 = 0; i0 < F_ * CPR; i0 += 32) {
+                                const int i = i0 + lane;
+                                if (i < F_ * CPR) {
+                                    const int f = i / CPR, v = i - f * CPR;
+                                    const float4 val = lds128(src + (uint32_t)f * (TC_ATTN_PITCH * 2) + (uint32_t)(v * 16));
+                                    *reinterpret_cast<float4 *>(dst + (int64_t)f * at.P * at.C + v * 8) = val;
+                                }
+                            }
+                        };
                         int prob = ew;
                         for (; prob + TC_EPI_WARPS < nprob; prob += 2 * TC_EPI_WARPS) {
                             const uint32_t qb2[2] = {qaddr(prob), qaddr(prob + TC_EPI_WARPS)};
                             attention_problems<F_, D_, NMM_ATTN_TILE_CH, 2>(qb2, lane, at.scale_log2e);
                             __syncwarp();
+                            if (warp == 4 && lane == 0) TRACE(tile_no, prob == ew ? 11 : 14);
                             if (!(p.debug & 64)) { copy_out(prob); copy_out(prob + TC_EPI_WARPS); }
+                            if (warp == 4 && lane == 0 && prob == ew) TRACE(tile_no, 13);
                         }
                         if (prob < nprob) {
                             const uint32_t qb1[1] = {qaddr(prob)};

@@ -44,7 +44,7 @@ def main():
     names = ["mma:start", "mma:accfree", "mma:1stfull", "mma:issued", "tma:first", "tma:last", "epi:wait", "epi:ready", "c0:ldtm", "c0:sts", "c0:lds", "c0:stg",
              "epi:rel", "epi8:ready", "epi8:rel"]
     print(which, C, "cycles relative to first event;", " ".join(f"{n:>11s}" for n in names))
-    for i, r in enumerate(rows[:20]):
+    for i, r in enumerate(rows[:14]):
         print(f"tile {i:2d}: " + " ".join(f"{(v - t0) if v else -1:11d}" for v in r[:15]))
 
 main()
