@@ -49,8 +49,18 @@ __device__ __forceinline__ void split_bf16x2(float x, float y, uint32_t &hi, uin
 // ldmatrix -> mma -> shuffle-softmax -> mma of a single problem is latency-bound, two in flight roughly halve the time per problem
 // when few warps share the tile (the fused QKV epilogue has 8).  qb[u] = shared-memory address of problem u's q rows (row 0, its head's
 // first column); the result overwrites those q columns.
-template <int F, int DH, int W, int NP>
-__device__ __forceinline__ void attention_problems(const uint32_t (&qb)[NP], int lane, float scale_log2e) {
+// `store(u, row, col, v)`: two adjacent bf16 context values (packed in v) of problem u, frame `row`, head-dim columns col, col + 1.
+// The stand-alone kernel puts them into the problem's q slot (SmemQSlotStore); the fused QKV epilogue writes them straight to global.
+template <int W>
+struct SmemQSlotStore {
+    const uint32_t *qb;
+    __device__ __forceinline__ void operator()(int u, int row, int col, uint32_t v) const {
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(qb[u] + (uint32_t)row * ((3 * W + 8) * 2) + (uint32_t)(col * 2)), "r"(v) : "memory");
+    }
+};
+
+template <int F, int DH, int W, int NP, typename Store>
+__device__ __forceinline__ void attention_problems(const uint32_t (&qb)[NP], int lane, float scale_log2e, const Store &store) {
     constexpr int NT = F / 8;
     constexpr uint32_t RS = (3 * W + 8) * 2;    // row stride in bytes
     constexpr uint32_t KOFF = W * 2, VOFF = 2 * W * 2;
@@ -162,7 +172,6 @@ __device__ __forceinline__ void attention_problems(const uint32_t (&qb)[NP], int
     }
     __syncwarp();                                   // all of this warp's reads of the q rows are done: reuse them for O
     // ---- O = P V: one ldmatrix.x4.trans feeds 32 (F == 8) or 16 (F == 16) output columns ---------------------------------------------
-    const uint32_t o_off = (uint32_t)crow * RS + (uint32_t)(ccol * 2);
     if constexpr (F == 8 && NP == 2) {
         // Two 8-frame problems share every m16n8k16: A = blockdiag(P_0, P_1) (rows 0-7 / keys 0-7 = problem 0, rows 8-15 / keys 8-15 =
         // problem 1), B = [V_0; V_1] -> D rows 0-7 = P_0 V_0, rows 8-15 = P_1 V_1.  Half the tensor-core instructions of two separate
@@ -179,8 +188,8 @@ __device__ __forceinline__ void attention_problems(const uint32_t (&qb)[NP], int
                     float o[4] = {0.f, 0.f, 0.f, 0.f};
                     mma_k16(o, ph[0][0], 0u, 0u, ph[1][0], bv[2 * q], bv[2 * q + 1]);
                     mma_k16(o, pl_[0][0], 0u, 0u, pl_[1][0], bv[2 * q], bv[2 * q + 1]);
-                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(qb[0] + o_off + (n0 + 8 * q) * 2), "r"(pack_bf16x2(o[0], o[1])) : "memory");
-                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(qb[1] + o_off + (n0 + 8 * q) * 2), "r"(pack_bf16x2(o[2], o[3])) : "memory");
+                    store(0, crow, ccol + (n0 + 8 * q), pack_bf16x2(o[0], o[1]));
+                    store(1, crow, ccol + (n0 + 8 * q), pack_bf16x2(o[2], o[3]));
                 }
             }
         }
@@ -197,7 +206,7 @@ __device__ __forceinline__ void attention_problems(const uint32_t (&qb)[NP], int
                     float o[4] = {0.f, 0.f, 0.f, 0.f};
                     mma_k8(o, ph[u][0], 0u, bv[q]);
                     mma_k8(o, pl_[u][0], 0u, bv[q]);
-                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(qb[u] + o_off + (n0 + 8 * q) * 2), "r"(pack_bf16x2(o[0], o[1])) : "memory");
+                    store(u, crow, ccol + (n0 + 8 * q), pack_bf16x2(o[0], o[1]));
                 }
             }
         }
@@ -211,7 +220,7 @@ __device__ __forceinline__ void attention_problems(const uint32_t (&qb)[NP], int
                 float o[4] = {0.f, 0.f, 0.f, 0.f};
                 mma_k8(o, ph[u][0], 0u, b0);
                 mma_k8(o, pl_[u][0], 0u, b0);
-                asm volatile("st.shared.b32 [%0], %1;" ::"r"(qb[u] + o_off + n0 * 2), "r"(pack_bf16x2(o[0], o[1])) : "memory");
+                store(u, crow, ccol + n0, pack_bf16x2(o[0], o[1]));
             }
         }
     } else {
@@ -228,8 +237,8 @@ __device__ __forceinline__ void attention_problems(const uint32_t (&qb)[NP], int
                     float o[4] = {0.f, 0.f, 0.f, 0.f};
                     mma_k16(o, ph[u][0], ph[u][1], ph[u][2], ph[u][3], bv[2 * q], bv[2 * q + 1]);
                     mma_k16(o, pl_[u][0], pl_[u][1], pl_[u][2], pl_[u][3], bv[2 * q], bv[2 * q + 1]);
-                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(qb[u] + o_off + (n0 + 8 * q) * 2), "r"(pack_bf16x2(o[0], o[1])) : "memory");
-                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(qb[u] + o_off + 8 * RS + (n0 + 8 * q) * 2), "r"(pack_bf16x2(o[2], o[3])) : "memory");
+                    store(u, crow, ccol + (n0 + 8 * q), pack_bf16x2(o[0], o[1]));
+                    store(u, crow + 8, ccol + (n0 + 8 * q), pack_bf16x2(o[2], o[3]));
                 }
             }
         }
@@ -242,8 +251,8 @@ __device__ __forceinline__ void attention_problems(const uint32_t (&qb)[NP], int
                 float o[4] = {0.f, 0.f, 0.f, 0.f};
                 mma_k16(o, ph[u][0], ph[u][1], ph[u][2], ph[u][3], b0, b1);
                 mma_k16(o, pl_[u][0], pl_[u][1], pl_[u][2], pl_[u][3], b0, b1);
-                asm volatile("st.shared.b32 [%0], %1;" ::"r"(qb[u] + o_off + N1 * 2), "r"(pack_bf16x2(o[0], o[1])) : "memory");
-                asm volatile("st.shared.b32 [%0], %1;" ::"r"(qb[u] + o_off + 8 * RS + N1 * 2), "r"(pack_bf16x2(o[2], o[3])) : "memory");
+                store(u, crow, ccol + N1, pack_bf16x2(o[0], o[1]));
+                store(u, crow + 8, ccol + N1, pack_bf16x2(o[2], o[3]));
             }
         }
     }
@@ -257,7 +266,7 @@ __device__ __forceinline__ void attention_tile_mma(uint32_t sm_u32, int npos, in
     for (int prob = warp; prob < npos * HB; prob += nwarps) {
         const int pl = prob / HB, hd = prob - pl * HB;
         const uint32_t qb[1] = {sm_u32 + (uint32_t)(pl * F) * RS + (uint32_t)(hd * DH * 2)};
-        attention_problems<F, DH, W, 1>(qb, lane, scale_log2e);
+        attention_problems<F, DH, W, 1>(qb, lane, scale_log2e, SmemQSlotStore<W>{qb});
     }
 }
 

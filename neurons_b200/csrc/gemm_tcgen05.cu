@@ -74,6 +74,8 @@ struct AttnParams {
     int tiles_per_img;       // P / ppt
     float scale_log2e;       // d_h^-1/2 * log2(e)
 };
+constexpr int TC_ATTN_HELPERS = 8;                       // QKV + attention: warps 12-19 share the attention phase with the epilogue warps
+constexpr int TC_ATTN_WARPS = TC_EPI_WARPS + TC_ATTN_HELPERS;
 constexpr int TC_ATTN_PITCH = 3 * NMM_ATTN_TILE_CH + 8;   // elements per row of the shared-memory q|k|v tile (496 bytes)
 constexpr int TC_GN_WARPS = 4;                            // GNA: warps 12-15 normalise the A tile in shared memory (one 128-byte row each)
 constexpr int TC_A_HALF = TC_A_BYTES / 2;                 // GNA: the A stage is two boxes of 64 channels x 64 positions
@@ -105,11 +107,66 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
     return v;
 }
 
+// Attention phase of the fused QKV kernel: the (position, head) problems of the shared q|k|v tile at `xb`, shared by `nw` warps (the
+// 8 epilogue warps + 8 helper warps: two warps per scheduler leave the mma.sync / ldmatrix / shuffle chains latency-bound).  Two
+// problems at a time per warp when the tile has enough of them; each finished problem's F x d_h block of context is copied to
+// global memory by the same warp (16-byte stores; 4-byte stores straight from the accumulator fragments measured 15 % slower), so no
+// block-wide barrier is needed between the math and the copy.
+__device__ __forceinline__ void fused_attention_phase(const AttnParams &at, uint32_t xb, int64_t m_blk, int n_blk, int widx, int nw, int lane) {
+    const int img = (int)(m_blk / at.tiles_per_img);
+    const int p0 = (int)(m_blk - (int64_t)img * at.tiles_per_img) * at.ppt;
+    bf16 *dst0 = at.ctx + ((int64_t)img * at.F * at.P + p0) * at.C + n_blk * NMM_ATTN_TILE_CH;
+    auto run = [&](auto FF, auto DD) {
+        constexpr int F_ = decltype(FF)::value, D_ = decltype(DD)::value;
+        constexpr int HB_ = NMM_ATTN_TILE_CH / D_;                        // heads per tile: 2 (d_h 40) or 1 (d_h 80)
+        const int nprob = at.ppt * HB_;
+        auto qaddr = [&](int prob) {
+            const int pl = prob / HB_, hd = prob - pl * HB_;
+            return xb + (uint32_t)(pl * F_) * (TC_ATTN_PITCH * 2) + (uint32_t)(hd * D_ * 2);
+        };
+        auto copy_out = [&](int prob) {                                   // F rows x (d_h / 8) 16-byte chunks, all bounds compile-time
+            constexpr int CPR = D_ / 8;
+            const int pl = prob / HB_, hd = prob - pl * HB_;
+            const uint32_t src = xb + (uint32_t)(pl * F_) * (TC_ATTN_PITCH * 2) + (uint32_t)(hd * D_ * 2);
+            bf16 *dst = dst0 + (int64_t)pl * at.C + hd * D_;
+#pragma unroll
+            for (int i0 = 0; i0 < F_ * CPR; i0 += 32) {
+                const int i = i0 + lane;
+                if (i < F_ * CPR) {
+                    const int f = i / CPR, v = i - f * CPR;
+                    const float4 val = lds128(src + (uint32_t)f * (TC_ATTN_PITCH * 2) + (uint32_t)(v * 16));
+                    *reinterpret_cast<float4 *>(dst + (int64_t)f * at.P * at.C + v * 8) = val;
+                }
+            }
+        };
+        int prob = widx;
+        for (; prob + nw < nprob; prob += 2 * nw) {
+            const uint32_t qb2[2] = {qaddr(prob), qaddr(prob + nw)};
+            attention_problems<F_, D_, NMM_ATTN_TILE_CH, 2>(qb2, lane, at.scale_log2e, SmemQSlotStore<NMM_ATTN_TILE_CH>{qb2});
+            __syncwarp();
+            copy_out(prob); copy_out(prob + nw);
+        }
+        if (prob < nprob) {
+            const uint32_t qb1[1] = {qaddr(prob)};
+            attention_problems<F_, D_, NMM_ATTN_TILE_CH, 1>(qb1, lane, at.scale_log2e, SmemQSlotStore<NMM_ATTN_TILE_CH>{qb1});
+            __syncwarp();
+            copy_out(prob);
+        }
+    };
+    if (at.F == 8) {
+        if (at.dh == 40) run(std::integral_constant<int, 8>{}, std::integral_constant<int, 40>{});
+        else run(std::integral_constant<int, 8>{}, std::integral_constant<int, 80>{});
+    } else {
+        if (at.dh == 40) run(std::integral_constant<int, 16>{}, std::integral_constant<int, 40>{});
+        else run(std::integral_constant<int, 16>{}, std::integral_constant<int, 80>{});
+    }
+}
+
 // LNF: LayerNorm-folding roles compiled in (consumer transform / producer statistics).  Kept out of the default instantiation:
 // a run-time branch inside the unrolled epilogue loops costs the GEGLU epilogue its instruction-level parallelism (measured
 // 128 -> 204 us at C = 320).
 template <int EPI, int CG, bool LNF, bool GNA>
-__global__ void __launch_bounds__(GNA ? TC_THREADS + 32 * TC_GN_WARPS : TC_THREADS, 1)
+__global__ void __launch_bounds__(EPI == NMM_EPI_QKV_ATTN ? TC_THREADS + 32 * TC_ATTN_HELPERS : GNA ? TC_THREADS + 32 * TC_GN_WARPS : TC_THREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
                  const __grid_constant__ CUtensorMap tm_h,      // fp32 [M,N], box 32 x 32, 128-byte swizzle (residual load / h store)
                  const __grid_constant__ CUtensorMap tm_o,      // bf16 [M,N or N/2], box 32 x 32, 64-byte swizzle (`out` store)
@@ -274,6 +331,17 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 if (++as == 2) { as = 0; aphase ^= 1u; }
             }
         }
+    } else if (EPI == NMM_EPI_QKV_ATTN && warp >= 4 + TC_EPI_WARPS) {
+        // ===================== attention helpers (QKV + attention): share the tile's problems with the epilogue warps =============
+        const uint32_t xb = epi_base;
+        for (int64_t ct = cluster_id; ct < p.cluster_tiles; ct += num_clusters) {
+            const int64_t m_grp = ct / p.n_tiles;
+            const int n_blk = (int)(ct - m_grp * p.n_tiles);
+            if (p.debug & 1) break;                                                  // (timing experiment without epilogue: no barriers either)
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_ATTN_WARPS) : "memory");     // the tile has been dumped
+            fused_attention_phase(at, xb, m_grp * CG + rank, n_blk, warp - 4, TC_ATTN_WARPS, lane);
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_ATTN_WARPS) : "memory");     // done with the tile
+        }
     } else if (GNA && warp >= 4 + TC_EPI_WARPS) {
         // ===================== GroupNorm converter (GNA): normalise the A tile in place =====================
         // Thread (j, row): the 128-byte row of channel kb*64 + row in half j (64 positions of image bf_j).  The affine is per
@@ -415,65 +483,10 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
-                asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");      // the whole q|k|v tile is in shared memory
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_ATTN_WARPS) : "memory");     // the whole q|k|v tile is in shared memory
                 if (warp == 4 && lane == 0) TRACE(tile_no, 9);
-                {
-                    // problems (pl, head) of this warp, two at a time (interleaved instruction streams); each finished problem's
-                    // F x d_h block of context is copied to global memory by the same warp: no block-wide barrier in between
-                    const int img = (int)(m_blk / at.tiles_per_img);
-                    const int p0 = (int)(m_blk - (int64_t)img * at.tiles_per_img) * at.ppt;
-                    bf16 *dst0 = at.ctx + ((int64_t)img * at.F * at.P + p0) * at.C + n_blk * NMM_ATTN_TILE_CH;
-                    const int hb = NMM_ATTN_TILE_CH / at.dh;              // heads per tile: 2 (d_h 40) or 1 (d_h 80)
-                    const int nprob = at.ppt * hb;
-                    auto qaddr = [&](int prob) {
-                        const int pl = prob / hb, hd = prob - pl * hb;
-                        return xb + (uint32_t)(pl * at.F) * (TC_ATTN_PITCH * 2) + (uint32_t)(hd * at.dh * 2);
-                    };
-                    auto run = [&](auto FF, auto DD) {
-                        constexpr int F_ = decltype(FF)::value, D_ = decltype(DD)::value;
-                        auto copy_out = [&](int prob) {                   // F rows x (d_h / 8) 16-byte chunks, all bounds compile-time
-                            constexpr int HB_ = NMM_ATTN_TILE_CH / D_, CPR = D_ / 8;
-                            const int pl = prob / HB_, hd = prob - pl * HB_;
-                            const uint32_t src = xb + (uint32_t)(pl * F_) * (TC_ATTN_PITCH * 2) + (uint32_t)(hd * D_ * 2);
-                            bf16 *dst = dst0 + (int64_t)pl * at.C + hd * D_;
-#pragma unroll
-                            for (int i0 = 0; i0 < F_ * CPR; i0 += 32) {
-                                const int i = i0 + lane;
-                                if (i < F_ * CPR) {
-                                    const int f = i / CPR, v = i - f * CPR;
-                                    const float4 val = lds128(src + (uint32_t)f * (TC_ATTN_PITCH * 2) + (uint32_t)(v * 16));
-                                    *reinterpret_cast<float4 *>(dst + (int64_t)f * at.P * at.C + v * 8) = val;
-                                }
-                            }
-                        };
-                        int prob = ew;
-                        for (; prob + TC_EPI_WARPS < nprob; prob += 2 * TC_EPI_WARPS) {
-                            const uint32_t qb2[2] = {qaddr(prob), qaddr(prob + TC_EPI_WARPS)};
-                            attention_problems<F_, D_, NMM_ATTN_TILE_CH, 2>(qb2, lane, at.scale_log2e);
-                            __syncwarp();
-                            if (warp == 4 && lane == 0) TRACE(tile_no, prob == ew ? 11 : 14);
-                            if (!(p.debug & 64)) { copy_out(prob); copy_out(prob + TC_EPI_WARPS); }
-                            if (warp == 4 && lane == 0 && prob == ew) TRACE(tile_no, 13);
-                        }
-                        if (prob < nprob) {
-                            const uint32_t qb1[1] = {qaddr(prob)};
-                            attention_problems<F_, D_, NMM_ATTN_TILE_CH, 1>(qb1, lane, at.scale_log2e);
-                            __syncwarp();
-                            if (!(p.debug & 64)) copy_out(prob);
-                        }
-                    };
-                    if (p.debug & 32) {
-                        // timing experiment: no attention math
-                    } else if (at.F == 8) {
-                        if (at.dh == 40) run(std::integral_constant<int, 8>{}, std::integral_constant<int, 40>{});
-                        else run(std::integral_constant<int, 8>{}, std::integral_constant<int, 80>{});
-                    } else {
-                        if (at.dh == 40) run(std::integral_constant<int, 16>{}, std::integral_constant<int, 40>{});
-                        else run(std::integral_constant<int, 16>{}, std::integral_constant<int, 80>{});
-                    }
-                }
-                if (warp == 4 && lane == 0) TRACE(tile_no, 10);
-                asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");      // every warp is done with the tile: free for the next dump
+                fused_attention_phase(at, xb, m_blk, n_blk, ew, TC_ATTN_WARPS, lane);
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_ATTN_WARPS) : "memory");     // every warp is done with the tile: free for the next dump
                 if (warp == 4 && lane == 0) TRACE(tile_no, 12);
                 if (++as == 2) { as = 0; aphase ^= 1u; }
                 continue;
@@ -867,7 +880,7 @@ static int launch_tc_t(const CUtensorMap &ta, const CUtensorMap &tw, const CUten
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(GNA ? TC_THREADS + 32 * TC_GN_WARPS : TC_THREADS);
+    cfg.blockDim = dim3(EPI == NMM_EPI_QKV_ATTN ? TC_THREADS + 32 * TC_ATTN_HELPERS : GNA ? TC_THREADS + 32 * TC_GN_WARPS : TC_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
