@@ -455,26 +455,30 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 wait_acc();
                 {
                     const uint32_t rowaddr = xb + (uint32_t)(q * 32 + lane) * (TC_ATTN_PITCH * 2);
-                    const int cbeg = half ? 128 : 0, cend = half ? 240 : 128;
-                    for (int c0 = cbeg; c0 < cend; c0 += 32) {
-                        if (c0 + 32 <= cend) {
-                            uint32_t r[32];
-                            ptx::tmem_ld32(t_row + (uint32_t)c0, r);
+                    // half 0: columns [0, 128) = 4 x 32; half 1: [128, 240) = 3 x 32 + 16.  Two TMEM loads in flight per wait.
+                    auto put8 = [&](int c, const uint32_t *r) {          // 8 fp32 accumulator columns -> 8 bf16 = one 16-byte store
+                        sts128(rowaddr + (uint32_t)(c * 2), pack_bf16x2(__uint_as_float(r[0]), __uint_as_float(r[1])), pack_bf16x2(__uint_as_float(r[2]), __uint_as_float(r[3])),
+                               pack_bf16x2(__uint_as_float(r[4]), __uint_as_float(r[5])), pack_bf16x2(__uint_as_float(r[6]), __uint_as_float(r[7])));
+                    };
+                    const int cbeg = half ? 128 : 0;
+#pragma unroll
+                    for (int k = 0; k < 2; k++) {
+                        const int c0 = cbeg + 64 * k;
+                        uint32_t ra[32], rb[32];
+                        ptx::tmem_ld32(t_row + (uint32_t)c0, ra);
+                        if (k == 0 || !half) {
+                            ptx::tmem_ld32(t_row + (uint32_t)(c0 + 32), rb);
                             ptx::tmem_ld_wait();
 #pragma unroll
-                            for (int j = 0; j < 4; j++)
-                                sts128(rowaddr + (uint32_t)((c0 + 8 * j) * 2),
-                                       pack_bf16x2(__uint_as_float(r[8 * j]), __uint_as_float(r[8 * j + 1])), pack_bf16x2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3])),
-                                       pack_bf16x2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5])), pack_bf16x2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7])));
-                        } else {
-                            uint32_t r[16];
-                            ptx::tmem_ld16(t_row + (uint32_t)c0, r);
+                            for (int j = 0; j < 4; j++) { put8(c0 + 8 * j, ra + 8 * j); put8(c0 + 32 + 8 * j, rb + 8 * j); }
+                        } else {                                             // half 1, second step: 32 + 16 columns (192 .. 239)
+                            uint32_t rc[16];
+                            ptx::tmem_ld16(t_row + (uint32_t)(c0 + 32), rc);
                             ptx::tmem_ld_wait();
 #pragma unroll
-                            for (int j = 0; j < 2; j++)
-                                sts128(rowaddr + (uint32_t)((c0 + 8 * j) * 2),
-                                       pack_bf16x2(__uint_as_float(r[8 * j]), __uint_as_float(r[8 * j + 1])), pack_bf16x2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3])),
-                                       pack_bf16x2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5])), pack_bf16x2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7])));
+                            for (int j = 0; j < 4; j++) put8(c0 + 8 * j, ra + 8 * j);
+#pragma unroll
+                            for (int j = 0; j < 2; j++) put8(c0 + 32 + 8 * j, rc + 8 * j);
                         }
                     }
                 }
