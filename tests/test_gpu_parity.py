@@ -411,3 +411,26 @@ def test_qkv_attention_fused_matches_two_kernel_path(C, F, H, W, B):
     s = torch.einsum("bfphd,bgphd->bphfg", z[:, :, :, 0], z[:, :, :, 1]) * dh ** -0.5
     ref = torch.einsum("bphfg,bgphd->bfphd", s.softmax(-1), z[:, :, :, 2]).reshape(N, C)
     assert _maxabs(fused, ref) <= 2e-2 * max(1.0, ref.abs().max().item())
+
+
+def test_fused_and_unfused_kernel_paths_agree(monkeypatch):
+    """The module with every fusion (GroupNorm inside proj_in, attention inside the QKV projection) against the same module with the
+    stand-alone kernels (NMM_NO_GN_FUSE / NMM_NO_ATTN_FUSE): same arithmetic up to the bf16 rounding of P in the attention."""
+    cfg = mo.MotionConfig(320)
+    params = {k: helpers.round_bf16(v) for k, v in mo.make_params(cfg, 5).items()}
+    m = helpers.mirror_module(cfg, params, DEV, torch.bfloat16)
+    x = helpers.round_bf16(mo.make_input((2, 320, 8, 16, 16), 6, layout="bfchw")).to(DEV, torch.bfloat16)
+    with torch.no_grad():
+        m(x, None, None)                                   # first call packs the parameters (extra launches)
+        n0 = nb.launch_count()
+        y_fused = m(x, None, None).float()
+        n_fused = nb.launch_count() - n0
+        monkeypatch.setenv("NMM_NO_GN_FUSE", "1")
+        monkeypatch.setenv("NMM_NO_ATTN_FUSE", "1")
+        n0 = nb.launch_count()
+        y_plain = m(x, None, None).float()
+        n_plain = nb.launch_count() - n0
+    assert n_fused == 12 and n_plain == 15
+    assert (y_fused - y_plain).abs().max().item() <= 2 ** -6 * y_plain.abs().max().item()
+    ref = mo.forward_reference_order(params, x.float().cpu(), cfg)
+    assert _maxabs(y_fused, ref) <= helpers.TOL_BF16 and _maxabs(y_plain, ref) <= helpers.TOL_BF16
