@@ -52,6 +52,7 @@ struct TcParams {
     int64_t m_tiles;
     int cluster;             // CTAs per tile along M: 1 (cta_group::1) or 2 (cta_group::2 pair, each CTA stages half of W)
     int64_t cluster_tiles;   // ceil(m_tiles / cluster) * n_tiles
+    int wide;                // 1: block_n = 320 computed as two N = 160 MMAs per k-step into ONE accumulator (no TMEM double buffering); CTA pairs only
     int epi_buf;             // bytes of shared memory per epilogue warp (8 KB; 12 KB when a residual epilogue also writes a bf16 copy)
     unsigned long long *trace;   // NMM_TRACE builds only: per-tile timestamps of CTA 0 (development instrumentation)
     int debug;               // NMM_GEMM_DEBUG (timing experiments only, results invalid): 1 = epilogue does nothing, 2 = no TMA loads
@@ -278,7 +279,13 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         if (leader) ptx::mbar_expect_tx(full_bar(stage), 2u * stage_bytes);
                         const uint32_t bar0 = full_bar(stage) & ptx::PEER_MASK;
                         ptx::tma_load_2d_2sm(&tm_a, bar0, sa, kb * TC_BK, (int32_t)(m_blk * TC_BM));
-                        ptx::tma_load_2d_2sm(&tm_w, bar0, sa + TC_A_BYTES, kb * TC_BK, n_blk * p.block_n + (int)(rank * b_rows));
+                        if (p.wide) {      // two N = 160 blocks, this CTA stages its 80-row half of each
+                            const uint32_t hb = b_rows / 2;
+                            ptx::tma_load_2d_2sm(&tm_w, bar0, sa + TC_A_BYTES, kb * TC_BK, n_blk * p.block_n + (int)(rank * hb));
+                            ptx::tma_load_2d_2sm(&tm_w, bar0, sa + TC_A_BYTES + hb * TC_BK * 2, kb * TC_BK, n_blk * p.block_n + p.block_n / 2 + (int)(rank * hb));
+                        } else {
+                            ptx::tma_load_2d_2sm(&tm_w, bar0, sa + TC_A_BYTES, kb * TC_BK, n_blk * p.block_n + (int)(rank * b_rows));
+                        }
                     }
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
@@ -287,7 +294,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     } else if (warp == 1) {
         // ===================== MMA issuer (one thread of the even CTA) =====================
         if (lane == 0 && leader) {
-            const uint32_t idesc = ptx::umma_idesc_bf16(TC_BM * CG, (uint32_t)p.block_n) | (GNA ? ptx::UMMA_IDESC_A_MN_MAJOR : 0u);
+            const uint32_t n_mma = p.wide ? (uint32_t)p.block_n / 2 : (uint32_t)p.block_n;      // columns per MMA instruction
+            const uint32_t idesc = ptx::umma_idesc_bf16(TC_BM * CG, n_mma) | (GNA ? ptx::UMMA_IDESC_A_MN_MAJOR : 0u);
             int stage = 0; uint32_t phase = 0;
             int as = 0; uint32_t aphase = 0;
             int tile_no = 0;
@@ -319,16 +327,27 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                             ptx::umma_bf16<CG>(d_tmem, a_desc + (uint64_t)(k * (2048 >> 4)), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
                     } else {
                         const uint64_t a_desc = ptx::umma_smem_desc_sw128(sa);
+                        if (p.wide) {
+                            // second N block: its rows follow the first block's in this CTA's W stage (n_mma / CG rows x 128 bytes further)
+                            const uint64_t b_desc2 = ptx::umma_smem_desc_sw128(sa + TC_A_BYTES + (n_mma / CG) * TC_BK * 2);
 #pragma unroll
-                        for (int k = 0; k < TC_BK / 16; k++)             // +32 bytes per K=16 step inside the swizzle atom
-                            ptx::umma_bf16<CG>(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                            for (int k = 0; k < TC_BK / 16; k++) {
+                                ptx::umma_bf16<CG>(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                                ptx::umma_bf16<CG>(d_tmem + n_mma, a_desc + (uint64_t)(k * 2), b_desc2 + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                            }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < TC_BK / 16; k++)         // +32 bytes per K=16 step inside the swizzle atom
+                                ptx::umma_bf16<CG>(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
                     }
                     ptx::umma_commit<CG>(empty_bar(stage));               // stage reusable (in both CTAs) once these MMAs retire
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
                 ptx::umma_commit<CG>(tfull_bar(as));                      // accumulator complete (signalled in both CTAs)
                 TRACE(tile_no, 3);
-                if (++as == 2) { as = 0; aphase ^= 1u; }
+                if (p.wide) aphase ^= 1u;                                 // single accumulator: its barriers change phase every tile
+                else if (++as == 2) { as = 0; aphase ^= 1u; }
             }
         }
     } else if (EPI == NMM_EPI_QKV_ATTN && warp >= 4 + TC_EPI_WARPS) {
@@ -717,7 +736,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 if (CG == 1) ptx::mbar_arrive(tempty_bar(as));
                 else ptx::mbar_arrive_cluster(tempty_bar(as) & ptx::PEER_MASK);      // the even CTA's barrier
             }
-            if (++as == 2) { as = 0; aphase ^= 1u; }
+            if (p.wide) aphase ^= 1u;
+            else if (++as == 2) { as = 0; aphase ^= 1u; }
         }
         if (lane == 0) ptx::bulk_wait_all();                              // all TMA stores of this warp have completed
     }
@@ -840,9 +860,9 @@ static int num_sms() {
 //   per tile      num_kb * that + a fixed per-tile overhead (barrier round trips, epilogue tail)
 //   whole GEMM    ceil(cluster_tiles / resident clusters) * per tile            (wave quantisation)
 // The per-SM ingest of ~64 B/clk is why only (CG = 2, bn = 256) can keep the tensor pipe fully fed, and why small tiles lose.
-struct TilePlan { int block_n, cluster; };
-static TilePlan choose_tiles(int64_t m_tiles, int N, int K, int sms, int gran, int force_cluster, int force_bn) {
-    TilePlan best = {0, 1};
+struct TilePlan { int block_n, cluster, wide; };
+static TilePlan choose_tiles(int64_t m_tiles, int N, int K, int sms, int gran, int force_cluster, int force_bn, bool allow_wide = false) {
+    TilePlan best = {0, 1, 0};
     double best_cost = 1e300;
     const int num_kb = (K + TC_BK - 1) / TC_BK;
     for (int cg = 1; cg <= 2; cg++) {
@@ -858,8 +878,17 @@ static TilePlan choose_tiles(int64_t m_tiles, int N, int K, int sms, int gran, i
             const int64_t cluster_tiles = m_groups * (N / bn);
             const int64_t resident = sms / cg;
             const double cost = (double)ceil_div(cluster_tiles, resident) * per_tile;
-            if (cost < best_cost) { best_cost = cost; best.block_n = bn; best.cluster = cg; }
+            if (cost < best_cost) { best_cost = cost; best.block_n = bn; best.cluster = cg; best.wide = 0; }
         }
+    }
+    // Wide pair tile: 256 x 320 per CTA pair as two N = 160 MMAs per k-step into one 320-column accumulator.  Per CTA and k-block
+    // 16 KB of A + 20 KB of W feed 128 x 320 outputs (1.45x the arithmetic intensity of 256 x 160), but with a single accumulator the
+    // epilogue (~16 cycles per column) is not hidden behind the next tile's MMAs: it pays for long K and few waves (ff_out).
+    if (allow_wide && N % 320 == 0 && sms % 2 == 0 && m_tiles >= 2 && force_cluster != 1 && (force_bn == 0 || force_bn == 320)) {
+        const double mma = 2.0 * 320, fill = (16384.0 + 320 * 128.0 / 2) / 64.0;
+        const double per_tile = num_kb * (mma > fill ? mma : fill) + 3000.0 + 20.0 * 320;
+        const double cost = (double)ceil_div(ceil_div(m_tiles, 2) * (N / 320), (int64_t)(sms / 2)) * per_tile;
+        if (cost < best_cost || force_bn == 320) { best_cost = cost; best.block_n = 320; best.cluster = 2; best.wide = 1; }
     }
     return best;
 }
@@ -934,12 +963,14 @@ int launch_linear_tc(const LinearArgs &a, cudaStream_t st) {
                 !linear_tc_gn_fusable(a.M, a.P, a.gn_x, a.xsb, a.xsc, a.xsf) || (int64_t)a.gn_B * a.F * a.P != a.M))
         return fail(NMM_ERR_UNSUPPORTED, "GroupNorm-fused A operand: needs the STORE epilogue, P %% 64 == 0, M %% 128 == 0 and 16-byte aligned x");
     const int gran = a.epilogue == NMM_EPI_GEGLU ? 64 : 32;
-    const TilePlan plan = attn ? TilePlan{3 * NMM_ATTN_TILE_CH, 1} :
+    const bool allow_wide = a.epilogue == NMM_EPI_RESIDUAL && !gna && a.ln_part_in == nullptr && a.ln_part_out == nullptr && !(debug_flags & 2) && !getenv("NMM_NO_WIDE_TILE");
+    const TilePlan plan = attn ? TilePlan{3 * NMM_ATTN_TILE_CH, 1, 0} :
                           choose_tiles(p.m_tiles, a.N, a.K, sms, gran, gna ? 1 : (force_cluster == 1 || force_cluster == 2) ? force_cluster : 0,
-                                       (force_bn >= gran && force_bn <= 256 && force_bn % gran == 0 && a.N % force_bn == 0) ? force_bn : 0);
+                                       (force_bn >= gran && force_bn <= 320 && force_bn % gran == 0 && a.N % force_bn == 0) ? force_bn : 0, allow_wide);
     if (plan.block_n == 0) return fail(NMM_ERR_UNSUPPORTED, "tcgen05 GEMM: no N tile for N=%d", a.N);
     p.block_n = plan.block_n;
     p.cluster = plan.cluster;
+    p.wide = plan.wide;
     const int64_t m_groups = ceil_div(p.m_tiles, p.cluster);
     p.n_tiles = a.N / p.block_n;
     p.cluster_tiles = m_groups * p.n_tiles;
@@ -952,7 +983,7 @@ int launch_linear_tc(const LinearArgs &a, cudaStream_t st) {
     if (stages < 2) return fail(NMM_ERR_UNSUPPORTED, "tcgen05 GEMM: tile does not fit shared memory");
     p.stages = stages;
     int cols = 32;
-    while (cols < 2 * p.block_n) cols <<= 1;
+    while (cols < (p.wide ? 1 : 2) * p.block_n) cols <<= 1;       // wide tiles keep one accumulator
     p.tmem_cols = cols;
     const size_t smem = fixed + (size_t)stages * stage_bytes;
     CUtensorMap ta, tw, th, to;
@@ -961,7 +992,7 @@ int launch_linear_tc(const LinearArgs &a, cudaStream_t st) {
                  : make_tmap(&ta, a.A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.M, a.K, a.K, TC_BM, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != NMM_OK) return rc;
     // each CTA of a pair fetches its slice of the W tile
-    rc = make_tmap(&tw, a.W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.N, a.K, a.K, p.block_n / p.cluster, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B);
+    rc = make_tmap(&tw, a.W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.N, a.K, a.K, p.block_n / p.cluster / (p.wide ? 2 : 1), TC_BK, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != NMM_OK) return rc;
     memset(&th, 0, sizeof(th));
     memset(&to, 0, sizeof(to));

@@ -434,3 +434,20 @@ def test_fused_and_unfused_kernel_paths_agree(monkeypatch):
     assert (y_fused - y_plain).abs().max().item() <= 2 ** -6 * y_plain.abs().max().item()
     ref = mo.forward_reference_order(params, x.float().cpu(), cfg)
     assert _maxabs(y_fused, ref) <= helpers.TOL_BF16 and _maxabs(y_plain, ref) <= helpers.TOL_BF16
+
+
+@pytest.mark.parametrize("M,N,K,copy", [(16384, 640, 2560, True), (4096, 1280, 5120, False), (16384 + 128, 640, 2560, True)])
+def test_linear_residual_wide_pair_tile(M, N, K, copy):
+    """Shapes for which the planner picks the 256 x 320 pair tile (two N = 160 MMAs per k-step into one accumulator): ff_out at the
+    C = 640 / 1280 levels.  Reference: fp64 matmul on the GPU (plumbing only)."""
+    g = torch.Generator(device=DEV).manual_seed(M + N)
+    A = torch.randn(M, K, device=DEV, generator=g).to(torch.bfloat16)
+    W = (torch.randn(N, K, device=DEV, generator=g) / K ** 0.5).to(torch.bfloat16)
+    b = torch.randn(N, device=DEV, generator=g)
+    h = torch.randn(M, N, device=DEV, generator=g)
+    ref = h.double() + A.double() @ W.double().T + b.double()
+    out = ops.linear(A, W, b, nlib.EPI_RESIDUAL, h=h, want_out=copy)
+    if copy:      # nmm_linear: with `out` the sum goes to `out` alone (h is only read), as in the last feed-forward of the module
+        assert (out.double() - ref).abs().max().item() <= 2 ** -8 * 1.01 * ref.abs().max().item() + 1e-3
+    else:
+        assert (h.double() - ref).abs().max().item() <= 1e-3
