@@ -16,6 +16,15 @@
 // Both operands are K-major in global memory ([rows, K] row-major), which is exactly how activations (token-major) and
 // nn.Linear weights ([out, in]) are laid out, so no transposes are ever materialised.
 //
+// Variants compiled from the same kernel:
+//   GNA (proj_in)          the A tile is TMA-loaded straight from x[b,c,f,p] (an M-major operand: MN-major SW128 descriptor) and
+//                          GroupNorm-normalised in shared memory by 4 converter warps (12-15) before the MMA reads it;
+//   NMM_EPI_QKV_ATTN       A rows are (position, frame) pairs (3-D tensor map, frames before positions), N tile = q | k | v of 80
+//                          channels; the epilogue dumps the tile to shared memory as bf16 and runs the temporal attention there
+//                          (mma.sync core shared with attention_kernel.cu) together with 8 helper warps (12-19);
+//   wide (p.wide)          256 x 320 pair tile as two N = 160 MMAs per k-step into one accumulator (long-K residual GEMMs);
+//   LNF                    LayerNorm folded into producer / consumer epilogues (measured slower; kept as a tested option).
+//
 // Measured bounds that shaped this (profiles/, scripts/micro/tmem_bw.cu, scripts/gemm_trace.py):
 //   * tcgen05.ld moves >= 245 B/clk/SM and overlaps fully with tcgen05.mma -- TMEM reads are not the limit;
 //   * a 128 x 240 tile needs 46 KB of operand fill per 480 MMA-cycles; with ~2500-cycle TMA latency under load and 3 stages the
