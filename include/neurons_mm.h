@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define NMM_ABI_VERSION 1
+#define NMM_ABI_VERSION 2
 #if defined(__GNUC__)
 #define NMM_API __attribute__((visibility("default")))
 #else
@@ -107,6 +107,24 @@ typedef struct nmm_params {
     const void *proj_out_w, *proj_out_b;/* temporal_transformer.proj_out.{weight,bias}       [C,C],[C]*/
 } nmm_params;
 
+/* Run-time options (process-wide; development / A-B measurement switches -- every default is the production path and no option
+ * changes results beyond rounding).  Initial values come from the environment variables named below, read ONCE at first use;
+ * nmm_set_option overrides them.  Nothing in the launch path calls getenv. */
+typedef enum nmm_option {
+    NMM_OPT_FUSED_MODULE = 0,   /* 1: C = 320 calls run on the one-kernel path (fused_module.cu).  env NMM_NO_FUSED_MODULE=1 -> 0  */
+    NMM_OPT_GN_FUSE = 1,        /* 1: GroupNorm applied inside proj_in's tensor-core kernel.          env NMM_NO_GN_FUSE=1 -> 0     */
+    NMM_OPT_ATTN_FUSE = 2,      /* 1: temporal attention inside the QKV projection's epilogue.        env NMM_NO_ATTN_FUSE=1 -> 0   */
+    NMM_OPT_WIDE_TILE = 3,      /* 1: 256 x 320 pair tiles for long-K residual GEMMs.                 env NMM_NO_WIDE_TILE=1 -> 0   */
+    NMM_OPT_GEMM_CLUSTER = 4,   /* 0: planner decides; 1 / 2: force CTAs per tile.                    env NMM_GEMM_CLUSTER          */
+    NMM_OPT_GEMM_BLOCK_N = 5,   /* 0: planner decides; else force the N tile.                         env NMM_GEMM_BLOCK_N          */
+    NMM_OPT_CHUNK_TOKENS = 6,   /* 0: whole tensor; else tokens per position chunk (negative result). env NMM_CHUNK_TOKENS          */
+    NMM_OPT_ATTN_VARIANT = 7,   /* 0: specialised mma kernel; 1: run-time-shaped mma; 2: SIMT.        env NMM_ATTN_GENERIC / _SIMT  */
+    NMM_OPT_SPLIT_K = 8,        /* 1: split-K for GEMMs with too few tiles for the machine (C = 1280 levels).  env NMM_NO_SPLIT_K=1 -> 0 */
+    NMM_OPT_COUNT = 9
+} nmm_option;
+NMM_API int nmm_set_option(int32_t option, int64_t value);
+NMM_API int64_t nmm_get_option(int32_t option);
+
 /* ---- library / device ------------------------------------------------------------------------ */
 NMM_API int nmm_abi_version(void);
 NMM_API const char *nmm_last_error(void);
@@ -119,7 +137,7 @@ NMM_API uint64_t nmm_launch_count(void);
  * launch with CUDA events on the launch stream (eager launches only; launches inside a stream capture are skipped).
  * nmm_profile_end synchronises on the recorded events and fills one entry per kernel (NMM_PROFILE_KERNELS entries):
  * launches, summed device ms, and the summed ALGORITHMIC flops / bytes of those launches. */
-#define NMM_PROFILE_KERNELS 7
+#define NMM_PROFILE_KERNELS 8
 typedef struct nmm_kernel_profile {
     const char *name;
     uint64_t launches;
@@ -137,9 +155,22 @@ NMM_API int nmm_workspace_bytes(const nmm_shape *s, size_t *out_bytes);
 /* Convert + re-lay-out the module's parameters once (QKV concatenated, GEGLU value/gate rows
  * interleaved in groups of four, GEMM operands in the arithmetic dtype, biases / norm affines / PE in fp32). */
 NMM_API int nmm_pack_params(const nmm_shape *s, const nmm_params *src, void *packed, size_t packed_bytes, void *stream);
-/* y = module(x).  x, y: element type s->dtype with the strides in *s.  x and y must not alias. */
-NMM_API int nmm_forward(const nmm_shape *s, const void *x, void *y, const void *packed, void *workspace,
+/* y = module(x).  x, y: element type s->dtype with the strides in *s.  x and y must not alias.
+ * `packed_bytes` must equal nmm_packed_params_bytes(s): a buffer packed for another dtype / ln_fold / geometry selects another
+ * layout and is refused instead of being read out of bounds.
+ * Replaces VanillaTemporalModule.forward, animatediff/models/motion_module.py:77-82 (-> :134-158, :210-222, :270-329).
+ * bf16, C = 320, 8 heads, 8 or 16 frames, H*W % (128 / frames) == 0: GroupNorm statistics + ONE fused kernel for the rest
+ * (csrc/fused_module.cu); other shapes: the multi-kernel pipeline (csrc/api.cu). */
+NMM_API int nmm_forward(const nmm_shape *s, const void *x, void *y, const void *packed, size_t packed_bytes, void *workspace,
                 size_t workspace_bytes, void *stream);
+/* The 64-byte header nmm_pack_params writes at the start of a packed buffer for this geometry (magic, ABI, dtype, ln_fold, C, heads,
+ * layers, attention blocks, max_len, pos_enc, total bytes): lets a host check what a buffer was packed for. */
+NMM_API int nmm_packed_header(const nmm_shape *s, void *out, size_t out_bytes);
+/* Test hook of the fused C = 320 kernel: nmm_forward plus an fp32 [N, C] snapshot (token order n = (b*F + f)*P + p) of the residual
+ * stream after stage `stage_id`: 0 = proj_in (motion_module.py:145), 1 + i = attention block i (:213-217), 1 + A = feed-forward (:219).
+ * NMM_ERR_UNSUPPORTED when the call would not run on the fused kernel. */
+NMM_API int nmm_forward_stage(const nmm_shape *s, const void *x, void *y, const void *packed, size_t packed_bytes, void *workspace,
+                size_t workspace_bytes, int32_t stage_id, float *stage_out, void *stream);
 
 /* ---- per-stage entry points (kernel-level parity tests and micro-benchmarks) ------------------- */
 /* GroupNorm(32, C, eps_gn) statistics per (b, f, group): motion_module.py:142.  mean/rstd: fp32 [B*F*32]. */

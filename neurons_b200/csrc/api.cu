@@ -27,6 +27,29 @@ int fail(int status, const char *fmt, ...) {
     return status;
 }
 
+// ---- run-time options ------------------------------------------------------------------------------------------
+namespace {
+std::atomic<int64_t> g_opts[NMM_OPT_COUNT];
+std::once_flag g_opts_once;
+void init_opts() {
+    auto flag_off = [](const char *name) { const char *e = getenv(name); return (e && *e && strcmp(e, "0") != 0) ? 0 : 1; };
+    auto num = [](const char *name) { const char *e = getenv(name); return e ? atoll(e) : 0ll; };
+    g_opts[NMM_OPT_FUSED_MODULE] = flag_off("NMM_NO_FUSED_MODULE");
+    g_opts[NMM_OPT_GN_FUSE] = flag_off("NMM_NO_GN_FUSE");
+    g_opts[NMM_OPT_ATTN_FUSE] = flag_off("NMM_NO_ATTN_FUSE");
+    g_opts[NMM_OPT_WIDE_TILE] = flag_off("NMM_NO_WIDE_TILE");
+    g_opts[NMM_OPT_GEMM_CLUSTER] = num("NMM_GEMM_CLUSTER");
+    g_opts[NMM_OPT_GEMM_BLOCK_N] = num("NMM_GEMM_BLOCK_N");
+    g_opts[NMM_OPT_CHUNK_TOKENS] = num("NMM_CHUNK_TOKENS");
+    g_opts[NMM_OPT_ATTN_VARIANT] = getenv("NMM_ATTN_SIMT") ? 2 : getenv("NMM_ATTN_GENERIC") ? 1 : 0;
+    g_opts[NMM_OPT_SPLIT_K] = flag_off("NMM_NO_SPLIT_K");
+}
+}  // namespace
+int64_t opt(int option) {
+    std::call_once(g_opts_once, init_opts);
+    return (option >= 0 && option < NMM_OPT_COUNT) ? g_opts[option].load(std::memory_order_relaxed) : 0;
+}
+
 // ---- per-kernel device timing ---------------------------------------------------------------------------------
 namespace {
 struct ProfRecord { cudaEvent_t start, stop; int kid; double flops, bytes; };
@@ -61,9 +84,14 @@ ProfScope::~ProfScope() {
 }
 
 // ---- packed parameter layout -------------------------------------------------------------------------
-struct AttnOff { size_t ln_w, ln_b, wqkv, wqkv_t, wo, bo, pe, g_qkv, c_qkv, pew; };   // wqkv_t: tile-ordered copy (fused attention); g/c/pew: LayerNorm folding
+struct AttnOff { size_t ln_w, ln_b, wqkv, wqkv_t, wo, bo, pe, g_qkv, c_qkv, pew, wo_tail; };   // wqkv_t: tile-ordered copy (fused attention); g/c/pew: LayerNorm folding; wo_tail: fused module
 struct LayerOff { AttnOff attn[NMM_MAX_ATTN]; size_t ff_ln_w, ff_ln_b, w1, b1, w2, b2, g1, c1; };
-struct PackedLayout { size_t gn_w, gn_b, w_in, b_in; LayerOff layer[NMM_MAX_LAYERS]; size_t w_out, b_out, total; };
+struct PackedLayout { size_t header, gn_w, gn_b, w_in, b_in; LayerOff layer[NMM_MAX_LAYERS]; size_t w_out, b_out, cbias, total; };
+
+// First 256 bytes of every packed buffer: what it was packed for.  nmm_forward refuses a buffer whose header does not match the call
+// (another dtype / head count / LayerNorm-folding mode would select another layout and read out of bounds).
+struct PackedHeader { uint32_t magic, abi; int32_t dtype, ln_fold, C, heads, layers, A, max_len, pos_enc; uint64_t total; };
+constexpr uint32_t PACKED_MAGIC = 0x4D4D4E32u;      // "2NMM"
 
 // does this module keep a tile-ordered q|k|v weight for the fused QKV + attention kernel?  (shape-independent part of the test)
 static bool attn_fuse_weights(const Geo &g) {
@@ -76,6 +104,7 @@ static PackedLayout packed_layout(const Geo &g) {
     size_t off = 0;
     const size_t C = g.C, ws = dtype_size(g.dtype);
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    L.header = take(sizeof(PackedHeader));
     L.gn_w = take(C * 4); L.gn_b = take(C * 4);
     L.w_in = take(C * C * ws); L.b_in = take(C * 4);
     for (int l = 0; l < g.layers; l++) {
@@ -87,6 +116,7 @@ static PackedLayout packed_layout(const Geo &g) {
             a.pe = take(g.pos_enc ? (size_t)g.max_len * C * 4 : 0);
             a.g_qkv = take(g.ln_fold ? 3 * C * 4 : 0); a.c_qkv = take(g.ln_fold ? 3 * C * 4 : 0);
             a.pew = take(g.ln_fold && g.pos_enc ? (size_t)g.max_len * 3 * C * 4 : 0);
+            a.wo_tail = take(fused_module_weights(g) ? (size_t)4 * C * 16 * ws : 0);      // 16 of every 80 to_out input channels
         }
         LayerOff &lo = L.layer[l];
         lo.ff_ln_w = take(C * 4); lo.ff_ln_b = take(C * 4);
@@ -95,6 +125,7 @@ static PackedLayout packed_layout(const Geo &g) {
         lo.g1 = take(g.ln_fold ? 8 * C * 4 : 0); lo.c1 = take(g.ln_fold ? 8 * C * 4 : 0);
     }
     L.w_out = take(C * C * ws); L.b_out = take(C * 4);
+    L.cbias = take(fused_module_weights(g) ? (size_t)(g.A + 2) * C * 4 : 0);       // cumulative biases of the residual stream (fused module)
     L.total = off;
     return L;
 }
@@ -110,8 +141,7 @@ static PackedLayout packed_layout(const Geo &g) {
 static int chunk_positions(const Geo &g) {
     // Measured on B200 (profiles/r1_chunk_sweep.txt): chunking LOSES at every chunk size (4096 tokens: 14.2 ms/step, 16384: 8.7,
     // off: 8.0) -- the per-kernel fixed cost (launch, ramp, tail; ~10 us) outweighs the saved HBM traffic, so it is off by default.
-    int64_t target = 0;                                      // tokens per chunk; 0 = whole tensor
-    if (const char *e = getenv("NMM_CHUNK_TOKENS")) target = atoll(e);
+    const int64_t target = opt(NMM_OPT_CHUNK_TOKENS);       // tokens per chunk; 0 = whole tensor
     if (target <= 0 || g.P % 64 != 0) return g.P;
     int64_t pc = target / ((int64_t)g.B * g.F) / 64 * 64;
     if (pc < 64) pc = 64;
@@ -307,6 +337,35 @@ static int fold_linear(int src_dtype, const void *w, const void *gamma, const vo
     return fold_linear_t<bf16>(w, gamma, beta, bias, pe, (bf16 *)dst_w, g_out, c_out, pew_out, rows, cols, half, max_len, pew_pitch, st);
 }
 
+// ---- extra packed tensors of the fused C = 320 module kernel (fused_module.cu) ----------------------------------------------------
+// to_out input channels 64-79 of every head pair (80 channels) as an un-swizzled K-major B operand, one contiguous 5 KB block per
+// (pair, N half):  dst[hp][half][chunk 0..1][row 0..159][8] = Wo[half * 160 + row][hp * 80 + 64 + chunk * 8 + e]
+__global__ void wo_tail_kernel(const bf16 *__restrict__ wo, bf16 *__restrict__ dst, int C) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int total = 4 * 2 * 2 * 160 * 8;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int e = i & 7, row = (i >> 3) % 160, chunk = (i / (8 * 160)) & 1, half = (i / (8 * 160 * 2)) & 1, hp = i / (8 * 160 * 4);
+        dst[i] = wo[(size_t)(half * 160 + row) * C + hp * 80 + 64 + chunk * 8 + e];
+    }
+}
+// cb[0] = b_in; cb[1 + i] = cb[i] + bo_i; cb[A + 1] = cb[A] + b2 (fp32, packed biases): what the readers of the TMEM-resident
+// residual stream add, since the GEMMs accumulate onto it without their bias.
+struct BiasList { const float *b[NMM_MAX_ATTN + 2]; int n; };
+__global__ void cumulative_bias_kernel(float *__restrict__ cb, BiasList list, int C) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float acc = 0.f;
+    for (int k = 0; k < list.n; k++) { acc += list.b[k][c]; cb[(size_t)k * C + c] = acc; }
+}
+__global__ void write_header_kernel(PackedHeader hd, PackedHeader *dst) {
+    pdl_wait();
+    pdl_launch_dependents();
+    if (threadIdx.x == 0 && blockIdx.x == 0) *dst = hd;
+}
+
 // Sinusoidal table when the caller does not hand over the module's own `pe` buffer (motion_module.py:234-238).
 __global__ void make_pe_kernel(float *__restrict__ pe, int max_len, int C) {
     pdl_wait();                    // PDL: the previous kernel has completed (no-op without the launch attribute)
@@ -334,6 +393,14 @@ uint64_t nmm_launch_count(void) { return g_launches.load(std::memory_order_relax
 int nmm_device_check(void) { return device_check(); }
 int nmm_validate(const nmm_shape *s) { return validate(s); }
 
+int nmm_set_option(int32_t option, int64_t value) {
+    if (option < 0 || option >= NMM_OPT_COUNT) return fail(NMM_ERR_BAD_ARG, "unknown option %d", option);
+    std::call_once(g_opts_once, init_opts);
+    g_opts[option].store(value, std::memory_order_relaxed);
+    return NMM_OK;
+}
+int64_t nmm_get_option(int32_t option) { return opt(option); }
+
 int nmm_profile_begin(void) {
     std::lock_guard<std::mutex> lk(g_prof.mu);
     for (auto &r : g_prof.rec) g_prof.pool.emplace_back(r.start, r.stop);
@@ -347,7 +414,7 @@ int nmm_profile_end(nmm_kernel_profile *out, int32_t max_kernels) {
     g_prof.enabled = false;
     if (!out || max_kernels < K_COUNT) return fail(NMM_ERR_BAD_ARG, "nmm_profile_end needs room for %d kernels", (int)K_COUNT);
     static const char *names[K_COUNT] = {"gn_stats", "gn_tokens", "layernorm_pe", "temporal_attention", "linear_fp32_fma",
-                                         "linear_bf16_tcgen05", "pack_params"};
+                                         "linear_bf16_tcgen05", "pack_params", "fused_module_tcgen05"};
     for (int k = 0; k < K_COUNT; k++) { out[k].name = names[k]; out[k].launches = 0; out[k].total_ms = 0; out[k].flops = 0; out[k].bytes = 0; }
     int rc = NMM_OK;
     for (auto &r : g_prof.rec) {
@@ -397,6 +464,14 @@ int nmm_pack_params(const nmm_shape *s, const nmm_params *src, void *packed, siz
         rc = launch_convert_rows((srcp), sd, base + (off), (dd), (rows), (cols), (half), st);        \
         if (rc != NMM_OK) return rc;                                                                 \
     } while (0)
+    {
+        PackedHeader hd;
+        memset(&hd, 0, sizeof(hd));
+        hd.magic = PACKED_MAGIC; hd.abi = NMM_ABI_VERSION; hd.dtype = g.dtype; hd.ln_fold = g.ln_fold ? 1 : 0; hd.C = g.C; hd.heads = g.heads;
+        hd.layers = g.layers; hd.A = g.A; hd.max_len = g.max_len; hd.pos_enc = g.pos_enc ? 1 : 0; hd.total = L.total;
+        launch_pdl(write_header_kernel, 1, 32, 0, st, hd, (PackedHeader *)(base + L.header));
+        NMM_LAUNCHED("write_header_kernel");
+    }
     PACK(src->gn_w, L.gn_w, NMM_F32, C, 1, 0); PACK(src->gn_b, L.gn_b, NMM_F32, C, 1, 0);
     PACK(src->proj_in_w, L.w_in, wd, C, C, 0); PACK(src->proj_in_b, L.b_in, NMM_F32, C, 1, 0);
     for (int l = 0; l < g.layers; l++) {
@@ -433,6 +508,10 @@ int nmm_pack_params(const nmm_shape *s, const nmm_params *src, void *packed, siz
                 PACK(ap.to_q, ao.wqkv, wd, C, C, 0); PACK(ap.to_k, ao.wqkv + wbytes, wd, C, C, 0); PACK(ap.to_v, ao.wqkv + 2 * wbytes, wd, C, C, 0);
                 if (attn_fuse_weights(g) && (rc = launch_qkv_tile_order(base + ao.wqkv, base + ao.wqkv_t, (int)C, st)) != NMM_OK) return rc;
             }
+            if (fused_module_weights(g)) {
+                launch_pdl(wo_tail_kernel, 40, 256, 0, st, (const bf16 *)(base + ao.wo), (bf16 *)(base + ao.wo_tail), (int)C);
+                NMM_LAUNCHED("wo_tail_kernel");
+            }
         }
         PACK(lp.ff_norm_w, lo.ff_ln_w, NMM_F32, C, 1, 0); PACK(lp.ff_norm_b, lo.ff_ln_b, NMM_F32, C, 1, 0);
         PACK(lp.ff_proj_b, lo.b1, NMM_F32, 8 * C, 1, (int)(4 * C));
@@ -447,10 +526,54 @@ int nmm_pack_params(const nmm_shape *s, const nmm_params *src, void *packed, siz
     }
     PACK(src->proj_out_w, L.w_out, wd, C, C, 0); PACK(src->proj_out_b, L.b_out, NMM_F32, C, 1, 0);
 #undef PACK
+    if (fused_module_weights(g)) {
+        BiasList bl;
+        bl.n = g.A + 2;
+        bl.b[0] = (const float *)(base + L.b_in);
+        for (int i = 0; i < g.A; i++) bl.b[1 + i] = (const float *)(base + L.layer[0].attn[i].bo);
+        bl.b[g.A + 1] = (const float *)(base + L.layer[0].b2);
+        launch_pdl(cumulative_bias_kernel, (unsigned)ceil_div(C, 128), 128, 0, st, (float *)(base + L.cbias), bl, (int)C);
+        NMM_LAUNCHED("cumulative_bias_kernel");
+    }
     return NMM_OK;
 }
 
-int nmm_forward(const nmm_shape *s, const void *x, void *y, const void *packed, void *workspace, size_t workspace_bytes, void *stream) {
+static int forward_impl(const nmm_shape *s, const void *x, void *y, const void *packed, size_t packed_bytes, void *workspace, size_t workspace_bytes,
+                        void *stream, float *stage_dump, int stage_id);
+
+int nmm_forward(const nmm_shape *s, const void *x, void *y, const void *packed, size_t packed_bytes, void *workspace, size_t workspace_bytes,
+                void *stream) {
+    return forward_impl(s, x, y, packed, packed_bytes, workspace, workspace_bytes, stream, nullptr, -1);
+}
+
+int nmm_forward_stage(const nmm_shape *s, const void *x, void *y, const void *packed, size_t packed_bytes, void *workspace, size_t workspace_bytes,
+                      int32_t stage_id, float *stage_out, void *stream) {
+    if (!stage_out || stage_id < 0) return fail(NMM_ERR_BAD_ARG, "nmm_forward_stage needs a stage id and an output buffer");
+    int rc = validate(s);
+    if (rc != NMM_OK) return rc;
+    const Geo g = geo_of(s);
+    if (!fused_module_eligible(g, s, x)) return fail(NMM_ERR_UNSUPPORTED, "nmm_forward_stage: this call does not run on the fused module kernel");
+    if (stage_id > g.A + 1) return fail(NMM_ERR_BAD_ARG, "stage id %d outside [0, %d]", stage_id, g.A + 1);
+    return forward_impl(s, x, y, packed, packed_bytes, workspace, workspace_bytes, stream, stage_out, stage_id);
+}
+
+// The header nmm_pack_params writes for this geometry (reading the device copy back would need a synchronisation inside nmm_forward,
+// which must stay graph-capturable: nmm_forward checks packed_bytes, hosts / tests compare headers).
+int nmm_packed_header(const nmm_shape *s, void *out, size_t out_bytes) {
+    int rc = validate(s);
+    if (rc != NMM_OK) return rc;
+    if (!out || out_bytes < sizeof(PackedHeader)) return fail(NMM_ERR_BAD_ARG, "nmm_packed_header needs %zu bytes", sizeof(PackedHeader));
+    const Geo g = geo_of(s);
+    PackedHeader hd;
+    memset(&hd, 0, sizeof(hd));
+    hd.magic = PACKED_MAGIC; hd.abi = NMM_ABI_VERSION; hd.dtype = g.dtype; hd.ln_fold = g.ln_fold ? 1 : 0; hd.C = g.C; hd.heads = g.heads;
+    hd.layers = g.layers; hd.A = g.A; hd.max_len = g.max_len; hd.pos_enc = g.pos_enc ? 1 : 0; hd.total = packed_layout(g).total;
+    memcpy(out, &hd, sizeof(hd));
+    return NMM_OK;
+}
+
+static int forward_impl(const nmm_shape *s, const void *x, void *y, const void *packed, size_t packed_bytes, void *workspace, size_t workspace_bytes,
+                        void *stream, float *stage_dump, int stage_id) {
     int rc = validate(s);
     if (rc != NMM_OK) return rc;
     if (!x || !y || !packed || !workspace) return fail(NMM_ERR_BAD_ARG, "NULL argument");
@@ -459,6 +582,9 @@ int nmm_forward(const nmm_shape *s, const void *x, void *y, const void *packed, 
     const Geo g = geo_of(s);
     const PackedLayout L = packed_layout(g);
     const WorkLayout w = work_layout(g);
+    if (packed_bytes != L.total)
+        return fail(NMM_ERR_WORKSPACE, "packed parameter buffer of %zu bytes does not match this call's layout (%zu bytes): packed for another dtype / ln_fold / geometry?",
+                    packed_bytes, L.total);
     if (workspace_bytes < w.total) return fail(NMM_ERR_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, w.total);
     if (!aligned(workspace, 1024) || !aligned(packed, 256)) return fail(NMM_ERR_BAD_ARG, "workspace must be 1024-byte and packed params 256-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
@@ -471,6 +597,28 @@ int nmm_forward(const nmm_shape *s, const void *x, void *y, const void *packed, 
 
     // GroupNorm statistics over the whole tensor                                       motion_module.py:142
     if ((rc = launch_gn_stats(g, s, x, gn_partial, st)) != NMM_OK) return rc;
+
+    // C = 320, 8 heads, 8 / 16 frames, bf16: everything else of the call is ONE kernel (fused_module.cu)
+    if (fused_module_eligible(g, s, x)) {
+        FusedArgs fa;
+        memset(&fa, 0, sizeof(fa));
+        fa.x = x; fa.y = y;
+        fa.xsb = s->x_stride_b; fa.xsc = s->x_stride_c; fa.xsf = s->x_stride_f; fa.ysb = s->y_stride_b; fa.ysc = s->y_stride_c; fa.ysf = s->y_stride_f;
+        fa.B = g.B; fa.F = g.F; fa.P = g.P; fa.A = g.A;
+        fa.gn_partial = gn_partial; fa.gn_splits = gn_splits_of(g); fa.gn_count = (double)(g.C / NMM_GN_GROUPS) * g.P; fa.gn_eps = s->eps_gn;
+        fa.gn_w = F32(L.gn_w); fa.gn_b = F32(L.gn_b);
+        const LayerOff &lo = L.layer[0];
+        fa.w_in = pk + L.w_in; fa.w_out = pk + L.w_out; fa.w1 = pk + lo.w1; fa.w2 = pk + lo.w2;
+        for (int i = 0; i < g.A; i++) {
+            const AttnOff &ao = lo.attn[i];
+            fa.wqkv_t[i] = pk + ao.wqkv_t; fa.wo[i] = pk + ao.wo; fa.wo_tail[i] = pk + ao.wo_tail;
+            fa.ln_w[i] = F32(ao.ln_w); fa.ln_b[i] = F32(ao.ln_b); fa.pe[i] = g.pos_enc ? F32(ao.pe) : nullptr;
+        }
+        fa.ff_ln_w = F32(lo.ff_ln_w); fa.ff_ln_b = F32(lo.ff_ln_b); fa.b1 = F32(lo.b1); fa.cbias = F32(L.cbias); fa.b_out = F32(L.b_out);
+        fa.ln_eps = s->eps_ln;
+        fa.stage_dump = stage_dump; fa.stage_id = stage_id;
+        return launch_fused_module(fa, st);
+    }
 
     const int pc = chunk_positions(g);
     const size_t es = dtype_size(g.dtype);

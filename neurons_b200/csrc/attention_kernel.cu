@@ -440,7 +440,7 @@ static int launch_attn_mma(const Geo &g, const bf16 *qkv, bf16 *ctx, cudaStream_
         if (g.heads % hb == 0 && (hb * g.dh) % 64 == 0 && hb * g.dh <= 320) { HB = hb; break; }
     if (HB == 0) return -100;
     // SD1.5 levels (d_h = 40 / 80 / 160, head groups of exactly 320 channels): compile-time specialised kernel
-    if ((g.dh == 40 || g.dh == 80 || g.dh == 160) && HB * g.dh == 320 && (int64_t)g.F * g.P * 3 * g.C < (1ll << 31) && !getenv("NMM_ATTN_GENERIC")) {
+    if ((g.dh == 40 || g.dh == 80 || g.dh == 160) && HB * g.dh == 320 && (int64_t)g.F * g.P * 3 * g.C < (1ll << 31) && opt(NMM_OPT_ATTN_VARIANT) == 0) {
         const size_t row_b = (size_t)(3 * 320 + 8) * 2;
         static const int pb_env = getenv("NMM_ATTN_PB") ? atoi(getenv("NMM_ATTN_PB")) : 0;
         int PBf = pb_env > 0 ? pb_env : (int)((40 * 1024) / (g.F * row_b));
@@ -508,7 +508,7 @@ int launch_temporal_attention(const Geo &g, const void *qkv, void *ctx, cudaStre
     if (g.F > NMM_MAX_FRAMES) return fail(NMM_ERR_UNSUPPORTED, "frames %d > %d", g.F, NMM_MAX_FRAMES);
     const bool al = aligned(qkv, 16) && aligned(ctx, 16);
     if (g.dtype == NMM_BF16) {
-        if (al && !getenv("NMM_ATTN_SIMT")) {
+        if (al && opt(NMM_OPT_ATTN_VARIANT) != 2) {
             const int rc = launch_attn_mma(g, (const bf16 *)qkv, (bf16 *)ctx, st);
             if (rc != -100) return rc;
         }

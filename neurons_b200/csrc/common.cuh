@@ -30,8 +30,11 @@ extern std::atomic<uint64_t> g_launches;
                                __FILE__, __LINE__);                                                 \
     } while (0)
 
+// ---- run-time options (nmm_option; api.cu): one relaxed atomic load, initialised once from the environment ----
+int64_t opt(int option);
+
 // ---- optional per-kernel device timing (bench.py roofline): CUDA events around every launch, on the launch stream ----
-enum KernelId { K_GN_STATS = 0, K_GN_TOKENS, K_LAYERNORM, K_ATTENTION, K_LINEAR_SIMT, K_LINEAR_TC, K_PACK, K_COUNT };
+enum KernelId { K_GN_STATS = 0, K_GN_TOKENS, K_LAYERNORM, K_ATTENTION, K_LINEAR_SIMT, K_LINEAR_TC, K_PACK, K_FUSED_MODULE, K_COUNT };
 struct ProfScope {          // records start on construction, stop on destruction; no-op unless profiling is enabled
     int slot;
     cudaStream_t st;
@@ -273,6 +276,24 @@ inline double linear_bytes(const LinearArgs &a, int es) {
     }
     return b;
 }
+// The whole module in one kernel (fused_module.cu): C = 320, 8 heads, 8 or 16 frames, bf16.
+struct FusedArgs {
+    const void *x; void *y;
+    int64_t xsb, xsc, xsf, ysb, ysc, ysf;
+    int B, F, P, A;
+    const double *gn_partial; int gn_splits; double gn_count; float gn_eps;
+    const float *gn_w, *gn_b;
+    const void *w_in, *w_out, *w1, *w2;                     // packed bf16 weights (w1 GEGLU-interleaved)
+    const void *wqkv_t[NMM_MAX_ATTN], *wo[NMM_MAX_ATTN];    // q|k|v in head-pair tile order; to_out
+    const void *wo_tail[NMM_MAX_ATTN];                      // to_out columns 64-79 of every head pair, un-swizzled operand layout
+    const float *ln_w[NMM_MAX_ATTN], *ln_b[NMM_MAX_ATTN], *pe[NMM_MAX_ATTN];
+    const float *ff_ln_w, *ff_ln_b, *b1, *cbias, *b_out;
+    float ln_eps;
+    float *stage_dump; int stage_id;                         // tests: snapshot of the residual stream after stage stage_id (or null)
+};
+bool fused_module_weights(const Geo &g);
+bool fused_module_eligible(const Geo &g, const nmm_shape *s, const void *x);
+int launch_fused_module(const FusedArgs &a, cudaStream_t st);
 int launch_linear_simt(const LinearArgs &a, cudaStream_t st);     // fp32
 int launch_linear_tc(const LinearArgs &a, cudaStream_t st);       // bf16 tcgen05
 // parameter packing

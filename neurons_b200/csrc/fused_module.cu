@@ -1,0 +1,845 @@
+// The whole VanillaTemporalModule.forward at C = 320 (d_h = 40, 8 heads) in ONE persistent kernel
+// (motion_module.py:134-158 -> :210-222 -> :270-329; motion_module_new.py:258-287, :441-471, :497-518).
+//
+// Why one kernel: at C = 320 every stage of the multi-kernel pipeline is bound by HBM, not by the tensor cores -- one call moves
+// ~1.76 GB (fp32 residual stream read + written by each of the 4 residual GEMMs and 3 LayerNorms, q|k|v, the [N,4C] GEGLU
+// activations) for 295 GFLOP: 271 us of pure HBM time against 180 us of tensor time at the cuBLAS peak.  But the module is LOCAL to
+// a spatial position once the GroupNorm statistics are known: a tile of 128 tokens = (128 / F) positions x F frames can run
+// GroupNorm-apply -> proj_in -> [LN + PE -> QKV -> attention -> to_out (+h)] x A -> LN -> GEGLU -> ff_out (+h) -> proj_out (+x)
+// without ever leaving the SM.  HBM traffic per call drops to x (twice: statistics + tile) and y; only the 4.5 MB of weights
+// stream through shared memory (from L2), once per tile.
+//
+// Data placement per CTA (one 128-token tile at a time, persistent over tiles):
+//   TMEM   H  = columns [0, 320)    the fp32 RESIDUAL STREAM: proj_in writes it, to_out / ff_out accumulate onto it with the MMA's
+//                                   own accumulate input (the residual add costs nothing), proj_out finally overwrites it.  Biases
+//                                   are not added into TMEM: readers add the cumulative bias vector cb_k (packed at pack time).
+//          S  = columns [320, 512)  scratch accumulators: two 80-column buffers for the q / k / v units of a head pair,
+//                                   or one 128-column buffer for a GEGLU chunk.
+//   SMEM   A1  80 KB  the A operand of the current stage (GroupNorm tokens / LayerNorm output / bf16 h), K-major WITHOUT
+//                     swizzle: [40 chunks of 8 channels][128 rows][16 B] -- the thread that owns a row (= its TMEM lane)
+//                     writes 16-byte pieces at consecutive addresses across the warp: conflict-free.
+//          T   60 KB  q | k | v of one head pair as bf16 (30 chunks, rows position-major and XOR-swizzled for ldmatrix),
+//                     later the GEGLU activation chunks (3 x 16 KB, the A operand of the chained ff_out MMAs);
+//          CTX 20 KB  attention output of the head pair in A-operand layout;   T + CTX double as the x staging tile.
+//          RING 3 x 20 KB weight stages filled by TMA (128-byte swizzle; to_out's 16-channel tail by a 1-D bulk copy).
+// Row order inside the tile: m = f * ppt + pl (frame-major; ppt = 128 / F positions): a warp's 32 TMEM lanes are consecutive
+// positions of one or two frames, so the x loads and y stores of the NCHW tensors are full 32-byte sectors per channel.
+//
+// Roles (640 threads): warp 0 = TMA producer of the weight stream, warp 1 = tcgen05.mma issuer (one thread), warp 2 = TMEM
+// allocator, warps 4-19 = 16 "epilogue" warps (4 per TMEM lane quadrant) that do everything else: x load + GroupNorm apply,
+// LayerNorm (+PE) straight out of TMEM, q|k|v dumps, the mma.sync temporal attention, GEGLU, the y store.
+// The three programs (producer / MMA / epilogue) are the same static sequence per tile; they meet only at mbarriers.
+//
+// GEGLU (+) ff_out chaining: chunk j of the 4C axis (128 packed W1 rows = 64 value/gate pairs) is computed into S, GEGLU'd by the
+// epilogue warps into a 128 x 64 bf16 A tile, and immediately consumed by ff_out's K = 64 slice -- the [N, 4C] intermediate
+// never exists.  The MMA order G_0, G_1, F_0, G_2, F_1, ... keeps the tensor pipe busy while the epilogue works.
+#include <cuda.h>
+
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "attention_core.cuh"
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace nmm {
+
+constexpr int FM_C = 320, FM_DH = 40;
+constexpr int FM_EW = 16;                                  // epilogue warps
+constexpr int FM_THREADS = 128 + 32 * FM_EW;               // 640
+constexpr int FM_ETHREADS = 32 * FM_EW;
+constexpr uint32_t FM_CHUNK = 2048;                        // bytes of one 8-channel chunk of a 128-row operand tile
+constexpr uint32_t FM_A1 = 0;                              // 40 chunks
+constexpr uint32_t FM_T = 40 * FM_CHUNK;                   // 30 chunks (q: 0-9, k: 10-19, v: 20-29)
+constexpr uint32_t FM_CTX = FM_T + 30 * FM_CHUNK;          // 10 chunks
+constexpr int FM_STAGES = 3;
+constexpr uint32_t FM_STAGE_BYTES = 20480;
+constexpr uint32_t FM_RING = FM_CTX + 10 * FM_CHUNK;
+constexpr uint32_t FM_SCR = FM_RING + FM_STAGES * FM_STAGE_BYTES;     // 4 KB: GroupNorm mean/rstd table, LayerNorm partial sums
+constexpr uint32_t FM_BAR = FM_SCR + 4096;
+constexpr uint32_t FM_SMEM_BYTES = FM_BAR + 1024 + 1024;   // + alignment slack
+constexpr uint32_t FM_ACT_BYTES = 8 * FM_CHUNK;            // one GEGLU activation tile: 128 rows x 64 channels
+constexpr int FM_ACT_BUFS = 3;
+constexpr int FM_FF_CHUNKS = 4 * FM_C / 64;                // 20
+constexpr uint32_t FM_TAIL_BYTES = 2 * 160 * 16;           // to_out tail of one N half: [2 chunks][160 rows][16 B]
+// TMEM columns
+constexpr uint32_t FM_TM_H = 0, FM_TM_S = 320, FM_TM_COLS = 512;
+static_assert(FM_SMEM_BYTES <= 227 * 1024, "shared memory budget");
+
+struct FmMaps {                 // weight tensor maps (bf16, 64-element = 128-byte swizzled rows)
+    CUtensorMap win, wout;      // [320, 320],   box 160 rows
+    CUtensorMap w1;             // [2560, 320],  box 128 rows (GEGLU-interleaved rows, api.cu)
+    CUtensorMap w2;             // [320, 1280],  box 160 rows
+    CUtensorMap wqkv[NMM_MAX_ATTN];   // [960, 320] tile order (q|k|v rows of a head pair adjacent), box 80 rows
+    CUtensorMap wo[NMM_MAX_ATTN];     // [320, 320], box 160 rows
+};
+
+struct FmParams {
+    const bf16 *x; bf16 *y;
+    int64_t xsb, xsc, xsf, ysb, ysc, ysf;
+    int B, F, P, A, ppt, tiles_per_b;
+    int64_t ntiles;
+    // GroupNorm
+    const double *gn_partial; int gn_splits; double gn_count; float gn_eps;
+    const float *gn_w, *gn_b;
+    // per attention block
+    const float *ln_w[NMM_MAX_ATTN], *ln_b[NMM_MAX_ATTN], *pe[NMM_MAX_ATTN];
+    const bf16 *wo_tail[NMM_MAX_ATTN];            // [4 pairs][2 halves][2 chunks][160 rows][8]
+    // feed-forward
+    const float *ff_ln_w, *ff_ln_b, *b1;
+    const float *cbias;                           // [A + 2][320] cumulative biases: b_in, + bo_0, ..., + b2
+    const float *b_out;
+    float ln_eps, scale_log2e;
+    float *stage_dump; int stage_id;              // tests: fp32 [N, 320] snapshot of the residual stream after stage `stage_id`
+};
+
+// ---- small device helpers -----------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fm_sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 fm_lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t fm_lds_u16(uint32_t addr) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
+    return (uint32_t)v;
+}
+__device__ __forceinline__ void fm_sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void fm_bar_epi() { asm volatile("bar.sync 1, %0;" ::"n"(FM_ETHREADS) : "memory"); }      // all 16 epilogue warps
+__device__ __forceinline__ void fm_bar_quad(int q) { asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory"); }    // the 4 warps of a lane quadrant
+
+// row of (local position pl, frame f) inside the q|k|v tile: position-major (the F frames of a position are F consecutive
+// 16-byte pieces of a chunk -> one ldmatrix reads 128 contiguous bytes) with the low 3 frame bits XOR-ed by the position, so that
+// the dump -- whose lanes are consecutive POSITIONS of one frame -- is conflict-free too.
+template <int F>
+__device__ __forceinline__ uint32_t fm_trow(int pl, int f) { return (uint32_t)(pl * F + (f & 8) + ((f & 7) ^ (pl & 7))); }
+
+// ---- temporal attention on the q|k|v tile (same arithmetic as attention_core.cuh; other addressing) ----------------------------------
+// One warp, NP problems = (position pl[u], head hd[u] of the pair).  O (bf16) overwrites the problem's q slot.
+template <int F, int NP>
+__device__ __forceinline__ void fm_attention(uint32_t T, const int (&pl)[NP], const int (&hd)[NP], int lane, float scale_log2e) {
+    constexpr int NT = F / 8;
+    const int lrow = lane & 7, lmat = lane >> 3;
+    const int crow = lane >> 2, ccol = (lane & 3) * 2;
+    uint32_t qb[NP], kb[NP], vb[NP];          // chunk bases of the problem's head
+    uint32_t r_lo[NP], r_hi[NP];              // tile-row byte offsets of frame lrow / lrow + 8
+#pragma unroll
+    for (int u = 0; u < NP; u++) {
+        qb[u] = T + (uint32_t)(hd[u] * 5) * FM_CHUNK;
+        kb[u] = qb[u] + 10 * FM_CHUNK;
+        vb[u] = qb[u] + 20 * FM_CHUNK;
+        r_lo[u] = fm_trow<F>(pl[u], lrow) * 16;
+        r_hi[u] = F == 16 ? fm_trow<F>(pl[u], lrow + 8) * 16 : 0u;
+    }
+    float s[NP][NT][4];
+#pragma unroll
+    for (int u = 0; u < NP; u++)
+#pragma unroll
+        for (int j = 0; j < NT; j++) { s[u][j][0] = s[u][j][1] = s[u][j][2] = s[u][j][3] = 0.f; }
+    // ---- S = Q K^T ----
+    if constexpr (F == 8) {
+#pragma unroll
+        for (int u = 0; u < NP; u++) {
+            uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
+            ldsm_x4(qb[u] + (uint32_t)lmat * FM_CHUNK + r_lo[u], a0, a1, a2, a3);        // chunks 0-3 of q, frames 0-7
+            ldsm_x4(kb[u] + (uint32_t)lmat * FM_CHUNK + r_lo[u], b0, b1, b2, b3);
+            mma_k16(s[u][0], a0, 0u, a1, 0u, b0, b1);
+            mma_k16(s[u][0], a2, 0u, a3, 0u, b2, b3);
+        }
+#pragma unroll
+        for (int u = 0; u < NP; u++) {
+            uint32_t a0, b0;
+            ldsm_x1(qb[u] + 4 * FM_CHUNK + r_lo[u], a0);                                   // channels 32-39
+            ldsm_x1(kb[u] + 4 * FM_CHUNK + r_lo[u], b0);
+            mma_k8(s[u][0], a0, 0u, b0);
+        }
+    } else {
+#pragma unroll
+        for (int c0 = 0; c0 < 4; c0 += 2) {
+#pragma unroll
+            for (int u = 0; u < NP; u++) {
+                uint32_t a0, a1, a2, a3;
+                // matrices: (frames 0-7, chunk c0), (frames 8-15, c0), (frames 0-7, c0 + 1), (frames 8-15, c0 + 1)
+                ldsm_x4(qb[u] + (uint32_t)(c0 + (lmat >> 1)) * FM_CHUNK + ((lmat & 1) ? r_hi[u] : r_lo[u]), a0, a1, a2, a3);
+#pragma unroll
+                for (int j = 0; j < NT; j++) {
+                    uint32_t b0, b1;
+                    ldsm_x2(kb[u] + (uint32_t)(c0 + (lmat & 1)) * FM_CHUNK + (j ? r_hi[u] : r_lo[u]), b0, b1);
+                    mma_k16(s[u][j], a0, a1, a2, a3, b0, b1);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < NP; u++) {
+            uint32_t a0, a1;
+            ldsm_x2(qb[u] + 4 * FM_CHUNK + ((lmat & 1) ? r_hi[u] : r_lo[u]), a0, a1);
+#pragma unroll
+            for (int j = 0; j < NT; j++) {
+                uint32_t b0;
+                ldsm_x1(kb[u] + 4 * FM_CHUNK + (j ? r_hi[u] : r_lo[u]), b0);
+                mma_k8(s[u][j], a0, a1, b0);
+            }
+        }
+    }
+    // ---- softmax over the keys (fp32, base-2), rows crow (regs 0,1) and crow + 8 (regs 2,3; F == 16) ----
+    uint32_t ph[NP][4], pw[NP][4];
+#pragma unroll
+    for (int u = 0; u < NP; u++) {
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < NT; j++) { mx0 = fmaxf(mx0, fmaxf(s[u][j][0], s[u][j][1])); mx1 = fmaxf(mx1, fmaxf(s[u][j][2], s[u][j][3])); }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        if constexpr (F == 16) { mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2)); }
+        float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < NT; j++) {
+            s[u][j][0] = exp2f((s[u][j][0] - mx0) * scale_log2e); s[u][j][1] = exp2f((s[u][j][1] - mx0) * scale_log2e);
+            sum0 += s[u][j][0] + s[u][j][1];
+            if constexpr (F == 16) {
+                s[u][j][2] = exp2f((s[u][j][2] - mx1) * scale_log2e); s[u][j][3] = exp2f((s[u][j][3] - mx1) * scale_log2e);
+                sum1 += s[u][j][2] + s[u][j][3];
+            }
+        }
+        sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+        if constexpr (F == 16) { sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2); }
+        const float inv0 = 1.0f / sum0, inv1 = (F == 16) ? 1.0f / sum1 : 0.f;
+        ph[u][0] = ph[u][1] = ph[u][2] = ph[u][3] = 0u; pw[u][0] = pw[u][1] = pw[u][2] = pw[u][3] = 0u;
+        split_bf16x2(s[u][0][0] * inv0, s[u][0][1] * inv0, ph[u][0], pw[u][0]);
+        if constexpr (F == 16) {
+            split_bf16x2(s[u][0][2] * inv1, s[u][0][3] * inv1, ph[u][1], pw[u][1]);
+            split_bf16x2(s[u][1][0] * inv0, s[u][1][1] * inv0, ph[u][2], pw[u][2]);
+            split_bf16x2(s[u][1][2] * inv1, s[u][1][3] * inv1, ph[u][3], pw[u][3]);
+        }
+    }
+    __syncwarp();                                    // every lane has read its q rows: they may be overwritten with O
+    // O (frame `row`, head-dim columns col, col + 1 packed in v) -> the problem's q slot
+    auto store = [&](int u, int row, int col, uint32_t v) {
+        fm_sts32(qb[u] + (uint32_t)(col >> 3) * FM_CHUNK + fm_trow<F>(pl[u], row) * 16 + (uint32_t)((col & 7) * 2), v);
+    };
+    if constexpr (F == 8) {
+        static_assert(F != 8 || NP == 2, "8 frames: two problems per warp share every m16n8k16 through a block-diagonal P");
+        // ldmatrix matrices 0, 2 <- problem 0's V rows (keys 0-7), 1, 3 <- problem 1's
+        const uint32_t vsel = (lmat & 1) ? vb[NP - 1] + r_lo[NP - 1] : vb[0] + r_lo[0];
+#pragma unroll
+        for (int n0 = 0; n0 < FM_DH; n0 += 16) {
+            uint32_t bv[4] = {0u, 0u, 0u, 0u};
+            if (n0 + 16 <= FM_DH) ldsm_x4_t(vsel + (uint32_t)(n0 / 8 + (lmat >> 1)) * FM_CHUNK, bv[0], bv[1], bv[2], bv[3]);
+            else ldsm_x2_t(vsel + (uint32_t)(n0 / 8) * FM_CHUNK, bv[0], bv[1]);
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                if (n0 + 8 * q < FM_DH) {
+                    float o[4] = {0.f, 0.f, 0.f, 0.f};
+                    mma_k16(o, ph[0][0], 0u, 0u, ph[NP - 1][0], bv[2 * q], bv[2 * q + 1]);
+                    mma_k16(o, pw[0][0], 0u, 0u, pw[NP - 1][0], bv[2 * q], bv[2 * q + 1]);
+                    store(0, crow, ccol + n0 + 8 * q, pack_bf16x2(o[0], o[1]));
+                    store(NP - 1, crow, ccol + n0 + 8 * q, pack_bf16x2(o[2], o[3]));
+                }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int n0 = 0; n0 + 16 <= FM_DH; n0 += 16) {
+#pragma unroll
+            for (int u = 0; u < NP; u++) {
+                uint32_t bv[4];
+                // matrices: (keys 0-7, n0), (keys 8-15, n0), (keys 0-7, n0 + 8), (keys 8-15, n0 + 8)
+                ldsm_x4_t(vb[u] + (uint32_t)(n0 / 8 + (lmat >> 1)) * FM_CHUNK + ((lmat & 1) ? r_hi[u] : r_lo[u]), bv[0], bv[1], bv[2], bv[3]);
+#pragma unroll
+                for (int q = 0; q < 2; q++) {
+                    float o[4] = {0.f, 0.f, 0.f, 0.f};
+                    mma_k16(o, ph[u][0], ph[u][1], ph[u][2], ph[u][3], bv[2 * q], bv[2 * q + 1]);
+                    mma_k16(o, pw[u][0], pw[u][1], pw[u][2], pw[u][3], bv[2 * q], bv[2 * q + 1]);
+                    store(u, crow, ccol + n0 + 8 * q, pack_bf16x2(o[0], o[1]));
+                    store(u, crow + 8, ccol + n0 + 8 * q, pack_bf16x2(o[2], o[3]));
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < NP; u++) {
+            uint32_t b0, b1;
+            ldsm_x2_t(vb[u] + 4 * FM_CHUNK + ((lmat & 1) ? r_hi[u] : r_lo[u]), b0, b1);
+            float o[4] = {0.f, 0.f, 0.f, 0.f};
+            mma_k16(o, ph[u][0], ph[u][1], ph[u][2], ph[u][3], b0, b1);
+            mma_k16(o, pw[u][0], pw[u][1], pw[u][2], pw[u][3], b0, b1);
+            store(u, crow, ccol + 32, pack_bf16x2(o[0], o[1]));
+            store(u, crow + 8, ccol + 32, pack_bf16x2(o[2], o[3]));
+        }
+    }
+}
+
+// ---- the kernel -----------------------------------------------------------------------------------------------------------------------
+template <int F>
+__global__ void __launch_bounds__(FM_THREADS, 1) fused_module_kernel(const __grid_constant__ FmMaps maps, const FmParams p) {
+    constexpr int PPT = 128 / F;                       // positions per tile
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t sb = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char *sm = smem_raw + (sb - ptx::smem_u32(smem_raw));
+    const uint32_t A1 = sb + FM_A1, T = sb + FM_T, CTX = sb + FM_CTX, RING = sb + FM_RING, BAR = sb + FM_BAR;
+    float *scr = reinterpret_cast<float *>(sm + FM_SCR);
+    auto wfull = [&](int s) { return BAR + 8u * s; };
+    auto wempty = [&](int s) { return BAR + 8u * (3 + s); };
+    const uint32_t a1_ready = BAR + 8u * 6, h_done = BAR + 8u * 7;
+    auto s_full = [&](int b) { return BAR + 8u * (8 + b); };
+    auto s_free = [&](int b) { return BAR + 8u * (10 + b); };
+    const uint32_t ctx_ready = BAR + 8u * 12, ctx_free = BAR + 8u * 13, g_full = BAR + 8u * 14, g_free = BAR + 8u * 15;
+    auto act_ready = [&](int b) { return BAR + 8u * (16 + b); };
+    auto act_free = [&](int b) { return BAR + 8u * (19 + b); };
+    const uint32_t tmem_slot = BAR + 8u * 24;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&maps.win); ptx::prefetch_tensormap(&maps.wout); ptx::prefetch_tensormap(&maps.w1); ptx::prefetch_tensormap(&maps.w2);
+        for (int i = 0; i < p.A; i++) { ptx::prefetch_tensormap(&maps.wqkv[i]); ptx::prefetch_tensormap(&maps.wo[i]); }
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < FM_STAGES; s++) { ptx::mbar_init(wfull(s), 1); ptx::mbar_init(wempty(s), 1); }
+        ptx::mbar_init(a1_ready, FM_EW); ptx::mbar_init(h_done, 1);
+        for (int b = 0; b < 2; b++) { ptx::mbar_init(s_full(b), 1); ptx::mbar_init(s_free(b), FM_EW); }
+        ptx::mbar_init(ctx_ready, FM_EW); ptx::mbar_init(ctx_free, 1);
+        ptx::mbar_init(g_full, 1); ptx::mbar_init(g_free, FM_EW);
+        for (int b = 0; b < FM_ACT_BUFS; b++) { ptx::mbar_init(act_ready(b), FM_EW); ptx::mbar_init(act_free(b), 1); }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 2) ptx::tmem_alloc<1>(tmem_slot, FM_TM_COLS);
+    pdl_wait();                       // everything above overlapped the previous kernel (gn_stats) -- now its sums are visible
+    pdl_launch_dependents();
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    const int64_t tile0 = blockIdx.x, tstep = gridDim.x;
+    const int A = p.A;
+
+    if (warp == 0) {
+        // =========================== weight producer ===========================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            auto begin = [&](uint32_t bytes) {
+                ptx::mbar_wait(wempty(stage), phase ^ 1u);
+                ptx::mbar_expect_tx(wfull(stage), bytes);
+            };
+            auto next = [&]() { if (++stage == FM_STAGES) { stage = 0; phase ^= 1u; } };
+            auto box = [&](const CUtensorMap *m, uint32_t off, int k_elem, int row) {
+                ptx::tma_load_2d(m, wfull(stage), RING + (uint32_t)stage * FM_STAGE_BYTES + off, k_elem, row);
+            };
+            auto gemm320 = [&](const CUtensorMap *m) {           // K = 320, N = 320: 5 k-blocks x 2 halves of 160 rows
+                for (int kb = 0; kb < 5; kb++)
+                    for (int half = 0; half < 2; half++) { begin(160 * 128); box(m, 0, kb * 64, half * 160); next(); }
+            };
+            for (int64_t t = tile0; t < p.ntiles; t += tstep) {
+                gemm320(&maps.win);
+                for (int i = 0; i < A; i++) {
+                    auto tproj = [&](int hp) {                   // to_out slice of head pair hp: K = 64 + 16
+                        for (int half = 0; half < 2; half++) { begin(160 * 128); box(&maps.wo[i], 0, hp * 80, half * 160); next(); }
+                        begin(2 * FM_TAIL_BYTES);
+                        ptx::bulk_load_1d(RING + (uint32_t)stage * FM_STAGE_BYTES, p.wo_tail[i] + (size_t)hp * (2 * FM_TAIL_BYTES / 2), 2 * FM_TAIL_BYTES, wfull(stage));
+                        next();
+                    };
+                    for (int hp = 0; hp < 4; hp++) {
+                        for (int s = 0; s < 3; s++) {            // q / k / v unit of the pair: 80 rows, K = 320 as fills of 2 + 2 + 1 k-blocks
+                            const int row = hp * 240 + s * 80;
+                            for (int f = 0; f < 3; f++) {
+                                const int nkb = f < 2 ? 2 : 1;
+                                begin((uint32_t)nkb * 80 * 128);
+                                for (int j = 0; j < nkb; j++) box(&maps.wqkv[i], (uint32_t)j * 80 * 128, (2 * f + j) * 64, row);
+                                next();
+                            }
+                            if (s == 1 && hp > 0) tproj(hp - 1);
+                        }
+                    }
+                    tproj(3);
+                }
+                for (int j = 0; j <= FM_FF_CHUNKS; j++) {
+                    if (j < FM_FF_CHUNKS)
+                        for (int kb = 0; kb < 5; kb++) { begin(128 * 128); box(&maps.w1, 0, kb * 64, j * 128); next(); }
+                    if (j > 0)
+                        for (int half = 0; half < 2; half++) { begin(160 * 128); box(&maps.w2, 0, (j - 1) * 64, half * 160); next(); }
+                }
+                gemm320(&maps.wout);
+            }
+        }
+    } else if (warp == 1) {
+        // =========================== MMA issuer ===========================
+        if (lane == 0) {
+            const uint32_t id160 = ptx::umma_idesc_bf16(128, 160), id80 = ptx::umma_idesc_bf16(128, 80), id128 = ptx::umma_idesc_bf16(128, 128);
+            int stage = 0; uint32_t phase = 0;
+            uint32_t n_a1 = 0, n_ctx = 0, n_unit = 0, n_g = 0;   // running use counters of the barriers (phase = count parity)
+            auto wait_fill = [&]() { ptx::mbar_wait(wfull(stage), phase); ptx::tc_fence_after(); };
+            auto release = [&]() { ptx::umma_commit<1>(wempty(stage)); if (++stage == FM_STAGES) { stage = 0; phase ^= 1u; } };
+            auto stage_addr = [&]() { return RING + (uint32_t)stage * FM_STAGE_BYTES; };
+            auto adesc = [&](uint32_t base, int chunk) { return ptx::umma_smem_desc_interleave(base + (uint32_t)chunk * FM_CHUNK, FM_CHUNK, 128); };
+            auto wait_a1 = [&]() { ptx::mbar_wait(a1_ready, n_a1 & 1u); n_a1++; ptx::tc_fence_after(); };
+            auto gemm320 = [&](bool accumulate) {                // H (+)= A1 . W^T
+                for (int kb = 0; kb < 5; kb++)
+                    for (int half = 0; half < 2; half++) {
+                        wait_fill();
+                        const uint64_t bd = ptx::umma_smem_desc_sw128(stage_addr());
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                            ptx::umma_bf16<1>(tmem_base + FM_TM_H + half * 160, adesc(A1, kb * 8 + 2 * k), bd + (uint64_t)(k * 2), id160, (accumulate || (kb | k) != 0) ? 1u : 0u);
+                        release();
+                    }
+            };
+            for (int64_t t = tile0; t < p.ntiles; t += tstep) {
+                wait_a1();                                       // GroupNorm tokens are in A1 (and the previous tile's y epilogue is done with H)
+                gemm320(false);
+                ptx::umma_commit<1>(h_done);
+                for (int i = 0; i < A; i++) {
+                    wait_a1();                                   // LayerNorm_i(h) + pe
+                    auto tproj = [&](bool last) {                // H += ctx . Wo[:, pair]^T
+                        ptx::mbar_wait(ctx_ready, n_ctx & 1u); n_ctx++;
+                        ptx::tc_fence_after();
+                        for (int half = 0; half < 2; half++) {
+                            wait_fill();
+                            const uint64_t bd = ptx::umma_smem_desc_sw128(stage_addr());
+#pragma unroll
+                            for (int k = 0; k < 4; k++)
+                                ptx::umma_bf16<1>(tmem_base + FM_TM_H + half * 160, adesc(CTX, 2 * k), bd + (uint64_t)(k * 2), id160, 1u);
+                            release();
+                        }
+                        wait_fill();
+                        for (int half = 0; half < 2; half++)     // channels 64-79 of the pair: un-swizzled 16-channel weight tail
+                            ptx::umma_bf16<1>(tmem_base + FM_TM_H + half * 160, adesc(CTX, 8),
+                                              ptx::umma_smem_desc_interleave(stage_addr() + (uint32_t)half * FM_TAIL_BYTES, 160 * 16, 128), id160, 1u);
+                        release();
+                        ptx::umma_commit<1>(ctx_free);
+                        if (last) ptx::umma_commit<1>(h_done);
+                    };
+                    for (int hp = 0; hp < 4; hp++) {
+                        for (int s = 0; s < 3; s++) {
+                            const int b = n_unit & 1;
+                            ptx::mbar_wait(s_free(b), ((n_unit >> 1) & 1u) ^ 1u);      // the epilogue has drained this buffer's previous unit
+                            ptx::tc_fence_after();
+                            for (int f = 0; f < 3; f++) {
+                                const int nkb = f < 2 ? 2 : 1;
+                                wait_fill();
+                                for (int j = 0; j < nkb; j++) {
+                                    const int kb = 2 * f + j;
+                                    const uint64_t bd = ptx::umma_smem_desc_sw128(stage_addr() + (uint32_t)j * 80 * 128);
+#pragma unroll
+                                    for (int k = 0; k < 4; k++)
+                                        ptx::umma_bf16<1>(tmem_base + FM_TM_S + b * 80, adesc(A1, kb * 8 + 2 * k), bd + (uint64_t)(k * 2), id80, (kb | k) != 0 ? 1u : 0u);
+                                }
+                                release();
+                            }
+                            ptx::umma_commit<1>(s_full(b));
+                            n_unit++;
+                            if (s == 1 && hp > 0) tproj(false);
+                        }
+                    }
+                    tproj(true);
+                }
+                wait_a1();                                       // LayerNorm_ff(h)
+                for (int j = 0; j <= FM_FF_CHUNKS; j++) {
+                    if (j < FM_FF_CHUNKS) {                      // G_j: S = A1 . W1[chunk j]^T
+                        ptx::mbar_wait(g_free, (n_g & 1u) ^ 1u);
+                        ptx::tc_fence_after();
+                        for (int kb = 0; kb < 5; kb++) {
+                            wait_fill();
+                            const uint64_t bd = ptx::umma_smem_desc_sw128(stage_addr());
+#pragma unroll
+                            for (int k = 0; k < 4; k++)
+                                ptx::umma_bf16<1>(tmem_base + FM_TM_S, adesc(A1, kb * 8 + 2 * k), bd + (uint64_t)(k * 2), id128, (kb | k) != 0 ? 1u : 0u);
+                            release();
+                        }
+                        ptx::umma_commit<1>(g_full);
+                        n_g++;
+                    }
+                    if (j > 0) {                                 // F_{j-1}: H += act . W2[:, chunk j-1]^T
+                        const uint32_t g = n_g - (j < FM_FF_CHUNKS ? 2u : 1u);       // global index of chunk j - 1
+                        const int b = (int)(g % FM_ACT_BUFS);
+                        ptx::mbar_wait(act_ready(b), (g / FM_ACT_BUFS) & 1u);
+                        ptx::tc_fence_after();
+                        const uint32_t act = T + (uint32_t)b * FM_ACT_BYTES;
+                        for (int half = 0; half < 2; half++) {
+                            wait_fill();
+                            const uint64_t bd = ptx::umma_smem_desc_sw128(stage_addr());
+#pragma unroll
+                            for (int k = 0; k < 4; k++)
+                                ptx::umma_bf16<1>(tmem_base + FM_TM_H + half * 160, adesc(act, 2 * k), bd + (uint64_t)(k * 2), id160, 1u);
+                            release();
+                        }
+                        ptx::umma_commit<1>(act_free(b));
+                    }
+                }
+                ptx::umma_commit<1>(h_done);
+                wait_a1();                                       // bf16(h)
+                gemm320(false);                                  // proj_out overwrites H
+                ptx::umma_commit<1>(h_done);
+            }
+        }
+    } else if (warp >= 4) {
+        // =========================== epilogue warps ===========================
+        const int ew = warp - 4, q = ew & 3, sub = ew >> 2;
+        const int et = (int)threadIdx.x - 128;
+        const int m = q * 32 + lane;                             // tile row = TMEM lane
+        const int f_m = m / PPT, pl_m = m % PPT;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+        uint32_t n_hd = 0, n_unit = 0, n_ctx = 0, n_g = 0;
+        auto wait_h = [&]() { ptx::mbar_wait(h_done, n_hd & 1u); n_hd++; ptx::tc_fence_after(); };
+        auto publish_a1 = [&]() {                                // generic-proxy writes of A1 -> visible to the tensor core, then arrive
+            ptx::fence_proxy_async();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(a1_ready);
+        };
+        // LayerNorm (+ pe) of the residual stream (TMEM H + cumulative bias) -> A1.  Each thread: its row, 80 of the 320 columns.
+        auto layer_norm = [&](const float *__restrict__ cb, const float *__restrict__ gamma, const float *__restrict__ beta, const float *__restrict__ pe) {
+            const int cbeg = 80 * sub;
+            const uint32_t h0 = ptx::tmem_ld1(t_lane + FM_TM_H);
+            ptx::tmem_ld_wait();
+            const float x0 = __uint_as_float(h0) + __ldg(cb);    // shift by the row's first element: keeps the one-pass variance well conditioned
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                uint32_t r[16];
+                ptx::tmem_ld16(t_lane + FM_TM_H + cbeg + 16 * k, r);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int j4 = 0; j4 < 4; j4++) {
+                    const float4 c4 = __ldg(reinterpret_cast<const float4 *>(cb + cbeg + 16 * k) + j4);
+                    const float d0 = __uint_as_float(r[4 * j4]) + c4.x - x0, d1 = __uint_as_float(r[4 * j4 + 1]) + c4.y - x0;
+                    const float d2 = __uint_as_float(r[4 * j4 + 2]) + c4.z - x0, d3 = __uint_as_float(r[4 * j4 + 3]) + c4.w - x0;
+                    s1 += (d0 + d1) + (d2 + d3);
+                    s2 = fmaf(d0, d0, s2); s2 = fmaf(d1, d1, s2); s2 = fmaf(d2, d2, s2); s2 = fmaf(d3, d3, s2);
+                }
+            }
+            reinterpret_cast<float2 *>(scr)[m * 4 + sub] = make_float2(s1, s2);
+            fm_bar_quad(q);
+            float S1 = 0.f, S2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; i++) { const float2 t2 = reinterpret_cast<const float2 *>(scr)[m * 4 + i]; S1 += t2.x; S2 += t2.y; }
+            const float md = S1 * (1.0f / FM_C);
+            const float mean = x0 + md;
+            const float rstd = rsqrtf(fmaxf(S2 * (1.0f / FM_C) - md * md, 0.f) + p.ln_eps);
+            const float *per = pe ? pe + (size_t)f_m * FM_C : nullptr;
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                const int c0 = cbeg + 16 * k;
+                uint32_t r[16];
+                ptx::tmem_ld16(t_lane + FM_TM_H + c0, r);
+                ptx::tmem_ld_wait();
+                float o[16];
+#pragma unroll
+                for (int j4 = 0; j4 < 4; j4++) {
+                    const float4 c4 = __ldg(reinterpret_cast<const float4 *>(cb + c0) + j4);
+                    const float4 gm = __ldg(reinterpret_cast<const float4 *>(gamma + c0) + j4);
+                    const float4 bt = __ldg(reinterpret_cast<const float4 *>(beta + c0) + j4);
+                    o[4 * j4] = fmaf((__uint_as_float(r[4 * j4]) + c4.x - mean) * rstd, gm.x, bt.x);
+                    o[4 * j4 + 1] = fmaf((__uint_as_float(r[4 * j4 + 1]) + c4.y - mean) * rstd, gm.y, bt.y);
+                    o[4 * j4 + 2] = fmaf((__uint_as_float(r[4 * j4 + 2]) + c4.z - mean) * rstd, gm.z, bt.z);
+                    o[4 * j4 + 3] = fmaf((__uint_as_float(r[4 * j4 + 3]) + c4.w - mean) * rstd, gm.w, bt.w);
+                    if (per) {
+                        const float4 pp = __ldg(reinterpret_cast<const float4 *>(per + c0) + j4);
+                        o[4 * j4] += pp.x; o[4 * j4 + 1] += pp.y; o[4 * j4 + 2] += pp.z; o[4 * j4 + 3] += pp.w;
+                    }
+                }
+                const uint32_t dst = A1 + (uint32_t)(c0 >> 3) * FM_CHUNK + (uint32_t)m * 16;
+                fm_sts128(dst, pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+                fm_sts128(dst + FM_CHUNK, pack_bf16x2(o[8], o[9]), pack_bf16x2(o[10], o[11]), pack_bf16x2(o[12], o[13]), pack_bf16x2(o[14], o[15]));
+            }
+            publish_a1();
+        };
+        // tests: snapshot of the residual stream (H + cumulative bias) of this tile's rows
+        auto dump_stage = [&](int id, const float *__restrict__ cb, int64_t token) {
+            if (p.stage_dump == nullptr || p.stage_id != id) return;
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                const int c0 = 80 * sub + 16 * k;
+                uint32_t r[16];
+                ptx::tmem_ld16(t_lane + FM_TM_H + c0, r);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; j++) p.stage_dump[token * FM_C + c0 + j] = __uint_as_float(r[j]) + __ldg(cb + c0 + j);
+            }
+        };
+
+        for (int64_t t = tile0; t < p.ntiles; t += tstep) {
+            const int b = (int)(t / p.tiles_per_b);
+            const int p0 = (int)(t - (int64_t)b * p.tiles_per_b) * PPT;
+            const int64_t token = ((int64_t)b * F + f_m) * p.P + p0 + pl_m;        // this thread's row in (b, f, p) token order
+            // ---- phase 0: x tile -> staging [c][m] (raw bf16), GroupNorm statistics of the F images -> scr ----
+            {
+                const uint32_t stg = T;                              // T + CTX = 80 KB = [320 channels][128 rows] bf16
+                const bf16 *xb = p.x + (int64_t)b * p.xsb + p0;
+                uint4 v[10];
+#pragma unroll
+                for (int i = 0; i < 10; i++) {                       // 5120 pieces of 8 positions: all loads first
+                    const int it = et + FM_ETHREADS * i;
+                    const int c = it >> 4, piece = it & 15;
+                    const int m0 = piece * 8, f = m0 / PPT, pl0 = m0 % PPT;
+                    v[i] = __ldg(reinterpret_cast<const uint4 *>(xb + (int64_t)c * p.xsc + (int64_t)f * p.xsf + pl0));
+                }
+                for (int i = et; i < F * NMM_GN_GROUPS; i += FM_ETHREADS) {
+                    float mean, rstd;
+                    gn_finalize_one(p.gn_partial, (b * F + i / NMM_GN_GROUPS) * NMM_GN_GROUPS + i % NMM_GN_GROUPS, p.gn_splits, p.gn_count, p.gn_eps, mean, rstd);
+                    scr[2 * i] = mean; scr[2 * i + 1] = rstd;
+                }
+#pragma unroll
+                for (int i = 0; i < 10; i++) {
+                    const int it = et + FM_ETHREADS * i;
+                    fm_sts128(stg + (uint32_t)(it >> 4) * 256 + (uint32_t)(it & 15) * 16, v[i].x, v[i].y, v[i].z, v[i].w);
+                }
+                fm_bar_epi();
+                // staging -> A1: normalise + affine, 8 channels of this row at a time
+                for (int ck = 10 * sub; ck < 10 * sub + 10; ck++) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int i2 = 0; i2 < 4; i2++) {
+                        float o2[2];
+#pragma unroll
+                        for (int e = 0; e < 2; e++) {
+                            const int c = ck * 8 + 2 * i2 + e;
+                            const int grp = c / (FM_C / NMM_GN_GROUPS);
+                            const float mu = scr[2 * (f_m * NMM_GN_GROUPS + grp)], rs = scr[2 * (f_m * NMM_GN_GROUPS + grp) + 1];
+                            const float ca = rs * __ldg(p.gn_w + c), cbv = __ldg(p.gn_b + c) - mu * ca;
+                            const float xv = __uint_as_float(fm_lds_u16(stg + (uint32_t)c * 256 + (uint32_t)m * 2) << 16);
+                            o2[e] = fmaf(xv, ca, cbv);
+                        }
+                        w[i2] = pack_bf16x2(o2[0], o2[1]);
+                    }
+                    fm_sts128(A1 + (uint32_t)ck * FM_CHUNK + (uint32_t)m * 16, w[0], w[1], w[2], w[3]);
+                }
+                publish_a1();
+            }
+            wait_h();                                                // proj_in done: H = tokens . W_in^T
+            dump_stage(0, p.cbias, token);
+            // ---- attention blocks ----
+            for (int i = 0; i < A; i++) {
+                layer_norm(p.cbias + i * FM_C, p.ln_w[i], p.ln_b[i], p.pe[i]);
+                for (int hp = 0; hp < 4; hp++) {
+                    for (int s = 0; s < 3; s++) {
+                        // dump this warp's share of the unit's 80 accumulator columns as bf16 into the q|k|v tile
+                        const int bsel = n_unit & 1;
+                        ptx::mbar_wait(s_full(bsel), (n_unit >> 1) & 1u);
+                        n_unit++;
+                        ptx::tc_fence_after();
+                        const int cb0 = sub < 2 ? 24 * sub : 48 + 16 * (sub - 2);           // 3 + 3 + 2 + 2 chunks
+                        const uint32_t tcol = t_lane + FM_TM_S + bsel * 80 + cb0;
+                        uint32_t ra[16], rb[8];
+                        ptx::tmem_ld16(tcol, ra);
+                        if (sub < 2) ptx::tmem_ld8(tcol + 16, rb);
+                        ptx::tmem_ld_wait();
+                        ptx::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(s_free(bsel));                       // the accumulator buffer may be overwritten
+                        const uint32_t dst = T + (uint32_t)(s * 10 + (cb0 >> 3)) * FM_CHUNK + fm_trow<F>(pl_m, f_m) * 16;
+#define FM_PK(a, i) pack_bf16x2(__uint_as_float(a[i]), __uint_as_float(a[i + 1]))
+                        fm_sts128(dst, FM_PK(ra, 0), FM_PK(ra, 2), FM_PK(ra, 4), FM_PK(ra, 6));
+                        fm_sts128(dst + FM_CHUNK, FM_PK(ra, 8), FM_PK(ra, 10), FM_PK(ra, 12), FM_PK(ra, 14));
+                        if (sub < 2) fm_sts128(dst + 2 * FM_CHUNK, FM_PK(rb, 0), FM_PK(rb, 2), FM_PK(rb, 4), FM_PK(rb, 6));
+#undef FM_PK
+                    }
+                    fm_bar_epi();                                    // the pair's q | k | v tile is complete
+                    if constexpr (F == 8) {                          // 32 problems: (position, head) = ew and ew + 16
+                        const int pls[2] = {ew >> 1, (ew >> 1) + 8}, hds[2] = {ew & 1, ew & 1};
+                        fm_attention<8, 2>(T, pls, hds, lane, p.scale_log2e);
+                    } else {                                         // 16 problems
+                        const int pls[1] = {ew >> 1}, hds[1] = {ew & 1};
+                        fm_attention<16, 1>(T, pls, hds, lane, p.scale_log2e);
+                    }
+                    fm_bar_epi();                                    // every problem's O sits in its q slot
+                    ptx::mbar_wait(ctx_free, (n_ctx & 1u) ^ 1u);     // the previous pair's to_out MMAs have read CTX
+                    n_ctx++;
+                    for (int it = et; it < 10 * 128; it += FM_ETHREADS) {          // q slots (tile order) -> CTX (A-operand order)
+                        const int j = it >> 7, mm = it & 127;
+                        const uint4 v = fm_lds128(T + (uint32_t)j * FM_CHUNK + fm_trow<F>(mm % PPT, mm / PPT) * 16);
+                        fm_sts128(CTX + (uint32_t)j * FM_CHUNK + (uint32_t)mm * 16, v.x, v.y, v.z, v.w);
+                    }
+                    ptx::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(ctx_ready);
+                    fm_bar_epi();                                    // the tile may be overwritten by the next pair's dumps
+                }
+                wait_h();                                            // to_out of all four pairs accumulated onto H
+                dump_stage(1 + i, p.cbias + (i + 1) * FM_C, token);
+            }
+            // ---- feed-forward: LayerNorm -> [GEGLU chunk -> ff_out slice] x 20 ----
+            layer_norm(p.cbias + A * FM_C, p.ff_ln_w, p.ff_ln_b, nullptr);
+            for (int j = 0; j < FM_FF_CHUNKS; j++) {
+                ptx::mbar_wait(g_full, n_g & 1u);
+                ptx::tc_fence_after();
+                uint32_t r[32];
+                ptx::tmem_ld32(t_lane + FM_TM_S + 32 * sub, r);
+                ptx::tmem_ld_wait();
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(g_free);             // S may take the next chunk while the GELUs run
+                const float *b1 = p.b1 + j * 128 + 32 * sub;
+                uint32_t o[8];
+#pragma unroll
+                for (int i4 = 0; i4 < 8; i4++) {                     // accumulator columns 4i .. 4i+3 = value 2q, value 2q+1, gate 2q, gate 2q+1
+                    const float4 bb = __ldg(reinterpret_cast<const float4 *>(b1) + i4);
+                    float v0, v1, g0, g1, y0, y1;
+                    f32x2_unpack(f32x2_add(f32x2_pack(__uint_as_float(r[4 * i4]), __uint_as_float(r[4 * i4 + 1])), f32x2_pack(bb.x, bb.y)), v0, v1);
+                    f32x2_unpack(f32x2_add(f32x2_pack(__uint_as_float(r[4 * i4 + 2]), __uint_as_float(r[4 * i4 + 3])), f32x2_pack(bb.z, bb.w)), g0, g1);
+                    geglu_pair(v0, g0, v1, g1, y0, y1);
+                    o[i4] = pack_bf16x2(y0, y1);
+                }
+                const int ab = (int)(n_g % FM_ACT_BUFS);
+                ptx::mbar_wait(act_free(ab), ((n_g / FM_ACT_BUFS) & 1u) ^ 1u);       // ff_out has consumed this buffer's previous chunk
+                n_g++;
+                const uint32_t dst = T + (uint32_t)ab * FM_ACT_BYTES + (uint32_t)(2 * sub) * FM_CHUNK + (uint32_t)m * 16;
+                fm_sts128(dst, o[0], o[1], o[2], o[3]);
+                fm_sts128(dst + FM_CHUNK, o[4], o[5], o[6], o[7]);
+                ptx::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(act_ready(ab));
+            }
+            wait_h();                                                // h = h + ff(...)
+            const float *cbf = p.cbias + (A + 1) * FM_C;
+            dump_stage(1 + A, cbf, token);
+            // ---- bf16(h) -> A1, the A operand of proj_out ----
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                const int c0 = 80 * sub + 16 * k;
+                uint32_t r[16];
+                ptx::tmem_ld16(t_lane + FM_TM_H + c0, r);
+                ptx::tmem_ld_wait();
+                float o[16];
+#pragma unroll
+                for (int j4 = 0; j4 < 4; j4++) {
+                    const float4 c4 = __ldg(reinterpret_cast<const float4 *>(cbf + c0) + j4);
+                    o[4 * j4] = __uint_as_float(r[4 * j4]) + c4.x; o[4 * j4 + 1] = __uint_as_float(r[4 * j4 + 1]) + c4.y;
+                    o[4 * j4 + 2] = __uint_as_float(r[4 * j4 + 2]) + c4.z; o[4 * j4 + 3] = __uint_as_float(r[4 * j4 + 3]) + c4.w;
+                }
+                const uint32_t dst = A1 + (uint32_t)(c0 >> 3) * FM_CHUNK + (uint32_t)m * 16;
+                fm_sts128(dst, pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+                fm_sts128(dst + FM_CHUNK, pack_bf16x2(o[8], o[9]), pack_bf16x2(o[10], o[11]), pack_bf16x2(o[12], o[13]), pack_bf16x2(o[14], o[15]));
+            }
+            publish_a1();
+            wait_h();                                                // H = h . W_out^T
+            // ---- y[b, c, f, p] = acc + b_out[c] + x[b, c, f, p]: 16 (or 8) consecutive lanes = consecutive positions of one frame ----
+            {
+                const bf16 *xr = p.x + (int64_t)b * p.xsb + (int64_t)f_m * p.xsf + p0 + pl_m;
+                bf16 *yr = p.y + (int64_t)b * p.ysb + (int64_t)f_m * p.ysf + p0 + pl_m;
+#pragma unroll
+                for (int k = 0; k < 5; k++) {
+                    const int c0 = 80 * sub + 16 * k;
+                    float xv[16];
+#pragma unroll
+                    for (int j = 0; j < 16; j++) xv[j] = __bfloat162float(__ldg(xr + (int64_t)(c0 + j) * p.xsc));
+                    uint32_t r[16];
+                    ptx::tmem_ld16(t_lane + FM_TM_H + c0, r);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; j++)
+                        yr[(int64_t)(c0 + j) * p.ysc] = __float2bfloat16_rn(__uint_as_float(r[j]) + __ldg(p.b_out + c0 + j) + xv[j]);
+                }
+            }
+            ptx::tc_fence_before();        // orders this tile's TMEM reads before the next tile's a1_ready arrive -> proj_in may overwrite H
+        }
+    }
+    __syncwarp();
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<1>(tmem_base, FM_TM_COLS);
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------------------------------
+typedef CUresult (*FmEncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static FmEncodeTiledFn fm_encode_fn() {
+    static FmEncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<FmEncodeTiledFn>(ptr);
+    });
+    return fn;
+}
+// bf16 weight [rows, cols] row-major; box = box_rows x 64 columns, 128-byte swizzle
+static int fm_weight_map(CUtensorMap *tm, const void *ptr, int rows, int cols, int box_rows) {
+    FmEncodeTiledFn fn = fm_encode_fn();
+    if (!fn) return fail(NMM_ERR_DEVICE, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+    if (!aligned(ptr, 16)) return fail(NMM_ERR_BAD_ARG, "packed weights must be 16-byte aligned");
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(NMM_ERR_CUDA, "cuTensorMapEncodeTiled (fused module weights) failed with CUresult %d", (int)r);
+    return NMM_OK;
+}
+
+// Which modules keep the extra packed tensors of the fused kernel (shape-independent part; api.cu packed_layout)
+bool fused_module_weights(const Geo &g) {
+    return g.dtype == NMM_BF16 && !g.ln_fold && g.C == FM_C && g.heads == 8 && g.layers == 1 && g.A >= 1 && g.A <= NMM_MAX_ATTN;
+}
+// ... and which calls can run on it
+bool fused_module_eligible(const Geo &g, const nmm_shape *s, const void *x) {
+    if (!opt(NMM_OPT_FUSED_MODULE) || !fused_module_weights(g)) return false;
+    if (g.F != 8 && g.F != 16) return false;
+    if (g.P % (128 / g.F) != 0) return false;
+    return aligned(x, 16) && s->x_stride_b % 8 == 0 && s->x_stride_c % 8 == 0 && s->x_stride_f % 8 == 0;
+}
+
+int launch_fused_module(const FusedArgs &a, cudaStream_t st) {
+    FmMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    int rc;
+    if ((rc = fm_weight_map(&maps.win, a.w_in, FM_C, FM_C, 160)) != NMM_OK) return rc;
+    if ((rc = fm_weight_map(&maps.wout, a.w_out, FM_C, FM_C, 160)) != NMM_OK) return rc;
+    if ((rc = fm_weight_map(&maps.w1, a.w1, 8 * FM_C, FM_C, 128)) != NMM_OK) return rc;
+    if ((rc = fm_weight_map(&maps.w2, a.w2, FM_C, 4 * FM_C, 160)) != NMM_OK) return rc;
+    for (int i = 0; i < a.A; i++) {
+        if ((rc = fm_weight_map(&maps.wqkv[i], a.wqkv_t[i], 3 * FM_C, FM_C, 80)) != NMM_OK) return rc;
+        if ((rc = fm_weight_map(&maps.wo[i], a.wo[i], FM_C, FM_C, 160)) != NMM_OK) return rc;
+    }
+    FmParams p;
+    memset(&p, 0, sizeof(p));
+    p.x = (const bf16 *)a.x; p.y = (bf16 *)a.y;
+    p.xsb = a.xsb; p.xsc = a.xsc; p.xsf = a.xsf; p.ysb = a.ysb; p.ysc = a.ysc; p.ysf = a.ysf;
+    p.B = a.B; p.F = a.F; p.P = a.P; p.A = a.A; p.ppt = 128 / a.F; p.tiles_per_b = a.P / p.ppt;
+    p.ntiles = (int64_t)a.B * p.tiles_per_b;
+    p.gn_partial = a.gn_partial; p.gn_splits = a.gn_splits; p.gn_count = a.gn_count; p.gn_eps = a.gn_eps; p.gn_w = a.gn_w; p.gn_b = a.gn_b;
+    for (int i = 0; i < a.A; i++) { p.ln_w[i] = a.ln_w[i]; p.ln_b[i] = a.ln_b[i]; p.pe[i] = a.pe[i]; p.wo_tail[i] = (const bf16 *)a.wo_tail[i]; }
+    p.ff_ln_w = a.ff_ln_w; p.ff_ln_b = a.ff_ln_b; p.b1 = a.b1; p.cbias = a.cbias; p.b_out = a.b_out;
+    p.ln_eps = a.ln_eps; p.scale_log2e = (1.0f / sqrtf((float)FM_DH)) * 1.4426950408889634f;
+    p.stage_dump = a.stage_dump; p.stage_id = a.stage_id;
+    if (p.ntiles <= 0) return NMM_OK;
+
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = (int)(p.ntiles < sms ? p.ntiles : sms);
+    auto kern = a.F == 8 ? fused_module_kernel<8> : fused_module_kernel<16>;
+    static DeviceOnce once8, once16;
+    if ((a.F == 8 ? once8 : once16).first()) NMM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FM_SMEM_BYTES));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(FM_THREADS);
+    cfg.dynamicSmemBytes = FM_SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    {
+        const double N = (double)a.B * a.F * a.P;
+        // algorithmic work: every Linear of the module + the attention; bytes: x, y and the weights once
+        const double flops = 2.0 * N * FM_C * FM_C * (14.0 + 4.0 * a.A) + 4.0 * a.A * N * a.F * FM_C;
+        const double bytes = 2.0 * N * FM_C * 2 + (double)FM_C * FM_C * (14.0 + 4.0 * a.A) * 2;
+        ProfScope prof(K_FUSED_MODULE, st, flops, bytes);
+        cudaError_t le = cudaLaunchKernelEx(&cfg, kern, maps, p);
+        if (le != cudaSuccess) return fail(NMM_ERR_CUDA, "cudaLaunchKernelEx(fused_module_kernel) failed: %s", cudaGetErrorString(le));
+    }
+    NMM_LAUNCHED("fused_module_kernel");
+    return NMM_OK;
+}
+
+}  // namespace nmm

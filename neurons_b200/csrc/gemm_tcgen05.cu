@@ -91,6 +91,11 @@ constexpr int TC_GN_WARPS = 4;                            // GNA: warps 12-15 no
 constexpr int TC_A_HALF = TC_A_BYTES / 2;                 // GNA: the A stage is two boxes of 64 channels x 64 positions
 
 #ifdef NMM_TRACE
+#define TC_DEBUG(p) ((p).debug)
+#else
+#define TC_DEBUG(p) 0            // the timing experiments are compiled out of the product library
+#endif
+#ifdef NMM_TRACE
 // event slots per tile (CTA 0 only, first TRACE_TILES tiles): 0 mma:tile start, 1 mma:accumulator free, 2 mma:first stage full,
 // 3 mma:all issued, 4 prod:first load issued, 5 prod:last load issued, 6 epi(w4):before tfull wait, 7 epi:accumulator ready,
 // 8..11 epi(w4): chunk k done, 12 epi(w4): released, 13 epi(w8): ready, 14 epi(w8): released
@@ -245,7 +250,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 const int64_t m_blk = m_grp * CG + rank;
                 if constexpr (EPI == NMM_EPI_RESIDUAL) {
                     // the epilogue will read-modify-write this tile's fp32 residual rows: pull them into L2 now
-                    if (!(p.debug & 2))
+                    if (!(TC_DEBUG(p) & 2))
                         for (int c0 = 0; c0 < p.block_n; c0 += 32)
                             for (int r0 = 0; r0 < TC_BM; r0 += 32)
                                 ptx::tma_prefetch_l2_2d(&tm_h, n_blk * p.block_n + c0, (int32_t)(m_blk * TC_BM + r0));
@@ -264,7 +269,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     if (kb == 0) TRACE(tile_no, 4);
                     if (kb == num_kb - 1) TRACE(tile_no, 5);
                     const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
-                    if (p.debug & 2) {                                  // timing experiment: MMA on whatever is in shared memory
+                    if (TC_DEBUG(p) & 2) {                                  // timing experiment: MMA on whatever is in shared memory
                         if (leader) ptx::mbar_arrive(full_bar(stage));
                     } else if (EPI == NMM_EPI_QKV_ATTN) {
                         // A rows = (position, frame) pairs of one image: box (64 channels, F frames, 128/F positions) of the tokens
@@ -324,7 +329,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     if constexpr (GNA) {
                         // M-major A: 64-position blocks 8 KB apart (LBO), 8-channel groups 1 KB apart (SBO); K = 16 channels = 2 KB
                         const uint64_t a_desc = ptx::umma_smem_desc_mn_sw128(sa, TC_A_HALF, 1024);
-                        if (p.debug & 16) {            // timing experiment: K-major descriptors on the same bytes (results invalid)
+                        if (TC_DEBUG(p) & 16) {            // timing experiment: K-major descriptors on the same bytes (results invalid)
                             const uint64_t a_k = ptx::umma_smem_desc_sw128(sa);
                             const uint32_t idk = idesc & ~ptx::UMMA_IDESC_A_MN_MAJOR;
 #pragma unroll
@@ -365,7 +370,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         for (int64_t ct = cluster_id; ct < p.cluster_tiles; ct += num_clusters) {
             const int64_t m_grp = ct / p.n_tiles;
             const int n_blk = (int)(ct - m_grp * p.n_tiles);
-            if (p.debug & 1) break;                                                  // (timing experiment without epilogue: no barriers either)
+            if (TC_DEBUG(p) & 1) break;                                                  // (timing experiment without epilogue: no barriers either)
             asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_ATTN_WARPS) : "memory");     // the tile has been dumped
             fused_attention_phase(at, xb, m_grp * CG + rank, n_blk, warp - 4, TC_ATTN_WARPS, lane);
             asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_ATTN_WARPS) : "memory");     // done with the tile
@@ -402,7 +407,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 ptx::mbar_wait(full_bar(stage), phase);
                 const uint32_t rbase = smem_base + (uint32_t)stage * stage_bytes + (uint32_t)(j * TC_A_HALF + row * 128);
                 const uint64_t ca2 = f32x2_pack(ca, ca), cb2 = f32x2_pack(cb, cb);
-                if (!(p.debug & 4)) {
+                if (!(TC_DEBUG(p) & 4)) {
                     // all 8 loads first (independent, pipelined), then the arithmetic, then the stores
                     uint32_t w[8][4];
 #pragma unroll
@@ -421,7 +426,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         sts128(rbase + (uint32_t)(((i + row) & 7) << 4), w[i][0], w[i][1], w[i][2], w[i][3]);
                     }
                 }
-                if (!(p.debug & 8)) ptx::fence_proxy_async();               // generic-proxy writes -> visible to the tensor core's async proxy
+                if (!(TC_DEBUG(p) & 8)) ptx::fence_proxy_async();               // generic-proxy writes -> visible to the tensor core's async proxy
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(conv_bar(stage));
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -471,7 +476,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     if (warp == 8 && lane == 0) TRACE(tile_no, 13);
                 }
             };
-            if (p.debug & 1) {
+            if (TC_DEBUG(p) & 1) {
                 // timing experiment: drain nothing
             } else if constexpr (EPI == NMM_EPI_QKV_ATTN) {
                 // ---- QKV + attention: the 128 x 240 accumulator tile is q | k | v (80 channels each) of 128/F positions x F frames.
@@ -827,12 +832,12 @@ static int make_tmap_tokens_pf(CUtensorMap *tm, const void *tok, int B, int C, i
 bool linear_tc_attn_fusable(int C, int heads, int F, int P) {
     if (heads <= 0 || C % heads != 0 || C % NMM_ATTN_TILE_CH != 0) return false;
     const int dh = C / heads;
-    return (dh == 40 || dh == 80) && (F == 8 || F == 16) && P % (TC_BM / F) == 0 && !getenv("NMM_NO_ATTN_FUSE");
+    return (dh == 40 || dh == 80) && (F == 8 || F == 16) && P % (TC_BM / F) == 0 && opt(NMM_OPT_ATTN_FUSE) != 0;
 }
 
 // Can proj_in take its A operand straight from x (GroupNorm applied in shared memory)?  See LinearArgs::gn_x.
 bool linear_tc_gn_fusable(int64_t M, int P, const void *x, int64_t sb, int64_t sc, int64_t sf) {
-    return P % 64 == 0 && M % TC_BM == 0 && aligned(x, 16) && sb % 8 == 0 && sc % 8 == 0 && sf % 8 == 0 && !getenv("NMM_NO_GN_FUSE");
+    return P % 64 == 0 && M % TC_BM == 0 && aligned(x, 16) && sb % 8 == 0 && sc % 8 == 0 && sf % 8 == 0 && opt(NMM_OPT_GN_FUSE) != 0;
 }
 
 #ifdef NMM_TRACE
@@ -903,8 +908,7 @@ static TilePlan choose_tiles(int64_t m_tiles, int N, int K, int sms, int gran, i
 }
 
 void plan_linear_tc(int64_t M, int N, int K, int epilogue, int *block_n, int *cluster) {
-    const int force_cluster = getenv("NMM_GEMM_CLUSTER") ? atoi(getenv("NMM_GEMM_CLUSTER")) : 0;
-    const int force_bn = getenv("NMM_GEMM_BLOCK_N") ? atoi(getenv("NMM_GEMM_BLOCK_N")) : 0;
+    const int force_cluster = (int)opt(NMM_OPT_GEMM_CLUSTER), force_bn = (int)opt(NMM_OPT_GEMM_BLOCK_N);
     const int gran = epilogue == NMM_EPI_GEGLU ? 64 : 32;
     const TilePlan plan = choose_tiles(ceil_div(M, TC_BM), N, K, num_sms(), gran, (force_cluster == 1 || force_cluster == 2) ? force_cluster : 0,
                                        (force_bn >= gran && force_bn <= 256 && force_bn % gran == 0 && N % force_bn == 0) ? force_bn : 0);
@@ -952,11 +956,16 @@ int launch_linear_tc(const LinearArgs &a, cudaStream_t st) {
     p.M = a.M; p.N = a.N; p.K = a.K;
     p.m_tiles = ceil_div(a.M, TC_BM);
     const int sms = num_sms();
-    // NMM_GEMM_CLUSTER=1|2 / NMM_GEMM_BLOCK_N force a tiling (development).
-    const int debug_flags = getenv("NMM_GEMM_DEBUG") ? atoi(getenv("NMM_GEMM_DEBUG")) : 0;
+    // NMM_OPT_GEMM_CLUSTER / NMM_OPT_GEMM_BLOCK_N force a tiling (development).  The result-invalidating timing experiments
+    // (NMM_GEMM_DEBUG: epilogue off / no TMA loads / ...) exist only in the -DNMM_TRACE development build.
+#ifdef NMM_TRACE
+    static const int debug_flags = getenv("NMM_GEMM_DEBUG") ? atoi(getenv("NMM_GEMM_DEBUG")) : 0;
+#else
+    constexpr int debug_flags = 0;
+#endif
     // (the no-TMA timing experiment is only wired for single-CTA tiles)
-    const int force_cluster = (debug_flags & 2) ? 1 : getenv("NMM_GEMM_CLUSTER") ? atoi(getenv("NMM_GEMM_CLUSTER")) : 0;
-    const int force_bn = getenv("NMM_GEMM_BLOCK_N") ? atoi(getenv("NMM_GEMM_BLOCK_N")) : 0;
+    const int force_cluster = (debug_flags & 2) ? 1 : (int)opt(NMM_OPT_GEMM_CLUSTER);
+    const int force_bn = (int)opt(NMM_OPT_GEMM_BLOCK_N);
     p.debug = debug_flags;
     p.trace = nullptr;
 #ifdef NMM_TRACE
@@ -972,7 +981,7 @@ int launch_linear_tc(const LinearArgs &a, cudaStream_t st) {
                 !linear_tc_gn_fusable(a.M, a.P, a.gn_x, a.xsb, a.xsc, a.xsf) || (int64_t)a.gn_B * a.F * a.P != a.M))
         return fail(NMM_ERR_UNSUPPORTED, "GroupNorm-fused A operand: needs the STORE epilogue, P %% 64 == 0, M %% 128 == 0 and 16-byte aligned x");
     const int gran = a.epilogue == NMM_EPI_GEGLU ? 64 : 32;
-    const bool allow_wide = a.epilogue == NMM_EPI_RESIDUAL && !gna && a.ln_part_in == nullptr && a.ln_part_out == nullptr && !(debug_flags & 2) && !getenv("NMM_NO_WIDE_TILE");
+    const bool allow_wide = a.epilogue == NMM_EPI_RESIDUAL && !gna && a.ln_part_in == nullptr && a.ln_part_out == nullptr && !(debug_flags & 2) && opt(NMM_OPT_WIDE_TILE) != 0;
     const TilePlan plan = attn ? TilePlan{3 * NMM_ATTN_TILE_CH, 1, 0} :
                           choose_tiles(p.m_tiles, a.N, a.K, sms, gran, gna ? 1 : (force_cluster == 1 || force_cluster == 2) ? force_cluster : 0,
                                        (force_bn >= gran && force_bn <= 320 && force_bn % gran == 0 && a.N % force_bn == 0) ? force_bn : 0, allow_wide);

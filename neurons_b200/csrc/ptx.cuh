@@ -178,6 +178,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+    uint32_t r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+    return r;
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
@@ -215,6 +226,19 @@ __device__ __forceinline__ uint64_t umma_smem_desc_mn_sw128(uint32_t smem_addr, 
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)2 << 61;
+    return d;
+}
+// Shared-memory matrix descriptor for a K-major operand WITHOUT swizzle ("interleave"): 8-row x 16-byte core matrices of 128
+// contiguous bytes; `lbo_bytes` = distance between the two 16-byte K chunks of a K = 16 step, `sbo_bytes` = distance between
+// consecutive 8-row groups (validated on B200 by scripts/micro/umma_probe.cu, profiles/r2_umma_probe.txt).  The fused module
+// kernel keeps its A operands as [K / 8 chunks][128 rows][16 B]: lbo = 2048, sbo = 128 -- a layout that one thread per row can
+// write with conflict-free 16-byte stores.
+__device__ __forceinline__ uint64_t umma_smem_desc_interleave(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
     return d;
 }
 constexpr uint32_t UMMA_IDESC_A_MN_MAJOR = 1u << 15;     // instruction descriptor: A operand is M-major

@@ -56,7 +56,8 @@ class KernelProfile(C.Structure):
                 ("bytes", C.c_double)]
 
 
-PROFILE_KERNELS = 7
+PROFILE_KERNELS = 8
+ABI_VERSION = 2
 
 # name -> (restype, argtypes); must list every NMM_API symbol of include/neurons_mm.h (tests/test_abi.py checks)
 _SP = C.POINTER(Shape)
@@ -65,13 +66,17 @@ SIGNATURES = {
     "nmm_last_error": (C.c_char_p, []),
     "nmm_device_check": (C.c_int, []),
     "nmm_launch_count": (C.c_uint64, []),
+    "nmm_set_option": (C.c_int, [C.c_int32, C.c_int64]),
+    "nmm_get_option": (C.c_int64, [C.c_int32]),
     "nmm_profile_begin": (C.c_int, []),
     "nmm_profile_end": (C.c_int, [C.POINTER(KernelProfile), C.c_int32]),
     "nmm_validate": (C.c_int, [_SP]),
     "nmm_packed_params_bytes": (C.c_int, [_SP, C.POINTER(C.c_size_t)]),
     "nmm_workspace_bytes": (C.c_int, [_SP, C.POINTER(C.c_size_t)]),
     "nmm_pack_params": (C.c_int, [_SP, C.POINTER(Params), C.c_void_p, C.c_size_t, C.c_void_p]),
-    "nmm_forward": (C.c_int, [_SP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "nmm_forward": (C.c_int, [_SP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "nmm_packed_header": (C.c_int, [_SP, C.c_void_p, C.c_size_t]),
+    "nmm_forward_stage": (C.c_int, [_SP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int32, C.c_void_p, C.c_void_p]),
     "nmm_groupnorm_stats": (C.c_int, [_SP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "nmm_groupnorm_tokens": (C.c_int, [_SP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "nmm_groupnorm_linear": (C.c_int, [_SP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -103,8 +108,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)          # AttributeError if the ABI and this binding disagree
         fn.restype = res
         fn.argtypes = args
-    if lib.nmm_abi_version() != 1:
-        raise RuntimeError(f"libneurons_mm.so ABI version {lib.nmm_abi_version()} != 1")
+    if lib.nmm_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"libneurons_mm.so ABI version {lib.nmm_abi_version()} != {ABI_VERSION}")
     _lib = lib
     return lib
 
@@ -124,6 +129,37 @@ def profile_end():
     check(load().nmm_profile_end(arr, PROFILE_KERNELS))
     return {k.name.decode(): dict(launches=int(k.launches), total_ms=float(k.total_ms), flops=float(k.flops), bytes=float(k.bytes))
             for k in arr}
+
+
+# nmm_option (include/neurons_mm.h)
+OPT_FUSED_MODULE, OPT_GN_FUSE, OPT_ATTN_FUSE, OPT_WIDE_TILE, OPT_GEMM_CLUSTER, OPT_GEMM_BLOCK_N, OPT_CHUNK_TOKENS, OPT_ATTN_VARIANT, OPT_SPLIT_K = range(9)
+
+
+def set_option(option: int, value: int):
+    check(load().nmm_set_option(option, value))
+
+
+def get_option(option: int) -> int:
+    return int(load().nmm_get_option(option))
+
+
+class options:
+    """Context manager: `with lib.options({lib.OPT_FUSED_MODULE: 0}): ...` -- set run-time options, restore them on exit."""
+
+    def __init__(self, values: dict):
+        self.values = dict(values)
+        self.saved = {}
+
+    def __enter__(self):
+        for k, v in self.values.items():
+            self.saved[k] = get_option(k)
+            set_option(k, v)
+        return self
+
+    def __exit__(self, *exc):
+        for k, v in self.saved.items():
+            set_option(k, v)
+        return False
 
 
 def launch_count() -> int:

@@ -27,8 +27,12 @@ from typing import Dict, Optional
 import torch
 from torch import nn
 
+import os
+
 from . import ops
 from .ops import ModuleConfig
+
+_WEIGHT_CHECK = os.environ.get("NMM_WEIGHT_CHECK", "0") not in ("", "0")      # debug: checksum the live parameters on every call
 
 
 def zero_module(module: nn.Module) -> nn.Module:
@@ -186,7 +190,8 @@ def config_of(module: nn.Module) -> ModuleConfig:
         raise NotImplementedError("neurons_b200: inner_dim != in_channels is not supported")
     pos = getattr(a0, "pos_encoder", None)
     return ModuleConfig(channels=channels, heads=int(a0.heads), layers=len(blocks), attn_blocks=len(b0.attention_blocks),
-                        pos_enc=pos is not None, max_len=int(pos.pe.shape[1]) if pos is not None else 0)
+                        pos_enc=pos is not None, max_len=int(pos.pe.shape[1]) if pos is not None else 0,
+                        ln_fold=bool(module.__dict__.get("_nmm_ln_fold", False)))      # set by tests / experiments before the first call
 
 
 def _param_tensors(module: nn.Module) -> Dict[str, torch.Tensor]:
@@ -196,8 +201,14 @@ def _param_tensors(module: nn.Module) -> Dict[str, torch.Tensor]:
 
 
 class _Engine:
-    """Packed copy of one module's parameters, keyed on (data_ptr, dtype, device) of every source tensor --
-    NOT on tensor._version, which `.data +=` (LoRA merge) does not bump (SURVEY 7 'Live weights')."""
+    """Packed copy of one module's parameters.
+
+    Cache key: (dtype, device) of the call + (data_ptr, _version) of every source tensor.  `_version` catches every in-place update
+    made through the tensor itself (load_state_dict / copy_, optimizer steps, `p += d`); `data_ptr` catches replaced parameters
+    (.to(), .half()).  What neither sees is a write through `.data` (`p.data += d`: the reference's LoRA merge,
+    convert_lora_safetensor_to_diffusers.py:27-47, detaches the version counter): call `neurons_b200.invalidate(model)` after such
+    a merge, or run with NMM_WEIGHT_CHECK=1 (debug: a device-side checksum of all parameters is compared on every call, at the cost
+    of one reduction + host sync per call) to be told when it happened."""
 
     def __init__(self):
         self.key = None
@@ -205,15 +216,29 @@ class _Engine:
         self.cfg = None
         self.tensors = None      # name -> tensor, collected once (module.to() / .data updates keep the same objects)
         self.shape_cache = {}    # (shape, strides, dtype) -> (nmm_shape struct, workspace bytes)
+        self.pack_stream = None  # stream the packing kernels ran on + an event recorded behind them
+        self.pack_event = None
+        self.checksum = None
+
+    @staticmethod
+    def _key(x, tensors):
+        return (x.dtype, x.device) + tuple((t.data_ptr(), t._version) for t in tensors.values())
+
+    @staticmethod
+    def _checksum(tensors):
+        return float(sum(t.detach().double().abs().sum() for t in tensors.values()))
 
     def get(self, module: nn.Module, x: torch.Tensor):
         if self.tensors is None:
             self.tensors = _param_tensors(module)
         tensors = self.tensors
-        key = (x.dtype, x.device) + tuple([t.data_ptr() for t in tensors.values()])
+        key = self._key(x, tensors)
         if key != self.key:
             self.tensors = tensors = _param_tensors(module)      # re-scan the tree (parameters may have been replaced)
-            key = (x.dtype, x.device) + tuple([t.data_ptr() for t in tensors.values()])
+            key = self._key(x, tensors)
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("neurons_b200: the module's parameters must be packed before CUDA-graph capture: run one forward "
+                                   "outside the capture first (packing inside a capture would bake stale weights into the graph)")
             self.cfg = config_of(module)
             dev_tensors = {}
             for k, t in tensors.items():
@@ -221,7 +246,24 @@ class _Engine:
                     raise RuntimeError(f"neurons_b200: parameter '{k}' is on {t.device}, input on {x.device}")
                 dev_tensors[k] = t.reshape(t.shape[-2:]) if k.endswith("pos_encoder.pe") else t
             self.packed = ops.pack_params(self.cfg, dev_tensors, x.dtype, x.device)
+            self.pack_stream = torch.cuda.current_stream(x.device)
+            self.pack_event = torch.cuda.Event()
+            self.pack_event.record(self.pack_stream)
             self.key = key
+            self.shape_cache.clear()
+            if _WEIGHT_CHECK:
+                self.checksum = self._checksum(tensors)
+        else:
+            if self.pack_event is not None:
+                cur = torch.cuda.current_stream(x.device)
+                if cur != self.pack_stream:
+                    cur.wait_event(self.pack_event)          # first use on another stream: order it behind the packing kernels
+                    self.pack_stream = cur                   # (later calls on this stream are ordered by the stream itself)
+            if _WEIGHT_CHECK and not torch.cuda.is_current_stream_capturing():
+                now = self._checksum(tensors)
+                if now != self.checksum:
+                    raise RuntimeError("neurons_b200 (NMM_WEIGHT_CHECK): parameters changed in place through `.data` since they were "
+                                       "packed -- call neurons_b200.invalidate(model) after merging LoRA / editing weights")
         return self.cfg, self.packed
 
 
@@ -257,6 +299,7 @@ def invalidate(model: nn.Module) -> int:
             eng.key = None
             eng.packed = None
             eng.tensors = None
+            eng.pack_event = None
             n += 1
     return n
 

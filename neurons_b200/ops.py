@@ -43,9 +43,11 @@ def _dtype_code(dt: torch.dtype) -> int:
     raise TypeError(f"neurons_mm supports float32 and bfloat16 activations, got {dt}")
 
 
+_LN_FOLD_ENV = os.environ.get("NMM_LN_FOLD")       # read ONCE at import: the packed layout depends on it (pack and forward must agree)
+
+
 def _ln_fold(cfg: "ModuleConfig") -> int:
-    env = os.environ.get("NMM_LN_FOLD")
-    return int(bool(cfg.ln_fold) if env is None else env != "0")
+    return int(bool(cfg.ln_fold) if _LN_FOLD_ENV is None else _LN_FOLD_ENV != "0")
 
 
 def _stream_ptr(device) -> int:
@@ -172,9 +174,10 @@ def workspace_bytes(shape: _lib.Shape) -> int:
 
 
 def forward_packed(x: torch.Tensor, packed: torch.Tensor, cfg: ModuleConfig, out: Optional[torch.Tensor] = None,
-                   shape_cache: Optional[dict] = None) -> torch.Tensor:
+                   shape_cache: Optional[dict] = None, stage: Optional[int] = None):
     """y = module(x) through nmm_forward.  Returns logical [B,C,F,H,W] over [B,F,C,H,W] storage.
-    `shape_cache` (optional dict owned by the caller) memoises the validated nmm_shape + workspace size per input geometry."""
+    `shape_cache` (optional dict owned by the caller) memoises the validated nmm_shape + workspace size per input geometry.
+    `stage` (tests): also return the fused kernel's fp32 [N, C] residual-stream snapshot after that stage (nmm_forward_stage)."""
     _require_cuda(x, "x")
     _require_cuda(packed, "packed")
     x = _dense_hw(x)
@@ -191,14 +194,33 @@ def forward_packed(x: torch.Tensor, packed: torch.Tensor, cfg: ModuleConfig, out
             shape_cache[key] = hit
     shape, ws_bytes = hit
     ws, ws_ptr = _aligned_ws(ws_bytes, x.device)
+    lib = _lib.load()
+    if stage is not None:
+        stage_out = torch.empty((B * F * H * W, Cc), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(lib.nmm_forward_stage(C.byref(shape), x.data_ptr(), out.data_ptr(), packed.data_ptr(), packed.numel(), ws_ptr, ws_bytes,
+                                             int(stage), stage_out.data_ptr(), _stream_ptr(x.device)))
+        return out, stage_out
     if x.device.index != torch.cuda.current_device():
         with torch.cuda.device(x.device):
-            _lib.check(_lib.load().nmm_forward(C.byref(shape), x.data_ptr(), out.data_ptr(), packed.data_ptr(), ws_ptr,
-                                               ws_bytes, _stream_ptr(x.device)))
+            _lib.check(lib.nmm_forward(C.byref(shape), x.data_ptr(), out.data_ptr(), packed.data_ptr(), packed.numel(), ws_ptr,
+                                       ws_bytes, _stream_ptr(x.device)))
     else:
-        _lib.check(_lib.load().nmm_forward(C.byref(shape), x.data_ptr(), out.data_ptr(), packed.data_ptr(), ws_ptr,
-                                           ws_bytes, _stream_ptr(x.device)))
+        _lib.check(lib.nmm_forward(C.byref(shape), x.data_ptr(), out.data_ptr(), packed.data_ptr(), packed.numel(), ws_ptr,
+                                   ws_bytes, _stream_ptr(x.device)))
     return out
+
+
+def packed_header(cfg: ModuleConfig, dtype: torch.dtype) -> bytes:
+    """The 64-byte header nmm_pack_params writes for (cfg, dtype): compare with bytes(packed[:64].cpu())."""
+    s = _lib.Shape()
+    s.batch = s.frames = s.height = s.width = 1
+    s.channels, s.heads, s.layers, s.attn_blocks = cfg.channels, cfg.heads, cfg.layers, cfg.attn_blocks
+    s.pos_enc, s.max_len, s.dtype = int(cfg.pos_enc), cfg.max_len, _dtype_code(dtype)
+    s.eps_gn, s.eps_ln, s.ln_fold = GN_EPS, LN_EPS, _ln_fold(cfg)
+    buf = C.create_string_buffer(64)
+    _lib.check(_lib.load().nmm_packed_header(C.byref(s), buf, 64))
+    return buf.raw
 
 
 # ---- torch.library registration: torch.ops.neurons_mm.forward ---------------------------------------------------

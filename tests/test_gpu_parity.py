@@ -280,15 +280,15 @@ def test_module_properties_full_size(dtype):
         assert torch.equal(m(x, None, None), x)
 
 
-def test_layernorm_folding_matches_separate_layernorm(monkeypatch):
-    # NMM_LN_FOLD=1 folds the LayerNorms into the QKV / GEGLU GEMMs (3 launches fewer per call); the default runs the
-    # separate LayerNorm kernel.  Both variants must meet the bar and agree closely.
+def test_layernorm_folding_matches_separate_layernorm():
+    # ln_fold folds the LayerNorms into the QKV / GEGLU GEMMs (3 launches fewer per call); the default runs the
+    # separate LayerNorm kernel.  Both variants must meet the bar and agree closely.  (Multi-kernel pipeline: fused module off.)
     fx, cfg, params, x = helpers.load_golden("c320_f16_8x8_a2_view")
     xb = x.to(DEV, torch.bfloat16)
-    with torch.no_grad():
+    with torch.no_grad(), nlib.options({nlib.OPT_FUSED_MODULE: 0}):
         y_sep = helpers.mirror_module(cfg, params, DEV, torch.bfloat16)(xb, None, None)
-        monkeypatch.setenv("NMM_LN_FOLD", "1")
         m2 = helpers.mirror_module(cfg, params, DEV, torch.bfloat16)
+        m2.__dict__["_nmm_ln_fold"] = True
         m2(xb, None, None)
         n0 = nb.launch_count()
         y_fold = m2(xb, None, None)
@@ -329,6 +329,43 @@ def test_lora_style_inplace_update_needs_invalidate():
     assert _maxabs(y1, mo.forward_reference_order(p2, x, cfg)) <= helpers.TOL_FP32
 
 
+def test_inplace_updates_through_the_tensor_repack_automatically():
+    """Updates that bump tensor._version -- load_state_dict / copy_ (load_weights, animatediff/utils/util.py:107-121), `p += d`,
+    optimizer steps -- are seen by the packed-parameter cache without invalidate(); only `.data` writes need it (test above)."""
+    fx, cfg, params, x = helpers.load_golden("c64_f16_4x4_a1_view")
+    m = helpers.mirror_module(cfg, params, DEV)
+    xd = x.to(DEV)
+    with torch.no_grad():
+        y0 = m(xd, None, None)
+        p2 = {k: v.clone() for k, v in params.items()}
+        p2["temporal_transformer.proj_out.weight"] += 0.05
+        m.load_state_dict(p2, strict=False)                        # copy_ into the existing parameters: same data_ptr, new _version
+        y1 = m(xd, None, None)
+        assert _maxabs(y1, mo.forward_reference_order(p2, x, cfg)) <= helpers.TOL_FP32
+        m.temporal_transformer.proj_out.bias += 0.25               # in place through the tensor itself
+        p2["temporal_transformer.proj_out.bias"] += 0.25
+        y2 = m(xd, None, None)
+        assert _maxabs(y2, mo.forward_reference_order(p2, x, cfg)) <= helpers.TOL_FP32
+    assert not torch.equal(y1, y0) and not torch.equal(y2, y1)
+
+
+def test_packed_buffer_mismatch_is_refused():
+    """nmm_forward checks the packed buffer's size against the call's layout (a buffer packed for another dtype / heads
+    must not be read out of bounds) and the buffer starts with a header naming what it was packed for."""
+    cfg = mo.MotionConfig(64)
+    params = {k: v.to(DEV) for k, v in mo.make_params(cfg, 1).items()}
+    packed32 = ops.pack_params(_cfg(cfg), params, torch.float32, torch.device(DEV))
+    packed16 = ops.pack_params(_cfg(cfg), params, torch.bfloat16, torch.device(DEV))
+    assert bytes(packed32[:64].cpu().numpy().tobytes()) == ops.packed_header(_cfg(cfg), torch.float32)
+    assert bytes(packed16[:64].cpu().numpy().tobytes()) == ops.packed_header(_cfg(cfg), torch.bfloat16)
+    x = torch.zeros(1, 64, 4, 2, 2, device=DEV)
+    with pytest.raises(nlib.NmmError, match="does not match"):
+        ops.forward_packed(x, packed16, _cfg(cfg))                 # fp32 call, bf16 pack
+    cfg2 = mo.MotionConfig(64, attn_blocks=1)
+    with pytest.raises(nlib.NmmError, match="does not match"):
+        ops.forward_packed(x, packed32, _cfg(cfg2))
+
+
 def test_unsupported_inputs_raise():
     cfg = mo.MotionConfig(64)
     m = helpers.mirror_module(cfg, mo.make_params(cfg, 1), DEV)
@@ -349,7 +386,11 @@ def test_launch_counter_and_graph_capture():
         y_eager = m(x, None, None)
         n0 = nb.launch_count()
         m(x, None, None)
-        per_call = nb.launch_count() - n0
+        assert nb.launch_count() - n0 == 2                    # C = 320: GroupNorm statistics + the one-kernel module
+        with nlib.options({nlib.OPT_FUSED_MODULE: 0}):
+            n0 = nb.launch_count()
+            m(x, None, None)
+            per_call = nb.launch_count() - n0
         # gn_stats, GroupNorm-fused proj_in (16x16 positions: x is TMA-loaded by the GEMM), 2x(ln, qkv with the attention in its epilogue,
         # out), ln geglu ff_out, proj_out
         assert per_call == 1 + 1 + 2 * 3 + 3 + 1
@@ -413,27 +454,32 @@ def test_qkv_attention_fused_matches_two_kernel_path(C, F, H, W, B):
     assert _maxabs(fused, ref) <= 2e-2 * max(1.0, ref.abs().max().item())
 
 
-def test_fused_and_unfused_kernel_paths_agree(monkeypatch):
-    """The module with every fusion (GroupNorm inside proj_in, attention inside the QKV projection) against the same module with the
-    stand-alone kernels (NMM_NO_GN_FUSE / NMM_NO_ATTN_FUSE): same arithmetic up to the bf16 rounding of P in the attention."""
+def test_fused_and_unfused_kernel_paths_agree():
+    """The three ways a C = 320 call can run: the one-kernel module (fused_module.cu), the multi-kernel pipeline with its fusions
+    (GroupNorm inside proj_in, attention inside the QKV projection) and the pipeline of stand-alone kernels: same arithmetic up to
+    bf16 roundings of intermediates."""
     cfg = mo.MotionConfig(320)
     params = {k: helpers.round_bf16(v) for k, v in mo.make_params(cfg, 5).items()}
     m = helpers.mirror_module(cfg, params, DEV, torch.bfloat16)
     x = helpers.round_bf16(mo.make_input((2, 320, 8, 16, 16), 6, layout="bfchw")).to(DEV, torch.bfloat16)
+
+    def run():
+        n0 = nb.launch_count()
+        y = m(x, None, None).float()
+        return y, nb.launch_count() - n0
+
     with torch.no_grad():
         m(x, None, None)                                   # first call packs the parameters (extra launches)
-        n0 = nb.launch_count()
-        y_fused = m(x, None, None).float()
-        n_fused = nb.launch_count() - n0
-        monkeypatch.setenv("NMM_NO_GN_FUSE", "1")
-        monkeypatch.setenv("NMM_NO_ATTN_FUSE", "1")
-        n0 = nb.launch_count()
-        y_plain = m(x, None, None).float()
-        n_plain = nb.launch_count() - n0
-    assert n_fused == 12 and n_plain == 15
+        y_one, n_one = run()
+        with nlib.options({nlib.OPT_FUSED_MODULE: 0}):
+            y_fused, n_fused = run()
+            with nlib.options({nlib.OPT_GN_FUSE: 0, nlib.OPT_ATTN_FUSE: 0}):
+                y_plain, n_plain = run()
+    assert n_one == 2 and n_fused == 12 and n_plain == 15
     assert (y_fused - y_plain).abs().max().item() <= 2 ** -6 * y_plain.abs().max().item()
+    assert (y_one - y_plain).abs().max().item() <= 2 ** -6 * y_plain.abs().max().item()
     ref = mo.forward_reference_order(params, x.float().cpu(), cfg)
-    assert _maxabs(y_fused, ref) <= helpers.TOL_BF16 and _maxabs(y_plain, ref) <= helpers.TOL_BF16
+    assert _maxabs(y_one, ref) <= helpers.TOL_BF16 and _maxabs(y_fused, ref) <= helpers.TOL_BF16 and _maxabs(y_plain, ref) <= helpers.TOL_BF16
 
 
 @pytest.mark.parametrize("M,N,K,copy", [(16384, 640, 2560, True), (4096, 1280, 5120, False), (16384 + 128, 640, 2560, True)])
