@@ -43,6 +43,7 @@ void init_opts() {
     g_opts[NMM_OPT_CHUNK_TOKENS] = num("NMM_CHUNK_TOKENS");
     g_opts[NMM_OPT_ATTN_VARIANT] = getenv("NMM_ATTN_SIMT") ? 2 : getenv("NMM_ATTN_GENERIC") ? 1 : 0;
     g_opts[NMM_OPT_SPLIT_K] = flag_off("NMM_NO_SPLIT_K");
+    g_opts[NMM_OPT_FUSED_CLUSTER] = num("NMM_FUSED_CLUSTER");
 }
 }  // namespace
 int64_t opt(int option) {
@@ -86,11 +87,20 @@ ProfScope::~ProfScope() {
 // ---- packed parameter layout -------------------------------------------------------------------------
 struct AttnOff { size_t ln_w, ln_b, wqkv, wqkv_t, wo, bo, pe, g_qkv, c_qkv, pew, wo_tail; };   // wqkv_t: tile-ordered copy (fused attention); g/c/pew: LayerNorm folding; wo_tail: fused module
 struct LayerOff { AttnOff attn[NMM_MAX_ATTN]; size_t ff_ln_w, ff_ln_b, w1, b1, w2, b2, g1, c1; };
-struct PackedLayout { size_t header, gn_w, gn_b, w_in, b_in; LayerOff layer[NMM_MAX_LAYERS]; size_t w_out, b_out, cbias, total; };
+struct PackedLayout {
+    size_t header, gn_w, gn_b, w_in, b_in;
+    LayerOff layer[NMM_MAX_LAYERS];
+    size_t w_out, b_out;
+    // fused C = 320 module kernel: proj_in weight with the GroupNorm gamma folded in, its bias (+ beta . W_in^T), scratch for the fold,
+    // cumulative biases, and the per-phase fp32 vector blocks (FmParams, fused_module.cu)
+    size_t w_in_g, b_in_g, fold_tmp, cbias, vec_attn[NMM_MAX_ATTN], vec_ff, vec_fin;
+    size_t total;
+};
 
 // First 256 bytes of every packed buffer: what it was packed for.  nmm_forward refuses a buffer whose header does not match the call
 // (another dtype / head count / LayerNorm-folding mode would select another layout and read out of bounds).
-struct PackedHeader { uint32_t magic, abi; int32_t dtype, ln_fold, C, heads, layers, A, max_len, pos_enc; uint64_t total; };
+struct PackedHeader { uint32_t magic, abi; int32_t dtype, ln_fold, C, heads, layers, A, max_len, pos_enc; uint64_t total; uint64_t reserved[2]; };
+static_assert(sizeof(PackedHeader) == 64, "packed header is 64 bytes");
 constexpr uint32_t PACKED_MAGIC = 0x4D4D4E32u;      // "2NMM"
 
 // does this module keep a tile-ordered q|k|v weight for the fused QKV + attention kernel?  (shape-independent part of the test)
@@ -125,7 +135,14 @@ static PackedLayout packed_layout(const Geo &g) {
         lo.g1 = take(g.ln_fold ? 8 * C * 4 : 0); lo.c1 = take(g.ln_fold ? 8 * C * 4 : 0);
     }
     L.w_out = take(C * C * ws); L.b_out = take(C * 4);
-    L.cbias = take(fused_module_weights(g) ? (size_t)(g.A + 2) * C * 4 : 0);       // cumulative biases of the residual stream (fused module)
+    {
+        const bool fm = fused_module_weights(g);
+        const size_t rows = g.pos_enc ? (size_t)g.max_len : 1;
+        L.w_in_g = take(fm ? C * C * ws : 0); L.b_in_g = take(fm ? C * 4 : 0); L.fold_tmp = take(fm ? C * 4 : 0);
+        L.cbias = take(fm ? (size_t)(g.A + 2) * C * 4 : 0);
+        for (int i = 0; i < g.A; i++) L.vec_attn[i] = take(fm ? (2 + rows) * C * 4 : 0);
+        L.vec_ff = take(fm ? 3 * C * 4 : 0); L.vec_fin = take(fm ? 2 * C * 4 : 0);
+    }
     L.total = off;
     return L;
 }
@@ -360,6 +377,21 @@ __global__ void cumulative_bias_kernel(float *__restrict__ cb, BiasList list, in
     float acc = 0.f;
     for (int k = 0; k < list.n; k++) { acc += list.b[k][c]; cb[(size_t)k * C + c] = acc; }
 }
+// dst = [a | b | c + d[r] for r < rows]   (vectors of C floats; c, d may be null: treated as zero; d has `rows` rows)
+__global__ void vector_block_kernel(float *__restrict__ dst, const float *__restrict__ a, const float *__restrict__ b, const float *__restrict__ c,
+                                    const float *__restrict__ d, int rows, int C) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int total = (2 + rows) * C;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int r = i / C, col = i - r * C;
+        float v;
+        if (r == 0) v = a[col];
+        else if (r == 1) v = b[col];
+        else v = (c ? c[col] : 0.f) + (d ? d[(size_t)(r - 2) * C + col] : 0.f);
+        dst[i] = v;
+    }
+}
 __global__ void write_header_kernel(PackedHeader hd, PackedHeader *dst) {
     pdl_wait();
     pdl_launch_dependents();
@@ -527,13 +559,31 @@ int nmm_pack_params(const nmm_shape *s, const nmm_params *src, void *packed, siz
     PACK(src->proj_out_w, L.w_out, wd, C, C, 0); PACK(src->proj_out_b, L.b_out, NMM_F32, C, 1, 0);
 #undef PACK
     if (fused_module_weights(g)) {
+        // proj_in with the GroupNorm affine folded in:  (xhat * gamma + beta) . W^T + b  =  xhat . (gamma (.) W)^T + (b + beta . W^T)
+        rc = fold_linear(sd, src->proj_in_w, src->gn_w, src->gn_b, src->proj_in_b, nullptr, base + L.w_in_g, (float *)(base + L.fold_tmp),
+                         (float *)(base + L.b_in_g), nullptr, C, C, 0, 0, 0, st);
+        if (rc != NMM_OK) return rc;
+        const LayerOff &lo = L.layer[0];
         BiasList bl;
         bl.n = g.A + 2;
-        bl.b[0] = (const float *)(base + L.b_in);
-        for (int i = 0; i < g.A; i++) bl.b[1 + i] = (const float *)(base + L.layer[0].attn[i].bo);
-        bl.b[g.A + 1] = (const float *)(base + L.layer[0].b2);
-        launch_pdl(cumulative_bias_kernel, (unsigned)ceil_div(C, 128), 128, 0, st, (float *)(base + L.cbias), bl, (int)C);
+        bl.b[0] = (const float *)(base + L.b_in_g);
+        for (int i = 0; i < g.A; i++) bl.b[1 + i] = (const float *)(base + lo.attn[i].bo);
+        bl.b[g.A + 1] = (const float *)(base + lo.b2);
+        float *cb = (float *)(base + L.cbias);
+        launch_pdl(cumulative_bias_kernel, (unsigned)ceil_div(C, 128), 128, 0, st, cb, bl, (int)C);
         NMM_LAUNCHED("cumulative_bias_kernel");
+        auto F32p = [&](size_t o) { return (const float *)(base + o); };
+        for (int i = 0; i < g.A; i++) {     // cb_i | gamma_i | beta_i + pe_i[f]
+            launch_pdl(vector_block_kernel, 16, 256, 0, st, (float *)(base + L.vec_attn[i]), (const float *)(cb + (size_t)i * C), F32p(lo.attn[i].ln_w),
+                       F32p(lo.attn[i].ln_b), g.pos_enc ? F32p(lo.attn[i].pe) : (const float *)nullptr, g.pos_enc ? g.max_len : 1, (int)C);
+            NMM_LAUNCHED("vector_block_kernel");
+        }
+        launch_pdl(vector_block_kernel, 16, 256, 0, st, (float *)(base + L.vec_ff), (const float *)(cb + (size_t)g.A * C), F32p(lo.ff_ln_w), F32p(lo.ff_ln_b),
+                   (const float *)nullptr, 1, (int)C);
+        NMM_LAUNCHED("vector_block_kernel");
+        launch_pdl(vector_block_kernel, 16, 256, 0, st, (float *)(base + L.vec_fin), (const float *)(cb + (size_t)(g.A + 1) * C), F32p(L.b_out),
+                   (const float *)nullptr, (const float *)nullptr, 0, (int)C);
+        NMM_LAUNCHED("vector_block_kernel");
     }
     return NMM_OK;
 }
@@ -604,17 +654,16 @@ static int forward_impl(const nmm_shape *s, const void *x, void *y, const void *
         memset(&fa, 0, sizeof(fa));
         fa.x = x; fa.y = y;
         fa.xsb = s->x_stride_b; fa.xsc = s->x_stride_c; fa.xsf = s->x_stride_f; fa.ysb = s->y_stride_b; fa.ysc = s->y_stride_c; fa.ysf = s->y_stride_f;
-        fa.B = g.B; fa.F = g.F; fa.P = g.P; fa.A = g.A;
+        fa.B = g.B; fa.F = g.F; fa.P = g.P; fa.A = g.A; fa.pos_enc = g.pos_enc ? 1 : 0;
         fa.gn_partial = gn_partial; fa.gn_splits = gn_splits_of(g); fa.gn_count = (double)(g.C / NMM_GN_GROUPS) * g.P; fa.gn_eps = s->eps_gn;
-        fa.gn_w = F32(L.gn_w); fa.gn_b = F32(L.gn_b);
         const LayerOff &lo = L.layer[0];
-        fa.w_in = pk + L.w_in; fa.w_out = pk + L.w_out; fa.w1 = pk + lo.w1; fa.w2 = pk + lo.w2;
+        fa.w_in_g = pk + L.w_in_g; fa.w_out = pk + L.w_out; fa.w1 = pk + lo.w1; fa.w2 = pk + lo.w2;
         for (int i = 0; i < g.A; i++) {
             const AttnOff &ao = lo.attn[i];
             fa.wqkv_t[i] = pk + ao.wqkv_t; fa.wo[i] = pk + ao.wo; fa.wo_tail[i] = pk + ao.wo_tail;
-            fa.ln_w[i] = F32(ao.ln_w); fa.ln_b[i] = F32(ao.ln_b); fa.pe[i] = g.pos_enc ? F32(ao.pe) : nullptr;
+            fa.vec_attn[i] = F32(L.vec_attn[i]);
         }
-        fa.ff_ln_w = F32(lo.ff_ln_w); fa.ff_ln_b = F32(lo.ff_ln_b); fa.b1 = F32(lo.b1); fa.cbias = F32(L.cbias); fa.b_out = F32(L.b_out);
+        fa.vec_ff = F32(L.vec_ff); fa.vec_fin = F32(L.vec_fin); fa.b1 = F32(lo.b1);
         fa.ln_eps = s->eps_ln;
         fa.stage_dump = stage_dump; fa.stage_id = stage_id;
         return launch_fused_module(fa, st);

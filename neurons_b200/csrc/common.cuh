@@ -280,14 +280,13 @@ inline double linear_bytes(const LinearArgs &a, int es) {
 struct FusedArgs {
     const void *x; void *y;
     int64_t xsb, xsc, xsf, ysb, ysc, ysf;
-    int B, F, P, A;
+    int B, F, P, A, pos_enc;
     const double *gn_partial; int gn_splits; double gn_count; float gn_eps;
-    const float *gn_w, *gn_b;
-    const void *w_in, *w_out, *w1, *w2;                     // packed bf16 weights (w1 GEGLU-interleaved)
+    const void *w_in_g, *w_out, *w1, *w2;                   // packed bf16 weights (w_in_g: GroupNorm gamma folded in; w1 GEGLU-interleaved)
     const void *wqkv_t[NMM_MAX_ATTN], *wo[NMM_MAX_ATTN];    // q|k|v in head-pair tile order; to_out
     const void *wo_tail[NMM_MAX_ATTN];                      // to_out columns 64-79 of every head pair, un-swizzled operand layout
-    const float *ln_w[NMM_MAX_ATTN], *ln_b[NMM_MAX_ATTN], *pe[NMM_MAX_ATTN];
-    const float *ff_ln_w, *ff_ln_b, *b1, *cbias, *b_out;
+    const float *vec_attn[NMM_MAX_ATTN], *vec_ff, *vec_fin; // fp32 vector blocks (FmParams, fused_module.cu)
+    const float *b1;
     float ln_eps;
     float *stage_dump; int stage_id;                         // tests: snapshot of the residual stream after stage stage_id (or null)
 };
