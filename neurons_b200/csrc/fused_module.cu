@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(FM_THREADS, 1) fused_module_kernel(const __gri
                                 next();
                             }
                             if (i == 0) FM_TRACE(220 + 3 * hp + s);
-                            if (s == 1 && hp > 0) tproj(hp - 1);
+                            if (s == 2 && hp > 0) tproj(hp - 1);       // after the pair's last unit: the attention of pair hp waits for that unit, not for this
                         }
                     }
                     tproj(3);
@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(FM_THREADS, 1) fused_module_kernel(const __gri
             auto adesc = [&](uint32_t base, int chunk) { return ptx::umma_smem_desc_interleave(base + (uint32_t)chunk * FM_CHUNK, FM_CHUNK, 128); };
             // barriers the epilogue warps (of both CTAs) arrive on: acquire at cluster scope
             auto wait_epi = [&](uint32_t bar, uint32_t parity) {
-                if constexpr (CG == 1) ptx::mbar_wait(bar, parity); else ptx::mbar_wait_cluster(bar, parity);
+                ptx::mbar_wait(bar, parity);
                 ptx::tc_fence_after();
             };
             auto wait_a1 = [&]() { wait_epi(a1_ready, n_a1 & 1u); n_a1++; };
@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(FM_THREADS, 1) fused_module_kernel(const __gri
                             commit(s_full(b));
                             n_unit++;
                             FM_TRACE(102 + 20 * i + 3 * hp + s);
-                            if (s == 1 && hp > 0) { tproj(false); FM_TRACE(102 + 20 * i + 12 + hp - 1); }
+                            if (s == 2 && hp > 0) { tproj(false); FM_TRACE(102 + 20 * i + 12 + hp - 1); }
                         }
                     }
                     tproj(true);
@@ -559,7 +559,7 @@ __global__ void __launch_bounds__(FM_THREADS, 1) fused_module_kernel(const __gri
         auto wait_h = [&]() { ptx::mbar_wait(h_done, n_hd & 1u); n_hd++; ptx::tc_fence_after(); };
         // arrive on a barrier the MMA thread waits on (it lives in the even CTA of a pair)
         auto arrive_mma = [&](uint32_t bar) {
-            if constexpr (CG == 1) ptx::mbar_arrive(bar); else ptx::mbar_arrive_cluster(bar & ptx::PEER_MASK);
+            if constexpr (CG == 1) ptx::mbar_arrive(bar); else ptx::mbar_arrive_remote(bar & ptx::PEER_MASK);
         };
         auto publish_a1 = [&]() {                                // generic-proxy writes of A1 -> visible to the tensor core, then arrive
             ptx::fence_proxy_async();
@@ -789,14 +789,17 @@ __global__ void __launch_bounds__(FM_THREADS, 1) fused_module_kernel(const __gri
             stage_vec(VF + 8 * FM_C * 4, p.vec_fin, 160);            // cb_{A+1} | b_out
             fm_bar_epi();
             for (int j = 0; j < FM_FF_CHUNKS; j++) {
+                if (j == 10) FM_ETRACE(240);
                 ptx::mbar_wait(g_full, n_g & 1u);
                 ptx::tc_fence_after();
+                if (j == 10) FM_ETRACE(241);
                 uint32_t r[32];
                 ptx::tmem_ld32(t_lane + FM_TM_S + 32 * sub, r);
                 ptx::tmem_ld_wait();
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) arrive_mma(g_free);             // S may take the next chunk while the GELUs run
+                if (j == 10) FM_ETRACE(242);
                 const uint32_t b1v = VF + (uint32_t)(j * 128 + 32 * sub) * 4;
                 uint32_t o[8];
 #pragma unroll
@@ -809,7 +812,9 @@ __global__ void __launch_bounds__(FM_THREADS, 1) fused_module_kernel(const __gri
                     o[i4] = pack_bf16x2(y0, y1);
                 }
                 const int ab = (int)(n_g % FM_ACT_BUFS);
+                if (j == 10) FM_ETRACE(243);
                 ptx::mbar_wait(act_free(ab), ((n_g / FM_ACT_BUFS) & 1u) ^ 1u);       // ff_out has consumed this buffer's previous chunk
+                if (j == 10) FM_ETRACE(244);
                 n_g++;
                 const uint32_t dst = T + (uint32_t)ab * FM_ACT_BYTES + (uint32_t)(2 * sub) * FM_CHUNK + (uint32_t)m * 16;
                 fm_sts128(dst, o[0], o[1], o[2], o[3]);

@@ -88,6 +88,12 @@ __device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap *m, uint32_t b
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
+// Same, with the default (CTA-scope release) semantics: what a consumer->producer "buffer free" / "operand written" signal needs when the
+// data itself stays in this CTA's shared / tensor memory (made visible by fence.proxy.async / tcgen05.fence before the arrive).  The
+// cluster-scope release above costs a MEMBAR + error barriers per arrive -- hundreds of cycles in a per-chunk handshake.
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar_cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
 
 // 2-D tiled store shared -> global (bulk async group); out-of-range rows / columns of the box are clipped by the hardware.
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap *m, uint32_t src_smem, int32_t c0, int32_t c1) {

@@ -56,8 +56,10 @@ for j in range(20):
     names[45 + j] = f"ff chunk {j}: act published"
     names[150 + j] = f"mma: G_{j} issued"
     names[175 + j] = f"mma: F_{j} issued"
+names.update({240: "chunk10: start (waiting for the accumulator)", 241: "chunk10: accumulator ready", 242: "chunk10: loaded from TMEM", 243: "chunk10: GELUs done",
+              244: "chunk10: activation buffer free"})
 prev = {0: t0, 1: t0, 2: t0}
 for k in sorted(t, key=lambda k: t[k]):
-    side_ = 0 if k < 100 else (1 if k < 220 else 2)
+    side_ = 0 if (k < 100 or k >= 240) else (1 if k < 220 else 2)
     print(f"{t[k] - t0:9d}  (+{t[k] - prev[side_]:7d})  {('EPI', 'MMA', 'PRD')[side_]}  {names.get(k, k)}")
     prev[side_] = t[k]
