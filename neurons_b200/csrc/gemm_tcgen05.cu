@@ -102,7 +102,7 @@ constexpr int TC_A_HALF = TC_A_BYTES / 2;                 // GNA: the A stage is
 constexpr int TRACE_TILES = 48, TRACE_SLOTS = 16;
 #define TRACE(tile_no, slot)                                                                          \
     do {                                                                                              \
-        if (p.trace != nullptr && blockIdx.x == 0 && (tile_no) < TRACE_TILES) p.trace[(tile_no) * TRACE_SLOTS + (slot)] = clock64(); \
+        if (p.trace != nullptr && blockIdx.x == 0 && (tile_no) < TRACE_TILES && (threadIdx.x & 31) == 0) p.trace[(tile_no) * TRACE_SLOTS + (slot)] = clock64(); \
     } while (0)
 #else
 #define TRACE(tile_no, slot) do { } while (0)
@@ -209,7 +209,10 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int num_kb = (p.K + TC_BK - 1) / TC_BK;
     // Tile schedule: a cluster walks (m_group, n_blk) pairs; CTA `rank` of the cluster owns m-block m_group*CG + rank.
     // Both CTAs of a pair run the same number of iterations (a phantom m-block past the end is all zero-fill + clipped).
-    const uint32_t rank = CG > 1 ? ptx::cluster_ctarank() : 0u;
+    // rank inside the (CG, 1, 1) cluster = blockIdx.x % CG, taken from blockIdx on purpose: the compiler must KNOW it is uniform.  With
+    // %cluster_ctarank the leader-only MMA role compiled as divergent code -- every tcgen05.mma / TMA operand was built in vector
+    // registers and moved to the uniform file by a waterfall loop, ~100 issue cycles per MMA (more than an N = 160 MMA takes to run).
+    const uint32_t rank = CG > 1 ? (blockIdx.x % (unsigned)CG) : 0u;
     const bool leader = rank == 0;
     const int64_t cluster_id = blockIdx.x / CG, num_clusters = gridDim.x / CG;
 
@@ -241,7 +244,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 
     if (warp == 0) {
         // ===================== TMA producer (every CTA: its A rows, its slice of W) =====================
-        if (lane == 0) {
+        // (the whole warp runs the schedule and the barrier waits; one elected lane issues -- keeps every TMA operand in uniform registers)
+        {
             int stage = 0; uint32_t phase = 0;
             int tile_no = 0;
             for (int64_t ct = cluster_id; ct < p.cluster_tiles; ct += num_clusters, tile_no++) {
@@ -250,7 +254,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 const int64_t m_blk = m_grp * CG + rank;
                 if constexpr (EPI == NMM_EPI_RESIDUAL) {
                     // the epilogue will read-modify-write this tile's fp32 residual rows: pull them into L2 now
-                    if (!(TC_DEBUG(p) & 2))
+                    if (!(TC_DEBUG(p) & 2) && ptx::elect_one())
                         for (int c0 = 0; c0 < p.block_n; c0 += 32)
                             for (int r0 = 0; r0 < TC_BM; r0 += 32)
                                 ptx::tma_prefetch_l2_2d(&tm_h, n_blk * p.block_n + c0, (int32_t)(m_blk * TC_BM + r0));
@@ -269,6 +273,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     if (kb == 0) TRACE(tile_no, 4);
                     if (kb == num_kb - 1) TRACE(tile_no, 5);
                     const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
+                    if (ptx::elect_one()) {
                     if (TC_DEBUG(p) & 2) {                                  // timing experiment: MMA on whatever is in shared memory
                         if (leader) ptx::mbar_arrive(full_bar(stage));
                     } else if (EPI == NMM_EPI_QKV_ATTN) {
@@ -301,13 +306,16 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                             ptx::tma_load_2d_2sm(&tm_w, bar0, sa + TC_A_BYTES, kb * TC_BK, n_blk * p.block_n + (int)(rank * b_rows));
                         }
                     }
+                    }
+                    __syncwarp();
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (one thread of the even CTA) =====================
-        if (lane == 0 && leader) {
+        // (whole warp; one elected lane issues the tcgen05 instructions)
+        if (leader) {
             const uint32_t n_mma = p.wide ? (uint32_t)p.block_n / 2 : (uint32_t)p.block_n;      // columns per MMA instruction
             const uint32_t idesc = ptx::umma_idesc_bf16(TC_BM * CG, n_mma) | (GNA ? ptx::UMMA_IDESC_A_MN_MAJOR : 0u);
             int stage = 0; uint32_t phase = 0;
@@ -326,6 +334,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     ptx::tc_fence_after();
                     const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
                     const uint64_t b_desc = ptx::umma_smem_desc_sw128(sa + TC_A_BYTES);
+                    if (ptx::elect_one()) {
                     if constexpr (GNA) {
                         // M-major A: 64-position blocks 8 KB apart (LBO), 8-channel groups 1 KB apart (SBO); K = 16 channels = 2 KB
                         const uint64_t a_desc = ptx::umma_smem_desc_mn_sw128(sa, TC_A_HALF, 1024);
@@ -356,9 +365,12 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         }
                     }
                     ptx::umma_commit<CG>(empty_bar(stage));               // stage reusable (in both CTAs) once these MMAs retire
+                    }
+                    __syncwarp();
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
-                ptx::umma_commit<CG>(tfull_bar(as));                      // accumulator complete (signalled in both CTAs)
+                if (ptx::elect_one()) ptx::umma_commit<CG>(tfull_bar(as));    // accumulator complete (signalled in both CTAs)
+                __syncwarp();
                 TRACE(tile_no, 3);
                 if (p.wide) aphase ^= 1u;                                 // single accumulator: its barriers change phase every tile
                 else if (++as == 2) { as = 0; aphase ^= 1u; }
