@@ -193,6 +193,50 @@ def cpu_reference_time(sample: str, threads: int):
     return flops, run, desc
 
 
+def gpu_eager_baseline(dev, steps: int = 3):
+    """The reference's op sequence (oracle port, op-for-op the reference's torch calls incl. its layout copies) on CUDA tensors under
+    stock torch eager -- "the reference on the same box": what cuBLAS + ATen make of the same step, in bf16 and in fp32 (TF32 off).
+    A reported anchor, not the product path.  Returns {dtype: {ms_per_step, tflops}}."""
+    from neurons_b200 import workloads as wl
+    from oracle import motion_oracle as mo
+    calls = wl.unet_step_calls(LATENT)
+    flops = wl.step_flops(calls, BATCH, FRAMES)
+    out = {}
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        for dt in (torch.bfloat16, torch.float32):
+            params, xs = {}, []
+            g = torch.Generator().manual_seed(7)
+            for c in calls:
+                if c.channels not in params:
+                    cfg = mo.MotionConfig(c.channels, 8, 1, c.attn_blocks, True, c.max_len)
+                    params[c.channels] = (cfg, {k: ((torch.rand(s, generator=g) * 2 - 1) / (s[-1] ** 0.5 if len(s) == 2 else 1.0)).to(dev, dt)
+                                                for k, s in mo.param_shapes(cfg).items()})
+                xs.append(torch.randn(BATCH, FRAMES, c.channels, c.side, c.side, device=dev, dtype=dt).permute(0, 2, 1, 3, 4))
+
+            def step():
+                for c, x in zip(calls, xs):
+                    cfg, prm = params[c.channels]
+                    mo.forward_reference_order(prm, x, cfg)
+            with torch.no_grad():
+                step()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(steps):
+                    step()
+                e1.record()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out["bf16" if dt == torch.bfloat16 else "f32"] = {"ms_per_step": ms, "tflops": flops / (ms * 1e-3) / 1e12}
+            del params, xs
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+    return out
+
+
 def run_reference_arm(args, rank):
     """--impl reference: the reference's own CPU implementation of the path (oracle port; the reference is pure Python
     and ships no installable package), all host threads, same metric/config.  Rank 0 only."""
@@ -232,6 +276,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the host-CPU baseline leg")
     ap.add_argument("--no-clips", action="store_true", help="skip the 25-step clip loop (secondary metric)")
+    ap.add_argument("--no-eager", action="store_true", help="skip the stock-torch-eager GPU anchor")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -359,6 +404,12 @@ def main():
         torch.cuda.synchronize()
         copy_ms = 1e3 * (time.perf_counter() - t0) / 3
 
+    eager = None
+    if rank == 0 and not args.no_eager:
+        try:
+            eager = gpu_eager_baseline(dev)
+        except Exception as e:        # a reported anchor only: never fail the bench line over it
+            eager = {"error": repr(e)[:200]}
     clip_ms, clip_flops = (0.0, 0.0) if args.no_clips else clip_loop(nb, wl, dev)
     clip4_ms, clip4_flops = (0.0, 0.0) if args.no_clips else clip_loop(nb, wl, dev, clips=2, clip_batch=4)       # BASELINE configs[3]: 4 clips per GPU
     # max over ranks
@@ -372,27 +423,41 @@ def main():
 
     if rank == 0:
         peaks = measured_peaks()
-        gemm = prof["linear_bf16_tcgen05"]
-        # the GEMM is timed inside a long (multi-second) step -> sustained cuBLAS figure is the denominator
-        peak_tf = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
-        ach = gemm["flops"] / (gemm["total_ms"] * 1e-3) / 1e12 if gemm["total_ms"] > 0 else 0.0
+        gemm, fused = prof["linear_bf16_tcgen05"], prof["fused_module_tcgen05"]
+        # Denominator: the BURST cuBLAS figure.  The timed region is a fraction of a second at ~max SM clock (see `clocks`); the
+        # sustained figure belongs to seconds-long loops under the power cap.  Both fractions are printed.
+        peak_tf = peaks["bf16_tflops"] or peaks["bf16_tflops_sustained"]
+        tc_ms = gemm["total_ms"] + fused["total_ms"]
+        tc_flops = gemm["flops"] + fused["flops"]
+
+        def tf(v):
+            return v["flops"] / (v["total_ms"] * 1e-3) / 1e12 if v["total_ms"] > 0 else 0.0
+        ach = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
         traffic = None          # DRAM bytes per launch of the dominant kernel from the committed ncu capture of this same step
-        tpath = os.path.join(ROOT, "profiles", "r1_ncu_gemm_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r2_ncu_gemm_traffic.json")
         if os.path.isfile(tpath):
             with open(tpath) as f:
                 traffic = json.load(f).get("dram_bytes_per_launch")
-        roofline = {"kernel": "linear_tc_kernel (tcgen05 bf16 GEMM + fused epilogue)", "bound": "tensor", "achieved": ach,
-                    "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None, "traffic": traffic,
-                    "traffic_note": "dram__bytes_read+write per launch, ncu capture of this step (profiles/r1_ncu_step_summary.txt); "
+        roofline = {"kernel": "tcgen05 kernels: linear_tc_kernel (bf16 GEMM + fused epilogue; C >= 640 levels) and fused_module_kernel (the whole "
+                              "C = 320 module in one kernel)",
+                    "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None,
+                    "frac_of_sustained_peak": ach / peaks["bf16_tflops_sustained"] if peaks.get("bf16_tflops_sustained") else None,
+                    "traffic": traffic,
+                    "traffic_note": "dram__bytes_read+write per linear_tc_kernel launch, ncu capture of this step (profiles/); "
                                     "algorithmic bytes per launch = %.1f MB" % (gemm["bytes"] / max(gemm["launches"], 1) / 1e6),
-                    "peak_source": peaks["source"] + ", bf16_tflops_sustained", "launches": gemm["launches"],
+                    "peak_source": peaks["source"] + ", bf16_tflops (burst)", "launches": gemm["launches"] + fused["launches"],
+                    "per_kernel": {"linear_tc_kernel": {"launches": gemm["launches"], "ms_per_step": gemm["total_ms"] / args.steps, "tflops": tf(gemm),
+                                                        "frac": tf(gemm) / peak_tf if peak_tf else None},
+                                   "fused_module_kernel": {"launches": fused["launches"], "ms_per_step": fused["total_ms"] / args.steps, "tflops": tf(fused),
+                                                           "frac": tf(fused) / peak_tf if peak_tf else None,
+                                                           "hbm_GBps": fused["bytes"] / (fused["total_ms"] * 1e-3) / 1e9 if fused["total_ms"] > 0 else None}},
                     "measured_over": f"a second pass of the same {args.steps} steps with a CUDA-event pair around every kernel launch "
                                      f"({ms_profiled / args.steps:.3f} ms/step with the events in the stream)",
-                    "share_of_step": gemm["total_ms"] / ms_profiled if ms_profiled else None,
+                    "share_of_step": tc_ms / ms_profiled if ms_profiled else None,
                     "other_kernels": {k: {"launches": v["launches"], "ms_per_step": v["total_ms"] / args.steps,
                                           "GBps": (v["bytes"] / (v["total_ms"] * 1e-3) / 1e9) if v["total_ms"] > 0 else None,
                                           "frac_of_hbm_peak": (v["bytes"] / (v["total_ms"] * 1e-3) / 1e9 / peaks["hbm_gbs"]) if v["total_ms"] > 0 and peaks["hbm_gbs"] else None}
-                                      for k, v in prof.items() if v["launches"] and k != "linear_bf16_tcgen05"}}
+                                      for k, v in prof.items() if v["launches"] and k not in ("linear_bf16_tcgen05", "fused_module_tcgen05")}}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
@@ -407,6 +472,8 @@ def main():
                         "note": "PCIe-bound when copies_alone_ms_per_step >= ms_per_step of the device-resident arm: the step's inputs and outputs "
                                 "(h2d + d2h bytes) cross the host link inside the timed region, both directions concurrently"},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+                "gpu_eager_baseline": None if eager is None else dict(eager, note="the oracle port's op sequence (= the reference's torch calls) on CUDA tensors under "
+                                                                                   "stock torch eager on this GPU, same step; fp32 with TF32 off"),
                 "clips": None if args.no_clips else {
                     "metric": "25-step video clips/s, motion modules only", "value": world * 1e3 / clip_ms, "unit": "clips/s", "ms_per_clip": clip_ms,
                     "tflops": world * clip_flops / (clip_ms * 1e-3) / 1e12,

@@ -216,8 +216,6 @@ class _Engine:
         self.cfg = None
         self.tensors = None      # name -> tensor, collected once (module.to() / .data updates keep the same objects)
         self.shape_cache = {}    # (shape, strides, dtype) -> (nmm_shape struct, workspace bytes)
-        self.pack_stream = None  # stream the packing kernels ran on + an event recorded behind them
-        self.pack_event = None
         self.checksum = None
 
     @staticmethod
@@ -246,19 +244,14 @@ class _Engine:
                     raise RuntimeError(f"neurons_b200: parameter '{k}' is on {t.device}, input on {x.device}")
                 dev_tensors[k] = t.reshape(t.shape[-2:]) if k.endswith("pos_encoder.pe") else t
             self.packed = ops.pack_params(self.cfg, dev_tensors, x.dtype, x.device)
-            self.pack_stream = torch.cuda.current_stream(x.device)
-            self.pack_event = torch.cuda.Event()
-            self.pack_event.record(self.pack_stream)
+            # once per (module, weights): wait for the packing kernels, so that the packed buffer may be used from ANY stream afterwards
+            # (another stream, or a CUDA-graph capture, must not depend on un-captured work of the stream that packed)
+            torch.cuda.current_stream(x.device).synchronize()
             self.key = key
             self.shape_cache.clear()
             if _WEIGHT_CHECK:
                 self.checksum = self._checksum(tensors)
         else:
-            if self.pack_event is not None:
-                cur = torch.cuda.current_stream(x.device)
-                if cur != self.pack_stream:
-                    cur.wait_event(self.pack_event)          # first use on another stream: order it behind the packing kernels
-                    self.pack_stream = cur                   # (later calls on this stream are ordered by the stream itself)
             if _WEIGHT_CHECK and not torch.cuda.is_current_stream_capturing():
                 now = self._checksum(tensors)
                 if now != self.checksum:
@@ -299,7 +292,6 @@ def invalidate(model: nn.Module) -> int:
             eng.key = None
             eng.packed = None
             eng.tensors = None
-            eng.pack_event = None
             n += 1
     return n
 

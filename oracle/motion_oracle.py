@@ -154,7 +154,7 @@ def forward_reference_order(params: Dict[str, torch.Tensor], x: torch.Tensor, cf
     P = H * W
     nh, dh = cfg.heads, cfg.head_dim
     t = "temporal_transformer."
-    pe = positional_encoding(cfg.max_len, C).to(x.dtype) if cfg.pos_enc else None
+    pe = positional_encoding(cfg.max_len, C).to(device=x.device, dtype=x.dtype) if cfg.pos_enc else None
 
     h = x.permute(0, 2, 1, 3, 4).reshape(B * F, C, H, W)                    # :137  b c f h w -> (b f) c h w
     residual = h                                                           # :140
@@ -178,7 +178,7 @@ def forward_reference_order(params: Dict[str, torch.Tensor], x: torch.Tensor, cf
             def split(z):                                                            # motion_module_new.py:181-186
                 return z.reshape(B * P, F, nh, dh).permute(0, 2, 1, 3).reshape(B * P * nh, F, dh)
             q, k, v = split(q), split(k), split(v)
-            s = torch.baddbmm(torch.empty(q.shape[0], F, F, dtype=q.dtype), q, k.transpose(-1, -2),
+            s = torch.baddbmm(torch.empty(q.shape[0], F, F, dtype=q.dtype, device=q.device), q, k.transpose(-1, -2),
                               beta=0, alpha=dh ** -0.5)                               # motion_module_new.py:263-269
             p = s.softmax(dim=-1)                                                    # :277
             o = torch.bmm(p, v)                                                      # :283

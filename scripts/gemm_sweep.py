@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Development tool: sweep N-tile width and CTA-pair mode of the tcgen05 GEMM over the step's shapes (forces the tiling through
-NMM_GEMM_BLOCK_N / NMM_GEMM_CLUSTER) and print device time per variant."""
+nmm_set_option: NMM_OPT_GEMM_BLOCK_N / NMM_OPT_GEMM_CLUSTER) and print device time per variant."""
 import json, os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -35,10 +35,9 @@ def main():
             for cg in (1, 2):
                 for bn in range(256, 63, -gran):
                     if N % bn: continue
-                    os.environ["NMM_GEMM_CLUSTER"] = str(cg); os.environ["NMM_GEMM_BLOCK_N"] = str(bn)
-                    ms = timed(fn, flush)
+                    with nlib.options({nlib.OPT_GEMM_CLUSTER: cg, nlib.OPT_GEMM_BLOCK_N: bn}):
+                        ms = timed(fn, flush)
                     res.append((ms, bn, cg))
-            os.environ.pop("NMM_GEMM_CLUSTER"); os.environ.pop("NMM_GEMM_BLOCK_N")
             auto = timed(fn, flush)
             res.sort()
             fl = 2.0 * M * N * K

@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--frames", type=int, default=8)
     ap.add_argument("--latent", type=int, default=64)
     ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--ln-fold", action="store_true", help="fold the LayerNorms into the QKV / GEGLU GEMMs (multi-kernel pipeline levels)")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     kw = dict(num_attention_heads=8, num_transformer_block=1, attention_block_types=("Temporal_Self", "Temporal_Self"),
@@ -29,6 +30,9 @@ def main():
         with torch.no_grad():
             with torch.device(dev):
                 mods = [nb.get_motion_module(C, "Vanilla", kw).to(torch.bfloat16).eval() for _ in range(4)]
+            if a.ln_fold:
+                for m in mods:
+                    m.__dict__["_nmm_ln_fold"] = True
             xs = [torch.randn(a.batch, a.frames, C, side, side, device=dev, dtype=torch.bfloat16).permute(0, 2, 1, 3, 4) for _ in range(4)]
             for m, x in zip(mods, xs):
                 m(x, None, None)
