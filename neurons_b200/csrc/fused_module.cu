@@ -586,7 +586,10 @@ __global__ void __launch_bounds__(FM_THREADS, 1) fused_module_kernel(const __gri
             float x0;
             asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x0) : "r"(vb));
             x0 += __uint_as_float(h0);                               // shift by the row's first element: keeps the one-pass variance well conditioned
-            float s1 = 0.f, s2 = 0.f;
+            // (packed fp32x2 arithmetic: the phase is instruction-bound -- 16 warps x 80 columns -- and FADD2 / FFMA2 halve the FP count;
+            //  same operation order per element as the scalar form, hence the same roundings)
+            const uint64_t nx0 = f32x2_pack(-x0, -x0);
+            uint64_t s1p = f32x2_pack(0.f, 0.f), s2p = s1p;
 #pragma unroll
             for (int k = 0; k < 5; k++) {
                 uint32_t r[16];
@@ -597,13 +600,17 @@ __global__ void __launch_bounds__(FM_THREADS, 1) fused_module_kernel(const __gri
                 ptx::tmem_ld_wait();
 #pragma unroll
                 for (int j4 = 0; j4 < 4; j4++) {
-                    const float d0 = __uint_as_float(r[4 * j4]) + c4[j4].x - x0, d1 = __uint_as_float(r[4 * j4 + 1]) + c4[j4].y - x0;
-                    const float d2 = __uint_as_float(r[4 * j4 + 2]) + c4[j4].z - x0, d3 = __uint_as_float(r[4 * j4 + 3]) + c4[j4].w - x0;
-                    s1 += (d0 + d1) + (d2 + d3);
-                    s2 = fmaf(d0, d0, s2); s2 = fmaf(d1, d1, s2); s2 = fmaf(d2, d2, s2); s2 = fmaf(d3, d3, s2);
+                    const uint64_t d01 = f32x2_add(f32x2_add(f32x2_pack(__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1])), f32x2_pack(c4[j4].x, c4[j4].y)), nx0);
+                    const uint64_t d23 = f32x2_add(f32x2_add(f32x2_pack(__uint_as_float(r[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3])), f32x2_pack(c4[j4].z, c4[j4].w)), nx0);
+                    s1p = f32x2_add(s1p, f32x2_add(d01, d23));
+                    s2p = f32x2_fma(d01, d01, s2p);
+                    s2p = f32x2_fma(d23, d23, s2p);
                 }
             }
-            reinterpret_cast<float2 *>(scr)[m * 4 + sub] = make_float2(s1, s2);
+            float s1a, s1b, s2a, s2b;
+            f32x2_unpack(s1p, s1a, s1b);
+            f32x2_unpack(s2p, s2a, s2b);
+            reinterpret_cast<float2 *>(scr)[m * 4 + sub] = make_float2(s1a + s1b, s2a + s2b);
             fm_bar_quad(q);
             float S1 = 0.f, S2 = 0.f;
 #pragma unroll
@@ -611,6 +618,7 @@ __global__ void __launch_bounds__(FM_THREADS, 1) fused_module_kernel(const __gri
             const float md = S1 * (1.0f / FM_C);
             const float mean = x0 + md;
             const float rstd = rsqrtf(fmaxf(S2 * (1.0f / FM_C) - md * md, 0.f) + p.ln_eps);
+            const uint64_t nmean = f32x2_pack(-mean, -mean), rs2 = f32x2_pack(rstd, rstd);
 #pragma unroll
             for (int k = 0; k < 5; k++) {
                 const int c0 = cbeg + 16 * k;
@@ -620,19 +628,25 @@ __global__ void __launch_bounds__(FM_THREADS, 1) fused_module_kernel(const __gri
 #pragma unroll
                 for (int j4 = 0; j4 < 4; j4++) c4[j4] = lds4(cbv + (uint32_t)(16 * k + 4 * j4) * 4);
                 ptx::tmem_ld_wait();
-                float o[16];
+                uint32_t o[8];
 #pragma unroll
                 for (int j4 = 0; j4 < 4; j4++) {
                     const float4 gm = lds4(gmv + (uint32_t)(16 * k + 4 * j4) * 4);
                     const float4 bt = lds4(btv + (uint32_t)(16 * k + 4 * j4) * 4);
-                    o[4 * j4] = fmaf((__uint_as_float(r[4 * j4]) + c4[j4].x - mean) * rstd, gm.x, bt.x);
-                    o[4 * j4 + 1] = fmaf((__uint_as_float(r[4 * j4 + 1]) + c4[j4].y - mean) * rstd, gm.y, bt.y);
-                    o[4 * j4 + 2] = fmaf((__uint_as_float(r[4 * j4 + 2]) + c4[j4].z - mean) * rstd, gm.z, bt.z);
-                    o[4 * j4 + 3] = fmaf((__uint_as_float(r[4 * j4 + 3]) + c4[j4].w - mean) * rstd, gm.w, bt.w);
+                    // ((h + cb) - mean) * rstd * gamma + (beta + pe)
+                    uint64_t t01 = f32x2_add(f32x2_add(f32x2_pack(__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1])), f32x2_pack(c4[j4].x, c4[j4].y)), nmean);
+                    uint64_t t23 = f32x2_add(f32x2_add(f32x2_pack(__uint_as_float(r[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3])), f32x2_pack(c4[j4].z, c4[j4].w)), nmean);
+                    t01 = f32x2_fma(f32x2_mul(t01, rs2), f32x2_pack(gm.x, gm.y), f32x2_pack(bt.x, bt.y));
+                    t23 = f32x2_fma(f32x2_mul(t23, rs2), f32x2_pack(gm.z, gm.w), f32x2_pack(bt.z, bt.w));
+                    float a0, a1, a2, a3;
+                    f32x2_unpack(t01, a0, a1);
+                    f32x2_unpack(t23, a2, a3);
+                    o[2 * j4] = pack_bf16x2(a0, a1);
+                    o[2 * j4 + 1] = pack_bf16x2(a2, a3);
                 }
                 const uint32_t dst = A1 + (uint32_t)(c0 >> 3) * FM_CHUNK + (uint32_t)m * 16;
-                fm_sts128(dst, pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
-                fm_sts128(dst + FM_CHUNK, pack_bf16x2(o[8], o[9]), pack_bf16x2(o[10], o[11]), pack_bf16x2(o[12], o[13]), pack_bf16x2(o[14], o[15]));
+                fm_sts128(dst, o[0], o[1], o[2], o[3]);
+                fm_sts128(dst + FM_CHUNK, o[4], o[5], o[6], o[7]);
             }
             publish_a1();
         };
@@ -653,23 +667,31 @@ __global__ void __launch_bounds__(FM_THREADS, 1) fused_module_kernel(const __gri
                 }
             }
         };
-        // x tile -> staging [c][m] (raw bf16, 16-byte pieces of 8 positions; T + CTX = 80 KB)
+        // x tile -> staging (T + CTX = 80 KB): one 32-bit word per (channel PAIR, row): word (c / 2) * 128 + m = {x[c][m], x[c + 1][m]}, so that the
+        // row's owner reads / writes two channels per shared-memory access.  Global side: 16-byte pieces of 8 positions of one channel.
+        auto prmt = [](uint32_t a, uint32_t b, uint32_t sel) { uint32_t d; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel)); return d; };
         auto load_x_tile = [&](const bf16 *xb, uint4 (&v)[10]) {
 #pragma unroll
-            for (int i = 0; i < 10; i++) {
-                const int it = et + FM_ETHREADS * i;
-                const int c = it >> 4, piece = it & 15;
+            for (int i = 0; i < 5; i++) {
+                const int it = et + FM_ETHREADS * i;                   // 2560 items: (channel pair, piece of 8 positions)
+                const int cp = it >> 4, piece = it & 15;
                 const int m0 = piece * 8, f = m0 / PPT, pl0 = m0 % PPT;
-                v[i] = __ldg(reinterpret_cast<const uint4 *>(xb + (int64_t)c * p.xsc + (int64_t)f * p.xsf + pl0));
+                const bf16 *src = xb + (int64_t)(2 * cp) * p.xsc + (int64_t)f * p.xsf + pl0;
+                v[2 * i] = __ldg(reinterpret_cast<const uint4 *>(src));
+                v[2 * i + 1] = __ldg(reinterpret_cast<const uint4 *>(src + p.xsc));
             }
         };
         auto store_x_tile = [&](const uint4 (&v)[10]) {
 #pragma unroll
-            for (int i = 0; i < 10; i++) {
+            for (int i = 0; i < 5; i++) {
                 const int it = et + FM_ETHREADS * i;
-                fm_sts128(T + (uint32_t)(it >> 4) * 256 + (uint32_t)(it & 15) * 16, v[i].x, v[i].y, v[i].z, v[i].w);
+                const uint4 a = v[2 * i], c = v[2 * i + 1];
+                const uint32_t dst = T + (uint32_t)((it >> 4) * 128 + (it & 15) * 8) * 4;
+                fm_sts128(dst, prmt(a.x, c.x, 0x5410), prmt(a.x, c.x, 0x7632), prmt(a.y, c.y, 0x5410), prmt(a.y, c.y, 0x7632));
+                fm_sts128(dst + 16, prmt(a.z, c.z, 0x5410), prmt(a.z, c.z, 0x7632), prmt(a.w, c.w, 0x5410), prmt(a.w, c.w, 0x7632));
             }
         };
+        auto lds32 = [](uint32_t addr) { uint32_t v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v; };
 
         for (int64_t t = tile0; t < p.ntiles; t += tstep) {
             const int b = (int)(t / p.tiles_per_b);
@@ -696,16 +718,16 @@ __global__ void __launch_bounds__(FM_THREADS, 1) fused_module_kernel(const __gri
                 fm_bar_epi();
                 if (warp == 0 && lane == 0) ptx::mbar_arrive(x_taken);       // the prefetcher may run one more tile ahead
                 FM_ETRACE(1);
-                for (int ck = 10 * sub; ck < 10 * sub + 10; ck++) {         // this row, 8 channels at a time
-                    float o[8];
+                for (int ck = 10 * sub; ck < 10 * sub + 10; ck++) {         // this row, 8 channels (4 staged pairs) at a time
+                    uint32_t w[4];
 #pragma unroll
-                    for (int e = 0; e < 8; e++) {
-                        const int c = ck * 8 + e;
+                    for (int i2 = 0; i2 < 4; i2++) {
+                        const int c = ck * 8 + 2 * i2;                      // both channels of a pair lie in one GroupNorm group (10 channels)
                         const float2 ab = reinterpret_cast<const float2 *>(scr)[f_m * NMM_GN_GROUPS + c / (FM_C / NMM_GN_GROUPS)];
-                        o[e] = fmaf(__uint_as_float(fm_lds_u16(T + (uint32_t)c * 256 + (uint32_t)m * 2) << 16), ab.x, ab.y);
+                        const uint32_t xw = lds32(T + (uint32_t)((ck * 4 + i2) * 128 + m) * 4);
+                        w[i2] = pack_bf16x2(fmaf(bf16_lo(xw), ab.x, ab.y), fmaf(bf16_hi(xw), ab.x, ab.y));
                     }
-                    fm_sts128(A1 + (uint32_t)ck * FM_CHUNK + (uint32_t)m * 16, pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
-                              pack_bf16x2(o[6], o[7]));
+                    fm_sts128(A1 + (uint32_t)ck * FM_CHUNK + (uint32_t)m * 16, w[0], w[1], w[2], w[3]);
                 }
                 publish_a1();
             }
@@ -873,34 +895,38 @@ __global__ void __launch_bounds__(FM_THREADS, 1) fused_module_kernel(const __gri
                     float4 b4[4];
 #pragma unroll
                     for (int j4 = 0; j4 < 4; j4++) b4[j4] = lds4(sb + FM_SCR + (uint32_t)(c0 + 4 * j4) * 4);
-                    uint32_t xv[16];
+                    uint32_t xw[8];
 #pragma unroll
-                    for (int j = 0; j < 16; j++) xv[j] = fm_lds_u16(T + (uint32_t)(c0 + j) * 256 + (uint32_t)m * 2);
+                    for (int j = 0; j < 8; j++) xw[j] = lds32(T + (uint32_t)((c0 / 2 + j) * 128 + m) * 4);
                     ptx::tmem_ld_wait();
                     const float bb[16] = {b4[0].x, b4[0].y, b4[0].z, b4[0].w, b4[1].x, b4[1].y, b4[1].z, b4[1].w,
                                           b4[2].x, b4[2].y, b4[2].z, b4[2].w, b4[3].x, b4[3].y, b4[3].z, b4[3].w};
 #pragma unroll
-                    for (int j = 0; j < 16; j++) {
-                        const bf16 yv = __float2bfloat16_rn(__uint_as_float(r[j]) + bb[j] + __uint_as_float(xv[j] << 16));
-                        asm volatile("st.shared.u16 [%0], %1;" ::"r"(T + (uint32_t)(c0 + j) * 256 + (uint32_t)m * 2), "h"(*reinterpret_cast<const uint16_t *>(&yv)) : "memory");
-                    }
+                    for (int j = 0; j < 8; j++)
+                        fm_sts32(T + (uint32_t)((c0 / 2 + j) * 128 + m) * 4, pack_bf16x2(__uint_as_float(r[2 * j]) + bb[2 * j] + bf16_lo(xw[j]),
+                                                                                             __uint_as_float(r[2 * j + 1]) + bb[2 * j + 1] + bf16_hi(xw[j])));
                 }
                 ptx::tc_fence_before();      // this tile's TMEM reads are ordered before the next tile's a1_ready arrive -> proj_in may overwrite H
                 fm_bar_epi();
                 bf16 *yb = p.y + (int64_t)b * p.ysb + p0;
                 if (p.y_vec16) {
 #pragma unroll
-                    for (int i = 0; i < 10; i++) {
+                    for (int i = 0; i < 5; i++) {
                         const int it = et + FM_ETHREADS * i;
-                        const int c = it >> 4, piece = it & 15;
+                        const int cp = it >> 4, piece = it & 15;
                         const int m0 = piece * 8, f = m0 / PPT, pl0 = m0 % PPT;
-                        const uint4 w = fm_lds128(T + (uint32_t)c * 256 + (uint32_t)piece * 16);
-                        *reinterpret_cast<uint4 *>(yb + (int64_t)c * p.ysc + (int64_t)f * p.ysf + pl0) = w;
+                        const uint32_t src = T + (uint32_t)(cp * 128 + piece * 8) * 4;
+                        const uint4 lo = fm_lds128(src), hi = fm_lds128(src + 16);
+                        bf16 *dst = yb + (int64_t)(2 * cp) * p.ysc + (int64_t)f * p.ysf + pl0;
+                        *reinterpret_cast<uint4 *>(dst) = make_uint4(prmt(lo.x, lo.y, 0x5410), prmt(lo.z, lo.w, 0x5410), prmt(hi.x, hi.y, 0x5410), prmt(hi.z, hi.w, 0x5410));
+                        *reinterpret_cast<uint4 *>(dst + p.ysc) = make_uint4(prmt(lo.x, lo.y, 0x7632), prmt(lo.z, lo.w, 0x7632), prmt(hi.x, hi.y, 0x7632), prmt(hi.z, hi.w, 0x7632));
                     }
                 } else {                                             // y rows not 16-byte aligned: element stores (lanes = consecutive positions)
-                    for (int c = sub; c < FM_C; c += 4) {
-                        const uint32_t w = fm_lds_u16(T + (uint32_t)c * 256 + (uint32_t)m * 2);
-                        reinterpret_cast<uint16_t *>(yb + (int64_t)c * p.ysc + (int64_t)f_m * p.ysf)[pl_m] = (uint16_t)w;
+                    for (int cp = sub; cp < FM_C / 2; cp += 4) {
+                        const uint32_t w = lds32(T + (uint32_t)(cp * 128 + m) * 4);
+                        uint16_t *d0 = reinterpret_cast<uint16_t *>(yb + (int64_t)(2 * cp) * p.ysc + (int64_t)f_m * p.ysf);
+                        d0[pl_m] = (uint16_t)(w & 0xffffu);
+                        reinterpret_cast<uint16_t *>(yb + (int64_t)(2 * cp + 1) * p.ysc + (int64_t)f_m * p.ysf)[pl_m] = (uint16_t)(w >> 16);
                     }
                 }
                 fm_bar_epi();                                        // the staging tile is free for the next tile's x
