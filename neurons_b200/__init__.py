@@ -9,9 +9,9 @@ The arithmetic lives in libneurons_mm.so (C ABI: include/neurons_mm.h), built by
 """
 from .lib import NmmError, launch_count, load as load_library          # noqa: F401
 from .ops import ModuleConfig                                           # noqa: F401
-from .motion_module import (VanillaTemporalModule, get_motion_module, invalidate, motion_forward, patch,   # noqa: F401
+from .motion_module import (VanillaTemporalModule, config_of, get_motion_module, invalidate, motion_forward, patch,   # noqa: F401
                             zero_module)
 from .resnet_norm import InflatedGroupNorm, patch_group_norms            # noqa: F401
 
-__all__ = ["VanillaTemporalModule", "get_motion_module", "patch", "invalidate", "motion_forward", "zero_module",
+__all__ = ["VanillaTemporalModule", "get_motion_module", "patch", "invalidate", "motion_forward", "zero_module", "config_of",
            "ModuleConfig", "NmmError", "launch_count", "load_library", "InflatedGroupNorm", "patch_group_norms"]

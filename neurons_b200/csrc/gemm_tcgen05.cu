@@ -231,9 +231,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         ptx::fence_mbar_init();
     }
     if (warp == 2) ptx::tmem_alloc<CG>(tmem_slot, (uint32_t)p.tmem_cols);
-    // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail;
-    // from here on this kernel touches memory the previous kernel produced.
-    pdl_wait();
+    // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail.  Each role
+    // executes griddepcontrol.wait itself, right before it first touches memory the previous kernel may have written -- the producer
+    // only after it has put the first stages' WEIGHT tiles in flight (weights are never written by a kernel of the stream).
     pdl_launch_dependents();
     ptx::tc_fence_before();
     if (CG > 1) ptx::cluster_sync();                 // the peer's barriers must exist before any remote arrive / complete_tx
@@ -248,6 +248,53 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         {
             int stage = 0; uint32_t phase = 0;
             int tile_no = 0;
+            // W tile of k-block kb -> the stage (any time: weights are constant); A tile -> the stage (after griddepcontrol.wait)
+            auto issue_w = [&](int kb, int n_blk, uint32_t sa, uint32_t bar) {
+                if constexpr (CG == 1) {
+                    ptx::tma_load_2d(&tm_w, bar, sa + TC_A_BYTES, kb * TC_BK, n_blk * p.block_n);
+                } else {
+                    const uint32_t bar0 = bar & ptx::PEER_MASK;
+                    if (p.wide) {      // two N = 160 blocks, this CTA stages its 80-row half of each
+                        const uint32_t hb = b_rows / 2;
+                        ptx::tma_load_2d_2sm(&tm_w, bar0, sa + TC_A_BYTES, kb * TC_BK, n_blk * p.block_n + (int)(rank * hb));
+                        ptx::tma_load_2d_2sm(&tm_w, bar0, sa + TC_A_BYTES + hb * TC_BK * 2, kb * TC_BK, n_blk * p.block_n + p.block_n / 2 + (int)(rank * hb));
+                    } else {
+                        ptx::tma_load_2d_2sm(&tm_w, bar0, sa + TC_A_BYTES, kb * TC_BK, n_blk * p.block_n + (int)(rank * b_rows));
+                    }
+                }
+            };
+            auto issue_a = [&](int kb, int64_t m_blk, uint32_t sa, uint32_t bar, const int (&gp)[2], const int (&gf)[2], const int (&gb)[2]) {
+                if constexpr (EPI == NMM_EPI_QKV_ATTN) {
+                    // A rows = (position, frame) pairs of one image: box (64 channels, F frames, 128/F positions) of the tokens
+                    // viewed as (c, b*F + f, p) -> shared-memory row pl * F + f, the attention tile order
+                    const int img = (int)(m_blk / at.tiles_per_img);
+                    ptx::tma_load_3d(&tm_a, bar, sa, kb * TC_BK, img * at.F, (int)(m_blk - (int64_t)img * at.tiles_per_img) * at.ppt);
+                } else if constexpr (GNA) {
+                    // A = x[b, kb*64 .. +64 channels, f, 64 positions] for each half of the 128-token tile (M-major boxes)
+                    ptx::tma_load_4d(&tm_a, bar, sa, gp[0], kb * TC_BK, gf[0], gb[0]);
+                    ptx::tma_load_4d(&tm_a, bar, sa + TC_A_HALF, gp[1], kb * TC_BK, gf[1], gb[1]);
+                } else if constexpr (CG == 1) {
+                    ptx::tma_load_2d(&tm_a, bar, sa, kb * TC_BK, (int32_t)(m_blk * TC_BM));
+                } else {
+                    ptx::tma_load_2d_2sm(&tm_a, bar & ptx::PEER_MASK, sa, kb * TC_BK, (int32_t)(m_blk * TC_BM));
+                }
+            };
+            // both CTAs' bytes of a pair are counted on the even CTA's barrier (the only one the MMA thread waits on)
+            auto expect = [&](uint32_t bar) { if (CG == 1 || leader) ptx::mbar_expect_tx(bar, (uint32_t)CG * stage_bytes); };
+            // the first tile's first stages: weights before the dependency wait, activations after it
+            int pre = 0;
+            if (!(TC_DEBUG(p) & 2)) {
+                pre = num_kb < p.stages ? num_kb : p.stages;
+                if (ptx::elect_one()) {
+                    const int n_blk0 = (int)(cluster_id % p.n_tiles);
+                    for (int kb = 0; kb < pre; kb++) {
+                        expect(full_bar(kb));
+                        issue_w(kb, n_blk0, smem_base + (uint32_t)kb * stage_bytes, full_bar(kb));
+                    }
+                }
+                __syncwarp();
+            }
+            pdl_wait();
             for (int64_t ct = cluster_id; ct < p.cluster_tiles; ct += num_clusters, tile_no++) {
                 const int64_t m_grp = ct / p.n_tiles;
                 const int n_blk = (int)(ct - m_grp * p.n_tiles);
@@ -269,43 +316,19 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     }
                 }
                 for (int kb = 0; kb < num_kb; kb++) {
-                    ptx::mbar_wait(empty_bar(stage), phase ^ 1u);       // the MMAs that read this stage have retired
+                    const bool prefilled = tile_no == 0 && kb < pre;     // W already in flight, expect_tx already posted
+                    if (!prefilled) ptx::mbar_wait(empty_bar(stage), phase ^ 1u);       // the MMAs that read this stage have retired
                     if (kb == 0) TRACE(tile_no, 4);
                     if (kb == num_kb - 1) TRACE(tile_no, 5);
                     const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
                     if (ptx::elect_one()) {
-                    if (TC_DEBUG(p) & 2) {                                  // timing experiment: MMA on whatever is in shared memory
-                        if (leader) ptx::mbar_arrive(full_bar(stage));
-                    } else if (EPI == NMM_EPI_QKV_ATTN) {
-                        // A rows = (position, frame) pairs of one image: box (64 channels, F frames, 128/F positions) of the tokens
-                        // viewed as (c, b*F + f, p) -> shared-memory row pl * F + f, the attention tile order
-                        ptx::mbar_expect_tx(full_bar(stage), stage_bytes);
-                        const int img = (int)(m_blk / at.tiles_per_img);
-                        ptx::tma_load_3d(&tm_a, full_bar(stage), sa, kb * TC_BK, img * at.F, (int)(m_blk - (int64_t)img * at.tiles_per_img) * at.ppt);
-                        ptx::tma_load_2d(&tm_w, full_bar(stage), sa + TC_A_BYTES, kb * TC_BK, n_blk * p.block_n);
-                    } else if (GNA) {
-                        // A = x[b, kb*64 .. +64 channels, f, 64 positions] for each half of the 128-token tile (M-major boxes)
-                        ptx::mbar_expect_tx(full_bar(stage), stage_bytes);
-                        ptx::tma_load_4d(&tm_a, full_bar(stage), sa, gp[0], kb * TC_BK, gf[0], gb[0]);
-                        ptx::tma_load_4d(&tm_a, full_bar(stage), sa + TC_A_HALF, gp[1], kb * TC_BK, gf[1], gb[1]);
-                        ptx::tma_load_2d(&tm_w, full_bar(stage), sa + TC_A_BYTES, kb * TC_BK, n_blk * p.block_n);
-                    } else if (CG == 1) {
-                        ptx::mbar_expect_tx(full_bar(stage), stage_bytes);
-                        ptx::tma_load_2d(&tm_a, full_bar(stage), sa, kb * TC_BK, (int32_t)(m_blk * TC_BM));
-                        ptx::tma_load_2d(&tm_w, full_bar(stage), sa + TC_A_BYTES, kb * TC_BK, n_blk * p.block_n);
-                    } else {
-                        // both CTAs' bytes are counted on the even CTA's barrier (the only one the MMA thread waits on)
-                        if (leader) ptx::mbar_expect_tx(full_bar(stage), 2u * stage_bytes);
-                        const uint32_t bar0 = full_bar(stage) & ptx::PEER_MASK;
-                        ptx::tma_load_2d_2sm(&tm_a, bar0, sa, kb * TC_BK, (int32_t)(m_blk * TC_BM));
-                        if (p.wide) {      // two N = 160 blocks, this CTA stages its 80-row half of each
-                            const uint32_t hb = b_rows / 2;
-                            ptx::tma_load_2d_2sm(&tm_w, bar0, sa + TC_A_BYTES, kb * TC_BK, n_blk * p.block_n + (int)(rank * hb));
-                            ptx::tma_load_2d_2sm(&tm_w, bar0, sa + TC_A_BYTES + hb * TC_BK * 2, kb * TC_BK, n_blk * p.block_n + p.block_n / 2 + (int)(rank * hb));
+                        if (TC_DEBUG(p) & 2) {                              // timing experiment: MMA on whatever is in shared memory
+                            if (leader) ptx::mbar_arrive(full_bar(stage));
                         } else {
-                            ptx::tma_load_2d_2sm(&tm_w, bar0, sa + TC_A_BYTES, kb * TC_BK, n_blk * p.block_n + (int)(rank * b_rows));
+                            if (!prefilled) expect(full_bar(stage));
+                            issue_a(kb, m_blk, sa, full_bar(stage), gp, gf, gb);
+                            if (!prefilled) issue_w(kb, n_blk, sa, full_bar(stage));
                         }
-                    }
                     }
                     __syncwarp();
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -378,6 +401,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         }
     } else if (EPI == NMM_EPI_QKV_ATTN && warp >= 4 + TC_EPI_WARPS) {
         // ===================== attention helpers (QKV + attention): share the tile's problems with the epilogue warps =============
+        pdl_wait();
         const uint32_t xb = epi_base;
         for (int64_t ct = cluster_id; ct < p.cluster_tiles; ct += num_clusters) {
             const int64_t m_grp = ct / p.n_tiles;
@@ -392,6 +416,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         // Thread (j, row): the 128-byte row of channel kb*64 + row in half j (64 positions of image bf_j).  The affine is per
         // (image, channel), so the 128-byte swizzle inside the row is irrelevant; the 16-byte chunks are visited in a rotated
         // order so that 8 consecutive lanes hit 8 different bank groups.
+        pdl_wait();
         const int t = (int)threadIdx.x - 32 * (4 + TC_EPI_WARPS);
         const int j = t >> 6, row = t & 63;
         const int cpg = gn.C / NMM_GN_GROUPS;
@@ -446,6 +471,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         }
     } else if (warp >= 4 && warp < 4 + TC_EPI_WARPS) {
         // ===================== epilogue (every CTA: its own 128 TMEM lanes) =====================
+        pdl_wait();
         const int ew = warp - 4;
         const int q = warp & 3;                                           // TMEM lane quadrant this warp may access
         const int half = ew >> 2;                                         // which of the quadrant's two warps
