@@ -152,6 +152,86 @@ def clip_loop(nb, wl, dev, clips: int = 3, clip_batch: int = 1):
     return e0.elapsed_time(e1) / clips, flops_clip           # ms per replayed 25-step loop (= clip_batch clips), flops of that loop
 
 
+def clip_e2e(nb, wl, dev, rank: int, world: int, clips_per_rank: int = 2):
+    """Clip-level end to end (BASELINE configs[2] shape), everything inside the timed region: per clip the H2D copy of its latents +
+    conditioning from pinned host memory, 25 graph-replayed denoising steps (28 motion-module calls + the fused CFG / DDIM update,
+    nmm_cfg_ddim_step, on the clip's latents), a decoded-frame-sized result per clip ([3, 16, 256, 256] fp16; nearest up-sampling stands
+    for the VAE, which is outside the path) copied D2H, and -- once, at the end -- the gather of every rank's frames over NCCL
+    (neurons_b200.sharding.gather_clips: the only collective of the path).  Clips are assigned round-robin exactly like the reference.
+    Returns (seconds for this rank's clips incl. the gather, clips on this rank, bytes H2D per clip, bytes D2H per clip)."""
+    import torch.distributed as dist
+    from neurons_b200 import ops, sampler, sharding
+    F, L, steps = 16, 32, 25
+    calls = wl.unet_step_calls(L) + wl.controlnet_step_calls(L)
+    num_clips = clips_per_rank * world
+    mine = sharding.shard_indices(num_clips, rank, world)
+    sch = sampler.DDIMSchedule()
+    ts = sch.timesteps(steps)
+    with torch.no_grad():
+        mods, xs = [], []
+        for c in calls:
+            kw = dict(num_attention_heads=8, num_transformer_block=1, attention_block_types=("Temporal_Self",) * c.attn_blocks,
+                      temporal_position_encoding=True, temporal_position_encoding_max_len=c.max_len, temporal_attention_dim_div=1,
+                      zero_initialize=False)
+            with torch.device(dev):
+                mods.append(nb.get_motion_module(c.channels, "Vanilla", kw).to(torch.bfloat16).eval())
+            xs.append(torch.randn(2, F, c.channels, c.side, c.side, device=dev, dtype=torch.bfloat16).permute(0, 2, 1, 3, 4))
+        lat = torch.zeros(1, 4, F, L, L, device=dev, dtype=torch.bfloat16)
+        cond = torch.zeros(1, 4, 1, L, L, device=dev, dtype=torch.bfloat16)
+        host_lat = [torch.randn(1, 4, F, L, L).to(torch.bfloat16).pin_memory() for _ in mine]
+        host_cond = [torch.randn(1, 4, 1, L, L).to(torch.bfloat16).pin_memory() for _ in mine]
+        host_frames = [torch.empty(3, F, 8 * L, 8 * L, dtype=torch.float16).pin_memory() for _ in mine]
+        frames_dev = torch.empty(len(mine), 3, F, 8 * L, 8 * L, device=dev, dtype=torch.float16)
+        eps_u = torch.empty_like(lat)
+        eps_c = torch.empty_like(lat)
+
+        def one_step_modules():
+            y = None
+            for i, (m, x) in enumerate(zip(mods, xs)):
+                out = m(x, None, None)
+                if i == 19:                                   # the UNet's last motion-module call: 320 channels at the full latent resolution
+                    y = out
+            # the step's noise prediction for the clip: 4 channels of that output, CFG pair (uncond | cond)
+            eps_u.copy_(y[0:1, :4]); eps_c.copy_(y[1:2, :4])
+
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            one_step_modules()
+            side.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                one_step_modules()
+        torch.cuda.current_stream().wait_stream(side)
+
+        def run_clip(k):
+            lat.copy_(host_lat[k], non_blocking=True)
+            cond.copy_(host_cond[k], non_blocking=True)
+            for t in ts:
+                graph.replay()
+                a_t, a_prev = sch.alphas(t, steps)
+                ops.cfg_ddim_step(lat, eps_u, eps_c, 8.5, a_t, a_prev)
+            fr = torch.nn.functional.interpolate(lat[0, :3].float(), scale_factor=8, mode="nearest").to(torch.float16)      # [3, F, 256, 256]
+            frames_dev[k].copy_(fr)
+            host_frames[k].copy_(fr, non_blocking=True)
+
+        run_clip(0)                                         # warm-up
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for k in range(len(mine)):
+            run_clip(k)
+        out = sharding.gather_clips(frames_dev, num_clips) if world > 1 else frames_dev
+        torch.cuda.synchronize()
+        secs = time.perf_counter() - t0
+        assert rank != 0 or out.shape[0] == num_clips
+    h2d = host_lat[0].numel() * 2 + host_cond[0].numel() * 2
+    d2h = host_frames[0].numel() * 2
+    return secs, len(mine), h2d, d2h
+
+
 def cpu_reference_time(sample: str, threads: int):
     """Time the oracle port of the reference module (fp32, torch CPU, all host threads) on a bounded sample.
     Returns (tflops, seconds, description).  This is the ONE place bench.py executes oracle/ (as the baseline)."""
@@ -412,11 +492,12 @@ def main():
             eager = {"error": repr(e)[:200]}
     clip_ms, clip_flops = (0.0, 0.0) if args.no_clips else clip_loop(nb, wl, dev)
     clip4_ms, clip4_flops = (0.0, 0.0) if args.no_clips else clip_loop(nb, wl, dev, clips=2, clip_batch=4)       # BASELINE configs[3]: 4 clips per GPU
+    ce_secs, ce_n, ce_h2d, ce_d2h = (0.0, 0, 0, 0) if args.no_clips else clip_e2e(nb, wl, dev, rank, world)
     # max over ranks
-    t = torch.tensor([ms_total, e2e_ms, clip_ms, clip4_ms], device=dev, dtype=torch.float64)
+    t = torch.tensor([ms_total, e2e_ms, clip_ms, clip4_ms, ce_secs], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms, clip_ms, clip4_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
+    ms_total, e2e_ms, clip_ms, clip4_ms, ce_secs = float(t[0]), float(t[1]), float(t[2]), float(t[3]), float(t[4])
     ms_step = ms_total / args.steps
     value = world * flops_step / (ms_step * 1e-3) / 1e12
     e2e_value = world * flops_step / (e2e_ms * 1e-3) / 1e12
@@ -468,7 +549,7 @@ def main():
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic", "config": workload_config(world), "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                        "copies_alone_ms_per_step": copy_ms,
+                        "copies_alone_ms_per_step": copy_ms, "e2e_over_copies_alone": e2e_ms / copy_ms if copy_ms else None,
                         "note": "PCIe-bound when copies_alone_ms_per_step >= ms_per_step of the device-resident arm: the step's inputs and outputs "
                                 "(h2d + d2h bytes) cross the host link inside the timed region, both directions concurrently"},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
@@ -477,6 +558,11 @@ def main():
                 "clips": None if args.no_clips else {
                     "metric": "25-step video clips/s, motion modules only", "value": world * 1e3 / clip_ms, "unit": "clips/s", "ms_per_clip": clip_ms,
                     "tflops": world * clip_flops / (clip_ms * 1e-3) / 1e12,
+                    "e2e": {"value": world * ce_n / ce_secs if ce_secs else None, "unit": "clips/s", "clips_per_rank": ce_n, "seconds": ce_secs,
+                            "h2d_bytes_per_clip": ce_h2d, "d2h_bytes_per_clip": ce_d2h,
+                            "what": "per clip: pinned H2D of latents + conditioning, 25 graph-replayed steps (28 motion-module calls + fused CFG/DDIM "
+                                    "update), a [3,16,256,256] fp16 frame tensor D2H; ONE NCCL gather of all ranks' frames at the end "
+                                    "(sharding.gather_clips); all inside the timed region, max over ranks"},
                     "batch4": {"value": world * 4e3 / clip4_ms, "unit": "clips/s", "ms_per_4_clips": clip4_ms,
                                "tflops": world * clip4_flops / (clip4_ms * 1e-3) / 1e12,
                                "workload": "BASELINE configs[3] shape: the same loop with 4 clips per GPU (CFG batch 8)"},

@@ -69,6 +69,34 @@ def test_ddim_25_step_cosine_vs_oracle():
 
 
 @pytest.mark.gpu
+@pytest.mark.timeout(1500)
+def test_ddim_25_step_cosine_at_unet_channel_widths():
+    """The same bar on a stack at the UNet's real widths -- 320 / 640 / 1280 channels, 10 motion modules (the fused C = 320 kernel, the
+    d_h = 80 fused QKV + attention kernel and the d_h = 160 stand-alone attention path all take part), CFG batch 2, 8 frames, 8x8 latent --
+    against the reference arithmetic (oracle, fp32 on the same bf16-rounded weights) through all 25 DDIM steps."""
+    dev = "cuda:0"
+    stack, cfgs, params = _stack_and_params((320, 640, 1280), seed=5)
+    mods = [helpers.mirror_module(c, p, dev, torch.bfloat16) for c, p in zip(cfgs, params)]
+    g = torch.Generator().manual_seed(17)
+    lat0 = torch.randn(1, 4, 8, 8, 8, generator=g)
+    noise = torch.randn(1, 4, 8, 8, 8, generator=g)
+    ctx = torch.randn(2, 16, generator=g)
+    sch = sampler.DDIMSchedule()
+
+    def den_gpu(x2, t, c):
+        return stack(lambda i, h: mods[i](h.to(torch.bfloat16), None, None).float(), x2, t, c)
+
+    def den_ref(x2, t, c):
+        return stack(lambda i, h: mo.forward_reference_order(params[i], h, cfgs[i]), x2, t, c)
+
+    out_gpu = sampler.denoise(den_gpu, lat0.to(dev), ctx.to(dev), sch, 25, 8.5, noise=noise.to(dev)).float().cpu()
+    out_ref = sampler.denoise(den_ref, lat0, ctx, sch, 25, 8.5, noise=noise)
+    assert torch.isfinite(out_gpu).all() and torch.isfinite(out_ref).all()
+    cos = torch.nn.functional.cosine_similarity(out_gpu.flatten(), out_ref.flatten(), dim=0).item()
+    assert cos >= 0.999, cos
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
 @pytest.mark.parametrize("n", [4 * 16 * 32 * 32, 1003, 8])
 @pytest.mark.parametrize("with_cfg", [True, False])
