@@ -215,7 +215,9 @@ def clip_e2e(nb, wl, dev, rank: int, world: int, clips_per_rank: int = 2):
             frames_dev[k].copy_(fr)
             host_frames[k].copy_(fr, non_blocking=True)
 
-        run_clip(0)                                         # warm-up
+        run_clip(0)                                         # warm-up (also of the NCCL communicator: its lazy initialisation is not the path)
+        if world > 1:
+            sharding.gather_clips(frames_dev, num_clips)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
