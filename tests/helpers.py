@@ -13,7 +13,11 @@ TOL_BF16 = 2e-2     # north_star: max-abs vs the reference on identical (bf16-ro
 
 
 def golden_names():
-    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.pt")))
+    """Module-level fixtures (oracle/gen_golden.py).  `unet_step_inputs.pt` has another schema (oracle/gen_unet_golden.py,
+    tests/test_unet_activations.py) and is not one of them."""
+    names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "c*_f*.pt")))
+    assert names, "no golden fixtures found"
+    return names
 
 
 def load_golden(name):
