@@ -201,9 +201,7 @@ static int launch_attn_t(const Geo &g, const T *qkv, T *ctx, cudaStream_t st) {
     do {                                                                                                                 \
         auto kern = temporal_attention_kernel<T, VEC, FM>;                                                               \
         static DeviceOnce once; /* per instantiation and device; never inside a stream capture after warm-up */            \
-        if (once.first()) {                                                                                              \
-            NMM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));          \
-        }                                                                                                                \
+        NMM_CUDA_OK(once.max_smem(kern, (int)smem_cap));          \
         ProfScope prof(K_ATTENTION, st, 4.0 * g.N * g.F * g.C, 4.0 * g.N * g.C * sizeof(T));                             \
         launch_pdl(kern, grid, threads, smem, st, qkv, ctx, g.B, g.F, g.P, g.C, g.heads, PB, HB, scale);                          \
     } while (0)
@@ -459,9 +457,7 @@ static int launch_attn_mma(const Geo &g, const bf16 *qkv, bf16 *ctx, cudaStream_
     do {                                                                                                                 \
         auto kern = temporal_attention_mma_fixed_kernel<FF, DD>;                                                         \
         static DeviceOnce once;                                                                                          \
-        if (once.first()) {                                                                                              \
-            NMM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));            \
-        }                                                                                                                \
+        NMM_CUDA_OK(once.max_smem(kern, 200 * 1024));          \
         ProfScope prof(K_ATTENTION, st, 4.0 * g.N * g.F * g.C, 4.0 * g.N * g.C * 2);                                      \
         launch_pdl(kern, gridf, thr_f, smem_f, st, qkv, ctx, g.P, g.C, PBf, sl2);                                          \
     } while (0)
@@ -491,9 +487,7 @@ static int launch_attn_mma(const Geo &g, const bf16 *qkv, bf16 *ctx, cudaStream_
     do {                                                                                                                 \
         auto kern = temporal_attention_mma_kernel<FF>;                                                                   \
         static DeviceOnce once;                                                                                          \
-        if (once.first()) {                                                                                              \
-            NMM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));            \
-        }                                                                                                                \
+        NMM_CUDA_OK(once.max_smem(kern, 200 * 1024));          \
         ProfScope prof(K_ATTENTION, st, 4.0 * g.N * g.F * g.C, 4.0 * g.N * g.C * 2);                                      \
         launch_pdl(kern, grid, warps * 32, smem, st, qkv, ctx, g.B, g.P, g.C, g.heads, PB, HB, scale_log2e);                      \
     } while (0)

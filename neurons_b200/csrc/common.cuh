@@ -9,6 +9,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 
 #include "../../include/neurons_mm.h"
@@ -43,14 +44,23 @@ struct ProfScope {          // records start on construction, stop on destructio
 };
 
 // cudaFuncSetAttribute is per device: a "done" flag per (kernel instantiation, device ordinal).  Usage:
-//     static DeviceOnce once;  if (once.first()) NMM_CUDA_OK(cudaFuncSetAttribute(...));
+//     static DeviceOnce once;  NMM_CUDA_OK(once.max_smem(kern, bytes));
+// The flag is published only AFTER the attribute call has returned (and the call itself is serialised), so a second host
+// thread on the same device can never launch a > 48 KB kernel before the attribute is in place.
 struct DeviceOnce {
+    std::mutex mu;
     std::atomic<bool> done[64];
     DeviceOnce() { for (auto &d : done) d.store(false, std::memory_order_relaxed); }
-    bool first() {                      // true exactly until mark() has been called for the current device
+    template <typename K>
+    cudaError_t max_smem(K kern, int bytes) {
         int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
-        return !done[dev].exchange(true, std::memory_order_relaxed);
+        const bool known = cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64;
+        if (known && done[dev].load(std::memory_order_acquire)) return cudaSuccess;
+        std::lock_guard<std::mutex> lk(mu);
+        if (known && done[dev].load(std::memory_order_relaxed)) return cudaSuccess;
+        const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e == cudaSuccess && known) done[dev].store(true, std::memory_order_release);
+        return e;
     }
 };
 

@@ -1084,7 +1084,7 @@ int launch_fused_module(const FusedArgs &a, cudaStream_t st) {
     const int grid = (int)(p.ntiles < max_grid ? p.ntiles : max_grid);
     auto kern = a.F == 8 ? (cg == 2 ? fused_module_kernel<8, 2> : fused_module_kernel<8, 1>) : (cg == 2 ? fused_module_kernel<16, 2> : fused_module_kernel<16, 1>);
     static DeviceOnce once[4];
-    if (once[(a.F == 16 ? 2 : 0) + (cg - 1)].first()) NMM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FM_SMEM_BYTES));
+    NMM_CUDA_OK(once[(a.F == 16 ? 2 : 0) + (cg - 1)].max_smem(kern, (int)FM_SMEM_BYTES));
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)grid);

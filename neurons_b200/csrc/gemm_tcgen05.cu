@@ -897,11 +897,14 @@ extern "C" __attribute__((visibility("default"))) int nmm_debug_trace_dump(const
 }
 #endif
 
-static int num_sms() {
-    static int n = 0;
+static int num_sms() {                 // SM count of the CURRENT device (cached per ordinal)
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    int n = cache[dev].load(std::memory_order_relaxed);
     if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cache[dev].store(n, std::memory_order_relaxed);
     }
     return n;
 }
@@ -960,7 +963,7 @@ static int launch_tc_t(const CUtensorMap &ta, const CUtensorMap &tw, const CUten
                        const AttnParams &at = AttnParams()) {
     auto kern = linear_tc_kernel<EPI, CG, LNF, GNA>;
     static DeviceOnce once;           // per template instantiation and device
-    if (once.first()) NMM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX));
+    NMM_CUDA_OK(once.max_smem(kern, TC_SMEM_MAX));
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)grid);

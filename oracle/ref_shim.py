@@ -30,7 +30,10 @@ _cached = None
 
 
 def reference_root() -> str | None:
-    for cand in (os.environ.get(_REF_ENV), _DEFAULT_REF):
+    """$NEURONS_REF, /root/reference, or <repo>/baseline/_ref (the base contract's install target; empty here: the reference is pure
+    Python without a setup.py / pyproject, so there is nothing to pip-install -- see DESIGN.md section 7)."""
+    repo_ref = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+    for cand in (os.environ.get(_REF_ENV), _DEFAULT_REF, repo_ref):
         if cand and os.path.isfile(os.path.join(cand, "animatediff", "models", "motion_module.py")):
             return cand
     return None

@@ -36,8 +36,31 @@ def timed(fn, flush, iters=5, warm=2):
     return ts[len(ts) // 2]
 
 
+def timed_chain(fns, reps):
+    """Per-launch time (ms) of `reps` rounds over the variants in `fns` launched back to back in one stream: programmatic dependent
+    launch active, no events or flushes between the launches; the variants use distinct buffers (together larger than L2).  The chain
+    is captured in a CUDA graph so that the host (ctypes + allocator, ~20 us per call) is not what is being timed."""
+    for fn in fns:
+        fn()
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for _ in range(reps):
+            for fn in fns:
+                fn()
+    graph.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / (reps * len(fns))
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--chain", type=int, default=0, help="N > 0: time N rounds of back-to-back launches over 4 buffer sets (in-stream cost) instead of isolated launches")
     ap.add_argument("--batch", type=int, default=2)
     ap.add_argument("--frames", type=int, default=8)
     ap.add_argument("--latent", type=int, default=64)
@@ -59,12 +82,13 @@ def main():
         M = B * F * P
         cfg = ops.ModuleConfig(C)
         g = torch.Generator(device=dev).manual_seed(0)
-        x = torch.randn(B, F, C, side, side, device=dev, dtype=bf, generator=g).permute(0, 2, 1, 3, 4)
         gw, gb = torch.ones(C, device=dev), torch.zeros(C, device=dev)
-        act = torch.randn(M, C, device=dev, dtype=bf, generator=g)
-        act4 = torch.randn(M, 4 * C, device=dev, dtype=bf, generator=g)
-        qkv = torch.randn(M, 3 * C, device=dev, dtype=bf, generator=g)
-        h = torch.randn(M, C, device=dev, generator=g)
+        nsets = 4 if a.chain else 1
+        sets = []
+        for _ in range(nsets):
+            sets.append(dict(x=torch.randn(B, F, C, side, side, device=dev, dtype=bf, generator=g).permute(0, 2, 1, 3, 4),
+                             act=torch.randn(M, C, device=dev, dtype=bf, generator=g), act4=torch.randn(M, 4 * C, device=dev, dtype=bf, generator=g),
+                             qkv=torch.randn(M, 3 * C, device=dev, dtype=bf, generator=g), h=torch.randn(M, C, device=dev, generator=g)))
         w_cc = torch.randn(C, C, device=dev, dtype=bf, generator=g) / C ** 0.5
         w_qkv = torch.randn(3 * C, C, device=dev, dtype=bf, generator=g) / C ** 0.5
         w_1 = torch.randn(8 * C, C, device=dev, dtype=bf, generator=g) / C ** 0.5
@@ -73,25 +97,26 @@ def main():
         bias8 = torch.randn(8 * C, device=dev, generator=g)
         pe = torch.randn(24, C, device=dev, generator=g)
         es = 2
+        # (name, factory over a buffer set, flops, bytes)
         stages = [
-            ("gn_stats", lambda: ops.groupnorm_stats(cfg, x), 0.0, M * C * es),
-            ("gn_tokens(+stats)", lambda: ops.groupnorm_tokens(cfg, x, gw, gb), 0.0, 3 * M * C * es),
-            ("gn_stats+proj_in fused", lambda: ops.groupnorm_linear(cfg, x, gw, gb, w_cc, bias), 2.0 * M * C * C, M * C * (2 * es + 4)),
-            ("layernorm_pe", lambda: ops.layernorm_pe(cfg, (B, F, side, side), h, gw, gb, pe, bf), 0.0, M * C * (4 + es)),
-            ("attention", lambda: ops.temporal_attention(cfg, (B, F, side, side), qkv), 4.0 * M * F * C, 4 * M * C * es),
-            ("qkv+attention fused", lambda: ops.qkv_attention(cfg, (B, F, side, side), act, w_qkv), 2.0 * M * C * 3 * C + 4.0 * M * F * C, M * C * es * 2),
-            ("proj_in  C->C  store h", lambda: ops.linear(act, w_cc, bias, nlib.EPI_STORE, h=h, want_out=False), 2.0 * M * C * C, M * C * (es + 4)),
-            ("qkv      C->3C store", lambda: ops.linear(act, w_qkv, None, nlib.EPI_STORE), 2.0 * M * C * 3 * C, M * C * es * 4),
-            ("to_out   C->C  residual", lambda: ops.linear(act, w_cc, bias, nlib.EPI_RESIDUAL, h=h, want_out=False), 2.0 * M * C * C, M * C * (es + 8)),
-            ("geglu    C->8C", lambda: ops.linear(act, w_1, bias8, nlib.EPI_GEGLU), 2.0 * M * C * 8 * C, M * C * es * 5),
-            ("ff_out   4C->C residual+copy", lambda: ops.linear(act4, w_2, bias, nlib.EPI_RESIDUAL, h=h, want_out=True), 2.0 * M * 4 * C * C, M * C * (4 * es + 4 + es)),
-            ("proj_out C->C  nchw+x", lambda: ops.linear(act, w_cc, bias, nlib.EPI_OUTPUT, cfg=cfg, x=x), 2.0 * M * C * C, M * C * es * 3),
+            ("gn_stats", lambda d: (lambda: ops.groupnorm_stats(cfg, d["x"])), 0.0, M * C * es),
+            ("gn_tokens(+stats)", lambda d: (lambda: ops.groupnorm_tokens(cfg, d["x"], gw, gb)), 0.0, 3 * M * C * es),
+            ("gn_stats+proj_in fused", lambda d: (lambda: ops.groupnorm_linear(cfg, d["x"], gw, gb, w_cc, bias)), 2.0 * M * C * C, M * C * (2 * es + 4)),
+            ("layernorm_pe", lambda d: (lambda: ops.layernorm_pe(cfg, (B, F, side, side), d["h"], gw, gb, pe, bf)), 0.0, M * C * (4 + es)),
+            ("attention", lambda d: (lambda: ops.temporal_attention(cfg, (B, F, side, side), d["qkv"])), 4.0 * M * F * C, 4 * M * C * es),
+            ("qkv+attention fused", lambda d: (lambda: ops.qkv_attention(cfg, (B, F, side, side), d["act"], w_qkv)), 2.0 * M * C * 3 * C + 4.0 * M * F * C, M * C * es * 2),
+            ("proj_in  C->C  store h", lambda d: (lambda: ops.linear(d["act"], w_cc, bias, nlib.EPI_STORE, h=d["h"], want_out=False)), 2.0 * M * C * C, M * C * (es + 4)),
+            ("qkv      C->3C store", lambda d: (lambda: ops.linear(d["act"], w_qkv, None, nlib.EPI_STORE)), 2.0 * M * C * 3 * C, M * C * es * 4),
+            ("to_out   C->C  residual", lambda d: (lambda: ops.linear(d["act"], w_cc, bias, nlib.EPI_RESIDUAL, h=d["h"], want_out=False)), 2.0 * M * C * C, M * C * (es + 8)),
+            ("geglu    C->8C", lambda d: (lambda: ops.linear(d["act"], w_1, bias8, nlib.EPI_GEGLU)), 2.0 * M * C * 8 * C, M * C * es * 5),
+            ("ff_out   4C->C residual+copy", lambda d: (lambda: ops.linear(d["act4"], w_2, bias, nlib.EPI_RESIDUAL, h=d["h"], want_out=True)), 2.0 * M * 4 * C * C, M * C * (4 * es + 4 + es)),
+            ("proj_out C->C  nchw+x", lambda d: (lambda: ops.linear(d["act"], w_cc, bias, nlib.EPI_OUTPUT, cfg=cfg, x=d["x"])), 2.0 * M * C * C, M * C * es * 3),
         ]
-        for name, fn, flops, byts in stages:
+        for name, make, flops, byts in stages:
             if only and not any(t in name for t in only):
                 continue
             try:
-                ms = timed(fn, flush)
+                ms = timed_chain([make(d) for d in sets], a.chain) if a.chain else timed(make(sets[0]), flush)
             except nlib.NmmError as e:           # e.g. the fused QKV + attention kernel at d_h = 160
                 print(f"C={C:5d} M={M:6d} {name:32s} not supported here ({e.status})", flush=True)
                 continue
@@ -100,7 +125,7 @@ def main():
             r = rows[-1]
             print(f"C={C:5d} M={M:6d} {name:32s} {ms*1e3:9.1f} us  {r['tflops']:8.1f} TF/s ({r['frac_tensor']*100:5.1f}%)  "
                   f"{r['gbps']:8.1f} GB/s ({r['frac_hbm']*100:5.1f}%)", flush=True)
-        del x, act, act4, qkv, h
+        del sets
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     json.dump(rows, open(a.out, "w"), indent=1)
 
