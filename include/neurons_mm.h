@@ -53,8 +53,13 @@ typedef enum nmm_status {
 
 typedef enum nmm_dtype {
     NMM_F32 = 0,                /* parity mode: fp32 storage, fp32 FMA arithmetic (bar: max-abs 1e-4) */
-    NMM_BF16 = 1                /* production mode: bf16 storage + tcgen05 bf16 MMA, fp32 accumulate,
+    NMM_BF16 = 1,               /* production mode: bf16 storage + tcgen05 bf16 MMA, fp32 accumulate,
                                    fp32 residual stream, norms / softmax in fp32 (bar: max-abs 2e-2)  */
+    NMM_F32X3 = 2               /* fp32 storage (x, y, source parameters: float), fp32-grade arithmetic on the tensor cores:
+                                   every Linear runs as three bf16 tcgen05 MMAs per product -- hi.hi + hi.lo + lo.hi of
+                                   the two-term bf16 splits of both operands, fp32 accumulation in TMEM (bar: max-abs 1e-4,
+                                   like NMM_F32, which stays as the FMA-pipe checker).  Needs channels % 64 == 0.
+                                   nmm_shape.dtype only; nmm_params.dtype stays the source element type.              */
 } nmm_dtype;
 
 /* Shape + hyper-parameters of one module call.  Mirrors the arguments that reach

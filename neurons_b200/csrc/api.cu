@@ -188,7 +188,9 @@ static int validate(const nmm_shape *s) {
     if (!s) return fail(NMM_ERR_BAD_ARG, "shape is NULL");
     if (s->batch <= 0 || s->channels <= 0 || s->frames <= 0 || s->height <= 0 || s->width <= 0)
         return fail(NMM_ERR_BAD_ARG, "non-positive dimension");
-    if (s->dtype != NMM_F32 && s->dtype != NMM_BF16) return fail(NMM_ERR_BAD_ARG, "unknown dtype %d", s->dtype);
+    if (s->dtype != NMM_F32 && s->dtype != NMM_BF16 && s->dtype != NMM_F32X3) return fail(NMM_ERR_BAD_ARG, "unknown dtype %d", s->dtype);
+    if (s->dtype == NMM_F32X3 && s->channels % 64 != 0)
+        return fail(NMM_ERR_UNSUPPORTED, "NMM_F32X3 (3 x bf16 tensor-core mode) needs channels %% 64 == 0 (got %d); use NMM_F32", s->channels);
     if (s->channels % NMM_GN_GROUPS != 0) return fail(NMM_ERR_BAD_ARG, "channels (%d) must be divisible by %d GroupNorm groups", s->channels, NMM_GN_GROUPS);
     if (s->heads <= 0 || s->channels % s->heads != 0) return fail(NMM_ERR_BAD_ARG, "channels (%d) must be divisible by heads (%d)", s->channels, s->heads);
     if (s->layers <= 0 || s->layers > NMM_MAX_LAYERS) return fail(NMM_ERR_UNSUPPORTED, "num_transformer_block %d outside [1,%d]", s->layers, NMM_MAX_LAYERS);
@@ -231,6 +233,18 @@ __global__ void convert_rows_kernel(const TS *__restrict__ src, TD *__restrict__
     }
 }
 
+// NMM_F32X3 weights: dst is bf16 [rows, 2 * cols], row r = hi plane | lo plane of src row map(r)  (w = hi + lo + O(2^-17 w))
+template <typename TS>
+__global__ void split_rows_kernel(const TS *__restrict__ src, bf16 *__restrict__ dst, int64_t rows, int64_t cols, int64_t half) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int64_t total = rows * cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / cols, c = i - r * cols;
+        split1_store(dst + r * 2 * cols, (int)cols, (int)c, to_f32(src[geglu_src_row(r, half) * cols + c]));
+    }
+}
+
 int launch_convert_rows(const void *src, int src_dtype, void *dst, int dst_dtype, int64_t rows, int64_t cols, int half, cudaStream_t st) {
     if (!src || !dst) return fail(NMM_ERR_BAD_ARG, "NULL parameter tensor");
     const int64_t total = rows * cols;
@@ -238,6 +252,13 @@ int launch_convert_rows(const void *src, int src_dtype, void *dst, int dst_dtype
     const int threads = 256;
     const int blocks = (int)std::min<int64_t>(ceil_div(total, threads), 148 * 16);
     ProfScope prof(K_PACK, st, 0.0, (double)total * (dtype_size(src_dtype) + dtype_size(dst_dtype)));
+    if (dst_dtype == NMM_F32X3) {
+        if (src_dtype == NMM_F32) launch_pdl(split_rows_kernel<float>, blocks, threads, 0, st, (const float *)src, (bf16 *)dst, rows, cols, (int64_t)half);
+        else if (src_dtype == NMM_BF16) launch_pdl(split_rows_kernel<bf16>, blocks, threads, 0, st, (const bf16 *)src, (bf16 *)dst, rows, cols, (int64_t)half);
+        else return fail(NMM_ERR_BAD_ARG, "unknown parameter dtype");
+        NMM_LAUNCHED("split_rows_kernel");
+        return NMM_OK;
+    }
     if (src_dtype == NMM_F32 && dst_dtype == NMM_F32) launch_pdl(convert_rows_kernel<float, float>, blocks, threads, 0, st, (const float *)src, (float *)dst, rows, cols, half);
     else if (src_dtype == NMM_F32 && dst_dtype == NMM_BF16) launch_pdl(convert_rows_kernel<float, bf16>, blocks, threads, 0, st, (const float *)src, (bf16 *)dst, rows, cols, half);
     else if (src_dtype == NMM_BF16 && dst_dtype == NMM_F32) launch_pdl(convert_rows_kernel<bf16, float>, blocks, threads, 0, st, (const bf16 *)src, (float *)dst, rows, cols, half);
@@ -410,6 +431,11 @@ __global__ void make_pe_kernel(float *__restrict__ pe, int max_len, int C) {
 }
 
 static int linear(const Geo &g, const LinearArgs &a, cudaStream_t st) {
+    if (g.dtype == NMM_F32X3) {          // fp32-grade on the tensor cores: operands are hi | lo bf16 planes (gemm_tcgen05.cu, X3)
+        LinearArgs b = a;
+        b.x3 = 1;
+        return launch_linear_tc(b, st);
+    }
     return g.dtype == NMM_BF16 ? launch_linear_tc(a, st) : launch_linear_simt(a, st);
 }
 
@@ -735,6 +761,7 @@ static int forward_impl(const nmm_shape *s, const void *x, void *y, const void *
                 if (attn_fused) {
                     a.epilogue = NMM_EPI_QKV_ATTN; a.W = pk + ao.wqkv_t; a.out = ctx; a.attn_B = g.B; a.attn_heads = g.heads;
                 }
+                if (g.dtype == NMM_F32X3) { a.h = (float *)big; a.out = nullptr; }      // q|k|v stay fp32 for the fp32 attention kernel
                 if ((rc = linear(g, a, st)) != NMM_OK) return rc;
                 clear_fold(a);
                 // softmax(q k^T / sqrt(dh)) v over frames                               motion_module_new.py:258-287
@@ -753,13 +780,13 @@ static int forward_impl(const nmm_shape *s, const void *x, void *y, const void *
             clear_fold(a);
             const bool last = (l == g.layers - 1);
             a.epilogue = NMM_EPI_RESIDUAL; a.N = g.C; a.K = 4 * g.C; a.A = big; a.W = pk + lo.w2; a.bias = F32(lo.b2); a.h = h; a.out = nullptr;
-            if (last && g.dtype == NMM_BF16) { a.out = tok; a.no_h_store = 1; }   // bf16 h + ff(...) = the A operand of proj_out (h itself is dead)
+            if (last && g.dtype != NMM_F32) { a.out = tok; a.no_h_store = 1; }   // h + ff(...) in the GEMM operand format = the A operand of proj_out (h itself is dead)
             else producer(a);
             if ((rc = linear(g, a, st)) != NMM_OK) return rc;
             clear_fold(a);
         }
         // y = proj_out(h) back in NCHW + x                                              :152-156
-        a.epilogue = NMM_EPI_OUTPUT; a.N = g.C; a.K = g.C; a.A = (g.dtype == NMM_BF16) ? (const void *)tok : (const void *)h;
+        a.epilogue = NMM_EPI_OUTPUT; a.N = g.C; a.K = g.C; a.A = (g.dtype != NMM_F32) ? (const void *)tok : (const void *)h;
         a.W = pk + L.w_out; a.bias = F32(L.b_out); a.h = nullptr; a.out = nullptr; a.x = xc; a.y = yc;
         if ((rc = linear(g, a, st)) != NMM_OK) return rc;
     }
@@ -890,7 +917,7 @@ int nmm_qkv_attention(const nmm_shape *s, const void *tokens, const void *wqkv, 
 
 int nmm_linear(int32_t dtype, int32_t epilogue, int64_t M, int32_t N, int32_t K, const void *A, const void *W, const float *bias,
                float *h, void *out, const nmm_shape *s, const void *x, void *y, void *stream) {
-    if (dtype != NMM_F32 && dtype != NMM_BF16) return fail(NMM_ERR_BAD_ARG, "unknown dtype %d", dtype);
+    if (dtype != NMM_F32 && dtype != NMM_BF16 && dtype != NMM_F32X3) return fail(NMM_ERR_BAD_ARG, "unknown dtype %d", dtype);
     if (!A || !W || M < 0 || N <= 0 || K <= 0) return fail(NMM_ERR_BAD_ARG, "bad GEMM arguments");
     int rc = device_check();
     if (rc != NMM_OK) return rc;
@@ -916,7 +943,8 @@ int nmm_linear(int32_t dtype, int32_t epilogue, int64_t M, int32_t N, int32_t K,
         }
         default: return fail(NMM_ERR_BAD_ARG, "unknown epilogue %d", epilogue);
     }
-    return dtype == NMM_BF16 ? launch_linear_tc(a, (cudaStream_t)stream) : launch_linear_simt(a, (cudaStream_t)stream);
+    a.x3 = dtype == NMM_F32X3 ? 1 : 0;      // A / W / out are bf16 hi | lo plane tensors ([rows, 2K] / [M, 2N]); x, y fp32
+    return dtype == NMM_F32 ? launch_linear_simt(a, (cudaStream_t)stream) : launch_linear_tc(a, (cudaStream_t)stream);
 }
 
 }  // extern "C"

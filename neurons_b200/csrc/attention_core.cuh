@@ -38,11 +38,7 @@ __device__ __forceinline__ void mma_k8(float (&d)[4], uint32_t a0, uint32_t a1, 
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a0), "r"(a1), "r"(b0));
 }
-// split two fp32 into bf16 hi and bf16 lo (residual) pairs
-__device__ __forceinline__ void split_bf16x2(float x, float y, uint32_t &hi, uint32_t &lo) {
-    hi = pack_bf16x2(x, y);
-    lo = pack_bf16x2(x - bf16_lo(hi), y - bf16_hi(hi));
-}
+// (split_bf16x2: two fp32 -> bf16 hi and bf16 lo (residual) pairs, common.cuh)
 
 
 // NP independent (position, head) problems of one warp, their instruction streams interleaved phase by phase: the chain

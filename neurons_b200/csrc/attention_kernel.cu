@@ -50,7 +50,7 @@ template <typename T> struct RowVec<T, 1> {
 // rows on different banks (row pitch in bytes = 3*HB*dh*s + 16).
 template <typename T, int VEC, int FMAX>
 __global__ void __launch_bounds__(256) temporal_attention_kernel(const T *__restrict__ qkv, T *__restrict__ ctx, int B, int F,
-                                                                 int P, int C, int heads, int PB, int HB, float scale) {
+                                                                 int P, int C, int heads, int PB, int HB, float scale, int split_out) {
     pdl_wait();                    // PDL: the previous kernel has completed (no-op without the launch attribute)
     pdl_launch_dependents();       // let the next kernel's launch + prologue overlap this kernel
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -161,6 +161,20 @@ __global__ void __launch_bounds__(256) temporal_attention_kernel(const T *__rest
         for (int r = warp; r < rows; r += nwarps) {
             const int f2 = r / npos, pl2 = r - f2 * npos;
             const T *src_row = sm + (pl2 * F + f2) * pitch;
+            if constexpr (sizeof(T) == 4) {
+                if (split_out) {                      // NMM_F32X3: ctx is the next GEMM's A operand, bf16 [N, 2C] hi | lo planes
+                    bf16 *srow = reinterpret_cast<bf16 *>(ctx) + ((int64_t)(b * F + f2) * P + p0 + pl2) * (2 * C);
+                    if (VEC > 1) {
+                        for (int v = lane; v < W / 4; v += 32) {
+                            const float4 f4 = *reinterpret_cast<const float4 *>(src_row + v * 4);
+                            split4_store(srow, C, c_off + v * 4, f4.x, f4.y, f4.z, f4.w);
+                        }
+                    } else {
+                        for (int e = lane; e < W; e += 32) split1_store(srow, C, c_off + e, to_f32(src_row[e]));
+                    }
+                    continue;
+                }
+            }
             T *dst_row = ctx + ((int64_t)(b * F + f2) * P + p0 + pl2) * C + c_off;
             if (VEC > 1) {
                 for (int v = lane; v < W / LV; v += 32)
@@ -173,7 +187,7 @@ __global__ void __launch_bounds__(256) temporal_attention_kernel(const T *__rest
 }
 
 template <typename T, int VEC>
-static int launch_attn_t(const Geo &g, const T *qkv, T *ctx, cudaStream_t st) {
+static int launch_attn_t(const Geo &g, const T *qkv, T *ctx, cudaStream_t st, int split_out = 0) {
     if (g.heads * g.F > 256 && g.F > 256) return fail(NMM_ERR_UNSUPPORTED, "frames too large");
     const size_t smem_cap = 200 * 1024, smem_pref = 32 * 1024;       // <= 32 KB: ~7 CTAs per SM, so load / compute / store phases of different CTAs overlap
     auto row_bytes = [&](int hb) { return (size_t)(3 * hb * g.dh) * sizeof(T) + 16; };
@@ -203,7 +217,7 @@ static int launch_attn_t(const Geo &g, const T *qkv, T *ctx, cudaStream_t st) {
         static DeviceOnce once; /* per instantiation and device; never inside a stream capture after warm-up */            \
         NMM_CUDA_OK(once.max_smem(kern, (int)smem_cap));          \
         ProfScope prof(K_ATTENTION, st, 4.0 * g.N * g.F * g.C, 4.0 * g.N * g.C * sizeof(T));                             \
-        launch_pdl(kern, grid, threads, smem, st, qkv, ctx, g.B, g.F, g.P, g.C, g.heads, PB, HB, scale);                          \
+        launch_pdl(kern, grid, threads, smem, st, qkv, ctx, g.B, g.F, g.P, g.C, g.heads, PB, HB, scale, split_out);                          \
     } while (0)
     if (g.F <= 8) ATTN_CASE(8);
     else if (g.F <= 16) ATTN_CASE(16);
@@ -509,8 +523,9 @@ int launch_temporal_attention(const Geo &g, const void *qkv, void *ctx, cudaStre
         if (g.dh % 8 == 0 && al) return launch_attn_t<bf16, 8>(g, (const bf16 *)qkv, (bf16 *)ctx, st);
         return launch_attn_t<bf16, 1>(g, (const bf16 *)qkv, (bf16 *)ctx, st);
     }
-    if (g.dh % 4 == 0 && al) return launch_attn_t<float, 4>(g, (const float *)qkv, (float *)ctx, st);
-    return launch_attn_t<float, 1>(g, (const float *)qkv, (float *)ctx, st);
+    const int split = g.dtype == NMM_F32X3 ? 1 : 0;      // the context feeds to_out's tensor-core GEMM: hi | lo bf16 planes
+    if (g.dh % 4 == 0 && al && g.C % 4 == 0) return launch_attn_t<float, 4>(g, (const float *)qkv, (float *)ctx, st, split);
+    return launch_attn_t<float, 1>(g, (const float *)qkv, (float *)ctx, st, split);
 }
 
 }  // namespace nmm

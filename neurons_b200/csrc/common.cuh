@@ -115,7 +115,7 @@ inline Geo geo_of(const nmm_shape *s) {
     g.ln_fold = s->ln_fold != 0 && s->dtype == NMM_BF16;
     return g;
 }
-inline size_t dtype_size(int dtype) { return dtype == NMM_BF16 ? 2 : 4; }
+inline size_t dtype_size(int dtype) { return dtype == NMM_BF16 ? 2 : 4; }      // NMM_F32 and NMM_F32X3 store fp32
 
 // ---- device helpers ------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
@@ -140,6 +140,24 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+// NMM_F32X3 operand format: an fp32 value as two bf16 terms, v = hi + lo + O(2^-17 |v|).  A [rows, K] fp32 operand is stored as a bf16
+// [rows, 2K] tensor: row r = hi plane (K values) | lo plane (K values).  split4_store writes four consecutive values of one row.
+__device__ __forceinline__ void split_bf16x2(float x, float y, uint32_t &hi, uint32_t &lo) {
+    hi = pack_bf16x2(x, y);
+    lo = pack_bf16x2(x - bf16_lo(hi), y - bf16_hi(hi));
+}
+__device__ __forceinline__ void split4_store(bf16 *row, int K, int c, float a, float b, float cc, float d) {      // c % 4 == 0, row 8-byte aligned, K % 4 == 0
+    uint32_t h0, l0, h1, l1;
+    split_bf16x2(a, b, h0, l0);
+    split_bf16x2(cc, d, h1, l1);
+    *reinterpret_cast<uint2 *>(row + c) = make_uint2(h0, h1);
+    *reinterpret_cast<uint2 *>(row + K + c) = make_uint2(l0, l1);
+}
+__device__ __forceinline__ void split1_store(bf16 *row, int K, int c, float v) {
+    const bf16 h = __float2bfloat16_rn(v);
+    row[c] = h;
+    row[K + c] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
 
 // exact (erf) GELU, as torch.nn.functional.gelu default -- motion_module_new.py:510-518
 __device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
@@ -212,7 +230,7 @@ __device__ __forceinline__ void gn_finalize_one(const double *__restrict__ parti
 int launch_gn_stats(const Geo &g, const nmm_shape *s, const void *x, double *partial, cudaStream_t st);
 int launch_gn_finalize(const Geo &g, const nmm_shape *s, const double *partial, float *mean, float *rstd, cudaStream_t st);
 int launch_gn_tokens(const Geo &g, const nmm_shape *s, const Geo &full, const void *x, const double *partial, const float *gn_w,
-                     const float *gn_b, void *tokens, cudaStream_t st);
+                     const float *gn_b, void *tokens, cudaStream_t st);      // NMM_F32X3: tokens = bf16 [N, 2C] hi | lo planes
 // LayerNorm (+PE)
 int launch_layernorm_pe(const Geo &g, const nmm_shape *s, const float *h, const float *w, const float *b,
                         const float *pe, void *out, cudaStream_t st);
@@ -235,6 +253,8 @@ struct LinearArgs {
     float *h;                // RESIDUAL: fp32 [M,N] in/out
     void *out;               // STORE: [M,N]; RESIDUAL: optional [M,N] copy; GEGLU: [M,N/2]   (dtype)
     int no_h_store;          // RESIDUAL: h is only read, the sum goes to `out` alone (the last feed-forward)
+    int x3;                  // NMM_F32X3 (tensor-core path only): A is bf16 [M, 2K] and W bf16 [N, 2K], each row = hi plane | lo plane; `out`
+                             // is written the same way ([M, 2N], GEGLU [M, N]); x / y of the OUTPUT epilogue are fp32 (gemm_tcgen05.cu, X3)
     // OUTPUT epilogue
     const void *x; void *y;
     int F, P;

@@ -37,7 +37,7 @@ inline EpiParams epi_params_of(const LinearArgs &a) {
     e.ln_part_out = a.ln_part_out; e.ln_part_in = a.ln_part_in; e.ln_nparts = a.ln_nparts; e.ln_K = a.K;
     e.ln_g = a.ln_g; e.ln_c = a.ln_c; e.ln_pew = a.ln_pew; e.ln_eps = a.ln_eps;
     e.nchw_vec = 0;
-    if (a.epilogue == NMM_EPI_OUTPUT && a.P > 0 && a.P % 32 == 0 && aligned(a.x, 16) && aligned(a.y, 16) && a.xsb % 8 == 0 &&
+    if (a.epilogue == NMM_EPI_OUTPUT && !a.x3 && a.P > 0 && a.P % 32 == 0 && aligned(a.x, 16) && aligned(a.y, 16) && a.xsb % 8 == 0 &&
         a.xsc % 8 == 0 && a.xsf % 8 == 0 && a.ysb % 8 == 0 && a.ysc % 8 == 0 && a.ysf % 8 == 0)
         e.nchw_vec = 1;
     return e;

@@ -180,7 +180,10 @@ __device__ __forceinline__ void fused_attention_phase(const AttnParams &at, uint
 // LNF: LayerNorm-folding roles compiled in (consumer transform / producer statistics).  Kept out of the default instantiation:
 // a run-time branch inside the unrolled epilogue loops costs the GEGLU epilogue its instruction-level parallelism (measured
 // 128 -> 204 us at C = 320).
-template <int EPI, int CG, bool LNF, bool GNA>
+// X3: fp32-grade mode (NMM_F32X3).  Both operands arrive as bf16 [rows, 2K] = [hi | lo] planes (v = hi + lo + O(2^-17 v)); the K loop runs
+// 3 * K / 64 k-blocks: hi.hi, hi.lo and lo.hi products accumulated in fp32 (the lo.lo term, 2^-16 relative, is dropped) -- the same
+// mainloop, three passes over the planes.  GEMM-operand outputs (`out`) are written as hi | lo planes too; x / y of the OUTPUT epilogue are fp32.
+template <int EPI, int CG, bool LNF, bool GNA, bool X3>
 __global__ void __launch_bounds__(EPI == NMM_EPI_QKV_ATTN ? TC_THREADS + 32 * TC_ATTN_HELPERS : GNA ? TC_THREADS + 32 * TC_GN_WARPS : TC_THREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
                  const __grid_constant__ CUtensorMap tm_h,      // fp32 [M,N], box 32 x 32, 128-byte swizzle (residual load / h store)
@@ -206,7 +209,11 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const uint32_t epi_base = bar_base + TC_BAR_BYTES;                          // 8 x 8 KB, 1024-byte aligned
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_kb = (p.K + TC_BK - 1) / TC_BK;
+    const int nk = (p.K + TC_BK - 1) / TC_BK;                        // k-blocks of one operand plane
+    const int num_kb = X3 ? 3 * nk : nk;
+    // X3: k-block kb = pass t * nk + j multiplies A plane (t == 2 ? lo : hi) by W plane (t == 1 ? lo : hi); small terms last
+    auto a_col = [&](int kb) { if constexpr (X3) { const int t = kb / nk, j = kb - t * nk; return (t == 2 ? nk + j : j) * TC_BK; } else return kb * TC_BK; };
+    auto w_col = [&](int kb) { if constexpr (X3) { const int t = kb / nk, j = kb - t * nk; return (t == 1 ? nk + j : j) * TC_BK; } else return kb * TC_BK; };
     // Tile schedule: a cluster walks (m_group, n_blk) pairs; CTA `rank` of the cluster owns m-block m_group*CG + rank.
     // Both CTAs of a pair run the same number of iterations (a phantom m-block past the end is all zero-fill + clipped).
     // rank inside the (CG, 1, 1) cluster = blockIdx.x % CG, taken from blockIdx on purpose: the compiler must KNOW it is uniform.  With
@@ -251,15 +258,15 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             // W tile of k-block kb -> the stage (any time: weights are constant); A tile -> the stage (after griddepcontrol.wait)
             auto issue_w = [&](int kb, int n_blk, uint32_t sa, uint32_t bar) {
                 if constexpr (CG == 1) {
-                    ptx::tma_load_2d(&tm_w, bar, sa + TC_A_BYTES, kb * TC_BK, n_blk * p.block_n);
+                    ptx::tma_load_2d(&tm_w, bar, sa + TC_A_BYTES, w_col(kb), n_blk * p.block_n);
                 } else {
                     const uint32_t bar0 = bar & ptx::PEER_MASK;
                     if (p.wide) {      // two N = 160 blocks, this CTA stages its 80-row half of each
                         const uint32_t hb = b_rows / 2;
-                        ptx::tma_load_2d_2sm(&tm_w, bar0, sa + TC_A_BYTES, kb * TC_BK, n_blk * p.block_n + (int)(rank * hb));
-                        ptx::tma_load_2d_2sm(&tm_w, bar0, sa + TC_A_BYTES + hb * TC_BK * 2, kb * TC_BK, n_blk * p.block_n + p.block_n / 2 + (int)(rank * hb));
+                        ptx::tma_load_2d_2sm(&tm_w, bar0, sa + TC_A_BYTES, w_col(kb), n_blk * p.block_n + (int)(rank * hb));
+                        ptx::tma_load_2d_2sm(&tm_w, bar0, sa + TC_A_BYTES + hb * TC_BK * 2, w_col(kb), n_blk * p.block_n + p.block_n / 2 + (int)(rank * hb));
                     } else {
-                        ptx::tma_load_2d_2sm(&tm_w, bar0, sa + TC_A_BYTES, kb * TC_BK, n_blk * p.block_n + (int)(rank * b_rows));
+                        ptx::tma_load_2d_2sm(&tm_w, bar0, sa + TC_A_BYTES, w_col(kb), n_blk * p.block_n + (int)(rank * b_rows));
                     }
                 }
             };
@@ -274,9 +281,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     ptx::tma_load_4d(&tm_a, bar, sa, gp[0], kb * TC_BK, gf[0], gb[0]);
                     ptx::tma_load_4d(&tm_a, bar, sa + TC_A_HALF, gp[1], kb * TC_BK, gf[1], gb[1]);
                 } else if constexpr (CG == 1) {
-                    ptx::tma_load_2d(&tm_a, bar, sa, kb * TC_BK, (int32_t)(m_blk * TC_BM));
+                    ptx::tma_load_2d(&tm_a, bar, sa, a_col(kb), (int32_t)(m_blk * TC_BM));
                 } else {
-                    ptx::tma_load_2d_2sm(&tm_a, bar & ptx::PEER_MASK, sa, kb * TC_BK, (int32_t)(m_blk * TC_BM));
+                    ptx::tma_load_2d_2sm(&tm_a, bar & ptx::PEER_MASK, sa, a_col(kb), (int32_t)(m_blk * TC_BM));
                 }
             };
             // both CTAs' bytes of a pair are counted on the even CTA's barrier (the only one the MMA thread waits on)
@@ -624,7 +631,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                                 float acc[16];
 #pragma unroll
                                 for (int j = 0; j < 16; j++) acc[j] = __uint_as_float(r[j]);
-                                epilogue_apply<EPI, bf16, 16>(e, row, col0, acc);
+                                epilogue_apply<EPI, std::conditional_t<X3, float, bf16>, 16>(e, row, col0, acc);
                             }
                         }
                     }
@@ -635,6 +642,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     const int col0 = n_blk * p.block_n + c0;
                     wait_acc();
                     uint32_t o[16];
+                    uint32_t olo[X3 ? 16 : 1];                             // X3: bf16 residuals of the outputs (the lo plane)
                     // both 32-column halves are requested before the single tcgen05.wait::ld: one exposed TMEM latency per chunk
                     uint32_t r[2][32];
                     ptx::tmem_ld32(t_row + (uint32_t)c0, r[0]);
@@ -667,7 +675,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                             }
                             float y0, y1;
                             geglu_pair(v0, g0, v1, g1, y0, y1);
-                            o[8 * hc + j] = pack_bf16x2(y0, y1);
+                            if constexpr (X3) split_bf16x2(y0, y1, o[8 * hc + j], olo[8 * hc + j]);
+                            else o[8 * hc + j] = pack_bf16x2(y0, y1);
                         }
                     };
                     if (e.bias != nullptr && !ln_in) { half_chunk(std::true_type{}, 0); half_chunk(std::true_type{}, 1); }
@@ -676,9 +685,17 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     __syncwarp();
 #pragma unroll
                     for (int j = 0; j < 4; j++) sts128(box_bf16_addr(box0, lane, j), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                    if constexpr (X3) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) sts128(box_bf16_addr(box1, lane, j), olo[4 * j], olo[4 * j + 1], olo[4 * j + 2], olo[4 * j + 3]);
+                    }
                     ptx::fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0) { ptx::tma_store_2d(&tm_o, box0, col0 / 2, (int32_t)row0); ptx::bulk_commit(); }
+                    if (lane == 0) {
+                        ptx::tma_store_2d(&tm_o, box0, col0 / 2, (int32_t)row0);
+                        if constexpr (X3) ptx::tma_store_2d(&tm_o, box1, p.N / 2 + col0 / 2, (int32_t)row0);      // lo plane: columns [N/2, N) of `out`
+                        ptx::bulk_commit();
+                    }
                     if (warp == 4 && lane == 0 && c0 / 128 < 4) TRACE(tile_no, 8 + c0 / 128);
                 }
             } else {
@@ -762,16 +779,28 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                                    __float_as_uint(v[4 * j + 3]));
                     }
                     if (want_o) {
+                        if constexpr (X3) {                               // hi plane -> obox, lo plane -> obox + 2 KB (both halves of a 4 KB box)
+                            uint32_t hi[16], lo[16];
 #pragma unroll
-                        for (int j = 0; j < 4; j++)
-                            sts128(box_bf16_addr(obox, lane, j), pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                                   pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+                            for (int j = 0; j < 16; j++) split_bf16x2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                sts128(box_bf16_addr(obox, lane, j), hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                                sts128(box_bf16_addr(obox + 2048u, lane, j), lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; j++)
+                                sts128(box_bf16_addr(obox, lane, j), pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                       pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+                        }
                     }
                     ptx::fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
                         if (want_h) ptx::tma_store_2d(&tm_h, box, col0, (int32_t)row0);
                         if (want_o) ptx::tma_store_2d(&tm_o, obox, col0, (int32_t)row0);
+                        if constexpr (X3) { if (want_o) ptx::tma_store_2d(&tm_o, obox + 2048u, p.N + col0, (int32_t)row0); }   // lo plane: columns [N, 2N)
                         ptx::bulk_commit();
                     }
                     if (warp == 4 && lane == 0 && k < 4) TRACE(tile_no, 8 + k);
@@ -957,11 +986,11 @@ void plan_linear_tc(int64_t M, int N, int K, int epilogue, int *block_n, int *cl
     *cluster = plan.cluster;
 }
 
-template <int EPI, int CG, bool LNF, bool GNA = false>
+template <int EPI, int CG, bool LNF, bool GNA = false, bool X3 = false>
 static int launch_tc_t(const CUtensorMap &ta, const CUtensorMap &tw, const CUtensorMap &th, const CUtensorMap &to, const TcParams &p,
                        const EpiParams &e, size_t smem, int grid, cudaStream_t st, double flops, double bytes, const GnParams &gn = GnParams(),
                        const AttnParams &at = AttnParams()) {
-    auto kern = linear_tc_kernel<EPI, CG, LNF, GNA>;
+    auto kern = linear_tc_kernel<EPI, CG, LNF, GNA, X3>;
     static DeviceOnce once;           // per template instantiation and device
     NMM_CUDA_OK(once.max_smem(kern, TC_SMEM_MAX));
     cudaLaunchConfig_t cfg;
@@ -992,6 +1021,10 @@ int launch_linear_tc(const LinearArgs &a, cudaStream_t st) {
     if (a.N % 32 != 0) return fail(NMM_ERR_UNSUPPORTED, "tcgen05 GEMM needs N %% 32 == 0 (N=%d)", a.N);
     if (a.epilogue == NMM_EPI_GEGLU && a.N % 64 != 0) return fail(NMM_ERR_UNSUPPORTED, "GEGLU epilogue needs N %% 64 == 0 (N=%d)", a.N);
     if (a.K % 8 != 0) return fail(NMM_ERR_UNSUPPORTED, "tcgen05 GEMM needs K %% 8 == 0 (K=%d)", a.K);
+    const bool x3 = a.x3 != 0;
+    if (x3 && (a.K % TC_BK != 0 || a.gn_x != nullptr || a.epilogue == NMM_EPI_QKV_ATTN || a.ln_part_in != nullptr || a.ln_part_out != nullptr ||
+               (a.epilogue == NMM_EPI_STORE && a.out != nullptr)))
+        return fail(NMM_ERR_UNSUPPORTED, "3 x bf16 (fp32-grade) tensor-core GEMM: needs K %% 64 == 0, no fused GroupNorm / attention / LayerNorm folding, and a STORE epilogue writing fp32 only");
     if (a.M <= 0) return NMM_OK;
     TcParams p;
     p.M = a.M; p.N = a.N; p.K = a.K;
@@ -1024,7 +1057,7 @@ int launch_linear_tc(const LinearArgs &a, cudaStream_t st) {
     const int gran = a.epilogue == NMM_EPI_GEGLU ? 64 : 32;
     const bool allow_wide = a.epilogue == NMM_EPI_RESIDUAL && !gna && a.ln_part_in == nullptr && a.ln_part_out == nullptr && !(debug_flags & 2) && opt(NMM_OPT_WIDE_TILE) != 0;
     const TilePlan plan = attn ? TilePlan{3 * NMM_ATTN_TILE_CH, 1, 0} :
-                          choose_tiles(p.m_tiles, a.N, a.K, sms, gran, gna ? 1 : (force_cluster == 1 || force_cluster == 2) ? force_cluster : 0,
+                          choose_tiles(p.m_tiles, a.N, x3 ? 3 * a.K : a.K, sms, gran, gna ? 1 : (force_cluster == 1 || force_cluster == 2) ? force_cluster : 0,
                                        (force_bn >= gran && force_bn <= 320 && force_bn % gran == 0 && a.N % force_bn == 0) ? force_bn : 0, allow_wide);
     if (plan.block_n == 0) return fail(NMM_ERR_UNSUPPORTED, "tcgen05 GEMM: no N tile for N=%d", a.N);
     p.block_n = plan.block_n;
@@ -1046,12 +1079,13 @@ int launch_linear_tc(const LinearArgs &a, cudaStream_t st) {
     p.tmem_cols = cols;
     const size_t smem = fixed + (size_t)stages * stage_bytes;
     CUtensorMap ta, tw, th, to;
+    const int64_t kcols = x3 ? 2 * (int64_t)a.K : a.K;          // X3: [hi | lo] planes side by side
     int rc = attn ? make_tmap_tokens_pf(&ta, a.A, a.attn_B, a.K, a.F, a.P, TC_BM / a.F)
              : gna ? make_tmap_x(&ta, a.gn_x, a.gn_B, a.K, a.F, a.P, a.xsb, a.xsc, a.xsf)
-                 : make_tmap(&ta, a.A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.M, a.K, a.K, TC_BM, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B);
+                 : make_tmap(&ta, a.A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.M, kcols, kcols, TC_BM, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != NMM_OK) return rc;
     // each CTA of a pair fetches its slice of the W tile
-    rc = make_tmap(&tw, a.W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.N, a.K, a.K, p.block_n / p.cluster / (p.wide ? 2 : 1), TC_BK, CU_TENSOR_MAP_SWIZZLE_128B);
+    rc = make_tmap(&tw, a.W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.N, kcols, kcols, p.block_n / p.cluster / (p.wide ? 2 : 1), TC_BK, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != NMM_OK) return rc;
     memset(&th, 0, sizeof(th));
     memset(&to, 0, sizeof(to));
@@ -1060,7 +1094,7 @@ int launch_linear_tc(const LinearArgs &a, cudaStream_t st) {
         if (rc != NMM_OK) return rc;
     }
     if (a.out != nullptr && a.epilogue != NMM_EPI_OUTPUT && !attn) {
-        const int64_t ncols = a.epilogue == NMM_EPI_GEGLU ? a.N / 2 : a.N;
+        const int64_t ncols = (a.epilogue == NMM_EPI_GEGLU ? a.N / 2 : a.N) * (x3 ? 2 : 1);
         rc = make_tmap(&to, a.out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.M, ncols, ncols, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
         if (rc != NMM_OK) return rc;
     }
@@ -1084,6 +1118,9 @@ int launch_linear_tc(const LinearArgs &a, cudaStream_t st) {
         return launch_tc_t<NMM_EPI_STORE, 1, false, true>(ta, tw, th, to, p, e, smem, grid, st, fl, by, gn);
     }
 #define TC_DISPATCH(EPI)                                                                                   \
+    if (x3)                                                                                                \
+        return p.cluster == 2 ? launch_tc_t<EPI, 2, false, false, true>(ta, tw, th, to, p, e, smem, grid, st, fl, by)    \
+                              : launch_tc_t<EPI, 1, false, false, true>(ta, tw, th, to, p, e, smem, grid, st, fl, by);   \
     if (lnf)                                                                                               \
         return p.cluster == 2 ? launch_tc_t<EPI, 2, true>(ta, tw, th, to, p, e, smem, grid, st, fl, by)    \
                               : launch_tc_t<EPI, 1, true>(ta, tw, th, to, p, e, smem, grid, st, fl, by);   \

@@ -5,6 +5,8 @@
 //   layernorm_pe    reads h (fp32) once, writes n once             bytes = N*C*(4+s)
 // Reference arithmetic: motion_module.py:142-144 (GroupNorm + permute/reshape), :212/:219 (LayerNorm),
 // :241-243 (x + pe[:, :f]).
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace nmm {
@@ -153,7 +155,8 @@ int launch_gn_finalize(const Geo &g, const nmm_shape *s, const double *partial, 
 //   tokens[(bf*P + p), c] = (x[b,c,f,p] - mean[bf,g]) * rstd[bf,g] * gamma[c] + beta[c]
 // Generic kernel: 32(c) x 32(p) tile through shared memory, any dtype / alignment / ragged edges.
 // ------------------------------------------------------------------------------------------------
-template <typename T>
+// SPLIT (NMM_F32X3): tokens is a bf16 [N, 2C] tensor, every row = hi plane | lo plane of the fp32 values.
+template <typename T, bool SPLIT = false>
 __global__ void __launch_bounds__(256) gn_tokens_generic_kernel(const T *__restrict__ x, const double *__restrict__ partial,
                                                                 const float *__restrict__ gamma, const float *__restrict__ beta,
                                                                 T *__restrict__ tokens, int C, int F, int P, int splits, double count,
@@ -186,7 +189,10 @@ __global__ void __launch_bounds__(256) gn_tokens_generic_kernel(const T *__restr
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         int pl = ty + i * 8, p = p0 + pl, c = c0 + tx;
-        if (c < C && p < P) tokens[((int64_t)bf * P + p) * C + c] = from_f32<T>(tile[tx][pl]);
+        if (c < C && p < P) {
+            if constexpr (SPLIT) split1_store(reinterpret_cast<bf16 *>(tokens) + ((int64_t)bf * P + p) * (2 * C), C, c, tile[tx][pl]);
+            else tokens[((int64_t)bf * P + p) * C + c] = from_f32<T>(tile[tx][pl]);
+        }
     }
 }
 
@@ -254,6 +260,9 @@ int launch_gn_tokens(const Geo &g, const nmm_shape *s, const Geo &full, const vo
     ProfScope prof(K_GN_TOKENS, st, 0.0, 2.0 * g.N * g.C * dtype_size(g.dtype));
     if (g.dtype == NMM_BF16)
         launch_pdl(gn_tokens_generic_kernel<bf16>, grid, 256, 0, st, (const bf16 *)x, partial, gn_w, gn_b, (bf16 *)tokens, g.C, g.F,
+                   g.P, splits, count, s->eps_gn, s->x_stride_b, s->x_stride_c, s->x_stride_f);
+    else if (g.dtype == NMM_F32X3)
+        launch_pdl(gn_tokens_generic_kernel<float, true>, grid, 256, 0, st, (const float *)x, partial, gn_w, gn_b, (float *)tokens, g.C, g.F,
                    g.P, splits, count, s->eps_gn, s->x_stride_b, s->x_stride_c, s->x_stride_f);
     else
         launch_pdl(gn_tokens_generic_kernel<float>, grid, 256, 0, st, (const float *)x, partial, gn_w, gn_b, (float *)tokens, g.C, g.F,
@@ -354,6 +363,8 @@ __device__ __forceinline__ float half_warp_sum(float v) {
     return v;
 }
 
+struct SplitOut { uint32_t pair; };      // tag (4 bytes per element like fp32): `out` is bf16 [N, 2C], row = hi plane | lo plane (NMM_F32X3)
+
 template <typename TOut, int IT4>
 __global__ void __launch_bounds__(256) layernorm_pe_vec_kernel(const float *__restrict__ h, const float *__restrict__ gamma,
                                                                const float *__restrict__ beta, const float *__restrict__ pe,
@@ -382,7 +393,7 @@ __global__ void __launch_bounds__(256) layernorm_pe_vec_kernel(const float *__re
     }
     const float rstd = rsqrtf(half_warp_sum(ss) * (1.0f / C) + eps);
     const float4 *per = pe ? reinterpret_cast<const float4 *>(pe + (int64_t)((row / P) % F) * C) : nullptr;
-    TOut *orow = out + row * C;
+    TOut *orow = out + row * C;               // (SplitOut: 4 bytes per element as well, so this is the row's hi plane)
 #pragma unroll
     for (int i = 0; i < IT4; i++) {
         const int c4 = l16 + 16 * i;
@@ -393,7 +404,8 @@ __global__ void __launch_bounds__(256) layernorm_pe_vec_kernel(const float *__re
         o.z = fmaf((v[i].z - mu) * rstd, gm.z, bt.z); o.w = fmaf((v[i].w - mu) * rstd, gm.w, bt.w);
         if (per) { const float4 pp = __ldg(per + c4); o.x += pp.x; o.y += pp.y; o.z += pp.z; o.w += pp.w; }
         if (valid) {
-            if constexpr (sizeof(TOut) == 2) reinterpret_cast<uint2 *>(orow)[c4] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+            if constexpr (std::is_same<TOut, SplitOut>::value) split4_store(reinterpret_cast<bf16 *>(orow), C, 4 * c4, o.x, o.y, o.z, o.w);
+            else if constexpr (sizeof(TOut) == 2) reinterpret_cast<uint2 *>(orow)[c4] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
             else reinterpret_cast<float4 *>(orow)[c4] = o;
         }
     }
@@ -421,7 +433,8 @@ __global__ void __launch_bounds__(256) layernorm_pe_generic_kernel(const float *
     for (int c = lane; c < C; c += 32) {
         float a = fmaf((hr[c] - mu) * rstd, gamma[c], beta[c]);
         if (per) a += per[c];
-        orow[c] = from_f32<TOut>(a);
+        if constexpr (std::is_same<TOut, SplitOut>::value) split1_store(reinterpret_cast<bf16 *>(orow), C, c, a);
+        else orow[c] = from_f32<TOut>(a);
     }
 }
 
@@ -453,6 +466,7 @@ static int launch_ln_t(const Geo &g, const nmm_shape *s, const float *h, const f
 int launch_layernorm_pe(const Geo &g, const nmm_shape *s, const float *h, const float *w, const float *b, const float *pe,
                         void *out, cudaStream_t st) {
     if (g.dtype == NMM_BF16) return launch_ln_t<bf16>(g, s, h, w, b, pe, (bf16 *)out, st);
+    if (g.dtype == NMM_F32X3) return launch_ln_t<SplitOut>(g, s, h, w, b, pe, (SplitOut *)out, st);
     return launch_ln_t<float>(g, s, h, w, b, pe, (float *)out, st);
 }
 

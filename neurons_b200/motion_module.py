@@ -191,7 +191,8 @@ def config_of(module: nn.Module) -> ModuleConfig:
     pos = getattr(a0, "pos_encoder", None)
     return ModuleConfig(channels=channels, heads=int(a0.heads), layers=len(blocks), attn_blocks=len(b0.attention_blocks),
                         pos_enc=pos is not None, max_len=int(pos.pe.shape[1]) if pos is not None else 0,
-                        ln_fold=bool(module.__dict__.get("_nmm_ln_fold", False)))      # set by tests / experiments before the first call
+                        ln_fold=bool(module.__dict__.get("_nmm_ln_fold", False)),      # set by tests / experiments before the first call
+                        fp32_tc=not bool(module.__dict__.get("_nmm_fp32_fma", False)))  # fp32 activations: tensor cores (3 x bf16) unless set
 
 
 def _param_tensors(module: nn.Module) -> Dict[str, torch.Tensor]:

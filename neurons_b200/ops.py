@@ -33,10 +33,18 @@ class ModuleConfig:
     # Measured on B200 it is slower (it moves work into the GEMM epilogue, which is the bottleneck: 8.5 vs 7.6 ms/step), so the
     # default keeps the separate, exactly-LayerNorm kernel; NMM_LN_FOLD=1 / ln_fold=True enables it (kept as a tested option).
     ln_fold: bool = False
+    # fp32 activations: True = every Linear on the tensor cores as 3 bf16 MMAs per product (NMM_F32X3; needs channels % 64 == 0,
+    # other widths use the FMA path); False (or env NMM_FP32_FMA=1) = the fp32 FMA-pipe GEMM (NMM_F32), kept as the checker.
+    fp32_tc: bool = True
 
 
-def _dtype_code(dt: torch.dtype) -> int:
+_FP32_FMA_ENV = os.environ.get("NMM_FP32_FMA")     # read ONCE at import (pack and forward must agree on the mode)
+
+
+def _dtype_code(dt: torch.dtype, cfg: Optional["ModuleConfig"] = None) -> int:
     if dt == torch.float32:
+        if cfg is not None and cfg.fp32_tc and cfg.channels % 64 == 0 and _FP32_FMA_ENV in (None, "0"):
+            return _lib.NMM_F32X3
         return _lib.NMM_F32
     if dt == torch.bfloat16:
         return _lib.NMM_BF16
@@ -68,7 +76,7 @@ def make_shape(cfg: ModuleConfig, x: torch.Tensor, y: Optional[torch.Tensor] = N
     s.batch, s.channels, s.frames, s.height, s.width = B, Cc, F, H, W
     s.heads, s.layers, s.attn_blocks = cfg.heads, cfg.layers, cfg.attn_blocks
     s.pos_enc, s.max_len = int(cfg.pos_enc), cfg.max_len
-    s.dtype = _dtype_code(x.dtype)
+    s.dtype = _dtype_code(x.dtype, cfg)
     s.eps_gn, s.eps_ln = GN_EPS, LN_EPS
     s.ln_fold = _ln_fold(cfg)
     s.x_stride_b, s.x_stride_c, s.x_stride_f = x.stride(0), x.stride(1), x.stride(2)
@@ -92,7 +100,7 @@ def packed_params_bytes(cfg: ModuleConfig, dtype: torch.dtype, frames: int = 1) 
     s.batch = s.height = s.width = 1
     s.frames = frames
     s.channels, s.heads, s.layers, s.attn_blocks = cfg.channels, cfg.heads, cfg.layers, cfg.attn_blocks
-    s.pos_enc, s.max_len, s.dtype = int(cfg.pos_enc), cfg.max_len, _dtype_code(dtype)
+    s.pos_enc, s.max_len, s.dtype = int(cfg.pos_enc), cfg.max_len, _dtype_code(dtype, cfg)
     s.eps_gn, s.eps_ln, s.ln_fold = GN_EPS, LN_EPS, _ln_fold(cfg)
     n = C.c_size_t()
     _lib.check(_lib.load().nmm_packed_params_bytes(C.byref(s), C.byref(n)))
@@ -152,7 +160,7 @@ def pack_params(cfg: ModuleConfig, tensors: Dict[str, torch.Tensor], compute_dty
     s = _lib.Shape()
     s.batch = s.frames = s.height = s.width = 1
     s.channels, s.heads, s.layers, s.attn_blocks = cfg.channels, cfg.heads, cfg.layers, cfg.attn_blocks
-    s.pos_enc, s.max_len, s.dtype = int(cfg.pos_enc), cfg.max_len, _dtype_code(compute_dtype)
+    s.pos_enc, s.max_len, s.dtype = int(cfg.pos_enc), cfg.max_len, _dtype_code(compute_dtype, cfg)
     s.eps_gn, s.eps_ln, s.ln_fold = GN_EPS, LN_EPS, _ln_fold(cfg)
     with torch.cuda.device(device):
         _lib.check(lib.nmm_pack_params(C.byref(s), C.byref(p), packed.data_ptr(), nbytes, _stream_ptr(device)))
@@ -216,7 +224,7 @@ def packed_header(cfg: ModuleConfig, dtype: torch.dtype) -> bytes:
     s = _lib.Shape()
     s.batch = s.frames = s.height = s.width = 1
     s.channels, s.heads, s.layers, s.attn_blocks = cfg.channels, cfg.heads, cfg.layers, cfg.attn_blocks
-    s.pos_enc, s.max_len, s.dtype = int(cfg.pos_enc), cfg.max_len, _dtype_code(dtype)
+    s.pos_enc, s.max_len, s.dtype = int(cfg.pos_enc), cfg.max_len, _dtype_code(dtype, cfg)
     s.eps_gn, s.eps_ln, s.ln_fold = GN_EPS, LN_EPS, _ln_fold(cfg)
     buf = C.create_string_buffer(64)
     _lib.check(_lib.load().nmm_packed_header(C.byref(s), buf, 64))
@@ -387,15 +395,31 @@ def temporal_attention(cfg: ModuleConfig, dims, qkv: torch.Tensor) -> torch.Tens
     return ctx
 
 
+def split_planes(t: torch.Tensor) -> torch.Tensor:
+    """fp32 [rows, K] -> the NMM_F32X3 operand format: bf16 [rows, 2K], row = hi plane | lo plane (t = hi + lo + O(2^-17 t))."""
+    hi = t.to(torch.bfloat16)
+    lo = (t.float() - hi.float()).to(torch.bfloat16)
+    return torch.cat([hi, lo], dim=1).contiguous()
+
+
+def merge_planes(t: torch.Tensor) -> torch.Tensor:
+    k = t.shape[1] // 2
+    return t[:, :k].float() + t[:, k:].float()
+
+
 def linear(A: torch.Tensor, Wt: torch.Tensor, bias: Optional[torch.Tensor] = None, epilogue: int = _lib.EPI_STORE,
            h: Optional[torch.Tensor] = None, want_out: bool = True, cfg: Optional[ModuleConfig] = None,
-           x: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
-    """D = A . Wt^T with a fused epilogue (see include/neurons_mm.h nmm_epilogue).  A: [M,K], Wt: [N,K]."""
+           x: Optional[torch.Tensor] = None, x3: bool = False) -> Optional[torch.Tensor]:
+    """D = A . Wt^T with a fused epilogue (see include/neurons_mm.h nmm_epilogue).  A: [M,K], Wt: [N,K].
+    x3=True (fp32 A / Wt): the 3 x bf16 tensor-core mode -- operands are converted to hi | lo planes here, `out` is merged back to fp32."""
     _require_cuda(A, "A")
     A, Wt = A.contiguous(), Wt.contiguous()
     M, K = A.shape
     N = Wt.shape[0]
     dt = _dtype_code(A.dtype)
+    if x3:
+        assert A.dtype == torch.float32 and Wt.dtype == torch.float32
+        A, Wt, dt = split_planes(A), split_planes(Wt), _lib.NMM_F32X3
     bias_ptr = None
     if bias is not None:
         bias = bias.float().contiguous()
@@ -408,15 +432,18 @@ def linear(A: torch.Tensor, Wt: torch.Tensor, bias: Optional[torch.Tensor] = Non
         B, Cc, F, H, W = x.shape
         out = torch.empty((B, F, Cc, H, W), dtype=x.dtype, device=x.device).permute(0, 2, 1, 3, 4)
         shape = make_shape(cfg, x, out)
+        shape.dtype = dt
         shape_ref = C.byref(shape)
         x_ptr, y_ptr = x.data_ptr(), out.data_ptr()
         out_ptr = None
     else:
         if want_out:
-            out = torch.empty((M, N // 2 if epilogue == _lib.EPI_GEGLU else N), dtype=A.dtype, device=A.device)
+            out = torch.empty((M, (N // 2 if epilogue == _lib.EPI_GEGLU else N) * (2 if x3 else 1)), dtype=A.dtype, device=A.device)
         out_ptr = out.data_ptr() if out is not None else None
     h_ptr = h.data_ptr() if h is not None else None
     with torch.cuda.device(A.device):
         _lib.check(_lib.load().nmm_linear(dt, epilogue, M, N, K, A.data_ptr(), Wt.data_ptr(), bias_ptr, h_ptr, out_ptr, shape_ref,
                                           x_ptr, y_ptr, _stream_ptr(A.device)))
+    if x3 and out is not None and epilogue != _lib.EPI_OUTPUT:
+        out = merge_planes(out)
     return out

@@ -29,13 +29,16 @@ def main():
               temporal_position_encoding=True, temporal_position_encoding_max_len=24, temporal_attention_dim_div=1, zero_initialize=False)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     lines = [f"# B=1, one module call; peaks: bf16 {peak_tf:.0f} TFLOP/s (burst), HBM {peak_bw:.0f} GB/s ({'measured' if peaks else 'fallback'})",
-             f"{'dtype':5s} {'C':>5s} {'F':>3s} {'side':>4s} {'tokens':>7s} {'GFLOP':>8s} {'us':>9s} {'TFLOP/s':>8s} {'%peak':>6s} {'floor MB':>9s} {'floor us':>8s} {'x floor':>7s}"]
-    dtypes = [torch.bfloat16] + ([torch.float32] if a.fp32 else [])
+             f"{'mode':6s} {'C':>5s} {'F':>3s} {'side':>4s} {'tokens':>7s} {'GFLOP':>8s} {'us':>9s} {'TFLOP/s':>8s} {'%peak':>6s} {'floor MB':>9s} {'floor us':>8s} {'x floor':>7s}"]
+    # fp32 activations run in two modes: f32x3 = every Linear as 3 bf16 tcgen05 MMAs per product (the default), f32fma = FMA-pipe GEMM (checker)
+    modes = [("bf16", torch.bfloat16, False)] + ([("f32x3", torch.float32, False), ("f32fma", torch.float32, True)] if a.fp32 else [])
     with torch.no_grad():
-        for dt in dtypes:
+        for label, dt, fma in modes:
             for C in (320, 640, 1280):
                 with torch.device(dev):
                     m = nb.get_motion_module(C, "Vanilla", kw).to(dt).eval()
+                if fma:
+                    m.__dict__["_nmm_fp32_fma"] = True
                 for F in (8, 16):
                     for side in (32, 64):
                         x = torch.randn(1, F, C, side, side, device=dev, dtype=dt).permute(0, 2, 1, 3, 4)
@@ -53,7 +56,7 @@ def main():
                         fl = wl.module_flops(C, N, F)
                         floor = wl.module_min_bytes(C, N, 2 if dt == torch.bfloat16 else 4)
                         floor_us = floor / (peak_bw * 1e3)
-                        lines.append(f"{'bf16' if dt == torch.bfloat16 else 'fp32':5s} {C:5d} {F:3d} {side:4d} {N:7d} {fl / 1e9:8.1f} {us:9.1f} {fl / us / 1e6:8.1f} "
+                        lines.append(f"{label:6s} {C:5d} {F:3d} {side:4d} {N:7d} {fl / 1e9:8.1f} {us:9.1f} {fl / us / 1e6:8.1f} "
                                      f"{100 * fl / us / 1e6 / peak_tf:6.1f} {floor / 1e6:9.1f} {floor_us:8.1f} {us / floor_us:7.1f}")
                         print(lines[-1], flush=True)
                         del x

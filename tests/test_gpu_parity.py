@@ -209,15 +209,42 @@ def test_linear_output_epilogue(C, F, H, W, B, layout, dtype):
 
 
 # ---- whole module ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", ["tc", "fma"])
 @pytest.mark.parametrize("name", helpers.golden_names())
-def test_module_golden_fp32(name):
+def test_module_golden_fp32(name, mode):
+    """fp32 activations, both arithmetic modes: "tc" = every Linear as 3 bf16 tcgen05 MMAs per product (NMM_F32X3, the default when
+    channels % 64 == 0; narrower modules run the FMA path either way), "fma" = the fp32 FMA-pipe GEMM (NMM_F32, the checker)."""
     fx, cfg, params, x = helpers.load_golden(name)
     m = helpers.mirror_module(cfg, params, DEV)
+    if mode == "fma":
+        m.__dict__["_nmm_fp32_fma"] = True
+    n0 = nlib.launch_count()
     with torch.no_grad():
         y = m(x.to(DEV), None, None)
     assert y.shape == x.shape and y.dtype == torch.float32
     assert y.stride() == fx["out_ref_fp32"].permute(0, 2, 1, 3, 4).contiguous().permute(0, 2, 1, 3, 4).stride()
     assert _maxabs(y, fx["out_ref_fp32"]) <= helpers.TOL_FP32
+    assert nlib.launch_count() > n0
+
+
+def test_fp32_tc_and_fma_modes_agree_and_differ_in_kernels():
+    """The two fp32 modes are different kernels (tcgen05 vs FMA) computing the same function: results agree far inside the bar, and
+    the profile shows which GEMM ran."""
+    fx, cfg, params, x = helpers.load_golden("c320_f8_8x8_a2")
+    ys, kernels = [], []
+    for fma in (False, True):
+        m = helpers.mirror_module(cfg, params, DEV)
+        if fma:
+            m.__dict__["_nmm_fp32_fma"] = True
+        with torch.no_grad():
+            m(x.to(DEV), None, None)                       # packs
+            nlib.profile_begin()
+            ys.append(m(x.to(DEV), None, None))
+            prof = nlib.profile_end()
+        kernels.append({k for k, v in prof.items() if v["launches"] > 0})
+    assert "linear_bf16_tcgen05" in kernels[0] and "linear_fp32_fma" not in kernels[0]
+    assert "linear_fp32_fma" in kernels[1] and "linear_bf16_tcgen05" not in kernels[1]
+    assert _maxabs(ys[0], ys[1].double()) <= 5e-5
 
 
 @pytest.mark.parametrize("name", helpers.golden_names())
@@ -497,3 +524,53 @@ def test_linear_residual_wide_pair_tile(M, N, K, copy):
         assert (out.double() - ref).abs().max().item() <= 2 ** -8 * 1.01 * ref.abs().max().item() + 1e-3
     else:
         assert (h.double() - ref).abs().max().item() <= 1e-3
+
+
+# ---- fp32-grade GEMM on the tensor cores (NMM_F32X3: hi.hi + hi.lo + lo.hi bf16 products, fp32 accumulation) -------------------------
+@pytest.mark.parametrize("M,N,K", [(256, 320, 320), (130, 640, 64), (1024, 1280, 1280), (4096, 320, 1280)])
+def test_linear_x3_store_and_residual(M, N, K):
+    A, W, bias = _gemm_inputs(M, N, K, torch.float32)
+    ref = A.double() @ W.double().T + bias.double()
+    Ad, Wd, bd = A.to(DEV), W.to(DEV), bias.to(DEV)
+    # two bf16 terms keep >= 16 mantissa bits of each operand: the error of a K-term dot product of N(0,1) x N(0,1/K) values has
+    # rms ~4e-6 (CPU emulation: 4.4e-6 at K = 1280 and K = 5120) -> max over ~1e6 outputs ~5e-5; the module-level bar is 1e-4
+    tol = 8e-5
+    h = torch.full((M, N), float("nan"), device=DEV)
+    assert ops.linear(Ad, Wd, bd, nlib.EPI_STORE, h=h, want_out=False, x3=True) is None
+    assert _maxabs(h, ref) <= tol
+    g = torch.Generator().manual_seed(11)
+    h0 = torch.randn(M, N, generator=g)
+    h = h0.to(DEV).clone()
+    ops.linear(Ad, Wd, bd, nlib.EPI_RESIDUAL, h=h, want_out=False, x3=True)
+    assert _maxabs(h, ref + h0.double()) <= tol
+    # with `out`: the sum leaves as hi | lo planes (the next GEMM's A operand), h untouched; the two-term split keeps 16 mantissa bits
+    h = h0.to(DEV).clone()
+    out = ops.linear(Ad, Wd, bd, nlib.EPI_RESIDUAL, h=h, want_out=True, x3=True)
+    assert torch.equal(h.cpu(), h0)
+    assert _maxabs(out, ref + h0.double()) <= tol + 2 ** -16 * (ref + h0.double()).abs().max().item()
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 2560, 320), (1024, 5120, 640)])
+def test_linear_x3_geglu(M, N, K):
+    A, W, bias = _gemm_inputs(M, N, K, torch.float32)
+    half = N // 2
+    u = A.double() @ W.double().T + bias.double()
+    ref = u[:, :half] * torch.nn.functional.gelu(u[:, half:])
+    Wi = torch.empty_like(W); Wi[0::4] = W[0:half:2]; Wi[1::4] = W[1:half:2]; Wi[2::4] = W[half::2]; Wi[3::4] = W[half + 1::2]
+    bi = torch.empty_like(bias); bi[0::4] = bias[0:half:2]; bi[1::4] = bias[1:half:2]; bi[2::4] = bias[half::2]; bi[3::4] = bias[half + 1::2]
+    out = ops.linear(A.to(DEV), Wi.to(DEV), bi.to(DEV), nlib.EPI_GEGLU, x3=True)
+    assert out.shape == (M, half)
+    assert _maxabs(out, ref) <= 8e-5 + 2 ** -16 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("C,F,H,W,B,layout", [(320, 8, 8, 8, 1, "bcfhw"), (64, 5, 3, 5, 2, "bfchw"), (640, 16, 4, 4, 1, "bfchw")])
+def test_linear_x3_output_epilogue(C, F, H, W, B, layout):
+    cfg = mo.MotionConfig(C)
+    N = B * F * H * W
+    A, Wt, bias = _gemm_inputs(N, C, C, torch.float32)
+    x = mo.make_input((B, C, F, H, W), 4, layout=layout)
+    y_tok = A.double() @ Wt.double().T + bias.double()
+    ref = y_tok.reshape(B, F, H * W, C).permute(0, 3, 1, 2).reshape(B, C, F, H, W) + x.double()
+    y = ops.linear(A.to(DEV), Wt.to(DEV), bias.to(DEV), nlib.EPI_OUTPUT, cfg=_cfg(cfg), x=x.to(DEV), x3=True)
+    assert y.dtype == torch.float32 and y.shape == x.shape and y.permute(0, 2, 1, 3, 4).is_contiguous()
+    assert _maxabs(y, ref) <= 8e-5
