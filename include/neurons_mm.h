@@ -200,6 +200,20 @@ NMM_API int nmm_groupnorm_linear(const nmm_shape *s, const void *x, const float 
 NMM_API int nmm_groupnorm_workspace_bytes(const nmm_shape *s, size_t *bytes);
 NMM_API int nmm_inflated_groupnorm(const nmm_shape *s, const void *x, void *y, const float *gn_w, const float *gn_b, int32_t silu,
                            void *workspace, size_t workspace_bytes, void *stream);
+/* GroupNorm statistics carried between neighbours instead of being recomputed (call order unet_blocks.py:407-411:
+ * resnet -> attn -> motion_module -> next resnet, whose norm1 -- resnet.py:182-198 -- normalises the motion module's output).
+ * "sums" = fp64 [B*F*32][2]: (sum, sum of squares) of a [b, c, f, h, w] tensor per (b, f, GroupNorm group), 16-byte aligned.
+ *   nmm_forward_stats             nmm_forward with x_sums (optional in: statistics of x -- the module's own GroupNorm skips its pass
+ *                                 over x) and y_sums (optional out: statistics of y as stored, emitted from the last kernel's epilogue
+ *                                 in bf16 mode -- proj_out / the fused module's y store -- and reduced without atomics, in a fixed order;
+ *                                 other modes run one statistics pass over y).  Either pointer may be NULL.
+ *   nmm_inflated_groupnorm_sums   nmm_inflated_groupnorm with the statistics of x handed over: one pass over x instead of two.
+ *   nmm_groupnorm_sums            the statistics of any tensor in this format (workspace: nmm_groupnorm_workspace_bytes). */
+NMM_API int nmm_forward_stats(const nmm_shape *s, const void *x, void *y, const void *packed, size_t packed_bytes, void *workspace,
+                              size_t workspace_bytes, const double *x_sums, double *y_sums, void *stream);
+NMM_API int nmm_inflated_groupnorm_sums(const nmm_shape *s, const void *x, void *y, const float *gn_w, const float *gn_b, int32_t silu,
+                                        const double *x_sums, void *workspace, size_t workspace_bytes, void *stream);
+NMM_API int nmm_groupnorm_sums(const nmm_shape *s, const void *x, double *sums, void *workspace, size_t workspace_bytes, void *stream);
 /* Denoise-loop glue: classifier-free guidance + one deterministic DDIM update in a single elementwise kernel,
  * pipeline_neuroclips.py:478-483 + DDIMScheduler.step (eta = 0, epsilon prediction, clip_sample = false):
  *   eps = eps_uncond + guidance * (eps_cond - eps_uncond)            (eps_cond == NULL: eps = eps_uncond, guidance ignored)

@@ -5,13 +5,14 @@ Public surface (mirrors /root/reference/animatediff/models/motion_module.py):
     patch(model), invalidate(model)                rebind forward on reference modules already inside a UNet / ControlNet
     torch.ops.neurons_mm.forward                   the custom op (CUDA dispatch key only)
     InflatedGroupNorm, patch_group_norms           the per-frame GroupNorm of ResnetBlock3D either side of the module (resnet.py:21-29)
+    patch(model, carry_stats=True)                 ... whose statistics then come from the motion module's last kernel (attach_sums / carried_sums)
 The arithmetic lives in libneurons_mm.so (C ABI: include/neurons_mm.h), built by `python -m neurons_b200.build`.
 """
 from .lib import NmmError, launch_count, load as load_library          # noqa: F401
 from .ops import ModuleConfig                                           # noqa: F401
-from .motion_module import (VanillaTemporalModule, config_of, get_motion_module, invalidate, motion_forward, patch,   # noqa: F401
-                            zero_module)
+from .motion_module import (VanillaTemporalModule, attach_sums, carried_sums, config_of, get_motion_module, invalidate,   # noqa: F401
+                            motion_forward, patch, zero_module)
 from .resnet_norm import InflatedGroupNorm, patch_group_norms            # noqa: F401
 
 __all__ = ["VanillaTemporalModule", "get_motion_module", "patch", "invalidate", "motion_forward", "zero_module", "config_of",
-           "ModuleConfig", "NmmError", "launch_count", "load_library", "InflatedGroupNorm", "patch_group_norms"]
+           "ModuleConfig", "NmmError", "launch_count", "load_library", "InflatedGroupNorm", "patch_group_norms", "attach_sums", "carried_sums"]

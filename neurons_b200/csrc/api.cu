@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "epilogue.cuh"
 
 namespace nmm {
 
@@ -165,7 +166,7 @@ static int chunk_positions(const Geo &g) {
     return pc >= g.P ? g.P : (int)pc;
 }
 
-struct WorkLayout { size_t gn_partial, tok, tok2, h, big, ctx, ln_part, total; };
+struct WorkLayout { size_t gn_partial, tok, tok2, h, big, ctx, ln_part, stat_part, total; };
 static WorkLayout work_layout(const Geo &g) {
     WorkLayout w;
     size_t off = 0;
@@ -180,6 +181,8 @@ static WorkLayout work_layout(const Geo &g) {
     // ([n][2 * n_tiles][2] fp32, n_tiles <= C / 32)
     w.tok2 = take(g.ln_fold ? NC * es : 0);
     w.ln_part = take(g.ln_fold ? NC / 32 * 2 * 2 * 4 : 0);
+    // N1: fp32 (sum, sum of squares) partials of y from the last kernel: [N / 32][C] (GEMM epilogue) or [tiles][F][32] (fused module, smaller)
+    w.stat_part = take(((size_t)g.N + 31) / 32 * g.C * sizeof(float2));
     w.total = off;
     return w;
 }
@@ -615,11 +618,18 @@ int nmm_pack_params(const nmm_shape *s, const nmm_params *src, void *packed, siz
 }
 
 static int forward_impl(const nmm_shape *s, const void *x, void *y, const void *packed, size_t packed_bytes, void *workspace, size_t workspace_bytes,
-                        void *stream, float *stage_dump, int stage_id);
+                        void *stream, float *stage_dump, int stage_id, const double *x_sums = nullptr, double *y_sums = nullptr);
 
 int nmm_forward(const nmm_shape *s, const void *x, void *y, const void *packed, size_t packed_bytes, void *workspace, size_t workspace_bytes,
                 void *stream) {
     return forward_impl(s, x, y, packed, packed_bytes, workspace, workspace_bytes, stream, nullptr, -1);
+}
+
+int nmm_forward_stats(const nmm_shape *s, const void *x, void *y, const void *packed, size_t packed_bytes, void *workspace, size_t workspace_bytes,
+                      const double *x_sums, double *y_sums, void *stream) {
+    if (x_sums != nullptr && !aligned(x_sums, 16)) return fail(NMM_ERR_BAD_ARG, "x_sums must be 16-byte aligned");
+    if (y_sums != nullptr && !aligned(y_sums, 16)) return fail(NMM_ERR_BAD_ARG, "y_sums must be 16-byte aligned");
+    return forward_impl(s, x, y, packed, packed_bytes, workspace, workspace_bytes, stream, nullptr, -1, x_sums, y_sums);
 }
 
 int nmm_forward_stage(const nmm_shape *s, const void *x, void *y, const void *packed, size_t packed_bytes, void *workspace, size_t workspace_bytes,
@@ -649,7 +659,7 @@ int nmm_packed_header(const nmm_shape *s, void *out, size_t out_bytes) {
 }
 
 static int forward_impl(const nmm_shape *s, const void *x, void *y, const void *packed, size_t packed_bytes, void *workspace, size_t workspace_bytes,
-                        void *stream, float *stage_dump, int stage_id) {
+                        void *stream, float *stage_dump, int stage_id, const double *x_sums, double *y_sums) {
     int rc = validate(s);
     if (rc != NMM_OK) return rc;
     if (!x || !y || !packed || !workspace) return fail(NMM_ERR_BAD_ARG, "NULL argument");
@@ -672,7 +682,21 @@ static int forward_impl(const nmm_shape *s, const void *x, void *y, const void *
     auto F32 = [&](size_t off) { return (const float *)(pk + off); };
 
     // GroupNorm statistics over the whole tensor                                       motion_module.py:142
-    if ((rc = launch_gn_stats(g, s, x, gn_partial, st)) != NMM_OK) return rc;
+    // (N1: a producer that already knows the per-(b, f, group) sums of x hands them over and the pass over x is skipped)
+    const double *gn_stats = gn_partial;
+    int gn_nsplit = gn_splits_of(g);
+    if (x_sums != nullptr) { gn_stats = x_sums; gn_nsplit = 1; }
+    else if ((rc = launch_gn_stats(g, s, x, gn_partial, st)) != NMM_OK) return rc;
+    float2 *stat_part = (float2 *)(ws + w.stat_part);
+    // statistics of y for the next GroupNorm when the last kernel cannot emit them (fp32 modes, ragged / unaligned y, chunked runs):
+    // one more pass over y with the statistics kernel, then the same [B*F*32][2] format
+    auto y_sums_by_pass = [&]() -> int {
+        nmm_shape sy = *s;
+        sy.x_stride_b = s->y_stride_b; sy.x_stride_c = s->y_stride_c; sy.x_stride_f = s->y_stride_f;
+        int r = launch_gn_stats(g, &sy, y, gn_partial, st);
+        if (r != NMM_OK) return r;
+        return launch_gn_partial_to_sums(g, gn_partial, y_sums, st);
+    };
 
     // C = 320, 8 heads, 8 / 16 frames, bf16: everything else of the call is ONE kernel (fused_module.cu)
     if (fused_module_eligible(g, s, x)) {
@@ -681,7 +705,7 @@ static int forward_impl(const nmm_shape *s, const void *x, void *y, const void *
         fa.x = x; fa.y = y;
         fa.xsb = s->x_stride_b; fa.xsc = s->x_stride_c; fa.xsf = s->x_stride_f; fa.ysb = s->y_stride_b; fa.ysc = s->y_stride_c; fa.ysf = s->y_stride_f;
         fa.B = g.B; fa.F = g.F; fa.P = g.P; fa.A = g.A; fa.pos_enc = g.pos_enc ? 1 : 0;
-        fa.gn_partial = gn_partial; fa.gn_splits = gn_splits_of(g); fa.gn_count = (double)(g.C / NMM_GN_GROUPS) * g.P; fa.gn_eps = s->eps_gn;
+        fa.gn_partial = gn_stats; fa.gn_splits = gn_nsplit; fa.gn_count = (double)(g.C / NMM_GN_GROUPS) * g.P; fa.gn_eps = s->eps_gn;
         const LayerOff &lo = L.layer[0];
         fa.w_in_g = pk + L.w_in_g; fa.w_out = pk + L.w_out; fa.w1 = pk + lo.w1; fa.w2 = pk + lo.w2;
         for (int i = 0; i < g.A; i++) {
@@ -692,7 +716,9 @@ static int forward_impl(const nmm_shape *s, const void *x, void *y, const void *
         fa.vec_ff = F32(L.vec_ff); fa.vec_fin = F32(L.vec_fin); fa.b1 = F32(lo.b1);
         fa.ln_eps = s->eps_ln;
         fa.stage_dump = stage_dump; fa.stage_id = stage_id;
-        return launch_fused_module(fa, st);
+        fa.y_part = y_sums != nullptr ? stat_part : nullptr;
+        if ((rc = launch_fused_module(fa, st)) != NMM_OK) return rc;
+        return y_sums != nullptr ? launch_y_sums_tiles(stat_part, y_sums, g.B, g.F, g.P / (128 / g.F), st) : NMM_OK;
     }
 
     const int pc = chunk_positions(g);
@@ -710,7 +736,7 @@ static int forward_impl(const nmm_shape *s, const void *x, void *y, const void *
         // normalise + re-layout to token-major                                          :142-144
         // bf16, whole image, 64-position aligned: proj_in TMA-loads x itself and normalises the tile in shared memory (no token buffer)
         const bool gn_fused = g.dtype == NMM_BF16 && !g.ln_fold && pn == g.P && linear_tc_gn_fusable(gc.N, pn, x, s->x_stride_b, s->x_stride_c, s->x_stride_f);
-        if (!gn_fused && (rc = launch_gn_tokens(gc, &sc, g, xc, gn_partial, F32(L.gn_w), F32(L.gn_b), tok, st)) != NMM_OK) return rc;
+        if (!gn_fused && (rc = launch_gn_tokens(gc, &sc, g, xc, gn_stats, F32(L.gn_w), F32(L.gn_b), tok, st, x_sums ? 1 : 0)) != NMM_OK) return rc;
 
         LinearArgs a;
         memset(&a, 0, sizeof(a));
@@ -741,7 +767,7 @@ static int forward_impl(const nmm_shape *s, const void *x, void *y, const void *
         a.epilogue = NMM_EPI_STORE; a.N = g.C; a.K = g.C; a.A = tok; a.W = pk + L.w_in; a.bias = F32(L.b_in); a.h = h; a.out = nullptr;
         producer(a);
         if (gn_fused) {
-            a.A = nullptr; a.gn_x = x; a.gn_partial = gn_partial; a.gn_splits = gn_splits_of(g);
+            a.A = nullptr; a.gn_x = x; a.gn_partial = gn_stats; a.gn_splits = gn_nsplit;
             a.gn_count = (double)(g.C / NMM_GN_GROUPS) * g.P; a.gn_eps = s->eps_gn; a.gn_w = F32(L.gn_w); a.gn_b = F32(L.gn_b); a.gn_B = g.B;
         }
         if ((rc = linear(g, a, st)) != NMM_OK) return rc;
@@ -788,9 +814,14 @@ static int forward_impl(const nmm_shape *s, const void *x, void *y, const void *
         // y = proj_out(h) back in NCHW + x                                              :152-156
         a.epilogue = NMM_EPI_OUTPUT; a.N = g.C; a.K = g.C; a.A = (g.dtype != NMM_F32) ? (const void *)tok : (const void *)h;
         a.W = pk + L.w_out; a.bias = F32(L.b_out); a.h = nullptr; a.out = nullptr; a.x = xc; a.y = yc;
+        // N1: proj_out's epilogue also emits the per-(32-row block, channel) sums of y (bf16 vector path, whole-image run)
+        const bool emit = y_sums != nullptr && g.dtype == NMM_BF16 && pn == g.P && output_vec_ok(a);
+        a.y_part = emit ? stat_part : nullptr;
         if ((rc = linear(g, a, st)) != NMM_OK) return rc;
+        a.y_part = nullptr;
+        if (emit) return launch_y_sums_channels(stat_part, y_sums, g.B * g.F, g.C, g.P, st);
     }
-    return NMM_OK;
+    return y_sums != nullptr ? y_sums_by_pass() : NMM_OK;
 }
 
 // ---- per-stage entry points ------------------------------------------------------------------------------
@@ -855,8 +886,8 @@ int nmm_groupnorm_workspace_bytes(const nmm_shape *s, size_t *bytes) {
     return NMM_OK;
 }
 
-int nmm_inflated_groupnorm(const nmm_shape *s, const void *x, void *y, const float *gn_w, const float *gn_b, int32_t silu, void *workspace,
-                           size_t workspace_bytes, void *stream) {
+static int inflated_groupnorm_impl(const nmm_shape *s, const void *x, void *y, const float *gn_w, const float *gn_b, int32_t silu, const double *x_sums,
+                                   void *workspace, size_t workspace_bytes, void *stream) {
     int rc = validate(s);
     if (rc != NMM_OK) return rc;
     if (!x || !y || !gn_w || !gn_b || !workspace) return fail(NMM_ERR_BAD_ARG, "NULL argument");
@@ -868,9 +899,36 @@ int nmm_inflated_groupnorm(const nmm_shape *s, const void *x, void *y, const flo
     cudaStream_t st = (cudaStream_t)stream;
     double *partial = (double *)workspace;
     float *mean = (float *)((char *)workspace + stats_off), *rstd = mean + (size_t)g.B * g.F * NMM_GN_GROUPS;
-    if ((rc = launch_gn_stats(g, s, x, partial, st)) != NMM_OK) return rc;
-    if ((rc = launch_gn_finalize(g, s, partial, mean, rstd, st)) != NMM_OK) return rc;
+    if (x_sums != nullptr) {           // statistics handed over by the producer of x: only the apply pass touches the tensor
+        if ((rc = launch_gn_finalize(g, s, x_sums, mean, rstd, st, 1)) != NMM_OK) return rc;
+    } else {
+        if ((rc = launch_gn_stats(g, s, x, partial, st)) != NMM_OK) return rc;
+        if ((rc = launch_gn_finalize(g, s, partial, mean, rstd, st)) != NMM_OK) return rc;
+    }
     return launch_gn_apply(g, s, x, y, mean, rstd, gn_w, gn_b, silu ? 1 : 0, st);
+}
+
+int nmm_inflated_groupnorm(const nmm_shape *s, const void *x, void *y, const float *gn_w, const float *gn_b, int32_t silu, void *workspace,
+                           size_t workspace_bytes, void *stream) {
+    return inflated_groupnorm_impl(s, x, y, gn_w, gn_b, silu, nullptr, workspace, workspace_bytes, stream);
+}
+
+int nmm_inflated_groupnorm_sums(const nmm_shape *s, const void *x, void *y, const float *gn_w, const float *gn_b, int32_t silu, const double *x_sums,
+                                void *workspace, size_t workspace_bytes, void *stream) {
+    if (!x_sums) return fail(NMM_ERR_BAD_ARG, "x_sums is NULL");
+    return inflated_groupnorm_impl(s, x, y, gn_w, gn_b, silu, x_sums, workspace, workspace_bytes, stream);
+}
+
+int nmm_groupnorm_sums(const nmm_shape *s, const void *x, double *sums, void *workspace, size_t workspace_bytes, void *stream) {
+    int rc = validate(s);
+    if (rc != NMM_OK) return rc;
+    if (!x || !sums || !workspace) return fail(NMM_ERR_BAD_ARG, "NULL argument");
+    if ((rc = device_check()) != NMM_OK) return rc;
+    const Geo g = geo_of(s);
+    if (workspace_bytes < gn_partial_bytes(g)) return fail(NMM_ERR_WORKSPACE, "workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = launch_gn_stats(g, s, x, (double *)workspace, st)) != NMM_OK) return rc;
+    return launch_gn_partial_to_sums(g, (const double *)workspace, sums, st);
 }
 
 int nmm_cfg_ddim_step(int32_t dtype, int64_t n, void *latents, const void *eps_uncond, const void *eps_cond, float guidance, double alpha_t,

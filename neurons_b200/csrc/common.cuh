@@ -228,9 +228,14 @@ __device__ __forceinline__ void gn_finalize_one(const double *__restrict__ parti
     rstd = (float)(1.0 / sqrt(var + (double)eps));
 }
 int launch_gn_stats(const Geo &g, const nmm_shape *s, const void *x, double *partial, cudaStream_t st);
-int launch_gn_finalize(const Geo &g, const nmm_shape *s, const double *partial, float *mean, float *rstd, cudaStream_t st);
+// splits_override > 0: `partial` holds that many (sum, sum of squares) pairs per (b, f, group) instead of gn_splits_of(g) -- 1 for
+// caller-provided "sums" (precomputed statistics)
+int launch_gn_finalize(const Geo &g, const nmm_shape *s, const double *partial, float *mean, float *rstd, cudaStream_t st, int splits_override = 0);
+int launch_y_sums_tiles(const float2 *part, double *sums, int B, int F, int tiles_per_b, cudaStream_t st);
+int launch_y_sums_channels(const float2 *part, double *sums, int BF, int C, int P, cudaStream_t st);
+int launch_gn_partial_to_sums(const Geo &g, const double *partial, double *sums, cudaStream_t st);
 int launch_gn_tokens(const Geo &g, const nmm_shape *s, const Geo &full, const void *x, const double *partial, const float *gn_w,
-                     const float *gn_b, void *tokens, cudaStream_t st);      // NMM_F32X3: tokens = bf16 [N, 2C] hi | lo planes
+                     const float *gn_b, void *tokens, cudaStream_t st, int splits_override = 0);      // NMM_F32X3: tokens = bf16 [N, 2C] hi | lo planes
 // LayerNorm (+PE)
 int launch_layernorm_pe(const Geo &g, const nmm_shape *s, const float *h, const float *w, const float *b,
                         const float *pe, void *out, cudaStream_t st);
@@ -259,6 +264,7 @@ struct LinearArgs {
     const void *x; void *y;
     int F, P;
     int64_t xsb, xsc, xsf, ysb, ysc, ysf;
+    float2 *y_part;          // OUTPUT epilogue (bf16 vector path), or null: [M / 32][N] (sum, sum of squares) of y as stored, per 32-row block and channel
     // GroupNorm-fused A operand (bf16 tensor-core path, STORE epilogue: proj_in).  A is NULL; the A tiles are TMA-loaded straight
     // from x [b, c, f, p] (channel rows of positions = an M-major operand), normalised in shared memory
     // (x * rstd*gamma[c] + beta[c] - mean*rstd*gamma[c], rounded to bf16 exactly like the stand-alone gn_tokens kernel) and fed to
@@ -319,6 +325,7 @@ struct FusedArgs {
     const float *b1;
     float ln_eps;
     float *stage_dump; int stage_id;                         // tests: snapshot of the residual stream after stage stage_id (or null)
+    float2 *y_part;                                          // or null: per (tile, frame, group) sums of y (N1: statistics for the next GroupNorm)
 };
 bool fused_module_weights(const Geo &g);
 bool fused_module_eligible(const Geo &g, const nmm_shape *s, const void *x);

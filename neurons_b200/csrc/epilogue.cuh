@@ -20,6 +20,7 @@ struct EpiParams {
     void *y;
     int F, P;
     int64_t xsb, xsc, xsf, ysb, ysc, ysf;
+    float2 *y_part;    // OUTPUT, nchw_vec path only: statistics of y for the next GroupNorm (LinearArgs::y_part)
     int nchw_vec;      // OUTPUT: P % 32 == 0 and x / y rows 16-byte aligned -> 8-position (16-byte) vector path
     int no_h_store;
     float *ln_part_out;
@@ -29,17 +30,22 @@ struct EpiParams {
     float ln_eps;
 };
 
+// OUTPUT epilogue: can the bf16 16-byte vector path run (and with it the y-statistics emission)?
+inline bool output_vec_ok(const LinearArgs &a) {
+    return a.epilogue == NMM_EPI_OUTPUT && !a.x3 && a.P > 0 && a.P % 32 == 0 && aligned(a.x, 16) && aligned(a.y, 16) && a.xsb % 8 == 0 &&
+           a.xsc % 8 == 0 && a.xsf % 8 == 0 && a.ysb % 8 == 0 && a.ysc % 8 == 0 && a.ysf % 8 == 0;
+}
+
 inline EpiParams epi_params_of(const LinearArgs &a) {
     EpiParams e;
     e.M = a.M; e.N = a.N; e.bias = a.bias; e.h = a.h; e.out = a.out; e.x = a.x; e.y = a.y; e.F = a.F; e.P = a.P;
     e.xsb = a.xsb; e.xsc = a.xsc; e.xsf = a.xsf; e.ysb = a.ysb; e.ysc = a.ysc; e.ysf = a.ysf;
     e.no_h_store = a.no_h_store;
+    e.y_part = a.y_part;
     e.ln_part_out = a.ln_part_out; e.ln_part_in = a.ln_part_in; e.ln_nparts = a.ln_nparts; e.ln_K = a.K;
     e.ln_g = a.ln_g; e.ln_c = a.ln_c; e.ln_pew = a.ln_pew; e.ln_eps = a.ln_eps;
-    e.nchw_vec = 0;
-    if (a.epilogue == NMM_EPI_OUTPUT && !a.x3 && a.P > 0 && a.P % 32 == 0 && aligned(a.x, 16) && aligned(a.y, 16) && a.xsb % 8 == 0 &&
-        a.xsc % 8 == 0 && a.xsf % 8 == 0 && a.ysb % 8 == 0 && a.ysc % 8 == 0 && a.ysf % 8 == 0)
-        e.nchw_vec = 1;
+    e.nchw_vec = output_vec_ok(a) ? 1 : 0;
+    if (!e.nchw_vec) e.y_part = nullptr;
     return e;
 }
 

@@ -38,6 +38,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <type_traits>
 #include <vector>
 
 #include "attention_core.cuh"
@@ -98,6 +99,7 @@ struct FmParams {
     int pos_enc, y_vec16;
     float ln_eps, scale_log2e;
     float *stage_dump; int stage_id;              // tests: fp32 [N, 320] snapshot of the residual stream after stage `stage_id`
+    float2 *y_part;                               // or null: [tile][F][32 groups] (sum, sum of squares) of the tile's y values as stored
     unsigned long long *trace;                    // -DNMM_TRACE builds: clock64 stamps of CTA 0's first tile (development)
 };
 
@@ -887,25 +889,59 @@ __global__ void __launch_bounds__(FM_THREADS, 1) fused_module_kernel(const __gri
                 fm_bar_epi();
                 wait_h();                                            // H = h . W_out^T
                 FM_ETRACE(67);
+                // (EMIT: also accumulate this row's per-GroupNorm-group sums of the ROUNDED outputs -- the next InflatedGroupNorm's statistics)
+                auto y_rows = [&](auto EMIT) {
+                    constexpr bool kEmit = decltype(EMIT)::value;
+                    float gs[kEmit ? 8 : 1], gq[kEmit ? 8 : 1];           // this thread's 80 channels = 8 groups of 10
+                    if constexpr (kEmit) {
 #pragma unroll
-                for (int k = 0; k < 5; k++) {
-                    const int c0 = 80 * sub + 16 * k;
-                    uint32_t r[16];
-                    ptx::tmem_ld16(t_lane + FM_TM_H + c0, r);
-                    float4 b4[4];
+                        for (int g8 = 0; g8 < 8; g8++) { gs[g8] = 0.f; gq[g8] = 0.f; }
+                    }
 #pragma unroll
-                    for (int j4 = 0; j4 < 4; j4++) b4[j4] = lds4(sb + FM_SCR + (uint32_t)(c0 + 4 * j4) * 4);
-                    uint32_t xw[8];
+                    for (int k = 0; k < 5; k++) {
+                        const int c0 = 80 * sub + 16 * k;
+                        uint32_t r[16];
+                        ptx::tmem_ld16(t_lane + FM_TM_H + c0, r);
+                        float4 b4[4];
 #pragma unroll
-                    for (int j = 0; j < 8; j++) xw[j] = lds32(T + (uint32_t)((c0 / 2 + j) * 128 + m) * 4);
-                    ptx::tmem_ld_wait();
-                    const float bb[16] = {b4[0].x, b4[0].y, b4[0].z, b4[0].w, b4[1].x, b4[1].y, b4[1].z, b4[1].w,
-                                          b4[2].x, b4[2].y, b4[2].z, b4[2].w, b4[3].x, b4[3].y, b4[3].z, b4[3].w};
+                        for (int j4 = 0; j4 < 4; j4++) b4[j4] = lds4(sb + FM_SCR + (uint32_t)(c0 + 4 * j4) * 4);
+                        uint32_t xw[8];
 #pragma unroll
-                    for (int j = 0; j < 8; j++)
-                        fm_sts32(T + (uint32_t)((c0 / 2 + j) * 128 + m) * 4, pack_bf16x2(__uint_as_float(r[2 * j]) + bb[2 * j] + bf16_lo(xw[j]),
-                                                                                             __uint_as_float(r[2 * j + 1]) + bb[2 * j + 1] + bf16_hi(xw[j])));
-                }
+                        for (int j = 0; j < 8; j++) xw[j] = lds32(T + (uint32_t)((c0 / 2 + j) * 128 + m) * 4);
+                        ptx::tmem_ld_wait();
+                        const float bb[16] = {b4[0].x, b4[0].y, b4[0].z, b4[0].w, b4[1].x, b4[1].y, b4[1].z, b4[1].w,
+                                              b4[2].x, b4[2].y, b4[2].z, b4[2].w, b4[3].x, b4[3].y, b4[3].z, b4[3].w};
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            const uint32_t yw = pack_bf16x2(__uint_as_float(r[2 * j]) + bb[2 * j] + bf16_lo(xw[j]),
+                                                            __uint_as_float(r[2 * j + 1]) + bb[2 * j + 1] + bf16_hi(xw[j]));
+                            fm_sts32(T + (uint32_t)((c0 / 2 + j) * 128 + m) * 4, yw);
+                            if constexpr (kEmit) {
+                                const int gl = (16 * k + 2 * j) / 10;      // compile-time: both channels of the pair lie in one group
+                                const float y0 = bf16_lo(yw), y1 = bf16_hi(yw);
+                                gs[gl] += y0 + y1;
+                                gq[gl] = fmaf(y0, y0, fmaf(y1, y1, gq[gl]));
+                            }
+                        }
+                    }
+                    if constexpr (kEmit) {
+                        // the PPT rows of one frame are PPT consecutive lanes: butterfly over them, the frame's first lane writes
+#pragma unroll
+                        for (int g8 = 0; g8 < 8; g8++) {
+#pragma unroll
+                            for (int o = PPT / 2; o > 0; o >>= 1) {
+                                gs[g8] += __shfl_xor_sync(0xffffffffu, gs[g8], o);
+                                gq[g8] += __shfl_xor_sync(0xffffffffu, gq[g8], o);
+                            }
+                        }
+                        if (pl_m == 0) {
+                            float2 *dst = p.y_part + ((int64_t)t * F + f_m) * NMM_GN_GROUPS + 8 * sub;
+#pragma unroll
+                            for (int g8 = 0; g8 < 8; g8++) dst[g8] = make_float2(gs[g8], gq[g8]);
+                        }
+                    }
+                };
+                if (p.y_part != nullptr) y_rows(std::true_type{}); else y_rows(std::false_type{});
                 ptx::tc_fence_before();      // this tile's TMEM reads are ordered before the next tile's a1_ready arrive -> proj_in may overwrite H
                 fm_bar_epi();
                 bf16 *yb = p.y + (int64_t)b * p.ysb + p0;
@@ -1072,6 +1108,7 @@ int launch_fused_module(const FusedArgs &a, cudaStream_t st) {
     p.y_vec16 = aligned(a.y, 16) && a.ysb % 8 == 0 && a.ysc % 8 == 0 && a.ysf % 8 == 0;
     p.ln_eps = a.ln_eps; p.scale_log2e = (1.0f / sqrtf((float)FM_DH)) * 1.4426950408889634f;
     p.stage_dump = a.stage_dump; p.stage_id = a.stage_id;
+    p.y_part = a.y_part;
 #ifdef NMM_TRACE
     if (!g_fm_trace) { cudaMalloc(&g_fm_trace, FM_TRACE_SLOTS * 8); cudaMemset(g_fm_trace, 0, FM_TRACE_SLOTS * 8); }
     p.trace = g_fm_trace;

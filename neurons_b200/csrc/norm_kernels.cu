@@ -142,9 +142,9 @@ __global__ void gn_finalize_kernel(const double *__restrict__ partial, float *__
     mean[i] = m; rstd[i] = r;
 }
 
-int launch_gn_finalize(const Geo &g, const nmm_shape *s, const double *partial, float *mean, float *rstd, cudaStream_t st) {
+int launch_gn_finalize(const Geo &g, const nmm_shape *s, const double *partial, float *mean, float *rstd, cudaStream_t st, int splits_override) {
     const int n = g.B * g.F * NMM_GN_GROUPS;
-    launch_pdl(gn_finalize_kernel, (n + 127) / 128, 128, 0, st, partial, mean, rstd, n, gn_splits(g),
+    launch_pdl(gn_finalize_kernel, (n + 127) / 128, 128, 0, st, partial, mean, rstd, n, splits_override > 0 ? splits_override : gn_splits(g),
                                                          (double)(g.C / NMM_GN_GROUPS) * g.P, s->eps_gn);
     NMM_LAUNCHED("gn_finalize_kernel");
     return NMM_OK;
@@ -240,11 +240,82 @@ __global__ void __launch_bounds__(256) gn_tokens_bf16_kernel(const bf16 *__restr
     reinterpret_cast<uint4 *>(dst)[1] = make_uint4(o[4], o[5], o[6], o[7]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// statistics of the module OUTPUT for the next InflatedGroupNorm (ResnetBlock3D.norm1, resnet.py:182-198;
+// call order unet_blocks.py:407-411).  The last kernel of the module emits fp32 partial (sum, sum of squares) of y as stored;
+// these kernels reduce them -- one warp per (b, f, group), fixed order, double accumulation, no atomics -- to the
+// [B*F*32][2] double "sums" format every GroupNorm consumer of the library accepts as precomputed statistics.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// part[tile][F][32] (fused module kernel; tile = b * tiles_per_b + tt)
+__global__ void __launch_bounds__(256) y_sums_from_tiles_kernel(const float2 *__restrict__ part, double *__restrict__ sums, int F, int tiles_per_b, int n) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int i = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (i >= n) return;                              // warp-uniform
+    const int g = i % NMM_GN_GROUPS, bf = i / NMM_GN_GROUPS, b = bf / F, f = bf - b * F;
+    double a = 0, c2 = 0;
+    for (int tt = lane; tt < tiles_per_b; tt += 32) {
+        const float2 v = __ldg(part + ((int64_t)(b * tiles_per_b + tt) * F + f) * NMM_GN_GROUPS + g);
+        a += (double)v.x; c2 += (double)v.y;
+    }
+    a = warp_sum_d(a); c2 = warp_sum_d(c2);
+    if (lane == 0) { sums[2 * (int64_t)i] = a; sums[2 * (int64_t)i + 1] = c2; }
+}
+// part[M / 32][C] (tensor-core GEMM, OUTPUT epilogue): image bf owns the row blocks [bf * P / 32, (bf + 1) * P / 32)
+__global__ void __launch_bounds__(256) y_sums_from_channels_kernel(const float2 *__restrict__ part, double *__restrict__ sums, int C, int p32, int n) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int i = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const int cpg = C / NMM_GN_GROUPS, g = i % NMM_GN_GROUPS, bf = i / NMM_GN_GROUPS;
+    double a = 0, c2 = 0;
+    for (int it = lane; it < p32 * cpg; it += 32) {
+        const int rb = it / cpg, c = g * cpg + (it - rb * cpg);
+        const float2 v = __ldg(part + ((int64_t)bf * p32 + rb) * C + c);
+        a += (double)v.x; c2 += (double)v.y;
+    }
+    a = warp_sum_d(a); c2 = warp_sum_d(c2);
+    if (lane == 0) { sums[2 * (int64_t)i] = a; sums[2 * (int64_t)i + 1] = c2; }
+}
+// partial[n][splits][2] (gn_stats) -> sums[n][2]
+__global__ void gn_partial_to_sums_kernel(const double *__restrict__ partial, double *__restrict__ sums, int n, int splits) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double a = 0, c2 = 0;
+    for (int k = 0; k < splits; k++) { a += partial[((int64_t)i * splits + k) * 2]; c2 += partial[((int64_t)i * splits + k) * 2 + 1]; }
+    sums[2 * (int64_t)i] = a; sums[2 * (int64_t)i + 1] = c2;
+}
+int launch_y_sums_tiles(const float2 *part, double *sums, int B, int F, int tiles_per_b, cudaStream_t st) {
+    const int n = B * F * NMM_GN_GROUPS;
+    launch_pdl(y_sums_from_tiles_kernel, (unsigned)ceil_div((int64_t)n * 32, 256), 256, 0, st, part, sums, F, tiles_per_b, n);
+    NMM_LAUNCHED("y_sums_from_tiles_kernel");
+    return NMM_OK;
+}
+int launch_y_sums_channels(const float2 *part, double *sums, int BF, int C, int P, cudaStream_t st) {
+    const int n = BF * NMM_GN_GROUPS;
+    launch_pdl(y_sums_from_channels_kernel, (unsigned)ceil_div((int64_t)n * 32, 256), 256, 0, st, part, sums, C, P / 32, n);
+    NMM_LAUNCHED("y_sums_from_channels_kernel");
+    return NMM_OK;
+}
+int launch_gn_partial_to_sums(const Geo &g, const double *partial, double *sums, cudaStream_t st) {
+    const int n = g.B * g.F * NMM_GN_GROUPS;
+    launch_pdl(gn_partial_to_sums_kernel, (unsigned)ceil_div(n, 128), 128, 0, st, partial, sums, n, gn_splits(g));
+    NMM_LAUNCHED("gn_partial_to_sums_kernel");
+    return NMM_OK;
+}
+
 // `g` / `s` describe the positions being converted (possibly a chunk of the image: x already offset to its first position);
 // `full` is the geometry the statistics were computed over (splits and element count of a whole group).
 int launch_gn_tokens(const Geo &g, const nmm_shape *s, const Geo &full, const void *x, const double *partial, const float *gn_w,
-                     const float *gn_b, void *tokens, cudaStream_t st) {
-    const int splits = gn_splits(full);
+                     const float *gn_b, void *tokens, cudaStream_t st, int splits_override) {
+    const int splits = splits_override > 0 ? splits_override : gn_splits(full);
     const double count = (double)(full.C / NMM_GN_GROUPS) * full.P;
     if (g.B * g.F > 65535) return fail(NMM_ERR_UNSUPPORTED, "batch*frames > 65535");
     if (g.dtype == NMM_BF16 && g.C % 64 == 0 && g.P % 64 == 0 && x_vec_ok<bf16>(g, s, x) && aligned(tokens, 16)) {

@@ -75,6 +75,7 @@ SIGNATURES = {
     "nmm_workspace_bytes": (C.c_int, [_SP, C.POINTER(C.c_size_t)]),
     "nmm_pack_params": (C.c_int, [_SP, C.POINTER(Params), C.c_void_p, C.c_size_t, C.c_void_p]),
     "nmm_forward": (C.c_int, [_SP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "nmm_forward_stats": (C.c_int, [_SP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nmm_packed_header": (C.c_int, [_SP, C.c_void_p, C.c_size_t]),
     "nmm_forward_stage": (C.c_int, [_SP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int32, C.c_void_p, C.c_void_p]),
     "nmm_groupnorm_stats": (C.c_int, [_SP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -83,6 +84,9 @@ SIGNATURES = {
                                        C.c_size_t, C.c_void_p]),
     "nmm_groupnorm_workspace_bytes": (C.c_int, [_SP, C.POINTER(C.c_size_t)]),
     "nmm_inflated_groupnorm": (C.c_int, [_SP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "nmm_inflated_groupnorm_sums": (C.c_int, [_SP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t,
+                                              C.c_void_p]),
+    "nmm_groupnorm_sums": (C.c_int, [_SP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "nmm_cfg_ddim_step": (C.c_int, [C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_double, C.c_double, C.c_void_p]),
     "nmm_layernorm_pe": (C.c_int, [_SP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nmm_temporal_attention": (C.c_int, [_SP, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -281,7 +281,30 @@ def motion_forward(module: nn.Module, input_tensor: torch.Tensor) -> torch.Tenso
     cfg, packed = eng.get(module, input_tensor)
     # same computation as torch.ops.neurons_mm.forward (ops.forward_packed is its CUDA implementation), called directly with this
     # module's shape cache so the per-call host work is one dict lookup, two allocations and one C call
-    return ops.forward_packed(input_tensor, packed, cfg, shape_cache=eng.shape_cache)
+    if not module.__dict__.get("_nmm_carry_stats", False):
+        return ops.forward_packed(input_tensor, packed, cfg, shape_cache=eng.shape_cache)
+    # patch(model, carry_stats=True): the GroupNorm statistics of y ride on the output tensor to the next InflatedGroupNorm
+    # (ResnetBlock3D.norm1, unet_blocks.py:407-411), and statistics riding on x are used instead of a pass over x
+    B, _, F = input_tensor.shape[:3]
+    y_sums = torch.empty((B * F * 32, 2), dtype=torch.float64, device=input_tensor.device)
+    y = ops.forward_packed(input_tensor, packed, cfg, shape_cache=eng.shape_cache, x_sums=carried_sums(input_tensor), y_sums=y_sums)
+    attach_sums(y, y_sums)
+    return y
+
+
+def attach_sums(t: torch.Tensor, sums: torch.Tensor) -> None:
+    """Let GroupNorm statistics ride on the tensor object they describe (valid while the tensor is not modified in place)."""
+    t._nmm_gn_sums = (sums, t._version, t.data_ptr(), tuple(t.shape), tuple(t.stride()))
+
+
+def carried_sums(t: torch.Tensor) -> Optional[torch.Tensor]:
+    rec = getattr(t, "_nmm_gn_sums", None)
+    if rec is None:
+        return None
+    sums, version, ptr, shape, stride = rec
+    if version != t._version or ptr != t.data_ptr() or shape != tuple(t.shape) or stride != tuple(t.stride()):
+        return None                               # the tensor changed since the statistics were taken: recompute
+    return sums
 
 
 def invalidate(model: nn.Module) -> int:
@@ -301,13 +324,16 @@ def _is_motion_module(m: nn.Module) -> bool:
     return type(m).__name__ == "VanillaTemporalModule" and hasattr(m, "temporal_transformer")
 
 
-def patch(model: nn.Module) -> int:
+def patch(model: nn.Module, carry_stats: bool = False) -> int:
     """Rebind `forward` on every VanillaTemporalModule inside `model` (reference instances included) to the CUDA op.
-    Returns the number of modules patched.  Unsupported configurations raise here, never fall back silently."""
+    Returns the number of modules patched.  Unsupported configurations raise here, never fall back silently.
+    carry_stats=True: each call also emits the GroupNorm statistics of its output (from the last kernel's epilogue) and attaches
+    them to the returned tensor; `patch_group_norms`-patched InflatedGroupNorms pick them up and skip their statistics pass."""
     n = 0
     for m in model.modules():
         if _is_motion_module(m):
             config_of(m)                              # raises on unsupported variants
+            m.__dict__["_nmm_carry_stats"] = bool(carry_stats)
 
             def _fwd(self, input_tensor, temb=None, encoder_hidden_states=None, attention_mask=None, anchor_frame_idx=None):
                 return motion_forward(self, input_tensor)

@@ -181,11 +181,19 @@ def workspace_bytes(shape: _lib.Shape) -> int:
     return n.value
 
 
+def _check_sums(t: torch.Tensor, x: torch.Tensor, name: str):
+    B, _, F = x.shape[:3]
+    if t.dtype != torch.float64 or t.shape != (B * F * 32, 2) or not t.is_contiguous() or t.device != x.device:
+        raise ValueError(f"{name} must be a contiguous float64 [{B * F * 32}, 2] tensor on {x.device} (sum, sum of squares per (b, f, group))")
+
+
 def forward_packed(x: torch.Tensor, packed: torch.Tensor, cfg: ModuleConfig, out: Optional[torch.Tensor] = None,
-                   shape_cache: Optional[dict] = None, stage: Optional[int] = None):
+                   shape_cache: Optional[dict] = None, stage: Optional[int] = None, x_sums: Optional[torch.Tensor] = None,
+                   y_sums: Optional[torch.Tensor] = None):
     """y = module(x) through nmm_forward.  Returns logical [B,C,F,H,W] over [B,F,C,H,W] storage.
     `shape_cache` (optional dict owned by the caller) memoises the validated nmm_shape + workspace size per input geometry.
-    `stage` (tests): also return the fused kernel's fp32 [N, C] residual-stream snapshot after that stage (nmm_forward_stage)."""
+    `stage` (tests): also return the fused kernel's fp32 [N, C] residual-stream snapshot after that stage (nmm_forward_stage).
+    `x_sums` / `y_sums` (float64 [B*F*32, 2]): GroupNorm statistics handed in for x / written for y (nmm_forward_stats)."""
     _require_cuda(x, "x")
     _require_cuda(packed, "packed")
     x = _dense_hw(x)
@@ -209,6 +217,16 @@ def forward_packed(x: torch.Tensor, packed: torch.Tensor, cfg: ModuleConfig, out
             _lib.check(lib.nmm_forward_stage(C.byref(shape), x.data_ptr(), out.data_ptr(), packed.data_ptr(), packed.numel(), ws_ptr, ws_bytes,
                                              int(stage), stage_out.data_ptr(), _stream_ptr(x.device)))
         return out, stage_out
+    if x_sums is not None or y_sums is not None:
+        if x_sums is not None:
+            _check_sums(x_sums, x, "x_sums")
+        if y_sums is not None:
+            _check_sums(y_sums, x, "y_sums")
+        with torch.cuda.device(x.device):
+            _lib.check(lib.nmm_forward_stats(C.byref(shape), x.data_ptr(), out.data_ptr(), packed.data_ptr(), packed.numel(), ws_ptr, ws_bytes,
+                                             x_sums.data_ptr() if x_sums is not None else None,
+                                             y_sums.data_ptr() if y_sums is not None else None, _stream_ptr(x.device)))
+        return out
     if x.device.index != torch.cuda.current_device():
         with torch.cuda.device(x.device):
             _lib.check(lib.nmm_forward(C.byref(shape), x.data_ptr(), out.data_ptr(), packed.data_ptr(), packed.numel(), ws_ptr,
@@ -301,10 +319,26 @@ def groupnorm_linear(cfg: ModuleConfig, x: torch.Tensor, gn_w: torch.Tensor, gn_
     return h
 
 
+def groupnorm_sums(x: torch.Tensor) -> torch.Tensor:
+    """(sum, sum of squares) of x [b, c, f, h, w] per (b, f, GroupNorm group): float64 [B*F*32, 2] (nmm_groupnorm_sums)."""
+    _require_cuda(x, "x")
+    x = _dense_hw(x)
+    shape = make_shape(ModuleConfig(x.shape[1], heads=1, pos_enc=False), x)
+    n = C.c_size_t()
+    lib = _lib.load()
+    _lib.check(lib.nmm_groupnorm_workspace_bytes(C.byref(shape), C.byref(n)))
+    ws, ws_ptr = _aligned_ws(n.value, x.device)
+    sums = torch.empty((x.shape[0] * x.shape[2] * 32, 2), dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.nmm_groupnorm_sums(C.byref(shape), x.data_ptr(), sums.data_ptr(), ws_ptr, n.value, _stream_ptr(x.device)))
+    return sums
+
+
 def inflated_groupnorm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5, silu: bool = False,
-                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                       out: Optional[torch.Tensor] = None, sums: Optional[torch.Tensor] = None) -> torch.Tensor:
     """InflatedGroupNorm(32, C, eps) of x [b, c, f, h, w] (+ SiLU): animatediff/models/resnet.py:21-29 (+ :185-186 / :198).
-    Returns a contiguous [b, c, f, h, w] tensor (what the reference's rearrange-back produces) unless `out` is given."""
+    Returns a contiguous [b, c, f, h, w] tensor (what the reference's rearrange-back produces) unless `out` is given.
+    `sums`: the statistics of x from its producer (forward_packed(..., y_sums=...)): the statistics pass over x is skipped."""
     if not x.is_cuda:
         raise RuntimeError("neurons_b200.ops.inflated_groupnorm: CUDA tensors only (there is no CPU path)")
     x = _dense_hw(x)
@@ -319,8 +353,13 @@ def inflated_groupnorm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor
     ws, ws_ptr = _aligned_ws(n.value, x.device)
     w, b = weight.float().contiguous(), bias.float().contiguous()
     with torch.cuda.device(x.device):
-        _lib.check(lib.nmm_inflated_groupnorm(C.byref(shape), x.data_ptr(), y.data_ptr(), w.data_ptr(), b.data_ptr(), int(silu), ws_ptr, n.value,
-                                              _stream_ptr(x.device)))
+        if sums is not None:
+            _check_sums(sums, x, "sums")
+            _lib.check(lib.nmm_inflated_groupnorm_sums(C.byref(shape), x.data_ptr(), y.data_ptr(), w.data_ptr(), b.data_ptr(), int(silu),
+                                                       sums.data_ptr(), ws_ptr, n.value, _stream_ptr(x.device)))
+        else:
+            _lib.check(lib.nmm_inflated_groupnorm(C.byref(shape), x.data_ptr(), y.data_ptr(), w.data_ptr(), b.data_ptr(), int(silu), ws_ptr, n.value,
+                                                  _stream_ptr(x.device)))
     return y
 
 

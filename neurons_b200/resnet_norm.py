@@ -23,7 +23,9 @@ def _gn_forward(self: nn.GroupNorm, x: torch.Tensor) -> torch.Tensor:
         raise RuntimeError("neurons_b200.InflatedGroupNorm: CUDA tensors only (there is no CPU path)")
     if torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad):
         raise RuntimeError("neurons_b200.InflatedGroupNorm is inference-only: call it under torch.no_grad()")
-    return ops.inflated_groupnorm(x, self.weight, self.bias, self.eps, silu=False)
+    # statistics emitted by the producer of x (a carry_stats-patched motion module): one pass over x instead of two
+    from .motion_module import carried_sums
+    return ops.inflated_groupnorm(x, self.weight, self.bias, self.eps, silu=False, sums=carried_sums(x))
 
 
 class InflatedGroupNorm(nn.GroupNorm):

@@ -76,7 +76,8 @@ def test_sizes(built_library):
     # the module runs chunk by chunk over position ranges (L2-resident intermediates): the workspace holds ONE chunk
     # (tokens 2 B + residual 4 B + qkv|act 8 B + ctx 2 B per token-channel) plus the GroupNorm partial sums
     tokens = 8 * 64 * 64
-    assert 4096 * 320 * (2 + 4 + 8 + 2) <= n.value <= tokens * 320 * (2 + 4 + 8 + 2) + (1 << 20)
+    # ... plus the per-(32-row block, channel) fp32 sums of y the last kernel can emit for the next GroupNorm (8 bytes each)
+    assert 4096 * 320 * (2 + 4 + 8 + 2) <= n.value <= tokens * 320 * (2 + 4 + 8 + 2) + tokens // 32 * 320 * 8 + (1 << 20)
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
