@@ -124,7 +124,8 @@ typedef enum nmm_option {
     NMM_OPT_GEMM_BLOCK_N = 5,   /* 0: planner decides; else force the N tile.                         env NMM_GEMM_BLOCK_N          */
     NMM_OPT_CHUNK_TOKENS = 6,   /* 0: whole tensor; else tokens per position chunk (negative result). env NMM_CHUNK_TOKENS          */
     NMM_OPT_ATTN_VARIANT = 7,   /* 0: specialised mma kernel; 1: run-time-shaped mma; 2: SIMT.        env NMM_ATTN_GENERIC / _SIMT  */
-    NMM_OPT_SPLIT_K = 8,        /* 1: split-K for GEMMs with too few tiles for the machine (C = 1280 levels).  env NMM_NO_SPLIT_K=1 -> 0 */
+    NMM_OPT_FUSED_Y_STATS = 8,  /* nmm_forward_stats on the one-kernel C = 320 path: 1 = y sums emitted from the kernel's y store; 0 (default) =
+                                   a statistics pass over the (L2-resident) y, measured faster there.  env NMM_FUSED_Y_STATS          */
     NMM_OPT_FUSED_CLUSTER = 9,  /* 0: CTA pairs when the tile count is even; 1: force the single-CTA fused kernel.  env NMM_FUSED_CLUSTER */
     NMM_OPT_COUNT = 10
 } nmm_option;

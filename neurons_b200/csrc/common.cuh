@@ -128,6 +128,21 @@ __device__ __forceinline__ float warp_max(float v) {
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
+// Element-wise sum of N values over a group of G consecutive lanes (G a power of two, N >= G) by recursive halving: each step a lane
+// keeps one half of its values and adds the partner's copy of that half (N - N/G shuffles instead of N log2 G).  Afterwards lane l of
+// the group holds the N / G group totals of indices l * N/G ... in v[0 .. N/G).
+template <int N, int G>
+__device__ __forceinline__ void lane_group_reduce_scatter(float (&v)[N], int lane) {
+#pragma unroll
+    for (int o = G / 2, n = N / 2; o > 0; o >>= 1, n >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < n; i++) {
+            const float send = up ? v[i] : v[i + n], keep = up ? v[i + n] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+}
 __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ float to_f32(bf16 v) { return __bfloat162float(v); }
 template <typename T> __device__ __forceinline__ T from_f32(float v);

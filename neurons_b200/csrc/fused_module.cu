@@ -892,10 +892,10 @@ __global__ void __launch_bounds__(FM_THREADS, 1) fused_module_kernel(const __gri
                 // (EMIT: also accumulate this row's per-GroupNorm-group sums of the ROUNDED outputs -- the next InflatedGroupNorm's statistics)
                 auto y_rows = [&](auto EMIT) {
                     constexpr bool kEmit = decltype(EMIT)::value;
-                    float gs[kEmit ? 8 : 1], gq[kEmit ? 8 : 1];           // this thread's 80 channels = 8 groups of 10
+                    float gv[kEmit ? 16 : 1];                             // this thread's 80 channels = 8 groups of 10: (sum, sum of squares) pairs
                     if constexpr (kEmit) {
 #pragma unroll
-                        for (int g8 = 0; g8 < 8; g8++) { gs[g8] = 0.f; gq[g8] = 0.f; }
+                        for (int i = 0; i < 16; i++) gv[i] = 0.f;
                     }
 #pragma unroll
                     for (int k = 0; k < 5; k++) {
@@ -919,26 +919,18 @@ __global__ void __launch_bounds__(FM_THREADS, 1) fused_module_kernel(const __gri
                             if constexpr (kEmit) {
                                 const int gl = (16 * k + 2 * j) / 10;      // compile-time: both channels of the pair lie in one group
                                 const float y0 = bf16_lo(yw), y1 = bf16_hi(yw);
-                                gs[gl] += y0 + y1;
-                                gq[gl] = fmaf(y0, y0, fmaf(y1, y1, gq[gl]));
+                                gv[2 * gl] += y0 + y1;
+                                gv[2 * gl + 1] = fmaf(y0, y0, fmaf(y1, y1, gv[2 * gl + 1]));
                             }
                         }
                     }
                     if constexpr (kEmit) {
-                        // the PPT rows of one frame are PPT consecutive lanes: butterfly over them, the frame's first lane writes
+                        // the PPT rows of one frame are PPT consecutive lanes: reduce-scatter over them, then lane pl_m of the frame holds
+                        // floats [pl_m * 16 / PPT, ...) of the frame's 16 (= 8 groups x (sum, sum of squares)) totals
+                        lane_group_reduce_scatter<16, PPT>(gv, lane);
+                        float *dst = reinterpret_cast<float *>(p.y_part + ((int64_t)t * F + f_m) * NMM_GN_GROUPS + 8 * sub) + pl_m * (16 / PPT);
 #pragma unroll
-                        for (int g8 = 0; g8 < 8; g8++) {
-#pragma unroll
-                            for (int o = PPT / 2; o > 0; o >>= 1) {
-                                gs[g8] += __shfl_xor_sync(0xffffffffu, gs[g8], o);
-                                gq[g8] += __shfl_xor_sync(0xffffffffu, gq[g8], o);
-                            }
-                        }
-                        if (pl_m == 0) {
-                            float2 *dst = p.y_part + ((int64_t)t * F + f_m) * NMM_GN_GROUPS + 8 * sub;
-#pragma unroll
-                            for (int g8 = 0; g8 < 8; g8++) dst[g8] = make_float2(gs[g8], gq[g8]);
-                        }
+                        for (int i = 0; i < 16 / PPT; i++) dst[i] = gv[i];
                     }
                 };
                 if (p.y_part != nullptr) y_rows(std::true_type{}); else y_rows(std::false_type{});

@@ -599,6 +599,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
                         for (int j = 0; j < 32; j++) srow[j] = r[j];
                         __syncwarp();
+                        float ysum[8];                             // (sum, sum of squares) of this lane's rows for its 4 channels (y_part)
                         if (rows_ok) {
 #pragma unroll
                             for (int j = 0; j < 4; j++) {
@@ -612,19 +613,21 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                                     o[i] = pack_bf16x2(sc[(2 * i) * TC_XPOSE_PITCH] + bias + bf16_lo(xw[i]),
                                                        sc[(2 * i + 1) * TC_XPOSE_PITCH] + bias + bf16_hi(xw[i]));
                                 *reinterpret_cast<uint4 *>(yrow + (int64_t)(col0 + c) * e.ysc) = make_uint4(o[0], o[1], o[2], o[3]);
-                                if (e.y_part != nullptr) {
-                                    // statistics of y AS STORED for the next GroupNorm: this lane's 8 rows of channel c, then the 4 lanes
-                                    // (rg) that share the channel -> one (sum, sum of squares) per 32-row block and channel, no atomics
+                                if (e.y_part != nullptr) {      // statistics of y AS STORED: this lane's 8 rows of channel c
                                     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
                                     for (int i = 0; i < 4; i++) {
                                         const float y0 = bf16_lo(o[i]), y1 = bf16_hi(o[i]);
                                         s1 += y0 + y1; s2 = fmaf(y0, y0, fmaf(y1, y1, s2));
                                     }
-                                    s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
-                                    s1 += __shfl_xor_sync(0xffffffffu, s1, 2); s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
-                                    if (rg == 0) e.y_part[(row0 >> 5) * e.N + col0 + c] = make_float2(s1, s2);
+                                    ysum[2 * j] = s1; ysum[2 * j + 1] = s2;
                                 }
+                            }
+                            if (e.y_part != nullptr) {
+                                // the 4 lanes (rg) that share a channel column: reduce-scatter, lane rg ends with the totals of channel
+                                // cq + 8 * rg -> one (sum, sum of squares) per 32-row block and channel, no atomics
+                                lane_group_reduce_scatter<8, 4>(ysum, lane);
+                                e.y_part[(row0 >> 5) * e.N + col0 + cq + 8 * rg] = make_float2(ysum[0], ysum[1]);
                             }
                         }
                         __syncwarp();

@@ -13,6 +13,7 @@ import neurons_b200 as nb  # noqa: E402
 from neurons_b200 import lib as nlib  # noqa: E402
 
 B, F, side = (int(v) for v in (sys.argv[1:4] if len(sys.argv) >= 4 else (2, 8, 16)))
+EMIT = len(sys.argv) >= 5 and sys.argv[4] == "emit"      # also emit the GroupNorm sums of y (N1)
 dev = torch.device("cuda", 0)
 kw = dict(num_attention_heads=8, num_transformer_block=1, attention_block_types=("Temporal_Self", "Temporal_Self"),
           temporal_position_encoding=True, temporal_position_encoding_max_len=24, temporal_attention_dim_div=1, zero_initialize=False)
@@ -24,7 +25,12 @@ with torch.no_grad():
     torch.cuda.synchronize()
     lib = nlib.load()
     lib.nmm_debug_fm_trace_dump(b"/dev/null")
-    m(x, None, None)
+    if EMIT:
+        from neurons_b200 import ops
+        eng = m.__dict__["_nmm_engine"]
+        ops.forward_packed(x, eng.packed, eng.cfg, y_sums=torch.empty(B * F * 32, 2, dtype=torch.float64, device=dev))
+    else:
+        m(x, None, None)
     torch.cuda.synchronize()
     path = os.path.join(ROOT, "gpurun_out", "fm_trace.txt")
     os.makedirs(os.path.dirname(path), exist_ok=True)

@@ -37,14 +37,23 @@ def test_carried_sums_are_dropped_when_the_tensor_changes():
 @pytest.mark.gpu
 @pytest.mark.skipif(not GPU, reason="needs a CUDA device")
 @pytest.mark.parametrize("C,F,H,W,B,dtype", [
-    (320, 8, 16, 16, 2, torch.bfloat16),      # one-kernel module: sums from its y store
+    (320, 8, 16, 16, 2, torch.bfloat16),      # one-kernel module: statistics pass over y (default) / sums from its y store (option)
     (320, 16, 8, 8, 1, torch.bfloat16),
     (640, 8, 8, 8, 2, torch.bfloat16),        # multi-kernel path: sums from proj_out's epilogue
     (1280, 8, 8, 8, 1, torch.bfloat16),
     (320, 8, 3, 5, 1, torch.bfloat16),        # ragged latent: statistics pass over y
     (320, 8, 8, 8, 1, torch.float32),         # fp32 modes: statistics pass over y
 ])
-def test_forward_stats_emits_sums_of_y_and_accepts_sums_of_x(C, F, H, W, B, dtype):
+@pytest.mark.parametrize("fused_emit", [0, 1])
+def test_forward_stats_emits_sums_of_y_and_accepts_sums_of_x(C, F, H, W, B, dtype, fused_emit):
+    from neurons_b200 import lib as nlib
+    if fused_emit and not (C == 320 and dtype == torch.bfloat16 and (H * W) % (128 // F) == 0):
+        pytest.skip("option only affects calls that run on the one-kernel path")
+    with nlib.options({nlib.OPT_FUSED_Y_STATS: fused_emit}):
+        _check_forward_stats(C, F, H, W, B, dtype)
+
+
+def _check_forward_stats(C, F, H, W, B, dtype):
     cfg = mo.MotionConfig(C)
     params = mo.make_params(cfg, 5)
     x = mo.make_input((B, C, F, H, W), 6, layout="bfchw")
