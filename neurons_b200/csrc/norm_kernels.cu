@@ -17,13 +17,30 @@ namespace nmm {
 // grid has >= ~8 CTAs per SM; each CTA writes one (sum, sumsq) pair in double.  Finalisation (mean,
 // rstd) is done by the consumer, so there are no atomics and the result is deterministic.
 // ------------------------------------------------------------------------------------------------
-constexpr int GN_THREADS = 256;
-constexpr int GN_CHUNK = 16384;     // elements per CTA (8 x 16-byte loads in flight per thread in bf16)
-
-static int gn_splits(const Geo &g) {
-    int64_t per_group = (int64_t)(g.C / NMM_GN_GROUPS) * g.P;
-    return (int)ceil_div(per_group, GN_CHUNK);
+// Launch shape: one CTA per (b, f, group, split); a CTA of TH threads keeps PT 16-byte loads per thread in flight (all issued before
+// the first accumulate).  The plan picks the smallest (TH, PT) whose chunk TH * PT * 8 covers a whole group, so that at the UNet
+// levels of the bench (10 x 4096, 20 x 1024, 40 x 256, 40 x 64 elements per group) a group is ONE CTA, the grid (B*F*32 CTAs) is a
+// single wave with >= 64 KB of loads in flight per SM, and the consumers finalise from one partial per group.  (Round 1 used fixed
+// 256 x 8 chunks: 1536 CTAs = 1.3 waves at the 64 x 64 level, 2.2 TB/s; the tail wave ran on a third of the machine.)
+constexpr int GN_MAX_THREADS = 512, GN_MAX_PT = 16;
+struct GnPlan { int threads, pt, splits; };
+static GnPlan gn_plan(const Geo &g) {
+    const int64_t total = (int64_t)(g.C / NMM_GN_GROUPS) * g.P;
+    const int64_t cap = (int64_t)GN_MAX_THREADS * GN_MAX_PT * 8;
+    GnPlan p;
+    p.splits = (int)ceil_div(total, cap);
+    const int64_t per = ceil_div(total, (int64_t)p.splits);            // elements one CTA must cover
+    static const int TH[4] = {64, 128, 256, 512}, PT[5] = {4, 5, 8, 10, 16};
+    int64_t best = -1;
+    p.threads = GN_MAX_THREADS; p.pt = GN_MAX_PT;
+    for (int t = 0; t < 4; t++)
+        for (int q = 0; q < 5; q++) {
+            const int64_t chunk = (int64_t)TH[t] * PT[q] * 8;
+            if (chunk >= per && (best < 0 || chunk < best || (chunk == best && TH[t] > p.threads))) { best = chunk; p.threads = TH[t]; p.pt = PT[q]; }
+        }
+    return p;
 }
+static int gn_splits(const Geo &g) { return gn_plan(g).splits; }
 int gn_splits_of(const Geo &g) { return gn_splits(g); }
 size_t gn_partial_bytes(const Geo &g) {
     return (size_t)g.B * g.F * NMM_GN_GROUPS * gn_splits(g) * 2 * sizeof(double);
@@ -49,10 +66,11 @@ __device__ __forceinline__ void accum16v(const uint4 v, float &s, float &ss) {
     }
 }
 
-template <typename T, bool VEC>
-__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const T *__restrict__ x, double *__restrict__ partial,
-                                                              int C, int F, int P, int splits, int64_t sb, int64_t sc,
-                                                              int64_t sf) {
+// VEC: PT 16-byte vectors per thread (chunk = blockDim.x * PT vectors); !VEC: element loop over the same chunk.
+template <typename T, bool VEC, int PT>
+__global__ void __launch_bounds__(GN_MAX_THREADS) gn_stats_kernel(const T *__restrict__ x, double *__restrict__ partial,
+                                                                  int C, int F, int P, int splits, int64_t sb, int64_t sc,
+                                                                  int64_t sf) {
     pdl_wait();                    // PDL: the previous kernel has completed (no-op without the launch attribute)
     pdl_launch_dependents();       // let the next kernel's launch + prologue overlap this kernel
     const int cpg = C / NMM_GN_GROUPS;
@@ -62,43 +80,47 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const T *__restric
     const int b = bf / F, f = bf % F;
     const T *base = x + (int64_t)b * sb + (int64_t)f * sf + (int64_t)grp * cpg * sc;
     const int64_t total = (int64_t)cpg * P;
-    const int64_t e0 = (int64_t)split * GN_CHUNK;
-    const int64_t e1 = min(total, e0 + (int64_t)GN_CHUNK);
+    constexpr int V = Vec16<T>::N;
+    const int64_t chunk = (int64_t)blockDim.x * PT * 8;                 // elements per CTA (8 = bf16 per vector; the fp32 path covers it in 2 PT rounds)
+    const int64_t e0 = (int64_t)split * chunk;
+    const int64_t e1 = min(total, e0 + chunk);
     float s = 0.f, ss = 0.f;
     if constexpr (VEC) {
-        constexpr int V = Vec16<T>::N;                 // P % V == 0, so a vector never straddles channels
-        constexpr int PER_THREAD = GN_CHUNK / (GN_THREADS * V);
-        const int tot = (int)total, base_e = (int)e0;  // cpg*P < 2^31 (validated)
-        // issue every load of this thread before the first accumulate (4 x 16 B in flight per thread for bf16)
-        uint4 v[PER_THREAD];
-        bool ok[PER_THREAD];
+        const int tot = (int)total;                    // cpg*P < 2^31 (validated); P % V == 0, so a vector never straddles channels
+        constexpr int ROUNDS = 8 / V;                   // fp32: 4 elements per vector -> two rounds of PT loads cover the same chunk
 #pragma unroll
-        for (int i = 0; i < PER_THREAD; i++) {
-            const int e = base_e + (i * GN_THREADS + (int)threadIdx.x) * V;
-            ok[i] = e < tot;
-            const int c = ok[i] ? e / P : 0;
-            const int p = ok[i] ? e - c * P : 0;
-            v[i] = ok[i] ? __ldg(reinterpret_cast<const uint4 *>(base + (int64_t)c * sc + p)) : make_uint4(0u, 0u, 0u, 0u);
+        for (int rd = 0; rd < ROUNDS; rd++) {
+            const int base_e = (int)e0 + rd * (int)blockDim.x * PT * V;
+            // issue every load of this round before the first accumulate
+            uint4 v[PT];
+#pragma unroll
+            for (int i = 0; i < PT; i++) {
+                const int e = base_e + (i * (int)blockDim.x + (int)threadIdx.x) * V;
+                const bool ok = e < tot;
+                const int c = ok ? e / P : 0;
+                const int p = ok ? e - c * P : 0;
+                v[i] = ok ? __ldg(reinterpret_cast<const uint4 *>(base + (int64_t)c * sc + p)) : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int i = 0; i < PT; i++) accum16v<T>(v[i], s, ss);      // zero vectors add nothing
         }
-#pragma unroll
-        for (int i = 0; i < PER_THREAD; i++) accum16v<T>(v[i], s, ss);      // zero vectors add nothing
     } else {
-        for (int64_t e = e0 + threadIdx.x; e < e1; e += GN_THREADS) {
+        for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
             int c = (int)(e / P); int p = (int)(e - (int64_t)c * P);
             float v = to_f32(base[(int64_t)c * sc + p]);
             s += v; ss = fmaf(v, v, ss);
         }
     }
-    // block reduce in double (per-thread fp32 partials cover <= 32 elements each)
-    __shared__ double sh[2][GN_THREADS / 32];
+    // block reduce in double (per-thread fp32 partials cover <= 128 elements each)
+    __shared__ double sh[2][GN_MAX_THREADS / 32];
     double ds = (double)warp_sum(s), dss = (double)warp_sum(ss);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (lane == 0) { sh[0][warp] = ds; sh[1][warp] = dss; }
     __syncthreads();
     if (threadIdx.x == 0) {
         double a = 0, c2 = 0;
-#pragma unroll
-        for (int i = 0; i < GN_THREADS / 32; i++) { a += sh[0][i]; c2 += sh[1][i]; }
+        const int nw = (int)blockDim.x >> 5;
+        for (int i = 0; i < nw; i++) { a += sh[0][i]; c2 += sh[1][i]; }
         partial[(int64_t)blockIdx.x * 2 + 0] = a;
         partial[(int64_t)blockIdx.x * 2 + 1] = c2;
     }
@@ -110,22 +132,32 @@ static bool x_vec_ok(const Geo &g, const nmm_shape *s, const void *x) {
     return g.P % V == 0 && s->x_stride_b % V == 0 && s->x_stride_c % V == 0 && s->x_stride_f % V == 0 && aligned(x, 16);
 }
 
+template <typename T, bool VEC>
+static void launch_gn_stats_pt(const GnPlan &pl, dim3 grid, cudaStream_t st, const T *x, double *partial, const Geo &g, const nmm_shape *s) {
+    const dim3 block((unsigned)pl.threads);
+#define GN_PT(N) launch_pdl(gn_stats_kernel<T, VEC, N>, grid, block, 0, st, x, partial, g.C, g.F, g.P, pl.splits, s->x_stride_b, s->x_stride_c, s->x_stride_f)
+    switch (pl.pt) {
+        case 4: GN_PT(4); break;
+        case 5: GN_PT(5); break;
+        case 8: GN_PT(8); break;
+        case 10: GN_PT(10); break;
+        default: GN_PT(16); break;
+    }
+#undef GN_PT
+}
+
 int launch_gn_stats(const Geo &g, const nmm_shape *s, const void *x, double *partial, cudaStream_t st) {
-    const int splits = gn_splits(g);
-    const int64_t blocks = (int64_t)g.B * g.F * NMM_GN_GROUPS * splits;
+    const GnPlan pl = gn_plan(g);
+    const int64_t blocks = (int64_t)g.B * g.F * NMM_GN_GROUPS * pl.splits;
     if (blocks > 0x7fffffff) return fail(NMM_ERR_UNSUPPORTED, "gn_stats grid too large");
-    dim3 grid((unsigned)blocks), block(GN_THREADS);
+    dim3 grid((unsigned)blocks);
     ProfScope prof(K_GN_STATS, st, 0.0, (double)g.N * g.C * dtype_size(g.dtype));
     if (g.dtype == NMM_BF16) {
-        if (x_vec_ok<bf16>(g, s, x))
-            launch_pdl(gn_stats_kernel<bf16, true>, grid, block, 0, st, (const bf16 *)x, partial, g.C, g.F, g.P, splits, s->x_stride_b, s->x_stride_c, s->x_stride_f);
-        else
-            launch_pdl(gn_stats_kernel<bf16, false>, grid, block, 0, st, (const bf16 *)x, partial, g.C, g.F, g.P, splits, s->x_stride_b, s->x_stride_c, s->x_stride_f);
+        if (x_vec_ok<bf16>(g, s, x)) launch_gn_stats_pt<bf16, true>(pl, grid, st, (const bf16 *)x, partial, g, s);
+        else launch_gn_stats_pt<bf16, false>(pl, grid, st, (const bf16 *)x, partial, g, s);
     } else {
-        if (x_vec_ok<float>(g, s, x))
-            launch_pdl(gn_stats_kernel<float, true>, grid, block, 0, st, (const float *)x, partial, g.C, g.F, g.P, splits, s->x_stride_b, s->x_stride_c, s->x_stride_f);
-        else
-            launch_pdl(gn_stats_kernel<float, false>, grid, block, 0, st, (const float *)x, partial, g.C, g.F, g.P, splits, s->x_stride_b, s->x_stride_c, s->x_stride_f);
+        if (x_vec_ok<float>(g, s, x)) launch_gn_stats_pt<float, true>(pl, grid, st, (const float *)x, partial, g, s);
+        else launch_gn_stats_pt<float, false>(pl, grid, st, (const float *)x, partial, g, s);
     }
     NMM_LAUNCHED("gn_stats_kernel");
     return NMM_OK;

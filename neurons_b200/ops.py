@@ -67,7 +67,9 @@ def _require_cuda(t: torch.Tensor, name: str):
         raise RuntimeError(f"neurons_mm: `{name}` must be a CUDA tensor (there is no CPU implementation of this path)")
 
 
-def make_shape(cfg: ModuleConfig, x: torch.Tensor, y: Optional[torch.Tensor] = None) -> _lib.Shape:
+def make_shape(cfg: ModuleConfig, x: torch.Tensor, y: Optional[torch.Tensor] = None, stage: bool = False) -> _lib.Shape:
+    """nmm_shape of a module call.  stage=True (per-stage entry points): fp32 tensors are plain fp32 (NMM_F32), never the hi | lo
+    plane format of the whole-module NMM_F32X3 mode."""
     if x.dim() != 5:
         # same invariant and message as the reference, motion_module.py:135
         raise AssertionError(f"Expected hidden_states to have ndim=5, but got ndim={x.dim()}.")
@@ -76,7 +78,7 @@ def make_shape(cfg: ModuleConfig, x: torch.Tensor, y: Optional[torch.Tensor] = N
     s.batch, s.channels, s.frames, s.height, s.width = B, Cc, F, H, W
     s.heads, s.layers, s.attn_blocks = cfg.heads, cfg.layers, cfg.attn_blocks
     s.pos_enc, s.max_len = int(cfg.pos_enc), cfg.max_len
-    s.dtype = _dtype_code(x.dtype, cfg)
+    s.dtype = _dtype_code(x.dtype, None if stage else cfg)
     s.eps_gn, s.eps_ln = GN_EPS, LN_EPS
     s.ln_fold = _ln_fold(cfg)
     s.x_stride_b, s.x_stride_c, s.x_stride_f = x.stride(0), x.stride(1), x.stride(2)
@@ -275,7 +277,7 @@ def _tokens(cfg: ModuleConfig, x: torch.Tensor):
 
 def groupnorm_stats(cfg: ModuleConfig, x: torch.Tensor):
     x = _dense_hw(x)
-    shape = make_shape(cfg, x)
+    shape = make_shape(cfg, x, stage=True)
     B, F = x.shape[0], x.shape[2]
     mean = torch.empty(B * F * 32, dtype=torch.float32, device=x.device)
     rstd = torch.empty_like(mean)
@@ -289,7 +291,7 @@ def groupnorm_stats(cfg: ModuleConfig, x: torch.Tensor):
 
 def groupnorm_tokens(cfg: ModuleConfig, x: torch.Tensor, gn_w: torch.Tensor, gn_b: torch.Tensor) -> torch.Tensor:
     x = _dense_hw(x)
-    shape = make_shape(cfg, x)
+    shape = make_shape(cfg, x, stage=True)
     tok = torch.empty((_tokens(cfg, x), cfg.channels), dtype=x.dtype, device=x.device)
     ws_bytes = workspace_bytes(shape)
     ws, ws_ptr = _aligned_ws(ws_bytes, x.device)
@@ -304,7 +306,7 @@ def groupnorm_linear(cfg: ModuleConfig, x: torch.Tensor, gn_w: torch.Tensor, gn_
                      bias: Optional[torch.Tensor]) -> torch.Tensor:
     """GroupNorm + token re-layout + Linear in one tensor-core kernel (bf16): fp32 [N, C_out].  motion_module.py:142-145."""
     x = _dense_hw(x)
-    shape = make_shape(cfg, x)
+    shape = make_shape(cfg, x, stage=True)
     c_out = weight.shape[0]
     h = torch.empty((_tokens(cfg, x), c_out), dtype=torch.float32, device=x.device)
     ws_bytes = workspace_bytes(shape)
@@ -323,7 +325,7 @@ def groupnorm_sums(x: torch.Tensor) -> torch.Tensor:
     """(sum, sum of squares) of x [b, c, f, h, w] per (b, f, GroupNorm group): float64 [B*F*32, 2] (nmm_groupnorm_sums)."""
     _require_cuda(x, "x")
     x = _dense_hw(x)
-    shape = make_shape(ModuleConfig(x.shape[1], heads=1, pos_enc=False), x)
+    shape = make_shape(ModuleConfig(x.shape[1], heads=1, pos_enc=False), x, stage=True)
     n = C.c_size_t()
     lib = _lib.load()
     _lib.check(lib.nmm_groupnorm_workspace_bytes(C.byref(shape), C.byref(n)))
@@ -345,7 +347,7 @@ def inflated_groupnorm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor
     y = out if out is not None else torch.empty(x.shape, dtype=x.dtype, device=x.device)
     if y.shape != x.shape or y.dtype != x.dtype or _dense_hw(y) is not y:
         raise ValueError("out must have the shape / dtype of x and dense (h, w)")
-    shape = make_shape(ModuleConfig(x.shape[1], heads=1, pos_enc=False), x, y)
+    shape = make_shape(ModuleConfig(x.shape[1], heads=1, pos_enc=False), x, y, stage=True)
     shape.eps_gn = eps
     n = C.c_size_t()
     lib = _lib.load()
