@@ -717,6 +717,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             } else {
                 // STORE / RESIDUAL: 32-column chunks.  RESIDUAL: the fp32 residual chunk is TMA-loaded into box (k & 1) one chunk
                 // ahead, summed in place and TMA-stored from the same box (or written as bf16 into the box when only `out` is wanted).
+                // (Measured alternative, round 2: residual rows loaded straight into registers -- lane = row, 8 x 16-byte loads per chunk,
+                //  two-box store ring, no load boxes -- is 35 % SLOWER (to_out 26.8 -> 36.2 us at C = 640): 32 rows x 16 B per instruction
+                //  touches 32 cache lines, and with 200+ KB of shared memory configured there is no L1 left to merge the sector halves.)
                 const int first = half * 32;
                 int k = 0;
                 if constexpr (EPI == NMM_EPI_RESIDUAL) {
@@ -1039,7 +1042,7 @@ int launch_linear_tc(const LinearArgs &a, cudaStream_t st) {
     if (a.K % 8 != 0) return fail(NMM_ERR_UNSUPPORTED, "tcgen05 GEMM needs K %% 8 == 0 (K=%d)", a.K);
     const bool x3 = a.x3 != 0;
     if (x3 && (a.K % TC_BK != 0 || a.gn_x != nullptr || a.epilogue == NMM_EPI_QKV_ATTN || a.ln_part_in != nullptr || a.ln_part_out != nullptr ||
-               (a.epilogue == NMM_EPI_STORE && a.out != nullptr)))
+               (a.epilogue == NMM_EPI_STORE && a.out != nullptr) || (a.epilogue == NMM_EPI_RESIDUAL && a.out != nullptr && !a.no_h_store)))
         return fail(NMM_ERR_UNSUPPORTED, "3 x bf16 (fp32-grade) tensor-core GEMM: needs K %% 64 == 0, no fused GroupNorm / attention / LayerNorm folding, and a STORE epilogue writing fp32 only");
     if (a.M <= 0) return NMM_OK;
     TcParams p;
