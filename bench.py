@@ -152,7 +152,7 @@ def clip_loop(nb, wl, dev, clips: int = 3, clip_batch: int = 1):
     return e0.elapsed_time(e1) / clips, flops_clip           # ms per replayed 25-step loop (= clip_batch clips), flops of that loop
 
 
-def clip_e2e(nb, wl, dev, rank: int, world: int, clips_per_rank: int = 2):
+def clip_e2e(nb, wl, dev, rank: int, world: int, clips_per_rank: int = 4):
     """Clip-level end to end (BASELINE configs[2] shape), everything inside the timed region: per clip the H2D copy of its latents +
     conditioning from pinned host memory, 25 graph-replayed denoising steps (28 motion-module calls + the fused CFG / DDIM update,
     nmm_cfg_ddim_step, on the clip's latents), a decoded-frame-sized result per clip ([3, 16, 256, 256] fp16; nearest up-sampling stands

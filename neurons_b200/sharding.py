@@ -38,8 +38,13 @@ def gather_clips(local: torch.Tensor, num_clips: int, group=None) -> Optional[to
     assert local.shape[0] == n_local, (local.shape, n_local)
     padded = local.new_zeros((per_rank,) + tuple(local.shape[1:]))
     padded[:n_local] = local
-    bucket = [torch.empty_like(padded) for _ in range(world)]
-    dist.all_gather(bucket, padded.contiguous(), group=group)
+    if padded.is_cuda:         # NCCL: one contiguous receive buffer, no per-rank staging copies
+        flat = padded.new_empty((world,) + tuple(padded.shape))
+        dist.all_gather_into_tensor(flat, padded.contiguous(), group=group)
+        bucket = list(flat.unbind(0))
+    else:
+        bucket = [torch.empty_like(padded) for _ in range(world)]
+        dist.all_gather(bucket, padded.contiguous(), group=group)
     if rank != 0:
         return None
     out = local.new_empty((num_clips,) + tuple(local.shape[1:]))

@@ -23,6 +23,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--calls", type=int, default=20, help="how many of the step's 20 calls to run")
     ap.add_argument("--latent", type=int, default=64)
+    ap.add_argument("--only", default="", help="comma-separated indices (into the first --calls calls) to profile; default all")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     kwargs = dict(num_attention_heads=8, num_transformer_block=1, attention_block_types=("Temporal_Self", "Temporal_Self"),
@@ -30,6 +31,8 @@ def main():
                   zero_initialize=False)
     torch.manual_seed(0)
     calls = wl.unet_step_calls(a.latent)[: a.calls]
+    if a.only:
+        calls = [calls[int(i)] for i in a.only.split(",")]
     mods, xs = [], []
     with torch.no_grad():
         for c in calls:

@@ -7,10 +7,10 @@ import re
 import subprocess
 import sys
 
-out_name = sys.argv[1] if len(sys.argv) > 1 else "r1_bench_n1_latest.json"
-subprocess.run([sys.executable, "scripts/ncu_summarise.py", "gpurun_out/step_metrics.csv", "profiles/r1_ncu_step_summary.txt",
-                "profiles/r1_ncu_gemm_traffic.json"], check=True)
-rows = list(csv.reader(open("gpurun_out/prof_call320_raw.csv")))
+out_name = sys.argv[1] if len(sys.argv) > 1 else "r2_bench_n1_latest.json"
+subprocess.run([sys.executable, "scripts/ncu_summarise.py", "gpurun_out/step_metrics.csv", "profiles/r2_ncu_step_summary.txt",
+                "profiles/r2_ncu_gemm_traffic.json"], check=True)
+rows = list(csv.reader(open("gpurun_out/prof_calls_raw.csv")))
 hdr = rows[0]
 ki = hdr.index("Kernel Name")
 want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
@@ -24,7 +24,7 @@ tot = 0.0
 for r in rows[2:]:
     out.append([r[ki][:70]] + [r[i] for i in idx])
     tot += float(r[idx[0]])
-csv.writer(open("profiles/r1_ncu_full_one_call_c320.csv", "w")).writerows(out)
+csv.writer(open("profiles/r2_ncu_full_calls_c320_c640.csv", "w")).writerows(out)
 for r in out[2:]:
     print(r[0][:50].ljust(50), r[1][:8], "us")
 print("sum", round(tot, 1), "us over", len(out) - 2, "kernels")
@@ -37,9 +37,9 @@ for r in rows[1:]:
         continue
     name = re.sub(r"\(.*", "", r[col["Kernel Name"]]).replace("void ", "").replace("nmm::", "")[:70]
     o.append((r[col["ID"]], name, r[col["Grid Size"]].replace(",", " "), r[col["Block Size"]].replace(",", " "), r[col["Metric Unit"]], r[col["Metric Value"]]))
-with open("profiles/r1_ncu_launch_list_bench.csv", "w") as f:
-    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'linear_tc|linear_simt|gn_|layernorm_pe|temporal_attention|cfg_ddim' "
-            "-c 600 --csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-clips\n")
+with open("profiles/r2_ncu_launch_list_bench.csv", "w") as f:
+    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'linear_tc|linear_simt|fused_module|gn_|layernorm_pe|temporal_attention|cfg_ddim' "
+            "-c 600 --csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-clips --no-eager\n")
     f.write("# first 600 launches of this library in the bench command (warm-up steps, then the timed step); cold-cache / serialised, not bench values\n")
     f.write("id,kernel,grid,block,unit,duration\n")
     for x in o:
