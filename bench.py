@@ -480,11 +480,13 @@ def main():
                     ys_host[i].copy_(x_stage[i], non_blocking=True)
         step_copies()
         torch.cuda.synchronize()
+        barrier()          # every rank copies at the same time: the floor must see the same host-fabric contention as the e2e arm does
         t0 = time.perf_counter()
         for _ in range(3):
             step_copies()
         torch.cuda.synchronize()
         copy_ms = 1e3 * (time.perf_counter() - t0) / 3
+        barrier()
 
     eager = None
     if rank == 0 and not args.no_eager:
@@ -496,10 +498,10 @@ def main():
     clip4_ms, clip4_flops = (0.0, 0.0) if args.no_clips else clip_loop(nb, wl, dev, clips=2, clip_batch=4)       # BASELINE configs[3]: 4 clips per GPU
     ce_secs, ce_n, ce_h2d, ce_d2h = (0.0, 0, 0, 0) if args.no_clips else clip_e2e(nb, wl, dev, rank, world)
     # max over ranks
-    t = torch.tensor([ms_total, e2e_ms, clip_ms, clip4_ms, ce_secs], device=dev, dtype=torch.float64)
+    t = torch.tensor([ms_total, e2e_ms, clip_ms, clip4_ms, ce_secs, copy_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms, clip_ms, clip4_ms, ce_secs = float(t[0]), float(t[1]), float(t[2]), float(t[3]), float(t[4])
+    ms_total, e2e_ms, clip_ms, clip4_ms, ce_secs, copy_ms = (float(v) for v in t)
     ms_step = ms_total / args.steps
     value = world * flops_step / (ms_step * 1e-3) / 1e12
     e2e_value = world * flops_step / (e2e_ms * 1e-3) / 1e12
