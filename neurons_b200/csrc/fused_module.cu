@@ -744,6 +744,11 @@ __global__ void __launch_bounds__(FM_THREADS, 1) fused_module_kernel(const __gri
             // ---- attention blocks ----
             for (int i = 0; i < A; i++) {
                 layer_norm(VA, p.pos_enc ? f_m : 0);
+                // The k | v dumps below overwrite the vector block at VA.  They are already ordered after every warp's last read of it
+                // (a1_ready collects all 16 x CG warps -> MMA -> tcgen05.commit -> s_full), but only through mbarriers, which
+                // compute-sanitizer's racecheck does not follow: this barrier costs nothing (the warps would wait for the MMA anyway)
+                // and makes the ordering visible to the tool.
+                fm_bar_epi();
                 FM_ETRACE(4 + 20 * i);
                 for (int hp = 0; hp < 4; hp++) {
                     for (int s = 0; s < 3; s++) {
