@@ -127,10 +127,7 @@ typedef enum nmm_option {
     NMM_OPT_FUSED_Y_STATS = 8,  /* nmm_forward_stats on the one-kernel C = 320 path: 1 = y sums emitted from the kernel's y store; 0 (default) =
                                    a statistics pass over the (L2-resident) y, measured faster there.  env NMM_FUSED_Y_STATS          */
     NMM_OPT_FUSED_CLUSTER = 9,  /* 0: CTA pairs when the tile count is even; 1: force the single-CTA fused kernel.  env NMM_FUSED_CLUSTER */
-    NMM_OPT_LN_TAIL = 10,       /* 1: the GEMM that completes a row block of the residual stream (proj_in / to_out / ff_out; C % 128 == 0) also
-                                   runs the next LayerNorm (+PE) on it -- the tile that arrives last does it, no LayerNorm launch.
-                                   env NMM_NO_LN_TAIL=1 -> 0                                                                      */
-    NMM_OPT_COUNT = 11
+    NMM_OPT_COUNT = 10
 } nmm_option;
 NMM_API int nmm_set_option(int32_t option, int64_t value);
 NMM_API int64_t nmm_get_option(int32_t option);

@@ -279,13 +279,6 @@ struct LinearArgs {
     const void *x; void *y;
     int F, P;
     int64_t xsb, xsc, xsf, ysb, ysc, ysf;
-    // LayerNorm tail (tensor-core path, STORE / RESIDUAL writing h, N % 128 == 0, N <= 1280): the CTA whose tile completes a 128-row block
-    // of h LAST (per-row-block arrival counter, zeroed by the caller, reset by the last arriver) normalises those rows -- LayerNorm(N)
-    // * gamma + beta (+ pe[frame of the row]) -> lnt_out in the GEMM operand format ([M, N] bf16; X3: hi | lo planes).  Uses F, P.
-    int *lnt_cnt;            // [ceil(M / 128)] or null
-    const float *lnt_gamma, *lnt_beta, *lnt_pe;
-    void *lnt_out;
-    float lnt_eps;
     float2 *y_part;          // OUTPUT epilogue (bf16 vector path), or null: [M / 32][N] (sum, sum of squares) of y as stored, per 32-row block and channel
     // GroupNorm-fused A operand (bf16 tensor-core path, STORE epilogue: proj_in).  A is NULL; the A tiles are TMA-loaded straight
     // from x [b, c, f, p] (channel rows of positions = an M-major operand), normalised in shared memory

@@ -20,10 +20,6 @@ struct EpiParams {
     void *y;
     int F, P;
     int64_t xsb, xsc, xsf, ysb, ysc, ysf;
-    int *lnt_cnt;      // LayerNorm tail (LinearArgs::lnt_*)
-    const float *lnt_gamma, *lnt_beta, *lnt_pe;
-    void *lnt_out;
-    float lnt_eps;
     float2 *y_part;    // OUTPUT, nchw_vec path only: statistics of y for the next GroupNorm (LinearArgs::y_part)
     int nchw_vec;      // OUTPUT: P % 32 == 0 and x / y rows 16-byte aligned -> 8-position (16-byte) vector path
     int no_h_store;
@@ -46,7 +42,6 @@ inline EpiParams epi_params_of(const LinearArgs &a) {
     e.xsb = a.xsb; e.xsc = a.xsc; e.xsf = a.xsf; e.ysb = a.ysb; e.ysc = a.ysc; e.ysf = a.ysf;
     e.no_h_store = a.no_h_store;
     e.y_part = a.y_part;
-    e.lnt_cnt = a.lnt_cnt; e.lnt_gamma = a.lnt_gamma; e.lnt_beta = a.lnt_beta; e.lnt_pe = a.lnt_pe; e.lnt_out = a.lnt_out; e.lnt_eps = a.lnt_eps;
     e.ln_part_out = a.ln_part_out; e.ln_part_in = a.ln_part_in; e.ln_nparts = a.ln_nparts; e.ln_K = a.K;
     e.ln_g = a.ln_g; e.ln_c = a.ln_c; e.ln_pew = a.ln_pew; e.ln_eps = a.ln_eps;
     e.nchw_vec = output_vec_ok(a) ? 1 : 0;

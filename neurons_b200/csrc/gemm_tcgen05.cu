@@ -25,6 +25,12 @@
 //   wide (p.wide)          256 x 320 pair tile as two N = 160 MMAs per k-step into one accumulator (long-K residual GEMMs);
 //   LNF                    LayerNorm folded into producer / consumer epilogues (measured slower; kept as a tested option).
 //
+// Tried in round 2 and removed (correct -- 235 GPU tests green -- but slower): a "LayerNorm tail", where the tile that arrives LAST on a
+// 128-row block of h (per-block arrival counter after bulk-store completion + __threadfence) runs the next LayerNorm on the block from
+// L2, so that no LayerNorm kernel is launched.  With only the 8 epilogue warps on a block the tail is a chain of exposed L2 latencies
+// (one row per warp: +120 us per GEMM at C = 640; 4 rows in flight per warp: +65 us; LayerNorm kernel it replaces: 12.7 us), and the
+// per-tile store-completion wait + device fence serialise the epilogue.  A LayerNorm needs thousands of rows in flight, not 128.
+//
 // Measured bounds that shaped this (profiles/, scripts/micro/tmem_bw.cu, scripts/gemm_trace.py):
 //   * tcgen05.ld moves >= 245 B/clk/SM and overlaps fully with tcgen05.mma -- TMEM reads are not the limit;
 //   * a 128 x 240 tile needs 46 KB of operand fill per 480 MMA-cycles; with ~2500-cycle TMA latency under load and 3 stages the
@@ -174,54 +180,6 @@ __device__ __forceinline__ void fused_attention_phase(const AttnParams &at, uint
     } else {
         if (at.dh == 40) run(std::integral_constant<int, 16>{}, std::integral_constant<int, 40>{});
         else run(std::integral_constant<int, 16>{}, std::integral_constant<int, 80>{});
-    }
-}
-
-// LayerNorm tail (LinearArgs::lnt_*): after a tile's h stores, the 8 epilogue warps count the tile in on its 128-row block; the CTA that
-// arrives last (every N tile of the block is in L2 / HBM and visible: bulk-store completion + __threadfence before the counter, the
-// classic last-block pattern) runs LayerNorm(+PE) over the block -- one warp per row, the row in registers as N / 128 float4 per lane
-// (ld.global.cg: written by other SMs' TMA stores), two-pass mean / variance in fp32 exactly like layernorm_pe_vec_kernel.
-// Row results do not depend on which CTA computes them, so the output is bit-reproducible.
-template <bool X3>
-__device__ __forceinline__ void ln_tail_rows(const EpiParams &e, int64_t row_begin, int64_t M, int N, int ew, int lane) {
-    constexpr int MAX_IT = 10;                           // N <= 1280
-    const int it = N >> 7;                               // float4 per lane
-    const float inv_n = 1.0f / (float)N;
-    for (int r = ew; r < TC_BM; r += TC_EPI_WARPS) {
-        const int64_t row = row_begin + r;
-        if (row >= M) break;                             // warp-uniform
-        const float4 *hr = reinterpret_cast<const float4 *>(e.h + row * N);
-        float4 v[MAX_IT];
-        float s = 0.f;
-#pragma unroll
-        for (int i = 0; i < MAX_IT; i++) {
-            if (i < it) { v[i] = __ldcg(hr + lane + 32 * i); s += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
-        }
-        const float mu = warp_sum(s) * inv_n;
-        float ss = 0.f;
-#pragma unroll
-        for (int i = 0; i < MAX_IT; i++) {
-            if (i < it) {
-                const float a = v[i].x - mu, b = v[i].y - mu, c = v[i].z - mu, d = v[i].w - mu;
-                ss = fmaf(a, a, ss); ss = fmaf(b, b, ss); ss = fmaf(c, c, ss); ss = fmaf(d, d, ss);
-            }
-        }
-        const float rstd = rsqrtf(warp_sum(ss) * inv_n + e.lnt_eps);
-        const float4 *per = e.lnt_pe ? reinterpret_cast<const float4 *>(e.lnt_pe + (int64_t)((row / e.P) % e.F) * N) : nullptr;
-#pragma unroll
-        for (int i = 0; i < MAX_IT; i++) {
-            if (i < it) {
-                const int c4 = lane + 32 * i;
-                const float4 gm = __ldg(reinterpret_cast<const float4 *>(e.lnt_gamma) + c4);
-                const float4 bt = __ldg(reinterpret_cast<const float4 *>(e.lnt_beta) + c4);
-                float4 o;
-                o.x = fmaf((v[i].x - mu) * rstd, gm.x, bt.x); o.y = fmaf((v[i].y - mu) * rstd, gm.y, bt.y);
-                o.z = fmaf((v[i].z - mu) * rstd, gm.z, bt.z); o.w = fmaf((v[i].w - mu) * rstd, gm.w, bt.w);
-                if (per) { const float4 pp = __ldg(per + c4); o.x += pp.x; o.y += pp.y; o.z += pp.z; o.w += pp.w; }
-                if constexpr (X3) split4_store(reinterpret_cast<bf16 *>(e.lnt_out) + row * (2 * (int64_t)N), N, 4 * c4, o.x, o.y, o.z, o.w);
-                else reinterpret_cast<uint2 *>(reinterpret_cast<bf16 *>(e.lnt_out) + row * (int64_t)N)[c4] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
-            }
-        }
     }
 }
 
@@ -886,26 +844,6 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             }
             if (p.wide) aphase ^= 1u;
             else if (++as == 2) { as = 0; aphase ^= 1u; }
-            if constexpr ((EPI == NMM_EPI_STORE || EPI == NMM_EPI_RESIDUAL) && !LNF) {
-                // LayerNorm tail: count this tile in on its row block; the last arriver normalises the block (see ln_tail_rows).
-                // (the accumulator has been handed back above, so the next tile's MMAs run underneath)
-                if (e.lnt_out != nullptr && m_blk * TC_BM < p.M) {
-                    if (lane == 0) { ptx::bulk_wait_all(); __threadfence(); }      // this warp's h stores are complete and visible device-wide
-                    __syncwarp();
-                    asm volatile("bar.sync 3, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
-                    if (warp == 4 && lane == 0) {
-                        const int old = atomicAdd(e.lnt_cnt + m_blk, 1);
-                        const uint32_t last = old == p.n_tiles - 1 ? 1u : 0u;
-                        if (last) e.lnt_cnt[m_blk] = 0;                            // self-cleaning: the counter is zero again for the next GEMM
-                        __threadfence();
-                        asm volatile("st.shared.b32 [%0], %1;" ::"r"(bar_base + 896u), "r"(last) : "memory");
-                    }
-                    asm volatile("bar.sync 3, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
-                    uint32_t last;
-                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(last) : "r"(bar_base + 896u) : "memory");
-                    if (last) ln_tail_rows<X3>(e, m_blk * TC_BM, p.M, p.N, ew, lane);
-                }
-            }
         }
         if (lane == 0) ptx::bulk_wait_all();                              // all TMA stores of this warp have completed
     }
@@ -1137,9 +1075,6 @@ int launch_linear_tc(const LinearArgs &a, cudaStream_t st) {
     if (attn && (a.out == nullptr || a.A == nullptr || a.N != 3 * a.K || a.attn_B <= 0 || !linear_tc_attn_fusable(a.K, a.attn_heads, a.F, a.P) ||
                  (int64_t)a.attn_B * a.F * a.P != a.M || a.ln_part_in != nullptr || a.ln_part_out != nullptr || a.gn_x != nullptr))
         return fail(NMM_ERR_UNSUPPORTED, "fused QKV + attention: needs d_h in {40, 80}, F in {8, 16}, P %% (128 / F) == 0");
-    if (a.lnt_out != nullptr && (a.lnt_cnt == nullptr || a.lnt_gamma == nullptr || a.lnt_beta == nullptr || a.h == nullptr || a.no_h_store || a.N % 128 != 0 ||
-                                 a.N > 1280 || (a.epilogue != NMM_EPI_STORE && a.epilogue != NMM_EPI_RESIDUAL) || a.ln_part_in != nullptr || a.ln_part_out != nullptr))
-        return fail(NMM_ERR_UNSUPPORTED, "LayerNorm tail: needs a STORE / RESIDUAL epilogue that writes h, N %% 128 == 0, N <= 1280, and no LayerNorm folding");
     const bool gna = a.gn_x != nullptr;
     if (gna && (a.epilogue != NMM_EPI_STORE || a.ln_part_in != nullptr || a.ln_part_out != nullptr || a.gn_B <= 0 ||
                 !linear_tc_gn_fusable(a.M, a.P, a.gn_x, a.xsb, a.xsc, a.xsf) || (int64_t)a.gn_B * a.F * a.P != a.M))
