@@ -983,7 +983,7 @@ static TilePlan choose_tiles(int64_t m_tiles, int N, int K, int sms, int gran, i
             if (force_bn && bn != force_bn) continue;
             const double mma = 2.0 * bn, fill = (16384.0 + bn * 128.0 / cg) / 64.0;
             // + per-tile overhead; a CTA pair also pays for keeping two CTAs in lock-step (measured: pairs lose for K = 320)
-            const double per_tile = num_kb * (mma > fill ? mma : fill) + 1500.0 + 4.0 * bn + (cg == 2 ? 1500.0 : 0.0);
+            const double per_tile = num_kb * (mma > fill ? mma : fill) + 1500.0 + 4.0 * bn + (cg == 2 ? (num_kb <= 10 ? 2500.0 : 1500.0) : 0.0);
             const int64_t cluster_tiles = m_groups * (N / bn);
             const int64_t resident = sms / cg;
             const double cost = (double)ceil_div(cluster_tiles, resident) * per_tile;
@@ -993,7 +993,8 @@ static TilePlan choose_tiles(int64_t m_tiles, int N, int K, int sms, int gran, i
     // Wide pair tile: 256 x 320 per CTA pair as two N = 160 MMAs per k-step into one 320-column accumulator.  Per CTA and k-block
     // 16 KB of A + 20 KB of W feed 128 x 320 outputs (1.45x the arithmetic intensity of 256 x 160), but with a single accumulator the
     // epilogue (~16 cycles per column) is not hidden behind the next tile's MMAs: it pays for long K and few waves (ff_out).
-    if (allow_wide && N % 320 == 0 && sms % 2 == 0 && m_tiles >= 2 && force_cluster != 1 && (force_bn == 0 || force_bn == 320)) {
+    // (K >= 1280 only: measured at K = 640 -- to_out of the C = 640 level -- the exposed epilogue loses: 39.1 us against 34.4 us for 128 x 160 tiles)
+    if (allow_wide && num_kb >= 20 && N % 320 == 0 && sms % 2 == 0 && m_tiles >= 2 && force_cluster != 1 && (force_bn == 0 || force_bn == 320)) {
         const double mma = 2.0 * 320, fill = (16384.0 + 320 * 128.0 / 2) / 64.0;
         const double per_tile = num_kb * (mma > fill ? mma : fill) + 3000.0 + 20.0 * 320;
         const double cost = (double)ceil_div(ceil_div(m_tiles, 2) * (N / 320), (int64_t)(sms / 2)) * per_tile;
