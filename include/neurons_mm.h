@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define NMM_ABI_VERSION 2
+#define NMM_ABI_VERSION 3
 #if defined(__GNUC__)
 #define NMM_API __attribute__((visibility("default")))
 #else
@@ -144,7 +144,7 @@ NMM_API uint64_t nmm_launch_count(void);
  * launch with CUDA events on the launch stream (eager launches only; launches inside a stream capture are skipped).
  * nmm_profile_end synchronises on the recorded events and fills one entry per kernel (NMM_PROFILE_KERNELS entries):
  * launches, summed device ms, and the summed ALGORITHMIC flops / bytes of those launches. */
-#define NMM_PROFILE_KERNELS 8
+#define NMM_PROFILE_KERNELS 12
 typedef struct nmm_kernel_profile {
     const char *name;
     uint64_t launches;
@@ -252,6 +252,61 @@ NMM_API int nmm_qkv_attention(const nmm_shape *s, const void *tokens, const void
  * M = s->batch*frames*height*width is implied by `s` for NMM_EPI_OUTPUT; otherwise M is explicit. */
 NMM_API int nmm_linear(int32_t dtype, int32_t epilogue, int64_t M, int32_t N, int32_t K, const void *A, const void *W,
                const float *bias, float *h, void *out, const nmm_shape *s, const void *x, void *y, void *stream);
+
+/* ---- spatial transformer: the neighbour of the motion module inside every CrossAttn block ------------------------
+ * Replaces Transformer3DModel.forward, /root/reference/animatediff/models/attention.py:95-148 (-> BasicTransformerBlock.forward
+ * :258-300; CrossAttention / FeedForward / GEGLU arithmetic: motion_module_new.py:119-339,429-534), in the configuration every NEURONS
+ * UNet / ControlNet uses (unet_blocks.py:222-237 etc.): GroupNorm(32, eps 1e-6), 1x1-convolution proj_in / proj_out
+ * (use_linear_projection = False; a Linear [C, C] weight is accepted as well -- same GEMM), LayerNorm norm1/2/3, attn1 = self-attention
+ * over the H*W positions of each frame, attn2 = cross-attention onto encoder_hidden_states [b, ctx_len, ctx_dim] (shared by the frames
+ * of a clip, attention.py:101), GEGLU feed-forward, no attention bias / mask, no cross-frame or temporal attention inside the block.
+ * Called from unet_blocks.py:273,409,509,752 immediately BEFORE the motion module of the same block; y has the [B, F, C, H, W]
+ * storage of attention.py:144, which is exactly what nmm_forward then takes as a view.                                              */
+typedef struct nmm_spatial_shape {
+    nmm_shape base;             /* batch, channels, frames, height, width, heads (attention_head_dim = channels / heads in {40, 80, 160}),
+                                   layers (num_layers), dtype (NMM_BF16 or NMM_F32), eps_gn, eps_ln, x / y strides;
+                                   attn_blocks, pos_enc, max_len, ln_fold are ignored                                                  */
+    int32_t ctx_len;            /* encoder_hidden_states tokens (77 CLIP tokens)                                                       */
+    int32_t ctx_dim;            /* cross_attention_dim (768)                                                                           */
+} nmm_spatial_shape;
+
+typedef struct nmm_spatial_layer_params {           /* transformer_blocks.L.* (attention.py:151-236)                                  */
+    const void *norm1_w, *norm1_b;                  /* norm1.{weight,bias}                         [C]                                */
+    const void *attn1_q, *attn1_k, *attn1_v;        /* attn1.to_{q,k,v}.weight                     [C,C]                              */
+    const void *attn1_out_w, *attn1_out_b;          /* attn1.to_out.0.{weight,bias}                [C,C],[C]                          */
+    const void *norm2_w, *norm2_b;                  /* norm2.{weight,bias}                         [C]                                */
+    const void *attn2_q;                            /* attn2.to_q.weight                           [C,C]                              */
+    const void *attn2_k, *attn2_v;                  /* attn2.to_{k,v}.weight                       [C,ctx_dim]                        */
+    const void *attn2_out_w, *attn2_out_b;          /* attn2.to_out.0.{weight,bias}                [C,C],[C]                          */
+    const void *norm3_w, *norm3_b;                  /* norm3.{weight,bias}                         [C]                                */
+    const void *ff_proj_w, *ff_proj_b;              /* ff.net.0.proj.{weight,bias}  (value | gate) [8C,C],[8C]                        */
+    const void *ff_out_w, *ff_out_b;                /* ff.net.2.{weight,bias}                      [C,4C],[C]                         */
+} nmm_spatial_layer_params;
+
+typedef struct nmm_spatial_params {
+    int32_t dtype;                                  /* NMM_F32 or NMM_BF16: element type of every tensor below                        */
+    const void *gn_w, *gn_b;                        /* norm.{weight,bias}                          [C]                                */
+    const void *proj_in_w, *proj_in_b;              /* proj_in.{weight,bias}                       [C,C(,1,1)],[C]                    */
+    nmm_spatial_layer_params layer[NMM_MAX_LAYERS];
+    const void *proj_out_w, *proj_out_b;            /* proj_out.{weight,bias}                      [C,C(,1,1)],[C]                    */
+} nmm_spatial_params;
+
+NMM_API int nmm_spatial_packed_params_bytes(const nmm_spatial_shape *s, size_t *out_bytes);
+NMM_API int nmm_spatial_workspace_bytes(const nmm_spatial_shape *s, size_t *out_bytes);
+NMM_API int nmm_spatial_pack_params(const nmm_spatial_shape *s, const nmm_spatial_params *src, void *packed, size_t packed_bytes, void *stream);
+/* y = Transformer3DModel(x, encoder_hidden_states).sample.  x, y: element type s->base.dtype with the strides in s->base (x is normally the
+ * contiguous "b c f h w" output of ResnetBlock3D; y [B,F,C,H,W] storage); encoder_hidden_states: contiguous [batch, ctx_len, ctx_dim] of the
+ * same element type.  Same ownership / stream / graph-capture rules as nmm_forward. */
+NMM_API int nmm_spatial_forward(const nmm_spatial_shape *s, const void *x, const void *encoder_hidden_states, void *y, const void *packed,
+                                size_t packed_bytes, void *workspace, size_t workspace_bytes, void *stream);
+/* softmax(q k^T / sqrt(head_dim)) v per (image, head), flash-style (scores never materialised): CrossAttention._attention,
+ * motion_module_new.py:258-287, with the head split / merge of :181-193 folded into the indexing.  q: `images` x [q_len rows] of
+ * heads * head_dim channels at the given row / image strides (elements); k, v: [kv_len rows] per kv image, kv image of q image i =
+ * i / kv_div (kv_div = frames for the text cross-attention, 1 for self-attention); o like q.  dtype NMM_BF16 (tensor cores; 16-byte
+ * aligned, strides % 8 == 0) or NMM_F32 (fp32 checker kernel).  head_dim in {40, 80, 160}. */
+NMM_API int nmm_spatial_attention(int32_t dtype, const void *q, const void *k, const void *v, void *o, int64_t q_row_stride, int64_t kv_row_stride,
+                                  int64_t o_row_stride, int64_t q_image_stride, int64_t kv_image_stride, int64_t o_image_stride, int32_t q_len,
+                                  int32_t kv_len, int32_t heads, int32_t head_dim, int32_t images, int32_t kv_div, void *stream);
 
 #ifdef __cplusplus
 }

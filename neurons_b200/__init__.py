@@ -6,6 +6,8 @@ Public surface (mirrors /root/reference/animatediff/models/motion_module.py):
     torch.ops.neurons_mm.forward                   the custom op (CUDA dispatch key only)
     InflatedGroupNorm, patch_group_norms           the per-frame GroupNorm of ResnetBlock3D either side of the module (resnet.py:21-29)
     patch(model, carry_stats=True)                 ... whose statistics then come from the motion module's last kernel (attach_sums / carried_sums)
+    Transformer3DModel, patch_spatial(model)      the spatial transformer that precedes the motion module in every CrossAttn block
+                                                   (attention.py:31-300): same kernels + a flash-style spatial attention
 The arithmetic lives in libneurons_mm.so (C ABI: include/neurons_mm.h), built by `python -m neurons_b200.build`.
 """
 from .lib import NmmError, launch_count, load as load_library          # noqa: F401
@@ -13,6 +15,9 @@ from .ops import ModuleConfig                                           # noqa: 
 from .motion_module import (VanillaTemporalModule, attach_sums, carried_sums, config_of, get_motion_module, invalidate,   # noqa: F401
                             motion_forward, patch, zero_module)
 from .resnet_norm import InflatedGroupNorm, patch_group_norms            # noqa: F401
+from .spatial_transformer import (SpatialConfig, Transformer3DModel, patch_spatial, spatial_attention, spatial_config_of,   # noqa: F401
+                                  spatial_forward)
 
 __all__ = ["VanillaTemporalModule", "get_motion_module", "patch", "invalidate", "motion_forward", "zero_module", "config_of",
-           "ModuleConfig", "NmmError", "launch_count", "load_library", "InflatedGroupNorm", "patch_group_norms", "attach_sums", "carried_sums"]
+           "ModuleConfig", "NmmError", "launch_count", "load_library", "InflatedGroupNorm", "patch_group_norms", "attach_sums", "carried_sums",
+           "SpatialConfig", "Transformer3DModel", "patch_spatial", "spatial_attention", "spatial_config_of", "spatial_forward"]

@@ -206,7 +206,7 @@ static int validate(const nmm_shape *s) {
     return NMM_OK;
 }
 
-static int device_check() {
+int device_check() {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) { cudaGetLastError(); return fail(NMM_ERR_DEVICE, "no CUDA device: %s", cudaGetErrorString(e)); }
@@ -441,6 +441,12 @@ static int linear(const Geo &g, const LinearArgs &a, cudaStream_t st) {
     }
     return g.dtype == NMM_BF16 ? launch_linear_tc(a, st) : launch_linear_simt(a, st);
 }
+int linear_dispatch(int dtype, const LinearArgs &a, cudaStream_t st) {
+    Geo g;
+    memset(&g, 0, sizeof(g));
+    g.dtype = dtype;
+    return linear(g, a, st);
+}
 
 }  // namespace nmm
 
@@ -475,8 +481,8 @@ int nmm_profile_end(nmm_kernel_profile *out, int32_t max_kernels) {
     g_prof.enabled = false;
     if (!out || max_kernels < K_COUNT) return fail(NMM_ERR_BAD_ARG, "nmm_profile_end needs room for %d kernels", (int)K_COUNT);
     static const char *names[K_COUNT] = {"gn_stats", "gn_tokens", "layernorm_pe", "temporal_attention", "linear_fp32_fma",
-                                         "linear_bf16_tcgen05", "pack_params", "fused_module_tcgen05"};
-    for (int k = 0; k < K_COUNT; k++) { out[k].name = names[k]; out[k].launches = 0; out[k].total_ms = 0; out[k].flops = 0; out[k].bytes = 0; }
+                                         "linear_bf16_tcgen05", "pack_params", "fused_module_tcgen05", "spatial_attention"};
+    for (int k = 0; k < max_kernels; k++) { out[k].name = k < K_COUNT ? names[k] : "unused"; out[k].launches = 0; out[k].total_ms = 0; out[k].flops = 0; out[k].bytes = 0; }
     int rc = NMM_OK;
     for (auto &r : g_prof.rec) {
         float ms = 0.f;

@@ -35,7 +35,7 @@ extern std::atomic<uint64_t> g_launches;
 int64_t opt(int option);
 
 // ---- optional per-kernel device timing (bench.py roofline): CUDA events around every launch, on the launch stream ----
-enum KernelId { K_GN_STATS = 0, K_GN_TOKENS, K_LAYERNORM, K_ATTENTION, K_LINEAR_SIMT, K_LINEAR_TC, K_PACK, K_FUSED_MODULE, K_COUNT };
+enum KernelId { K_GN_STATS = 0, K_GN_TOKENS, K_LAYERNORM, K_ATTENTION, K_LINEAR_SIMT, K_LINEAR_TC, K_PACK, K_FUSED_MODULE, K_SPATIAL_ATTN, K_COUNT };
 struct ProfScope {          // records start on construction, stop on destruction; no-op unless profiling is enabled
     int slot;
     cudaStream_t st;
@@ -257,6 +257,19 @@ int launch_layernorm_pe(const Geo &g, const nmm_shape *s, const float *h, const 
 // attention
 int launch_temporal_attention(const Geo &g, const void *qkv, void *ctx, cudaStream_t st);
 
+// spatial (long-sequence, flash-style) attention of the UNet's Transformer3DModel blocks: spatial_attention.cu
+struct FlashArgs {
+    const void *q, *k, *v;   // rows of heads * dh channels (a column slice of a projection output); head h = columns [h * dh, (h + 1) * dh)
+    void *o;
+    int64_t q_rs, kv_rs, o_rs;      // row strides (elements)
+    int64_t q_bs, kv_bs, o_bs;      // image strides (elements); the k / v image of q image i is i / kv_div
+    int Lq, Lkv, heads, images, kv_div, dh;
+    int dtype;                      // NMM_BF16 (mma.sync flash kernel) or NMM_F32 (fp32 checker kernel)
+    float scale, scale_log2e;       // dh^-1/2 and dh^-1/2 * log2(e)
+};
+int launch_spatial_attention(const FlashArgs &a, cudaStream_t st);
+int device_check();
+
 // GEMM + epilogue
 // Internal epilogue (not part of the C ABI enum): the QKV projection with the temporal attention fused into its epilogue --
 // the tile's q | k | v never leave the SM (gemm_tcgen05.cu, "QKV + attention").
@@ -347,6 +360,7 @@ bool fused_module_eligible(const Geo &g, const nmm_shape *s, const void *x);
 int launch_fused_module(const FusedArgs &a, cudaStream_t st);
 int launch_linear_simt(const LinearArgs &a, cudaStream_t st);     // fp32
 int launch_linear_tc(const LinearArgs &a, cudaStream_t st);       // bf16 tcgen05
+int linear_dispatch(int dtype, const LinearArgs &a, cudaStream_t st);     // bf16 -> tcgen05, NMM_F32X3 -> tcgen05 3 x bf16, NMM_F32 -> FMA
 // parameter packing
 int launch_convert_rows(const void *src, int src_dtype, void *dst, int dst_dtype, int64_t rows, int64_t cols,
                         int interleave_half /*0 or rows/2*/, cudaStream_t st);

@@ -51,16 +51,32 @@ class Params(C.Structure):
                 ("proj_out_b", C.c_void_p)]
 
 
+class SpatialShape(C.Structure):
+    _fields_ = [("base", Shape), ("ctx_len", C.c_int32), ("ctx_dim", C.c_int32)]
+
+
+class SpatialLayerParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "norm1_w", "norm1_b", "attn1_q", "attn1_k", "attn1_v", "attn1_out_w", "attn1_out_b", "norm2_w", "norm2_b", "attn2_q", "attn2_k",
+        "attn2_v", "attn2_out_w", "attn2_out_b", "norm3_w", "norm3_b", "ff_proj_w", "ff_proj_b", "ff_out_w", "ff_out_b")]
+
+
+class SpatialParams(C.Structure):
+    _fields_ = [("dtype", C.c_int32), ("gn_w", C.c_void_p), ("gn_b", C.c_void_p), ("proj_in_w", C.c_void_p), ("proj_in_b", C.c_void_p),
+                ("layer", SpatialLayerParams * NMM_MAX_LAYERS), ("proj_out_w", C.c_void_p), ("proj_out_b", C.c_void_p)]
+
+
 class KernelProfile(C.Structure):
     _fields_ = [("name", C.c_char_p), ("launches", C.c_uint64), ("total_ms", C.c_double), ("flops", C.c_double),
                 ("bytes", C.c_double)]
 
 
-PROFILE_KERNELS = 8
-ABI_VERSION = 2
+PROFILE_KERNELS = 12
+ABI_VERSION = 3
 
 # name -> (restype, argtypes); must list every NMM_API symbol of include/neurons_mm.h (tests/test_abi.py checks)
 _SP = C.POINTER(Shape)
+_SSP = C.POINTER(SpatialShape)
 SIGNATURES = {
     "nmm_abi_version": (C.c_int, []),
     "nmm_last_error": (C.c_char_p, []),
@@ -93,6 +109,12 @@ SIGNATURES = {
     "nmm_qkv_attention": (C.c_int, [_SP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nmm_linear": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                              C.c_void_p, C.c_void_p, _SP, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nmm_spatial_packed_params_bytes": (C.c_int, [_SSP, C.POINTER(C.c_size_t)]),
+    "nmm_spatial_workspace_bytes": (C.c_int, [_SSP, C.POINTER(C.c_size_t)]),
+    "nmm_spatial_pack_params": (C.c_int, [_SSP, C.POINTER(SpatialParams), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "nmm_spatial_forward": (C.c_int, [_SSP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "nmm_spatial_attention": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                        C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
 }
 
 _lib = None

@@ -227,24 +227,34 @@ class _Engine:
     def _checksum(tensors):
         return float(sum(t.detach().double().abs().sum() for t in tensors.values()))
 
+    # hooks (the spatial transformer's engine, spatial_transformer.py, overrides these three)
+    def _tensors_of(self, module: nn.Module):
+        return _param_tensors(module)
+
+    def _config_of(self, module: nn.Module):
+        return config_of(module)
+
+    def _pack(self, cfg, dev_tensors, x: torch.Tensor):
+        return ops.pack_params(cfg, dev_tensors, x.dtype, x.device)
+
     def get(self, module: nn.Module, x: torch.Tensor):
         if self.tensors is None:
-            self.tensors = _param_tensors(module)
+            self.tensors = self._tensors_of(module)
         tensors = self.tensors
         key = self._key(x, tensors)
         if key != self.key:
-            self.tensors = tensors = _param_tensors(module)      # re-scan the tree (parameters may have been replaced)
+            self.tensors = tensors = self._tensors_of(module)      # re-scan the tree (parameters may have been replaced)
             key = self._key(x, tensors)
             if torch.cuda.is_current_stream_capturing():
                 raise RuntimeError("neurons_b200: the module's parameters must be packed before CUDA-graph capture: run one forward "
                                    "outside the capture first (packing inside a capture would bake stale weights into the graph)")
-            self.cfg = config_of(module)
+            self.cfg = self._config_of(module)
             dev_tensors = {}
             for k, t in tensors.items():
                 if t.device != x.device:
                     raise RuntimeError(f"neurons_b200: parameter '{k}' is on {t.device}, input on {x.device}")
                 dev_tensors[k] = t.reshape(t.shape[-2:]) if k.endswith("pos_encoder.pe") else t
-            self.packed = ops.pack_params(self.cfg, dev_tensors, x.dtype, x.device)
+            self.packed = self._pack(self.cfg, dev_tensors, x)
             # once per (module, weights): wait for the packing kernels, so that the packed buffer may be used from ANY stream afterwards
             # (another stream, or a CUDA-graph capture, must not depend on un-captured work of the stream that packed)
             torch.cuda.current_stream(x.device).synchronize()

@@ -24,7 +24,7 @@ def test_header_symbols_all_exported_and_bound(built_library):
     for s in syms:
         assert hasattr(built_library, s), f"{s} declared in neurons_mm.h but not exported"
     assert sorted(nlib.SIGNATURES.keys()) == syms, "ctypes binding and header disagree"
-    assert built_library.nmm_abi_version() == 2
+    assert built_library.nmm_abi_version() == 3
 
 
 def _shape(**kw):
