@@ -319,6 +319,74 @@ def gpu_eager_baseline(dev, steps: int = 3):
     return out
 
 
+def spatial_leg(nb, nlib, dev, steps: int = 5, eager: bool = True):
+    """SURVEY 8(f) N3, the motion module's neighbour: the 16 spatial Transformer3DModel calls of the SAME UNet step (config 2: CFG batch 2,
+    8 frames, 64 x 64 latent, bf16; 2 down + 3 up calls per CrossAttn level + the mid block, unet.py:157-258), device-resident, with the
+    per-kernel split (second pass, CUDA-event pairs) and stock torch eager on the same GPU for the same calls.  Secondary metric."""
+    from oracle import spatial_oracle as so          # flop count + the eager anchor's op sequence only; never the product path
+    levels = [(320, LATENT, 5), (640, LATENT // 2, 5), (1280, LATENT // 4, 5), (1280, LATENT // 8, 1)]
+    mods, xs, cfgs = [], [], []
+    ctx = torch.randn(BATCH, 77, 768, device=dev, dtype=torch.bfloat16)
+    flops = 0.0
+    for C, side, n in levels:
+        cfg = so.SpatialConfig(C, 8, 1, 768, True)
+        for _ in range(n):
+            with torch.device(dev):
+                m = nb.Transformer3DModel(num_attention_heads=8, attention_head_dim=C // 8, in_channels=C, cross_attention_dim=768,
+                                          unet_use_cross_frame_attention=False, unet_use_temporal_attention=False)
+            mods.append(m.to(torch.bfloat16).eval())
+            xs.append(torch.randn(BATCH, C, FRAMES, side, side, device=dev, dtype=torch.bfloat16))
+            cfgs.append(cfg)
+            flops += so.flops(cfg, BATCH, FRAMES, side * side, 77)
+
+    def step():
+        for m, x in zip(mods, xs):
+            m(x, encoder_hidden_states=ctx)
+
+    def timed(fn, k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / k
+    with torch.no_grad():
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        n0 = nb.launch_count()
+        ms = timed(step, steps)
+        launches = nb.launch_count() - n0
+        nlib.profile_begin()
+        for _ in range(steps):
+            step()
+        prof = nlib.profile_end()
+        out = {"workload": "the 16 spatial Transformer3DModel calls of the same UNet step (GroupNorm, 1x1 proj_in, self-attention over h*w, "
+                           "77-token text cross-attention, GEGLU FF, proj_out + residual); inputs larger than L2 (16 distinct activations + weights)",
+               "ms_per_step": ms, "tflops": flops / (ms * 1e-3) / 1e12, "flops_per_step": flops, "gpu_launches": int(launches),
+               "kernels": {k: {"launches": v["launches"], "ms_per_step": v["total_ms"] / steps,
+                               "tflops": v["flops"] / (v["total_ms"] * 1e-3) / 1e12 if v["total_ms"] > 0 and v["flops"] > 0 else None}
+                           for k, v in prof.items() if v["launches"]}}
+        if eager:
+            try:
+                prm = [{k: v.detach() for k, v in m.state_dict().items()} for m in mods]
+
+                def eager_step():
+                    for p, x, cfg in zip(prm, xs, cfgs):
+                        so.forward_reference_order(p, x, ctx, cfg)
+                eager_step()
+                torch.cuda.synchronize()
+                ems = timed(eager_step, 2)
+                out["gpu_eager_baseline"] = {"ms_per_step": ems, "tflops": flops / (ems * 1e-3) / 1e12,
+                                             "note": "the reference's op sequence (materialised scores) under stock torch eager, bf16, same GPU"}
+            except Exception as e:
+                out["gpu_eager_baseline"] = {"error": repr(e)[:200]}
+    del mods, xs
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_reference_arm(args, rank):
     """--impl reference: the reference's own CPU implementation of the path (oracle port; the reference is pure Python
     and ships no installable package), all host threads, same metric/config.  Rank 0 only."""
@@ -359,6 +427,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the host-CPU baseline leg")
     ap.add_argument("--no-clips", action="store_true", help="skip the 25-step clip loop (secondary metric)")
     ap.add_argument("--no-eager", action="store_true", help="skip the stock-torch-eager GPU anchor")
+    ap.add_argument("--no-spatial", action="store_true", help="skip the spatial-transformer leg (SURVEY 8(f) N3, secondary metric)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -494,6 +563,12 @@ def main():
             eager = gpu_eager_baseline(dev)
         except Exception as e:        # a reported anchor only: never fail the bench line over it
             eager = {"error": repr(e)[:200]}
+    spatial = None
+    if rank == 0 and not args.no_spatial:
+        try:
+            spatial = spatial_leg(nb, nlib, dev, eager=not args.no_eager)
+        except Exception as e:        # secondary metric: never fail the bench line over it
+            spatial = {"error": repr(e)[:200]}
     clip_ms, clip_flops = (0.0, 0.0) if args.no_clips else clip_loop(nb, wl, dev)
     clip4_ms, clip4_flops = (0.0, 0.0) if args.no_clips else clip_loop(nb, wl, dev, clips=2, clip_batch=4)       # BASELINE configs[3]: 4 clips per GPU
     ce_secs, ce_n, ce_h2d, ce_d2h = (0.0, 0, 0, 0) if args.no_clips else clip_e2e(nb, wl, dev, rank, world)
@@ -572,6 +647,7 @@ def main():
                                "workload": "BASELINE configs[3] shape: the same loop with 4 clips per GPU (CFG batch 8)"},
                     "workload": "BASELINE configs[2] shape: 25 DDIM steps x (20 UNet + 8 SparseCtrl ControlNet motion-module calls), CFG batch 2, "
                                 "16 frames, 32x32 latent, bf16; one step captured in a CUDA graph; the rest of the UNet is outside the path"},
+                "spatial_transformer": spatial,
                 "flops_per_step": flops_step}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -106,7 +106,7 @@ def _batch_to_heads(t: torch.Tensor, heads: int) -> torch.Tensor:
 
 def _attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float) -> torch.Tensor:
     """CrossAttention._attention, motion_module_new.py:258-287 (no mask; softmax in the input dtype)."""
-    scores = torch.baddbmm(torch.empty(q.shape[0], q.shape[1], k.shape[1], dtype=q.dtype), q, k.transpose(-1, -2), beta=0, alpha=scale)
+    scores = torch.baddbmm(torch.empty(q.shape[0], q.shape[1], k.shape[1], dtype=q.dtype, device=q.device), q, k.transpose(-1, -2), beta=0, alpha=scale)
     probs = scores.softmax(dim=-1)
     return torch.bmm(probs, v)
 
