@@ -45,6 +45,7 @@ void init_opts() {
     g_opts[NMM_OPT_ATTN_VARIANT] = getenv("NMM_ATTN_SIMT") ? 2 : getenv("NMM_ATTN_GENERIC") ? 1 : 0;
     g_opts[NMM_OPT_FUSED_Y_STATS] = num("NMM_FUSED_Y_STATS");
     g_opts[NMM_OPT_FUSED_CLUSTER] = num("NMM_FUSED_CLUSTER");
+    g_opts[NMM_OPT_SPATIAL_ATTN] = num("NMM_SPATIAL_ATTN");
 }
 }  // namespace
 int64_t opt(int option) {

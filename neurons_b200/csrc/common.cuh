@@ -268,6 +268,8 @@ struct FlashArgs {
     float scale, scale_log2e;       // dh^-1/2 and dh^-1/2 * log2(e)
 };
 int launch_spatial_attention(const FlashArgs &a, cudaStream_t st);
+bool spatial_attention_tc_eligible(const FlashArgs &a);                            // spatial_attention_tc.cu (tcgen05 / TMEM / TMA)
+int launch_spatial_attention_tc(const FlashArgs &a, int swap_v, cudaStream_t st);
 int device_check();
 
 // GEMM + epilogue

@@ -229,6 +229,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr)
         : "memory");
 }
+// registers -> TMEM, same shape as tmem_ld16 (lane i of the warp writes TMEM lane base+i, 16 consecutive columns)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        :
+        : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+          "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- UMMA descriptors -----------------------------------------------------------------------------
@@ -271,6 +281,7 @@ __device__ __forceinline__ uint64_t umma_smem_desc_interleave(uint32_t smem_addr
     return d;
 }
 constexpr uint32_t UMMA_IDESC_A_MN_MAJOR = 1u << 15;     // instruction descriptor: A operand is M-major
+constexpr uint32_t UMMA_IDESC_B_MN_MAJOR = 1u << 16;     // instruction descriptor: B operand is N-major
 // Instruction descriptor, kind::f16: D fp32 (c_format=1 @4), A/B bf16 (format 1 @7, @10), both K-major (bits 15,16 = 0),
 // N >> 3 @17, M >> 4 @24.
 __host__ __device__ inline uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {

@@ -21,7 +21,8 @@
 namespace nmm {
 
 constexpr int FA_BM = 128;      // queries per CTA
-constexpr int FA_BN = 64;       // keys per tile
+constexpr int FA_BN = 64;       // keys per compute tile (S fragment = 16 x 64 per warp)
+constexpr int FA_ST = 128;      // keys per pipeline stage = two compute tiles per __syncthreads (barrier stalls were 11 % of issue slots at 64)
 constexpr int FA_THREADS = 256;
 
 template <int DH>
@@ -29,7 +30,7 @@ struct FaCfg {
     static constexpr int PITCH = ((DH / 8) % 2 == 1) ? DH : DH + 8;     // elements
     static constexpr int CH = DH / 8;                                   // 16-byte chunks per row
     static constexpr int Q_BYTES = FA_BM * PITCH * 2;
-    static constexpr int KV_BYTES = FA_BN * PITCH * 2;
+    static constexpr int KV_BYTES = FA_ST * PITCH * 2;
     static constexpr int SMEM = Q_BYTES + 4 * KV_BYTES;                 // Q | K stage 0, 1 | V stage 0, 1
     static constexpr int KS16 = DH / 16;                                // full k16 steps of S = Q K^T
     static constexpr bool TAIL8 = (DH % 16) == 8;
@@ -41,6 +42,13 @@ __device__ __forceinline__ void cp_async16(uint32_t saddr, const void *g, bool v
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(saddr), "l"(g), "r"(sz) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// 2^x on the SFU, one instruction (exp2f() adds a denormal-range rescue: FSETP + FMUL + FMUL per value); flush-to-zero is what a
+// softmax weight below 2^-126 should do anyway.  ex2(-inf) = +0.
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <int DH>
@@ -69,9 +77,9 @@ __global__ void __launch_bounds__(FA_THREADS, DH <= 80 ? 2 : 1) spatial_attentio
     cp_async_commit();
     auto load_kv = [&](int t, int stage) {
         const uint32_t sk = sk0 + stage * Cfg::KV_BYTES, sv = sv0 + stage * Cfg::KV_BYTES;
-        for (int i = tid; i < FA_BN * CH; i += FA_THREADS) {
+        for (int i = tid; i < FA_ST * CH; i += FA_THREADS) {
             const int r = i / CH, c = i - r * CH;
-            const int key = t * FA_BN + r;
+            const int key = t * FA_ST + r;
             const bool ok = key < Lkv;
             const int64_t off = (int64_t)(ok ? key : Lkv - 1) * a.kv_rs + c * 8;
             const uint32_t so = (uint32_t)(r * PITCH + c * 8) * 2;
@@ -102,7 +110,7 @@ __global__ void __launch_bounds__(FA_THREADS, DH <= 80 ? 2 : 1) spatial_attentio
     for (int n = 0; n < NT; n++) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
     const float sl = a.scale_log2e;
-    const int nt = (Lkv + FA_BN - 1) / FA_BN;
+    const int nt = (Lkv + FA_ST - 1) / FA_ST;
     const uint32_t k_lane = (uint32_t)((lane & 7) * PITCH + 8 * (lane >> 3)) * 2;
     const uint32_t v_lane = (uint32_t)(((lane & 7) + 8 * ((lane >> 3) & 1)) * PITCH + 8 * (lane >> 4)) * 2;
 
@@ -111,7 +119,12 @@ __global__ void __launch_bounds__(FA_THREADS, DH <= 80 ? 2 : 1) spatial_attentio
         __syncthreads();                       // tile t landed for everyone; everyone is done with tile t - 1 (the other stage)
         if (t + 1 < nt) load_kv(t + 1, (t + 1) & 1);
         cp_async_commit();
-        const uint32_t sk = sk0 + (t & 1) * Cfg::KV_BYTES + k_lane, sv = sv0 + (t & 1) * Cfg::KV_BYTES + v_lane;
+#pragma unroll 1
+        for (int half = 0; half < FA_ST / FA_BN; half++) {
+        const int key0 = t * FA_ST + half * FA_BN;
+        if (key0 >= Lkv) break;
+        const uint32_t sk = sk0 + (t & 1) * Cfg::KV_BYTES + (uint32_t)(half * FA_BN * PITCH) * 2 + k_lane;
+        const uint32_t sv = sv0 + (t & 1) * Cfg::KV_BYTES + (uint32_t)(half * FA_BN * PITCH) * 2 + v_lane;
 
         // ---- S = Q K^T (16 x 64 per warp) ----
         float s[8][4];
@@ -138,8 +151,8 @@ __global__ void __launch_bounds__(FA_THREADS, DH <= 80 ? 2 : 1) spatial_attentio
                 mma_k8(s[j], qt[0], qt[1], b0);
             }
         }
-        if (t == nt - 1 && (Lkv & (FA_BN - 1)) != 0) {      // keys past the end of a ragged last tile
-            const int kbase = t * FA_BN + 2 * (lane & 3);
+        if (key0 + FA_BN > Lkv) {      // keys past the end of a ragged last tile
+            const int kbase = key0 + 2 * (lane & 3);
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 if (kbase + 8 * j >= Lkv) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
@@ -155,17 +168,18 @@ __global__ void __launch_bounds__(FA_THREADS, DH <= 80 ? 2 : 1) spatial_attentio
         }
         mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
         mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-        const float al0 = exp2f((m0 - mx0) * sl), al1 = exp2f((m1 - mx1) * sl);
+        const float al0 = fast_exp2((m0 - mx0) * sl), al1 = fast_exp2((m1 - mx1) * sl);
         m0 = mx0; m1 = mx1;
         const float ms0 = mx0 * sl, ms1 = mx1 * sl;
         float r0 = 0.f, r1 = 0.f;
         uint32_t p[8][2];
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            const float e0 = exp2f(fmaf(s[j][0], sl, -ms0)), e1 = exp2f(fmaf(s[j][1], sl, -ms0));
-            const float e2 = exp2f(fmaf(s[j][2], sl, -ms1)), e3 = exp2f(fmaf(s[j][3], sl, -ms1));
-            r0 += e0 + e1; r1 += e2 + e3;
+            const float e0 = fast_exp2(fmaf(s[j][0], sl, -ms0)), e1 = fast_exp2(fmaf(s[j][1], sl, -ms0));
+            const float e2 = fast_exp2(fmaf(s[j][2], sl, -ms1)), e3 = fast_exp2(fmaf(s[j][3], sl, -ms1));
             p[j][0] = pack_bf16x2(e0, e1); p[j][1] = pack_bf16x2(e2, e3);
+            // the row sum adds the ROUNDED weights: O / l is then an exact weighted mean with the weights the tensor core used
+            r0 += bf16_lo(p[j][0]) + bf16_hi(p[j][0]); r1 += bf16_lo(p[j][1]) + bf16_hi(p[j][1]);
         }
         l0 = fmaf(l0, al0, r0); l1 = fmaf(l1, al1, r1);       // per-thread partial sums; the quad is reduced once at the end
 #pragma unroll
@@ -188,6 +202,7 @@ __global__ void __launch_bounds__(FA_THREADS, DH <= 80 ? 2 : 1) spatial_attentio
                 mma_k16(o[NT - 1], a0, a1, a2, a3, b0, b1);
             }
         }
+        }      // half
     }
     // ---- normalise, stage the warp's 16 x d_h block in its own (dead) Q rows, 16-byte stores ----
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
@@ -288,6 +303,8 @@ static int launch_flash_f32_t(const FlashArgs &a, cudaStream_t st) {
 int launch_spatial_attention(const FlashArgs &a, cudaStream_t st) {
     if (a.Lq <= 0 || a.Lkv <= 0 || a.images <= 0 || a.heads <= 0 || a.kv_div <= 0) return fail(NMM_ERR_BAD_ARG, "spatial attention: non-positive size");
     if (a.images > 65535 || a.heads > 65535) return fail(NMM_ERR_UNSUPPORTED, "spatial attention: more than 65535 images / heads");
+    const int variant = (int)opt(NMM_OPT_SPATIAL_ATTN);
+    if (variant != 1 && spatial_attention_tc_eligible(a)) return launch_spatial_attention_tc(a, variant == 2 ? 1 : 0, st);
     if (a.dtype == NMM_BF16) {
         if (!aligned(a.q, 16) || !aligned(a.k, 16) || !aligned(a.v, 16) || !aligned(a.o, 16) || a.q_rs % 8 || a.kv_rs % 8 || a.o_rs % 8 || a.q_bs % 8 ||
             a.kv_bs % 8 || a.o_bs % 8)

@@ -159,7 +159,7 @@ def profile_end():
 
 # nmm_option (include/neurons_mm.h)
 (OPT_FUSED_MODULE, OPT_GN_FUSE, OPT_ATTN_FUSE, OPT_WIDE_TILE, OPT_GEMM_CLUSTER, OPT_GEMM_BLOCK_N, OPT_CHUNK_TOKENS, OPT_ATTN_VARIANT, OPT_FUSED_Y_STATS,
- OPT_FUSED_CLUSTER) = range(10)
+ OPT_FUSED_CLUSTER, OPT_SPATIAL_ATTN) = range(11)
 
 
 def set_option(option: int, value: int):
