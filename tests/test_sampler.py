@@ -134,3 +134,51 @@ def test_denoise_fused_step_matches_unfused_and_keeps_input():
     b = sampler.denoise(den, lat0, None, sch, 25, 8.5, fused_step=True)
     assert torch.equal(lat0, keep)
     assert (a - b).abs().max().item() <= 1e-5 * a.abs().max().item()
+
+
+def _reference_next_step():
+    """The reference's own DDIM update, animatediff/utils/util.py:211-222 (`next_step`, the inversion direction of the same eta = 0
+    update), compiled from the reference file where it lies (util.py itself imports packages this image lacks).  None off-box."""
+    import ast
+    from oracle import ref_shim
+    root = ref_shim.reference_root()
+    if root is None:
+        return None
+    import os
+    path = os.path.join(root, "animatediff", "utils", "util.py")
+    if not os.path.isfile(path):
+        return None
+    tree = ast.parse(open(path).read())
+    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "next_step")
+    import numpy as np
+    from typing import Union
+    ns = {"torch": torch, "np": np, "Union": Union}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)
+    return ns["next_step"]
+
+
+@pytest.mark.skipif(_reference_next_step() is None, reason="reference tree not mounted")
+def test_ddim_update_pinned_to_reference_next_step():
+    """PIN for the scheduler piece of row N2: diffusers' DDIMScheduler is not installable here, but the reference carries the same
+    eta = 0 update in its own tree (util.py:211-222, used for DDIM inversion): x(t - d) -> x(t) with the alphas_cumprod indexing and
+    the final_alpha_cumprod convention of the scheduler object it is handed.  Our forward step t -> t - d followed by the reference's
+    step t - d -> t with the same epsilon must return the input, for every timestep of the 25-step schedule (incl. the last, which
+    uses final_alpha_cumprod), and the reference step run on OUR schedule object must equal our formula with the alphas exchanged."""
+    from types import SimpleNamespace
+    next_step = _reference_next_step()
+    sch = sampler.DDIMSchedule()
+    n = 25
+    fake = SimpleNamespace(config=SimpleNamespace(num_train_timesteps=sch.num_train_timesteps), num_inference_steps=n,
+                           alphas_cumprod=sch.alphas_cumprod, final_alpha_cumprod=torch.tensor(sch.final_alpha_cumprod, dtype=torch.float64))
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 4, 3, 5, 5, generator=g, dtype=torch.float64)
+    eps = torch.randn(2, 4, 3, 5, 5, generator=g, dtype=torch.float64)
+    ts = sch.timesteps(n)
+    assert ts[0] == 961 and ts[-1] == 1 and len(ts) == n
+    for t in ts:
+        x_prev = sch.step(eps, t, x, n)
+        back = next_step(eps, t, x_prev, fake)                       # reference: (t - 40) -> t
+        assert (back - x).abs().max().item() <= 1e-12, t
+        a_t, a_prev = sch.alphas(t, n)
+        direct = (a_t ** 0.5) * (x - ((1 - a_prev) ** 0.5) * eps) / (a_prev ** 0.5) + ((1 - a_t) ** 0.5) * eps
+        assert (next_step(eps, t, x, fake) - direct).abs().max().item() <= 1e-12, t
