@@ -289,7 +289,7 @@ def _is_spatial_transformer(m: nn.Module) -> bool:
 
 def patch_spatial(model: nn.Module) -> int:
     """Rebind `forward` on every Transformer3DModel inside `model` (reference instances included).  Returns the number patched
-    (16 in the SD-1.5 UNet3DConditionModel, 6 in SparseControlNetModel); unsupported configurations raise here."""
+    (16 in the SD-1.5 UNet3DConditionModel, 7 in SparseControlNetModel); unsupported configurations raise here."""
     n = 0
     for m in model.modules():
         if _is_spatial_transformer(m):
