@@ -269,7 +269,7 @@ struct FlashArgs {
 };
 int launch_spatial_attention(const FlashArgs &a, cudaStream_t st);
 bool spatial_attention_tc_eligible(const FlashArgs &a);                            // spatial_attention_tc.cu (tcgen05 / TMEM / TMA)
-int launch_spatial_attention_tc(const FlashArgs &a, int swap_v, cudaStream_t st);
+int launch_spatial_attention_tc(const FlashArgs &a, int variant, cudaStream_t st);
 int device_check();
 
 // GEMM + epilogue

@@ -304,7 +304,7 @@ int launch_spatial_attention(const FlashArgs &a, cudaStream_t st) {
     if (a.Lq <= 0 || a.Lkv <= 0 || a.images <= 0 || a.heads <= 0 || a.kv_div <= 0) return fail(NMM_ERR_BAD_ARG, "spatial attention: non-positive size");
     if (a.images > 65535 || a.heads > 65535) return fail(NMM_ERR_UNSUPPORTED, "spatial attention: more than 65535 images / heads");
     const int variant = (int)opt(NMM_OPT_SPATIAL_ATTN);
-    if (variant != 1 && spatial_attention_tc_eligible(a)) return launch_spatial_attention_tc(a, variant == 2 ? 1 : 0, st);
+    if (variant != 1 && spatial_attention_tc_eligible(a)) return launch_spatial_attention_tc(a, variant, st);
     if (a.dtype == NMM_BF16) {
         if (!aligned(a.q, 16) || !aligned(a.k, 16) || !aligned(a.v, 16) || !aligned(a.o, 16) || a.q_rs % 8 || a.kv_rs % 8 || a.o_rs % 8 || a.q_bs % 8 ||
             a.kv_bs % 8 || a.o_bs % 8)
@@ -316,6 +316,11 @@ int launch_spatial_attention(const FlashArgs &a, cudaStream_t st) {
             default: break;
         }
     } else if (a.dtype == NMM_F32) {
+        // the fp32 kernel is the CHECKER (one warp per query, keys streamed from L2): fine at test sizes, minutes at the 64 x 64 level.
+        // Refuse instead of appearing to hang; bf16 is the production mode of the spatial transformer.
+        if ((double)a.Lq * a.Lkv * a.images * a.heads > 1.1e9)
+            return fail(NMM_ERR_UNSUPPORTED, "fp32 spatial attention is a checker for small shapes (%d x %d keys x %d images x %d heads is too large): "
+                        "run the spatial transformer in bf16", a.Lq, a.Lkv, a.images, a.heads);
         switch (a.dh) {
             case 40: return launch_flash_f32_t<40>(a, st);
             case 80: return launch_flash_f32_t<80>(a, st);

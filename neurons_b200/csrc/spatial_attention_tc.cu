@@ -27,7 +27,6 @@ namespace nmm {
 
 constexpr int FT_BM = 128;          // queries per CTA
 constexpr int FT_BN = 128;          // keys per tile
-constexpr int FT_THREADS = 192;
 constexpr int FT_TMEM_COLS = 256;
 constexpr int FT_O_COL = 128;       // O accumulator columns [128, 128 + DHP)
 constexpr uint32_t FT_CHUNK = FT_BN * 16;      // bytes of one 16-byte chunk column of a 128-row operand tile
@@ -44,7 +43,8 @@ struct FtCfg {
     static constexpr uint32_t P_BYTES = (FT_BN / 8) * FT_CHUNK;
     static constexpr uint32_t OFF_Q = 0, OFF_K = TILE_BYTES, OFF_V = OFF_K + NS * TILE_BYTES, OFF_P = OFF_V + NS * VTILE_BYTES;
     static constexpr uint32_t OFF_BAR = OFF_P + P_BYTES;
-    static constexpr uint32_t SMEM = OFF_BAR + 256 + 128;   // + alignment slack
+    static constexpr uint32_t OFF_MAX = OFF_BAR + 256;      // SP == 2: row-max exchange between the two threads of a row, [2 parities][2 halves][128] floats
+    static constexpr uint32_t SMEM = OFF_MAX + 2048 + 128;  // + alignment slack
 };
 
 struct FtParams {
@@ -52,7 +52,11 @@ struct FtParams {
     int64_t o_rs, o_bs;
     int Lq, Lkv;
     float scale_log2e;
-    int swap_v_desc;            // development: LBO / SBO of the N-major V descriptor exchanged
+#ifdef NMM_TRACE                // development build only (python -m neurons_b200.build --trace): timing experiments + per-tile timeline
+    int no_kv_traffic;          // no K / V loads after the first fill (results invalid)
+    unsigned long long *trace;  // per-tile clock64 timeline of CTA (0,0,0), [role 0 softmax / 1 mma][tile < 16][event < 8], or null
+    int debug;                  // results invalid: 1 = no ex2, 2 = no P stores, 4 = P V reduced to one MMA; 8 = pack by truncation
+#endif
 };
 
 __device__ __forceinline__ float ft_exp2(float x) {
@@ -61,8 +65,39 @@ __device__ __forceinline__ float ft_exp2(float x) {
     return y;
 }
 
-template <int DH>
-__global__ void __launch_bounds__(FT_THREADS, 2)
+// SP = softmax threads per query row (1: a thread owns all 128 scores of its row; 2: warps w and w + 4 own 64 columns each of the same
+// TMEM lanes -- 4 softmax warps per scheduler at 2 CTAs / SM instead of 2, which is what keeps the SFU fed while other warps are in their
+// TMEM-load / max / P-store stretches).
+// 2^x for x <= ~8 WITHOUT the SFU: round x to the nearest integer n with the 1.5 * 2^23 trick, 2^(x - n) by a degree-3 minimax polynomial
+// on [-0.5, 0.5] (max relative error 7.5e-5, against the 2^-9 of the bf16 rounding that follows), n added to the exponent field.  9 FMA- /
+// ALU-pipe instructions; FT_POLY (template parameter) of every 8 weights go this way, because the kernel is bounded by the 16 / clk / SM SFU (ex2 and the
+// F2FP packing share it): the timeline of scripts/spatial_attn_trace.py shows the SFU ~95 % busy while the softmax warps are in their
+// exponentials and those stretches making up 76 % of a tile's time.
+__device__ __forceinline__ float ft_exp2_poly(float x) {
+    x = fmaxf(x, -125.0f);
+    const float fi = x + 12582912.0f;
+    const float f = x - (fi - 12582912.0f);
+    float p = fmaf(0.0551716536f, f, 0.2426111251f);
+    p = fmaf(p, f, 0.6932609677f);
+    p = fmaf(p, f, 0.9999280572f);
+    return __uint_as_float(__float_as_uint(p) + (__float_as_uint(fi) << 23));
+}
+
+#ifndef NMM_TRACE
+#define FT_TRACE(role, t, ev) do { } while (0)
+#define FT_DEBUG(bit) false
+#else
+#define FT_DEBUG(bit) ((p.debug & (bit)) != 0)
+#define FT_TRACE(role, t, ev)                                                                                                   \
+    do {                                                                                                                        \
+        if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && (t) < 16 &&           \
+            ((role) == 1 || warp == 0))                                                                                         \
+            p.trace[((role) * 16 + (t)) * 8 + (ev)] = (unsigned long long)clock64();                                            \
+    } while (0)
+#endif
+
+template <int DH, int SP, int FT_POLY>
+__global__ void __launch_bounds__(64 + 128 * SP, 2)
 spatial_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
                             const FtParams p) {
     using Cfg = FtCfg<DH>;
@@ -79,12 +114,13 @@ spatial_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
     auto b_vempty = [&](int s) { return s_bar + 88 + 8 * s; };
     volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gbase + Cfg::OFF_BAR + 128);
 
+    constexpr int FT_THREADS = 64 + 128 * SP, W_TMA = 4 * SP, W_MMA = 4 * SP + 1, COLS = FT_BN / SP;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q0 = blockIdx.x * FT_BM, head = blockIdx.y, img = blockIdx.z;
     const int nt = (p.Lkv + FT_BN - 1) / FT_BN;
 
     if (tid == 0) {
-        ptx::mbar_init(b_q, 1); ptx::mbar_init(b_sfull, 1); ptx::mbar_init(b_sfree, 4); ptx::mbar_init(b_pfull, 4); ptx::mbar_init(b_pv, 1);
+        ptx::mbar_init(b_q, 1); ptx::mbar_init(b_sfull, 1); ptx::mbar_init(b_sfree, 4 * SP); ptx::mbar_init(b_pfull, 4 * SP); ptx::mbar_init(b_pv, 1);
         for (int s = 0; s < NS; s++) { ptx::mbar_init(b_kfull(s), 1); ptx::mbar_init(b_kempty(s), 1); ptx::mbar_init(b_vfull(s), 1); ptx::mbar_init(b_vempty(s), 1); }
         ptx::fence_mbar_init();
     }
@@ -103,7 +139,7 @@ spatial_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
         *reinterpret_cast<uint4 *>(gbase + Cfg::OFF_V + st * Cfg::VTILE_BYTES + CH * FT_CHUNK + r * 16) = make_uint4(r < FT_BN ? 0x3F80u : 0u, 0u, 0u, 0u);
     }
     ptx::fence_proxy_async();
-    if (warp == 5) ptx::tmem_alloc<1>(ptx::smem_u32(const_cast<uint32_t *>(tmem_slot)), FT_TMEM_COLS);
+    if (warp == W_MMA) ptx::tmem_alloc<1>(ptx::smem_u32(const_cast<uint32_t *>(tmem_slot)), FT_TMEM_COLS);
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -111,33 +147,51 @@ spatial_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
     pdl_wait();
     pdl_launch_dependents();
 
-    if (warp == 4) {
-        // ===================== TMA producer =====================
-        if (ptx::elect_one()) {
-            ptx::prefetch_tensormap(&tm_q); ptx::prefetch_tensormap(&tm_k); ptx::prefetch_tensormap(&tm_v);
+    if (warp == W_TMA) {
+        // ===================== TMA producer: lane 0 streams K, lane 1 streams V =====================
+        // (two independent streams: K(t+1) is wanted early -- S(t+1) is issued under the softmax of tile t -- and must not queue behind the
+        // wait for V's buffer, which P(t) V(t) releases late; with one stream the d_h = 80 kernel, whose rings are one stage deep, lost 35 %)
+        if (lane == 0) {
+            ptx::prefetch_tensormap(&tm_q); ptx::prefetch_tensormap(&tm_k);
             ptx::mbar_expect_tx(b_q, Cfg::TX_BYTES);
             ptx::tma_load_4d(&tm_q, b_q, s_q, 0, q0, head * CH, img);
             for (int t = 0; t < nt; t++) {
                 const int s = t % NS, fill = t / NS;
                 if (fill > 0) ptx::mbar_wait(b_kempty(s), (uint32_t)(fill - 1) & 1u);
+#ifdef NMM_TRACE
+                if (p.no_kv_traffic && fill > 0) { ptx::mbar_arrive(b_kfull(s)); continue; }
+#endif
                 ptx::mbar_expect_tx(b_kfull(s), Cfg::TX_BYTES);
                 ptx::tma_load_4d(&tm_k, b_kfull(s), s_k + s * Cfg::TILE_BYTES, 0, t * FT_BN, head * CH, img);
+            }
+        } else if (lane == 1) {
+            ptx::prefetch_tensormap(&tm_v);
+            for (int t = 0; t < nt; t++) {
+                const int s = t % NS, fill = t / NS;
                 if (fill > 0) ptx::mbar_wait(b_vempty(s), (uint32_t)(fill - 1) & 1u);
+#ifdef NMM_TRACE
+                if (p.no_kv_traffic && fill > 0) { ptx::mbar_arrive(b_vfull(s)); continue; }
+#endif
                 ptx::mbar_expect_tx(b_vfull(s), Cfg::TX_BYTES);
                 ptx::tma_load_4d(&tm_v, b_vfull(s), s_v + s * Cfg::VTILE_BYTES, 0, t * FT_BN, head * CH, img);
             }
         }
         __syncwarp();
-    } else if (warp == 5) {
+    } else if (warp == W_MMA) {
         // ===================== MMA issuer =====================
         const uint32_t idesc_s = ptx::umma_idesc_bf16(FT_BM, FT_BN);
         const uint32_t idesc_o = ptx::umma_idesc_bf16(FT_BM, NV) | ptx::UMMA_IDESC_B_MN_MAJOR;
-        const uint32_t v_lbo = p.swap_v_desc ? FT_CHUNK : 128u, v_sbo = p.swap_v_desc ? 128u : FT_CHUNK;
+        // V is an N-major operand in the un-swizzled layout: 16-byte channel chunks FT_CHUNK apart (SBO), 8-key groups 128 B apart (LBO)
+        // (the other assignment of the two fields was tried on B200 and is wrong: profiles/r2_spatial_attention_probe.txt history)
+        const uint32_t v_lbo = 128u, v_sbo = FT_CHUNK;
         auto issue_s = [&](int t) {           // S(t) = Q K(t)^T
             const int s = t % NS;
+            FT_TRACE(1, t, 0);
             ptx::mbar_wait(b_kfull(s), (uint32_t)(t / NS) & 1u);
+            FT_TRACE(1, t, 1);
             if (t > 0) ptx::mbar_wait(b_sfree, (uint32_t)(t - 1) & 1u);      // the softmax warps hold S(t-1) in registers
             ptx::tc_fence_after();
+            FT_TRACE(1, t, 2);
             if (ptx::elect_one()) {
                 const uint64_t a = ptx::umma_smem_desc_interleave(s_q, FT_CHUNK, 128);
                 const uint64_t b = ptx::umma_smem_desc_interleave(s_k + s * Cfg::TILE_BYTES, FT_CHUNK, 128);
@@ -154,50 +208,65 @@ spatial_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
         for (int t = 0; t < nt; t++) {
             if (t + 1 < nt) issue_s(t + 1);
             const int s = t % NS;
+            FT_TRACE(1, t, 3);
             ptx::mbar_wait(b_vfull(s), (uint32_t)(t / NS) & 1u);
+            FT_TRACE(1, t, 4);
             ptx::mbar_wait(b_pfull, (uint32_t)t & 1u);
             ptx::tc_fence_after();
+            FT_TRACE(1, t, 5);
             if (ptx::elect_one()) {          // O += P(t) V(t)
                 const uint64_t a = ptx::umma_smem_desc_interleave(s_p, FT_CHUNK, 128);
                 const uint64_t b = ptx::umma_smem_desc_interleave(s_v + s * Cfg::VTILE_BYTES, v_lbo, v_sbo);
 #pragma unroll
-                for (int k = 0; k < FT_BN / 16; k++)
+                for (int k = 0; k < (FT_DEBUG(4) ? 1 : FT_BN / 16); k++)
                     ptx::umma_bf16<1>(tmem + FT_O_COL, a + (uint64_t)((k * 2 * FT_CHUNK) >> 4), b + (uint64_t)((k * 16 * 16) >> 4), idesc_o, (t | k) != 0 ? 1u : 0u);
                 ptx::umma_commit<1>(b_pv);
                 ptx::umma_commit<1>(b_vempty(s));
             }
             __syncwarp();
+            FT_TRACE(1, t, 6);
         }
     } else {
-        // ===================== softmax: thread = query row q0 + tid = TMEM lane tid =====================
-        const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);
+        // ===================== softmax: query row = TMEM lane (warp % 4) * 32 + lane; columns [half * COLS, (half + 1) * COLS) =====
+        const int half = warp >> 2, qw = warp & 3, lrow = qw * 32 + lane;
+        const uint32_t t_row = tmem + ((uint32_t)(qw * 32) << 16);
         const float sl = p.scale_log2e;
+        float *maxbuf = reinterpret_cast<float *>(gbase + Cfg::OFF_MAX);
         float m_ref = -INFINITY;
         for (int t = 0; t < nt; t++) {
+            FT_TRACE(0, t, 0);
             ptx::mbar_wait(b_sfull, (uint32_t)t & 1u);
             ptx::tc_fence_after();
-            uint32_t sr[128];
+            FT_TRACE(0, t, 1);
+            uint32_t sr[COLS];
 #pragma unroll
-            for (int c = 0; c < 4; c++) ptx::tmem_ld32(t_row + c * 32, *reinterpret_cast<uint32_t (*)[32]>(&sr[c * 32]));
+            for (int c = 0; c < COLS / 32; c++) ptx::tmem_ld32(t_row + half * COLS + c * 32, *reinterpret_cast<uint32_t (*)[32]>(&sr[c * 32]));
             ptx::tmem_ld_wait();
             ptx::tc_fence_before();
             __syncwarp();
             if (ptx::elect_one()) ptx::mbar_arrive(b_sfree);          // S(t) is in registers: the tensor core may overwrite it with S(t+1)
             __syncwarp();
+            FT_TRACE(0, t, 2);
             float *sf = reinterpret_cast<float *>(sr);
             if ((t + 1) * FT_BN > p.Lkv) {                            // keys past the end of the image (zero-filled K rows): no weight
-                const int valid = p.Lkv - t * FT_BN;
+                const int valid = p.Lkv - t * FT_BN - half * COLS;
 #pragma unroll
-                for (int c = 0; c < 128; c++)
+                for (int c = 0; c < COLS; c++)
                     if (c >= valid) sf[c] = -INFINITY;
             }
-            // (one warp per scheduler per CTA: four independent chains for the max and for the sum, or their latency is the critical path)
+            // (few warps per scheduler: four independent chains for the max, or their latency is the critical path)
             float mx4[4] = {sf[0], sf[1], sf[2], sf[3]};
 #pragma unroll
-            for (int c = 4; c < 128; c += 4) {
+            for (int c = 4; c < COLS; c += 4) {
                 mx4[0] = fmaxf(mx4[0], sf[c]); mx4[1] = fmaxf(mx4[1], sf[c + 1]); mx4[2] = fmaxf(mx4[2], sf[c + 2]); mx4[3] = fmaxf(mx4[3], sf[c + 3]);
             }
-            const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+            float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+            if constexpr (SP == 2) {                                  // the row's other 64 columns belong to warp (warp ^ 4): exchange the maxima
+                float *mb = maxbuf + (t & 1) * 256;                   // double-buffered by tile parity: one named barrier per tile is enough
+                mb[half * 128 + lrow] = mx;
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + qw) : "memory");
+                mx = fmaxf(mx, mb[(half ^ 1) * 128 + lrow]);
+            }
             // reference max: raise it only when the running max is more than 2^8 above it (p <= 256 otherwise)
             const bool raise = (mx - m_ref) * sl > 8.0f;              // true at t = 0 (m_ref = -inf)
             const float m_new = raise ? mx : m_ref;
@@ -205,11 +274,34 @@ spatial_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
             // when it has long completed.  (The row sum is column d_h of O: see the ones column of V above.  Packing by truncation -- a PRMT
             // instead of F2FP, which shares the SFU pipe with ex2 -- was measured: same time, slightly larger error; round-to-nearest kept.)
             const float ms = m_new * sl;
-            uint32_t pk[64];
+            const uint32_t prow = s_p + (uint32_t)lrow * 16 + (uint32_t)(half * (COLS / 8)) * FT_CHUNK;
+            auto exp_chunk = [&](int kc, uint32_t (&q)[4]) {          // 8 scores -> 8 bf16 weights: 6 on the SFU, 2 on the FMA / ALU pipes
 #pragma unroll
-            for (int c = 0; c < 64; c++) pk[c] = pack_bf16x2(ft_exp2(fmaf(sf[2 * c], sl, -ms)), ft_exp2(fmaf(sf[2 * c + 1], sl, -ms)));
-            if (t > 0) ptx::mbar_wait(b_pv, (uint32_t)(t - 1) & 1u);  // P(t-1) V(t-1) done: P's buffer is free and O's rows are at rest
-            if (t > 0 && __any_sync(0xffffffffu, raise)) {
+                for (int i = 0; i < 4; i++) {
+                    const float x0 = fmaf(sf[kc * 8 + 2 * i], sl, -ms), x1 = fmaf(sf[kc * 8 + 2 * i + 1], sl, -ms);
+#ifdef NMM_TRACE
+                    if (FT_DEBUG(1)) { q[i] = pack_bf16x2(x0, x1); continue; }
+                    if (FT_DEBUG(8)) { q[i] = __byte_perm(__float_as_uint(ft_exp2(x0)), __float_as_uint(ft_exp2(x1)), 0x7632); continue; }
+#endif
+                    q[i] = pack_bf16x2((2 * i >= 8 - FT_POLY) ? ft_exp2_poly(x0) : ft_exp2(x0), (2 * i + 1 >= 8 - FT_POLY) ? ft_exp2_poly(x1) : ft_exp2(x1));
+                }
+            };
+            auto store_chunk = [&](int kc, const uint32_t (&q)[4]) {
+#ifdef NMM_TRACE
+                if (FT_DEBUG(2)) { if (q[0] == 0x12345678u && q[1] == q[2] + q[3]) asm volatile("st.shared.b32 [%0], %1;" ::"r"(prow), "r"(q[3]) : "memory"); return; }
+#endif
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + kc * FT_CHUNK), "r"(q[0]), "r"(q[1]), "r"(q[2]), "r"(q[3]) : "memory");
+            };
+            // first half of the exponentials before the wait for P(t-1) V(t-1) (P's buffer is busy until then), the rest interleaved with
+            // the stores: no burst of 16-byte stores + proxy fence at the end of the tile with the SFU idle behind it
+            constexpr int NCH = COLS / 8, PRE = NCH / 2;
+            uint32_t pk[PRE][4];
+#pragma unroll
+            for (int kc = 0; kc < PRE; kc++) exp_chunk(kc, pk[kc]);
+            FT_TRACE(0, t, 3);
+            if (t > 0) ptx::mbar_wait(b_pv, (uint32_t)(t - 1) & 1u);
+            FT_TRACE(0, t, 4);  // P(t-1) V(t-1) done: P's buffer is free and O's rows are at rest
+            if (t > 0 && __any_sync(0xffffffffu, raise) && half == 0) {   // (both threads of a row see the same maxima; the first one rescales)
                 const float f = ft_exp2((m_ref - m_new) * sl);        // 1 for the rows that keep their reference
                 ptx::tc_fence_after();
 #pragma unroll
@@ -224,28 +316,31 @@ spatial_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
                 ptx::tmem_st_wait();
             }
             m_ref = m_new;
-            const uint32_t prow = s_p + (uint32_t)tid * 16;
 #pragma unroll
-            for (int kc = 0; kc < FT_BN / 8; kc++)
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + kc * FT_CHUNK), "r"(pk[4 * kc]), "r"(pk[4 * kc + 1]), "r"(pk[4 * kc + 2]),
-                             "r"(pk[4 * kc + 3])
-                             : "memory");
+            for (int kc = 0; kc < PRE; kc++) {
+                store_chunk(kc, pk[kc]);
+                uint32_t q[4];
+                exp_chunk(PRE + kc, q);
+                store_chunk(PRE + kc, q);
+            }
+            FT_TRACE(0, t, 5);
             ptx::fence_proxy_async();          // generic-proxy stores -> visible to the tensor core's async-proxy reads
             ptx::tc_fence_before();
             __syncwarp();
             if (ptx::elect_one()) ptx::mbar_arrive(b_pfull);
             __syncwarp();
+            FT_TRACE(0, t, 6);
         }
-        // ---- O / l -> global (one query row per thread: d_h contiguous bf16) ----
+        // ---- O / l -> global (d_h contiguous bf16 per query row; the row's threads take alternate 16-channel pieces) ----
         ptx::mbar_wait(b_pv, (uint32_t)(nt - 1) & 1u);
         ptx::tc_fence_after();
         const uint32_t lraw = ptx::tmem_ld1(t_row + FT_O_COL + DH);      // the row sum: column d_h of O
         ptx::tmem_ld_wait();
         const float inv = 1.0f / __uint_as_float(lraw);
-        const int row = q0 + tid;
+        const int row = q0 + lrow;
         bf16 *og = (bf16 *)p.o + (int64_t)img * p.o_bs + (int64_t)row * p.o_rs + head * DH;
 #pragma unroll
-        for (int c = 0; c < CH; c += 2) {
+        for (int c = 2 * half; c < CH; c += 2 * SP) {
             uint32_t orow[16];
             ptx::tmem_ld16(t_row + FT_O_COL + c * 8, orow);
             ptx::tmem_ld_wait();
@@ -264,7 +359,7 @@ spatial_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 5) {
+    if (warp == W_MMA) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc<1>(tmem, FT_TMEM_COLS);
     }
@@ -298,6 +393,16 @@ static int ft_map(CUtensorMap *tm, const void *ptr, int64_t rows, int64_t row_st
     return NMM_OK;
 }
 
+#ifdef NMM_TRACE
+static unsigned long long *g_ft_trace = nullptr;
+extern "C" __attribute__((visibility("default"))) int nmm_debug_ft_trace(unsigned long long *host_out) {      // 2 x 16 x 8 clock64 values
+    if (!g_ft_trace) { cudaMalloc(&g_ft_trace, 2 * 16 * 8 * 8); cudaMemset(g_ft_trace, 0, 2 * 16 * 8 * 8); return 1; }
+    cudaDeviceSynchronize();
+    cudaMemcpy(host_out, g_ft_trace, 2 * 16 * 8 * 8, cudaMemcpyDeviceToHost);
+    return 0;
+}
+#endif
+
 bool spatial_attention_tc_eligible(const FlashArgs &a) {
     if (a.dtype != NMM_BF16 || (a.dh != 40 && a.dh != 80) || a.kv_div != 1 || a.Lkv < 256) return false;
     // the tensor maps address whole rows: a row stride that covers the row's channels and image strides that are whole rows
@@ -305,11 +410,11 @@ bool spatial_attention_tc_eligible(const FlashArgs &a) {
            aligned(a.k, 16) && aligned(a.v, 16) && aligned(a.o, 16);
 }
 
-template <int DH>
-static int launch_ft(const FlashArgs &a, int swap_v, cudaStream_t st) {
+template <int DH, int SP, int PL>
+static int launch_ft(const FlashArgs &a, int debug, cudaStream_t st) {
     using Cfg = FtCfg<DH>;
     static DeviceOnce once;
-    NMM_CUDA_OK(once.max_smem(spatial_attention_tc_kernel<DH>, (int)Cfg::SMEM));
+    NMM_CUDA_OK(once.max_smem(spatial_attention_tc_kernel<DH, SP, PL>, (int)Cfg::SMEM));
     CUtensorMap tq, tk, tv;
     int rc;
     // q / k / v are column slices of a wider row (q | k | v of one projection): the map starts at the slice, the chunk dimension spans the
@@ -318,18 +423,33 @@ static int launch_ft(const FlashArgs &a, int swap_v, cudaStream_t st) {
     if ((rc = ft_map(&tk, a.k, a.Lkv, a.kv_rs, a.kv_bs, a.images, DH)) != NMM_OK) return rc;
     if ((rc = ft_map(&tv, a.v, a.Lkv, a.kv_rs, a.kv_bs, a.images, DH)) != NMM_OK) return rc;
     FtParams p;
-    p.o = a.o; p.o_rs = a.o_rs; p.o_bs = a.o_bs; p.Lq = a.Lq; p.Lkv = a.Lkv; p.scale_log2e = a.scale_log2e; p.swap_v_desc = swap_v;
+    p.o = a.o; p.o_rs = a.o_rs; p.o_bs = a.o_bs; p.Lq = a.Lq; p.Lkv = a.Lkv; p.scale_log2e = a.scale_log2e;
+#ifdef NMM_TRACE
+    p.no_kv_traffic = (debug & 16) ? 1 : 0; p.debug = debug & 15; p.trace = g_ft_trace;
+#else
+    (void)debug;
+#endif
     const dim3 grid((unsigned)ceil_div(a.Lq, FT_BM), (unsigned)a.heads, (unsigned)a.images);
     const double per = (double)a.images * a.heads;
     ProfScope prof(K_SPATIAL_ATTN, st, 4.0 * per * a.Lq * (double)a.Lkv * DH, 2.0 * 4.0 * per * a.Lq * DH);
-    NMM_CUDA_OK(launch_pdl(spatial_attention_tc_kernel<DH>, grid, dim3(FT_THREADS), (size_t)Cfg::SMEM, st, tq, tk, tv, p));
+    NMM_CUDA_OK(launch_pdl(spatial_attention_tc_kernel<DH, SP, PL>, grid, dim3(64 + 128 * SP), (size_t)Cfg::SMEM, st, tq, tk, tv, p));
     NMM_LAUNCHED("spatial_attention_tc_kernel");
     return NMM_OK;
 }
 
-int launch_spatial_attention_tc(const FlashArgs &a, int swap_v, cudaStream_t st) {
-    if (a.dh == 40) return launch_ft<40>(a, swap_v, st);
-    if (a.dh == 80) return launch_ft<80>(a, swap_v, st);
+int launch_spatial_attention_tc(const FlashArgs &a, int variant, cudaStream_t st) {
+    // NMM_OPT_SPATIAL_ATTN: 0 / 3 = one softmax thread per query row (measured faster once the polynomial share relieved the SFU), 2 = two;
+    // 10..14 = polynomial share 0 / 2 / 3 / 4 / 6 of 8 (A/B; 3 is the default);
+    // 100 + bits = timing experiments of the -DNMM_TRACE development build (results invalid; ignored by the production build)
+    const int debug = variant >= 100 ? variant - 100 : 0;
+    const int sp = variant == 2 ? 2 : 1;
+    if (variant >= 10 && variant <= 14) {          // A/B: polynomial share 0 / 2 / 3 / 4 / 6 of 8 (one softmax thread per row)
+        const int pl = variant - 10;
+        if (a.dh == 40) return pl == 0 ? launch_ft<40, 1, 0>(a, 0, st) : pl == 1 ? launch_ft<40, 1, 2>(a, 0, st) : pl == 2 ? launch_ft<40, 1, 3>(a, 0, st) : pl == 3 ? launch_ft<40, 1, 4>(a, 0, st) : launch_ft<40, 1, 6>(a, 0, st);
+        if (a.dh == 80) return pl == 0 ? launch_ft<80, 1, 0>(a, 0, st) : pl == 1 ? launch_ft<80, 1, 2>(a, 0, st) : pl == 2 ? launch_ft<80, 1, 3>(a, 0, st) : pl == 3 ? launch_ft<80, 1, 4>(a, 0, st) : launch_ft<80, 1, 6>(a, 0, st);
+    }
+    if (a.dh == 40) return sp == 1 ? launch_ft<40, 1, 3>(a, debug, st) : launch_ft<40, 2, 3>(a, debug, st);
+    if (a.dh == 80) return sp == 1 ? launch_ft<80, 1, 3>(a, debug, st) : launch_ft<80, 2, 3>(a, debug, st);
     return fail(NMM_ERR_UNSUPPORTED, "tcgen05 spatial attention: d_h %d", a.dh);
 }
 

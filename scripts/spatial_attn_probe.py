@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Development probe: the tcgen05 spatial-attention kernel against an fp64 softmax attention, for the run-time variants of
-NMM_OPT_SPATIAL_ATTN (0 = tcgen05, 1 = mma.sync, 2 = tcgen05 with the V descriptor's LBO / SBO exchanged), plus timing."""
+"""Development probe: the spatial-attention kernels against an fp64 softmax attention, for the run-time variants of NMM_OPT_SPATIAL_ATTN
+(0 = tcgen05 kernel as planned, 1 = mma.sync kernel, 2 = tcgen05 with two softmax threads per query row, 10..14 = polynomial-ex2 share
+0 / 2 / 3 / 4 / 6 of 8), plus timing at the 64 x 64 (d_h 40) and 32 x 32 (d_h 80) levels.   python scripts/spatial_attn_probe.py 1,0,2"""
 import os
 import sys
 
