@@ -7,7 +7,7 @@ timeout 600 ncu --profile-from-start off --clock-control none --csv --metrics $M
 tail -2 gpurun_out/ncu_step.log
 # launch list of the bench command itself (times only)
 # (bench.py first launches ~500 torch initialisation kernels: filter on this library's kernels)
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'linear_tc|linear_simt|fused_module|gn_|layernorm_pe|temporal_attention|cfg_ddim' -c 600 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-clips --no-eager > gpurun_out/ncu_launch.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'linear_tc|linear_simt|fused_module|gn_|layernorm_pe|temporal_attention|spatial_attention|cfg_ddim' -c 900 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-clips --no-eager > gpurun_out/ncu_launch.log 2>&1
 tail -2 gpurun_out/ncu_launch.log | cut -c1-200
 # full sections: one C = 320 call (gn_stats + the one-kernel module) and one C = 640 call (12 kernels of the multi-kernel path)
 timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -o gpurun_out/prof_calls -f python scripts/profile_step.py --calls 6 --only 0,2 > gpurun_out/ncu_full.log 2>&1
