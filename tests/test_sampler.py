@@ -97,6 +97,54 @@ def test_ddim_25_step_cosine_at_unet_channel_widths():
 
 
 @pytest.mark.gpu
+@pytest.mark.timeout(1500)
+def test_ddim_25_step_cosine_spatial_plus_motion_blocks():
+    """The call order of the UNet's CrossAttn blocks (unet_blocks.py:409-411) through the whole loop: every stage of the stack is a spatial
+    Transformer3DModel (self-attention over h*w, text cross-attention, GEGLU) followed by the motion module that consumes
+    its [B,F,C,H,W]-storage view, at 320 / 640 channels, CFG batch 2, 8 frames, 16x16 latent (so the d_h = 40 self-attention runs on the
+    tcgen05 kernel at the first level: 256 keys), bf16 on the GPU against the reference arithmetic of both modules (oracles, fp32 on the
+    same bf16-rounded weights) over all 25 DDIM steps."""
+    import neurons_b200 as nb
+    from oracle import spatial_oracle as so
+    dev = "cuda:0"
+    stack, cfgs, params = _stack_and_params((320, 640), seed=9)
+    mods = [helpers.mirror_module(c, p, dev, torch.bfloat16) for c, p in zip(cfgs, params)]
+    scfgs = [so.SpatialConfig(c.channels, 8, 1, 768, True) for c in cfgs]
+    sparams = [{k: helpers.round_bf16(v) for k, v in so.make_params(sc, 40 + i).items()} for i, sc in enumerate(scfgs)]
+    smods = []
+    for sc, sp in zip(scfgs, sparams):
+        m = nb.Transformer3DModel(num_attention_heads=8, attention_head_dim=sc.head_dim, in_channels=sc.channels, cross_attention_dim=768,
+                                  unet_use_cross_frame_attention=False, unet_use_temporal_attention=False)
+        m.load_state_dict(sp, strict=True)
+        smods.append(m.eval().to(dev).to(torch.bfloat16))
+    g = torch.Generator().manual_seed(23)
+    lat0 = torch.randn(1, 4, 8, 16, 16, generator=g)
+    noise = torch.randn(1, 4, 8, 16, 16, generator=g)
+    ctx = torch.randn(2, 16, generator=g)
+    ehs = helpers.round_bf16(torch.randn(2, 77, 768, generator=g))          # uncond | cond text states
+    ehs_dev = ehs.to(dev).to(torch.bfloat16)
+    sch = sampler.DDIMSchedule()
+
+    def den_gpu(x2, t, c):
+        def block(i, h):
+            y = smods[i](h.to(torch.bfloat16), encoder_hidden_states=ehs_dev).sample
+            return mods[i](y, None, None).float()
+        return stack(block, x2, t, c)
+
+    def den_ref(x2, t, c):
+        def block(i, h):
+            y = so.forward_reference_order(sparams[i], h, ehs, scfgs[i])
+            return mo.forward_reference_order(params[i], y, cfgs[i])
+        return stack(block, x2, t, c)
+
+    out_gpu = sampler.denoise(den_gpu, lat0.to(dev), ctx.to(dev), sch, 25, 8.5, noise=noise.to(dev)).float().cpu()
+    out_ref = sampler.denoise(den_ref, lat0, ctx, sch, 25, 8.5, noise=noise)
+    assert torch.isfinite(out_gpu).all() and torch.isfinite(out_ref).all()
+    cos = torch.nn.functional.cosine_similarity(out_gpu.flatten(), out_ref.flatten(), dim=0).item()
+    assert cos >= 0.999, cos
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
 @pytest.mark.parametrize("n", [4 * 16 * 32 * 32, 1003, 8])
 @pytest.mark.parametrize("with_cfg", [True, False])
