@@ -657,6 +657,12 @@ def main():
                     "workload": "BASELINE configs[2] shape: 25 DDIM steps x (20 UNet + 8 SparseCtrl ControlNet motion-module calls), CFG batch 2, "
                                 "16 frames, 32x32 latent, bf16; one step captured in a CUDA graph; the rest of the UNet is outside the path"},
                 "spatial_transformer": spatial,
+                "unet_step_transformers": None if not spatial or "ms_per_step" not in spatial else {
+                    "what": "both transformer families of the same UNet step: 20 motion-module calls (`value`) + 16 spatial Transformer3DModel calls",
+                    "ms_per_step": ms_step + spatial["ms_per_step"],
+                    "tflops": (flops_step + spatial["flops_per_step"]) / ((ms_step + spatial["ms_per_step"]) * 1e-3) / 1e12,
+                    "gpu_eager_ms_per_step": (eager["bf16"]["ms_per_step"] + spatial["gpu_eager_baseline"]["ms_per_step"])
+                    if eager and "bf16" in eager and "ms_per_step" in spatial.get("gpu_eager_baseline", {}) else None},
                 "flops_per_step": flops_step}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -64,3 +64,45 @@ def test_gather_world2_gloo(num_clips):
         p.join(120)
         assert p.exitcode == 0
     assert ret.get() is True
+
+
+def _enhance_worker(rank, world, port, num_clips, ret):
+    """The whole N2 clip loop on 2 ranks: stage-3 inputs sharded round-robin, every clip through enhance_clip with a toy denoiser,
+    final latents gathered to rank 0 in the global clip order; compared with the single-process run of the same loop."""
+    from neurons_b200 import pipeline
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(0)
+        inputs = pipeline.Stage3Inputs(torch.rand(num_clips, 3, 8, 8, generator=g), torch.rand(num_clips, 6, 3, 8, 8, generator=g),
+                                       [f"clip {i}" for i in range(num_clips)])
+        encode = lambda frames: frames.mean(dim=1, keepdim=True).repeat(1, 4, 1, 1)[..., ::2, ::2]       # [n,3,8,8] -> [n,4,4,4] "latents"
+        text = lambda caption: torch.full((2, 3, 4), float(len(caption)))
+        make = lambda key_lat: (lambda x2, t, ctx: 0.1 * x2 + 0.01 * key_lat.mean() + 1e-3 * ctx.mean())
+        kw = dict(num_inference_steps=3, guidance_scale=8.5, low_strength=0.3, seed=0)
+        mine = pipeline.enhance_shard(inputs, rank, world, encode, text, make, **kw)
+        assert [i for i, _ in mine] == sharding.shard_indices(num_clips, rank, world)
+        local = torch.stack([lat[0] for _, lat in mine]) if mine else torch.zeros((0, 4, 16, 4, 4))
+        out = sharding.gather_clips(local, num_clips)
+        if rank == 0:
+            alone = pipeline.enhance_shard(inputs, 0, 1, encode, text, make, **kw)
+            ref = torch.stack([lat[0] for _, lat in alone])
+            ret.put(bool(out is not None and out.shape == ref.shape and torch.equal(out, ref)))
+        else:
+            assert out is None
+    finally:
+        dist.destroy_process_group()
+
+
+def test_enhance_shard_world2_gloo():
+    ctx = mp.get_context("spawn")
+    ret = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_enhance_worker, args=(r, 2, port, 5, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert ret.get() is True
