@@ -83,6 +83,26 @@ __device__ __forceinline__ float ft_exp2_poly(float x) {
     return __uint_as_float(__float_as_uint(p) + (__float_as_uint(fi) << 23));
 }
 
+// Two of them at once on the packed fp32x2 pipe (FADD2 / FFMA2: one instruction, two lanes): 6 packed + 6 scalar instructions per pair
+// instead of 18 -- the kernel's issue slots are its busiest resource once the SFU is relieved.
+__device__ __forceinline__ void ft_exp2_poly2(uint64_t x, float &y0, float &y1) {
+    float x0, x1;
+    f32x2_unpack(x, x0, x1);
+    const uint64_t xc = f32x2_pack(fmaxf(x0, -125.0f), fmaxf(x1, -125.0f));
+    const uint64_t magic = f32x2_pack(12582912.0f, 12582912.0f);
+    const uint64_t fi = f32x2_add(xc, magic);
+    const uint64_t t = f32x2_add(fi, f32x2_pack(-12582912.0f, -12582912.0f));
+    const uint64_t f = f32x2_fma(t, f32x2_pack(-1.0f, -1.0f), xc);
+    uint64_t p = f32x2_fma(f32x2_pack(0.0551716536f, 0.0551716536f), f, f32x2_pack(0.2426111251f, 0.2426111251f));
+    p = f32x2_fma(p, f, f32x2_pack(0.6932609677f, 0.6932609677f));
+    p = f32x2_fma(p, f, f32x2_pack(0.9999280572f, 0.9999280572f));
+    float p0, p1, i0, i1;
+    f32x2_unpack(p, p0, p1);
+    f32x2_unpack(fi, i0, i1);
+    y0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(i0) << 23));
+    y1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(i1) << 23));
+}
+
 #ifndef NMM_TRACE
 #define FT_TRACE(role, t, ev) do { } while (0)
 #define FT_DEBUG(bit) false
@@ -275,15 +295,21 @@ spatial_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
             // instead of F2FP, which shares the SFU pipe with ex2 -- was measured: same time, slightly larger error; round-to-nearest kept.)
             const float ms = m_new * sl;
             const uint32_t prow = s_p + (uint32_t)lrow * 16 + (uint32_t)(half * (COLS / 8)) * FT_CHUNK;
-            auto exp_chunk = [&](int kc, uint32_t (&q)[4]) {          // 8 scores -> 8 bf16 weights: 6 on the SFU, 2 on the FMA / ALU pipes
+            const uint64_t sl2 = f32x2_pack(sl, sl), nms2 = f32x2_pack(-ms, -ms);
+            auto exp_chunk = [&](int kc, uint32_t (&q)[4]) {          // 8 scores -> 8 bf16 weights: 8 - FT_POLY on the SFU, FT_POLY on the FMA / ALU pipes
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
-                    const float x0 = fmaf(sf[kc * 8 + 2 * i], sl, -ms), x1 = fmaf(sf[kc * 8 + 2 * i + 1], sl, -ms);
+                    const uint64_t x = f32x2_fma(f32x2_pack(sf[kc * 8 + 2 * i], sf[kc * 8 + 2 * i + 1]), sl2, nms2);      // (s - m_ref) * scale * log2 e, two at once
+                    float x0, x1, e0, e1;
+                    f32x2_unpack(x, x0, x1);
 #ifdef NMM_TRACE
                     if (FT_DEBUG(1)) { q[i] = pack_bf16x2(x0, x1); continue; }
                     if (FT_DEBUG(8)) { q[i] = __byte_perm(__float_as_uint(ft_exp2(x0)), __float_as_uint(ft_exp2(x1)), 0x7632); continue; }
 #endif
-                    q[i] = pack_bf16x2((2 * i >= 8 - FT_POLY) ? ft_exp2_poly(x0) : ft_exp2(x0), (2 * i + 1 >= 8 - FT_POLY) ? ft_exp2_poly(x1) : ft_exp2(x1));
+                    constexpr int FIRST = 8 - FT_POLY;                // elements FIRST .. 7 of every 8 take the polynomial
+                    if (2 * i >= FIRST) ft_exp2_poly2(x, e0, e1);
+                    else { e0 = ft_exp2(x0); e1 = (2 * i + 1 >= FIRST) ? ft_exp2_poly(x1) : ft_exp2(x1); }
+                    q[i] = pack_bf16x2(e0, e1);
                 }
             };
             auto store_chunk = [&](int kc, const uint32_t (&q)[4]) {
