@@ -310,6 +310,32 @@ NMM_API int nmm_spatial_attention(int32_t dtype, const void *q, const void *k, c
                                   int64_t o_row_stride, int64_t q_image_stride, int64_t kv_image_stride, int64_t o_image_stride, int32_t q_len,
                                   int32_t kv_len, int32_t heads, int32_t head_dim, int32_t images, int32_t kv_div, void *stream);
 
+/* ---- temporal attention of the blurry-video decoder -----------------------------------------------------------------
+ * Replaces the `temp_attn` + blend lines of AttnUpDecoderBlock2D.forward / UNetMidBlock2D.forward,
+ * /root/reference/model_variants/video_decoder.py:237-248 and :394-406:
+ *     y = weight * x + (1 - weight) * rearrange(temp_attn(rearrange(x, '(b t) c h w -> (b h w) t c')), '... -> (b t) c h w')
+ * with temp_attn = diffusers' Attention(c, heads = c / dim_head, norm_num_groups = 32, eps, residual_connection = True, bias = True,
+ * rescale_output_factor, _from_deprecated_attn_block = True) (video_decoder.py:204-216,353-365; class imported from the un-vendored
+ * `diffusers.models.attention_processor`).  PARITY UNPINNED: the class cannot be imported here, its arithmetic is restated
+ * (oracle/decoder_oracle.py).  x, y: [(b t), c, h, w] = a [b, c, t, h, w] tensor in [B, F, C, H, W] storage, described by nmm_shape with
+ * frames = t, heads = c / dim_head, eps_gn = the block's resnet_eps (1e-6), dtype NMM_F32 or NMM_BF16; layers / attn_blocks / pos_enc /
+ * max_len / ln_fold are ignored. */
+typedef struct nmm_decoder_attn_params {
+    int32_t dtype;                                  /* NMM_F32 or NMM_BF16: element type of every tensor below              */
+    const void *gn_w, *gn_b;                        /* temp_attn.group_norm.{weight,bias}        [C]                        */
+    const void *to_q_w, *to_q_b;                    /* temp_attn.to_q.{weight,bias}              [C,C],[C]                  */
+    const void *to_k_w, *to_k_b, *to_v_w, *to_v_b;  /* temp_attn.to_k / to_v                                                */
+    const void *to_out_w, *to_out_b;                /* temp_attn.to_out.0.{weight,bias}          [C,C],[C]                  */
+} nmm_decoder_attn_params;
+NMM_API int nmm_decoder_attn_packed_bytes(int32_t channels, int32_t dtype, size_t *out_bytes);
+NMM_API int nmm_decoder_attn_workspace_bytes(const nmm_shape *s, size_t *out_bytes);
+/* blend_weight = the block's scalar `weights[i]` (video_decoder.py:217,366; folded into the output projection at pack time: re-pack when
+ * it changes); rescale_output_factor must be 1 (it is in every block of DecoderVideo), otherwise NMM_ERR_UNSUPPORTED. */
+NMM_API int nmm_decoder_attn_pack(int32_t channels, int32_t dtype, const nmm_decoder_attn_params *src, float blend_weight,
+                                  float rescale_output_factor, void *packed, size_t packed_bytes, void *stream);
+NMM_API int nmm_decoder_temporal_attention(const nmm_shape *s, const void *x, void *y, const void *packed, size_t packed_bytes, void *workspace,
+                                           size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -66,6 +66,11 @@ class SpatialParams(C.Structure):
                 ("layer", SpatialLayerParams * NMM_MAX_LAYERS), ("proj_out_w", C.c_void_p), ("proj_out_b", C.c_void_p)]
 
 
+class DecoderAttnParams(C.Structure):
+    _fields_ = [("dtype", C.c_int32)] + [(n, C.c_void_p) for n in ("gn_w", "gn_b", "to_q_w", "to_q_b", "to_k_w", "to_k_b", "to_v_w", "to_v_b",
+                                                                    "to_out_w", "to_out_b")]
+
+
 class KernelProfile(C.Structure):
     _fields_ = [("name", C.c_char_p), ("launches", C.c_uint64), ("total_ms", C.c_double), ("flops", C.c_double),
                 ("bytes", C.c_double)]
@@ -113,6 +118,10 @@ SIGNATURES = {
     "nmm_spatial_workspace_bytes": (C.c_int, [_SSP, C.POINTER(C.c_size_t)]),
     "nmm_spatial_pack_params": (C.c_int, [_SSP, C.POINTER(SpatialParams), C.c_void_p, C.c_size_t, C.c_void_p]),
     "nmm_spatial_forward": (C.c_int, [_SSP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "nmm_decoder_attn_packed_bytes": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
+    "nmm_decoder_attn_workspace_bytes": (C.c_int, [_SP, C.POINTER(C.c_size_t)]),
+    "nmm_decoder_attn_pack": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(DecoderAttnParams), C.c_float, C.c_float, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "nmm_decoder_temporal_attention": (C.c_int, [_SP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
     "nmm_spatial_attention": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                         C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
 }
