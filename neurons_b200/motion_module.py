@@ -224,6 +224,11 @@ class _Engine:
         return (x.dtype, x.device) + tuple((t.data_ptr(), t._version) for t in tensors.values())
 
     @staticmethod
+    def _flags(module):
+        # per-module mode switches that change the packed layout: part of the key, so flipping one re-packs instead of being ignored
+        return (bool(module.__dict__.get("_nmm_ln_fold", False)), bool(module.__dict__.get("_nmm_fp32_fma", False)))
+
+    @staticmethod
     def _checksum(tensors):
         return float(sum(t.detach().double().abs().sum() for t in tensors.values()))
 
@@ -241,10 +246,10 @@ class _Engine:
         if self.tensors is None:
             self.tensors = self._tensors_of(module)
         tensors = self.tensors
-        key = self._key(x, tensors)
+        key = self._key(x, tensors) + self._flags(module)
         if key != self.key:
             self.tensors = tensors = self._tensors_of(module)      # re-scan the tree (parameters may have been replaced)
-            key = self._key(x, tensors)
+            key = self._key(x, tensors) + self._flags(module)
             if torch.cuda.is_current_stream_capturing():
                 raise RuntimeError("neurons_b200: the module's parameters must be packed before CUDA-graph capture: run one forward "
                                    "outside the capture first (packing inside a capture would bake stale weights into the graph)")
