@@ -50,10 +50,11 @@ struct FtCfg {
 struct FtParams {
     void *o;
     int64_t o_rs, o_bs;
+    const void *k, *v;          // cp.async loader (CPA): K / V base pointers (column slice of the projection output), row / image strides
+    int64_t kv_rs, kv_bs;
     int Lq, Lkv;
     float scale_log2e;
 #ifdef NMM_TRACE                // development build only (python -m neurons_b200.build --trace): timing experiments + per-tile timeline
-    int no_kv_traffic;          // no K / V loads after the first fill (results invalid)
     unsigned long long *trace;  // per-tile clock64 timeline of CTA (0,0,0), [role 0 softmax / 1 mma][tile < 16][event < 8], or null
     int debug;                  // results invalid: 1 = no ex2, 2 = no P stores, 4 = P V reduced to one MMA; 8 = pack by truncation
 #endif
@@ -116,7 +117,7 @@ __device__ __forceinline__ void ft_exp2_poly2(uint64_t x, float &y0, float &y1) 
     } while (0)
 #endif
 
-template <int DH, int SP, int FT_POLY>
+template <int DH, int SP, int FT_POLY, bool NOKV = false, bool CPA = false>
 __global__ void __launch_bounds__(64 + 128 * SP, 2)
 spatial_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
                             const FtParams p) {
@@ -141,7 +142,7 @@ spatial_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
 
     if (tid == 0) {
         ptx::mbar_init(b_q, 1); ptx::mbar_init(b_sfull, 1); ptx::mbar_init(b_sfree, 4 * SP); ptx::mbar_init(b_pfull, 4 * SP); ptx::mbar_init(b_pv, 1);
-        for (int s = 0; s < NS; s++) { ptx::mbar_init(b_kfull(s), 1); ptx::mbar_init(b_kempty(s), 1); ptx::mbar_init(b_vfull(s), 1); ptx::mbar_init(b_vempty(s), 1); }
+        for (int s = 0; s < NS; s++) { ptx::mbar_init(b_kfull(s), CPA ? 16 : 1); ptx::mbar_init(b_kempty(s), 1); ptx::mbar_init(b_vfull(s), CPA ? 16 : 1); ptx::mbar_init(b_vempty(s), 1); }
         ptx::fence_mbar_init();
     }
     // Pad chunks (TMA never writes them).  Q / K: zeros (0 x 0 instead of 0 x garbage in the padded k-step).  V: channel d_h of every key
@@ -171,6 +172,45 @@ spatial_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
         // ===================== TMA producer: lane 0 streams K, lane 1 streams V =====================
         // (two independent streams: K(t+1) is wanted early -- S(t+1) is issued under the softmax of tile t -- and must not queue behind the
         // wait for V's buffer, which P(t) V(t) releases late; with one stream the d_h = 80 kernel, whose rings are one stage deep, lost 35 %)
+        if constexpr (CPA) {
+            // K / V through the LSU instead of the TMA unit: a K or V tile in the un-swizzled core-matrix order is 128 x d_h/8 separate 16-byte
+            // segments for the TMA (1280 per key tile at d_h = 40, shared by the SM's two CTAs: ~90 % of a tile's time), but one cp.async
+            // per lane here -- lanes 0-15 stream K, 16-31 stream V; 8 consecutive lanes take 8 consecutive keys of one 16-byte channel chunk
+            // (128 contiguous bytes of shared memory), the two lane groups adjacent chunks (32 / 64 contiguous bytes per key in global
+            // memory).  Completion: cp.async.mbarrier.arrive.noinc on the full barrier (16 arrivals); the MMA warp adds a proxy fence.
+            const int hl = lane & 15, is_v = lane >> 4;
+            if (lane == 0) {
+                ptx::prefetch_tensormap(&tm_q);
+                ptx::mbar_expect_tx(b_q, Cfg::TX_BYTES);
+                ptx::tma_load_4d(&tm_q, b_q, s_q, 0, q0, head * CH, img);
+            }
+            const bf16 *src0 = (const bf16 *)(is_v ? p.v : p.k) + (int64_t)img * p.kv_bs + head * DH;
+            for (int t = 0; t < nt; t++) {
+                const int s = t % NS, fill = t / NS;
+                const uint32_t full = is_v ? b_vfull(s) : b_kfull(s), empty = is_v ? b_vempty(s) : b_kempty(s);
+                if (fill > 0) ptx::mbar_wait(empty, (uint32_t)(fill - 1) & 1u);
+                const uint32_t dst0 = (is_v ? s_v + s * Cfg::VTILE_BYTES : s_k + s * Cfg::TILE_BYTES) + (uint32_t)(hl & 7) * 16;
+                if (!(NOKV && fill > 0)) {
+#pragma unroll 2
+                    for (int rg = 0; rg < FT_BN / 8; rg++) {
+                        const int key = t * FT_BN + rg * 8 + (hl & 7);
+                        const bool ok = key < p.Lkv;
+                        const bf16 *src = src0 + (int64_t)(ok ? key : p.Lkv - 1) * p.kv_rs;
+#pragma unroll
+                        for (int cp = 0; cp < (CH + 1) / 2; cp++) {
+                            const int c = 2 * cp + (hl >> 3);
+                            if (c < CH) {
+                                const int sz = ok ? 16 : 0;
+                                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + (uint32_t)c * FT_CHUNK + (uint32_t)rg * 128), "l"(src + c * 8),
+                                             "r"(sz)
+                                             : "memory");
+                            }
+                        }
+                    }
+                }
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full) : "memory");
+            }
+        } else
         if (lane == 0) {
             ptx::prefetch_tensormap(&tm_q); ptx::prefetch_tensormap(&tm_k);
             ptx::mbar_expect_tx(b_q, Cfg::TX_BYTES);
@@ -178,9 +218,7 @@ spatial_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
             for (int t = 0; t < nt; t++) {
                 const int s = t % NS, fill = t / NS;
                 if (fill > 0) ptx::mbar_wait(b_kempty(s), (uint32_t)(fill - 1) & 1u);
-#ifdef NMM_TRACE
-                if (p.no_kv_traffic && fill > 0) { ptx::mbar_arrive(b_kfull(s)); continue; }
-#endif
+                if (NOKV && fill > 0) { ptx::mbar_arrive(b_kfull(s)); continue; }      // timing experiment (results invalid): no K traffic after the first fill
                 ptx::mbar_expect_tx(b_kfull(s), Cfg::TX_BYTES);
                 ptx::tma_load_4d(&tm_k, b_kfull(s), s_k + s * Cfg::TILE_BYTES, 0, t * FT_BN, head * CH, img);
             }
@@ -189,9 +227,7 @@ spatial_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
             for (int t = 0; t < nt; t++) {
                 const int s = t % NS, fill = t / NS;
                 if (fill > 0) ptx::mbar_wait(b_vempty(s), (uint32_t)(fill - 1) & 1u);
-#ifdef NMM_TRACE
-                if (p.no_kv_traffic && fill > 0) { ptx::mbar_arrive(b_vfull(s)); continue; }
-#endif
+                if (NOKV && fill > 0) { ptx::mbar_arrive(b_vfull(s)); continue; }
                 ptx::mbar_expect_tx(b_vfull(s), Cfg::TX_BYTES);
                 ptx::tma_load_4d(&tm_v, b_vfull(s), s_v + s * Cfg::VTILE_BYTES, 0, t * FT_BN, head * CH, img);
             }
@@ -208,6 +244,7 @@ spatial_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
             const int s = t % NS;
             FT_TRACE(1, t, 0);
             ptx::mbar_wait(b_kfull(s), (uint32_t)(t / NS) & 1u);
+            if constexpr (CPA) ptx::fence_proxy_async();                    // cp.async wrote K through the generic proxy; the MMA reads it through the async proxy
             FT_TRACE(1, t, 1);
             if (t > 0) ptx::mbar_wait(b_sfree, (uint32_t)(t - 1) & 1u);      // the softmax warps hold S(t-1) in registers
             ptx::tc_fence_after();
@@ -230,6 +267,7 @@ spatial_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
             const int s = t % NS;
             FT_TRACE(1, t, 3);
             ptx::mbar_wait(b_vfull(s), (uint32_t)(t / NS) & 1u);
+            if constexpr (CPA) ptx::fence_proxy_async();
             FT_TRACE(1, t, 4);
             ptx::mbar_wait(b_pfull, (uint32_t)t & 1u);
             ptx::tc_fence_after();
@@ -436,11 +474,11 @@ bool spatial_attention_tc_eligible(const FlashArgs &a) {
            aligned(a.k, 16) && aligned(a.v, 16) && aligned(a.o, 16);
 }
 
-template <int DH, int SP, int PL>
+template <int DH, int SP, int PL, bool NOKV = false, bool CPA = false>
 static int launch_ft(const FlashArgs &a, int debug, cudaStream_t st) {
     using Cfg = FtCfg<DH>;
     static DeviceOnce once;
-    NMM_CUDA_OK(once.max_smem(spatial_attention_tc_kernel<DH, SP, PL>, (int)Cfg::SMEM));
+    NMM_CUDA_OK(once.max_smem(spatial_attention_tc_kernel<DH, SP, PL, NOKV, CPA>, (int)Cfg::SMEM));
     CUtensorMap tq, tk, tv;
     int rc;
     // q / k / v are column slices of a wider row (q | k | v of one projection): the map starts at the slice, the chunk dimension spans the
@@ -449,16 +487,16 @@ static int launch_ft(const FlashArgs &a, int debug, cudaStream_t st) {
     if ((rc = ft_map(&tk, a.k, a.Lkv, a.kv_rs, a.kv_bs, a.images, DH)) != NMM_OK) return rc;
     if ((rc = ft_map(&tv, a.v, a.Lkv, a.kv_rs, a.kv_bs, a.images, DH)) != NMM_OK) return rc;
     FtParams p;
-    p.o = a.o; p.o_rs = a.o_rs; p.o_bs = a.o_bs; p.Lq = a.Lq; p.Lkv = a.Lkv; p.scale_log2e = a.scale_log2e;
+    p.o = a.o; p.o_rs = a.o_rs; p.o_bs = a.o_bs; p.k = a.k; p.v = a.v; p.kv_rs = a.kv_rs; p.kv_bs = a.kv_bs; p.Lq = a.Lq; p.Lkv = a.Lkv; p.scale_log2e = a.scale_log2e;
 #ifdef NMM_TRACE
-    p.no_kv_traffic = (debug & 16) ? 1 : 0; p.debug = debug & 15; p.trace = g_ft_trace;
+    p.debug = debug & 15; p.trace = g_ft_trace;
 #else
     (void)debug;
 #endif
     const dim3 grid((unsigned)ceil_div(a.Lq, FT_BM), (unsigned)a.heads, (unsigned)a.images);
     const double per = (double)a.images * a.heads;
     ProfScope prof(K_SPATIAL_ATTN, st, 4.0 * per * a.Lq * (double)a.Lkv * DH, 2.0 * 4.0 * per * a.Lq * DH);
-    NMM_CUDA_OK(launch_pdl(spatial_attention_tc_kernel<DH, SP, PL>, grid, dim3(64 + 128 * SP), (size_t)Cfg::SMEM, st, tq, tk, tv, p));
+    NMM_CUDA_OK(launch_pdl(spatial_attention_tc_kernel<DH, SP, PL, NOKV, CPA>, grid, dim3(64 + 128 * SP), (size_t)Cfg::SMEM, st, tq, tk, tv, p));
     NMM_LAUNCHED("spatial_attention_tc_kernel");
     return NMM_OK;
 }
@@ -469,6 +507,9 @@ int launch_spatial_attention_tc(const FlashArgs &a, int variant, cudaStream_t st
     // 100 + bits = timing experiments of the -DNMM_TRACE development build (results invalid; ignored by the production build)
     const int debug = variant >= 100 ? variant - 100 : 0;
     const int sp = variant == 2 ? 2 : 1;
+    if (variant == 16) return a.dh == 40 ? launch_ft<40, 1, 3, false, true>(a, 0, st) : launch_ft<80, 1, 3, false, true>(a, 0, st);     // A/B: cp.async K / V loader
+    if (variant == 17) return a.dh == 40 ? launch_ft<40, 1, 3, true, true>(a, 0, st) : launch_ft<80, 1, 3, true, true>(a, 0, st);
+    if (variant == 15) return a.dh == 40 ? launch_ft<40, 1, 3, true>(a, 0, st) : launch_ft<80, 1, 3, true>(a, 0, st);      // timing experiment: no K / V traffic
     if (variant >= 10 && variant <= 14) {          // A/B: polynomial share 0 / 2 / 3 / 4 / 6 of 8 (one softmax thread per row)
         const int pl = variant - 10;
         if (a.dh == 40) return pl == 0 ? launch_ft<40, 1, 0>(a, 0, st) : pl == 1 ? launch_ft<40, 1, 2>(a, 0, st) : pl == 2 ? launch_ft<40, 1, 3>(a, 0, st) : pl == 3 ? launch_ft<40, 1, 4>(a, 0, st) : launch_ft<40, 1, 6>(a, 0, st);
