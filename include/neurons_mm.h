@@ -127,8 +127,8 @@ typedef enum nmm_option {
     NMM_OPT_FUSED_Y_STATS = 8,  /* nmm_forward_stats on the one-kernel C = 320 path: 1 = y sums emitted from the kernel's y store; 0 (default) =
                                    a statistics pass over the (L2-resident) y, measured faster there.  env NMM_FUSED_Y_STATS          */
     NMM_OPT_FUSED_CLUSTER = 9,  /* 0: CTA pairs when the tile count is even; 1: force the single-CTA fused kernel.  env NMM_FUSED_CLUSTER */
-    NMM_OPT_SPATIAL_ATTN = 10,  /* spatial self-attention (d_h 40 / 80, >= 256 keys): 0 = tcgen05 kernel (planner); 1 = mma.sync kernel;
-                                   2 / 3 = tcgen05 with two / one softmax threads per query row.  env NMM_SPATIAL_ATTN */
+    NMM_OPT_SPATIAL_ATTN = 10,  /* spatial self-attention (d_h 40 / 80, >= 256 keys): 0 = tcgen05 kernel (planner: two query tiles per CTA); 1 = mma.sync kernel;
+                                   other values: A/B variants of the tcgen05 kernel (csrc/spatial_attention_tc.cu).  env NMM_SPATIAL_ATTN */
     NMM_OPT_COUNT = 11
 } nmm_option;
 NMM_API int nmm_set_option(int32_t option, int64_t value);

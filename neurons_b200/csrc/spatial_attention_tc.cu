@@ -429,6 +429,256 @@ spatial_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
     }
 }
 
+// =====================================================================================================================================
+// Two query tiles per CTA (256 queries of one (image, head)), ONE CTA per SM: the same two softmax pipelines per SM as two CTAs of the
+// kernel above, but they share every K / V tile -- half the TMA work per query (the K / V segment rate is what binds that kernel once the
+// SFU is relieved) and room for two-stage K / V rings at d_h = 80 too (192 KB of shared memory, 448 of the 512 TMEM columns).
+// Warps 0-3: softmax of query tile 0, warps 4-7: query tile 1 (warp w and w + 4 own the same TMEM lanes, different columns), warp 8: TMA,
+// warp 9: MMA.  TMEM: S0 [0,128) S1 [128,256) O0 [256, 256+NV) O1 [384, 384+NV).  One softmax thread per row, 3 of 8 exponentials by polynomial.
+template <int DH, int NS_>
+struct Ft2Cfg {
+    using B = FtCfg<DH>;
+    static constexpr int NS = NS_;
+    static constexpr uint32_t OFF_Q = 0, OFF_K = 2 * B::TILE_BYTES, OFF_V = OFF_K + NS * B::TILE_BYTES, OFF_P = OFF_V + NS * B::VTILE_BYTES;
+    static constexpr uint32_t OFF_BAR = OFF_P + 2 * B::P_BYTES;
+    static constexpr uint32_t SMEM = OFF_BAR + 256 + 128;
+};
+
+template <int DH, int NS_>
+__global__ void __launch_bounds__(320, 1)
+spatial_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
+                             const FtParams p) {
+    using Cfg = FtCfg<DH>;
+    using C2 = Ft2Cfg<DH, NS_>;
+    constexpr int DHP = Cfg::DHP, NV = Cfg::NV, CH = Cfg::CH, CHP = Cfg::CHP, CHV = Cfg::CHV, NS = C2::NS, FT_POLY = 3;
+    constexpr int THREADS = 320, W_TMA = 8, W_MMA = 9;
+    extern __shared__ uint8_t ft_smem_raw[];
+    const uint32_t base = (ptx::smem_u32(ft_smem_raw) + 127u) & ~127u;
+    uint8_t *gbase = ft_smem_raw + (base - ptx::smem_u32(ft_smem_raw));
+    const uint32_t s_q = base + C2::OFF_Q, s_k = base + C2::OFF_K, s_v = base + C2::OFF_V, s_p = base + C2::OFF_P, s_bar = base + C2::OFF_BAR;
+    // barriers (8 bytes each): per query tile sfull / sfree / pfull / pv; shared q, K / V rings
+    const uint32_t b_q = s_bar;
+    auto b_sfull = [&](int qt) { return s_bar + 8 + 8 * qt; };
+    auto b_sfree = [&](int qt) { return s_bar + 24 + 8 * qt; };
+    auto b_pfull = [&](int qt) { return s_bar + 40 + 8 * qt; };
+    auto b_pv = [&](int qt) { return s_bar + 56 + 8 * qt; };
+    auto b_kfull = [&](int s) { return s_bar + 72 + 8 * s; };        // up to 4 stages each
+    auto b_kempty = [&](int s) { return s_bar + 104 + 8 * s; };
+    auto b_vfull = [&](int s) { return s_bar + 136 + 8 * s; };
+    auto b_vempty = [&](int s) { return s_bar + 168 + 8 * s; };
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gbase + C2::OFF_BAR + 240);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q0 = blockIdx.x * 2 * FT_BM, head = blockIdx.y, img = blockIdx.z;
+    const int nt = (p.Lkv + FT_BN - 1) / FT_BN;
+
+    if (tid == 0) {
+        ptx::mbar_init(b_q, 1);
+        for (int qt = 0; qt < 2; qt++) { ptx::mbar_init(b_sfull(qt), 1); ptx::mbar_init(b_sfree(qt), 4); ptx::mbar_init(b_pfull(qt), 4); ptx::mbar_init(b_pv(qt), 1); }
+        for (int s = 0; s < NS; s++) { ptx::mbar_init(b_kfull(s), 1); ptx::mbar_init(b_kempty(s), 1); ptx::mbar_init(b_vfull(s), 1); ptx::mbar_init(b_vempty(s), 1); }
+        ptx::fence_mbar_init();
+    }
+    // pad chunks: zeros for Q (2 tiles) and K (NS stages), the ones column for V (see the one-tile kernel)
+    if constexpr (CHP > CH) {
+        for (int i = tid; i < (2 + NS) * (int)(FT_CHUNK / 16); i += THREADS) {
+            const int tile = i / (int)(FT_CHUNK / 16), r = i - tile * (int)(FT_CHUNK / 16);
+            *reinterpret_cast<uint4 *>(gbase + tile * Cfg::TILE_BYTES + CH * FT_CHUNK + r * 16) = make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
+    for (int i = tid; i < NS * (CHV - CH) * (int)(FT_CHUNK / 16); i += THREADS) {
+        const int per = (CHV - CH) * (int)(FT_CHUNK / 16);
+        const int st = i / per, r = i - st * per;
+        *reinterpret_cast<uint4 *>(gbase + C2::OFF_V + st * Cfg::VTILE_BYTES + CH * FT_CHUNK + r * 16) = make_uint4(r < FT_BN ? 0x3F80u : 0u, 0u, 0u, 0u);
+    }
+    ptx::fence_proxy_async();
+    if (warp == W_MMA) ptx::tmem_alloc<1>(ptx::smem_u32(const_cast<uint32_t *>(tmem_slot)), 512);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    pdl_wait();
+    pdl_launch_dependents();
+
+    if (warp == W_TMA) {
+        if (lane == 0) {
+            ptx::prefetch_tensormap(&tm_q); ptx::prefetch_tensormap(&tm_k);
+            ptx::mbar_expect_tx(b_q, 2 * Cfg::TX_BYTES);
+            ptx::tma_load_4d(&tm_q, b_q, s_q, 0, q0, head * CH, img);
+            ptx::tma_load_4d(&tm_q, b_q, s_q + Cfg::TILE_BYTES, 0, q0 + FT_BM, head * CH, img);       // rows past the image: zero-filled
+            for (int t = 0; t < nt; t++) {
+                const int s = t % NS, fill = t / NS;
+                if (fill > 0) ptx::mbar_wait(b_kempty(s), (uint32_t)(fill - 1) & 1u);
+                ptx::mbar_expect_tx(b_kfull(s), Cfg::TX_BYTES);
+                ptx::tma_load_4d(&tm_k, b_kfull(s), s_k + s * Cfg::TILE_BYTES, 0, t * FT_BN, head * CH, img);
+            }
+        } else if (lane == 1) {
+            ptx::prefetch_tensormap(&tm_v);
+            for (int t = 0; t < nt; t++) {
+                const int s = t % NS, fill = t / NS;
+                if (fill > 0) ptx::mbar_wait(b_vempty(s), (uint32_t)(fill - 1) & 1u);
+                ptx::mbar_expect_tx(b_vfull(s), Cfg::TX_BYTES);
+                ptx::tma_load_4d(&tm_v, b_vfull(s), s_v + s * Cfg::VTILE_BYTES, 0, t * FT_BN, head * CH, img);
+            }
+        }
+        __syncwarp();
+    } else if (warp == W_MMA) {
+        const uint32_t idesc_s = ptx::umma_idesc_bf16(FT_BM, FT_BN);
+        const uint32_t idesc_o = ptx::umma_idesc_bf16(FT_BM, NV) | ptx::UMMA_IDESC_B_MN_MAJOR;
+        auto issue_s = [&](int t) {           // S_qt(t) = Q_qt K(t)^T for both query tiles; K(t)'s buffer is released after the second
+            const int s = t % NS;
+            ptx::mbar_wait(b_kfull(s), (uint32_t)(t / NS) & 1u);
+            for (int qt = 0; qt < 2; qt++) {
+                if (t > 0) ptx::mbar_wait(b_sfree(qt), (uint32_t)(t - 1) & 1u);
+                ptx::tc_fence_after();
+                if (ptx::elect_one()) {
+                    const uint64_t a = ptx::umma_smem_desc_interleave(s_q + qt * Cfg::TILE_BYTES, FT_CHUNK, 128);
+                    const uint64_t b = ptx::umma_smem_desc_interleave(s_k + s * Cfg::TILE_BYTES, FT_CHUNK, 128);
+#pragma unroll
+                    for (int k = 0; k < DHP / 16; k++)
+                        ptx::umma_bf16<1>(tmem + qt * 128, a + (uint64_t)((k * 2 * FT_CHUNK) >> 4), b + (uint64_t)((k * 2 * FT_CHUNK) >> 4), idesc_s, k != 0 ? 1u : 0u);
+                    ptx::umma_commit<1>(b_sfull(qt));
+                    if (qt == 1) ptx::umma_commit<1>(b_kempty(s));
+                }
+                __syncwarp();
+            }
+        };
+        ptx::mbar_wait(b_q, 0);
+        issue_s(0);
+        for (int t = 0; t < nt; t++) {
+            if (t + 1 < nt) issue_s(t + 1);
+            const int s = t % NS;
+            ptx::mbar_wait(b_vfull(s), (uint32_t)(t / NS) & 1u);
+            for (int qt = 0; qt < 2; qt++) {
+                ptx::mbar_wait(b_pfull(qt), (uint32_t)t & 1u);
+                ptx::tc_fence_after();
+                if (ptx::elect_one()) {          // O_qt += P_qt(t) V(t)
+                    const uint64_t a = ptx::umma_smem_desc_interleave(s_p + qt * Cfg::P_BYTES, FT_CHUNK, 128);
+                    const uint64_t b = ptx::umma_smem_desc_interleave(s_v + s * Cfg::VTILE_BYTES, 128u, FT_CHUNK);
+#pragma unroll
+                    for (int k = 0; k < FT_BN / 16; k++)
+                        ptx::umma_bf16<1>(tmem + 256 + qt * 128, a + (uint64_t)((k * 2 * FT_CHUNK) >> 4), b + (uint64_t)((k * 16 * 16) >> 4), idesc_o, (t | k) != 0 ? 1u : 0u);
+                    ptx::umma_commit<1>(b_pv(qt));
+                    if (qt == 1) ptx::umma_commit<1>(b_vempty(s));
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===================== softmax of query tile qt: thread = query row = TMEM lane =====================
+        const int qt = warp >> 2, qw = warp & 3, lrow = qw * 32 + lane;
+        const uint32_t t_s = tmem + ((uint32_t)(qw * 32) << 16) + qt * 128, t_o = tmem + ((uint32_t)(qw * 32) << 16) + 256 + qt * 128;
+        const uint32_t prow = s_p + qt * Cfg::P_BYTES + (uint32_t)lrow * 16;
+        const float sl = p.scale_log2e;
+        float m_ref = -INFINITY;
+        for (int t = 0; t < nt; t++) {
+            ptx::mbar_wait(b_sfull(qt), (uint32_t)t & 1u);
+            ptx::tc_fence_after();
+            uint32_t sr[FT_BN];
+#pragma unroll
+            for (int c = 0; c < FT_BN / 32; c++) ptx::tmem_ld32(t_s + c * 32, *reinterpret_cast<uint32_t (*)[32]>(&sr[c * 32]));
+            ptx::tmem_ld_wait();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (ptx::elect_one()) ptx::mbar_arrive(b_sfree(qt));
+            __syncwarp();
+            float *sf = reinterpret_cast<float *>(sr);
+            if ((t + 1) * FT_BN > p.Lkv) {
+                const int valid = p.Lkv - t * FT_BN;
+#pragma unroll
+                for (int c = 0; c < FT_BN; c++)
+                    if (c >= valid) sf[c] = -INFINITY;
+            }
+            float mx4[4] = {sf[0], sf[1], sf[2], sf[3]};
+#pragma unroll
+            for (int c = 4; c < FT_BN; c += 4) {
+                mx4[0] = fmaxf(mx4[0], sf[c]); mx4[1] = fmaxf(mx4[1], sf[c + 1]); mx4[2] = fmaxf(mx4[2], sf[c + 2]); mx4[3] = fmaxf(mx4[3], sf[c + 3]);
+            }
+            const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+            const bool raise = (mx - m_ref) * sl > 8.0f;
+            const float m_new = raise ? mx : m_ref;
+            const float ms = m_new * sl;
+            const uint64_t sl2 = f32x2_pack(sl, sl), nms2 = f32x2_pack(-ms, -ms);
+            auto exp_chunk = [&](int kc, uint32_t (&q)[4]) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const uint64_t x = f32x2_fma(f32x2_pack(sf[kc * 8 + 2 * i], sf[kc * 8 + 2 * i + 1]), sl2, nms2);
+                    float x0, x1, e0, e1;
+                    f32x2_unpack(x, x0, x1);
+                    constexpr int FIRST = 8 - FT_POLY;
+                    if (2 * i >= FIRST) ft_exp2_poly2(x, e0, e1);
+                    else { e0 = ft_exp2(x0); e1 = (2 * i + 1 >= FIRST) ? ft_exp2_poly(x1) : ft_exp2(x1); }
+                    q[i] = pack_bf16x2(e0, e1);
+                }
+            };
+            auto store_chunk = [&](int kc, const uint32_t (&q)[4]) {
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + kc * FT_CHUNK), "r"(q[0]), "r"(q[1]), "r"(q[2]), "r"(q[3]) : "memory");
+            };
+            constexpr int NCH = FT_BN / 8, PRE = NCH / 2;
+            uint32_t pk[PRE][4];
+#pragma unroll
+            for (int kc = 0; kc < PRE; kc++) exp_chunk(kc, pk[kc]);
+            if (t > 0) ptx::mbar_wait(b_pv(qt), (uint32_t)(t - 1) & 1u);
+            if (t > 0 && __any_sync(0xffffffffu, raise)) {
+                const float f = ft_exp2((m_ref - m_new) * sl);
+                ptx::tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < NV; c += 16) {
+                    uint32_t orow[16];
+                    ptx::tmem_ld16(t_o + c, orow);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; i++) orow[i] = __float_as_uint(__uint_as_float(orow[i]) * f);
+                    ptx::tmem_st16(t_o + c, orow);
+                }
+                ptx::tmem_st_wait();
+            }
+            m_ref = m_new;
+#pragma unroll
+            for (int kc = 0; kc < PRE; kc++) {
+                store_chunk(kc, pk[kc]);
+                uint32_t q[4];
+                exp_chunk(PRE + kc, q);
+                store_chunk(PRE + kc, q);
+            }
+            ptx::fence_proxy_async();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (ptx::elect_one()) ptx::mbar_arrive(b_pfull(qt));
+            __syncwarp();
+        }
+        ptx::mbar_wait(b_pv(qt), (uint32_t)(nt - 1) & 1u);
+        ptx::tc_fence_after();
+        const uint32_t lraw = ptx::tmem_ld1(t_o + DH);
+        ptx::tmem_ld_wait();
+        const float inv = 1.0f / __uint_as_float(lraw);
+        const int row = q0 + qt * FT_BM + lrow;
+        bf16 *og = (bf16 *)p.o + (int64_t)img * p.o_bs + (int64_t)row * p.o_rs + head * DH;
+#pragma unroll
+        for (int c = 0; c < CH; c += 2) {
+            uint32_t orow[16];
+            ptx::tmem_ld16(t_o + c * 8, orow);
+            ptx::tmem_ld_wait();
+            if (row < p.Lq) {
+                *reinterpret_cast<uint4 *>(og + c * 8) = make_uint4(pack_bf16x2(__uint_as_float(orow[0]) * inv, __uint_as_float(orow[1]) * inv),
+                                                                     pack_bf16x2(__uint_as_float(orow[2]) * inv, __uint_as_float(orow[3]) * inv),
+                                                                     pack_bf16x2(__uint_as_float(orow[4]) * inv, __uint_as_float(orow[5]) * inv),
+                                                                     pack_bf16x2(__uint_as_float(orow[6]) * inv, __uint_as_float(orow[7]) * inv));
+                if (c + 1 < CH)
+                    *reinterpret_cast<uint4 *>(og + c * 8 + 8) = make_uint4(pack_bf16x2(__uint_as_float(orow[8]) * inv, __uint_as_float(orow[9]) * inv),
+                                                                             pack_bf16x2(__uint_as_float(orow[10]) * inv, __uint_as_float(orow[11]) * inv),
+                                                                             pack_bf16x2(__uint_as_float(orow[12]) * inv, __uint_as_float(orow[13]) * inv),
+                                                                             pack_bf16x2(__uint_as_float(orow[14]) * inv, __uint_as_float(orow[15]) * inv));
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == W_MMA) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<1>(tmem, 512);
+    }
+}
+
 // ---- host side ----------------------------------------------------------------------------------------------------------------------
 typedef CUresult (*FtEncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
                                     const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -501,12 +751,38 @@ static int launch_ft(const FlashArgs &a, int debug, cudaStream_t st) {
     return NMM_OK;
 }
 
+template <int DH, int NS>
+static int launch_ft2(const FlashArgs &a, cudaStream_t st) {
+    using C2 = Ft2Cfg<DH, NS>;
+    static DeviceOnce once;
+    NMM_CUDA_OK(once.max_smem(spatial_attention_tc2_kernel<DH, NS>, (int)C2::SMEM));
+    CUtensorMap tq, tk, tv;
+    int rc;
+    if ((rc = ft_map(&tq, a.q, a.Lq, a.q_rs, a.q_bs, a.images, DH)) != NMM_OK) return rc;
+    if ((rc = ft_map(&tk, a.k, a.Lkv, a.kv_rs, a.kv_bs, a.images, DH)) != NMM_OK) return rc;
+    if ((rc = ft_map(&tv, a.v, a.Lkv, a.kv_rs, a.kv_bs, a.images, DH)) != NMM_OK) return rc;
+    FtParams p;
+    memset(&p, 0, sizeof(p));
+    p.o = a.o; p.o_rs = a.o_rs; p.o_bs = a.o_bs; p.Lq = a.Lq; p.Lkv = a.Lkv; p.scale_log2e = a.scale_log2e;
+    const dim3 grid((unsigned)ceil_div(a.Lq, 2 * FT_BM), (unsigned)a.heads, (unsigned)a.images);
+    const double per = (double)a.images * a.heads;
+    ProfScope prof(K_SPATIAL_ATTN, st, 4.0 * per * a.Lq * (double)a.Lkv * DH, 2.0 * 4.0 * per * a.Lq * DH);
+    NMM_CUDA_OK(launch_pdl(spatial_attention_tc2_kernel<DH, NS>, grid, dim3(320), (size_t)C2::SMEM, st, tq, tk, tv, p));
+    NMM_LAUNCHED("spatial_attention_tc2_kernel");
+    return NMM_OK;
+}
+
 int launch_spatial_attention_tc(const FlashArgs &a, int variant, cudaStream_t st) {
+    // default: two query tiles per CTA (one CTA per SM; K / V tiles shared by the two softmax pipelines; 3 K / V stages at d_h = 40, 2 at 80).  20 / 21 / 22: force 2 / 3 / 4 K / V stages
+    // (d_h = 80: 2 only); 23: the one-tile kernel (two CTAs per SM) that the variants below select explicitly
+    if (variant == 0 || variant == 21) return a.dh == 40 ? launch_ft2<40, 3>(a, st) : launch_ft2<80, 2>(a, st);
+    if (variant == 20) return a.dh == 40 ? launch_ft2<40, 2>(a, st) : launch_ft2<80, 2>(a, st);
+    if (variant == 22) return a.dh == 40 ? launch_ft2<40, 4>(a, st) : launch_ft2<80, 2>(a, st);
     // NMM_OPT_SPATIAL_ATTN: 0 / 3 = one softmax thread per query row (measured faster once the polynomial share relieved the SFU), 2 = two;
     // 10..14 = polynomial share 0 / 2 / 3 / 4 / 6 of 8 (A/B; 3 is the default);
     // 100 + bits = timing experiments of the -DNMM_TRACE development build (results invalid; ignored by the production build)
     const int debug = variant >= 100 ? variant - 100 : 0;
-    const int sp = variant == 2 ? 2 : 1;
+    const int sp = variant == 2 ? 2 : 1;      // (variant 3 / 23: one thread per row, one query tile per CTA)
     if (variant == 16) return a.dh == 40 ? launch_ft<40, 1, 3, false, true>(a, 0, st) : launch_ft<80, 1, 3, false, true>(a, 0, st);     // A/B: cp.async K / V loader
     if (variant == 17) return a.dh == 40 ? launch_ft<40, 1, 3, true, true>(a, 0, st) : launch_ft<80, 1, 3, true, true>(a, 0, st);
     if (variant == 15) return a.dh == 40 ? launch_ft<40, 1, 3, true>(a, 0, st) : launch_ft<80, 1, 3, true>(a, 0, st);      // timing experiment: no K / V traffic

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Development probe: the spatial-attention kernels against an fp64 softmax attention, for the run-time variants of NMM_OPT_SPATIAL_ATTN
-(0 = tcgen05 kernel as planned, 1 = mma.sync kernel, 2 = tcgen05 with two softmax threads per query row, 10..14 = polynomial-ex2 share
-0 / 2 / 3 / 4 / 6 of 8), plus timing at the 64 x 64 (d_h 40) and 32 x 32 (d_h 80) levels.   python scripts/spatial_attn_probe.py 1,0,2"""
+(0 = tcgen05 kernel as planned: two query tiles per CTA; 1 = mma.sync kernel; 23 = one query tile per CTA, two CTAs per SM; 2 = that with two
+softmax threads per query row; 10..14 = polynomial-ex2 share 0 / 2 / 3 / 4 / 6 of 8; 15 = no K / V traffic (timing only); 16 = cp.async loader;
+20 / 21 / 22 = two query tiles with 2 / 3 / 4 K / V stages), plus timing at the 64 x 64 (d_h 40) and 32 x 32 (d_h 80) levels.   python scripts/spatial_attn_probe.py 1,0,2"""
 import os
 import sys
 
