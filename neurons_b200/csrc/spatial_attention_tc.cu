@@ -53,6 +53,7 @@ struct FtParams {
     const void *k, *v;          // cp.async loader (CPA): K / V base pointers (column slice of the projection output), row / image strides
     int64_t kv_rs, kv_bs;
     int Lq, Lkv;
+    int kv_div;                 // K / V image of query image i = i / kv_div (text cross-attention: the frames of a clip share K / V)
     float scale_log2e;
 #ifdef NMM_TRACE                // development build only (python -m neurons_b200.build --trace): timing experiments + per-tile timeline
     unsigned long long *trace;  // per-tile clock64 timeline of CTA (0,0,0), [role 0 softmax / 1 mma][tile < 16][event < 8], or null
@@ -471,6 +472,7 @@ spatial_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __g
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q0 = blockIdx.x * 2 * FT_BM, head = blockIdx.y, img = blockIdx.z;
     const int nt = (p.Lkv + FT_BN - 1) / FT_BN;
+    const int kv_img = img / p.kv_div;
 
     if (tid == 0) {
         ptx::mbar_init(b_q, 1);
@@ -509,7 +511,7 @@ spatial_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __g
                 const int s = t % NS, fill = t / NS;
                 if (fill > 0) ptx::mbar_wait(b_kempty(s), (uint32_t)(fill - 1) & 1u);
                 ptx::mbar_expect_tx(b_kfull(s), Cfg::TX_BYTES);
-                ptx::tma_load_4d(&tm_k, b_kfull(s), s_k + s * Cfg::TILE_BYTES, 0, t * FT_BN, head * CH, img);
+                ptx::tma_load_4d(&tm_k, b_kfull(s), s_k + s * Cfg::TILE_BYTES, 0, t * FT_BN, head * CH, kv_img);
             }
         } else if (lane == 1) {
             ptx::prefetch_tensormap(&tm_v);
@@ -517,7 +519,7 @@ spatial_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __g
                 const int s = t % NS, fill = t / NS;
                 if (fill > 0) ptx::mbar_wait(b_vempty(s), (uint32_t)(fill - 1) & 1u);
                 ptx::mbar_expect_tx(b_vfull(s), Cfg::TX_BYTES);
-                ptx::tma_load_4d(&tm_v, b_vfull(s), s_v + s * Cfg::VTILE_BYTES, 0, t * FT_BN, head * CH, img);
+                ptx::tma_load_4d(&tm_v, b_vfull(s), s_v + s * Cfg::VTILE_BYTES, 0, t * FT_BN, head * CH, kv_img);
             }
         }
         __syncwarp();
@@ -718,7 +720,9 @@ extern "C" __attribute__((visibility("default"))) int nmm_debug_ft_trace(unsigne
 #endif
 
 bool spatial_attention_tc_eligible(const FlashArgs &a) {
-    if (a.dtype != NMM_BF16 || (a.dh != 40 && a.dh != 80) || a.kv_div != 1 || a.Lkv < 256) return false;
+    if (a.dtype != NMM_BF16 || (a.dh != 40 && a.dh != 80) || a.images % a.kv_div != 0) return false;
+    // self-attention from 256 keys up; the 77-key text cross-attention (kv_div > 1) only behind NMM_OPT_SPATIAL_ATTN = 24 (A/B)
+    if (a.kv_div != 1 || a.Lkv < 256) { if (opt(NMM_OPT_SPATIAL_ATTN) != 24) return false; }
     // the tensor maps address whole rows: a row stride that covers the row's channels and image strides that are whole rows
     return a.q_rs % 8 == 0 && a.kv_rs % 8 == 0 && a.q_bs % 8 == 0 && a.kv_bs % 8 == 0 && a.o_rs % 8 == 0 && a.o_bs % 8 == 0 && aligned(a.q, 16) &&
            aligned(a.k, 16) && aligned(a.v, 16) && aligned(a.o, 16);
@@ -737,7 +741,7 @@ static int launch_ft(const FlashArgs &a, int debug, cudaStream_t st) {
     if ((rc = ft_map(&tk, a.k, a.Lkv, a.kv_rs, a.kv_bs, a.images, DH)) != NMM_OK) return rc;
     if ((rc = ft_map(&tv, a.v, a.Lkv, a.kv_rs, a.kv_bs, a.images, DH)) != NMM_OK) return rc;
     FtParams p;
-    p.o = a.o; p.o_rs = a.o_rs; p.o_bs = a.o_bs; p.k = a.k; p.v = a.v; p.kv_rs = a.kv_rs; p.kv_bs = a.kv_bs; p.Lq = a.Lq; p.Lkv = a.Lkv; p.scale_log2e = a.scale_log2e;
+    p.o = a.o; p.o_rs = a.o_rs; p.o_bs = a.o_bs; p.k = a.k; p.v = a.v; p.kv_rs = a.kv_rs; p.kv_bs = a.kv_bs; p.Lq = a.Lq; p.Lkv = a.Lkv; p.kv_div = 1; p.scale_log2e = a.scale_log2e;
 #ifdef NMM_TRACE
     p.debug = debug & 15; p.trace = g_ft_trace;
 #else
@@ -759,11 +763,11 @@ static int launch_ft2(const FlashArgs &a, cudaStream_t st) {
     CUtensorMap tq, tk, tv;
     int rc;
     if ((rc = ft_map(&tq, a.q, a.Lq, a.q_rs, a.q_bs, a.images, DH)) != NMM_OK) return rc;
-    if ((rc = ft_map(&tk, a.k, a.Lkv, a.kv_rs, a.kv_bs, a.images, DH)) != NMM_OK) return rc;
-    if ((rc = ft_map(&tv, a.v, a.Lkv, a.kv_rs, a.kv_bs, a.images, DH)) != NMM_OK) return rc;
+    if ((rc = ft_map(&tk, a.k, a.Lkv, a.kv_rs, a.kv_bs, a.images / a.kv_div, DH)) != NMM_OK) return rc;
+    if ((rc = ft_map(&tv, a.v, a.Lkv, a.kv_rs, a.kv_bs, a.images / a.kv_div, DH)) != NMM_OK) return rc;
     FtParams p;
     memset(&p, 0, sizeof(p));
-    p.o = a.o; p.o_rs = a.o_rs; p.o_bs = a.o_bs; p.Lq = a.Lq; p.Lkv = a.Lkv; p.scale_log2e = a.scale_log2e;
+    p.o = a.o; p.o_rs = a.o_rs; p.o_bs = a.o_bs; p.Lq = a.Lq; p.Lkv = a.Lkv; p.kv_div = a.kv_div; p.scale_log2e = a.scale_log2e;
     const dim3 grid((unsigned)ceil_div(a.Lq, 2 * FT_BM), (unsigned)a.heads, (unsigned)a.images);
     const double per = (double)a.images * a.heads;
     ProfScope prof(K_SPATIAL_ATTN, st, 4.0 * per * a.Lq * (double)a.Lkv * DH, 2.0 * 4.0 * per * a.Lq * DH);
@@ -775,7 +779,7 @@ static int launch_ft2(const FlashArgs &a, cudaStream_t st) {
 int launch_spatial_attention_tc(const FlashArgs &a, int variant, cudaStream_t st) {
     // default: two query tiles per CTA (one CTA per SM; K / V tiles shared by the two softmax pipelines; 3 K / V stages at d_h = 40, 2 at 80).  20 / 21 / 22: force 2 / 3 / 4 K / V stages
     // (d_h = 80: 2 only); 23: the one-tile kernel (two CTAs per SM) that the variants below select explicitly
-    if (variant == 0 || variant == 21) return a.dh == 40 ? launch_ft2<40, 3>(a, st) : launch_ft2<80, 2>(a, st);
+    if (variant == 0 || variant == 21 || variant == 24) return a.dh == 40 ? launch_ft2<40, 3>(a, st) : launch_ft2<80, 2>(a, st);
     if (variant == 20) return a.dh == 40 ? launch_ft2<40, 2>(a, st) : launch_ft2<80, 2>(a, st);
     if (variant == 22) return a.dh == 40 ? launch_ft2<40, 4>(a, st) : launch_ft2<80, 2>(a, st);
     // NMM_OPT_SPATIAL_ATTN: 0 / 3 = one softmax thread per query row (measured faster once the polynomial share relieved the SFU), 2 = two;
