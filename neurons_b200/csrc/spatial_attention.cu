@@ -20,18 +20,20 @@
 
 namespace nmm {
 
-constexpr int FA_BM = 128;      // queries per CTA
 constexpr int FA_BN = 64;       // keys per compute tile (S fragment = 16 x 64 per warp)
 constexpr int FA_ST = 128;      // keys per pipeline stage = two compute tiles per __syncthreads (barrier stalls were 11 % of issue slots at 64)
-constexpr int FA_THREADS = 256;
 
-template <int DH>
+// WARPS = 8 (128 queries per CTA) for the self-attention, 4 (64 queries per CTA, twice the CTAs per SM) for short key sequences -- the
+// 77-token text cross-attention is a single key stage per CTA and lives on latency hiding across CTAs, not on K / V reuse.
+template <int DH, int WARPS = 8>
 struct FaCfg {
+    static constexpr int FA_BM = 16 * WARPS, FA_THREADS = 32 * WARPS;
     static constexpr int PITCH = ((DH / 8) % 2 == 1) ? DH : DH + 8;     // elements
     static constexpr int CH = DH / 8;                                   // 16-byte chunks per row
     static constexpr int Q_BYTES = FA_BM * PITCH * 2;
     static constexpr int KV_BYTES = FA_ST * PITCH * 2;
-    static constexpr int SMEM = Q_BYTES + 4 * KV_BYTES;                 // Q | K stage 0, 1 | V stage 0, 1
+    static constexpr int STAGES = WARPS == 8 ? 2 : 1;                   // the 4-warp variant only ever sees one key stage (<= 128 keys)
+    static constexpr int SMEM = Q_BYTES + 2 * STAGES * KV_BYTES;        // Q | K stages | V stages
     static constexpr int KS16 = DH / 16;                                // full k16 steps of S = Q K^T
     static constexpr bool TAIL8 = (DH % 16) == 8;
     static constexpr int NT = DH / 8;                                   // n8 tiles of O
@@ -51,9 +53,10 @@ __device__ __forceinline__ float fast_exp2(float x) {
 }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int DH>
-__global__ void __launch_bounds__(FA_THREADS, DH <= 80 ? 2 : 1) spatial_attention_kernel(const FlashArgs a) {
-    using Cfg = FaCfg<DH>;
+template <int DH, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS, DH <= 80 ? 16 / WARPS : 8 / WARPS) spatial_attention_kernel(const FlashArgs a) {
+    using Cfg = FaCfg<DH, WARPS>;
+    constexpr int FA_BM = Cfg::FA_BM, FA_THREADS = Cfg::FA_THREADS;
     constexpr int PITCH = Cfg::PITCH, CH = Cfg::CH, NT = Cfg::NT, KS16 = Cfg::KS16;
     extern __shared__ __align__(128) uint8_t fa_smem[];
     pdl_wait();
@@ -65,7 +68,7 @@ __global__ void __launch_bounds__(FA_THREADS, DH <= 80 ? 2 : 1) spatial_attentio
     const bf16 *kg = (const bf16 *)a.k + (int64_t)kv_img * a.kv_bs + head * DH;
     const bf16 *vg = (const bf16 *)a.v + (int64_t)kv_img * a.kv_bs + head * DH;
     const uint32_t sq = (uint32_t)__cvta_generic_to_shared(fa_smem);
-    const uint32_t sk0 = sq + Cfg::Q_BYTES, sv0 = sk0 + 2 * Cfg::KV_BYTES;
+    const uint32_t sk0 = sq + Cfg::Q_BYTES, sv0 = sk0 + Cfg::STAGES * Cfg::KV_BYTES;
     const int Lq = a.Lq, Lkv = a.Lkv;
 
     for (int i = tid; i < FA_BM * CH; i += FA_THREADS) {
@@ -275,18 +278,25 @@ __global__ void __launch_bounds__(128) spatial_attention_f32_kernel(const float 
     }
 }
 
-template <int DH>
-static int launch_flash_t(const FlashArgs &a, cudaStream_t st) {
-    using Cfg = FaCfg<DH>;
+template <int DH, int WARPS>
+static int launch_flash_w(const FlashArgs &a, cudaStream_t st) {
+    using Cfg = FaCfg<DH, WARPS>;
     static DeviceOnce once;
-    NMM_CUDA_OK(once.max_smem(spatial_attention_kernel<DH>, Cfg::SMEM));
-    const dim3 grid((unsigned)ceil_div(a.Lq, FA_BM), (unsigned)a.heads, (unsigned)a.images);
+    NMM_CUDA_OK(once.max_smem(spatial_attention_kernel<DH, WARPS>, Cfg::SMEM));
+    const dim3 grid((unsigned)ceil_div(a.Lq, Cfg::FA_BM), (unsigned)a.heads, (unsigned)a.images);
     const double per = (double)a.images * a.heads;
     ProfScope prof(K_SPATIAL_ATTN, st, 4.0 * per * a.Lq * (double)a.Lkv * DH,
                    2.0 * (2.0 * per * a.Lq * DH + 2.0 * per / a.kv_div * a.Lkv * DH));
-    NMM_CUDA_OK(launch_pdl(spatial_attention_kernel<DH>, grid, dim3(FA_THREADS), (size_t)Cfg::SMEM, st, a));
+    NMM_CUDA_OK(launch_pdl(spatial_attention_kernel<DH, WARPS>, grid, dim3(Cfg::FA_THREADS), (size_t)Cfg::SMEM, st, a));
     NMM_LAUNCHED("spatial_attention_kernel");
     return NMM_OK;
+}
+
+template <int DH>
+static int launch_flash_t(const FlashArgs &a, cudaStream_t st) {
+    // one key stage (<= 128 keys: the text cross-attention) and enough queries to fill the GPU with the smaller CTAs
+    if (a.Lkv <= FA_ST && opt(NMM_OPT_SPATIAL_ATTN) != 25) return launch_flash_w<DH, 4>(a, st);
+    return launch_flash_w<DH, 8>(a, st);
 }
 
 template <int DH>
