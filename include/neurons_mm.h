@@ -301,6 +301,11 @@ NMM_API int nmm_spatial_pack_params(const nmm_spatial_shape *s, const nmm_spatia
  * same element type.  Same ownership / stream / graph-capture rules as nmm_forward. */
 NMM_API int nmm_spatial_forward(const nmm_spatial_shape *s, const void *x, const void *encoder_hidden_states, void *y, const void *packed,
                                 size_t packed_bytes, void *workspace, size_t workspace_bytes, void *stream);
+/* nmm_spatial_forward that also emits the GroupNorm sums of y ("sums" format of nmm_forward_stats: fp64 [B*F*32][2]) from proj_out's
+ * epilogue: the motion module called next on y (unet_blocks.py:409-411) takes them as x_sums and skips its statistics pass over y --
+ * SURVEY 8(f) N1 with the real producer.  y_sums may be NULL. */
+NMM_API int nmm_spatial_forward_stats(const nmm_spatial_shape *s, const void *x, const void *encoder_hidden_states, void *y, const void *packed,
+                                      size_t packed_bytes, void *workspace, size_t workspace_bytes, double *y_sums, void *stream);
 /* softmax(q k^T / sqrt(head_dim)) v per (image, head), flash-style (scores never materialised): CrossAttention._attention,
  * motion_module_new.py:258-287, with the head split / merge of :181-193 folded into the indexing.  q: `images` x [q_len rows] of
  * heads * head_dim channels at the given row / image strides (elements); k, v: [kv_len rows] per kv image, kv image of q image i =

@@ -14,6 +14,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "epilogue.cuh"
 
 namespace nmm {
 namespace {
@@ -58,7 +59,7 @@ SpLayout sp_layout(const Geo &g, int ctx_dim) {
     return L;
 }
 
-struct SpWork { size_t gn_partial, tok, h, big, ctx, kv, total; };
+struct SpWork { size_t gn_partial, tok, h, big, ctx, kv, stat_part, total; };
 SpWork sp_work(const Geo &g, int ctx_len) {
     SpWork w;
     size_t off = 0;
@@ -72,6 +73,7 @@ SpWork sp_work(const Geo &g, int ctx_len) {
     w.big = take(N * 4 * C * std::max(opnd, es));
     w.ctx = take(N * C * std::max(opnd, es));
     w.kv = take((size_t)g.B * ctx_len * 2 * C * 4);
+    w.stat_part = take((N + 31) / 32 * C * sizeof(float2));      // N1: (sum, sum of squares) partials of y per 32-row block and channel
     w.total = off;
     return w;
 }
@@ -185,8 +187,8 @@ int nmm_spatial_attention(int32_t dtype, const void *q, const void *k, const voi
     return launch_spatial_attention(a, (cudaStream_t)stream);
 }
 
-int nmm_spatial_forward(const nmm_spatial_shape *s, const void *x, const void *encoder_hidden_states, void *y, const void *packed, size_t packed_bytes,
-                        void *workspace, size_t workspace_bytes, void *stream) {
+static int spatial_forward_impl(const nmm_spatial_shape *s, const void *x, const void *encoder_hidden_states, void *y, const void *packed, size_t packed_bytes,
+                                void *workspace, size_t workspace_bytes, double *y_sums, void *stream) {
     int rc = sp_validate(s);
     if (rc != NMM_OK) return rc;
     if (!x || !y || !packed || !workspace || !encoder_hidden_states) return fail(NMM_ERR_BAD_ARG, "NULL argument");
@@ -276,7 +278,31 @@ int nmm_spatial_forward(const nmm_spatial_shape *s, const void *x, const void *e
     // y = proj_out(h) back in NCHW + x, stored as [B, F, C, H, W]                         :130-144
     a.epilogue = NMM_EPI_OUTPUT; a.N = C; a.K = C; a.A = (g.dtype == NMM_BF16) ? (const void *)tok : (const void *)h;
     a.W = pk + L.w_out; a.bias = F32(L.b_out); a.h = nullptr; a.out = nullptr; a.x = x; a.y = y;
-    return linear_dispatch(g.dtype, a, st);
+    // N1: the GroupNorm sums of y for the motion module that consumes it next (unet_blocks.py:409-411) -- emitted by this epilogue
+    // (bf16 vector path; per 32-row block and channel, then one warp per (image, group) in a fixed order: no atomics), else one pass over y
+    float2 *stat_part = (float2 *)(ws + w.stat_part);
+    const bool emit = y_sums != nullptr && g.dtype == NMM_BF16 && output_vec_ok(a);
+    a.y_part = emit ? stat_part : nullptr;
+    if ((rc = linear_dispatch(g.dtype, a, st)) != NMM_OK) return rc;
+    if (emit) return launch_y_sums_channels(stat_part, y_sums, g.B * g.F, g.C, g.P, st);
+    if (y_sums != nullptr) {
+        nmm_shape sy = *bs;
+        sy.x_stride_b = bs->y_stride_b; sy.x_stride_c = bs->y_stride_c; sy.x_stride_f = bs->y_stride_f;
+        if ((rc = launch_gn_stats(g, &sy, y, gn_partial, st)) != NMM_OK) return rc;
+        return launch_gn_partial_to_sums(g, gn_partial, y_sums, st);
+    }
+    return NMM_OK;
+}
+
+int nmm_spatial_forward(const nmm_spatial_shape *s, const void *x, const void *encoder_hidden_states, void *y, const void *packed, size_t packed_bytes,
+                        void *workspace, size_t workspace_bytes, void *stream) {
+    return spatial_forward_impl(s, x, encoder_hidden_states, y, packed, packed_bytes, workspace, workspace_bytes, nullptr, stream);
+}
+
+int nmm_spatial_forward_stats(const nmm_spatial_shape *s, const void *x, const void *encoder_hidden_states, void *y, const void *packed,
+                              size_t packed_bytes, void *workspace, size_t workspace_bytes, double *y_sums, void *stream) {
+    if (y_sums != nullptr && !aligned(y_sums, 16)) return fail(NMM_ERR_BAD_ARG, "y_sums must be 16-byte aligned");
+    return spatial_forward_impl(s, x, encoder_hidden_states, y, packed, packed_bytes, workspace, workspace_bytes, y_sums, stream);
 }
 
 }  // extern "C"

@@ -122,6 +122,8 @@ SIGNATURES = {
     "nmm_decoder_attn_workspace_bytes": (C.c_int, [_SP, C.POINTER(C.c_size_t)]),
     "nmm_decoder_attn_pack": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(DecoderAttnParams), C.c_float, C.c_float, C.c_void_p, C.c_size_t, C.c_void_p]),
     "nmm_decoder_temporal_attention": (C.c_int, [_SP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "nmm_spatial_forward_stats": (C.c_int, [_SSP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p,
+                                            C.c_void_p]),
     "nmm_spatial_attention": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                         C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
 }

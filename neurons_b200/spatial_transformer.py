@@ -195,7 +195,7 @@ def pack_spatial_params(cfg: SpatialConfig, tensors: Dict[str, torch.Tensor], co
 
 
 def spatial_forward_packed(x: torch.Tensor, encoder_hidden_states: torch.Tensor, packed: torch.Tensor, cfg: SpatialConfig,
-                           shape_cache: Optional[dict] = None) -> torch.Tensor:
+                           shape_cache: Optional[dict] = None, y_sums: Optional[torch.Tensor] = None) -> torch.Tensor:
     """y = Transformer3DModel(x, encoder_hidden_states).sample through nmm_spatial_forward: logical [B,C,F,H,W] over [B,F,C,H,W] storage
     (the strides attention.py:139's rearrange gives)."""
     ops._require_cuda(x, "hidden_states")
@@ -225,8 +225,13 @@ def spatial_forward_packed(x: torch.Tensor, encoder_hidden_states: torch.Tensor,
     s, ws_bytes = hit
     ws, ws_ptr = ops._aligned_ws(ws_bytes, x.device)
     with torch.cuda.device(x.device):
-        _lib.check(lib.nmm_spatial_forward(C.byref(s), x.data_ptr(), ehs.data_ptr(), out.data_ptr(), packed.data_ptr(), packed.numel(), ws_ptr,
-                                           ws_bytes, ops._stream_ptr(x.device)))
+        if y_sums is not None:
+            ops._check_sums(y_sums, x, "y_sums")
+            _lib.check(lib.nmm_spatial_forward_stats(C.byref(s), x.data_ptr(), ehs.data_ptr(), out.data_ptr(), packed.data_ptr(), packed.numel(), ws_ptr,
+                                                     ws_bytes, y_sums.data_ptr(), ops._stream_ptr(x.device)))
+        else:
+            _lib.check(lib.nmm_spatial_forward(C.byref(s), x.data_ptr(), ehs.data_ptr(), out.data_ptr(), packed.data_ptr(), packed.numel(), ws_ptr,
+                                               ws_bytes, ops._stream_ptr(x.device)))
     return out
 
 
@@ -280,20 +285,31 @@ def spatial_forward(module: nn.Module, hidden_states: torch.Tensor, encoder_hidd
         raise RuntimeError("neurons_b200: the spatial-transformer op is inference-only; call it under torch.no_grad()")
     eng = _engine_of(module)
     cfg, packed = eng.get(module, hidden_states)
-    return spatial_forward_packed(hidden_states, encoder_hidden_states, packed, cfg, shape_cache=eng.shape_cache)
+    if not module.__dict__.get("_nmm_carry_stats", False):
+        return spatial_forward_packed(hidden_states, encoder_hidden_states, packed, cfg, shape_cache=eng.shape_cache)
+    # patch_spatial(model, carry_stats=True): proj_out's epilogue also emits the GroupNorm sums of the output; they ride on the tensor to
+    # the motion module called next (patch(model, carry_stats=True)), which then skips its statistics pass
+    from .motion_module import attach_sums
+    B, _, F = hidden_states.shape[:3]
+    y_sums = torch.empty((B * F * 32, 2), dtype=torch.float64, device=hidden_states.device)
+    y = spatial_forward_packed(hidden_states, encoder_hidden_states, packed, cfg, shape_cache=eng.shape_cache, y_sums=y_sums)
+    attach_sums(y, y_sums)
+    return y
 
 
 def _is_spatial_transformer(m: nn.Module) -> bool:
     return type(m).__name__ == "Transformer3DModel" and hasattr(m, "transformer_blocks") and hasattr(m, "proj_in")
 
 
-def patch_spatial(model: nn.Module) -> int:
-    """Rebind `forward` on every Transformer3DModel inside `model` (reference instances included).  Returns the number patched
+def patch_spatial(model: nn.Module, carry_stats: bool = False) -> int:
+    """Rebind `forward` on every Transformer3DModel inside `model` (reference instances included).  carry_stats=True: each call also emits
+    the GroupNorm sums of its output for the motion module behind it (use with patch(model, carry_stats=True)).  Returns the number patched
     (16 in the SD-1.5 UNet3DConditionModel, 7 in SparseControlNetModel); unsupported configurations raise here."""
     n = 0
     for m in model.modules():
         if _is_spatial_transformer(m):
             spatial_config_of(m)
+            m.__dict__["_nmm_carry_stats"] = bool(carry_stats)
             out_cls = getattr(sys.modules.get(type(m).__module__), "Transformer3DModelOutput", Transformer3DModelOutput)
 
             def _fwd(self, hidden_states, encoder_hidden_states=None, timestep=None, return_dict: bool = True, _out=out_cls):

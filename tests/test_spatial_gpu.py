@@ -115,3 +115,40 @@ def test_spatial_then_motion_chain():
         assert nb.launch_count() > n0
         ref = mo.forward_reference_order(mparams, so.forward_reference_order(params, x, ctx, cfg), mcfg)
     assert (y.cpu() - ref).abs().max().item() <= 2 * TOL_FP32
+
+
+@pytest.mark.parametrize("C,side", [(640, 16), (320, 16)])
+def test_spatial_emits_groupnorm_sums_for_the_motion_module(C, side):
+    """SURVEY 8(f) N1 with its real producer: patch_spatial(carry_stats=True) makes proj_out's epilogue emit the GroupNorm sums of the
+    spatial transformer's output; the motion module behind it (patch(carry_stats=True)) takes them instead of running its own statistics
+    pass.  Same result (the sums are those of y as stored), one gn_stats launch fewer per block."""
+    import torch.nn as nn
+    import neurons_b200 as nb
+    from neurons_b200 import lib as nlib
+    from oracle import motion_oracle as mo
+    from tests.helpers import mirror_module
+    cfg = so.SpatialConfig(C, 8, 1, 768, True)
+    params = {k: round_bf16(v) for k, v in so.make_params(cfg, 3).items()}
+    x, ctx = so.make_inputs(cfg, 2, 8, side, side, 77, 4)
+    mcfg = mo.MotionConfig(C, 8, 1, 2, True, 24)
+    mparams = mo.make_params(mcfg, 5)
+    with torch.no_grad():
+        holder = nn.Module()
+        holder.sp = _mirror(cfg, params, torch.bfloat16)
+        holder.mm = mirror_module(mcfg, mparams, device="cuda", dtype=torch.bfloat16)
+        xb, cb = x.cuda().bfloat16(), ctx.cuda().bfloat16()
+
+        def run():
+            nlib.profile_begin()
+            y = holder.mm(holder.sp(xb, encoder_hidden_states=cb).sample, None, None)
+            prof = nlib.profile_end()
+            return y.float().cpu(), prof["gn_stats"]["launches"]
+        assert nb.patch(holder, carry_stats=True) == 1        # the motion module emits the sums of ITS output in both runs (a statistics pass
+        y0, n0 = run()                                        # on the one-kernel C = 320 path, proj_out's epilogue elsewhere)
+        assert nb.patch_spatial(holder, carry_stats=True) == 1
+        y1, n1 = run()
+        sums = nb.carried_sums(holder.sp(xb, encoder_hidden_states=cb).sample)
+        ref = nb.ops.groupnorm_sums(holder.sp(xb, encoder_hidden_states=cb).sample)
+    assert n1 == n0 - 1, (n0, n1)           # the motion module's statistics pass over its input is gone
+    assert sums is not None and torch.allclose(sums, ref, rtol=1e-5, atol=1e-3)
+    assert (y1 - y0).abs().max().item() <= 2.0 ** -6
