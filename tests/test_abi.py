@@ -87,3 +87,46 @@ def test_compute_refuses_without_gpu(built_library):
     rc = built_library.nmm_temporal_attention(C.byref(s), buf, buf, None)
     assert rc == -5      # NMM_ERR_DEVICE: no fallback
     assert b"CUDA" in built_library.nmm_last_error()
+
+
+def _spatial_shape(ctx_len=77, ctx_dim=768, **kw):
+    s = nlib.SpatialShape()
+    b = _shape(**kw)
+    for name, _ in nlib.Shape._fields_:
+        setattr(s.base, name, getattr(b, name))
+    s.ctx_len, s.ctx_dim = ctx_len, ctx_dim
+    return s
+
+
+def test_spatial_and_decoder_sizes_and_validation(built_library):
+    """Host-side checks of the SURVEY 8(f) N3 / N4 entry points (no compute): sizes, struct layouts, refusals."""
+    assert C.sizeof(nlib.SpatialShape) == C.sizeof(nlib.Shape) + 8
+    assert C.sizeof(nlib.SpatialLayerParams) == 20 * 8
+    assert C.sizeof(nlib.SpatialParams) == 8 + 4 * 8 + 4 * C.sizeof(nlib.SpatialLayerParams) + 2 * 8
+    assert C.sizeof(nlib.DecoderAttnParams) == 8 + 10 * 8
+    n = C.c_size_t()
+    s = _spatial_shape(height=64, width=64, batch=2)
+    assert built_library.nmm_spatial_packed_params_bytes(C.byref(s), C.byref(n)) == 0
+    # C^2 (2 + 3 + 1 + 1 + 1 + 8 + 4) + 2 C D weights in bf16 + fp32 vectors: ~4.5 MB at C = 320
+    assert 2 * (20 * 320 * 320 + 2 * 320 * 768) < n.value < 2 * (20 * 320 * 320 + 2 * 320 * 768) + (1 << 18)
+    assert built_library.nmm_spatial_workspace_bytes(C.byref(s), C.byref(n)) == 0
+    tokens = 2 * 8 * 64 * 64
+    assert tokens * 320 * (2 + 4 + 8 + 2) <= n.value <= tokens * 320 * (2 + 4 + 8 + 2) + tokens // 32 * 320 * 8 + (4 << 20)
+    for bad, status in ((_spatial_shape(channels=256), -2),                 # head dim 32: not 40 / 80 / 160
+                        (_spatial_shape(ctx_dim=100), -1),                  # ctx_dim % 8
+                        (_spatial_shape(ctx_len=0), -1),
+                        (_spatial_shape(dtype=nlib.NMM_F32X3, channels=320), -2)):
+        assert built_library.nmm_spatial_workspace_bytes(C.byref(bad), C.byref(n)) == status, built_library.nmm_last_error()
+    assert built_library.nmm_decoder_attn_packed_bytes(128, nlib.NMM_BF16, C.byref(n)) == 0
+    assert 2 * 4 * 128 * 128 < n.value < 2 * 4 * 128 * 128 + (1 << 14)
+    assert built_library.nmm_decoder_attn_packed_bytes(0, nlib.NMM_BF16, C.byref(n)) == -1
+    d = _shape(channels=128, heads=1, frames=6, height=28, width=28, dtype=nlib.NMM_F32)
+    assert built_library.nmm_decoder_attn_workspace_bytes(C.byref(d), C.byref(n)) == 0
+    assert n.value >= 6 * 28 * 28 * 128 * 4 * 5
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
+def test_spatial_compute_refuses_without_gpu(built_library):
+    buf = (C.c_char * 4096)()
+    rc = built_library.nmm_spatial_attention(nlib.NMM_BF16, buf, buf, buf, buf, 960, 960, 320, 960 * 64, 960 * 64, 320 * 64, 64, 64, 8, 40, 1, 1, None)
+    assert rc == -5 and b"CUDA" in built_library.nmm_last_error()

@@ -152,3 +152,43 @@ def test_spatial_emits_groupnorm_sums_for_the_motion_module(C, side):
     assert n1 == n0 - 1, (n0, n1)           # the motion module's statistics pass over its input is gone
     assert sums is not None and torch.allclose(sums, ref, rtol=1e-5, atol=1e-3)
     assert (y1 - y0).abs().max().item() <= 2.0 ** -6
+
+
+def test_spatial_forward_graph_capture_and_errors():
+    """The spatial call allocates nothing, never synchronises and encodes its tensor maps on the host: it can be captured in a CUDA graph
+    and replayed on new data; a packed buffer of the wrong size, a missing text tensor and a CPU tensor raise instead of falling back."""
+    import neurons_b200 as nb
+    from neurons_b200 import spatial_transformer as st
+    cfg = so.SpatialConfig(320, 8, 1, 768, True)
+    params = {k: round_bf16(v) for k, v in so.make_params(cfg, 8).items()}
+    m = _mirror(cfg, params, torch.bfloat16)
+    x, ctx = so.make_inputs(cfg, 1, 2, 16, 16, 77, 9)
+    xs, cs = x.cuda().bfloat16(), ctx.cuda().bfloat16()
+    with torch.no_grad():
+        y_eager = m(xs, encoder_hidden_states=cs).sample.clone()           # also packs the parameters (required before capture)
+        g = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            m(xs, encoder_hidden_states=cs)                                 # warm-up on the capture stream
+            with torch.cuda.graph(g, stream=s):
+                y_graph = m(xs, encoder_hidden_states=cs).sample
+        torch.cuda.current_stream().wait_stream(s)
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(y_graph, y_eager)
+        x2, _ = so.make_inputs(cfg, 1, 2, 16, 16, 77, 10)
+        xs.copy_(x2.cuda().bfloat16())                                       # new data in the captured input buffer
+        g.replay()
+        torch.cuda.synchronize()
+        ref = so.forward_reference_order(params, round_bf16(x2), round_bf16(ctx), cfg)
+        assert (y_graph.float().cpu() - ref).abs().max().item() <= TOL_BF16
+        eng = m.__dict__["_nmm_engine"]
+        with pytest.raises(nb.NmmError):
+            st.spatial_forward_packed(xs, cs, eng.packed[:-256], eng.cfg)
+        with pytest.raises(ValueError):
+            m(xs, encoder_hidden_states=None)
+        with pytest.raises(RuntimeError):
+            m(xs.cpu(), encoder_hidden_states=cs.cpu())
+        with pytest.raises(TypeError):
+            m(xs, encoder_hidden_states=cs.float())
