@@ -24,7 +24,8 @@ def _attention_fp64(q, k, v, heads, kv_div):
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "fp32"])
 @pytest.mark.parametrize("dh", [40, 80, 160])
-@pytest.mark.parametrize("Lq,Lkv,images,kv_div", [(64, 64, 3, 1), (192, 192, 2, 1), (1024, 1024, 1, 1), (200, 77, 4, 2), (20, 20, 2, 1), (300, 1, 1, 1)])
+@pytest.mark.parametrize("Lq,Lkv,images,kv_div", [(64, 64, 3, 1), (192, 192, 2, 1), (1024, 1024, 1, 1), (200, 77, 4, 2), (20, 20, 2, 1), (300, 1, 1, 1),
+                                                  (300, 300, 3, 1), (513, 513, 2, 1), (256, 256, 5, 1)])      # ragged / odd tile counts on the tcgen05 kernel
 def test_spatial_attention_vs_fp64(dtype, dh, Lq, Lkv, images, kv_div):
     import neurons_b200 as nb
     if dtype == torch.float32 and Lq * Lkv > 200 * 200:
