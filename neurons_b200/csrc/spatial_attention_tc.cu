@@ -4,19 +4,23 @@
 // (the mma.sync kernel of spatial_attention.cu keeps d_h = 160, the 77-token cross-attention and the small levels: its legacy HMMA pipe
 // saturates at ~260 TFLOP/s, profiles/r2_ncu_spatial_attention.txt).
 //
-// One CTA = 128 queries of one (image, head); 192 threads = 4 softmax warps (one query row per thread = one TMEM lane), 1 TMA warp,
-// 1 MMA warp; 2 CTAs per SM (256 TMEM columns, <= 92 KB shared memory each), so one CTA's tensor-core phases run under the other's
-// exponentials.  Per 128-key tile t:
+// Two kernels share the design below.  spatial_attention_tc2_kernel (the DEFAULT): one CTA = TWO 128-query tiles of one (image, head), one
+// CTA per SM, 2 x 4 softmax warps + TMA warp + MMA warp; the two tiles share every K / V tile (the TMA pays per 16-byte segment of the
+// core-matrix order, which bound the one-tile kernel once the SFU was relieved).  spatial_attention_tc_kernel: one 128-query tile per CTA, two
+// CTAs per SM -- the predecessor, kept with its A/B switches (NMM_OPT_SPATIAL_ATTN: 23 one-tile, 2 two softmax threads per row, 10..14 share
+// of polynomial exponentials, 15 no K / V traffic (timing only), 16 cp.async loader, 20..22 K / V stages of the two-tile kernel, 24 text
+// cross-attention on this kernel); measurements in profiles/r2_spatial_attention_probe.txt, story in DESIGN.md section 5.  Per 128-key tile t:
 //   TMA warp   K(t), V(t) -> shared memory as [16-byte channel chunk][key][8 channels]: a 4-D tensor map (8, rows, chunks, images) whose box
 //              (8, 128, d_h/8, 1) lands exactly in the un-swizzled core-matrix order tcgen05 reads (K-major for Q / K, N-major for V);
-//              rows past the end of the image are zero-filled by the hardware
-//   MMA warp   S = Q K(t)^T  (M128 N128 K16 x d_h/16, d_h = 40 zero-padded to 48) -> TMEM columns [0, 128); issued as soon as the softmax
-//              warps have READ S(t-1) into registers, i.e. under their exponentials;   O += P(t) V(t)  (M128 N48|80 K16 x 8) -> TMEM columns
-//              [128, 128 + d_h): O accumulates in tensor memory over ALL tiles
-//   softmax    tcgen05.ld of the thread's 128 scores, row max, p = 2^((s - m_ref) * scale*log2e) in fp32 (ex2.approx), bf16 P written to
-//              shared memory in the K-major operand order ([key chunk][row][16 B]: conflict-free 16-byte stores).  m_ref is the row's
-//              REFERENCE max, raised only when the running max exceeds it by more than 2^8 (then O's row in TMEM and the running sum are
-//              rescaled once: rare after the first tiles); p <= 256 is exact enough in bf16 and the final O / l is independent of m_ref.
+//              rows past the end of the image are zero-filled by the hardware; K and V are separate streams (lanes 0 / 1)
+//   MMA warp   S = Q K(t)^T  (M128 N128 K16 x d_h/16, d_h = 40 zero-padded to 48) -> TMEM; issued as soon as the softmax warps have READ
+//              S(t-1) into registers, i.e. under their exponentials;   O += P(t) V(t)  (M128 N48|96 K16 x 8) -> TMEM: O accumulates in
+//              tensor memory over ALL tiles, and V's extra ONES column makes column d_h of O the row sum of the bf16 weights
+//   softmax    tcgen05.ld of the thread's 128 scores, row max, p = 2^((s - m_ref) * scale*log2e): 5 of 8 on the SFU (ex2.approx), 3 of 8 by
+//              a polynomial on the FMA / ALU pipes, packed fp32x2 arithmetic; half of them before the wait for P(t-1) V(t-1), the rest
+//              interleaved with the 16-byte stores of the bf16 P tile in the K-major operand order ([key chunk][row][16 B]).  m_ref is the
+//              row's REFERENCE max, raised only when the running max exceeds it by more than 2^8 (then O's row in TMEM is rescaled
+//              once: rare after the first tiles); p <= 256 is exact enough in bf16 and the final O / l is independent of m_ref.
 // Nothing but Q, K, V is read from and O written to HBM; the score matrix (537 MB per frame in the reference at the 64 x 64 level) never exists.
 #include <mutex>
 
