@@ -449,7 +449,7 @@ struct Ft2Cfg {
     static constexpr uint32_t SMEM = OFF_BAR + 256 + 128;
 };
 
-template <int DH, int NS_>
+template <int DH, int NS_, bool NOKV = false>
 __global__ void __launch_bounds__(320, 1)
 spatial_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
                              const FtParams p) {
@@ -514,6 +514,7 @@ spatial_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __g
             for (int t = 0; t < nt; t++) {
                 const int s = t % NS, fill = t / NS;
                 if (fill > 0) ptx::mbar_wait(b_kempty(s), (uint32_t)(fill - 1) & 1u);
+                if (NOKV && fill > 0) { ptx::mbar_arrive(b_kfull(s)); continue; }          // timing experiment (results invalid)
                 ptx::mbar_expect_tx(b_kfull(s), Cfg::TX_BYTES);
                 ptx::tma_load_4d(&tm_k, b_kfull(s), s_k + s * Cfg::TILE_BYTES, 0, t * FT_BN, head * CH, kv_img);
             }
@@ -522,6 +523,7 @@ spatial_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __g
             for (int t = 0; t < nt; t++) {
                 const int s = t % NS, fill = t / NS;
                 if (fill > 0) ptx::mbar_wait(b_vempty(s), (uint32_t)(fill - 1) & 1u);
+                if (NOKV && fill > 0) { ptx::mbar_arrive(b_vfull(s)); continue; }
                 ptx::mbar_expect_tx(b_vfull(s), Cfg::TX_BYTES);
                 ptx::tma_load_4d(&tm_v, b_vfull(s), s_v + s * Cfg::VTILE_BYTES, 0, t * FT_BN, head * CH, kv_img);
             }
@@ -759,11 +761,11 @@ static int launch_ft(const FlashArgs &a, int debug, cudaStream_t st) {
     return NMM_OK;
 }
 
-template <int DH, int NS>
+template <int DH, int NS, bool NOKV = false>
 static int launch_ft2(const FlashArgs &a, cudaStream_t st) {
     using C2 = Ft2Cfg<DH, NS>;
     static DeviceOnce once;
-    NMM_CUDA_OK(once.max_smem(spatial_attention_tc2_kernel<DH, NS>, (int)C2::SMEM));
+    NMM_CUDA_OK(once.max_smem(spatial_attention_tc2_kernel<DH, NS, NOKV>, (int)C2::SMEM));
     CUtensorMap tq, tk, tv;
     int rc;
     if ((rc = ft_map(&tq, a.q, a.Lq, a.q_rs, a.q_bs, a.images, DH)) != NMM_OK) return rc;
@@ -775,7 +777,7 @@ static int launch_ft2(const FlashArgs &a, cudaStream_t st) {
     const dim3 grid((unsigned)ceil_div(a.Lq, 2 * FT_BM), (unsigned)a.heads, (unsigned)a.images);
     const double per = (double)a.images * a.heads;
     ProfScope prof(K_SPATIAL_ATTN, st, 4.0 * per * a.Lq * (double)a.Lkv * DH, 2.0 * 4.0 * per * a.Lq * DH);
-    NMM_CUDA_OK(launch_pdl(spatial_attention_tc2_kernel<DH, NS>, grid, dim3(320), (size_t)C2::SMEM, st, tq, tk, tv, p));
+    NMM_CUDA_OK(launch_pdl(spatial_attention_tc2_kernel<DH, NS, NOKV>, grid, dim3(320), (size_t)C2::SMEM, st, tq, tk, tv, p));
     NMM_LAUNCHED("spatial_attention_tc2_kernel");
     return NMM_OK;
 }
@@ -785,6 +787,7 @@ int launch_spatial_attention_tc(const FlashArgs &a, int variant, cudaStream_t st
     // (d_h = 80: 2 only); 23: the one-tile kernel (two CTAs per SM) that the variants below select explicitly
     if (variant == 0 || variant == 21 || variant == 24) return a.dh == 40 ? launch_ft2<40, 3>(a, st) : launch_ft2<80, 2>(a, st);
     if (variant == 20) return a.dh == 40 ? launch_ft2<40, 2>(a, st) : launch_ft2<80, 2>(a, st);
+    if (variant == 26) return a.dh == 40 ? launch_ft2<40, 3, true>(a, st) : launch_ft2<80, 2, true>(a, st);      // timing only: no K / V traffic
     if (variant == 22) return a.dh == 40 ? launch_ft2<40, 4>(a, st) : launch_ft2<80, 2>(a, st);
     // NMM_OPT_SPATIAL_ATTN: 0 / 3 = one softmax thread per query row (measured faster once the polynomial share relieved the SFU), 2 = two;
     // 10..14 = polynomial share 0 / 2 / 3 / 4 / 6 of 8 (A/B; 3 is the default);
