@@ -9,7 +9,7 @@
 // core-matrix order, which bound the one-tile kernel once the SFU was relieved).  spatial_attention_tc_kernel: one 128-query tile per CTA, two
 // CTAs per SM -- the predecessor, kept with its A/B switches (NMM_OPT_SPATIAL_ATTN: 23 one-tile, 2 two softmax threads per row, 10..14 share
 // of polynomial exponentials, 15 no K / V traffic (timing only), 16 cp.async loader, 20..22 K / V stages of the two-tile kernel, 24 text
-// cross-attention on this kernel); measurements in profiles/r2_spatial_attention_probe.txt, story in DESIGN.md section 5.  Per 128-key tile t:
+// cross-attention on this kernel, 26 two-tile kernel without K / V traffic (timing only), 27 P through tensor memory); measurements in profiles/r2_spatial_attention_probe.txt, story in DESIGN.md section 5.  Per 128-key tile t:
 //   TMA warp   K(t), V(t) -> shared memory as [16-byte channel chunk][key][8 channels]: a 4-D tensor map (8, rows, chunks, images) whose box
 //              (8, 128, d_h/8, 1) lands exactly in the un-swizzled core-matrix order tcgen05 reads (K-major for Q / K, N-major for V);
 //              rows past the end of the image are zero-filled by the hardware; K and V are separate streams (lanes 0 / 1)
@@ -449,7 +449,7 @@ struct Ft2Cfg {
     static constexpr uint32_t SMEM = OFF_BAR + 256 + 128;
 };
 
-template <int DH, int NS_, bool NOKV = false>
+template <int DH, int NS_, bool NOKV = false, bool PT = false>
 __global__ void __launch_bounds__(320, 1)
 spatial_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
                              const FtParams p) {
@@ -563,8 +563,12 @@ spatial_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __g
                     const uint64_t a = ptx::umma_smem_desc_interleave(s_p + qt * Cfg::P_BYTES, FT_CHUNK, 128);
                     const uint64_t b = ptx::umma_smem_desc_interleave(s_v + s * Cfg::VTILE_BYTES, 128u, FT_CHUNK);
 #pragma unroll
-                    for (int k = 0; k < FT_BN / 16; k++)
-                        ptx::umma_bf16<1>(tmem + 256 + qt * 128, a + (uint64_t)((k * 2 * FT_CHUNK) >> 4), b + (uint64_t)((k * 16 * 16) >> 4), idesc_o, (t | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < FT_BN / 16; k++) {
+                        if constexpr (PT)          // P(t) sits in tensor memory (64 columns behind O_qt: two bf16 keys per column)
+                            ptx::umma_bf16_ts(tmem + 256 + qt * 128, tmem + 256 + qt * 128 + 64 + k * 8, b + (uint64_t)((k * 16 * 16) >> 4), idesc_o, (t | k) != 0 ? 1u : 0u);
+                        else
+                            ptx::umma_bf16<1>(tmem + 256 + qt * 128, a + (uint64_t)((k * 2 * FT_CHUNK) >> 4), b + (uint64_t)((k * 16 * 16) >> 4), idesc_o, (t | k) != 0 ? 1u : 0u);
+                    }
                     ptx::umma_commit<1>(b_pv(qt));
                     if (qt == 1) ptx::umma_commit<1>(b_vempty(s));
                 }
@@ -622,6 +626,35 @@ spatial_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __g
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + kc * FT_CHUNK), "r"(q[0]), "r"(q[1]), "r"(q[2]), "r"(q[3]) : "memory");
             };
             constexpr int NCH = FT_BN / 8, PRE = NCH / 2;
+            if constexpr (PT) {
+                // P through tensor memory: all 64 bf16x2 columns in registers, then two tcgen05.st of 32 columns into [O_qt + 64, O_qt + 128)
+                uint32_t pk2[2][32];
+#pragma unroll
+                for (int kc = 0; kc < NCH; kc++) {
+                    uint32_t q[4];
+                    exp_chunk(kc, q);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) pk2[kc / 8][(kc % 8) * 4 + i] = q[i];
+                }
+                if (t > 0) ptx::mbar_wait(b_pv(qt), (uint32_t)(t - 1) & 1u);
+                ptx::tc_fence_after();
+                if (t > 0 && __any_sync(0xffffffffu, raise)) {
+                    const float f = ft_exp2((m_ref - m_new) * sl);
+#pragma unroll
+                    for (int c = 0; c < NV; c += 16) {
+                        uint32_t orow[16];
+                        ptx::tmem_ld16(t_o + c, orow);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; i++) orow[i] = __float_as_uint(__uint_as_float(orow[i]) * f);
+                        ptx::tmem_st16(t_o + c, orow);
+                    }
+                }
+                m_ref = m_new;
+                ptx::tmem_st32(t_o + 64, pk2[0]);
+                ptx::tmem_st32(t_o + 96, pk2[1]);
+                ptx::tmem_st_wait();
+            } else {
             uint32_t pk[PRE][4];
 #pragma unroll
             for (int kc = 0; kc < PRE; kc++) exp_chunk(kc, pk[kc]);
@@ -647,6 +680,7 @@ spatial_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __g
                 uint32_t q[4];
                 exp_chunk(PRE + kc, q);
                 store_chunk(PRE + kc, q);
+            }
             }
             ptx::fence_proxy_async();
             ptx::tc_fence_before();
@@ -761,11 +795,12 @@ static int launch_ft(const FlashArgs &a, int debug, cudaStream_t st) {
     return NMM_OK;
 }
 
-template <int DH, int NS, bool NOKV = false>
+template <int DH, int NS, bool NOKV = false, bool PT = false>
 static int launch_ft2(const FlashArgs &a, cudaStream_t st) {
     using C2 = Ft2Cfg<DH, NS>;
+    static_assert(!PT || DH == 40, "P through TMEM: 2 x (128 S + 48 O + 64 P) columns only fit at d_h = 40");
     static DeviceOnce once;
-    NMM_CUDA_OK(once.max_smem(spatial_attention_tc2_kernel<DH, NS, NOKV>, (int)C2::SMEM));
+    NMM_CUDA_OK(once.max_smem(spatial_attention_tc2_kernel<DH, NS, NOKV, PT>, (int)C2::SMEM));
     CUtensorMap tq, tk, tv;
     int rc;
     if ((rc = ft_map(&tq, a.q, a.Lq, a.q_rs, a.q_bs, a.images, DH)) != NMM_OK) return rc;
@@ -777,7 +812,7 @@ static int launch_ft2(const FlashArgs &a, cudaStream_t st) {
     const dim3 grid((unsigned)ceil_div(a.Lq, 2 * FT_BM), (unsigned)a.heads, (unsigned)a.images);
     const double per = (double)a.images * a.heads;
     ProfScope prof(K_SPATIAL_ATTN, st, 4.0 * per * a.Lq * (double)a.Lkv * DH, 2.0 * 4.0 * per * a.Lq * DH);
-    NMM_CUDA_OK(launch_pdl(spatial_attention_tc2_kernel<DH, NS, NOKV>, grid, dim3(320), (size_t)C2::SMEM, st, tq, tk, tv, p));
+    NMM_CUDA_OK(launch_pdl(spatial_attention_tc2_kernel<DH, NS, NOKV, PT>, grid, dim3(320), (size_t)C2::SMEM, st, tq, tk, tv, p));
     NMM_LAUNCHED("spatial_attention_tc2_kernel");
     return NMM_OK;
 }
@@ -787,6 +822,7 @@ int launch_spatial_attention_tc(const FlashArgs &a, int variant, cudaStream_t st
     // (d_h = 80: 2 only); 23: the one-tile kernel (two CTAs per SM) that the variants below select explicitly
     if (variant == 0 || variant == 21 || variant == 24) return a.dh == 40 ? launch_ft2<40, 3>(a, st) : launch_ft2<80, 2>(a, st);
     if (variant == 20) return a.dh == 40 ? launch_ft2<40, 2>(a, st) : launch_ft2<80, 2>(a, st);
+    if (variant == 27) return a.dh == 40 ? launch_ft2<40, 3, false, true>(a, st) : launch_ft2<80, 2>(a, st);      // A/B: P through tensor memory (d_h = 40)
     if (variant == 26) return a.dh == 40 ? launch_ft2<40, 3, true>(a, st) : launch_ft2<80, 2, true>(a, st);      // timing only: no K / V traffic
     if (variant == 22) return a.dh == 40 ? launch_ft2<40, 4>(a, st) : launch_ft2<80, 2>(a, st);
     // NMM_OPT_SPATIAL_ATTN: 0 / 3 = one softmax thread per query row (measured faster once the polynomial share relieved the SFU), 2 = two;
