@@ -59,8 +59,8 @@ SpLayout sp_layout(const Geo &g, int ctx_dim) {
     return L;
 }
 
-struct SpWork { size_t gn_partial, tok, h, big, ctx, kv, stat_part, total; };
-SpWork sp_work(const Geo &g, int ctx_len) {
+struct SpWork { size_t gn_partial, tok, h, big, ctx, kv, stat_part, ctx32, ehs2, total; };
+SpWork sp_work(const Geo &g, int ctx_len, int ctx_dim) {
     SpWork w;
     size_t off = 0;
     const size_t es = dtype_size(g.dtype);
@@ -74,6 +74,9 @@ SpWork sp_work(const Geo &g, int ctx_len) {
     w.ctx = take(N * C * std::max(opnd, es));
     w.kv = take((size_t)g.B * ctx_len * 2 * C * 4);
     w.stat_part = take((N + 31) / 32 * C * sizeof(float2));      // N1: (sum, sum of squares) partials of y per 32-row block and channel
+    // NMM_F32X3: the fp32 attention output before it is split into hi | lo planes; the text states as hi | lo planes
+    w.ctx32 = take(g.dtype == NMM_F32X3 ? N * C * 4 : 0);
+    w.ehs2 = take(g.dtype == NMM_F32X3 ? (size_t)g.B * ctx_len * ctx_dim * 4 : 0);
     w.total = off;
     return w;
 }
@@ -84,7 +87,7 @@ int sp_validate(const nmm_spatial_shape *s) {
     b.attn_blocks = 1; b.pos_enc = 0; b.max_len = 0; b.ln_fold = 0;
     int rc = nmm_validate(&b);
     if (rc != NMM_OK) return rc;
-    if (b.dtype == NMM_F32X3) return fail(NMM_ERR_UNSUPPORTED, "spatial transformer: fp32 runs in NMM_F32 (FMA) mode; NMM_F32X3 is not wired for it");
+    if (b.dtype == NMM_F32X3 && s->ctx_dim % 64 != 0) return fail(NMM_ERR_UNSUPPORTED, "NMM_F32X3 needs ctx_dim %% 64 == 0 (got %d); use NMM_F32", s->ctx_dim);
     if (s->ctx_len <= 0 || s->ctx_dim <= 0 || s->ctx_dim % 8 != 0) return fail(NMM_ERR_BAD_ARG, "ctx_len / ctx_dim must be positive, ctx_dim %% 8 == 0");
     const int dh = b.channels / b.heads;
     if (dh != 40 && dh != 80 && dh != 160) return fail(NMM_ERR_UNSUPPORTED, "spatial transformer: head dim %d (supported: 40, 80, 160)", dh);
@@ -117,7 +120,7 @@ int nmm_spatial_workspace_bytes(const nmm_spatial_shape *s, size_t *out_bytes) {
     int rc = sp_validate(s);
     if (rc != NMM_OK) return rc;
     if (!out_bytes) return fail(NMM_ERR_BAD_ARG, "out_bytes is NULL");
-    *out_bytes = sp_work(sp_geo(s), s->ctx_len).total;
+    *out_bytes = sp_work(sp_geo(s), s->ctx_len, s->ctx_dim).total;
     return NMM_OK;
 }
 
@@ -148,7 +151,7 @@ int nmm_spatial_pack_params(const nmm_spatial_shape *s, const nmm_spatial_params
         launch_pdl(sp_write_header_kernel, 1, 32, 0, st, hd, (SpHeader *)(base + L.header));
         NMM_LAUNCHED("sp_write_header_kernel");
     }
-    const size_t wsz = dtype_size(wd);
+    const size_t wsz = wd == NMM_F32X3 ? 4 : dtype_size(wd);      // X3: a row is its hi plane | lo plane (2 x bf16 per element)
     PACK(src->gn_w, L.gn_w, NMM_F32, C, 1, 0); PACK(src->gn_b, L.gn_b, NMM_F32, C, 1, 0);
     PACK(src->proj_in_w, L.w_in, wd, C, C, 0); PACK(src->proj_in_b, L.b_in, NMM_F32, C, 1, 0);      // Conv2d [C, C, 1, 1] == Linear [C, C]
     for (int l = 0; l < g.layers; l++) {
@@ -197,7 +200,7 @@ static int spatial_forward_impl(const nmm_spatial_shape *s, const void *x, const
     const Geo g = sp_geo(s);
     const nmm_shape *bs = &s->base;
     const SpLayout L = sp_layout(g, s->ctx_dim);
-    const SpWork w = sp_work(g, s->ctx_len);
+    const SpWork w = sp_work(g, s->ctx_len, s->ctx_dim);
     if (packed_bytes != L.total)
         return fail(NMM_ERR_WORKSPACE, "packed parameter buffer of %zu bytes does not match this call's layout (%zu bytes): packed for another dtype / geometry?",
                     packed_bytes, L.total);
@@ -234,9 +237,18 @@ static int spatial_forward_impl(const nmm_spatial_shape *s, const void *x, const
     if ((rc = linear_dispatch(g.dtype, a, st)) != NMM_OK) return rc;
     a.gn_x = nullptr;
 
+    // NMM_F32X3 (fp32 activations, every Linear on the tensor cores as 3 bf16 MMAs): GEMM operands are hi | lo bf16 planes; q, k, v come out of
+    // their GEMMs as plain fp32 (STORE -> h-type buffer), the fp32 attention kernel's output is split into planes for to_out
+    const bool x3 = g.dtype == NMM_F32X3;
+    float *ctx32 = (float *)(ws + w.ctx32);
+    const void *ehs_op = encoder_hidden_states;
+    if (x3) {
+        if ((rc = launch_convert_rows(encoder_hidden_states, NMM_F32, ws + w.ehs2, NMM_F32X3, (int64_t)g.B * Lc, D, 0, st)) != NMM_OK) return rc;
+        ehs_op = ws + w.ehs2;
+    }
     FlashArgs fa;
     memset(&fa, 0, sizeof(fa));
-    fa.heads = g.heads; fa.dh = g.dh; fa.dtype = g.dtype; fa.images = g.B * g.F; fa.Lq = P;
+    fa.heads = g.heads; fa.dh = g.dh; fa.dtype = x3 ? NMM_F32 : g.dtype; fa.images = g.B * g.F; fa.Lq = P;
     fa.scale = 1.0f / sqrtf((float)g.dh); fa.scale_log2e = fa.scale * 1.4426950408889634f;
 
     for (int l = 0; l < g.layers; l++) {
@@ -244,25 +256,30 @@ static int spatial_forward_impl(const nmm_spatial_shape *s, const void *x, const
         // ---- attn1: self-attention over the P positions of each frame                  :262-280
         if ((rc = launch_layernorm_pe(g, bs, h, F32(o.ln1_w), F32(o.ln1_b), nullptr, tok, st)) != NMM_OK) return rc;
         a.epilogue = NMM_EPI_STORE; a.M = N; a.N = 3 * C; a.K = C; a.A = tok; a.W = pk + o.wqkv1; a.bias = nullptr; a.h = nullptr; a.out = big;
+        if (x3) { a.h = (float *)big; a.out = nullptr; }
         if ((rc = linear_dispatch(g.dtype, a, st)) != NMM_OK) return rc;
-        fa.q = big; fa.k = (const char *)big + (size_t)C * es; fa.v = (const char *)big + 2 * (size_t)C * es; fa.o = ctx;
+        fa.q = big; fa.k = (const char *)big + (size_t)C * es; fa.v = (const char *)big + 2 * (size_t)C * es; fa.o = x3 ? (void *)ctx32 : ctx;
         fa.q_rs = fa.kv_rs = 3 * C; fa.o_rs = C; fa.q_bs = fa.kv_bs = (int64_t)P * 3 * C; fa.o_bs = (int64_t)P * C;
         fa.Lkv = P; fa.kv_div = 1;
         if ((rc = launch_spatial_attention(fa, st)) != NMM_OK) return rc;
+        if (x3 && (rc = launch_convert_rows(ctx32, NMM_F32, ctx, NMM_F32X3, N, C, 0, st)) != NMM_OK) return rc;
         a.epilogue = NMM_EPI_RESIDUAL; a.N = C; a.K = C; a.A = ctx; a.W = pk + o.wo1; a.bias = F32(o.bo1); a.h = h; a.out = nullptr;
         if ((rc = linear_dispatch(g.dtype, a, st)) != NMM_OK) return rc;
 
         // ---- attn2: cross-attention onto the text tokens (k, v once per clip)          :282-292
-        a.epilogue = NMM_EPI_STORE; a.M = (int64_t)g.B * Lc; a.N = 2 * C; a.K = D; a.A = encoder_hidden_states; a.W = pk + o.wkv2; a.bias = nullptr;
+        a.epilogue = NMM_EPI_STORE; a.M = (int64_t)g.B * Lc; a.N = 2 * C; a.K = D; a.A = ehs_op; a.W = pk + o.wkv2; a.bias = nullptr;
         a.h = nullptr; a.out = kv;
+        if (x3) { a.h = (float *)kv; a.out = nullptr; }
         if ((rc = linear_dispatch(g.dtype, a, st)) != NMM_OK) return rc;
         if ((rc = launch_layernorm_pe(g, bs, h, F32(o.ln2_w), F32(o.ln2_b), nullptr, tok, st)) != NMM_OK) return rc;
         a.epilogue = NMM_EPI_STORE; a.M = N; a.N = C; a.K = C; a.A = tok; a.W = pk + o.wq2; a.bias = nullptr; a.h = nullptr; a.out = big;
+        if (x3) { a.h = (float *)big; a.out = nullptr; }
         if ((rc = linear_dispatch(g.dtype, a, st)) != NMM_OK) return rc;
-        fa.q = big; fa.k = kv; fa.v = (const char *)kv + (size_t)C * es; fa.o = ctx;
+        fa.q = big; fa.k = kv; fa.v = (const char *)kv + (size_t)C * es; fa.o = x3 ? (void *)ctx32 : ctx;
         fa.q_rs = C; fa.kv_rs = 2 * C; fa.o_rs = C; fa.q_bs = (int64_t)P * C; fa.kv_bs = (int64_t)Lc * 2 * C; fa.o_bs = (int64_t)P * C;
         fa.Lkv = Lc; fa.kv_div = g.F;
         if ((rc = launch_spatial_attention(fa, st)) != NMM_OK) return rc;
+        if (x3 && (rc = launch_convert_rows(ctx32, NMM_F32, ctx, NMM_F32X3, N, C, 0, st)) != NMM_OK) return rc;
         a.epilogue = NMM_EPI_RESIDUAL; a.N = C; a.K = C; a.A = ctx; a.W = pk + o.wo2; a.bias = F32(o.bo2); a.h = h; a.out = nullptr;
         if ((rc = linear_dispatch(g.dtype, a, st)) != NMM_OK) return rc;
 
@@ -271,12 +288,12 @@ static int spatial_forward_impl(const nmm_spatial_shape *s, const void *x, const
         a.epilogue = NMM_EPI_GEGLU; a.N = 8 * C; a.K = C; a.A = tok; a.W = pk + o.w1; a.bias = F32(o.b1); a.h = nullptr; a.out = big;
         if ((rc = linear_dispatch(g.dtype, a, st)) != NMM_OK) return rc;
         a.epilogue = NMM_EPI_RESIDUAL; a.N = C; a.K = 4 * C; a.A = big; a.W = pk + o.w2; a.bias = F32(o.b2); a.h = h; a.out = nullptr; a.no_h_store = 0;
-        if (l == g.layers - 1 && g.dtype == NMM_BF16) { a.out = tok; a.no_h_store = 1; }     // the sum is consumed once, by proj_out, as a bf16 operand
+        if (l == g.layers - 1 && g.dtype != NMM_F32) { a.out = tok; a.no_h_store = 1; }     // the sum is consumed once, by proj_out, as a bf16 operand
         if ((rc = linear_dispatch(g.dtype, a, st)) != NMM_OK) return rc;
         a.no_h_store = 0;
     }
     // y = proj_out(h) back in NCHW + x, stored as [B, F, C, H, W]                         :130-144
-    a.epilogue = NMM_EPI_OUTPUT; a.N = C; a.K = C; a.A = (g.dtype == NMM_BF16) ? (const void *)tok : (const void *)h;
+    a.epilogue = NMM_EPI_OUTPUT; a.N = C; a.K = C; a.A = (g.dtype != NMM_F32) ? (const void *)tok : (const void *)h;
     a.W = pk + L.w_out; a.bias = F32(L.b_out); a.h = nullptr; a.out = nullptr; a.x = x; a.y = y;
     // N1: the GroupNorm sums of y for the motion module that consumes it next (unet_blocks.py:409-411) -- emitted by this epilogue
     // (bf16 vector path; per 32-row block and channel, then one warp per (image, group) in a fixed order: no atomics), else one pass over y

@@ -37,6 +37,10 @@ class SpatialConfig:
     heads: int = 8
     layers: int = 1
     ctx_dim: int = 768
+    # fp32 activations: True = every Linear on the tensor cores as 3 bf16 MMAs per product (NMM_F32X3; needs channels, ctx_dim % 64 == 0),
+    # False (module flag `_nmm_fp32_fma` or env NMM_FP32_FMA=1) = the FMA-pipe GEMM (NMM_F32), the checker.  The attention itself is the
+    # fp32 checker kernel in both modes (small / medium shapes; the 64 x 64 level is refused in fp32: use bf16 there).
+    fp32_tc: bool = True
 
 
 class Transformer3DModelOutput:
@@ -126,11 +130,14 @@ def spatial_config_of(module: nn.Module) -> SpatialConfig:
     heads = int(b0.attn1.heads)
     if channels // heads not in (40, 80, 160):
         raise NotImplementedError(f"neurons_b200: spatial attention head dim {channels // heads} (supported: 40, 80, 160)")
-    return SpatialConfig(channels=channels, heads=heads, layers=len(blocks), ctx_dim=int(b0.attn2.to_k.in_features))
+    return SpatialConfig(channels=channels, heads=heads, layers=len(blocks), ctx_dim=int(b0.attn2.to_k.in_features),
+                         fp32_tc=not bool(module.__dict__.get("_nmm_fp32_fma", False)))
 
 
-def _dtype_code(dt: torch.dtype) -> int:
+def _dtype_code(dt: torch.dtype, cfg: Optional["SpatialConfig"] = None) -> int:
     if dt == torch.float32:
+        if cfg is not None and cfg.fp32_tc and cfg.channels % 64 == 0 and cfg.ctx_dim % 64 == 0 and ops._FP32_FMA_ENV in (None, "0"):
+            return _lib.NMM_F32X3
         return _lib.NMM_F32
     if dt == torch.bfloat16:
         return _lib.NMM_BF16
@@ -142,7 +149,7 @@ def _shape(cfg: SpatialConfig, dtype: torch.dtype, B=1, F=1, H=1, W=1, ctx_len=1
     b = s.base
     b.batch, b.channels, b.frames, b.height, b.width = B, cfg.channels, F, H, W
     b.heads, b.layers, b.attn_blocks, b.pos_enc, b.max_len = cfg.heads, cfg.layers, 1, 0, 0
-    b.dtype, b.eps_gn, b.eps_ln, b.ln_fold = _dtype_code(dtype), ops.GN_EPS, ops.LN_EPS, 0
+    b.dtype, b.eps_gn, b.eps_ln, b.ln_fold = _dtype_code(dtype, cfg), ops.GN_EPS, ops.LN_EPS, 0
     s.ctx_len, s.ctx_dim = ctx_len, cfg.ctx_dim
     return s
 

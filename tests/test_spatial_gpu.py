@@ -56,11 +56,15 @@ def _mirror(cfg, params, dtype):
     return m.eval().cuda().to(dtype)
 
 
+@pytest.mark.parametrize("mode", ["x3", "fma"])          # Linears on the tensor cores (3 x bf16 per product) / on the FMA pipe (the checker)
 @pytest.mark.parametrize("name", sp_golden_names())
-def test_spatial_module_golden_fp32(name):
+def test_spatial_module_golden_fp32(name, mode):
     fx, cfg, params, x, ctx = load_sp_golden(name)
     with torch.no_grad():
-        y = _mirror(cfg, params, torch.float32)(x.cuda(), encoder_hidden_states=ctx.cuda()).sample
+        m = _mirror(cfg, params, torch.float32)
+        if mode == "fma":
+            m.__dict__["_nmm_fp32_fma"] = True
+        y = m(x.cuda(), encoder_hidden_states=ctx.cuda()).sample
     assert y.shape == fx["out_ref_fp32"].shape and y.stride() == tuple(fx["out_ref_fp32"].permute(0, 2, 1, 3, 4).contiguous().permute(0, 2, 1, 3, 4).stride())
     err = (y.cpu() - fx["out_ref_fp32"]).abs().max().item()
     assert err <= TOL_FP32, err
