@@ -263,6 +263,7 @@ struct FlashArgs {
     void *o;
     int64_t q_rs, kv_rs, o_rs;      // row strides (elements)
     int64_t q_bs, kv_bs, o_bs;      // image strides (elements); the k / v image of q image i is i / kv_div
+    int64_t q_lo_off, kv_lo_off;    // launch_spatial_attention_x3 only: element offset of the lo plane inside a q / k-v row (hi | lo planes)
     int Lq, Lkv, heads, images, kv_div, dh;
     int dtype;                      // NMM_BF16 (mma.sync flash kernel) or NMM_F32 (fp32 checker kernel)
     float scale, scale_log2e;       // dh^-1/2 and dh^-1/2 * log2(e)
@@ -270,6 +271,7 @@ struct FlashArgs {
 int launch_spatial_attention(const FlashArgs &a, cudaStream_t st);
 bool spatial_attention_tc_eligible(const FlashArgs &a);                            // spatial_attention_tc.cu (tcgen05 / TMEM / TMA)
 int launch_spatial_attention_tc(const FlashArgs &a, int variant, cudaStream_t st);
+int launch_spatial_attention_x3(const FlashArgs &a, cudaStream_t st);               // spatial_attention_x3.cu: fp32-grade (hi | lo bf16 planes in, fp32 out)
 int device_check();
 
 // GEMM + epilogue

@@ -59,7 +59,7 @@ SpLayout sp_layout(const Geo &g, int ctx_dim) {
     return L;
 }
 
-struct SpWork { size_t gn_partial, tok, h, big, ctx, kv, stat_part, ctx32, ehs2, total; };
+struct SpWork { size_t gn_partial, tok, h, big, ctx, kv, stat_part, ctx32, ehs2, qkv2, kv2, total; };
 SpWork sp_work(const Geo &g, int ctx_len, int ctx_dim) {
     SpWork w;
     size_t off = 0;
@@ -77,6 +77,9 @@ SpWork sp_work(const Geo &g, int ctx_len, int ctx_dim) {
     // NMM_F32X3: the fp32 attention output before it is split into hi | lo planes; the text states as hi | lo planes
     w.ctx32 = take(g.dtype == NMM_F32X3 ? N * C * 4 : 0);
     w.ehs2 = take(g.dtype == NMM_F32X3 ? (size_t)g.B * ctx_len * ctx_dim * 4 : 0);
+    // ... and q | k | v (self-attention) / q (cross-attention) and the text k | v as hi | lo planes for the fp32-grade attention kernel
+    w.qkv2 = take(g.dtype == NMM_F32X3 ? N * 3 * C * 4 : 0);
+    w.kv2 = take(g.dtype == NMM_F32X3 ? (size_t)g.B * ctx_len * 2 * C * 4 : 0);
     w.total = off;
     return w;
 }
@@ -261,7 +264,13 @@ static int spatial_forward_impl(const nmm_spatial_shape *s, const void *x, const
         fa.q = big; fa.k = (const char *)big + (size_t)C * es; fa.v = (const char *)big + 2 * (size_t)C * es; fa.o = x3 ? (void *)ctx32 : ctx;
         fa.q_rs = fa.kv_rs = 3 * C; fa.o_rs = C; fa.q_bs = fa.kv_bs = (int64_t)P * 3 * C; fa.o_bs = (int64_t)P * C;
         fa.Lkv = P; fa.kv_div = 1;
-        if ((rc = launch_spatial_attention(fa, st)) != NMM_OK) return rc;
+        if (x3) {          // q | k | v fp32 [N, 3C] -> planes [N, 6C] (hi: q | k | v, lo: q | k | v), fp32-grade attention on the tensor cores
+            bf16 *qkv2 = (bf16 *)(ws + w.qkv2);
+            if ((rc = launch_convert_rows(big, NMM_F32, qkv2, NMM_F32X3, N, 3 * C, 0, st)) != NMM_OK) return rc;
+            fa.q = qkv2; fa.k = qkv2 + C; fa.v = qkv2 + 2 * C;
+            fa.q_rs = fa.kv_rs = 6 * C; fa.q_bs = fa.kv_bs = (int64_t)P * 6 * C; fa.q_lo_off = fa.kv_lo_off = 3 * C;
+            if ((rc = launch_spatial_attention_x3(fa, st)) != NMM_OK) return rc;
+        } else if ((rc = launch_spatial_attention(fa, st)) != NMM_OK) return rc;
         if (x3 && (rc = launch_convert_rows(ctx32, NMM_F32, ctx, NMM_F32X3, N, C, 0, st)) != NMM_OK) return rc;
         a.epilogue = NMM_EPI_RESIDUAL; a.N = C; a.K = C; a.A = ctx; a.W = pk + o.wo1; a.bias = F32(o.bo1); a.h = h; a.out = nullptr;
         if ((rc = linear_dispatch(g.dtype, a, st)) != NMM_OK) return rc;
@@ -278,7 +287,15 @@ static int spatial_forward_impl(const nmm_spatial_shape *s, const void *x, const
         fa.q = big; fa.k = kv; fa.v = (const char *)kv + (size_t)C * es; fa.o = x3 ? (void *)ctx32 : ctx;
         fa.q_rs = C; fa.kv_rs = 2 * C; fa.o_rs = C; fa.q_bs = (int64_t)P * C; fa.kv_bs = (int64_t)Lc * 2 * C; fa.o_bs = (int64_t)P * C;
         fa.Lkv = Lc; fa.kv_div = g.F;
-        if ((rc = launch_spatial_attention(fa, st)) != NMM_OK) return rc;
+        if (x3) {
+            bf16 *q2 = (bf16 *)(ws + w.qkv2), *kv2 = (bf16 *)(ws + w.kv2);
+            if ((rc = launch_convert_rows(big, NMM_F32, q2, NMM_F32X3, N, C, 0, st)) != NMM_OK) return rc;
+            if ((rc = launch_convert_rows(kv, NMM_F32, kv2, NMM_F32X3, (int64_t)g.B * Lc, 2 * C, 0, st)) != NMM_OK) return rc;
+            fa.q = q2; fa.k = kv2; fa.v = kv2 + C;
+            fa.q_rs = 2 * C; fa.q_bs = (int64_t)P * 2 * C; fa.q_lo_off = C;
+            fa.kv_rs = 4 * C; fa.kv_bs = (int64_t)Lc * 4 * C; fa.kv_lo_off = 2 * C;
+            if ((rc = launch_spatial_attention_x3(fa, st)) != NMM_OK) return rc;
+        } else if ((rc = launch_spatial_attention(fa, st)) != NMM_OK) return rc;
         if (x3 && (rc = launch_convert_rows(ctx32, NMM_F32, ctx, NMM_F32X3, N, C, 0, st)) != NMM_OK) return rc;
         a.epilogue = NMM_EPI_RESIDUAL; a.N = C; a.K = C; a.A = ctx; a.W = pk + o.wo2; a.bias = F32(o.bo2); a.h = h; a.out = nullptr;
         if ((rc = linear_dispatch(g.dtype, a, st)) != NMM_OK) return rc;

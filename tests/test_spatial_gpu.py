@@ -100,6 +100,24 @@ def test_spatial_full_size_image_independence(C, side, frames):
             assert err <= TOL_BF16, (b, f, err)
 
 
+@pytest.mark.parametrize("C,side,frames", [(320, 64, 2), (640, 32, 4)])
+def test_spatial_full_size_fp32_tensor_core_mode(C, side, frames):
+    """fp32 activations (the reference as shipped) at the UNet's latent sizes: Linears and attention on the tensor cores as 3 bf16 MMAs per
+    product (NMM_F32X3; the attention takes q, k, v and the softmax weights as hi | lo bf16 splits) -- one image against the fp32 oracle on that
+    image alone, bar 1e-4."""
+    cfg = so.SpatialConfig(C, 8, 1, 768, True)
+    params = so.make_params(cfg, 41)
+    x, ctx = so.make_inputs(cfg, 1, frames, side, side, 77, 42)
+    with torch.no_grad():
+        m = _mirror(cfg, params, torch.float32)
+        y = m(x.cuda(), encoder_hidden_states=ctx.cuda()).sample
+        torch.cuda.synchronize()
+        f = frames - 1
+        ref = so.forward_reference_order(params, x[:, :, f:f + 1], ctx, cfg)
+        err = (y[:, :, f:f + 1].cpu() - ref).abs().max().item()
+        assert err <= TOL_FP32, err
+
+
 def test_spatial_then_motion_chain():
     """The call order of every CrossAttn block (unet_blocks.py:409-411): spatial transformer -> motion module, the second consuming the
     first's [B,F,C,H,W]-storage view directly."""
