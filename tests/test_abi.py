@@ -115,7 +115,7 @@ def test_spatial_and_decoder_sizes_and_validation(built_library):
     for bad, status in ((_spatial_shape(channels=256), -2),                 # head dim 32: not 40 / 80 / 160
                         (_spatial_shape(ctx_dim=100), -1),                  # ctx_dim % 8
                         (_spatial_shape(ctx_len=0), -1),
-                        (_spatial_shape(dtype=nlib.NMM_F32X3, channels=320), -2)):
+                        (_spatial_shape(dtype=nlib.NMM_F32X3, ctx_dim=96), -2)):           # 3 x bf16 mode: ctx_dim % 64
         assert built_library.nmm_spatial_workspace_bytes(C.byref(bad), C.byref(n)) == status, built_library.nmm_last_error()
     assert built_library.nmm_decoder_attn_packed_bytes(128, nlib.NMM_BF16, C.byref(n)) == 0
     assert 2 * 4 * 128 * 128 < n.value < 2 * 4 * 128 * 128 + (1 << 14)
